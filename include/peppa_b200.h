@@ -1,0 +1,139 @@
+/* peppa_b200 -- C ABI of the B200-native contrastive-scoring hot path.
+ *
+ * The reference (gchrupala/peppa) has no FFI layer: its seam is the Python module API of
+ * pig/loss.py, pig/metrics.py, pig/triplet.py and pig/util.py:9-13.  The Python modules in
+ * peppa_b200/ keep those signatures and call ONLY the entry points declared here (ctypes, see
+ * INTEGRATION.md).  Plain pointers and sizes; no torch types.  All pointers are DEVICE
+ * pointers unless stated otherwise; matrices are row-major with an element leading
+ * dimension `ld*`; embedding operands of the tensor-core kernels are bf16, 16-byte aligned,
+ * with dim % 64 == 0 (the Python side zero-pads otherwise; zero padding changes neither dot
+ * products nor norms).  Every call only ENQUEUES work on `stream` (a cudaStream_t) and
+ * returns a status: 0 = ok, non-zero = error, message via pb2_last_error().  Re-entrant; no
+ * global state besides a cached driver entry point and per-device SM counts.
+ */
+#ifndef PEPPA_B200_H
+#define PEPPA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_VERSION 1
+
+#define PB2_OK 0
+#define PB2_ERR_ARG 1
+#define PB2_ERR_CUDA 2
+#define PB2_ERR_UNSUPPORTED 3
+
+/* element types accepted by the HBM-bound kernels */
+#define PB2_BF16 0
+#define PB2_F16 1
+#define PB2_F32 2
+
+const char* pb2_last_error(void);
+int pb2_version(void);
+
+/* ---- (c) triplet scoring: replaces pig/metrics.py:45-52 triplet_accuracy and the gathers of
+ * pig/triplet.py:71-73,89-91.  out[t] = cos(a_t,p_t) - cos(a_t,n_t) (discrete == 0) or
+ * (sign(.)+1)/2 in {0, 0.5, 1} (discrete != 0), F.cosine_similarity semantics (norms clamped
+ * at 1e-8).  *_idx are optional int64 row indices (NULL = row t). */
+int pb2_triplet_score(const void* anchor, const void* positive, const void* negative, const int64_t* anchor_idx,
+                      const int64_t* positive_idx, const int64_t* negative_idx, int64_t n_triplets, int dim,
+                      int64_t ld, int dtype, int discrete, float* out, void* stream);
+
+/* ---- row statistics: replaces U.norm(2, dim=1, keepdim=True) of pig/util.py:11-12.
+ * rinv[i] = 1/||x_i||_2 (no epsilon: a zero row gives +inf and NaN scores, like the reference),
+ * norm[i] = ||x_i||_2; either output may be NULL.  x is bf16. */
+int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream);
+
+/* out[k] = <x[ix[k]], y[iy[k]]> * sx * sy with sx = rinv_x[ix[k]] (1 if rinv_x == NULL), same
+ * for sy; ix / iy NULL = k.  The diagonal M_ii of pig/loss.py:43 and the positive's score of
+ * pig/metrics.py:8-20.  If dist_out != NULL also writes fl32(1 - out[k]) there. */
+int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
+                 const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out, float* dist_out,
+                 void* stream);
+
+/* ---- (a)/(b) similarity kernels: S = X * Y^T on the tcgen05 tensor cores (bf16 in, fp32
+ * accumulate in TMEM), epilogue fused per entry point; S itself reaches HBM only in
+ * pb2_sim_matrix.  X is [rows, dim], Y is [cols, dim]; s_ij = <x_i,y_j> * rinv_x[i] * rinv_y[j]
+ * * scale (rinv_* == NULL means 1). */
+
+/* pig/util.py:9-13 cosine_matrix (and the raw V A^T of pig/loss.py:19): out is fp32 [rows, cols]. */
+int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                   int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* out, int64_t ld_out,
+                   void* stream);
+
+/* pig/metrics.py:7-40 with one target per query row: rank[i] += #{ j != pos_col[i] :
+ * fl32(1 - s_ij) < pos_dist[i] }.  rank (int32) must be zeroed by the caller; column indices
+ * are offset by col_offset (sharded galleries).  No sort, no N x N store. */
+int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g, const float* pos_dist,
+                 const int64_t* pos_col, int64_t rows, int64_t cols, int64_t col_offset, int dim, int64_t ldq,
+                 int64_t ldg, int32_t* rank, void* stream);
+
+/* pig/loss.py:28-48 TripletLoss / contrastive, forward pass fused with the gradient matrix.
+ * For local rows i (global row id row_offset + i) and columns j (global id col_offset + j), i != j globally:
+ *   zc = margin + s_ij - diag_col[j],  zr = margin + s_ij - diag_row[i]
+ *   loss_partial[cta] += relu(zc) + relu(zr)            (fp32, one slot per CTA, deterministic)
+ *   row_cnt[i] += [zr >= 0]      col_cnt[j] += [zc >= 0]   (int32, caller-zeroed)
+ *   gmat[i,j] = fp16( ([zc >= 0] + [zr >= 0]) * rinv_x[i] * rinv_y[j] )   (0 on the diagonal)
+ * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()). */
+int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
+                  const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim,
+                  int64_t ldx, int64_t ldy, float margin, float* loss_partial, int n_partials, int32_t* row_cnt,
+                  int32_t* col_cnt, void* gmat, int64_t ld_g, void* stream);
+
+/* pig/loss.py:13-26 MILNCELoss: row-wise online log-sum-exp of s over all columns.
+ * part_max / part_sum are [n_col_tiles * 2, rows] fp32 partials in the log2 domain
+ * (pb2_sim_lse_parts() gives the first dimension); pb2_lse_merge folds them into lse[rows]
+ * (natural log).  Column LSE = the same call with X and Y swapped. */
+int pb2_sim_lse_parts(int64_t cols);
+int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                     int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* part_max, float* part_sum,
+                     void* stream);
+int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,
+                  int accumulate, void* stream);
+
+/* MIL-NCE gradient matrix: gmat[i,j] = fp16( (exp(s_ij - den_row[i]) + exp(s_ij - den_col[j])) * 2^13 ). */
+int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* den_row,
+                     const float* den_col, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
+                     float scale, void* gmat, int64_t ld_g, void* stream);
+
+/* ---- backward GEMMs on the tensor cores: out[M, dim] (=|+=) op(G) * Z, G fp16 [g_rows, g_cols],
+ * Z bf16.  transpose == 0: out = G * Z (M = g_rows, Z is [g_cols, dim]);
+ * transpose != 0: out = G^T * Z (M = g_cols, Z is [g_rows, dim]).  out fp32, scaled by alpha. */
+int pb2_grad_gemm(const void* gmat, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose, const void* z,
+                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, void* stream);
+
+/* Hinge finish (SURVEY 8a'): g_i = p_i * norm_x[i] + gdiag_i * rinv_y[i] * y_i,  gdiag_i = -(row_cnt[i] +
+ * col_cnt[i]); grad_x[i] = coef * rinv_x[i] * (g_i - xhat_i <g_i, xhat_i>), xhat = x * rinv_x.
+ * coef_dev (device scalar, may be NULL = 1) * coef_host multiplies the result. */
+int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
+                     const float* norm_x, const float* rinv_y, const int32_t* row_cnt, const int32_t* col_cnt,
+                     int64_t rows, int dim, int64_t ldx, int64_t ldy, float coef_host, const float* coef_dev,
+                     float* grad_x, int64_t ld_grad, void* stream);
+
+/* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
+int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
+                      float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);
+
+/* Deterministic fixed-order sum of n fp32 partials, scaled: out[0] = alpha * sum. */
+int pb2_sum_partials(const float* partials, int n, float alpha, float* out, void* stream);
+
+/* MIL-NCE loss from the merged statistics: out[0] = mean_i( logaddexp(lse_row[i], lse_col[i]) - diag[i] ),
+ * den[i] = logaddexp(lse_row[i], lse_col[i]). */
+int pb2_milnce_loss(const float* lse_row, const float* lse_col, const float* diag, int64_t n, float* den,
+                    float* out, void* stream);
+
+/* pig/loss.py:41-48 contrastive(M) on a materialised square fp32 matrix (HBM-bound):
+ * forward loss partials per CTA (+ optional gradient matrix dM scaled by coef). */
+int pb2_contrastive_matrix(const float* m, int64_t n, int64_t ld, float margin, float* loss_partial, int n_partials,
+                           float* grad_m, int64_t ld_grad, float coef_host, const float* coef_dev, void* stream);
+
+/* number of CTAs the persistent similarity kernels launch on the current device */
+int pb2_sim_grid(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPPA_B200_H */

@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI declared in ``include/peppa_b200.h``.
+
+The shared library is built in-tree (``peppa_b200/csrc/libpeppa_b200.so``) by
+``peppa_b200.build``.  There is no fallback: if the library is missing or a symbol is
+absent, importing/using the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpeppa_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "peppa_b200.h")
+
+PB2_BF16, PB2_F16, PB2_F32 = 0, 1, 2
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i = C.c_int
+_f = C.c_float
+
+# name -> argument ctypes (all return int unless listed in _RESTYPE)
+SIGNATURES = {
+    "pb2_version": [],
+    "pb2_last_error": [],
+    "pb2_sim_grid": [],
+    "pb2_triplet_score": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i, _i, _p, _p],
+    "pb2_row_norms": [_p, _i64, _i, _i64, _p, _p, _p],
+    "pb2_pair_dot": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p],
+    "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
+    "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i64, _i64, _p, _p],
+    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p],
+    "pb2_sim_lse_parts": [_i64],
+    "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _p, _p],
+    "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
+    "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
+    "pb2_grad_gemm": [_p, _i64, _i64, _i64, _i, _p, _i, _i64, _f, _i, _p, _i64, _p],
+    "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
+    "pb2_milnce_finish": [_p, _i64, _p, _i64, _i, _i64, _f, _p, _p, _i64, _p],
+    "pb2_sum_partials": [_p, _i, _f, _p, _p],
+    "pb2_milnce_loss": [_p, _p, _p, _i64, _p, _p, _p],
+    "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
+}
+_RESTYPE = {"pb2_last_error": C.c_char_p}
+# test hooks, not part of the public header
+_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name declared in include/peppa_b200.h."""
+    with open(HEADER_PATH) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"peppa_b200: native library not built ({LIB_PATH} missing). Run `python -m peppa_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    handle = C.CDLL(LIB_PATH)
+    for name, args in {**SIGNATURES, **_DEBUG}.items():
+        fn = getattr(handle, name)  # AttributeError if the export is missing
+        fn.argtypes = args
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    _lib = handle
+    return handle
+
+
+class Pb2Error(RuntimeError):
+    pass
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().pb2_last_error()
+        raise Pb2Error(f"peppa_b200 {what} failed (status {status}): {msg.decode() if msg else ''}")

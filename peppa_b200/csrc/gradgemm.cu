@@ -1,0 +1,263 @@
+// Backward GEMMs of the contrastive losses on the tensor cores:
+//     out[M, dim] (=|+=) alpha * op(G) * Z        G fp16 gradient matrix, Z bf16 embeddings
+// i.e. the autograd backward of torch.matmul in pig/util.py:13 / pig/loss.py:19
+// (dX = G Y, dY = G^T X).  G comes from the fused forward epilogue (sim.cu), already scaled
+// by the row/column norms, so both products use the raw bf16 embeddings.
+//
+// Operand layouts for tcgen05.mma (kind::f16, A = fp16, B = bf16, fp32 accumulate in TMEM):
+//   A = G   (transpose == 0): K-major, one TMA box [128 rows x 64 k] per stage.
+//   A = G^T (transpose != 0): MN-major, two TMA boxes [64 k x 64 m] per stage.
+//   B = Z^T always MN-major (Z is [K, dim] row-major): BN/64 TMA boxes [64 k x 64 n] per stage.
+// Same warp-specialised pipeline as sim.cu: TMA warp, MMA warp, 8 epilogue warps, 2 TMEM stages.
+#include "common.cuh"
+#include "host_util.h"
+#include "peppa_b200.h"
+
+namespace pb2 {
+namespace gg {
+
+constexpr int BM = 128, BK = 64, UK = 16;
+constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kBoxBytes = 64 * 64 * 2;  // one [64 x 64] 16-bit box
+
+struct Args {
+    int64_t m, k;  // output rows, contraction length
+    int n_rb, n_cb;
+    int64_t n_tiles;
+    int kblocks;
+    float alpha;
+    int accumulate;
+    float* out;
+    int64_t ld_out;
+    // descriptor strides (bytes); runtime so the self-test can probe alternatives
+    uint32_t mn_lbo, mn_sbo, mn_kstep;
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kTileBytes = kStages * kStageBytes;
+    static constexpr int kTotal = 1024 + kTileBytes + 256;
+};
+
+template <bool kTranspose, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z,
+                     const Args a) {
+    using L = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + L::kStages;
+    uint64_t* acc_full = bars + 2 * L::kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_g);
+        tma_prefetch_desc(&tm_z);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < L::kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc_full + s, 1);
+            mbar_init(acc_empty + s, kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+                const int rb = (int)(t / a.n_cb), cb = (int)(t % a.n_cb);
+                for (int kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStageBytes;
+                    uint8_t* sb = sa + L::kABytes;
+                    mbar_arrive_expect_tx(full + stage, L::kStageBytes);
+                    if (!kTranspose) {
+                        tma_load_2d(sa, &tm_g, full + stage, kb * BK, rb * BM, kEvictFirst);
+                    } else {
+                        tma_load_2d(sa, &tm_g, full + stage, rb * BM, kb * BK, kEvictFirst);
+                        tma_load_2d(sa + kBoxBytes, &tm_g, full + stage, rb * BM + 64, kb * BK, kEvictFirst);
+                    }
+#pragma unroll
+                    for (int cchunk = 0; cchunk < BN / 64; ++cchunk)
+                        tma_load_2d(sb + cchunk * kBoxBytes, &tm_z, full + stage, cb * BN + cchunk * 64, kb * BK,
+                                    kEvictLast);
+                    if (++stage == L::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc =
+                make_idesc(BM, BN, kFmtF16, kFmtBF16, kTranspose ? kMajorMN : kMajorK, kMajorMN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t it = 0;
+            for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+                const int as = (int)(it & 1);
+                mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint64_t da = kTranspose ? make_smem_desc(sa + k * a.mn_kstep, a.mn_lbo, a.mn_sbo)
+                                                       : make_smem_desc(sa + k * UK * 2, 16, 1024);
+                        const uint64_t db = make_smem_desc(sb + k * a.mn_kstep, a.mn_lbo, a.mn_sbo);
+                        umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty + stage);
+                    if (++stage == L::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(acc_full + as);
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        const int quad = warp & 3;
+        const int half = (warp - kEpiWarp0) >> 2;
+        constexpr int kChunksPerHalf = BN / 64;
+        int64_t it = 0;
+        for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+            const int as = (int)(it & 1);
+            const int rb = (int)(t / a.n_cb), cb = (int)(t % a.n_cb);
+            const int64_t row = (int64_t)rb * BM + quad * 32 + lane;
+            mbar_wait(acc_full + as, (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int ch = 0; ch < kChunksPerHalf; ++ch) {
+                const int cbase = (half * kChunksPerHalf + ch) * 32;
+                uint32_t v[32];
+                tmem_ld32(t_lane + cbase, v);
+                tmem_ld_wait();
+                if (row < a.m) {
+                    float* dst = a.out + row * a.ld_out + (int64_t)cb * BN + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]) * a.alpha, __uint_as_float(v[j + 1]) * a.alpha,
+                                               __uint_as_float(v[j + 2]) * a.alpha, __uint_as_float(v[j + 3]) * a.alpha);
+                        if (a.accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                            o.x += old.x;
+                            o.y += old.y;
+                            o.z += old.z;
+                            o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + as);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
+
+template <bool kTranspose, int BN>
+static int launch(const void* g, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int dim, int64_t ldz,
+                  float alpha, int accumulate, float* out, int64_t ld_out, cudaStream_t st) {
+    CUtensorMap tg, tz;
+    const int64_t m = kTranspose ? g_cols : g_rows;
+    const int64_t k = kTranspose ? g_rows : g_cols;
+    int rc = make_tmap_2d(&tg, g, 2, (uint64_t)g_rows, (uint64_t)g_cols, (uint64_t)ld_g * 2, kTranspose ? 64 : BM, 64);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tz, z, 2, (uint64_t)k, (uint64_t)dim, (uint64_t)ldz * 2, 64, 64);
+    if (rc) return rc;
+    Args a;
+    a.m = m;
+    a.k = k;
+    a.n_rb = (int)((m + BM - 1) / BM);
+    a.n_cb = dim / BN;
+    a.n_tiles = (int64_t)a.n_rb * a.n_cb;
+    a.kblocks = (int)((k + BK - 1) / BK);
+    a.alpha = alpha;
+    a.accumulate = accumulate;
+    a.out = out;
+    a.ld_out = ld_out;
+    a.mn_lbo = g_mn_lbo;
+    a.mn_sbo = g_mn_sbo;
+    a.mn_kstep = g_mn_kstep;
+    auto kern = grad_gemm_kernel<kTranspose, BN>;
+    constexpr int smem = Smem<BN>::kTotal;
+    static bool configured = false;
+    if (!configured) {
+        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "grad_gemm");
+        if (rc) return rc;
+        configured = true;
+    }
+    const int grid = (int)std::min<int64_t>(a.n_tiles, sm_count());
+    kern<<<grid, kThreads, smem, st>>>(tg, tz, a);
+    return check_launch("grad_gemm");
+}
+
+}  // namespace gg
+}  // namespace pb2
+
+using namespace pb2;
+
+extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep) {
+    gg::g_mn_lbo = lbo;
+    gg::g_mn_sbo = sbo;
+    gg::g_mn_kstep = kstep;
+    return PB2_OK;
+}
+
+extern "C" int pb2_grad_gemm(const void* gmat, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose,
+                             const void* z, int dim, int64_t ldz, float alpha, int accumulate, float* out,
+                             int64_t ld_out, void* stream) {
+    if (g_rows <= 0 || g_cols <= 0) return PB2_OK;
+    if (!gmat || !z || !out) return set_error(PB2_ERR_ARG, "grad_gemm: null");
+    if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "grad_gemm: dim must be a multiple of 64");
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0)
+        return set_error(PB2_ERR_ARG, "grad_gemm: out must be 16-byte aligned with ld_out %% 4 == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bn = dim % 256 == 0 ? 256 : (dim % 128 == 0 ? 128 : 64);
+#define PB2_GG(T, B) gg::launch<T, B>(gmat, g_rows, g_cols, ld_g, z, dim, ldz, alpha, accumulate, out, ld_out, st)
+    if (transpose) {
+        if (bn == 256) return PB2_GG(true, 256);
+        if (bn == 128) return PB2_GG(true, 128);
+        return PB2_GG(true, 64);
+    }
+    if (bn == 256) return PB2_GG(false, 256);
+    if (bn == 128) return PB2_GG(false, 128);
+    return PB2_GG(false, 64);
+#undef PB2_GG
+}

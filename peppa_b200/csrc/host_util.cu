@@ -1,0 +1,75 @@
+#include "host_util.h"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "peppa_b200.h"
+
+namespace pb2 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+const char* last_error() { return g_err; }
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PB2_OK;
+    return set_error(PB2_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+
+int sm_count() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
+                 uint32_t box_rows, uint32_t box_cols) {
+    auto fn = encode_fn();
+    if (!fn) return set_error(PB2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_bytes & 15))
+        return set_error(PB2_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PB2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return PB2_OK;
+}
+
+}  // namespace pb2
+
+extern "C" const char* pb2_last_error(void) { return pb2::last_error(); }
+extern "C" int pb2_version(void) { return PB2_VERSION; }

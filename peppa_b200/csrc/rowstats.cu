@@ -1,0 +1,379 @@
+// Light O(N*D) / O(N) kernels around the tensor-core passes: row norms (pig/util.py:11-12), paired
+// dot products (the diagonal of pig/loss.py:43 and the positive's score of pig/metrics.py:8-20),
+// merges of log-sum-exp partials, the normalisation Jacobian after the gradient GEMMs, and the
+// elementwise contrastive(M) of pig/loss.py:41-48 for callers that hold a materialised matrix.
+// All are HBM/L2-bound: one warp per row with 16-byte loads.
+#include "common.cuh"
+#include "host_util.h"
+#include "peppa_b200.h"
+
+namespace pb2 {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kNegInf = -__builtin_huge_valf();
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+    f[0] = __uint_as_float(u.x << 16);
+    f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16);
+    f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16);
+    f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16);
+    f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+// ---------------------------------------------------------------------------------- row norms
+__global__ void __launch_bounds__(256) row_norms_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, int dim,
+                                                        int64_t ld, float* __restrict__ rinv,
+                                                        float* __restrict__ norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const __nv_bfloat16* row = x + r * ld;
+        float ss = 0.f;
+        for (int k = lane * 8; k < dim; k += 256) {
+            float f[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(row + k), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            const float nr = sqrtf(ss);
+            if (norm) norm[r] = nr;
+            if (rinv) rinv[r] = 1.0f / nr;  // no epsilon, like the reference: zero row -> inf -> NaN scores
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- pair dot
+__global__ void __launch_bounds__(256)
+    pair_dot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                    const int64_t* __restrict__ ix, const int64_t* __restrict__ iy, const float* __restrict__ rinv_x,
+                    const float* __restrict__ rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy,
+                    float* __restrict__ out, float* __restrict__ dist_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t k = warp; k < n; k += nwarps) {
+        const int64_t rx = ix ? ix[k] : k, ry = iy ? iy[k] : k;
+        const __nv_bfloat16* px = x + rx * ldx;
+        const __nv_bfloat16* py = y + ry * ldy;
+        float acc = 0.f;
+        for (int d = lane * 8; d < dim; d += 256) {
+            float a[8], b[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(px + d), a);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(py + d), b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            // same operation order as the rank epilogue (sim.cu), no FMA contraction
+            const float s = __fmul_rn(__fmul_rn(acc, rinv_x ? rinv_x[rx] : 1.f), rinv_y ? rinv_y[ry] : 1.f);
+            if (out) out[k] = s;
+            if (dist_out) dist_out[k] = __fsub_rn(1.0f, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- LSE merge
+__global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict__ pmax, const float* __restrict__ psum,
+                                                        int n_parts, int64_t rows, float* __restrict__ lse,
+                                                        int accumulate) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float m = kNegInf;
+    for (int k = 0; k < n_parts; ++k) m = fmaxf(m, pmax[(int64_t)k * rows + r]);
+    float s = 0.f;
+    if (m > kNegInf)
+        for (int k = 0; k < n_parts; ++k) s += psum[(int64_t)k * rows + r] * exp2f(pmax[(int64_t)k * rows + r] - m);
+    float v = (m > kNegInf) ? (m + log2f(s)) * kLn2 : kNegInf;
+    if (accumulate) {
+        const float o = lse[r];
+        const float hi = fmaxf(o, v), lo = fminf(o, v);
+        v = (hi > kNegInf) ? hi + log1pf(expf(lo - hi)) : kNegInf;
+    }
+    lse[r] = v;
+}
+
+// fixed-order single-block sum -> deterministic
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ p, int n, float alpha,
+                                                            float* __restrict__ out) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += p[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = v * alpha;
+    }
+}
+
+__global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restrict__ lse_row,
+                                                           const float* __restrict__ lse_col,
+                                                           const float* __restrict__ diag, int64_t n,
+                                                           float* __restrict__ den, float* __restrict__ out) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float a = lse_row[i], b = lse_col[i];
+        const float hi = fmaxf(a, b), lo = fminf(a, b);
+        const float d = hi + log1pf(expf(lo - hi));
+        den[i] = d;
+        acc += d - diag[i];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = sh[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = v / (float)n;
+    }
+}
+
+// ------------------------------------------------------------------------------ hinge finish
+// One warp per row; the row (p, x, y) is held in registers for dim <= 1024, else re-read.
+__global__ void __launch_bounds__(256)
+    hinge_finish_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ y, const float* __restrict__ rinv_x,
+                        const float* __restrict__ norm_x, const float* __restrict__ rinv_y,
+                        const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ col_cnt, int64_t rows,
+                        int dim, int64_t ldx, int64_t ldy, float coef_host, const float* __restrict__ coef_dev,
+                        float* __restrict__ grad, int64_t ld_grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const float coef = coef_host * (coef_dev ? coef_dev[0] : 1.f);
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float rx = rinv_x[r], nx = norm_x[r];
+        const float gd = -(float)(row_cnt[r] + col_cnt[r]) * rinv_y[r];
+        const float* pr = p + r * ld_p;
+        const __nv_bfloat16* xr = x + r * ldx;
+        const __nv_bfloat16* yr = y + r * ldy;
+        float dot = 0.f;
+        for (int d = lane * 8; d < dim; d += 256) {
+            float a[8], b[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), a);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), b);
+            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
+            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(pv[e], nx, gd * b[e]), a[e] * rx, dot);
+        }
+        dot = warp_sum(dot);
+        for (int d = lane * 8; d < dim; d += 256) {
+            float a[8], b[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), a);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), b);
+            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
+            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float g = fmaf(pv[e], nx, gd * b[e]);
+                o[e] = coef * rx * (g - a[e] * rx * dot);
+            }
+            float* gr = grad + r * ld_grad + d;
+            *reinterpret_cast<float4*>(gr) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(gr + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    milnce_finish_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ y, int64_t rows,
+                         int dim, int64_t ldy, float coef_host, const float* __restrict__ coef_dev,
+                         float* __restrict__ grad, int64_t ld_grad) {
+    const float coef = coef_host * (coef_dev ? coef_dev[0] : 1.f);
+    const int vec_per_row = dim / 8;
+    const int64_t total = rows * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int d = (int)(i % vec_per_row) * 8;
+        float b[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(y + r * ldy + d), b);
+        const float4 p0 = *reinterpret_cast<const float4*>(p + r * ld_p + d);
+        const float4 p1 = *reinterpret_cast<const float4*>(p + r * ld_p + d + 4);
+        const float s = 1.0f / 8192.0f;
+        float* gr = grad + r * ld_grad + d;
+        *reinterpret_cast<float4*>(gr) = make_float4(coef * (p0.x * s - b[0]), coef * (p0.y * s - b[1]),
+                                                     coef * (p0.z * s - b[2]), coef * (p0.w * s - b[3]));
+        *reinterpret_cast<float4*>(gr + 4) = make_float4(coef * (p1.x * s - b[4]), coef * (p1.y * s - b[5]),
+                                                         coef * (p1.z * s - b[6]), coef * (p1.w * s - b[7]));
+    }
+}
+
+// ---------------------------------------------------------------------- contrastive(M) on a matrix
+// pass 1: one block per row: loss partial, indicator counts, off-diagonal gradient entries.
+__global__ void __launch_bounds__(256)
+    contrastive_rows_kernel(const float* __restrict__ m, int64_t n, int64_t ld, float margin,
+                            float* __restrict__ loss_partial, int32_t* __restrict__ row_cnt,
+                            int32_t* __restrict__ col_cnt, float* __restrict__ grad, int64_t ld_grad, float coef) {
+    __shared__ float shf[8];
+    __shared__ int shi[8];
+    float total = 0.f;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const float di = m[i * ld + i];
+        float l = 0.f;
+        int rc = 0;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+            if (j == i) continue;
+            const float v = m[i * ld + j];
+            const float zc = margin + v - m[j * ld + j];
+            const float zr = margin + v - di;
+            const bool ic = zc >= 0.f, ir = zr >= 0.f;
+            l += (ic ? zc : 0.f) + (ir ? zr : 0.f);
+            rc += ir;
+            if (ic) atomicAdd(col_cnt + j, 1);
+            if (grad) grad[i * ld_grad + j] = coef * ((ic ? 1.f : 0.f) + (ir ? 1.f : 0.f));
+        }
+        l = warp_sum(l);
+        for (int o = 16; o > 0; o >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, o);
+        if ((threadIdx.x & 31) == 0) {
+            shf[threadIdx.x >> 5] = l;
+            shi[threadIdx.x >> 5] = rc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            int c = 0;
+            for (int w = 0; w < 8; ++w) {
+                s += shf[w];
+                c += shi[w];
+            }
+            total += s;
+            row_cnt[i] = c;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss_partial[blockIdx.x] = total;
+}
+__global__ void contrastive_diag_kernel(int64_t n, const int32_t* __restrict__ row_cnt,
+                                        const int32_t* __restrict__ col_cnt, float* __restrict__ grad,
+                                        int64_t ld_grad, float coef) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i * ld_grad + i] = -coef * (float)(row_cnt[i] + col_cnt[i]);
+}
+__global__ void scale_by_dev_kernel(float* __restrict__ g, int64_t n, int64_t ld, const float* __restrict__ s) {
+    const float f = s[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += (int64_t)gridDim.x * blockDim.x)
+        g[(i / n) * ld + (i % n)] *= f;
+}
+
+static int grid_for_warps(int64_t rows) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 8));
+}
+
+}  // namespace pb2
+
+using namespace pb2;
+
+static bool vec_ok(const void* p, int64_t ld_elems, int elem_bytes) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_elems * elem_bytes) % 16 == 0;
+}
+
+extern "C" int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!x || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 2))
+        return set_error(PB2_ERR_ARG, "row_norms: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
+    row_norms_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, n, dim, ld, rinv,
+                                                                         norm);
+    return check_launch("row_norms");
+}
+
+extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
+                            const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out,
+                            float* dist_out, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!x || !y || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2))
+        return set_error(PB2_ERR_ARG, "pair_dot: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
+    pair_dot_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out);
+    return check_launch("pair_dot");
+}
+
+extern "C" int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,
+                             int accumulate, void* stream) {
+    if (rows <= 0) return PB2_OK;
+    if (!part_max || !part_sum || !lse || n_parts <= 0) return set_error(PB2_ERR_ARG, "lse_merge: bad arguments");
+    lse_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_max, part_sum, n_parts,
+                                                                                      rows, lse, accumulate);
+    return check_launch("lse_merge");
+}
+
+extern "C" int pb2_sum_partials(const float* partials, int n, float alpha, float* out, void* stream) {
+    if (!partials || !out || n < 0) return set_error(PB2_ERR_ARG, "sum_partials: bad arguments");
+    sum_partials_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n, alpha, out);
+    return check_launch("sum_partials");
+}
+
+extern "C" int pb2_milnce_loss(const float* lse_row, const float* lse_col, const float* diag, int64_t n, float* den,
+                               float* out, void* stream) {
+    if (n <= 0 || !lse_row || !lse_col || !diag || !den || !out)
+        return set_error(PB2_ERR_ARG, "milnce_loss: bad arguments");
+    milnce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse_row, lse_col, diag, n, den, out);
+    return check_launch("milnce_loss");
+}
+
+extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
+                                const float* norm_x, const float* rinv_y, const int32_t* row_cnt,
+                                const int32_t* col_cnt, int64_t rows, int dim, int64_t ldx, int64_t ldy,
+                                float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
+                                void* stream) {
+    if (rows <= 0) return PB2_OK;
+    if (!p || !x || !y || !rinv_x || !norm_x || !rinv_y || !row_cnt || !col_cnt || !grad_x)
+        return set_error(PB2_ERR_ARG, "hinge_finish: null");
+    if (dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "hinge_finish: alignment");
+    hinge_finish_kernel<<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
+        p, ld_p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, norm_x, rinv_y, row_cnt, col_cnt, rows, dim,
+        ldx, ldy, coef_host, coef_dev, grad_x, ld_grad);
+    return check_launch("hinge_finish");
+}
+
+extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
+                                 float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
+                                 void* stream) {
+    if (rows <= 0) return PB2_OK;
+    if (!p || !y || !grad_x) return set_error(PB2_ERR_ARG, "milnce_finish: null");
+    if (dim % 8 != 0 || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "milnce_finish: alignment");
+    const int64_t total = rows * (dim / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    milnce_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const __nv_bfloat16*)y, rows, dim, ldy,
+                                                                coef_host, coef_dev, grad_x, ld_grad);
+    return check_launch("milnce_finish");
+}
+
+extern "C" int pb2_contrastive_matrix(const float* m, int64_t n, int64_t ld, float margin, float* loss_partial,
+                                      int n_partials, float* grad_m, int64_t ld_grad, float coef_host,
+                                      const float* coef_dev, void* stream) {
+    // workspace for the indicator counts lives at the tail of loss_partial: [n_partials | 2n int32]
+    if (n <= 0 || !m || !loss_partial) return set_error(PB2_ERR_ARG, "contrastive_matrix: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>(n, n_partials);
+    int32_t* cnt = reinterpret_cast<int32_t*>(loss_partial + n_partials);
+    int rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials + sizeof(int32_t) * 2 * n, st),
+                        "contrastive_matrix memset");
+    if (rc) return rc;
+    contrastive_rows_kernel<<<grid, 256, 0, st>>>(m, n, ld, margin, loss_partial, cnt, cnt + n, grad_m, ld_grad,
+                                                  coef_host);
+    rc = check_launch("contrastive_rows");
+    if (rc || !grad_m) return rc;
+    contrastive_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cnt, cnt + n, grad_m, ld_grad, coef_host);
+    rc = check_launch("contrastive_diag");
+    if (rc || !coef_dev) return rc;
+    scale_by_dev_kernel<<<std::min<int64_t>((n * n + 255) / 256, (int64_t)sm_count() * 8), 256, 0, st>>>(
+        grad_m, n, ld_grad, coef_dev);
+    return check_launch("contrastive_scale");
+}

@@ -1,0 +1,181 @@
+"""Drop-in for ``pig/loss.py``: same classes / functions / signatures, fused sm_100a kernels inside.
+
+``TripletLoss(margin)(V, A)`` (pig/loss.py:28-39) and ``MILNCELoss()(V, A)`` (pig/loss.py:5-26)
+never materialise the N x N similarity matrix: the tcgen05 GEMM's epilogue reduces it to the
+loss, the indicator counts / log-sum-exp statistics and an fp16 gradient matrix, and two more
+tensor-core GEMMs turn that into dV and dA.  Gradients are produced during ``forward`` (the
+loss is a scalar, so backward is a scale by ``grad_output``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn
+
+from . import ops
+from .util import cosine_matrix  # noqa: F401  (pig/loss.py re-exports its own copy, :51-55)
+
+# Largest gradient-matrix block kept in HBM at once (rows x cols fp16).  Bigger problems are
+# walked block by block with accumulating gradient GEMMs.
+_MAX_BLOCK = 32768
+
+
+def _blocks(n, step):
+    return [(s, min(n, s + step)) for s in range(0, n, step)]
+
+
+class _HingeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, A, margin):
+        if V.dim() != 2 or A.dim() != 2 or V.shape[0] != A.shape[0]:
+            raise RuntimeError(f"TripletLoss expects V [N, D] and A [N, D]; got {tuple(V.shape)} and {tuple(A.shape)}")
+        vb = ops.as_bf16_rows(V)
+        ab = ops.as_bf16_rows(A, device=vb.device)
+        dev = vb.device
+        n = vb.shape[0]
+        need_grad = any(ctx.needs_input_grad[:2])
+        rv, nv = ops.row_norms(vb)
+        ra, na = ops.row_norms(ab)
+        diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
+        row_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        col_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        inv_n2 = 1.0 / float(n) ** 2
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        pv = pa = None
+        blocks = _blocks(n, _MAX_BLOCK)
+        for (r0, r1) in blocks:
+            for (c0, c1) in blocks:
+                g = ld = None
+                if need_grad:
+                    g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
+                part = ops.sim_hinge(vb[r0:r1], ab[c0:c1], rv[r0:r1], ra[c0:c1], diag[r0:r1], diag[c0:c1], margin,
+                                     row_cnt[r0:r1], col_cnt[c0:c1], g, ld or 0, row_offset=r0, col_offset=c0)
+                loss = loss + ops.sum_partials(part, inv_n2)
+                if need_grad:
+                    if pv is None:
+                        pv = torch.zeros(n, vb.shape[1], dtype=torch.float32, device=dev) if len(blocks) > 1 else \
+                            torch.empty(n, vb.shape[1], dtype=torch.float32, device=dev)
+                        pa = torch.zeros_like(pv) if len(blocks) > 1 else torch.empty_like(pv)
+                    acc = len(blocks) > 1
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ab[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vb[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
+        # zero-norm rows: the reference yields NaN (division by a zero norm, pig/util.py:11-12)
+        bad = ~(torch.isfinite(rv).all() & torch.isfinite(ra).all())
+        loss = torch.where(bad, torch.full_like(loss, float("nan")), loss)
+        if need_grad:
+            dV = ops.hinge_finish(pv, vb, ab, rv, nv, ra, row_cnt, col_cnt, inv_n2)
+            dA = ops.hinge_finish(pa, ab, vb, ra, na, rv, row_cnt, col_cnt, inv_n2)
+            ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
+            ctx.meta = (V.dtype, V.device, A.dtype, A.device)
+        return loss.to(V.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dV, dA = ctx.saved_tensors
+        vd, vdev, ad, adev = ctx.meta
+        go = grad_out.to(device=dV.device, dtype=torch.float32)
+        gV = (dV * go).to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
+        gA = (dA * go).to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
+        return gV, gA, None
+
+
+class _MilNceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, V, A):
+        if V.dim() != 2 or A.dim() != 2:
+            raise RuntimeError("MILNCELoss expects 2-D V and A")
+        if A.shape[0] != V.shape[0]:
+            raise NotImplementedError(
+                "MILNCELoss with K = len(A) / len(V) > 1 candidates per video is not implemented by the fused "
+                "path (the reference repo only ever uses K == 1)")
+        vb = ops.as_bf16_rows(V)
+        ab = ops.as_bf16_rows(A, device=vb.device)
+        dev = vb.device
+        n = vb.shape[0]
+        need_grad = any(ctx.needs_input_grad)
+        blocks = _blocks(n, _MAX_BLOCK)
+        lse_row = lse_col = None
+        for (c0, c1) in blocks:   # x = V A^T: row LSE over audio columns, column LSE = row LSE of A V^T
+            lse_row = ops.sim_lse_rows(vb, ab[c0:c1], lse=lse_row)
+            lse_col = ops.sim_lse_rows(ab, vb[c0:c1], lse=lse_col)
+        diag = ops.pair_dot(vb, ab)
+        loss, den = ops.milnce_loss(lse_row, lse_col, diag)
+        if need_grad:
+            acc = len(blocks) > 1
+            pv = torch.zeros(n, vb.shape[1], dtype=torch.float32, device=dev) if acc else \
+                torch.empty(n, vb.shape[1], dtype=torch.float32, device=dev)
+            pa = torch.zeros_like(pv) if acc else torch.empty_like(pv)
+            for (r0, r1) in blocks:
+                for (c0, c1) in blocks:
+                    g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
+                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den[c0:c1], g, ld)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ab[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vb[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
+            dV = ops.milnce_finish(pv, ab, 1.0 / n)
+            dA = ops.milnce_finish(pa, vb, 1.0 / n)
+            ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
+            ctx.meta = (V.dtype, V.device, A.dtype, A.device)
+        return loss.to(V.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dV, dA = ctx.saved_tensors
+        vd, vdev, ad, adev = ctx.meta
+        go = grad_out.to(device=dV.device, dtype=torch.float32)
+        gV = (dV * go).to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
+        gA = (dA * go).to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
+        return gV, gA
+
+
+class MILNCELoss(torch.nn.Module):
+    """The loss implemented is: log(pos/(2 * pos + neg)) = log(pos/(pos + neg/2)) - log(2)
+    (pig/loss.py:5-26; MIL-NCE of Miech et al. with one candidate per clip)."""
+
+    def __init__(self):
+        super(MILNCELoss, self).__init__()
+
+    def forward(self, V, A):
+        """Returns MIL-NCE loss.
+        Args:
+           V: Tensor of embeddings (e.g. video)
+           A: Tensor of embeddings (e.g. audio)
+        """
+        return _MilNceFn.apply(V, A)
+
+
+class TripletLoss(torch.nn.Module):
+    def __init__(self, margin):
+        super(TripletLoss, self).__init__()
+        self.margin = margin
+
+    def forward(self, V, A):
+        """Returns Triplet loss with margin.
+        Args:
+           V: Tensor of embeddings (e.g. video)
+           A: Tensor of embeddings (e.g. audio)
+        """
+        return _HingeFn.apply(V, A, float(self.margin))
+
+
+class _ContrastiveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, M, margin):
+        if M.dim() != 2 or M.shape[0] != M.shape[1]:
+            raise RuntimeError(f"contrastive expects a square similarity matrix, got {tuple(M.shape)}")
+        dev = ops.require_cuda(M.device)
+        m = M.detach().to(device=dev, dtype=torch.float32).contiguous()
+        loss, grad = ops.contrastive_matrix(m, margin, ctx.needs_input_grad[0])
+        if grad is not None:
+            ctx.save_for_backward(grad)
+            ctx.meta = (M.dtype, M.device)
+        return loss.to(M.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        dt, dev = ctx.meta
+        return (grad * grad_out.to(device=grad.device, dtype=torch.float32)).to(device=dev, dtype=dt), None
+
+
+def contrastive(M, margin=0.2):
+    "Returns contrastive margin loss over similarity matrix M."
+    return _ContrastiveFn.apply(M, float(margin))

@@ -1,0 +1,220 @@
+"""Tensor-level wrappers over the C ABI (``include/peppa_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function
+below hands raw device pointers and sizes to the native library and returns freshly
+allocated torch tensors.  No function in this module computes the hot path with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import PB2_BF16, PB2_F16, PB2_F32, check
+
+_DTYPE_CODE = {torch.bfloat16: PB2_BF16, torch.float16: PB2_F16, torch.float32: PB2_F32}
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("peppa_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    if device is not None and torch.device(device).type == "cuda":
+        return torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def as_bf16_rows(x: torch.Tensor, device=None) -> torch.Tensor:
+    """2-D contiguous bf16 copy on the GPU with the feature dimension zero-padded to a multiple
+    of 64 (zero columns change neither dot products nor norms)."""
+    if x.dim() != 2:
+        raise ValueError(f"expected a 2-D [N, D] embedding matrix, got shape {tuple(x.shape)}")
+    dev = require_cuda(device if device is not None else x.device)
+    y = x.detach().to(device=dev, dtype=torch.bfloat16)
+    d = y.shape[1]
+    if d % 64 != 0:
+        y = torch.nn.functional.pad(y, (0, 64 - d % 64))
+    return y.contiguous()
+
+
+def row_norms(x_bf16: torch.Tensor):
+    """(1/||x_i||, ||x_i||) in fp32 -- pig/util.py:11-12 without the divide."""
+    n, d = x_bf16.shape
+    rinv = torch.empty(n, dtype=torch.float32, device=x_bf16.device)
+    norm = torch.empty(n, dtype=torch.float32, device=x_bf16.device)
+    with torch.cuda.device(x_bf16.device):
+        check(_cabi.lib().pb2_row_norms(_ptr(x_bf16), n, d, x_bf16.stride(0), _ptr(rinv), _ptr(norm),
+                                        _stream(x_bf16.device)), "row_norms")
+    return rinv, norm
+
+
+def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False):
+    n = x.shape[0] if ix is None else ix.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_pair_dot(_ptr(x), _ptr(y), _ptr(ix), _ptr(iy), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1],
+                                       x.stride(0), y.stride(0), _ptr(out), _ptr(dist), _stream(x.device)), "pair_dot")
+    return (out, dist) if want_dist else out
+
+
+def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
+    r, c = x.shape[0], y.shape[0]
+    out = torch.empty(r, c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_sim_matrix(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0),
+                                         y.stride(0), float(scale), _ptr(out), out.stride(0) if r and c else c,
+                                         _stream(x.device)), "sim_matrix")
+    return out
+
+
+def sim_rank(q, g, rinv_q, rinv_g, pos_dist, pos_col, col_offset=0, rank=None):
+    r, c = q.shape[0], g.shape[0]
+    if rank is None:
+        rank = torch.zeros(r, dtype=torch.int32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_dist), _ptr(pos_col), r, c,
+                                       int(col_offset), q.shape[1], q.stride(0), g.stride(0), _ptr(rank),
+                                       _stream(q.device)), "sim_rank")
+    return rank
+
+
+def sim_grid(device) -> int:
+    with torch.cuda.device(device):
+        return int(_cabi.lib().pb2_sim_grid())
+
+
+def gmat_alloc(rows, cols, device):
+    """fp16 gradient-matrix buffer with a leading dimension padded for 16-byte vector stores."""
+    ld = ((cols + 63) // 64) * 64
+    return torch.empty(rows, ld, dtype=torch.float16, device=device), ld
+
+
+def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0,
+              row_offset=0, col_offset=0):
+    """Returns the per-CTA loss partials (fp32 [grid])."""
+    r, c = x.shape[0], y.shape[0]
+    n_part = sim_grid(x.device)
+    part = torch.empty(n_part, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
+                                        int(row_offset), int(col_offset), x.shape[1], x.stride(0), y.stride(0),
+                                        float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
+                                        int(ld_g), _stream(x.device)), "sim_hinge")
+    return part
+
+
+def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
+    """Row-wise log-sum-exp of s = scale * <x_i, y_j> over all j; optionally log-add into ``lse``."""
+    r, c = x.shape[0], y.shape[0]
+    lib = _cabi.lib()
+    n_parts = int(lib.pb2_sim_lse_parts(c))
+    pmax = torch.empty(n_parts, r, dtype=torch.float32, device=x.device)
+    psum = torch.empty(n_parts, r, dtype=torch.float32, device=x.device)
+    accumulate = lse is not None
+    if lse is None:
+        lse = torch.empty(r, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _stream(x.device)
+        check(lib.pb2_sim_lse_rows(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0), y.stride(0),
+                                   float(scale), _ptr(pmax), _ptr(psum), st), "sim_lse_rows")
+        check(lib.pb2_lse_merge(_ptr(pmax), _ptr(psum), n_parts, r, _ptr(lse), int(accumulate), st), "lse_merge")
+    return lse
+
+
+def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, scale=1.0):
+    r, c = x.shape[0], y.shape[0]
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_sim_lse_grad(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(den_row), _ptr(den_col), r, c,
+                                           x.shape[1], x.stride(0), y.stride(0), float(scale), _ptr(gmat), int(ld_g),
+                                           _stream(x.device)), "sim_lse_grad")
+
+
+def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False):
+    m = g_cols if transpose else g_rows
+    d = z.shape[1]
+    if out is None:
+        out = torch.empty(m, d, dtype=torch.float32, device=z.device)
+        accumulate = False
+    with torch.cuda.device(z.device):
+        check(_cabi.lib().pb2_grad_gemm(_ptr(gmat), g_rows, g_cols, int(ld_g), int(bool(transpose)), _ptr(z), d, z.stride(0),
+                                        float(alpha), int(bool(accumulate)), _ptr(out), out.stride(0), _stream(z.device)),
+              "grad_gemm")
+    return out
+
+
+def hinge_finish(p, x, y, rinv_x, norm_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
+    rows, d = x.shape
+    grad = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _ptr(rinv_x), _ptr(norm_x), _ptr(rinv_y),
+                                           _ptr(row_cnt), _ptr(col_cnt), rows, d, x.stride(0), y.stride(0), float(coef_host),
+                                           _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(x.device)), "hinge_finish")
+    return grad
+
+
+def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
+    rows, d = y.shape
+    grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(_cabi.lib().pb2_milnce_finish(_ptr(p), p.stride(0), _ptr(y), rows, d, y.stride(0), float(coef_host),
+                                            _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(y.device)), "milnce_finish")
+    return grad
+
+
+def sum_partials(part, alpha=1.0):
+    out = torch.empty((), dtype=torch.float32, device=part.device)
+    with torch.cuda.device(part.device):
+        check(_cabi.lib().pb2_sum_partials(_ptr(part), part.numel(), float(alpha), _ptr(out), _stream(part.device)),
+              "sum_partials")
+    return out
+
+
+def milnce_loss(lse_row, lse_col, diag):
+    n = lse_row.shape[0]
+    den = torch.empty(n, dtype=torch.float32, device=lse_row.device)
+    out = torch.empty((), dtype=torch.float32, device=lse_row.device)
+    with torch.cuda.device(lse_row.device):
+        check(_cabi.lib().pb2_milnce_loss(_ptr(lse_row), _ptr(lse_col), _ptr(diag), n, _ptr(den), _ptr(out),
+                                          _stream(lse_row.device)), "milnce_loss")
+    return out, den
+
+
+def contrastive_matrix(m, margin, want_grad, coef_dev=None):
+    """pig/loss.py:41-48 on a materialised fp32 square matrix; returns (loss, dM or None)."""
+    n = m.shape[0]
+    n_part = sim_grid(m.device) * 4
+    work = torch.empty(n_part + 2 * n, dtype=torch.float32, device=m.device)  # partials | int32 counts
+    grad = torch.empty(n, n, dtype=torch.float32, device=m.device) if want_grad else None
+    with torch.cuda.device(m.device):
+        check(_cabi.lib().pb2_contrastive_matrix(_ptr(m), n, m.stride(0), float(margin), _ptr(work), n_part, _ptr(grad),
+                                                 n if want_grad else 0, 1.0 / float(n) ** 2, _ptr(coef_dev),
+                                                 _stream(m.device)), "contrastive_matrix")
+        loss = sum_partials(work[:n_part], 1.0 / float(n) ** 2)
+    return loss, grad
+
+
+def triplet_score(anchor, positive, negative, ia=None, ip=None, in_=None, discrete=True):
+    """anchor/positive/negative: 2-D, same dtype (bf16/f16/f32), same leading dimension."""
+    t = anchor.shape[0] if ia is None else ia.shape[0]
+    d = anchor.shape[1]
+    out = torch.empty(t, dtype=torch.float32, device=anchor.device)
+    code = _DTYPE_CODE[anchor.dtype]
+    assert positive.dtype == anchor.dtype and negative.dtype == anchor.dtype
+    ld = anchor.stride(0) if anchor.shape[0] > 1 else d
+    for m in (positive, negative):
+        if m.shape[0] > 1 and m.stride(0) != ld:
+            raise ValueError("triplet_score: operands must share a leading dimension")
+    with torch.cuda.device(anchor.device):
+        check(_cabi.lib().pb2_triplet_score(_ptr(anchor), _ptr(positive), _ptr(negative), _ptr(ia), _ptr(ip), _ptr(in_), t, d,
+                                            ld, code, int(bool(discrete)), _ptr(out), _stream(anchor.device)),
+              "triplet_score")
+    return out

@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/peppa_b200.h declares;
+host-side argument checks that need no device; the product path fails loudly without CUDA."""
+import ctypes as C
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from peppa_b200 import _cabi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    return _cabi.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    declared = _cabi.header_symbols()
+    assert len(declared) >= 19
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(declared) == set(_cabi.SIGNATURES), "ctypes table and header disagree"
+    assert lib.pb2_version() == 1
+
+
+def test_argument_errors_are_reported_without_touching_a_device(lib):
+    null = C.c_void_p(0)
+    assert lib.pb2_triplet_score(null, null, null, null, null, null, 4, 512, 512, 0, 1, null, null) == 1
+    assert b"null" in lib.pb2_last_error()
+    assert lib.pb2_triplet_score(null, null, null, null, null, null, 0, 512, 512, 0, 1, null, null) == 0   # empty ok
+    assert lib.pb2_triplet_score(null, null, null, null, null, null, 4, 512, 512, 9, 1, null, null) == 1
+    assert lib.pb2_sim_lse_parts(1000) == 16
+    assert lib.pb2_grad_gemm(null, 8, 8, 64, 0, null, 512, 512, 1.0, 0, null, 512, null) == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from peppa_b200 import loss, metrics
+    x = torch.randn(8, 512)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        loss.TripletLoss(0.2)(x, x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        metrics.recall_at_n(x, x, torch.eye(8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        metrics.triplet_accuracy(x, x, x)
+
+
+def test_sampler_matches_golden_without_device():
+    """The Python-side sampler of peppa_b200.triplet consumes `random` like pig/triplet.py:99-104."""
+    import random
+
+    import numpy as np
+
+    from conftest import load_golden
+    from peppa_b200 import triplet
+    g = load_golden("triplet_sampler_g240.npz")
+    dur = g["duration"]
+    random.seed(666)
+    for k in range(5):
+        pos, neg = zip(*triplet._triplets(range(len(dur)), lambda i: dur[i]))
+        assert np.array_equal(np.array(pos), g["draws"][k, 0].numpy())
+        assert np.array_equal(np.array(neg), g["draws"][k, 1].numpy())
+    assert triplet.pairs([1, 2, 3, 4, 5]) == [[1, 2], [3, 4]] and triplet.pairs([1]) == []

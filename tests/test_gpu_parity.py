@@ -1,0 +1,237 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference-generated golden fixtures and
+the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): loss and gradients within 1e-3 relative error (norm-wise:
+max|x - ref| / max|ref|; bf16 inputs, fp32 accumulate); ranks / recall identical except rows where
+another candidate lies within 1e-6 of the positive; triplet outputs identical except |gap| < 1e-6.
+"""
+import random
+
+import pytest
+import torch
+
+from conftest import golden_files, load_golden, rel_err
+from oracle import pig_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def emb(n, alpha, d=512, seed=666):
+    g = torch.Generator().manual_seed(seed)
+    V = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    A = torch.nn.functional.normalize(alpha * V + torch.randn(n, d, generator=g), dim=1)
+    return V.bfloat16().float(), A.bfloat16().float()
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import peppa_b200.loss as loss
+    import peppa_b200.metrics as metrics
+    import peppa_b200.triplet as triplet
+    import peppa_b200.util as util
+    return type("PB", (), dict(loss=loss, metrics=metrics, triplet=triplet, util=util))
+
+
+def _grads(mod, V, A):
+    v = V.cuda().requires_grad_(True)
+    a = A.cuda().requires_grad_(True)
+    out = mod(v, a)
+    out.backward()
+    return out.detach().cpu(), v.grad.cpu(), a.grad.cpu()
+
+
+# ------------------------------------------------------------------------------------ golden
+@pytest.mark.parametrize("name", golden_files("sim_n"))
+def test_losses_against_reference_golden(pb, name):
+    g = load_golden(name)
+    for kind, mod in (("hinge", pb.loss.TripletLoss(0.2)), ("milnce", pb.loss.MILNCELoss())):
+        loss, dV, dA = _grads(mod, g["V"], g["A"])
+        assert rel_err(loss, g[f"{kind}_loss"]) < TOL, kind
+        assert rel_err(dV, g[f"{kind}_dV"]) < TOL and rel_err(dA, g[f"{kind}_dA"]) < TOL, kind
+        assert loss.dtype == torch.float32 and loss.dim() == 0
+
+
+@pytest.mark.parametrize("name", golden_files("sim_n"))
+def test_recall_against_reference_golden(pb, name):
+    g = load_golden(name)
+    V, A = g["V"], g["A"]
+    n = V.shape[0]
+    _, near = O.ranks_identity(V, A)
+    eye = torch.eye(n, device="cuda")
+    for k in (1, 5, 10):
+        got = pb.metrics.recall_at_n(V.cuda(), A.cuda(), eye, n=k)
+        assert got.dtype == torch.float32 and got.device.type == "cpu" and got.shape == (n,)
+        assert bool(((got == g[f"recall_at_{k}"]) | near).all())
+    got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), eye, N=10)
+    assert got.shape == (11, n) and bool((got[0] == 0).all())
+    assert bool(((got == g["recall_at_1_to_10"]) | near.unsqueeze(0)).all())
+    # general multi-target `correct`
+    multi = g["correct_multi"]
+    got = pb.metrics.recall_at_n(V.cuda(), A.cuda(), multi.cuda(), n=5)
+    ok = (got - g["recall_multi_at_5"]).abs() < 1e-6
+    assert int((~ok).sum()) <= int(near.sum()) + 2      # pairs involving a near-tie may differ
+    got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), multi.cuda(), N=10)
+    assert int(((got - g["recall_multi_1_to_10"]).abs() > 1e-6).any(dim=0).sum()) <= int(near.sum()) + 2
+    # cosine_matrix and contrastive(M)
+    M = pb.util.cosine_matrix(V.cuda(), A.cuda())
+    assert (M.cpu() - g["cosine_VA"]).abs().max() < 2e-6
+    c = pb.loss.contrastive(g["cosine_VA"].cuda(), margin=0.2)
+    assert rel_err(c.cpu(), g["contrastive_M"]) < 1e-5
+
+
+def test_rectangular_retrieval_golden(pb):
+    g = load_golden("sim_rect_40x96.npz")
+    got = pb.metrics.recall_at_n(g["V"].cuda(), g["A"].cuda(), g["correct"].cuda(), n=3)
+    assert torch.equal(got, g["recall_at_3"])
+    got = pb.metrics.recall_at_1_to_n(g["V"].cuda(), g["A"].cuda(), g["correct"].cuda(), N=10)
+    assert torch.equal(got, g["recall_at_1_to_10"])
+    assert (pb.util.cosine_matrix(g["A"].cuda(), g["V"].cuda()).cpu() - g["cosine"]).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("name", golden_files("triplet_t"))
+def test_triplet_accuracy_golden(pb, name):
+    g = load_golden(name)
+    a, p, n = g["anchor"].cuda(), g["positive"].cuda(), g["negative"].cuda()
+    for dt in (torch.float32, torch.bfloat16):      # fixtures are bf16-representable: both paths see the same values
+        gap = pb.metrics.triplet_accuracy(a.to(dt), p.to(dt), n.to(dt), discrete=False).float().cpu()
+        assert (gap - g["gap"]).abs().max() < (2e-6 if dt == torch.float32 else 1e-2)
+        disc = pb.metrics.triplet_accuracy(a.to(dt), p.to(dt), n.to(dt)).float().cpu()
+        assert bool(((disc == g["discrete"]) | (g["gap"].abs() < 1e-6)).all())
+    if a.shape[0] >= 600:      # exact ties and zero vectors are exactly 0.5
+        disc = pb.metrics.triplet_accuracy(a, p, n).cpu()
+        assert disc[3] == 0.5 and disc[5] == 0.5 and disc[11] == 0.5
+    batch = pb.triplet.TripletBatch(anchor=a, positive=p, negative=n)
+    assert torch.equal(pb.metrics.batch_triplet_accuracy(batch), pb.metrics.triplet_accuracy(a, p, n))
+
+
+def test_resampled_recall_golden(pb):
+    g = load_golden("resampled_g300.npz")
+    V, A = g["V"].cuda(), g["A"].cuda()
+    _, near = O.ranks_identity(g["V"], g["A"])
+    torch.manual_seed(666)
+    got = pb.metrics.resampled_recall(V, A, size=100, n_samples=6, n=10)
+    assert got.shape == (6, 100)
+    ix = g["sample_indices"]
+    assert bool(((got == g["resampled_recall_n10"]) | near[ix]).all())
+    torch.manual_seed(666)
+    got = pb.metrics.resampled_recall_at_1_to_n(V, A, size=100, n_samples=4, N=10)
+    assert got.shape == (4, 11, 100)
+    assert bool(((got == g["resampled_1_to_10"]) | near[ix[:4]].unsqueeze(1)).all())
+    with pytest.raises(AssertionError):
+        pb.metrics.resampled_recall(V[:50], A[:50], size=100)
+    with pytest.raises(AssertionError):
+        pb.metrics.resampled_recall(V, A[:-1], size=100)
+
+
+def test_triplet_scoring_golden(pb):
+    g = load_golden("triplet_sampler_g240.npz")
+    dur = g["duration"]
+    random.seed(666)
+    comp = pb.triplet.comparative_score_triplets([g["V"].cuda(), g["V2"].cuda()], [g["A"].cuda(), g["A2"].cuda()], dur,
+                                                 n_samples=5)
+    assert (comp["success"][0].cpu() - g["comp_success0"]).abs().max() < 2e-6
+    assert (comp["success"][1].cpu() - g["comp_success1"]).abs().max() < 2e-6
+    assert torch.equal(comp["duration"], g["comp_duration"])
+    random.seed(666)
+    sc = pb.triplet.score_triplets(g["V"].cuda(), g["A"].cuda(), dur, n_samples=5)
+    assert (sc["accuracy"] - g["score_accuracy"]).abs().max() < 1e-6
+    assert torch.equal(sc["duration"], g["score_duration"])
+
+
+def test_error_conventions(pb):
+    g = load_golden("sim_n8_a4.0.npz")
+    with pytest.raises(ZeroDivisionError):
+        pb.metrics.recall_at_n(g["V"].cuda(), g["A"].cuda(), torch.zeros(8, 8), n=1)
+    z = g["V"].clone()
+    z[2] = 0                                    # zero row -> NaN like pig/util.py:11-12
+    assert torch.isnan(pb.loss.TripletLoss(0.2)(z.cuda(), g["A"].cuda()))
+    assert torch.isnan(pb.util.cosine_matrix(z.cuda(), g["A"].cuda())[2]).all()
+    out = pb.loss.TripletLoss(0.2)(g["V"], g["A"])      # CPU tensors in -> CPU result, computed on the GPU
+    assert out.device.type == "cpu"
+
+
+# -------------------------------------------------------------------------- seeded, larger sizes
+@pytest.mark.parametrize("n,alpha", [(1024, 4.0), (1024, 0.5), (1000, 4.0), (2304, 1.0)])
+def test_losses_against_oracle(pb, n, alpha):
+    V, A = emb(n, alpha)
+    for kind, mod, ref in (("hinge", pb.loss.TripletLoss(0.2), lambda: O.hinge_loss_and_grads(V, A, 0.2)),
+                           ("milnce", pb.loss.MILNCELoss(), lambda: O.milnce_loss_and_grads(V, A))):
+        loss, dV, dA = _grads(mod, V, A)
+        rl, rdv, rda = ref()
+        assert rel_err(loss, rl) < TOL, kind
+        assert rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL, kind
+
+
+def test_non_unit_norm_inputs(pb):
+    """cosine_matrix is scale invariant per row; the fused path must be too (H2 of SURVEY 7)."""
+    V, A = emb(512, 4.0)
+    g = torch.Generator().manual_seed(3)
+    V = (V * torch.empty(512, 1).uniform_(0.05, 20.0, generator=g)).bfloat16().float()
+    A = (A * torch.empty(512, 1).uniform_(0.05, 20.0, generator=g)).bfloat16().float()
+    loss, dV, dA = _grads(pb.loss.TripletLoss(0.2), V, A)
+    rl, rdv, rda = O.hinge_loss_and_grads(V, A, 0.2)
+    assert rel_err(loss, rl) < TOL and rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL
+    ranks, near = O.ranks_identity(V, A)
+    got = pb.metrics.recall_at_n(V.cuda(), A.cuda(), None, n=5)
+    assert bool((((ranks < 5).float() == got) | near).all())
+
+
+@pytest.mark.parametrize("n,alpha", [(4096, 4.0), (4096, 0.5), (5000, 4.0)])
+def test_ranks_against_oracle(pb, n, alpha):
+    V, A = emb(n, alpha)
+    ranks, near = O.ranks_identity(V, A)
+    got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), None, N=10)
+    for k in range(1, 11):
+        assert bool((((ranks < k).float() == got[k]) | near).all()), k
+    assert int(near.sum()) < n // 100
+
+
+def test_retrieval_16k_properties(pb):
+    """C3 size (16384 x 16384): full oracle takes ~40 s on CPU, so check (i) exact ranks on a random
+    512-row subset against the blockwise oracle and (ii) size-independent properties."""
+    n = 16384
+    V, A = emb(n, 4.0)
+    got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), None, N=10)
+    assert got.shape == (11, n)
+    assert bool((got[1:] >= got[:-1]).all())                    # recall@n is monotone in n
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:512]
+    R = A[rows] / A[rows].norm(dim=1, keepdim=True)             # queries = references = audio
+    C = V / V.norm(dim=1, keepdim=True)
+    d = 1 - R @ C.T
+    pos = d[torch.arange(512), rows].unsqueeze(1)
+    ranks = (d < pos).sum(1)
+    near = ((d - pos).abs() <= 1e-6).sum(1) > 1
+    for k in (1, 5, 10):
+        assert bool((((ranks < k).float() == got[k][rows]) | near).all())
+    # permutation invariance: shuffling the gallery (and the targets with it) leaves recall unchanged
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(2))
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n)
+    got_p = pb.metrics.recall_at_n(V[perm].cuda(), A.cuda(), inv.cuda(), n=10)
+    assert int((got_p != got[10]).sum()) <= 8                   # only near-ties may move
+
+
+def test_triplets_1m_properties(pb):
+    """C4 size: 1M triplets.  Antisymmetry (swap positive and negative -> 1 - acc) and agreement with
+    the oracle on a 4096-row slice."""
+    t = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a, p, n = (torch.randn(t, 512, device="cuda", generator=g).bfloat16() for _ in range(3))
+    acc = pb.metrics.triplet_accuracy(a, p, n)
+    swapped = pb.metrics.triplet_accuracy(a, n, p)
+    assert torch.equal(acc.float() + swapped.float(), torch.ones(t, device="cuda"))
+    sl = slice(12345, 12345 + 4096)
+    ref = O.triplet_accuracy(a[sl].float().cpu(), p[sl].float().cpu(), n[sl].float().cpu())
+    gap = O.triplet_accuracy(a[sl].float().cpu(), p[sl].float().cpu(), n[sl].float().cpu(), discrete=False)
+    assert bool(((acc[sl].float().cpu() == ref) | (gap.abs() < 1e-6)).all())
+
+
+def test_empty_and_tiny_inputs(pb):
+    e = torch.empty(0, 512, device="cuda")
+    assert pb.metrics.triplet_accuracy(e, e, e).shape == (0,)
+    V, A = emb(1, 4.0)
+    assert pb.metrics.recall_at_n(V.cuda(), A.cuda(), torch.eye(1), n=1).tolist() == [1.0]
+    loss, dV, dA = _grads(pb.loss.TripletLoss(0.2), *emb(2, 4.0))
+    rl, rdv, rda = O.hinge_loss_and_grads(*emb(2, 4.0), 0.2)
+    assert rel_err(loss, rl) < TOL

@@ -1,0 +1,231 @@
+"""Bring-up probes for the B200 box: each step runs in its own process (a trap in one kernel
+must not take the others down).  ``python tools/gpu_probe.py all`` runs every step under a
+timeout and writes ``gpurun_out/probe_<step>.log``; ``python tools/gpu_probe.py <step>`` runs one.
+Development tooling only -- the judged checks are tests/ and bench.py.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _t(fn, iters=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters  # ms
+
+
+def emb(n, alpha=4.0, d=512, seed=666, device="cuda"):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    V = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    A = torch.nn.functional.normalize(alpha * V + torch.randn(n, d, generator=g), dim=1)
+    return V.bfloat16().to(device), A.bfloat16().to(device)
+
+
+def step_triplet():
+    import torch
+    from peppa_b200 import metrics
+    from oracle import pig_oracle as O
+    for dt in (torch.bfloat16, torch.float32, torch.float16):
+        g = torch.Generator().manual_seed(1)
+        a, p, n = (torch.randn(1000, 512, generator=g).to(dt) for _ in range(3))
+        got = metrics.triplet_accuracy(a.cuda(), p.cuda(), n.cuda(), discrete=False).float().cpu()
+        ref = O.triplet_accuracy(a.float(), p.float(), n.float(), discrete=False)
+        print(dt, "max abs gap err", (got - ref).abs().max().item())
+        gd = metrics.triplet_accuracy(a.cuda(), p.cuda(), n.cuda()).float().cpu()
+        rd = O.triplet_accuracy(a.float(), p.float(), n.float())
+        print(dt, "discrete mismatches", int((gd != rd).sum()))
+    from peppa_b200 import ops
+    for dt, T in ((torch.bfloat16, 1 << 20), (torch.float32, 1 << 20)):
+        a, p, n = (torch.randn(T, 512, device="cuda").to(dt) for _ in range(3))
+        ms = _t(lambda: ops.triplet_score(a, p, n))
+        byt = T * (3 * 512 * a.element_size() + 4)
+        print(f"triplet {dt} T={T}: {ms:.3f} ms  {byt / ms / 1e6:.1f} GB/s  {T / ms / 1e6:.2f} Gtriplets/s")
+
+
+def step_simmatrix():
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    for (r, c, d) in [(128, 256, 64), (128, 256, 512), (128, 64, 512), (300, 500, 512), (1024, 1024, 512), (1000, 1536, 128)]:
+        x = torch.randn(r, d, device="cuda").bfloat16()
+        y = torch.randn(c, d, device="cuda").bfloat16()
+        ref = x.float() @ y.float().T
+        for bn in (64, 128, 256):
+            lib.pb2_debug_force_bn(bn)
+            got = ops.sim_matrix(x, y)
+            torch.cuda.synchronize()
+            err = (got - ref).abs().max().item()
+            print(f"sim_matrix r={r} c={c} d={d} bn={bn}: max abs err {err:.3e} (ref max {ref.abs().max().item():.2f})",
+                  "OK" if err < 1e-2 else "MISMATCH")
+            if err >= 1e-2:
+                bad = (got - ref).abs() > 1e-2
+                idx = bad.nonzero()
+                print("   first bad", idx[:5].tolist(), "n_bad", int(bad.sum()), "got", got[bad][:5].tolist(), "ref",
+                      ref[bad][:5].tolist())
+    lib.pb2_debug_force_bn(0)
+    V, A = emb(16384)
+    rv, _ = ops.row_norms(V)
+    ra, _ = ops.row_norms(A)
+    for bn in (128, 256):
+        lib.pb2_debug_force_bn(bn)
+        ms = _t(lambda: ops.sim_matrix(V, A, rv, ra), iters=5)
+        print(f"sim_matrix 16384^2 bn={bn}: {ms:.3f} ms  {2 * 16384**2 * 512 / ms / 1e9:.1f} TFLOP/s")
+    lib.pb2_debug_force_bn(0)
+
+
+def step_rank():
+    import torch
+    from peppa_b200 import _cabi, metrics, ops
+    from oracle import pig_oracle as O
+    lib = _cabi.lib()
+    for n, alpha in ((8, 4.0), (100, 0.5), (1000, 4.0), (4096, 0.5)):
+        V, A = emb(n, alpha)
+        ranks_ref, near = O.ranks_identity(V.float().cpu(), A.float().cpu())
+        for bn in (64, 128, 256):
+            lib.pb2_debug_force_bn(bn)
+            rank, *_ = metrics._pair_ranks(V, A, None)
+            rank = rank.cpu().long()
+            bad = (rank != ranks_ref) & ~near
+            print(f"rank n={n} alpha={alpha} bn={bn}: mismatches {int(bad.sum())} (near-tie rows {int(near.sum())}),"
+                  f" raw diff rows {int((rank != ranks_ref).sum())}")
+    lib.pb2_debug_force_bn(0)
+    V, A = emb(16384)
+    rv, _ = ops.row_norms(V)
+    ra, _ = ops.row_norms(A)
+    idx = torch.arange(16384, device="cuda")
+    _, pd = ops.pair_dot(A, V, rinv_x=ra, rinv_y=rv, want_dist=True)
+    for bn in (128, 256):
+        lib.pb2_debug_force_bn(bn)
+        ms = _t(lambda: ops.sim_rank(A, V, ra, rv, pd, idx), iters=10)
+        print(f"sim_rank 16384^2 bn={bn}: {ms:.3f} ms  {2 * 16384**2 * 512 / ms / 1e9:.1f} TFLOP/s  {16384**2 / ms / 1e6:.1f} Gpairs/s")
+    lib.pb2_debug_force_bn(0)
+    ms = _t(lambda: metrics.recall_at_1_to_n(V, A, None, N=10), iters=5)
+    print(f"recall_at_1_to_n 16384^2 end-to-end API: {ms:.3f} ms")
+
+
+def step_gradgemm():
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    combos = [(8192, 1024, 2048)]
+    for (r, c, d) in [(128, 64, 256), (128, 128, 512), (256, 192, 512), (300, 500, 512), (1024, 1024, 512)]:
+        g = torch.randn(r, c, device="cuda").half()
+        gm, ld = ops.gmat_alloc(r, c, "cuda")
+        gm.zero_()
+        gm[:, :c] = g
+        for tr in (False, True):
+            z = torch.randn(c if not tr else r, d, device="cuda").bfloat16()
+            ref = (g.float() if not tr else g.float().T) @ z.float()
+            for (lbo, sbo, ks) in [(8192, 1024, 2048)]:
+                lib.pb2_debug_set_mn_desc(lbo, sbo, ks)
+                got = ops.grad_gemm(gm, r, c, ld, z, transpose=tr)
+                torch.cuda.synchronize()
+                err = (got - ref).abs().max().item()
+                print(f"grad_gemm r={r} c={c} d={d} T={tr} desc=({lbo},{sbo},{ks}): err {err:.3e} ref max {ref.abs().max():.1f}",
+                      "OK" if err < 0.05 else "MISMATCH")
+    lib.pb2_debug_set_mn_desc(8192, 1024, 2048)
+    n = 16384
+    gm, ld = ops.gmat_alloc(n, n, "cuda")
+    gm.normal_()
+    z = torch.randn(n, 512, device="cuda").bfloat16()
+    for tr in (False, True):
+        ms = _t(lambda: ops.grad_gemm(gm, n, n, ld, z, transpose=tr), iters=5)
+        print(f"grad_gemm 16384 T={tr}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s")
+
+
+def step_gradgemm_sweep():
+    """Only if the default MN-major descriptor is wrong: try the plausible alternatives."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    r, c, d = 128, 128, 256
+    g = torch.randn(r, c, device="cuda").half()
+    gm, ld = ops.gmat_alloc(r, c, "cuda")
+    gm.zero_()
+    gm[:, :c] = g
+    z = torch.randn(c, d, device="cuda").bfloat16()
+    ref = g.float() @ z.float()
+    for (lbo, sbo, ks) in [(8192, 1024, 2048), (1024, 8192, 2048), (8192, 1024, 32), (1024, 8192, 32), (16, 1024, 2048),
+                           (128, 1024, 2048), (8192, 128, 2048)]:
+        lib.pb2_debug_set_mn_desc(lbo, sbo, ks)
+        got = ops.grad_gemm(gm, r, c, ld, z, transpose=False)
+        torch.cuda.synchronize()
+        print(f"desc=({lbo},{sbo},{ks}) err {(got - ref).abs().max().item():.3e}")
+
+
+def step_loss():
+    import torch
+    from peppa_b200 import loss as L
+    from oracle import pig_oracle as O
+    for n, alpha in ((8, 4.0), (100, 0.5), (257, 4.0), (1024, 4.0), (1024, 0.5), (2048, 1.0)):
+        V, A = emb(n, alpha)
+        for name, mod, ref in (("hinge", L.TripletLoss(0.2), lambda v, a: O.hinge_loss_and_grads(v, a, 0.2)),
+                               ("milnce", L.MILNCELoss(), O.milnce_loss_and_grads)):
+            v = V.clone().requires_grad_(True)
+            a = A.clone().requires_grad_(True)
+            out = mod(v, a)
+            out.backward()
+            rl, rdv, rda = ref(V.float().cpu(), A.float().cpu())
+            el = abs(out.item() - rl.item()) / abs(rl.item())
+            ev = ((v.grad.float().cpu() - rdv).abs().max() / rdv.abs().max()).item()
+            ea = ((a.grad.float().cpu() - rda).abs().max() / rda.abs().max()).item()
+            print(f"{name} n={n} alpha={alpha}: loss {out.item():.6f} ref {rl.item():.6f} rel {el:.2e}  dV rel {ev:.2e}  dA rel {ea:.2e}",
+                  "OK" if max(el, ev, ea) < 1e-3 else "MISMATCH")
+    for n in (1024, 16384):
+        V, A = emb(n)
+        for name, mod in (("hinge", L.TripletLoss(0.2)), ("milnce", L.MILNCELoss())):
+            def run():
+                v = V.clone().requires_grad_(True)
+                a = A.clone().requires_grad_(True)
+                mod(v, a).backward()
+            ms = _t(run, iters=5)
+            print(f"{name} fwd+bwd n={n}: {ms:.3f} ms  {n * n / ms / 1e6:.2f} Gpairs/s  {6 * n * n * 512 / ms / 1e9:.1f} TFLOP/s(alg)")
+
+
+STEPS = {k[5:]: v for k, v in list(globals().items()) if k.startswith("step_")}
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what != "all":
+        STEPS[what]()
+        return
+    os.makedirs(OUT, exist_ok=True)
+    order = sys.argv[2:] or ["triplet", "simmatrix", "rank", "gradgemm", "loss"]
+    for s in order:
+        t0 = time.time()
+        log = os.path.join(OUT, f"probe_{s}.log")
+        with open(log, "w") as f:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), s], stdout=f, stderr=subprocess.STDOUT,
+                                   timeout=240, cwd=ROOT)
+                rc = r.returncode
+            except subprocess.TimeoutExpired:
+                rc = "timeout"
+        print(f"=== {s}: rc={rc} {time.time() - t0:.1f}s")
+        with open(log) as f:
+            txt = f.read()
+        print(txt[-6000:])
+
+
+if __name__ == "__main__":
+    main()

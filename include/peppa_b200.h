@@ -76,7 +76,7 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
  *   zc = margin + s_ij - diag_col[j],  zr = margin + s_ij - diag_row[i]
  *   loss_partial[cta] += relu(zc) + relu(zr)            (fp32, one slot per CTA, deterministic)
  *   row_cnt[i] += [zr >= 0]      col_cnt[j] += [zc >= 0]   (int32, caller-zeroed)
- *   gmat[i,j] = fp16( ([zc >= 0] + [zr >= 0]) * rinv_x[i] * rinv_y[j] )   (0 on the diagonal)
+ *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
  * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()). */
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
                   const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim,
@@ -99,19 +99,28 @@ int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const fl
                      const float* den_col, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                      float scale, void* gmat, int64_t ld_g, void* stream);
 
-/* ---- backward GEMMs on the tensor cores: out[M, dim] (=|+=) op(G) * Z, G fp16 [g_rows, g_cols],
- * Z bf16.  transpose == 0: out = G * Z (M = g_rows, Z is [g_cols, dim]);
- * transpose != 0: out = G^T * Z (M = g_cols, Z is [g_rows, dim]).  out fp32, scaled by alpha. */
-int pb2_grad_gemm(const void* gmat, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose, const void* z,
-                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, void* stream);
+/* ---- backward GEMMs on the tensor cores: out[M, dim] (=|+=) alpha * op(G) * Z with G [g_rows, g_cols]
+ * and Z 16-bit (PB2_F16 or PB2_BF16 each), fp32 accumulate, fp32 out.  transpose == 0: out = G * Z
+ * (M = g_rows, Z is [g_cols, dim]); transpose != 0: out = G^T * Z (M = g_cols, Z is [g_rows, dim]).
+ * The autograd backward of torch.matmul in pig/util.py:13 / pig/loss.py:19. */
+int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose,
+                  const void* z, int z_dtype, int dim, int64_t ldz, float alpha, int accumulate, float* out,
+                  int64_t ld_out, void* stream);
 
-/* Hinge finish (SURVEY 8a'): g_i = p_i * norm_x[i] + gdiag_i * rinv_y[i] * y_i,  gdiag_i = -(row_cnt[i] +
- * col_cnt[i]); grad_x[i] = coef * rinv_x[i] * (g_i - xhat_i <g_i, xhat_i>), xhat = x * rinv_x.
+/* out = fp16(x * rinv) (rinv == NULL: plain bf16 -> fp16 conversion): the embedding operand of
+ * pb2_grad_gemm.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and fp16 holds every
+ * normalised bf16 embedding value with 3 extra significand bits. */
+int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, int dim, int64_t ld, void* out, int64_t ld_out,
+                       void* stream);
+
+/* Hinge finish (SURVEY 8a'): g_i = p_i + gdiag_i * rinv_y[i] * y_i,  gdiag_i = -(row_cnt[i] + col_cnt[i]),
+ * p = G * Yhat from pb2_grad_gemm; grad_x[i] = coef * rinv_x[i] * (g_i - xhat_i <g_i, xhat_i>),
+ * xhat = x * rinv_x (the Jacobian of the row normalisation in pig/util.py:11-12).
  * coef_dev (device scalar, may be NULL = 1) * coef_host multiplies the result. */
 int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
-                     const float* norm_x, const float* rinv_y, const int32_t* row_cnt, const int32_t* col_cnt,
-                     int64_t rows, int dim, int64_t ldx, int64_t ldy, float coef_host, const float* coef_dev,
-                     float* grad_x, int64_t ld_grad, void* stream);
+                     const float* rinv_y, const int32_t* row_cnt, const int32_t* col_cnt, int64_t rows, int dim,
+                     int64_t ldx, int64_t ldy, float coef_host, const float* coef_dev, float* grad_x,
+                     int64_t ld_grad, void* stream);
 
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
@@ -125,8 +134,9 @@ int pb2_sum_partials(const float* partials, int n, float alpha, float* out, void
 int pb2_milnce_loss(const float* lse_row, const float* lse_col, const float* diag, int64_t n, float* den,
                     float* out, void* stream);
 
-/* pig/loss.py:41-48 contrastive(M) on a materialised square fp32 matrix (HBM-bound):
- * forward loss partials per CTA (+ optional gradient matrix dM scaled by coef). */
+/* pig/loss.py:41-48 contrastive(M) on a materialised square fp32 matrix (HBM-bound): forward loss
+ * partials (+ optional gradient matrix dM scaled by coef).  loss_partial must hold n_partials
+ * floats followed by 2*n int32 of scratch for the indicator counts. */
 int pb2_contrastive_matrix(const float* m, int64_t n, int64_t ld, float margin, float* loss_partial, int n_partials,
                            float* grad_m, int64_t ld_grad, float coef_host, const float* coef_dev, void* stream);
 

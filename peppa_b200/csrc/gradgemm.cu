@@ -32,6 +32,7 @@ struct Args {
     int64_t ld_out;
     // descriptor strides (bytes); runtime so the self-test can probe alternatives
     uint32_t mn_lbo, mn_sbo, mn_kstep;
+    uint32_t idesc;
 };
 
 template <int BN>
@@ -110,8 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc =
-                make_idesc(BM, BN, kFmtF16, kFmtBF16, kTranspose ? kMajorMN : kMajorK, kMajorMN);
+            const uint32_t idesc = a.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int64_t it = 0;
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
 
 template <bool kTranspose, int BN>
-static int launch(const void* g, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int dim, int64_t ldz,
-                  float alpha, int accumulate, float* out, int64_t ld_out, cudaStream_t st) {
+static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int z_fmt,
+                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, cudaStream_t st) {
     CUtensorMap tg, tz;
     const int64_t m = kTranspose ? g_cols : g_rows;
     const int64_t k = kTranspose ? g_rows : g_cols;
@@ -215,6 +215,7 @@ static int launch(const void* g, int64_t g_rows, int64_t g_cols, int64_t ld_g, c
     a.mn_lbo = g_mn_lbo;
     a.mn_sbo = g_mn_sbo;
     a.mn_kstep = g_mn_kstep;
+    a.idesc = make_idesc(BM, BN, (uint32_t)g_fmt, (uint32_t)z_fmt, kTranspose ? kMajorMN : kMajorK, kMajorMN);
     auto kern = grad_gemm_kernel<kTranspose, BN>;
     constexpr int smem = Smem<BN>::kTotal;
     static bool configured = false;
@@ -240,17 +241,22 @@ extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep)
     return PB2_OK;
 }
 
-extern "C" int pb2_grad_gemm(const void* gmat, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose,
-                             const void* z, int dim, int64_t ldz, float alpha, int accumulate, float* out,
-                             int64_t ld_out, void* stream) {
+extern "C" int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g,
+                             int transpose, const void* z, int z_dtype, int dim, int64_t ldz, float alpha,
+                             int accumulate, float* out, int64_t ld_out, void* stream) {
     if (g_rows <= 0 || g_cols <= 0) return PB2_OK;
     if (!gmat || !z || !out) return set_error(PB2_ERR_ARG, "grad_gemm: null");
     if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "grad_gemm: dim must be a multiple of 64");
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0)
         return set_error(PB2_ERR_ARG, "grad_gemm: out must be 16-byte aligned with ld_out %% 4 == 0");
+    if ((g_dtype != PB2_F16 && g_dtype != PB2_BF16) || (z_dtype != PB2_F16 && z_dtype != PB2_BF16))
+        return set_error(PB2_ERR_ARG, "grad_gemm: operands must be fp16 or bf16");
     cudaStream_t st = (cudaStream_t)stream;
     const int bn = dim % 256 == 0 ? 256 : (dim % 128 == 0 ? 128 : 64);
-#define PB2_GG(T, B) gg::launch<T, B>(gmat, g_rows, g_cols, ld_g, z, dim, ldz, alpha, accumulate, out, ld_out, st)
+    const int gf = g_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
+    const int zf = z_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
+#define PB2_GG(T, B) \
+    gg::launch<T, B>(gmat, gf, g_rows, g_cols, ld_g, z, zf, dim, ldz, alpha, accumulate, out, ld_out, st)
     if (transpose) {
         if (bn == 256) return PB2_GG(true, 256);
         if (bn == 128) return PB2_GG(true, 128);

@@ -49,6 +49,28 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const __nv_bfloat16* __r
     }
 }
 
+// ------------------------------------------------------------------- normalised fp16 copy
+// out = fp16(x * rinv): the B operand of the gradient GEMMs.  tcgen05 kind::f16 cannot mix an fp16
+// A with a bf16 B, so the gradient matrix (fp16, exact small integers for the hinge loss) is paired
+// with an fp16 copy of the normalised embeddings (|.| <= 1, 11-bit significand: rounding 2^-12).
+__global__ void __launch_bounds__(256)
+    rows_scale_f16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ rinv, int64_t n, int dim,
+                          int64_t ld, __half* __restrict__ out, int64_t ld_out) {
+    const int vec_per_row = dim / 8;
+    const int64_t total = n * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int d = (int)(i % vec_per_row) * 8;
+        float f[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(x + r * ld + d), f);
+        const float s = rinv ? rinv[r] : 1.f;
+        __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e] * s, f[2 * e + 1] * s);
+        *reinterpret_cast<uint4*>(out + r * ld_out + d) = *reinterpret_cast<const uint4*>(h);
+    }
+}
+
 // ----------------------------------------------------------------------------------- pair dot
 __global__ void __launch_bounds__(256)
     pair_dot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
@@ -144,7 +166,7 @@ __global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restri
 __global__ void __launch_bounds__(256)
     hinge_finish_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ x,
                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ rinv_x,
-                        const float* __restrict__ norm_x, const float* __restrict__ rinv_y,
+                        const float* __restrict__ rinv_y,
                         const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ col_cnt, int64_t rows,
                         int dim, int64_t ldx, int64_t ldy, float coef_host, const float* __restrict__ coef_dev,
                         float* __restrict__ grad, int64_t ld_grad) {
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(256)
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const float coef = coef_host * (coef_dev ? coef_dev[0] : 1.f);
     for (int64_t r = warp; r < rows; r += nwarps) {
-        const float rx = rinv_x[r], nx = norm_x[r];
+        const float rx = rinv_x[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * rinv_y[r];
         const float* pr = p + r * ld_p;
         const __nv_bfloat16* xr = x + r * ldx;
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(256)
             const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(pv[e], nx, gd * b[e]), a[e] * rx, dot);
+            for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(gd, b[e], pv[e]), a[e] * rx, dot);
         }
         dot = warp_sum(dot);
         for (int d = lane * 8; d < dim; d += 256) {
@@ -180,7 +202,7 @@ __global__ void __launch_bounds__(256)
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float g = fmaf(pv[e], nx, gd * b[e]);
+                const float g = fmaf(gd, b[e], pv[e]);
                 o[e] = coef * rx * (g - a[e] * rx * dot);
             }
             float* gr = grad + r * ld_grad + d;
@@ -291,6 +313,18 @@ extern "C" int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, floa
     return check_launch("row_norms");
 }
 
+extern "C" int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
+                                  int64_t ld_out, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!x || !out || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 2) || !vec_ok(out, ld_out, 2))
+        return set_error(PB2_ERR_ARG, "rows_scale_f16: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
+    const int64_t total = n * (dim / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    rows_scale_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rinv, n, dim, ld,
+                                                                  (__half*)out, ld_out);
+    return check_launch("rows_scale_f16");
+}
+
 extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
                             const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out,
                             float* dist_out, void* stream) {
@@ -326,17 +360,17 @@ extern "C" int pb2_milnce_loss(const float* lse_row, const float* lse_col, const
 }
 
 extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
-                                const float* norm_x, const float* rinv_y, const int32_t* row_cnt,
+                                const float* rinv_y, const int32_t* row_cnt,
                                 const int32_t* col_cnt, int64_t rows, int dim, int64_t ldx, int64_t ldy,
                                 float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
                                 void* stream) {
     if (rows <= 0) return PB2_OK;
-    if (!p || !x || !y || !rinv_x || !norm_x || !rinv_y || !row_cnt || !col_cnt || !grad_x)
+    if (!p || !x || !y || !rinv_x || !rinv_y || !row_cnt || !col_cnt || !grad_x)
         return set_error(PB2_ERR_ARG, "hinge_finish: null");
     if (dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
         return set_error(PB2_ERR_ARG, "hinge_finish: alignment");
     hinge_finish_kernel<<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
-        p, ld_p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, norm_x, rinv_y, row_cnt, col_cnt, rows, dim,
+        p, ld_p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim,
         ldx, ldy, coef_host, coef_dev, grad_x, ld_grad);
     return check_launch("hinge_finish");
 }

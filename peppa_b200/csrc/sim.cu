@@ -221,8 +221,8 @@ struct HingePolicy {
             rcnt += ir ? 1 : 0;
             const uint32_t b = __ballot_sync(0xffffffffu, ic);
             if (lane == j) ccnt = __popc(b);
-            const float g = ((ic ? 1.f : 0.f) + (ir ? 1.f : 0.f)) * w;
-            const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(g));
+            // fp16 bit patterns of 0, 1, 2: exact, no conversion instruction
+            const uint32_t h = (ic && ir) ? 0x4000u : ((ic || ir) ? 0x3c00u : 0u);
             if (j & 1) packed[j >> 1] |= h << 16;
             else packed[j >> 1] = h;
         }

@@ -41,6 +41,8 @@ class _HingeFn(torch.autograd.Function):
         inv_n2 = 1.0 / float(n) ** 2
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         pv = pa = None
+        if need_grad:       # fp16 copies of the normalised embeddings: operands of the gradient GEMMs
+            vh, ah = ops.rows_scale_f16(vb, rv), ops.rows_scale_f16(ab, ra)
         blocks = _blocks(n, _MAX_BLOCK)
         for (r0, r1) in blocks:
             for (c0, c1) in blocks:
@@ -56,14 +58,14 @@ class _HingeFn(torch.autograd.Function):
                             torch.empty(n, vb.shape[1], dtype=torch.float32, device=dev)
                         pa = torch.zeros_like(pv) if len(blocks) > 1 else torch.empty_like(pv)
                     acc = len(blocks) > 1
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ab[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vb[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
         # zero-norm rows: the reference yields NaN (division by a zero norm, pig/util.py:11-12)
         bad = ~(torch.isfinite(rv).all() & torch.isfinite(ra).all())
         loss = torch.where(bad, torch.full_like(loss, float("nan")), loss)
         if need_grad:
-            dV = ops.hinge_finish(pv, vb, ab, rv, nv, ra, row_cnt, col_cnt, inv_n2)
-            dA = ops.hinge_finish(pa, ab, vb, ra, na, rv, row_cnt, col_cnt, inv_n2)
+            dV = ops.hinge_finish(pv, vb, ab, rv, ra, row_cnt, col_cnt, inv_n2)
+            dA = ops.hinge_finish(pa, ab, vb, ra, rv, row_cnt, col_cnt, inv_n2)
             ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
             ctx.meta = (V.dtype, V.device, A.dtype, A.device)
         return loss.to(V.device)
@@ -101,6 +103,7 @@ class _MilNceFn(torch.autograd.Function):
         loss, den = ops.milnce_loss(lse_row, lse_col, diag)
         if need_grad:
             acc = len(blocks) > 1
+            vh, ah = ops.rows_scale_f16(vb), ops.rows_scale_f16(ab)
             pv = torch.zeros(n, vb.shape[1], dtype=torch.float32, device=dev) if acc else \
                 torch.empty(n, vb.shape[1], dtype=torch.float32, device=dev)
             pa = torch.zeros_like(pv) if acc else torch.empty_like(pv)
@@ -108,8 +111,8 @@ class _MilNceFn(torch.autograd.Function):
                 for (c0, c1) in blocks:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
                     ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den[c0:c1], g, ld)
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ab[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vb[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
             dV = ops.milnce_finish(pv, ab, 1.0 / n)
             dA = ops.milnce_finish(pa, vb, 1.0 / n)
             ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])

@@ -145,17 +145,27 @@ def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, acc
         out = torch.empty(m, d, dtype=torch.float32, device=z.device)
         accumulate = False
     with torch.cuda.device(z.device):
-        check(_cabi.lib().pb2_grad_gemm(_ptr(gmat), g_rows, g_cols, int(ld_g), int(bool(transpose)), _ptr(z), d, z.stride(0),
-                                        float(alpha), int(bool(accumulate)), _ptr(out), out.stride(0), _stream(z.device)),
-              "grad_gemm")
+        check(_cabi.lib().pb2_grad_gemm(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g), int(bool(transpose)),
+                                        _ptr(z), _DTYPE_CODE[z.dtype], d, z.stride(0), float(alpha), int(bool(accumulate)),
+                                        _ptr(out), out.stride(0), _stream(z.device)), "grad_gemm")
     return out
 
 
-def hinge_finish(p, x, y, rinv_x, norm_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
+def rows_scale_f16(x_bf16, rinv=None):
+    """fp16(x * rinv): the embedding operand of the gradient GEMMs."""
+    n, d = x_bf16.shape
+    out = torch.empty(n, d, dtype=torch.float16, device=x_bf16.device)
+    with torch.cuda.device(x_bf16.device):
+        check(_cabi.lib().pb2_rows_scale_f16(_ptr(x_bf16), _ptr(rinv), n, d, x_bf16.stride(0), _ptr(out), out.stride(0) if n else d,
+                                             _stream(x_bf16.device)), "rows_scale_f16")
+    return out
+
+
+def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
     rows, d = x.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _ptr(rinv_x), _ptr(norm_x), _ptr(rinv_y),
+        check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y),
                                            _ptr(row_cnt), _ptr(col_cnt), rows, d, x.stride(0), y.stride(0), float(coef_host),
                                            _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(x.device)), "hinge_finish")
     return grad

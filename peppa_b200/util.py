@@ -36,21 +36,20 @@ class _CosineMatrix(torch.autograd.Function):
     def backward(ctx, dS):
         S, ub, vb, ru, nu, rv, nv = ctx.saved_tensors
         dS = dS.to(device=S.device, dtype=torch.float32)
-        # d/dÛ = dS V̂, d/dV̂ = dSᵀ Û; fold the row/col norms and a power-of-two range scale into fp16
-        amax = (dS.abs() * ru[:, None] * rv[None, :]).amax().clamp_min(1e-30)
-        shift = torch.floor(torch.log2(16384.0 / amax))
-        scale = torch.exp2(shift)
+        # d/dÛ = dS V̂, d/dV̂ = dSᵀ Û; dS goes to fp16 with a power-of-two range scale
+        amax = dS.abs().amax().clamp_min(1e-30)
+        scale = torch.exp2(torch.floor(torch.log2(16384.0 / amax)))
         r, c = S.shape
         g, ld = ops.gmat_alloc(r, c, S.device)
-        g[:, :c] = (dS * ru[:, None] * rv[None, :] * scale).to(torch.float16)
+        g[:, :c] = (dS * scale).to(torch.float16)
         inv = (1.0 / scale).reshape(1)
         zeros_r = torch.zeros(r, dtype=torch.int32, device=S.device)
         zeros_c = torch.zeros(c, dtype=torch.int32, device=S.device)
-        pu = ops.grad_gemm(g, r, c, ld, vb, transpose=False)
-        pv = ops.grad_gemm(g, r, c, ld, ub, transpose=True)
+        pu = ops.grad_gemm(g, r, c, ld, ops.rows_scale_f16(vb, rv), transpose=False)
+        pv = ops.grad_gemm(g, r, c, ld, ops.rows_scale_f16(ub, ru), transpose=True)
         # hinge_finish with zero counts is exactly the normalisation Jacobian
-        dU = ops.hinge_finish(pu, ub, ub, ru, nu, ru, zeros_r, zeros_r, 1.0, inv)
-        dV = ops.hinge_finish(pv, vb, vb, rv, nv, rv, zeros_c, zeros_c, 1.0, inv)
+        dU = ops.hinge_finish(pu, ub, ub, ru, ru, zeros_r, zeros_r, 1.0, inv)
+        dV = ops.hinge_finish(pv, vb, vb, rv, rv, zeros_c, zeros_c, 1.0, inv)
         dU = dU[:, :ctx.in_dims[0]].to(device=ctx.in_devices[0], dtype=ctx.in_dtypes[0])
         dV = dV[:, :ctx.in_dims[1]].to(device=ctx.in_devices[1], dtype=ctx.in_dtypes[1])
         return dU, dV

@@ -31,7 +31,7 @@ def test_argument_errors_are_reported_without_touching_a_device(lib):
     assert lib.pb2_triplet_score(null, null, null, null, null, null, 0, 512, 512, 0, 1, null, null) == 0   # empty ok
     assert lib.pb2_triplet_score(null, null, null, null, null, null, 4, 512, 512, 9, 1, null, null) == 1
     assert lib.pb2_sim_lse_parts(1000) == 16
-    assert lib.pb2_grad_gemm(null, 8, 8, 64, 0, null, 512, 512, 1.0, 0, null, 512, null) == 1
+    assert lib.pb2_grad_gemm(null, 1, 8, 8, 64, 0, null, 0, 512, 512, 1.0, 0, null, 512, null) == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -120,35 +120,49 @@ def step_rank():
     print(f"recall_at_1_to_n 16384^2 end-to-end API: {ms:.3f} ms")
 
 
-def step_gradgemm():
+def _gradgemm(gdt, zdt, perf=True):
     import torch
-    from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    from peppa_b200 import ops
     torch.manual_seed(0)
-    combos = [(8192, 1024, 2048)]
-    for (r, c, d) in [(128, 64, 256), (128, 128, 512), (256, 192, 512), (300, 500, 512), (1024, 1024, 512)]:
-        g = torch.randn(r, c, device="cuda").half()
-        gm, ld = ops.gmat_alloc(r, c, "cuda")
-        gm.zero_()
-        gm[:, :c] = g
-        for tr in (False, True):
-            z = torch.randn(c if not tr else r, d, device="cuda").bfloat16()
+    for tr in (False, True):
+        for (r, c, d) in [(128, 64, 256), (128, 128, 512), (256, 192, 512), (300, 500, 512), (1024, 1024, 512)]:
+            g = torch.randn(r, c, device="cuda").to(gdt)
+            gm, ld = ops.gmat_alloc(r, c, "cuda")
+            gm = gm.view(torch.int16).view(gdt) if gdt != gm.dtype else gm
+            gm.zero_()
+            gm[:, :c] = g
+            z = torch.randn(c if not tr else r, d, device="cuda").to(zdt)
             ref = (g.float() if not tr else g.float().T) @ z.float()
-            for (lbo, sbo, ks) in [(8192, 1024, 2048)]:
-                lib.pb2_debug_set_mn_desc(lbo, sbo, ks)
-                got = ops.grad_gemm(gm, r, c, ld, z, transpose=tr)
-                torch.cuda.synchronize()
-                err = (got - ref).abs().max().item()
-                print(f"grad_gemm r={r} c={c} d={d} T={tr} desc=({lbo},{sbo},{ks}): err {err:.3e} ref max {ref.abs().max():.1f}",
-                      "OK" if err < 0.05 else "MISMATCH")
-    lib.pb2_debug_set_mn_desc(8192, 1024, 2048)
+            got = ops.grad_gemm(gm, r, c, ld, z, transpose=tr)
+            torch.cuda.synchronize()
+            err = (got - ref).abs().max().item()
+            print(f"grad_gemm {gdt} x {zdt} r={r} c={c} d={d} T={tr}: err {err:.3e} ref max {ref.abs().max():.1f}",
+                  "OK" if err < 0.05 else "MISMATCH", flush=True)
+    if not perf:
+        return
     n = 16384
     gm, ld = ops.gmat_alloc(n, n, "cuda")
+    gm = gm.view(torch.int16).view(gdt) if gdt != gm.dtype else gm
     gm.normal_()
-    z = torch.randn(n, 512, device="cuda").bfloat16()
+    z = torch.randn(n, 512, device="cuda").to(zdt)
     for tr in (False, True):
         ms = _t(lambda: ops.grad_gemm(gm, n, n, ld, z, transpose=tr), iters=5)
-        print(f"grad_gemm 16384 T={tr}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s")
+        print(f"grad_gemm 16384 T={tr}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+def step_gg_f16_f16():
+    import torch
+    _gradgemm(torch.float16, torch.float16)
+
+
+def step_gg_bf16_bf16():
+    import torch
+    _gradgemm(torch.bfloat16, torch.bfloat16, perf=False)
+
+
+def step_gg_f16_bf16():
+    import torch
+    _gradgemm(torch.float16, torch.bfloat16, perf=False)
 
 
 def step_gradgemm_sweep():
@@ -167,7 +181,7 @@ def step_gradgemm_sweep():
     for (lbo, sbo, ks) in [(8192, 1024, 2048), (1024, 8192, 2048), (8192, 1024, 32), (1024, 8192, 32), (16, 1024, 2048),
                            (128, 1024, 2048), (8192, 128, 2048)]:
         lib.pb2_debug_set_mn_desc(lbo, sbo, ks)
-        got = ops.grad_gemm(gm, r, c, ld, z, transpose=False)
+        got = ops.grad_gemm(gm, r, c, ld, z.half(), transpose=False)
         torch.cuda.synchronize()
         print(f"desc=({lbo},{sbo},{ks}) err {(got - ref).abs().max().item():.3e}")
 
@@ -210,7 +224,7 @@ def main():
         STEPS[what]()
         return
     os.makedirs(OUT, exist_ok=True)
-    order = sys.argv[2:] or ["triplet", "simmatrix", "rank", "gradgemm", "loss"]
+    order = sys.argv[2:] or ["triplet", "simmatrix", "rank", "gg_f16_f16", "gg_bf16_bf16", "gg_f16_bf16", "loss"]
     for s in order:
         t0 = time.time()
         log = os.path.join(OUT, f"probe_{s}.log")

@@ -33,6 +33,8 @@ extern "C" {
 
 const char* pb2_last_error(void);
 int pb2_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long pb2_launch_count(void);
 
 /* ---- (c) triplet scoring: replaces pig/metrics.py:45-52 triplet_accuracy and the gathers of
  * pig/triplet.py:71-73,89-91.  out[t] = cos(a_t,p_t) - cos(a_t,n_t) (discrete == 0) or
@@ -77,11 +79,13 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
  *   loss_partial[cta] += relu(zc) + relu(zr)            (fp32, one slot per CTA, deterministic)
  *   row_cnt[i] += [zr >= 0]      col_cnt[j] += [zc >= 0]   (int32, caller-zeroed)
  *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
- * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()). */
+ * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()).
+ * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
+ * rank[i] += #{ j != i : fl32(1 - s_ij) < pos_dist[i] } (loss and recall@k share one S pass). */
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
                   const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim,
                   int64_t ldx, int64_t ldy, float margin, float* loss_partial, int n_partials, int32_t* row_cnt,
-                  int32_t* col_cnt, void* gmat, int64_t ld_g, void* stream);
+                  int32_t* col_cnt, void* gmat, int64_t ld_g, const float* pos_dist, int32_t* rank, void* stream);
 
 /* pig/loss.py:13-26 MILNCELoss: row-wise online log-sum-exp of s over all columns.
  * part_max / part_sum are [n_col_tiles * 2, rows] fp32 partials in the log2 domain

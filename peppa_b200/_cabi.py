@@ -25,13 +25,14 @@ _f = C.c_float
 SIGNATURES = {
     "pb2_version": [],
     "pb2_last_error": [],
+    "pb2_launch_count": [],
     "pb2_sim_grid": [],
     "pb2_triplet_score": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i, _i, _p, _p],
     "pb2_row_norms": [_p, _i64, _i, _i64, _p, _p, _p],
     "pb2_pair_dot": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p],
     "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i64, _i64, _p, _p],
-    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p],
+    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],
     "pb2_sim_lse_parts": [_i64],
     "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _p, _p],
     "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
@@ -44,7 +45,7 @@ SIGNATURES = {
     "pb2_milnce_loss": [_p, _p, _p, _i64, _p, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
 }
-_RESTYPE = {"pb2_last_error": C.c_char_p}
+_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong}
 # test hooks, not part of the public header
 _DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 

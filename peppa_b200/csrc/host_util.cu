@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "peppa_b200.h"
@@ -25,7 +26,11 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return PB2_OK;
     return set_error(PB2_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
-int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+static std::atomic<long long> g_launches{0};
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_cuda(cudaGetLastError(), what);
+}
 
 int sm_count() {
     static int cached[64];
@@ -73,3 +78,4 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t ro
 
 extern "C" const char* pb2_last_error(void) { return pb2::last_error(); }
 extern "C" int pb2_version(void) { return PB2_VERSION; }
+extern "C" long long pb2_launch_count(void) { return pb2::g_launches.load(std::memory_order_relaxed); }

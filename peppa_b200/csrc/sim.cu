@@ -163,22 +163,29 @@ struct RankPolicy {
     __device__ void kernel_end(const Params&, float*) {}
 };
 
-struct HingePolicy {
-    struct Params {
-        const float* diag_row;
-        const float* diag_col;
-        int64_t row_offset, col_offset;
-        float margin;
-        float* loss_partial;
-        int32_t* row_cnt;
-        int32_t* col_cnt;
-        __half* gmat;
-        int64_t ld_g;
-    };
+struct HingeParams {
+    const float* diag_row;
+    const float* diag_col;
+    int64_t row_offset, col_offset;
+    float margin;
+    float* loss_partial;
+    int32_t* row_cnt;
+    int32_t* col_cnt;
+    __half* gmat;
+    int64_t ld_g;
+    const float* pos_dist;  // kRank only: fl32(1 - diag_row)
+    int32_t* rank;          // kRank only
+};
+constexpr int kColVecStride = 256;  // floats between column vectors in smem (= max BN)
+
+// kRank additionally counts, per row, the columns closer than the diagonal (recall@k of the same
+// similarity pass: the gallery workload shares one S pass between pig.loss and pig.metrics).
+template <bool kRank>
+struct HingePolicyT {
+    using Params = HingeParams;
     static constexpr int kColVecs = 2;  // rinv_y, margin - diag_col
-    float ri, mrow, loss;
-    int rcnt, dcol;
-    bool has_diag;
+    float ri, mrow, loss, pd;
+    int rcnt, dcol, rk;
     __device__ void kernel_begin(const Params&) { loss = 0.f; }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
         // out-of-range column: a NaN scale makes every comparison false (no loss, no counts)
@@ -187,6 +194,8 @@ struct HingePolicy {
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
         rcnt = 0;
+        rk = 0;
+        pd = (kRank && t.row_valid) ? p.pos_dist[t.row] : 0.f;
         if (t.row_valid) {
             ri = c.rinv_x ? c.rinv_x[t.row] : 1.f;
             mrow = p.margin - p.diag_row[t.row];
@@ -202,7 +211,7 @@ struct HingePolicy {
                           const float* cv) {
         const bool valid_chunk = cbase < t.cols_valid;  // warp-uniform
         if (!valid_chunk) return;
-        const float* cm = cv + (size_t)kMaxColVecsStride;  // second column vector (see kernel)
+        const float* cm = cv + kColVecStride;  // second column vector (see kernel)
         const int lane = lane_id();
         const int drel = dcol - cbase;                 // diagonal position inside this chunk, if any
         uint32_t packed[16];
@@ -210,8 +219,8 @@ struct HingePolicy {
         float l = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float w = ri * cv[j];
-            const float s = __uint_as_float(v[j]) * w;
+            const float s = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), ri), cv[j]);
+            if (kRank) rk += ((j != drel) && (__fsub_rn(1.0f, s) < pd)) ? 1 : 0;
             float zc = s + cm[j];
             float zr = s + mrow;
             const bool off = (j != drel);
@@ -240,6 +249,7 @@ struct HingePolicy {
     }
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {
         if (t.row_valid && rcnt) atomicAdd(p.row_cnt + t.row, rcnt);
+        if (kRank && t.row_valid && rk) atomicAdd(p.rank + t.row, rk);
     }
     __device__ void kernel_end(const Params& p, float* red) {
         // fixed-order reduction over the 256 epilogue threads -> one deterministic partial per CTA
@@ -254,7 +264,6 @@ struct HingePolicy {
             p.loss_partial[blockIdx.x] = s;
         }
     }
-    static constexpr int kMaxColVecsStride = 256;  // floats between column vectors in smem (= max BN)
 };
 
 struct LseRowPolicy {
@@ -325,7 +334,7 @@ struct LseGradPolicy {
     __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
                           const float* cv) {
         if (cbase >= t.cols_valid || !t.row_valid) return;
-        const float* cd = cv + HingePolicy::kMaxColVecsStride;
+        const float* cd = cv + kColVecStride;
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -603,7 +612,7 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
                              const float* diag_row, const float* diag_col, int64_t rows, int64_t cols,
                              int64_t row_offset, int64_t col_offset, int dim, int64_t ldx, int64_t ldy, float margin,
                              float* loss_partial, int n_partials, int32_t* row_cnt, int32_t* col_cnt, void* gmat,
-                             int64_t ld_g, void* stream) {
+                             int64_t ld_g, const float* pos_dist, int32_t* rank, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!diag_row || !diag_col || !loss_partial || !row_cnt || !col_cnt)
         return set_error(PB2_ERR_ARG, "sim_hinge: null");
@@ -613,10 +622,15 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
     int rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
                         "sim_hinge memset");
     if (rc) return rc;
-    HingePolicy::Params pp{diag_row, diag_col, row_offset, col_offset, margin, loss_partial,
-                           row_cnt,  col_cnt,  (__half*)gmat, ld_g};
-    return dispatch_sim<HingePolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream, "sim_hinge",
-                                     g_force_bn);
+    if ((pos_dist == nullptr) != (rank == nullptr))
+        return set_error(PB2_ERR_ARG, "sim_hinge: pos_dist and rank go together");
+    HingeParams pp{diag_row, diag_col, row_offset, col_offset,      margin, loss_partial,
+                   row_cnt,  col_cnt,  (__half*)gmat, ld_g, pos_dist, rank};
+    if (rank)
+        return dispatch_sim<HingePolicyT<true>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
+                                                "sim_hinge+rank", g_force_bn);
+    return dispatch_sim<HingePolicyT<false>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
+                                             "sim_hinge", g_force_bn);
 }
 
 // LSE partial layout is fixed to the 128-column tile so the caller can size buffers up front.

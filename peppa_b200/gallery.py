@@ -1,0 +1,135 @@
+"""Row-sharded audio<->video gallery: symmetric hinge loss (forward + gradients) and recall@1..N
+from ONE pass over the similarity matrix, on 1..P GPUs (BASELINE config 5).
+
+Rank r owns rows [r*N/P, (r+1)*N/P) of both the audio matrix A and the video matrix V.
+Rows of S are the local audio clips (queries, as in pig/metrics.py:8 where ``references`` = audio),
+columns are ALL video clips:
+
+  1. all-gather the video block (bf16), its row norms and the diagonal scores  (NCCL over NVLink)
+  2. fused tcgen05 pass over the [N/P x N] strip: hinge loss partials, indicator counts, rank
+     counts of the diagonal, and the fp16 gradient-matrix block           (pb2_sim_hinge + rank)
+  3. gradient GEMMs: dA rows are complete locally; dV partials are [N, D] per rank
+  4. all-reduce the column counts (int32) and the scalar loss; reduce-scatter the dV partials
+  5. normalisation Jacobian (pb2_hinge_finish) on the local rows
+
+The loss is symmetric in (V, A) (pig/loss.py:41-48 adds the row and the column hinge), so
+``contrastive(cosine_matrix(A, V))`` equals the reference's ``TripletLoss(V, A)``; the gradients are
+returned under their own names.  With world_size == 1 no collective is issued.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_BLOCK = 32768      # gradient-matrix block edge (rows x cols fp16 kept in HBM at once: 2 GiB)
+
+
+def _blocks(n, step):
+    return [(s, min(n, s + step)) for s in range(0, n, step)]
+
+
+class GalleryStep:
+    """Reusable buffers + one ``run`` per step.  ``group`` is a torch.distributed process group (or
+    None for the default group); ``world == 1`` needs no initialised process group at all."""
+
+    def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
+                 group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None):
+        # ``backend`` exists for the world_size-2 gloo tests of the orchestration on CPU boxes: they
+        # inject an emulation of the kernel entry points built from the oracle.  The product never
+        # passes it; the default is the CUDA ops module and there is no automatic selection.
+        self.ops = backend if backend is not None else ops
+        self.n_local, self.dim, self.margin, self.top_n = n_local, dim, float(margin), top_n
+        self.rank, self.world, self.group = rank, world, group
+        self.n_total = n_local * world
+        self.device = ops.require_cuda(device) if backend is None else torch.device(device or "cpu")
+        self.block = block
+        self.with_grad = with_grad
+        dev, n, nl = self.device, self.n_total, n_local
+        f32, i32 = torch.float32, torch.int32
+        self.v_full = torch.empty(n, dim, dtype=torch.bfloat16, device=dev) if world > 1 else None
+        self.rv_full = torch.empty(n, dtype=f32, device=dev) if world > 1 else None
+        self.diag_full = torch.empty(n, dtype=f32, device=dev) if world > 1 else None
+        self.row_cnt = torch.empty(nl, dtype=i32, device=dev)
+        self.col_cnt = torch.empty(n, dtype=i32, device=dev)
+        self.ranks = torch.empty(nl, dtype=i32, device=dev)
+        if with_grad:
+            self.p_a = torch.empty(nl, dim, dtype=f32, device=dev)
+            self.p_v = torch.empty(n, dim, dtype=f32, device=dev)
+            self.p_v_loc = torch.empty(nl, dim, dtype=f32, device=dev) if world > 1 else None
+            br, bc = min(block, nl), min(block, n)
+            self.gmat, self.ld_g = self.ops.gmat_alloc(br, bc, dev)
+
+    # -- collectives (no-ops for world == 1) ------------------------------------------------------
+    def _all_gather(self, out, loc):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, loc.contiguous(), group=self.group)
+
+    def _reduce_scatter(self, out, full):
+        import torch.distributed as dist
+        if dist.get_backend(self.group) == "gloo":      # gloo has no reduce_scatter: all-reduce + slice
+            dist.all_reduce(full, group=self.group)
+            out.copy_(full[self.rank * self.n_local:(self.rank + 1) * self.n_local])
+        else:
+            dist.reduce_scatter_tensor(out, full, group=self.group)
+
+    def run(self, a_loc: torch.Tensor, v_loc: torch.Tensor):
+        """a_loc, v_loc: [n_local, dim] bf16 on this rank's GPU.  Returns a dict with the global loss
+        (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
+        ([top_n + 1] fp32: global recall@n, row 0 == 0) and the local int32 ``ranks``."""
+        import torch.distributed as dist
+        ops = self.ops
+        nl, n, dev = self.n_local, self.n_total, self.device
+        r0g = self.rank * nl                                  # global id of the first local row
+        ra, _ = ops.row_norms(a_loc)
+        rv, _ = ops.row_norms(v_loc)
+        diag, pos_dist = ops.pair_dot(a_loc, v_loc, rinv_x=ra, rinv_y=rv, want_dist=True)
+        if self.world > 1:
+            self._all_gather(self.v_full, v_loc)
+            self._all_gather(self.rv_full, rv)
+            self._all_gather(self.diag_full, diag)
+            v_full, rv_full, diag_full = self.v_full, self.rv_full, self.diag_full
+        else:
+            v_full, rv_full, diag_full = v_loc, rv, diag
+        self.row_cnt.zero_()
+        self.col_cnt.zero_()
+        self.ranks.zero_()
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
+        if self.with_grad:
+            ah = ops.rows_scale_f16(a_loc, ra)
+            vh = ops.rows_scale_f16(v_full, rv_full)
+            acc_a, acc_v = len(cblocks) > 1, len(rblocks) > 1
+            if acc_a:
+                self.p_a.zero_()
+            if acc_v:
+                self.p_v.zero_()
+        for (r0, r1) in rblocks:
+            for (c0, c1) in cblocks:
+                part = ops.sim_hinge(a_loc[r0:r1], v_full[c0:c1], ra[r0:r1], rv_full[c0:c1], diag[r0:r1],
+                                     diag_full[c0:c1], self.margin, self.row_cnt[r0:r1], self.col_cnt[c0:c1],
+                                     self.gmat if self.with_grad else None, self.ld_g if self.with_grad else 0,
+                                     row_offset=r0g + r0, col_offset=c0, pos_dist=pos_dist[r0:r1],
+                                     rank=self.ranks[r0:r1])
+                loss = loss + ops.sum_partials(part, 1.0)
+                if self.with_grad:
+                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vh[c0:c1], transpose=False,
+                                  out=self.p_a[r0:r1], accumulate=acc_a)
+                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True,
+                                  out=self.p_v[c0:c1], accumulate=acc_v)
+        hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
+        hits = hits.sum(dim=1).to(torch.float32)
+        if self.world > 1:
+            dist.all_reduce(self.col_cnt, group=self.group)
+            dist.all_reduce(loss, group=self.group)
+            dist.all_reduce(hits, group=self.group)
+            if self.with_grad:
+                self._reduce_scatter(self.p_v_loc, self.p_v)
+        inv_n2 = 1.0 / float(n) ** 2
+        out = {"loss": loss * inv_n2, "recall": hits / float(n), "ranks": self.ranks, "dA": None, "dV": None}
+        if self.with_grad:
+            cc = self.col_cnt[r0g:r0g + nl]
+            p_v_loc = self.p_v_loc if self.world > 1 else self.p_v
+            out["dA"] = ops.hinge_finish(self.p_a, a_loc, v_loc, ra, rv, self.row_cnt, cc, inv_n2)
+            out["dV"] = ops.hinge_finish(p_v_loc, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
+        return out

@@ -16,6 +16,27 @@ from ._cabi import PB2_BF16, PB2_F16, PB2_F32, check
 _DTYPE_CODE = {torch.bfloat16: PB2_BF16, torch.float16: PB2_F16, torch.float32: PB2_F32}
 
 
+# bench.py sets this to a list to time individual kernels with CUDA events on the launching stream:
+# entries are (name, algorithmic flops of the launch, start event, end event).
+EVENT_LOG = None
+
+
+class _timed:
+    def __init__(self, name, flops, device):
+        self.name, self.flops, self.device = name, flops, device
+
+    def __enter__(self):
+        if EVENT_LOG is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *a):
+        if EVENT_LOG is not None:
+            self.e.record(torch.cuda.current_stream(self.device))
+            EVENT_LOG.append((self.name, self.flops, self.s, self.e))
+
+
 def require_cuda(device=None) -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("peppa_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
@@ -80,7 +101,7 @@ def sim_rank(q, g, rinv_q, rinv_g, pos_dist, pos_col, col_offset=0, rank=None):
     r, c = q.shape[0], g.shape[0]
     if rank is None:
         rank = torch.zeros(r, dtype=torch.int32, device=q.device)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _timed("sim_rank", 2.0 * r * c * q.shape[1], q.device):
         check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_dist), _ptr(pos_col), r, c,
                                        int(col_offset), q.shape[1], q.stride(0), g.stride(0), _ptr(rank),
                                        _stream(q.device)), "sim_rank")
@@ -99,16 +120,16 @@ def gmat_alloc(rows, cols, device):
 
 
 def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0,
-              row_offset=0, col_offset=0):
+              row_offset=0, col_offset=0, pos_dist=None, rank=None):
     """Returns the per-CTA loss partials (fp32 [grid])."""
     r, c = x.shape[0], y.shape[0]
     n_part = sim_grid(x.device)
     part = torch.empty(n_part, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("sim_hinge" + ("+rank" if rank is not None else ""), 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
                                         int(row_offset), int(col_offset), x.shape[1], x.stride(0), y.stride(0),
                                         float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
-                                        int(ld_g), _stream(x.device)), "sim_hinge")
+                                        int(ld_g), _ptr(pos_dist), _ptr(rank), _stream(x.device)), "sim_hinge")
     return part
 
 
@@ -144,7 +165,7 @@ def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, acc
     if out is None:
         out = torch.empty(m, d, dtype=torch.float32, device=z.device)
         accumulate = False
-    with torch.cuda.device(z.device):
+    with torch.cuda.device(z.device), _timed("grad_gemm", 2.0 * g_rows * g_cols * d, z.device):
         check(_cabi.lib().pb2_grad_gemm(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g), int(bool(transpose)),
                                         _ptr(z), _DTYPE_CODE[z.dtype], d, z.stride(0), float(alpha), int(bool(accumulate)),
                                         _ptr(out), out.stride(0), _stream(z.device)), "grad_gemm")

@@ -1,0 +1,66 @@
+"""CPU emulation of the kernel entry points used by peppa_b200.gallery.GalleryStep.  TEST ONLY.
+
+Each function restates the contract of the C-ABI call of the same name (include/peppa_b200.h) with
+plain torch-CPU arithmetic, so the multi-rank orchestration (sharding, collectives, merges) can be
+exercised under gloo with world_size 2 on a box without GPUs.  Never imported by the product.
+"""
+import torch
+
+
+def gmat_alloc(rows, cols, device):
+    ld = ((cols + 63) // 64) * 64
+    return torch.zeros(rows, ld, dtype=torch.float16, device=device), ld
+
+
+def row_norms(x):
+    n = torch.linalg.vector_norm(x.float(), dim=1)
+    return 1.0 / n, n
+
+
+def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False):
+    s = (x.float() * y.float()).sum(dim=1) * rinv_x * rinv_y
+    return (s, 1.0 - s) if want_dist else s
+
+
+def rows_scale_f16(x, rinv=None):
+    xf = x.float()
+    return (xf * rinv[:, None] if rinv is not None else xf).half()
+
+
+def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0, row_offset=0,
+              col_offset=0, pos_dist=None, rank=None):
+    S = (x.float() @ y.float().T) * rinv_x[:, None] * rinv_y[None, :]
+    r, c = S.shape
+    off = (torch.arange(r)[:, None] + row_offset) != (torch.arange(c)[None, :] + col_offset)
+    zc = margin + S - diag_col[None, :]
+    zr = margin + S - diag_row[:, None]
+    ic, ir = off & (zc >= 0), off & (zr >= 0)
+    row_cnt += ir.sum(dim=1).to(torch.int32)
+    col_cnt += ic.sum(dim=0).to(torch.int32)
+    if gmat is not None:
+        gmat[:r, :c] = (ic.float() + ir.float()).half()
+    if rank is not None:
+        rank += (off & ((1.0 - S) < pos_dist[:, None])).sum(dim=1).to(torch.int32)
+    return (torch.where(ic, zc, torch.zeros(())).sum() + torch.where(ir, zr, torch.zeros(())).sum()).reshape(1)
+
+
+def sum_partials(part, alpha=1.0):
+    return part.sum() * alpha
+
+
+def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False):
+    G = gmat[:g_rows, :g_cols].float()
+    res = alpha * ((G.T if transpose else G) @ z.float())
+    if out is None:
+        return res
+    if accumulate:
+        out += res
+    else:
+        out.copy_(res)
+    return out
+
+
+def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
+    g = p + (-(row_cnt + col_cnt).float() * rinv_y)[:, None] * y.float()
+    xh = x.float() * rinv_x[:, None]
+    return coef_host * rinv_x[:, None] * (g - xh * (g * xh).sum(dim=1, keepdim=True))

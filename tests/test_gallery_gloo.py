@@ -1,0 +1,83 @@
+"""CPU, world_size 2 over gloo: the row-sharded gallery step (peppa_b200/gallery.py) -- all-gather of
+the video block, merge of the partial column counts, reduce-scatter of the dV partials -- reproduces
+the single-process closed forms of the oracle.  Kernel entry points are emulated (tests/emu_ops.py);
+the CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _emb(n, alpha, d=128, seed=666):
+    g = torch.Generator().manual_seed(seed)
+    V = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    A = torch.nn.functional.normalize(alpha * V + torch.randn(n, d, generator=g), dim=1)
+    return V.bfloat16(), A.bfloat16()
+
+
+def _worker(rank, world, port, n_local, block, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu_ops
+        from peppa_b200.gallery import GalleryStep
+        V, A = _emb(n_local * world, 4.0)
+        sl = slice(rank * n_local, (rank + 1) * n_local)
+        step = GalleryStep(n_local, V.shape[1], margin=0.2, top_n=10, rank=rank, world=world, device="cpu", block=block,
+                           backend=emu_ops)
+        out = step.run(A[sl].contiguous(), V[sl].contiguous())
+        out2 = step.run(A[sl].contiguous(), V[sl].contiguous())           # buffers are reusable
+        assert torch.equal(out["dA"], out2["dA"]) and torch.equal(out["ranks"], out2["ranks"])
+        q.put((rank, out["loss"].item(), out["recall"].clone(), out["dA"].clone(), out["dV"].clone(), out["ranks"].clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("n_local,block", [(96, 32768), (80, 48)])
+def test_two_rank_gallery_matches_single_process_oracle(n_local, block):
+    from oracle import pig_oracle as O
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_local, block, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    V, A = _emb(n_local * world, 4.0)
+    # rows = audio, cols = video: contrastive(cosine_matrix(A, V)); symmetric, so it is TripletLoss(V, A)
+    loss, dA, dV = O.hinge_loss_and_grads(A.float(), V.float(), 0.2)
+    ref_loss_va = O.triplet_loss(V.float(), A.float(), 0.2)
+    ranks, near = O.ranks_identity(V.float(), A.float())
+    gdA = torch.cat([r[3] for r in res])
+    gdV = torch.cat([r[4] for r in res])
+    granks = torch.cat([r[5] for r in res]).long()
+    for r in res:
+        assert abs(r[1] - loss.item()) < 1e-5 * abs(loss.item()) and abs(r[1] - ref_loss_va.item()) < 1e-5
+    assert (gdA.double() - dA).abs().max() / dA.abs().max() < 1e-3      # fp16 operand rounding of the emulation
+    assert (gdV.double() - dV).abs().max() / dV.abs().max() < 1e-3
+    assert bool(((granks == ranks) | near).all())
+    recall = res[0][2]
+    assert recall[0] == 0 and torch.equal(res[0][2], res[1][2])
+    for k in (1, 5, 10):
+        assert abs(recall[k].item() - (granks < k).float().mean().item()) < 1e-6

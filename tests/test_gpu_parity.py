@@ -184,7 +184,8 @@ def test_ranks_against_oracle(pb, n, alpha):
     got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), None, N=10)
     for k in range(1, 11):
         assert bool((((ranks < k).float() == got[k]) | near).all()), k
-    assert int(near.sum()) < n // 100
+    if alpha >= 4.0:        # realistic regime: near-ties are rare (the adversarial one has ~5 % of rows)
+        assert int(near.sum()) < n // 100
 
 
 def test_retrieval_16k_properties(pb):
@@ -235,3 +236,23 @@ def test_empty_and_tiny_inputs(pb):
     loss, dV, dA = _grads(pb.loss.TripletLoss(0.2), *emb(2, 4.0))
     rl, rdv, rda = O.hinge_loss_and_grads(*emb(2, 4.0), 0.2)
     assert rel_err(loss, rl) < TOL
+
+
+@pytest.mark.parametrize("n,block", [(1536, 32768), (1280, 512), (1000, 384)])
+def test_gallery_step_single_gpu(pb, n, block):
+    """peppa_b200.gallery.GalleryStep (loss fwd+bwd + recall from one S pass, blocked gradient matrix)
+    against the oracle's closed forms; rows = audio, columns = video."""
+    from peppa_b200.gallery import GalleryStep
+    V, A = emb(n, 4.0)
+    step = GalleryStep(n, 512, margin=0.2, top_n=10, block=block)
+    out = step.run(A.cuda().bfloat16(), V.cuda().bfloat16())
+    loss, dA, dV = O.hinge_loss_and_grads(A, V, 0.2)
+    assert rel_err(out["loss"].cpu(), loss) < TOL
+    assert rel_err(out["dA"].cpu(), dA) < TOL and rel_err(out["dV"].cpu(), dV) < TOL
+    assert rel_err(out["loss"].cpu(), O.triplet_loss(V, A, 0.2)) < TOL        # symmetric in (V, A)
+    ranks, near = O.ranks_identity(V, A)
+    assert bool(((out["ranks"].cpu().long() == ranks) | near).all())
+    for k in (1, 5, 10):
+        assert abs(out["recall"][k].item() - (out["ranks"] < k).float().mean().item()) < 1e-6
+    again = step.run(A.cuda().bfloat16(), V.cuda().bfloat16())                 # deterministic, reusable buffers
+    assert torch.equal(again["dA"], out["dA"]) and again["loss"].item() == out["loss"].item()

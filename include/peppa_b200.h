@@ -76,8 +76,10 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
 /* pig/loss.py:28-48 TripletLoss / contrastive, forward pass fused with the gradient matrix.
  * For local rows i (global row id row_offset + i) and columns j (global id col_offset + j), i != j globally:
  *   zc = margin + s_ij - diag_col[j],  zr = margin + s_ij - diag_row[i]
- *   loss_partial[cta] += relu(zc) + relu(zr)            (fp32, one slot per CTA, deterministic)
  *   row_cnt[i] += [zr >= 0]      col_cnt[j] += [zc >= 0]   (int32, caller-zeroed)
+ *   loss_partial[cta] += ([zc >= 0] + [zr >= 0]) * s_ij    (fp32, one slot per CTA, deterministic);
+ *     relu(zc) + relu(zr) summed = these partials + sum_j (margin - diag_col[j]) col_cnt[j]
+ *     + sum_i (margin - diag_row[i]) row_cnt[i], completed by pb2_hinge_loss_terms
  *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
  * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()).
  * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
@@ -129,6 +131,12 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
                       float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);
+
+/* out[0] (=|+=) alpha * ( sum_k partials[k] + sum_k (margin - diag[k]) * cnt[k] ); either group may be
+ * NULL.  Completes the hinge loss from pb2_sim_hinge's partials and indicator counts (double
+ * accumulation, fixed order: deterministic). */
+int pb2_hinge_loss_terms(const float* partials, int n_partials, const float* diag, const int32_t* cnt, int64_t n,
+                         float margin, float alpha, float* out, int accumulate, void* stream);
 
 /* Deterministic fixed-order sum of n fp32 partials, scaled: out[0] = alpha * sum. */
 int pb2_sum_partials(const float* partials, int n, float alpha, float* out, void* stream);

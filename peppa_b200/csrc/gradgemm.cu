@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z,
                      const Args a) {
     using L = Smem<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128-byte-swizzled TMA/UMMA tiles need 1024-byte alignment; the kernel has no static shared
+    // memory, so the dynamic segment starts at the (aligned) base of the CTA's shared window.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + L::kStages;

@@ -138,6 +138,29 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restr
     }
 }
 
+// out (=|+=) alpha * ( sum partials + sum_k (margin - diag[k]) * cnt[k] ), double accumulation, fixed order
+__global__ void __launch_bounds__(1024)
+    hinge_loss_terms_kernel(const float* __restrict__ partials, int n_partials, const float* __restrict__ diag,
+                            const int32_t* __restrict__ cnt, int64_t n, float margin, float alpha,
+                            float* __restrict__ out, int accumulate) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    if (partials)
+        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += (double)partials[i];
+    if (diag && cnt)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)(margin - diag[i]) * (double)cnt[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += sh[w];
+        const float r = (float)(t * (double)alpha);
+        out[0] = accumulate ? out[0] + r : r;
+    }
+}
+
 __global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restrict__ lse_row,
                                                            const float* __restrict__ lse_col,
                                                            const float* __restrict__ diag, int64_t n,
@@ -349,6 +372,15 @@ extern "C" int pb2_sum_partials(const float* partials, int n, float alpha, float
     if (!partials || !out || n < 0) return set_error(PB2_ERR_ARG, "sum_partials: bad arguments");
     sum_partials_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n, alpha, out);
     return check_launch("sum_partials");
+}
+
+extern "C" int pb2_hinge_loss_terms(const float* partials, int n_partials, const float* diag, const int32_t* cnt,
+                                    int64_t n, float margin, float alpha, float* out, int accumulate, void* stream) {
+    if (!out || n_partials < 0 || n < 0 || ((diag == nullptr) != (cnt == nullptr)))
+        return set_error(PB2_ERR_ARG, "hinge_loss_terms: bad arguments");
+    hinge_loss_terms_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n_partials, diag, cnt, n, margin, alpha, out,
+                                                                accumulate);
+    return check_launch("hinge_loss_terms");
 }
 
 extern "C" int pb2_milnce_loss(const float* lse_row, const float* lse_col, const float* diag, int64_t n, float* den,

@@ -183,14 +183,20 @@ constexpr int kColVecStride = 256;  // floats between column vectors in smem (= 
 template <bool kRank>
 struct HingePolicyT {
     using Params = HingeParams;
-    static constexpr int kColVecs = 2;  // rinv_y, margin - diag_col
-    float ri, mrow, loss, pd;
+    static constexpr int kColVecs = 2;  // rinv_y, diag_col - margin
+    // Instruction budget: the MMA of a 128 x 256 x 512 tile takes ~4096 cycles, i.e. ~16 issue slots per
+    // element for the epilogue.  So: no per-element adds for z = margin + s - d; the indicators are
+    // threshold compares (fl32(s + c) >= 0  <=>  s >= -c exactly), the loss is accumulated as
+    // sum (ic + ir) * s per element and completed from the counts afterwards
+    // (pb2_hinge_loss_terms: + sum_j (m - d_j) col_cnt[j] + sum_i (m - d_i) row_cnt[i]); scores use
+    // packed FMUL2; column counts are byte-packed per thread and summed across the warp with REDUX.
+    float ri, thr_r, loss, pd;
     int rcnt, dcol, rk;
     __device__ void kernel_begin(const Params&) { loss = 0.f; }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
         // out-of-range column: a NaN scale makes every comparison false (no loss, no counts)
         v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : __int_as_float(0x7fc00000);
-        v[1] = valid ? (p.margin - p.diag_col[col]) : 0.f;
+        v[1] = valid ? -(p.margin - p.diag_col[col]) : 0.f;
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
         rcnt = 0;
@@ -198,54 +204,79 @@ struct HingePolicyT {
         pd = (kRank && t.row_valid) ? p.pos_dist[t.row] : 0.f;
         if (t.row_valid) {
             ri = c.rinv_x ? c.rinv_x[t.row] : 1.f;
-            mrow = p.margin - p.diag_row[t.row];
+            thr_r = -(p.margin - p.diag_row[t.row]);
             const int64_t rel = (p.row_offset + t.row) - p.col_offset - t.col0;
             dcol = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
             ri = __int_as_float(0x7fc00000);  // out-of-range row: NaN scores never count
-            mrow = 0.f;
+            thr_r = 0.f;
             dcol = -1;
+        }
+    }
+    template <bool kDiag>
+    __device__ __forceinline__ void chunk_impl(const Params& p, const TileCtx& t, int cbase, const uint32_t (&v)[32],
+                                               const float* cv) {
+        const float4* cv4 = reinterpret_cast<const float4*>(cv);
+        const float4* ct4 = reinterpret_cast<const float4*>(cv + kColVecStride);
+        const float2 ri2 = make_float2(ri, ri);
+        const int drel = dcol - cbase;  // diagonal position inside this chunk (kDiag only)
+        uint32_t packed[16], pk[8];
+        float l = 0.f;
+        int rc = 0, rkk = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 c4 = cv4[q], t4 = ct4[q];
+            // fl32(fl32(v * ri) * cj): the same two roundings as the rank kernel and pair_dot
+            const float2 s01 = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), ri2),
+                                          make_float2(c4.x, c4.y));
+            const float2 s23 = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), ri2),
+                                          make_float2(c4.z, c4.w));
+            float sv[4] = {s01.x, s01.y, s23.x, s23.y};
+            const float tc[4] = {t4.x, t4.y, t4.z, t4.w};
+            float g[4];
+            uint32_t pkq = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (kDiag && (4 * q + e) == drel) sv[e] = -3.0e38f;  // the diagonal never counts
+                const bool ic = sv[e] >= tc[e];
+                const bool ir = sv[e] >= thr_r;
+                g[e] = (ic ? 1.f : 0.f) + (ir ? 1.f : 0.f);
+                l = fmaf(g[e], sv[e], l);
+                rc += ir ? 1 : 0;
+                if (kRank) rkk += (__fsub_rn(1.0f, sv[e]) < pd) ? 1 : 0;
+                pkq += ic ? (1u << (8 * e)) : 0u;
+            }
+            pk[q] = pkq;
+            const __half2 h01 = __floats2half2_rn(g[0], g[1]), h23 = __floats2half2_rn(g[2], g[3]);
+            packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+            packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+        }
+        loss += l;
+        rcnt += rc;
+        if (kRank) rk += rkk;
+        // column counts: byte-packed (<= 32 per byte), summed over the warp's 32 rows with REDUX
+        const int lane = lane_id();
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, pk[q]);
+            if ((lane >> 2) == q) mine = tot;
+        }
+        const int ccnt = (int)((mine >> ((lane & 3) * 8)) & 0xffu);
+        if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);
+        if (p.gmat && t.row_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.gmat + t.row * p.ld_g + t.col0 + cbase);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         }
     }
     __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
                           const float* cv) {
-        const bool valid_chunk = cbase < t.cols_valid;  // warp-uniform
-        if (!valid_chunk) return;
-        const float* cm = cv + kColVecStride;  // second column vector (see kernel)
-        const int lane = lane_id();
-        const int drel = dcol - cbase;                 // diagonal position inside this chunk, if any
-        uint32_t packed[16];
-        int ccnt = 0;
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float s = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), ri), cv[j]);
-            if (kRank) rk += ((j != drel) && (__fsub_rn(1.0f, s) < pd)) ? 1 : 0;
-            float zc = s + cm[j];
-            float zr = s + mrow;
-            const bool off = (j != drel);
-            const bool ic = off && (zc >= 0.f);
-            const bool ir = off && (zr >= 0.f);
-            l += (ic ? zc : 0.f) + (ir ? zr : 0.f);
-            rcnt += ir ? 1 : 0;
-            const uint32_t b = __ballot_sync(0xffffffffu, ic);
-            if (lane == j) ccnt = __popc(b);
-            // fp16 bit patterns of 0, 1, 2: exact, no conversion instruction
-            const uint32_t h = (ic && ir) ? 0x4000u : ((ic || ir) ? 0x3c00u : 0u);
-            if (j & 1) packed[j >> 1] |= h << 16;
-            else packed[j >> 1] = h;
-        }
-        loss += l;
-        if (valid_chunk) {
-            const int64_t col = t.col0 + cbase + lane;
-            if (ccnt && col < t.col0 + t.cols_valid) atomicAdd(p.col_cnt + col, ccnt);
-            if (p.gmat && t.row_valid) {
-                uint4* dst = reinterpret_cast<uint4*>(p.gmat + t.row * p.ld_g + t.col0 + cbase);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-            }
-        }
+        if (cbase >= t.cols_valid) return;  // warp-uniform
+        const int drel = dcol - cbase;
+        if (__any_sync(0xffffffffu, drel >= 0 && drel < 32)) chunk_impl<true>(p, t, cbase, v, cv);
+        else chunk_impl<false>(p, t, cbase, v, cv);
     }
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {
         if (t.row_valid && rcnt) atomicAdd(p.row_cnt + t.row, rcnt);
@@ -369,8 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimCommon c,
                const typename Policy::Params p) {
     using L = SimSmem<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128-byte-swizzled TMA/UMMA tiles need 1024-byte alignment; the kernel has no static shared
+    // memory, so the dynamic segment starts at the (aligned) base of the CTA's shared window.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     float* colvec = reinterpret_cast<float*>(smem + L::kTileBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kColVecBytes);
     uint64_t* full = bars;                    // [kStages]

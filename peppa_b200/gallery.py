@@ -111,12 +111,13 @@ class GalleryStep:
                                      self.gmat if self.with_grad else None, self.ld_g if self.with_grad else 0,
                                      row_offset=r0g + r0, col_offset=c0, pos_dist=pos_dist[r0:r1],
                                      rank=self.ranks[r0:r1])
-                loss = loss + ops.sum_partials(part, 1.0)
+                ops.hinge_loss_terms(loss, partials=part)
                 if self.with_grad:
                     ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vh[c0:c1], transpose=False,
                                   out=self.p_a[r0:r1], accumulate=acc_a)
                     ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True,
                                   out=self.p_v[c0:c1], accumulate=acc_v)
+        ops.hinge_loss_terms(loss, diag=diag, cnt=self.row_cnt, margin=self.margin)      # local rows' term
         hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
         hits = hits.sum(dim=1).to(torch.float32)
         if self.world > 1:
@@ -125,6 +126,8 @@ class GalleryStep:
             dist.all_reduce(hits, group=self.group)
             if self.with_grad:
                 self._reduce_scatter(self.p_v_loc, self.p_v)
+        # column term from the merged counts (identical on every rank, added once after the all-reduce)
+        ops.hinge_loss_terms(loss, diag=diag_full, cnt=self.col_cnt, margin=self.margin)
         inv_n2 = 1.0 / float(n) ** 2
         out = {"loss": loss * inv_n2, "recall": hits / float(n), "ranks": self.ranks, "dA": None, "dV": None}
         if self.with_grad:

@@ -51,7 +51,7 @@ class _HingeFn(torch.autograd.Function):
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
                 part = ops.sim_hinge(vb[r0:r1], ab[c0:c1], rv[r0:r1], ra[c0:c1], diag[r0:r1], diag[c0:c1], margin,
                                      row_cnt[r0:r1], col_cnt[c0:c1], g, ld or 0, row_offset=r0, col_offset=c0)
-                loss = loss + ops.sum_partials(part, inv_n2)
+                ops.hinge_loss_terms(loss, partials=part, alpha=inv_n2)
                 if need_grad:
                     if pv is None:
                         pv = torch.zeros(n, vb.shape[1], dtype=torch.float32, device=dev) if len(blocks) > 1 else \
@@ -60,6 +60,8 @@ class _HingeFn(torch.autograd.Function):
                     acc = len(blocks) > 1
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
+        ops.hinge_loss_terms(loss, diag=diag, cnt=row_cnt, margin=margin, alpha=inv_n2)
+        ops.hinge_loss_terms(loss, diag=diag, cnt=col_cnt, margin=margin, alpha=inv_n2)
         # zero-norm rows: the reference yields NaN (division by a zero norm, pig/util.py:11-12)
         bad = ~(torch.isfinite(rv).all() & torch.isfinite(ra).all())
         loss = torch.where(bad, torch.full_like(loss, float("nan")), loss)

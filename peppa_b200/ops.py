@@ -209,6 +209,15 @@ def sum_partials(part, alpha=1.0):
     return out
 
 
+def hinge_loss_terms(out, partials=None, diag=None, cnt=None, margin=0.0, alpha=1.0, accumulate=True):
+    """out (=|+=) alpha * (sum partials + sum (margin - diag) * cnt): completes the hinge loss."""
+    with torch.cuda.device(out.device):
+        check(_cabi.lib().pb2_hinge_loss_terms(_ptr(partials), partials.numel() if partials is not None else 0, _ptr(diag),
+                                               _ptr(cnt), cnt.numel() if cnt is not None else 0, float(margin), float(alpha),
+                                               _ptr(out), int(bool(accumulate)), _stream(out.device)), "hinge_loss_terms")
+    return out
+
+
 def milnce_loss(lse_row, lse_col, diag):
     n = lse_row.shape[0]
     den = torch.empty(n, dtype=torch.float32, device=lse_row.device)

@@ -41,11 +41,21 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
         gmat[:r, :c] = (ic.float() + ir.float()).half()
     if rank is not None:
         rank += (off & ((1.0 - S) < pos_dist[:, None])).sum(dim=1).to(torch.int32)
-    return (torch.where(ic, zc, torch.zeros(())).sum() + torch.where(ir, zr, torch.zeros(())).sum()).reshape(1)
+    return ((ic.float() + ir.float()) * S).sum().reshape(1)      # completed by hinge_loss_terms
 
 
-def sum_partials(part, alpha=1.0):
-    return part.sum() * alpha
+def hinge_loss_terms(out, partials=None, diag=None, cnt=None, margin=0.0, alpha=1.0, accumulate=True):
+    t = torch.zeros((), dtype=torch.float64)
+    if partials is not None:
+        t = t + partials.double().sum()
+    if diag is not None:
+        t = t + ((margin - diag).double() * cnt.double()).sum()
+    r = (t * alpha).float()
+    if accumulate:
+        out += r
+    else:
+        out.copy_(r)
+    return out
 
 
 def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False):

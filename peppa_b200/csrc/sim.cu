@@ -194,8 +194,7 @@ struct HingePolicyT {
     int rcnt, dcol, rk;
     __device__ void kernel_begin(const Params&) { loss = 0.f; }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
-        // out-of-range column: a NaN scale makes every comparison false (no loss, no counts)
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : __int_as_float(0x7fc00000);
+        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
         v[1] = valid ? -(p.margin - p.diag_col[col]) : 0.f;
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
@@ -208,18 +207,21 @@ struct HingePolicyT {
             const int64_t rel = (p.row_offset + t.row) - p.col_offset - t.col0;
             dcol = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
-            ri = __int_as_float(0x7fc00000);  // out-of-range row: NaN scores never count
+            ri = 0.f;
             thr_r = 0.f;
             dcol = -1;
         }
     }
-    template <bool kDiag>
+    // kSlow: chunks that contain the diagonal, out-of-range columns or out-of-range rows; those
+    // elements get a hugely negative (finite) score so that no indicator fires and 0 * s stays 0.
+    template <bool kSlow>
     __device__ __forceinline__ void chunk_impl(const Params& p, const TileCtx& t, int cbase, const uint32_t (&v)[32],
                                                const float* cv) {
         const float4* cv4 = reinterpret_cast<const float4*>(cv);
         const float4* ct4 = reinterpret_cast<const float4*>(cv + kColVecStride);
         const float2 ri2 = make_float2(ri, ri);
-        const int drel = dcol - cbase;  // diagonal position inside this chunk (kDiag only)
+        const int drel = dcol - cbase;                          // diagonal position inside this chunk
+        const int nvalid = t.row_valid ? t.cols_valid - cbase : 0;  // valid columns of this row's chunk
         uint32_t packed[16], pk[8];
         float l = 0.f;
         int rc = 0, rkk = 0;
@@ -237,7 +239,7 @@ struct HingePolicyT {
             uint32_t pkq = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (kDiag && (4 * q + e) == drel) sv[e] = -3.0e38f;  // the diagonal never counts
+                if (kSlow && ((4 * q + e) == drel || (4 * q + e) >= nvalid)) sv[e] = -3.0e38f;
                 const bool ic = sv[e] >= tc[e];
                 const bool ir = sv[e] >= thr_r;
                 g[e] = (ic ? 1.f : 0.f) + (ir ? 1.f : 0.f);
@@ -263,7 +265,7 @@ struct HingePolicyT {
             if ((lane >> 2) == q) mine = tot;
         }
         const int ccnt = (int)((mine >> ((lane & 3) * 8)) & 0xffu);
-        if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);
+        if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // ccnt == 0 for out-of-range columns
         if (p.gmat && t.row_valid) {
             uint4* dst = reinterpret_cast<uint4*>(p.gmat + t.row * p.ld_g + t.col0 + cbase);
 #pragma unroll
@@ -275,7 +277,8 @@ struct HingePolicyT {
                           const float* cv) {
         if (cbase >= t.cols_valid) return;  // warp-uniform
         const int drel = dcol - cbase;
-        if (__any_sync(0xffffffffu, drel >= 0 && drel < 32)) chunk_impl<true>(p, t, cbase, v, cv);
+        const bool slow = (drel >= 0 && drel < 32) || !t.row_valid || (t.cols_valid - cbase) < 32;
+        if (__any_sync(0xffffffffu, slow)) chunk_impl<true>(p, t, cbase, v, cv);
         else chunk_impl<false>(p, t, cbase, v, cv);
     }
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {

@@ -6,8 +6,9 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) from the
 //               shared-memory descriptors into one of two TMEM accumulator stages.
 //   warp 2      TMEM allocator.
-//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time (thread == row), apply the row/column
-//               scales and the mode's reduction; the MMA of tile t+1 overlaps the epilogue of t.
+//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time (thread == row; the load of chunk c+1 is in
+//               flight while chunk c is processed), row/column scales, the mode's reduction; the
+//               MMA of tile t+1 overlaps the epilogue of tile t (two TMEM accumulator stages).
 //
 // Persistent: gridDim = #SMs, tiles walked in bands of 8 row blocks so that concurrently
 // running CTAs share X and Y tiles through L2.
@@ -16,8 +17,10 @@
 //   Store   pig/util.py:9-13   cosine_matrix (the only mode that writes S)
 //   Rank    pig/metrics.py:7-40  count of candidates closer than the positive
 //   Hinge   pig/loss.py:41-48  symmetric margin loss + indicator counts + fp16 gradient matrix
+//           (optionally also the rank counts of the diagonal: loss and recall@k from one pass)
 //   LseRow  pig/loss.py:19-25  online row log-sum-exp partials
 //   LseGrad MIL-NCE gradient matrix from the merged row/column statistics
+// Gradient-matrix tiles leave the SM through per-warp swizzled staging buffers and TMA stores.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
@@ -33,6 +36,11 @@ constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGroupM = 8;
 constexpr int kMaxColVecs = 3;
+constexpr int kColVecStride = 256;          // floats between column vectors in smem (= max BN)
+constexpr int kOutSlabBytes = 32 * 64 * 2;  // one warp's [32 rows x 64 fp16] staging slab (4 KiB)
+#define PB2_NAN __int_as_float(0x7fc00000)
+#define PB2_INF __int_as_float(0x7f800000)
+constexpr float kMasked = -3.0e38f;  // score of an excluded element: no indicator fires, 0 * s stays 0
 
 struct SimCommon {
     int64_t rows, cols;
@@ -61,11 +69,75 @@ struct TileCtx {
     int cols_valid;  // number of valid columns in this tile (<= BN)
     int cb;          // column-block index
     int half;        // which column half this warp covers
+    int quad;        // TMEM lane quadrant of this warp (rows quad*32 .. +31 of the tile)
 };
 
+// Per-warp output staging for gradient-matrix tiles: two 4 KiB slabs, 128-byte swizzled, each
+// written by the warp's 32 threads (one 128-byte row per thread) and drained by a TMA store.
+struct OutStage {
+    uint8_t* buf;             // this warp's 2 * kOutSlabBytes
+    const CUtensorMap* tmap;  // gradient matrix [rows, cols] fp16, box [32 x 64]
+    uint32_t slab;            // running slab counter of this warp
+    // 16 fp16 (two uint4) of this thread's row, chunk parity cp (0: columns 0-31, 1: columns 32-63)
+    __device__ __forceinline__ void write(int lane, int cp, const uint32_t (&packed)[16]) {
+        uint8_t* row = buf + (slab & 1u) * kOutSlabBytes + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c16 = (cp * 4 + k) ^ (lane & 7);  // 128B swizzle: 16-byte chunk index ^ (row % 8)
+            *reinterpret_cast<uint4*>(row + c16 * 16) =
+                make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+        }
+    }
+    __device__ __forceinline__ void begin_slab(int lane) {  // the slab buffer used two slabs ago must be drained
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+    }
+    __device__ __forceinline__ void end_slab(int lane, int32_t col, int32_t row) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmap, buf + (slab & 1u) * kOutSlabBytes, col, row);
+            tma_store_commit();
+        }
+        ++slab;
+    }
+    __device__ __forceinline__ void finish(int lane) {
+        if (lane == 0) tma_store_wait_all<0>();
+        __syncwarp();
+    }
+};
+
+// smallest float t such that, for every float s:  s >= t  <=>  fl32(1 - s) < pd
+// (the "strictly closer than the positive" test of pig/metrics.py:8-12 as a threshold on s;
+// exact, including the round-half-even tie -- brute-force checked in tests/test_rank_threshold.py)
+__device__ __forceinline__ float rank_threshold(float pd) {
+    if (!(pd == pd) || pd == -PB2_INF) return PB2_INF;
+    const float q = nextafterf(pd, -PB2_INF);
+    const double mid = 0.5 * ((double)q + (double)pd);
+    const double T = 1.0 - mid;
+    float tf = __double2float_ru(T);
+    if ((double)tf == T && (__float_as_uint(q) & 1u)) tf = nextafterf(tf, PB2_INF);
+    return tf;
+}
+
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// s = fl32(fl32(v * ri) * cj) for two adjacent columns (packed FMUL2; same two roundings everywhere)
+__device__ __forceinline__ float2 score2(uint32_t v0, uint32_t v1, float2 ri2, float c0, float c1) {
+    return __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v0), __uint_as_float(v1)), ri2), make_float2(c0, c1));
+}
+
 // ------------------------------------------------------------------------------- epilogues
-// Each policy: Params (POD, kernel argument), kColVecs (per-column fp32 vectors staged in smem;
-// vector 0 is always rinv_y or 1), per-thread state as members.
+// Each policy: Params (POD, kernel argument), kColVecs (per-column fp32 vectors staged in smem),
+// kStoresG (needs the OutStage), per-thread state as members.
 
 struct StorePolicy {
     struct Params {
@@ -73,6 +145,7 @@ struct StorePolicy {
         int64_t ld;
     };
     static constexpr int kColVecs = 1;
+    static constexpr bool kStoresG = false;
     float ri;
     __device__ void kernel_begin(const Params&) {}
     __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
@@ -81,8 +154,8 @@ struct StorePolicy {
     __device__ void tile_begin(const Params&, const SimCommon& c, const TileCtx& t) {
         ri = (t.row_valid ? (c.rinv_x ? c.rinv_x[t.row] : 1.f) : 0.f) * c.scale;
     }
-    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
-                          const float* cv) {
+    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage&) {
         if (!t.row_valid) return;
         float* dst = p.out + t.row * p.ld + t.col0 + cbase;
         const int nvalid = t.cols_valid - cbase;
@@ -114,38 +187,45 @@ struct RankPolicy {
         int32_t* rank;
     };
     static constexpr int kColVecs = 1;
-    float ri, pd;
+    static constexpr bool kStoresG = false;
+    float ri, thr;
     int pc;  // positive's column relative to the tile origin (may be out of range)
     int cnt;
     __device__ void kernel_begin(const Params&) {}
     __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
         // an out-of-range column must never count: NaN makes every comparison false
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : __int_as_float(0x7fc00000);
+        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : PB2_NAN;
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
         cnt = 0;
         if (t.row_valid) {
             ri = (c.rinv_x ? c.rinv_x[t.row] : 1.f) * c.scale;
-            pd = p.pos_dist[t.row];
+            thr = rank_threshold(p.pos_dist[t.row]);  // s >= thr  <=>  fl32(1 - s) < fl32(1 - s_pos)
             const int64_t rel = p.pos_col[t.row] - p.col_offset - t.col0;
             pc = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
             ri = 0.f;
-            pd = -__int_as_float(0x7f800000);  // -inf: nothing is closer
+            thr = PB2_INF;
             pc = -1;
         }
     }
-    __device__ void chunk(const Params&, const SimCommon&, const TileCtx&, int cbase, const uint32_t (&v)[32],
-                          const float* cv) {
-        // fl32(1 - s) < fl32(1 - s_pos), exactly the comparison argsort resolves in pig/metrics.py:8-12
+    __device__ void chunk(const Params&, const SimCommon&, const TileCtx&, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage&) {
+        const float4* cv4 = reinterpret_cast<const float4*>(cv);
+        const float2 ri2 = make_float2(ri, ri);
+        const int rel = pc - cbase;  // the positive itself never counts
         int c = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float s = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), ri), cv[j]);
-            c += (__fsub_rn(1.0f, s) < pd) ? 1 : 0;  // no FMA contraction: fl32(1 - fl32(s))
+        for (int q = 0; q < 8; ++q) {
+            const float4 c4 = cv4[q];
+            const float2 s01 = score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y);
+            const float2 s23 = score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w);
+            c += (s01.x >= thr) ? 1 : 0;
+            c += (s01.y >= thr) ? 1 : 0;
+            c += (s23.x >= thr) ? 1 : 0;
+            c += (s23.y >= thr) ? 1 : 0;
         }
-        const int rel = pc - cbase;
-        if (rel >= 0 && rel < 32) {  // the positive itself sits in this chunk: take its vote back
+        if (rel >= 0 && rel < 32) {  // take the positive's own vote back
             float sv = 0.f, cj = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -153,7 +233,7 @@ struct RankPolicy {
                     sv = __uint_as_float(v[j]);
                     cj = cv[j];
                 }
-            c -= (__fsub_rn(1.0f, __fmul_rn(__fmul_rn(sv, ri), cj)) < pd) ? 1 : 0;
+            c -= (__fmul_rn(__fmul_rn(sv, ri), cj) >= thr) ? 1 : 0;
         }
         cnt += c;
     }
@@ -171,124 +251,135 @@ struct HingeParams {
     float* loss_partial;
     int32_t* row_cnt;
     int32_t* col_cnt;
-    __half* gmat;
-    int64_t ld_g;
+    int has_gmat;
     const float* pos_dist;  // kRank only: fl32(1 - diag_row)
     int32_t* rank;          // kRank only
 };
-constexpr int kColVecStride = 256;  // floats between column vectors in smem (= max BN)
 
 // kRank additionally counts, per row, the columns closer than the diagonal (recall@k of the same
 // similarity pass: the gallery workload shares one S pass between pig.loss and pig.metrics).
+//
+// Instruction budget: the MMA of a 128 x 256 x 512 tile takes ~4096 cycles = ~16 issue slots per
+// element, split over an FMA pipe and an ALU pipe that each accept one warp instruction every
+// other cycle.  So per element:
+//   FMA pipe  score (2 packed FMUL2 per pair), the two hinge indicators as floats with a saturating
+//             FFMA ( sat((s - pred(thr)) * 2^120) is exactly [s >= thr] ), g = ic + ir, loss += g * s,
+//             row count += ir (packed FADD2 / FFMA2);
+//   ALU pipe  column-count compare + byte-packed add, rank compare + add, fp16 pack.
+// There is no per-element z = margin + s - d: fl32(s + c) >= 0  <=>  s >= -c exactly, and
+// sum relu(z) = sum g*s + sum_j (m - d_j) col_cnt[j] + sum_i (m - d_i) row_cnt[i] is completed from the
+// counts afterwards (pb2_hinge_loss_terms).  Column counts are summed over the warp's rows with REDUX.
+constexpr float kBig = 1.329227995784916e36f;  // 2^120
 template <bool kRank>
 struct HingePolicyT {
     using Params = HingeParams;
-    static constexpr int kColVecs = 2;  // rinv_y, diag_col - margin
-    // Instruction budget: the MMA of a 128 x 256 x 512 tile takes ~4096 cycles, i.e. ~16 issue slots per
-    // element for the epilogue.  So: no per-element adds for z = margin + s - d; the indicators are
-    // threshold compares (fl32(s + c) >= 0  <=>  s >= -c exactly), the loss is accumulated as
-    // sum (ic + ir) * s per element and completed from the counts afterwards
-    // (pb2_hinge_loss_terms: + sum_j (m - d_j) col_cnt[j] + sum_i (m - d_i) row_cnt[i]); scores use
-    // packed FMUL2; column counts are byte-packed per thread and summed across the warp with REDUX.
-    float ri, thr_r, loss, pd;
-    int rcnt, dcol, rk;
-    __device__ void kernel_begin(const Params&) { loss = 0.f; }
+    static constexpr int kColVecs = 3;  // rinv_y, thr_c = diag_col - margin, -pred(thr_c) * 2^120
+    static constexpr bool kStoresG = true;
+    float ri, rbig, thr_rank;
+    float2 loss2, rc2;
+    int dcol, rk;
+    __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
+        const float thr = valid ? (p.diag_col[col] - p.margin) : PB2_INF;
         v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
-        v[1] = valid ? -(p.margin - p.diag_col[col]) : 0.f;
+        v[1] = thr;
+        v[2] = valid ? -(nextafterf(thr, -PB2_INF) * kBig) : -PB2_INF;
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
-        rcnt = 0;
+        rc2 = make_float2(0.f, 0.f);
         rk = 0;
-        pd = (kRank && t.row_valid) ? p.pos_dist[t.row] : 0.f;
         if (t.row_valid) {
             ri = c.rinv_x ? c.rinv_x[t.row] : 1.f;
-            thr_r = -(p.margin - p.diag_row[t.row]);
+            rbig = -(nextafterf(p.diag_row[t.row] - p.margin, -PB2_INF) * kBig);
+            thr_rank = kRank ? rank_threshold(p.pos_dist[t.row]) : PB2_INF;
             const int64_t rel = (p.row_offset + t.row) - p.col_offset - t.col0;
             dcol = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
             ri = 0.f;
-            thr_r = 0.f;
+            rbig = -PB2_INF;
+            thr_rank = PB2_INF;
             dcol = -1;
         }
     }
-    // kSlow: chunks that contain the diagonal, out-of-range columns or out-of-range rows; those
-    // elements get a hugely negative (finite) score so that no indicator fires and 0 * s stays 0.
+    // kSlow: chunks containing the diagonal, out-of-range columns or out-of-range rows; those elements
+    // get the masked score.
     template <bool kSlow>
-    __device__ __forceinline__ void chunk_impl(const Params& p, const TileCtx& t, int cbase, const uint32_t (&v)[32],
-                                               const float* cv) {
+    __device__ __forceinline__ void chunk_impl(const Params& p, const TileCtx& t, int ch, int cbase,
+                                               const uint32_t (&v)[32], const float* cv, OutStage& os) {
         const float4* cv4 = reinterpret_cast<const float4*>(cv);
         const float4* ct4 = reinterpret_cast<const float4*>(cv + kColVecStride);
+        const float4* cb4 = reinterpret_cast<const float4*>(cv + 2 * kColVecStride);
         const float2 ri2 = make_float2(ri, ri);
-        const int drel = dcol - cbase;                          // diagonal position inside this chunk
+        const int drel = dcol - cbase;                              // diagonal position inside this chunk
         const int nvalid = t.row_valid ? t.cols_valid - cbase : 0;  // valid columns of this row's chunk
-        uint32_t packed[16], pk[8];
-        float l = 0.f;
-        int rc = 0, rkk = 0;
+        const int lane = lane_id();
+        uint32_t packed[16];
+        uint32_t mine = 0;
+        int rkk = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 c4 = cv4[q], t4 = ct4[q];
-            // fl32(fl32(v * ri) * cj): the same two roundings as the rank kernel and pair_dot
-            const float2 s01 = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), ri2),
-                                          make_float2(c4.x, c4.y));
-            const float2 s23 = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), ri2),
-                                          make_float2(c4.z, c4.w));
-            float sv[4] = {s01.x, s01.y, s23.x, s23.y};
-            const float tc[4] = {t4.x, t4.y, t4.z, t4.w};
-            float g[4];
-            uint32_t pkq = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (kSlow && ((4 * q + e) == drel || (4 * q + e) >= nvalid)) sv[e] = -3.0e38f;
-                const bool ic = sv[e] >= tc[e];
-                const bool ir = sv[e] >= thr_r;
-                g[e] = (ic ? 1.f : 0.f) + (ir ? 1.f : 0.f);
-                l = fmaf(g[e], sv[e], l);
-                rc += ir ? 1 : 0;
-                if (kRank) rkk += (__fsub_rn(1.0f, sv[e]) < pd) ? 1 : 0;
-                pkq += ic ? (1u << (8 * e)) : 0u;
+            const float4 c4 = cv4[q], t4 = ct4[q], b4 = cb4[q];
+            float2 s01 = score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y);
+            float2 s23 = score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w);
+            if (kSlow) {
+                if (4 * q + 0 == drel || 4 * q + 0 >= nvalid) s01.x = kMasked;
+                if (4 * q + 1 == drel || 4 * q + 1 >= nvalid) s01.y = kMasked;
+                if (4 * q + 2 == drel || 4 * q + 2 >= nvalid) s23.x = kMasked;
+                if (4 * q + 3 == drel || 4 * q + 3 >= nvalid) s23.y = kMasked;
             }
-            pk[q] = pkq;
-            const __half2 h01 = __floats2half2_rn(g[0], g[1]), h23 = __floats2half2_rn(g[2], g[3]);
+            // FMA pipe: indicators as exact 0/1 floats
+            const float2 ic01 = make_float2(fma_sat(s01.x, kBig, b4.x), fma_sat(s01.y, kBig, b4.y));
+            const float2 ic23 = make_float2(fma_sat(s23.x, kBig, b4.z), fma_sat(s23.y, kBig, b4.w));
+            const float2 ir01 = make_float2(fma_sat(s01.x, kBig, rbig), fma_sat(s01.y, kBig, rbig));
+            const float2 ir23 = make_float2(fma_sat(s23.x, kBig, rbig), fma_sat(s23.y, kBig, rbig));
+            const float2 g01 = __fadd2_rn(ic01, ir01), g23 = __fadd2_rn(ic23, ir23);
+            loss2 = __ffma2_rn(g01, s01, loss2);
+            loss2 = __ffma2_rn(g23, s23, loss2);
+            rc2 = __fadd2_rn(rc2, __fadd2_rn(ir01, ir23));
+            // ALU pipe: byte-packed column counts (same test as ic, as a compare), rank count
+            uint32_t pkq = 0;
+            pkq += (s01.x >= t4.x) ? 0x1u : 0u;
+            pkq += (s01.y >= t4.y) ? 0x100u : 0u;
+            pkq += (s23.x >= t4.z) ? 0x10000u : 0u;
+            pkq += (s23.y >= t4.w) ? 0x1000000u : 0u;
+            if (kRank) {
+                rkk += (s01.x >= thr_rank) ? 1 : 0;
+                rkk += (s01.y >= thr_rank) ? 1 : 0;
+                rkk += (s23.x >= thr_rank) ? 1 : 0;
+                rkk += (s23.y >= thr_rank) ? 1 : 0;
+            }
+            // column counts over the warp's 32 rows (<= 32 per byte): lanes 4q..4q+3 keep group q
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, pkq);
+            if ((lane >> 2) == q) mine = tot;
+            const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
             packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
             packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
         }
-        loss += l;
-        rcnt += rc;
         if (kRank) rk += rkk;
-        // column counts: byte-packed (<= 32 per byte), summed over the warp's 32 rows with REDUX
-        const int lane = lane_id();
-        uint32_t mine = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, pk[q]);
-            if ((lane >> 2) == q) mine = tot;
-        }
         const int ccnt = (int)((mine >> ((lane & 3) * 8)) & 0xffu);
         if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // ccnt == 0 for out-of-range columns
-        if (p.gmat && t.row_valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.gmat + t.row * p.ld_g + t.col0 + cbase);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        if (p.has_gmat) {
+            if ((ch & 1) == 0) os.begin_slab(lane);
+            os.write(lane, ch & 1, packed);
+            if (ch & 1) os.end_slab(lane, (int32_t)(t.col0 + cbase - 32), (int32_t)(t.row0 + t.quad * 32));
         }
     }
-    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
-                          const float* cv) {
-        if (cbase >= t.cols_valid) return;  // warp-uniform
+    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage& os) {
         const int drel = dcol - cbase;
         const bool slow = (drel >= 0 && drel < 32) || !t.row_valid || (t.cols_valid - cbase) < 32;
-        if (__any_sync(0xffffffffu, slow)) chunk_impl<true>(p, t, cbase, v, cv);
-        else chunk_impl<false>(p, t, cbase, v, cv);
+        if (__any_sync(0xffffffffu, slow)) chunk_impl<true>(p, t, ch, cbase, v, cv, os);
+        else chunk_impl<false>(p, t, ch, cbase, v, cv, os);
     }
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {
+        const int rcnt = (int)(rc2.x + rc2.y);  // exact: small integers in fp32
         if (t.row_valid && rcnt) atomicAdd(p.row_cnt + t.row, rcnt);
         if (kRank && t.row_valid && rk) atomicAdd(p.rank + t.row, rk);
     }
     __device__ void kernel_end(const Params& p, float* red) {
         // fixed-order reduction over the 256 epilogue threads -> one deterministic partial per CTA
         const int e = threadIdx.x - kEpiWarp0 * 32;
-        const float w = warp_sum(loss);
+        const float w = warp_sum(loss2.x + loss2.y);
         if ((e & 31) == 0) red[e >> 5] = w;
         named_bar_sync(2, kEpiThreads);
         if (e == 0) {
@@ -306,6 +397,7 @@ struct LseRowPolicy {
         float* part_sum;
     };
     static constexpr int kColVecs = 1;
+    static constexpr bool kStoresG = false;
     float ri, m, s;
     __device__ void kernel_begin(const Params&) {}
     __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
@@ -314,27 +406,30 @@ struct LseRowPolicy {
     __device__ void tile_begin(const Params&, const SimCommon& c, const TileCtx& t) {
         // work in the log2 domain: t = s_ij * log2(e)
         ri = (t.row_valid ? (c.rinv_x ? c.rinv_x[t.row] : 1.f) : 0.f) * c.scale * 1.4426950408889634f;
-        m = -__int_as_float(0x7f800000);
+        m = -PB2_INF;
         s = 0.f;
     }
-    __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
-                          const float* cv) {
+    __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage&) {
         const int nvalid = t.cols_valid - cbase;
         if (nvalid <= 0) return;
         float x[32];
-        float cm = -__int_as_float(0x7f800000);
+        float cm = -PB2_INF;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            x[j] = (j < nvalid) ? __uint_as_float(v[j]) * ri * cv[j] : -__int_as_float(0x7f800000);
+            x[j] = (j < nvalid) ? __uint_as_float(v[j]) * ri * cv[j] : -PB2_INF;
             cm = fmaxf(cm, x[j]);
         }
         const float mn = fmaxf(m, cm);
         // mn == -inf only if every logit so far is -inf; keep the state untouched then
-        if (mn > -__int_as_float(0x7f800000)) {
-            float acc = s * exp2f(m - mn);
+        if (mn > -PB2_INF) {
+            float a0 = s * ex2_approx(m - mn), a1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc += exp2f(x[j] - mn);
-            s = acc;
+            for (int j = 0; j < 32; j += 2) {
+                a0 += ex2_approx(x[j] - mn);
+                a1 += ex2_approx(x[j + 1] - mn);
+            }
+            s = a0 + a1;
             m = mn;
         }
     }
@@ -351,68 +446,70 @@ struct LseGradPolicy {
     struct Params {
         const float* den_row;
         const float* den_col;
-        __half* gmat;
-        int64_t ld_g;
     };
     static constexpr int kColVecs = 2;  // rinv_y, 13 - den_col * log2e
+    static constexpr bool kStoresG = true;
     float ri, drow;
     __device__ void kernel_begin(const Params&) {}
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
         v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
-        v[1] = valid ? (13.0f - p.den_col[col] * 1.4426950408889634f) : -__int_as_float(0x7f800000);
+        v[1] = valid ? (13.0f - p.den_col[col] * 1.4426950408889634f) : -PB2_INF;
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
         ri = (t.row_valid ? (c.rinv_x ? c.rinv_x[t.row] : 1.f) : 0.f) * c.scale * 1.4426950408889634f;
-        drow = t.row_valid ? (13.0f - p.den_row[t.row] * 1.4426950408889634f) : -__int_as_float(0x7f800000);
+        drow = t.row_valid ? (13.0f - p.den_row[t.row] * 1.4426950408889634f) : -PB2_INF;
     }
-    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int cbase, const uint32_t (&v)[32],
-                          const float* cv) {
-        if (cbase >= t.cols_valid || !t.row_valid) return;
+    __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage& os) {
         const float* cd = cv + kColVecStride;
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]) * ri * cv[j];
-            const float g = exp2f(x + drow) + exp2f(x + cd[j]);
-            const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(g));
-            if (j & 1) packed[j >> 1] |= h << 16;
-            else packed[j >> 1] = h;
+        for (int j = 0; j < 32; j += 2) {
+            const float x0 = __uint_as_float(v[j]) * ri * cv[j], x1 = __uint_as_float(v[j + 1]) * ri * cv[j + 1];
+            const float g0 = ex2_approx(x0 + drow) + ex2_approx(x0 + cd[j]);
+            const float g1 = ex2_approx(x1 + drow) + ex2_approx(x1 + cd[j + 1]);
+            const __half2 h = __floats2half2_rn(g0, g1);
+            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.gmat + t.row * p.ld_g + t.col0 + cbase);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        const int lane = lane_id();
+        if ((ch & 1) == 0) os.begin_slab(lane);
+        os.write(lane, ch & 1, packed);
+        if (ch & 1) os.end_slab(lane, (int32_t)(t.col0 + cbase - 32), (int32_t)(t.row0 + t.quad * 32));
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
     __device__ void kernel_end(const Params&, float*) {}
 };
 
 // ---------------------------------------------------------------------------------- kernel
-template <int BN>
+template <int BN, bool kOut>
 struct SimSmem {
     static constexpr int kStageBytes = (BM + BN) * BK * 2;
-    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int kTileBytes = kStages * kStageBytes;
-    static constexpr int kColVecBytes = 2 * kMaxColVecs * 256 * 4;  // [acc stage][vec][256]
+    static constexpr int kOutBytes = kOut ? kEpiWarps * 2 * kOutSlabBytes : 0;
+    static constexpr int kColVecBytes = 2 * kMaxColVecs * kColVecStride * 4;  // [acc stage][vec][256]
     static constexpr int kBarBytes = 256;
-    static constexpr int kTotal = 1024 /*align slack*/ + kTileBytes + kColVecBytes + kBarBytes;
+    static constexpr int kBudget = 227 * 1024 - kOutBytes - kColVecBytes - kBarBytes;
+    static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+    static constexpr int kTileBytes = kStages * kStageBytes;
+    static constexpr int kTotal = kTileBytes + kOutBytes + kColVecBytes + kBarBytes;
+    static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
 
 template <class Policy, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-    sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimCommon c,
-               const typename Policy::Params p) {
-    using L = SimSmem<BN>;
+    sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
+               const __grid_constant__ CUtensorMap tm_out, const SimCommon c, const typename Policy::Params p) {
+    using L = SimSmem<BN, Policy::kStoresG>;
     // 128-byte-swizzled TMA/UMMA tiles need 1024-byte alignment; the kernel has no static shared
     // memory, so the dynamic segment starts at the (aligned) base of the CTA's shared window.
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
-    float* colvec = reinterpret_cast<float*>(smem + L::kTileBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kColVecBytes);
-    uint64_t* full = bars;                    // [kStages]
-    uint64_t* empty = bars + L::kStages;      // [kStages]
-    uint64_t* acc_full = bars + 2 * L::kStages;   // [2]
-    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint8_t* out_stage = smem + L::kTileBytes;
+    float* colvec = reinterpret_cast<float*>(smem + L::kTileBytes + L::kOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kOutBytes + L::kColVecBytes);
+    uint64_t* full = bars;                       // [kStages]
+    uint64_t* empty = bars + L::kStages;         // [kStages]
+    uint64_t* acc_full = bars + 2 * L::kStages;  // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [kEpiWarps]
 
@@ -422,6 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_y);
+        if (Policy::kStoresG) tma_prefetch_desc(&tm_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < L::kStages; ++s) {
@@ -499,9 +597,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int e = threadIdx.x - kEpiWarp0 * 32;  // 0..255
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
         const int half = (warp - kEpiWarp0) >> 2;    // column half
-        constexpr int kChunksPerHalf = BN / 64;      // 32-column chunks per half (BN=64 -> 1)
+        constexpr int kChunks = BN / 64;             // 32-column chunks per half (BN=64 -> 1)
+        static_assert(!Policy::kStoresG || kChunks % 2 == 0, "gradient-matrix slabs are 64 columns wide");
         Policy pol;
         pol.kernel_begin(p);
+        OutStage os;
+        os.buf = out_stage + (warp - kEpiWarp0) * 2 * kOutSlabBytes;
+        os.tmap = &tm_out;
+        os.slab = 0;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
             const int as = (int)(it & 1);
@@ -515,32 +618,46 @@ __global__ void __launch_bounds__(kThreads, 1)
             ctx.cols_valid = (int)min((int64_t)BN, c.cols - ctx.col0);
             ctx.cb = cb;
             ctx.half = half;
-            float* cv = colvec + as * (kMaxColVecs * 256);
+            ctx.quad = quad;
+            float* cv = colvec + as * (kMaxColVecs * kColVecStride);
             for (int col = e; col < BN; col += kEpiThreads) {
                 float tmp[kMaxColVecs];
                 Policy::load_col(p, c, ctx.col0 + col, col < ctx.cols_valid, tmp);
 #pragma unroll
-                for (int k = 0; k < Policy::kColVecs; ++k) cv[k * 256 + col] = tmp[k];
+                for (int k = 0; k < Policy::kColVecs; ++k) cv[k * kColVecStride + col] = tmp[k];
             }
             pol.tile_begin(p, c, ctx);
             named_bar_sync(1, kEpiThreads);  // column vectors visible; previous user of this buffer done
             mbar_wait(acc_full + as, (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-            for (int ch = 0; ch < kChunksPerHalf; ++ch) {
-                const int cbase = (half * kChunksPerHalf + ch) * 32;
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld32(t_lane + cbase, v);
+            const int c0 = half * kChunks * 32;  // first column of this warp's half
+            // two register buffers: the TMEM load of chunk ch+1 is in flight while chunk ch is processed
+            uint32_t va[32], vb[32];
+            __syncwarp();
+            tmem_ld32(t_lane + c0, va);
+            if (kChunks == 1) {
                 tmem_ld_wait();
-                pol.chunk(p, c, ctx, cbase, v, cv + cbase);
+                pol.chunk(p, c, ctx, 0, c0, va, cv + c0, os);
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < kChunks; ch += 2) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(t_lane + c0 + (ch + 1) * 32, vb);
+                    pol.chunk(p, c, ctx, ch, c0 + ch * 32, va, cv + c0 + ch * 32, os);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (ch + 2 < kChunks) tmem_ld32(t_lane + c0 + (ch + 2) * 32, va);
+                    pol.chunk(p, c, ctx, ch + 1, c0 + (ch + 1) * 32, vb, cv + c0 + (ch + 1) * 32, os);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);
             pol.tile_end(p, c, ctx);
         }
+        if (Policy::kStoresG) os.finish(lane);
         pol.kernel_end(p, red);
     }
     tc_fence_before();
@@ -552,25 +669,35 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------ host
-static int pick_bn(int64_t rows, int64_t cols) {
+static int pick_bn(int64_t rows, int64_t cols, bool stores_g) {
     // widest tile that still yields at least ~one tile per SM; small problems are latency bound
     const int64_t sms = sm_count();
     const int64_t rb = (rows + BM - 1) / BM;
-    for (int bn : {256, 128}) {
-        if (rb * ((cols + bn - 1) / bn) >= sms) return bn;
-    }
+    if (rb * ((cols + 255) / 256) >= sms) return 256;
+    if (stores_g || rb * ((cols + 127) / 128) >= sms) return 128;
     return 64;
 }
+
+struct OutMatrix {  // optional fp16 gradient matrix drained by TMA stores
+    void* ptr = nullptr;
+    int64_t ld = 0;
+};
 
 template <class Policy, int BN>
 static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                       const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
-                      cudaStream_t st, const char* what) {
-    CUtensorMap tx, ty;
+                      const OutMatrix& om, cudaStream_t st, const char* what) {
+    CUtensorMap tx, ty, to;
     int rc = make_tmap_2d(&tx, x, 2, (uint64_t)rows, (uint64_t)dim, (uint64_t)ldx * 2, BM, BK);
     if (rc) return rc;
     rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN, BK);
     if (rc) return rc;
+    if (Policy::kStoresG && om.ptr) {
+        rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
+        if (rc) return rc;
+    } else {
+        to = tx;  // never dereferenced
+    }
     SimCommon c;
     c.rows = rows;
     c.cols = cols;
@@ -582,7 +709,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_y = rinv_y;
     c.scale = scale;
     auto kern = sim_kernel<Policy, BN>;
-    constexpr int smem = SimSmem<BN>::kTotal;
+    constexpr int smem = SimSmem<BN, Policy::kStoresG>::kTotal;
     static bool configured = false;  // per instantiation
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
@@ -590,31 +717,31 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
         configured = true;
     }
     const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid());
-    kern<<<grid, kThreads, smem, st>>>(tx, ty, c, pp);
+    kern<<<grid, kThreads, smem, st>>>(tx, ty, to, c, pp);
     return check_launch(what);
 }
+
+static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
 
 template <class Policy>
 static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                         const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
-                        void* stream, const char* what, int force_bn = 0) {
+                        void* stream, const char* what, int force_bn = 0, const OutMatrix& om = OutMatrix()) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (dim <= 0 || dim % BK != 0) return set_error(PB2_ERR_ARG, "%s: dim must be a positive multiple of 64", what);
     if (!x || !y) return set_error(PB2_ERR_ARG, "%s: null operand", what);
     if (rows > 0x7fffffffll * BM / 2 || cols > 0x7fffffffll) return set_error(PB2_ERR_ARG, "%s: too large", what);
     cudaStream_t st = (cudaStream_t)stream;
-    const int bn = force_bn ? force_bn : pick_bn(rows, cols);
-    switch (bn) {
-        case 256:
-            return launch_sim<Policy, 256>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, st, what);
-        case 128:
-            return launch_sim<Policy, 128>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, st, what);
-        default:
-            return launch_sim<Policy, 64>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, st, what);
-    }
+    int bn = force_bn ? force_bn : pick_bn(rows, cols, Policy::kStoresG);
+    if (Policy::kStoresG && bn == 64) bn = 128;
+    if (bn == 256)
+        return launch_sim<Policy, 256>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
+    if (bn == 128)
+        return launch_sim<Policy, 128>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
+    if constexpr (!Policy::kStoresG)
+        return launch_sim<Policy, 64>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
+    return set_error(PB2_ERR_ARG, "%s: unsupported tile width", what);
 }
-
-static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
 
 }  // namespace pb2
 
@@ -644,6 +771,12 @@ extern "C" int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, c
                                     g_force_bn);
 }
 
+static int check_gmat(const void* gmat, int64_t ld_g, int64_t cols, const char* what) {
+    if (gmat && (ld_g % 8 != 0 || ld_g < cols || (reinterpret_cast<uintptr_t>(gmat) & 15)))
+        return set_error(PB2_ERR_ARG, "%s: gmat needs 16-byte alignment, ld_g %% 8 == 0 and ld_g >= cols", what);
+    return PB2_OK;
+}
+
 extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
                              const float* diag_row, const float* diag_col, int64_t rows, int64_t cols,
                              int64_t row_offset, int64_t col_offset, int dim, int64_t ldx, int64_t ldy, float margin,
@@ -653,20 +786,23 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
     if (!diag_row || !diag_col || !loss_partial || !row_cnt || !col_cnt)
         return set_error(PB2_ERR_ARG, "sim_hinge: null");
     if (n_partials < pb2_sim_grid()) return set_error(PB2_ERR_ARG, "sim_hinge: loss_partial too small");
-    if (gmat && (ld_g % 8 != 0 || ld_g < ((cols + 31) / 32) * 32 || (reinterpret_cast<uintptr_t>(gmat) & 15)))
-        return set_error(PB2_ERR_ARG, "sim_hinge: gmat needs 16-byte alignment and ld_g >= round_up(cols, 32)");
-    int rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
-                        "sim_hinge memset");
+    int rc = check_gmat(gmat, ld_g, cols, "sim_hinge");
     if (rc) return rc;
     if ((pos_dist == nullptr) != (rank == nullptr))
         return set_error(PB2_ERR_ARG, "sim_hinge: pos_dist and rank go together");
-    HingeParams pp{diag_row, diag_col, row_offset, col_offset,      margin, loss_partial,
-                   row_cnt,  col_cnt,  (__half*)gmat, ld_g, pos_dist, rank};
+    rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
+                    "sim_hinge memset");
+    if (rc) return rc;
+    HingeParams pp{diag_row, diag_col, row_offset, col_offset, margin,   loss_partial,
+                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_dist, rank};
+    OutMatrix om;
+    om.ptr = gmat;
+    om.ld = ld_g;
     if (rank)
         return dispatch_sim<HingePolicyT<true>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
-                                                "sim_hinge+rank", g_force_bn);
+                                                "sim_hinge+rank", g_force_bn, om);
     return dispatch_sim<HingePolicyT<false>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
-                                             "sim_hinge", g_force_bn);
+                                             "sim_hinge", g_force_bn, om);
 }
 
 // LSE partial layout is fixed to the 128-column tile so the caller can size buffers up front.
@@ -686,9 +822,12 @@ extern "C" int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_
                                 int64_t ldx, int64_t ldy, float scale, void* gmat, int64_t ld_g, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!den_row || !den_col || !gmat) return set_error(PB2_ERR_ARG, "sim_lse_grad: null");
-    if (ld_g % 8 != 0 || ld_g < ((cols + 31) / 32) * 32 || (reinterpret_cast<uintptr_t>(gmat) & 15))
-        return set_error(PB2_ERR_ARG, "sim_lse_grad: gmat needs 16-byte alignment and ld_g >= round_up(cols, 32)");
-    LseGradPolicy::Params pp{den_row, den_col, (__half*)gmat, ld_g};
+    int rc = check_gmat(gmat, ld_g, cols, "sim_lse_grad");
+    if (rc) return rc;
+    LseGradPolicy::Params pp{den_row, den_col};
+    OutMatrix om;
+    om.ptr = gmat;
+    om.ld = ld_g;
     return dispatch_sim<LseGradPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
-                                       "sim_lse_grad", g_force_bn);
+                                       "sim_lse_grad", g_force_bn, om);
 }

@@ -256,3 +256,21 @@ def test_gallery_step_single_gpu(pb, n, block):
         assert abs(out["recall"][k].item() - (out["ranks"] < k).float().mean().item()) < 1e-6
     again = step.run(A.cuda().bfloat16(), V.cuda().bfloat16())                 # deterministic, reusable buffers
     assert torch.equal(again["dA"], out["dA"]) and again["loss"].item() == out["loss"].item()
+
+
+def test_rank_ties_are_strict(pb):
+    """Duplicate gallery rows give candidates whose score equals the positive's exactly: they must not
+    count (dist < dist_pos is strict, pig/metrics.py:8-12), in both the rank kernel and the fused
+    hinge+rank kernel."""
+    from peppa_b200.gallery import GalleryStep
+    n = 768
+    V, A = emb(n, 4.0)
+    V[1::2] = V[0::2]                      # every odd video row duplicates the even one before it
+    d = 1 - O.cosine_matrix(A, V)
+    pos = d[torch.arange(n), torch.arange(n)].unsqueeze(1)
+    ranks = (d < pos).sum(1)
+    near = (((d - pos).abs() <= 1e-6).sum(1) > 2)      # the positive and its duplicate are expected
+    got = pb.metrics._pair_ranks(V.cuda(), A.cuda(), None)[0].cpu().long()
+    assert bool(((got == ranks) | near).all())
+    fused = GalleryStep(n, 512).run(A.cuda().bfloat16(), V.cuda().bfloat16())["ranks"].cpu().long()
+    assert torch.equal(fused, got)          # same thresholds, same two roundings: bit-identical counts

@@ -51,10 +51,19 @@ int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, float* rinv, fl
 
 /* out[k] = <x[ix[k]], y[iy[k]]> * sx * sy with sx = rinv_x[ix[k]] (1 if rinv_x == NULL), same
  * for sy; ix / iy NULL = k.  The diagonal M_ii of pig/loss.py:43 and the positive's score of
- * pig/metrics.py:8-20.  If dist_out != NULL also writes fl32(1 - out[k]) there. */
+ * pig/metrics.py:8-20.  dist_out (optional) = fl32(1 - out[k]); thr_out (optional) = the rank
+ * threshold t_k: for every float s,  s >= t_k  <=>  fl32(1 - s) < dist_out[k]  (what pb2_sim_rank takes).
+ * CUDA-core fp32 arithmetic: use it for the hinge diagonal; for ranking prefer pb2_sim_diag. */
 int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
                  const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out, float* dist_out,
-                 void* stream);
+                 float* thr_out, void* stream);
+
+/* Paired scores s_k = <x_k, y_k> * rinv_x[k] * rinv_y[k] through the SAME tcgen05 pipeline as the full
+ * passes (only the diagonal tiles are visited), so that a gallery row duplicating the positive scores
+ * bit-identically to it -- as in the reference, where positive and candidates come out of one GEMM
+ * (pig/metrics.py:8) -- and "strictly closer" stays strict.  Outputs as pb2_pair_dot (each optional). */
+int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim,
+                 int64_t ldx, int64_t ldy, float* out, float* dist_out, float* thr_out, void* stream);
 
 /* ---- (a)/(b) similarity kernels: S = X * Y^T on the tcgen05 tensor cores (bf16 in, fp32
  * accumulate in TMEM), epilogue fused per entry point; S itself reaches HBM only in
@@ -66,10 +75,11 @@ int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x, const floa
                    int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* out, int64_t ld_out,
                    void* stream);
 
-/* pig/metrics.py:7-40 with one target per query row: rank[i] += #{ j != pos_col[i] :
- * fl32(1 - s_ij) < pos_dist[i] }.  rank (int32) must be zeroed by the caller; column indices
- * are offset by col_offset (sharded galleries).  No sort, no N x N store. */
-int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g, const float* pos_dist,
+/* pig/metrics.py:7-40 with one target per query row: rank[i] += #{ j != pos_col[i] : s_ij >= pos_thr[i] }
+ * = #{ j : fl32(1 - s_ij) < fl32(1 - s_pos) } with pos_thr from pb2_sim_diag / pb2_pair_dot.  rank (int32)
+ * must be zeroed by the caller; column indices are offset by col_offset (sharded galleries).
+ * No sort, no N x N store. */
+int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g, const float* pos_thr,
                  const int64_t* pos_col, int64_t rows, int64_t cols, int64_t col_offset, int dim, int64_t ldq,
                  int64_t ldg, int32_t* rank, void* stream);
 
@@ -83,11 +93,11 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
  *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
  * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()).
  * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
- * rank[i] += #{ j != i : fl32(1 - s_ij) < pos_dist[i] } (loss and recall@k share one S pass). */
+ * rank[i] += #{ j != i : s_ij >= pos_thr[i] } (loss and recall@k share one S pass). */
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
                   const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim,
                   int64_t ldx, int64_t ldy, float margin, float* loss_partial, int n_partials, int32_t* row_cnt,
-                  int32_t* col_cnt, void* gmat, int64_t ld_g, const float* pos_dist, int32_t* rank, void* stream);
+                  int32_t* col_cnt, void* gmat, int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream);
 
 /* pig/loss.py:13-26 MILNCELoss: row-wise online log-sum-exp of s over all columns.
  * part_max / part_sum are [n_col_tiles * 2, rows] fp32 partials in the log2 domain

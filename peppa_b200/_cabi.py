@@ -29,7 +29,8 @@ SIGNATURES = {
     "pb2_sim_grid": [],
     "pb2_triplet_score": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i, _i, _p, _p],
     "pb2_row_norms": [_p, _i64, _i, _i64, _p, _p, _p],
-    "pb2_pair_dot": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p],
+    "pb2_pair_dot": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
+    "pb2_sim_diag": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
     "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i64, _i64, _p, _p],
     "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],

@@ -182,6 +182,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// smallest float t such that, for every float s:  s >= t  <=>  fl32(1 - s) < pd
+// (the "strictly closer than the positive" test of pig/metrics.py:8-12 as a threshold on s;
+// exact, including the round-half-even tie -- brute-force checked in tests/test_rank_threshold.py)
+__device__ __forceinline__ float rank_threshold(float pd) {
+    if (!(pd == pd) || pd == -__int_as_float(0x7f800000)) return __int_as_float(0x7f800000);
+    const float q = nextafterf(pd, -__int_as_float(0x7f800000));
+    const double mid = 0.5 * ((double)q + (double)pd);
+    const double T = 1.0 - mid;
+    float tf = __double2float_ru(T);
+    if ((double)tf == T && (__float_as_uint(q) & 1u)) tf = nextafterf(tf, __int_as_float(0x7f800000));
+    return tf;
+}
+
+
 // ---- named barriers (sub-CTA sync among epilogue warps) ------------------------------------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256)
     pair_dot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                     const int64_t* __restrict__ ix, const int64_t* __restrict__ iy, const float* __restrict__ rinv_x,
                     const float* __restrict__ rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy,
-                    float* __restrict__ out, float* __restrict__ dist_out) {
+                    float* __restrict__ out, float* __restrict__ dist_out, float* __restrict__ thr_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256)
             // same operation order as the rank epilogue (sim.cu), no FMA contraction
             const float s = __fmul_rn(__fmul_rn(acc, rinv_x ? rinv_x[rx] : 1.f), rinv_y ? rinv_y[ry] : 1.f);
             if (out) out[k] = s;
-            if (dist_out) dist_out[k] = __fsub_rn(1.0f, s);
+            const float d = __fsub_rn(1.0f, s);
+            if (dist_out) dist_out[k] = d;
+            if (thr_out) thr_out[k] = rank_threshold(d);
         }
     }
 }
@@ -350,12 +352,13 @@ extern "C" int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, i
 
 extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
                             const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out,
-                            float* dist_out, void* stream) {
+                            float* dist_out, float* thr_out, void* stream) {
     if (n <= 0) return PB2_OK;
     if (!x || !y || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2))
         return set_error(PB2_ERR_ARG, "pair_dot: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
     pair_dot_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out);
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out,
+        thr_out);
     return check_launch("pair_dot");
 }
 

@@ -25,6 +25,8 @@
 #include "host_util.h"
 #include "peppa_b200.h"
 
+#include <type_traits>
+
 namespace pb2 {
 
 constexpr int BM = 128;       // tile rows  (UMMA M)
@@ -50,9 +52,14 @@ struct SimCommon {
     const float* rinv_x;  // may be null (=1)
     const float* rinv_y;  // may be null (=1)
     float scale;
+    int diag_only;  // visit only tiles (rb, rb): paired scores (BN == BM)
 };
 
 __device__ __forceinline__ void tile_coords(int64_t t, int n_rb, int n_cb, int& rb, int& cb) {
+    if (n_cb == 0) {  // diag_only
+        rb = cb = (int)t;
+        return;
+    }
     const int64_t per_band = (int64_t)kGroupM * n_cb;
     const int band = (int)(t / per_band);
     const int first = band * kGroupM;
@@ -106,19 +113,6 @@ struct OutStage {
         __syncwarp();
     }
 };
-
-// smallest float t such that, for every float s:  s >= t  <=>  fl32(1 - s) < pd
-// (the "strictly closer than the positive" test of pig/metrics.py:8-12 as a threshold on s;
-// exact, including the round-half-even tie -- brute-force checked in tests/test_rank_threshold.py)
-__device__ __forceinline__ float rank_threshold(float pd) {
-    if (!(pd == pd) || pd == -PB2_INF) return PB2_INF;
-    const float q = nextafterf(pd, -PB2_INF);
-    const double mid = 0.5 * ((double)q + (double)pd);
-    const double T = 1.0 - mid;
-    float tf = __double2float_ru(T);
-    if ((double)tf == T && (__float_as_uint(q) & 1u)) tf = nextafterf(tf, PB2_INF);
-    return tf;
-}
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     float d;
@@ -181,7 +175,7 @@ struct StorePolicy {
 
 struct RankPolicy {
     struct Params {
-        const float* pos_dist;
+        const float* pos_thr;  // rank_threshold(fl32(1 - s_pos)) per row (pb2_sim_diag / pb2_pair_dot)
         const int64_t* pos_col;
         int64_t col_offset;
         int32_t* rank;
@@ -200,7 +194,7 @@ struct RankPolicy {
         cnt = 0;
         if (t.row_valid) {
             ri = (c.rinv_x ? c.rinv_x[t.row] : 1.f) * c.scale;
-            thr = rank_threshold(p.pos_dist[t.row]);  // s >= thr  <=>  fl32(1 - s) < fl32(1 - s_pos)
+            thr = p.pos_thr[t.row];  // s >= thr  <=>  fl32(1 - s) < fl32(1 - s_pos)
             const int64_t rel = p.pos_col[t.row] - p.col_offset - t.col0;
             pc = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
@@ -243,6 +237,44 @@ struct RankPolicy {
     __device__ void kernel_end(const Params&, float*) {}
 };
 
+// Paired scores s_k = <x_k, y_k> computed BY THE SAME tensor-core arithmetic as the full passes (only
+// the diagonal tiles are visited): a gallery row that duplicates the positive then scores exactly
+// like it, as in the reference where both come out of one GEMM, and "strictly closer" stays strict.
+struct DiagPolicy {
+    struct Params {
+        float* out;   // s_k            (may be null)
+        float* dist;  // fl32(1 - s_k)  (may be null)
+        float* thr;   // rank_threshold(fl32(1 - s_k)) (may be null)
+    };
+    static constexpr int kColVecs = 1;
+    static constexpr bool kStoresG = false;
+    float ri;
+    __device__ void kernel_begin(const Params&) {}
+    __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
+        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
+    }
+    __device__ void tile_begin(const Params&, const SimCommon& c, const TileCtx& t) {
+        ri = (t.row_valid ? (c.rinv_x ? c.rinv_x[t.row] : 1.f) : 0.f) * c.scale;
+    }
+    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage&) {
+        // tile (rb, rb) with BN == BM: row quad*32 + lane pairs with column quad*32 + lane
+        if (cbase != t.quad * 32 || !t.row_valid) return;
+        const int lane = lane_id();
+        float sv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j == lane) sv = __uint_as_float(v[j]);
+        const float s = __fmul_rn(__fmul_rn(sv, ri), cv[lane]);
+        const float d = __fsub_rn(1.0f, s);
+        if (p.out) p.out[t.row] = s;
+        if (p.dist) p.dist[t.row] = d;
+        if (p.thr) p.thr[t.row] = rank_threshold(d);
+    }
+    __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
+    __device__ void kernel_end(const Params&, float*) {}
+};
+
 struct HingeParams {
     const float* diag_row;
     const float* diag_col;
@@ -252,7 +284,7 @@ struct HingeParams {
     int32_t* row_cnt;
     int32_t* col_cnt;
     int has_gmat;
-    const float* pos_dist;  // kRank only: fl32(1 - diag_row)
+    const float* pos_thr;   // kRank only: rank threshold of the diagonal score
     int32_t* rank;          // kRank only
 };
 
@@ -291,7 +323,7 @@ struct HingePolicyT {
         if (t.row_valid) {
             ri = c.rinv_x ? c.rinv_x[t.row] : 1.f;
             rbig = -(nextafterf(p.diag_row[t.row] - p.margin, -PB2_INF) * kBig);
-            thr_rank = kRank ? rank_threshold(p.pos_dist[t.row]) : PB2_INF;
+            thr_rank = kRank ? p.pos_thr[t.row] : PB2_INF;
             const int64_t rel = (p.row_offset + t.row) - p.col_offset - t.col0;
             dcol = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
@@ -705,6 +737,12 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.n_rb = (int)((rows + BM - 1) / BM);
     c.n_cb = (int)((cols + BN - 1) / BN);
     c.n_tiles = (int64_t)c.n_rb * c.n_cb;
+    c.diag_only = 0;
+    if (std::is_same<Policy, DiagPolicy>::value) {  // paired rows: only the diagonal tiles
+        c.diag_only = 1;
+        c.n_cb = 0;
+        c.n_tiles = c.n_rb;
+    }
     c.rinv_x = rinv_x;
     c.rinv_y = rinv_y;
     c.scale = scale;
@@ -762,11 +800,17 @@ extern "C" int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x,
                                      "sim_matrix", g_force_bn);
 }
 
+extern "C" int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim,
+                            int64_t ldx, int64_t ldy, float* out, float* dist_out, float* thr_out, void* stream) {
+    DiagPolicy::Params pp{out, dist_out, thr_out};
+    return dispatch_sim<DiagPolicy>(x, y, n, n, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream, "sim_diag", 128);
+}
+
 extern "C" int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g,
-                            const float* pos_dist, const int64_t* pos_col, int64_t rows, int64_t cols,
+                            const float* pos_thr, const int64_t* pos_col, int64_t rows, int64_t cols,
                             int64_t col_offset, int dim, int64_t ldq, int64_t ldg, int32_t* rank, void* stream) {
-    if (rows > 0 && cols > 0 && (!pos_dist || !pos_col || !rank)) return set_error(PB2_ERR_ARG, "sim_rank: null");
-    RankPolicy::Params pp{pos_dist, pos_col, col_offset, rank};
+    if (rows > 0 && cols > 0 && (!pos_thr || !pos_col || !rank)) return set_error(PB2_ERR_ARG, "sim_rank: null");
+    RankPolicy::Params pp{pos_thr, pos_col, col_offset, rank};
     return dispatch_sim<RankPolicy>(q, g, rows, cols, dim, ldq, ldg, rinv_q, rinv_g, 1.0f, pp, stream, "sim_rank",
                                     g_force_bn);
 }
@@ -781,20 +825,20 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
                              const float* diag_row, const float* diag_col, int64_t rows, int64_t cols,
                              int64_t row_offset, int64_t col_offset, int dim, int64_t ldx, int64_t ldy, float margin,
                              float* loss_partial, int n_partials, int32_t* row_cnt, int32_t* col_cnt, void* gmat,
-                             int64_t ld_g, const float* pos_dist, int32_t* rank, void* stream) {
+                             int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!diag_row || !diag_col || !loss_partial || !row_cnt || !col_cnt)
         return set_error(PB2_ERR_ARG, "sim_hinge: null");
     if (n_partials < pb2_sim_grid()) return set_error(PB2_ERR_ARG, "sim_hinge: loss_partial too small");
     int rc = check_gmat(gmat, ld_g, cols, "sim_hinge");
     if (rc) return rc;
-    if ((pos_dist == nullptr) != (rank == nullptr))
-        return set_error(PB2_ERR_ARG, "sim_hinge: pos_dist and rank go together");
+    if ((pos_thr == nullptr) != (rank == nullptr))
+        return set_error(PB2_ERR_ARG, "sim_hinge: pos_thr and rank go together");
     rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
                     "sim_hinge memset");
     if (rc) return rc;
     HingeParams pp{diag_row, diag_col, row_offset, col_offset, margin,   loss_partial,
-                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_dist, rank};
+                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank};
     OutMatrix om;
     om.ptr = gmat;
     om.ld = ld_g;

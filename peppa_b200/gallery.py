@@ -83,7 +83,7 @@ class GalleryStep:
         r0g = self.rank * nl                                  # global id of the first local row
         ra, _ = ops.row_norms(a_loc)
         rv, _ = ops.row_norms(v_loc)
-        diag, pos_dist = ops.pair_dot(a_loc, v_loc, rinv_x=ra, rinv_y=rv, want_dist=True)
+        diag, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv)        # S_ii and its rank threshold
         if self.world > 1:
             self._all_gather(self.v_full, v_loc)
             self._all_gather(self.rv_full, rv)
@@ -109,7 +109,7 @@ class GalleryStep:
                 part = ops.sim_hinge(a_loc[r0:r1], v_full[c0:c1], ra[r0:r1], rv_full[c0:c1], diag[r0:r1],
                                      diag_full[c0:c1], self.margin, self.row_cnt[r0:r1], self.col_cnt[c0:c1],
                                      self.gmat if self.with_grad else None, self.ld_g if self.with_grad else 0,
-                                     row_offset=r0g + r0, col_offset=c0, pos_dist=pos_dist[r0:r1],
+                                     row_offset=r0g + r0, col_offset=c0, pos_thr=pos_thr[r0:r1],
                                      rank=self.ranks[r0:r1])
                 ops.hinge_loss_terms(loss, partials=part)
                 if self.with_grad:

@@ -52,12 +52,15 @@ def _pair_ranks(candidates, references, correct):
     rq, _ = ops.row_norms(qb)
     rg, _ = ops.row_norms(gb)
     rows, cols, counts = _targets(correct, qb.shape[0], gb.shape[0], dev)
-    _, pos_dist = ops.pair_dot(qb, gb, ix=rows, iy=cols, rinv_x=rq, rinv_y=rg, want_dist=True)
     if counts is None:
         q, rq_p = qb, rq
     else:                           # several targets per row: one query copy per (row, target) pair
         q, rq_p = qb[rows].contiguous(), rq[rows].contiguous()
-    rank = ops.sim_rank(q, gb, rq_p, rg, pos_dist, cols)
+    # the target's own score comes from the same tensor-core arithmetic as every candidate's
+    identity = counts is None and cols.numel() == gb.shape[0] and bool((cols == rows).all())
+    tgt, rt = (gb, rg) if identity else (gb[cols].contiguous(), rg[cols].contiguous())
+    _, pos_thr = ops.sim_diag(q, tgt, rq_p, rt)
+    rank = ops.sim_rank(q, gb, rq_p, rg, pos_thr, cols)
     return rank, rows, counts, qb.shape[0]
 
 

@@ -77,14 +77,30 @@ def row_norms(x_bf16: torch.Tensor):
     return rinv, norm
 
 
-def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False):
+def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False, want_thr=False):
+    """CUDA-core paired dot products; returns score [, dist = fl32(1 - score)] [, rank threshold]."""
     n = x.shape[0] if ix is None else ix.shape[0]
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
+    thr = torch.empty(n, dtype=torch.float32, device=x.device) if want_thr else None
     with torch.cuda.device(x.device):
         check(_cabi.lib().pb2_pair_dot(_ptr(x), _ptr(y), _ptr(ix), _ptr(iy), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1],
-                                       x.stride(0), y.stride(0), _ptr(out), _ptr(dist), _stream(x.device)), "pair_dot")
-    return (out, dist) if want_dist else out
+                                       x.stride(0), y.stride(0), _ptr(out), _ptr(dist), _ptr(thr), _stream(x.device)),
+              "pair_dot")
+    res = (out,) + ((dist,) if want_dist else ()) + ((thr,) if want_thr else ())
+    return res if len(res) > 1 else out
+
+
+def sim_diag(x, y, rinv_x=None, rinv_y=None):
+    """Paired scores of row k of x with row k of y on the tensor-core pipeline (bit-identical to the
+    entries the full passes compute).  Returns (score, rank threshold)."""
+    n = x.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    thr = torch.empty(n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_sim_diag(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1], x.stride(0), y.stride(0),
+                                       _ptr(out), _ptr(None), _ptr(thr), _stream(x.device)), "sim_diag")
+    return out, thr
 
 
 def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
@@ -97,12 +113,12 @@ def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
     return out
 
 
-def sim_rank(q, g, rinv_q, rinv_g, pos_dist, pos_col, col_offset=0, rank=None):
+def sim_rank(q, g, rinv_q, rinv_g, pos_thr, pos_col, col_offset=0, rank=None):
     r, c = q.shape[0], g.shape[0]
     if rank is None:
         rank = torch.zeros(r, dtype=torch.int32, device=q.device)
     with torch.cuda.device(q.device), _timed("sim_rank", 2.0 * r * c * q.shape[1], q.device):
-        check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_dist), _ptr(pos_col), r, c,
+        check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_thr), _ptr(pos_col), r, c,
                                        int(col_offset), q.shape[1], q.stride(0), g.stride(0), _ptr(rank),
                                        _stream(q.device)), "sim_rank")
     return rank
@@ -120,7 +136,7 @@ def gmat_alloc(rows, cols, device):
 
 
 def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0,
-              row_offset=0, col_offset=0, pos_dist=None, rank=None):
+              row_offset=0, col_offset=0, pos_thr=None, rank=None):
     """Returns the per-CTA loss partials (fp32 [grid])."""
     r, c = x.shape[0], y.shape[0]
     n_part = sim_grid(x.device)
@@ -129,7 +145,7 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
                                         int(row_offset), int(col_offset), x.shape[1], x.stride(0), y.stride(0),
                                         float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
-                                        int(ld_g), _ptr(pos_dist), _ptr(rank), _stream(x.device)), "sim_hinge")
+                                        int(ld_g), _ptr(pos_thr), _ptr(rank), _stream(x.device)), "sim_hinge")
     return part
 
 

@@ -17,9 +17,11 @@ def row_norms(x):
     return 1.0 / n, n
 
 
-def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False):
+def sim_diag(x, y, rinv_x=None, rinv_y=None):
+    """(paired score, rank threshold).  The emulation keeps the threshold as the distance itself and
+    sim_hinge below applies the original test fl32(1 - s) < dist."""
     s = (x.float() * y.float()).sum(dim=1) * rinv_x * rinv_y
-    return (s, 1.0 - s) if want_dist else s
+    return s, 1.0 - s
 
 
 def rows_scale_f16(x, rinv=None):
@@ -28,7 +30,7 @@ def rows_scale_f16(x, rinv=None):
 
 
 def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0, row_offset=0,
-              col_offset=0, pos_dist=None, rank=None):
+              col_offset=0, pos_thr=None, rank=None):
     S = (x.float() @ y.float().T) * rinv_x[:, None] * rinv_y[None, :]
     r, c = S.shape
     off = (torch.arange(r)[:, None] + row_offset) != (torch.arange(c)[None, :] + col_offset)
@@ -40,7 +42,7 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
     if gmat is not None:
         gmat[:r, :c] = (ic.float() + ir.float()).half()
     if rank is not None:
-        rank += (off & ((1.0 - S) < pos_dist[:, None])).sum(dim=1).to(torch.int32)
+        rank += (off & ((1.0 - S) < pos_thr[:, None])).sum(dim=1).to(torch.int32)
     return ((ic.float() + ir.float()) * S).sum().reshape(1)      # completed by hinge_loss_terms
 
 

@@ -21,7 +21,7 @@ def _emb(n, alpha, d=128, seed=666):
     return V.bfloat16(), A.bfloat16()
 
 
-def _worker(rank, world, port, n_local, block, q):
+def _worker(rank, world, port, n_local, block, outdir):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,7 +37,8 @@ def _worker(rank, world, port, n_local, block, q):
         out = step.run(A[sl].contiguous(), V[sl].contiguous())
         out2 = step.run(A[sl].contiguous(), V[sl].contiguous())           # buffers are reusable
         assert torch.equal(out["dA"], out2["dA"]) and torch.equal(out["ranks"], out2["ranks"])
-        q.put((rank, out["loss"].item(), out["recall"].clone(), out["dA"].clone(), out["dV"].clone(), out["ranks"].clone()))
+        torch.save((rank, out["loss"].item(), out["recall"].clone(), out["dA"].clone(), out["dV"].clone(),
+                    out["ranks"].clone()), os.path.join(outdir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -51,19 +52,18 @@ def _free_port():
 
 
 @pytest.mark.parametrize("n_local,block", [(96, 32768), (80, 48)])
-def test_two_rank_gallery_matches_single_process_oracle(n_local, block):
+def test_two_rank_gallery_matches_single_process_oracle(n_local, block, tmp_path):
     from oracle import pig_oracle as O
     world = 2
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_local, block, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_local, block, str(tmp_path))) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=180)
         assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
     V, A = _emb(n_local * world, 4.0)
     # rows = audio, cols = video: contrastive(cosine_matrix(A, V)); symmetric, so it is TripletLoss(V, A)
     loss, dA, dV = O.hinge_loss_and_grads(A.float(), V.float(), 0.2)

@@ -32,10 +32,11 @@ namespace pb2 {
 constexpr int BM = 128;       // tile rows  (UMMA M)
 constexpr int BK = 64;        // K elements per stage (one 128-byte swizzle row of bf16)
 constexpr int UK = 16;        // K per tcgen05.mma for 16-bit inputs
-constexpr int kEpiWarp0 = 4;  // first epilogue warp
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
-constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kEpiWarp0 = 2;  // first epilogue warp (warp 0: TMA + TMEM alloc, warp 1: MMA)
+constexpr int kMaxEpiWarps = 16;
+// Epilogue warps come in groups of 4 (one per TMEM lane quadrant); G groups split the BN columns of a
+// tile between them.  More groups = more warps per scheduler to hide the epilogue's latencies.
+__host__ __device__ constexpr int sim_threads(int groups) { return (kEpiWarp0 + 4 * groups) * 32; }
 constexpr int kGroupM = 8;
 constexpr int kMaxColVecs = 3;
 constexpr int kColVecStride = 256;          // floats between column vectors in smem (= max BN)
@@ -75,7 +76,7 @@ struct TileCtx {
     bool row_valid;
     int cols_valid;  // number of valid columns in this tile (<= BN)
     int cb;          // column-block index
-    int half;        // which column half this warp covers
+    int half;        // which column group of the tile this warp covers
     int quad;        // TMEM lane quadrant of this warp (rows quad*32 .. +31 of the tile)
 };
 
@@ -170,7 +171,7 @@ struct StorePolicy {
         }
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
-    __device__ void kernel_end(const Params&, float*) {}
+    __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 struct RankPolicy {
@@ -234,7 +235,7 @@ struct RankPolicy {
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {
         if (t.row_valid && cnt) atomicAdd(p.rank + t.row, cnt);
     }
-    __device__ void kernel_end(const Params&, float*) {}
+    __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 // Paired scores s_k = <x_k, y_k> computed BY THE SAME tensor-core arithmetic as the full passes (only
@@ -272,7 +273,7 @@ struct DiagPolicy {
         if (p.thr) p.thr[t.row] = rank_threshold(d);
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
-    __device__ void kernel_end(const Params&, float*) {}
+    __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 struct HingeParams {
@@ -286,6 +287,7 @@ struct HingeParams {
     int has_gmat;
     const float* pos_thr;   // kRank only: rank threshold of the diagonal score
     int32_t* rank;          // kRank only
+    int dbg;                // bring-up knob (pb2_debug_flags): bit0 skip REDUX/col atomics, bit1 skip tmem wait cost probe
 };
 
 // kRank additionally counts, per row, the columns closer than the diagonal (recall@k of the same
@@ -307,9 +309,9 @@ struct HingePolicyT {
     using Params = HingeParams;
     static constexpr int kColVecs = 3;  // rinv_y, thr_c = diag_col - margin, -pred(thr_c) * 2^120
     static constexpr bool kStoresG = true;
-    float ri, rbig, thr_rank;
-    float2 loss2, rc2;
-    int dcol, rk;
+    float ri, rbig, kbig;
+    float2 loss2, rc2, rk2;
+    int dcol;
     __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
         const float thr = valid ? (p.diag_col[col] - p.margin) : PB2_INF;
@@ -319,17 +321,18 @@ struct HingePolicyT {
     }
     __device__ void tile_begin(const Params& p, const SimCommon& c, const TileCtx& t) {
         rc2 = make_float2(0.f, 0.f);
-        rk = 0;
+        rk2 = make_float2(0.f, 0.f);
         if (t.row_valid) {
             ri = c.rinv_x ? c.rinv_x[t.row] : 1.f;
             rbig = -(nextafterf(p.diag_row[t.row] - p.margin, -PB2_INF) * kBig);
-            thr_rank = kRank ? p.pos_thr[t.row] : PB2_INF;
+            // [s >= pos_thr] as sat((s - pred(pos_thr)) * 2^120), like the hinge indicators
+            kbig = kRank ? -(nextafterf(p.pos_thr[t.row], -PB2_INF) * kBig) : -PB2_INF;
             const int64_t rel = (p.row_offset + t.row) - p.col_offset - t.col0;
             dcol = (rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
         } else {
             ri = 0.f;
             rbig = -PB2_INF;
-            thr_rank = PB2_INF;
+            kbig = -PB2_INF;
             dcol = -1;
         }
     }
@@ -344,10 +347,13 @@ struct HingePolicyT {
         const float2 ri2 = make_float2(ri, ri);
         const int drel = dcol - cbase;                              // diagonal position inside this chunk
         const int nvalid = t.row_valid ? t.cols_valid - cbase : 0;  // valid columns of this row's chunk
-        const int lane = lane_id();
+        const int lane = threadIdx.x & 31;
         uint32_t packed[16];
         uint32_t mine = 0;
-        int rkk = 0;
+        // independent accumulators: no serial dependency chain longer than 8 per chunk
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+        float2 rka = make_float2(0.f, 0.f), rkb = make_float2(0.f, 0.f);
+        float2 rca = make_float2(0.f, 0.f), rcb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float4 c4 = cv4[q], t4 = ct4[q], b4 = cb4[q];
@@ -365,31 +371,34 @@ struct HingePolicyT {
             const float2 ir01 = make_float2(fma_sat(s01.x, kBig, rbig), fma_sat(s01.y, kBig, rbig));
             const float2 ir23 = make_float2(fma_sat(s23.x, kBig, rbig), fma_sat(s23.y, kBig, rbig));
             const float2 g01 = __fadd2_rn(ic01, ir01), g23 = __fadd2_rn(ic23, ir23);
-            loss2 = __ffma2_rn(g01, s01, loss2);
-            loss2 = __ffma2_rn(g23, s23, loss2);
-            rc2 = __fadd2_rn(rc2, __fadd2_rn(ir01, ir23));
-            // ALU pipe: byte-packed column counts (same test as ic, as a compare), rank count
-            uint32_t pkq = 0;
-            pkq += (s01.x >= t4.x) ? 0x1u : 0u;
-            pkq += (s01.y >= t4.y) ? 0x100u : 0u;
-            pkq += (s23.x >= t4.z) ? 0x10000u : 0u;
-            pkq += (s23.y >= t4.w) ? 0x1000000u : 0u;
+            la = __ffma2_rn(g01, s01, la);
+            lb = __ffma2_rn(g23, s23, lb);
+            rca = __fadd2_rn(rca, ir01);
+            rcb = __fadd2_rn(rcb, ir23);
             if (kRank) {
-                rkk += (s01.x >= thr_rank) ? 1 : 0;
-                rkk += (s01.y >= thr_rank) ? 1 : 0;
-                rkk += (s23.x >= thr_rank) ? 1 : 0;
-                rkk += (s23.y >= thr_rank) ? 1 : 0;
+                rka = __fadd2_rn(rka, make_float2(fma_sat(s01.x, kBig, kbig), fma_sat(s01.y, kBig, kbig)));
+                rkb = __fadd2_rn(rkb, make_float2(fma_sat(s23.x, kBig, kbig), fma_sat(s23.y, kBig, kbig)));
             }
+            // ALU pipe: byte-packed column counts (same test as ic, as a compare)
+            const uint32_t p0 = (s01.x >= t4.x) ? 0x1u : 0u, p1 = (s01.y >= t4.y) ? 0x100u : 0u;
+            const uint32_t p2 = (s23.x >= t4.z) ? 0x10000u : 0u, p3 = (s23.y >= t4.w) ? 0x1000000u : 0u;
+            const uint32_t pkq = (p0 | p1) | (p2 | p3);
             // column counts over the warp's 32 rows (<= 32 per byte): lanes 4q..4q+3 keep group q
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, pkq);
-            if ((lane >> 2) == q) mine = tot;
+            if (!(p.dbg & 1)) {
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, pkq);
+                if ((lane >> 2) == q) mine = tot;
+            } else {
+                mine += pkq;
+            }
             const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
             packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
             packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
         }
-        if (kRank) rk += rkk;
+        loss2 = __fadd2_rn(loss2, __fadd2_rn(la, lb));
+        rc2 = __fadd2_rn(rc2, __fadd2_rn(rca, rcb));
+        if (kRank) rk2 = __fadd2_rn(rk2, __fadd2_rn(rka, rkb));
         const int ccnt = (int)((mine >> ((lane & 3) * 8)) & 0xffu);
-        if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // ccnt == 0 for out-of-range columns
+        if (ccnt && !(p.dbg & 2)) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // 0 for out-of-range columns
         if (p.has_gmat) {
             if ((ch & 1) == 0) os.begin_slab(lane);
             os.write(lane, ch & 1, packed);
@@ -406,18 +415,18 @@ struct HingePolicyT {
     __device__ void tile_end(const Params& p, const SimCommon&, const TileCtx& t) {
         const int rcnt = (int)(rc2.x + rc2.y);  // exact: small integers in fp32
         if (t.row_valid && rcnt) atomicAdd(p.row_cnt + t.row, rcnt);
+        const int rk = (int)(rk2.x + rk2.y);
         if (kRank && t.row_valid && rk) atomicAdd(p.rank + t.row, rk);
     }
-    __device__ void kernel_end(const Params& p, float* red) {
-        // fixed-order reduction over the 256 epilogue threads -> one deterministic partial per CTA
+    __device__ void kernel_end(const Params& p, float* red, int n_epi_warps) {
+        // fixed-order reduction over the epilogue threads -> one deterministic partial per CTA
         const int e = threadIdx.x - kEpiWarp0 * 32;
         const float w = warp_sum(loss2.x + loss2.y);
         if ((e & 31) == 0) red[e >> 5] = w;
-        named_bar_sync(2, kEpiThreads);
+        named_bar_sync(2, n_epi_warps * 32);
         if (e == 0) {
             float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < kEpiWarps; ++i) s += red[i];
+            for (int i = 0; i < n_epi_warps; ++i) s += red[i];
             p.loss_partial[blockIdx.x] = s;
         }
     }
@@ -471,7 +480,7 @@ struct LseRowPolicy {
         p.part_max[slot] = m;
         p.part_sum[slot] = s;
     }
-    __device__ void kernel_end(const Params&, float*) {}
+    __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 struct LseGradPolicy {
@@ -509,16 +518,16 @@ struct LseGradPolicy {
         if (ch & 1) os.end_slab(lane, (int32_t)(t.col0 + cbase - 32), (int32_t)(t.row0 + t.quad * 32));
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
-    __device__ void kernel_end(const Params&, float*) {}
+    __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 // ---------------------------------------------------------------------------------- kernel
-template <int BN, bool kOut>
+template <int BN, int G, bool kOut>
 struct SimSmem {
     static constexpr int kStageBytes = (BM + BN) * BK * 2;
-    static constexpr int kOutBytes = kOut ? kEpiWarps * 2 * kOutSlabBytes : 0;
+    static constexpr int kOutBytes = kOut ? 4 * G * 2 * kOutSlabBytes : 0;
     static constexpr int kColVecBytes = 2 * kMaxColVecs * kColVecStride * 4;  // [acc stage][vec][256]
-    static constexpr int kBarBytes = 256;
+    static constexpr int kBarBytes = 512;
     static constexpr int kBudget = 227 * 1024 - kOutBytes - kColVecBytes - kBarBytes;
     static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
     static constexpr int kTileBytes = kStages * kStageBytes;
@@ -526,11 +535,14 @@ struct SimSmem {
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
 
-template <class Policy, int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <class Policy, int BN, int G>
+__global__ void __launch_bounds__(sim_threads(G), 1)
     sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                const __grid_constant__ CUtensorMap tm_out, const SimCommon c, const typename Policy::Params p) {
-    using L = SimSmem<BN, Policy::kStoresG>;
+    using L = SimSmem<BN, G, Policy::kStoresG>;
+    constexpr int kEpiWarps = 4 * G;
+    constexpr int kEpiThreads = kEpiWarps * 32;
+    constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
     // 128-byte-swizzled TMA/UMMA tiles need 1024-byte alignment; the kernel has no static shared
     // memory, so the dynamic segment starts at the (aligned) base of the CTA's shared window.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -543,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint64_t* acc_full = bars + 2 * L::kStages;  // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [kEpiWarps]
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [kMaxEpiWarps]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -564,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -626,11 +638,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
     } else if (warp >= kEpiWarp0) {
         // ======================================================================== epilogue
-        const int e = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+        const int e = threadIdx.x - kEpiWarp0 * 32;  // 0 .. kEpiThreads-1
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int half = (warp - kEpiWarp0) >> 2;    // column half
-        constexpr int kChunks = BN / 64;             // 32-column chunks per half (BN=64 -> 1)
+        const int half = (warp - kEpiWarp0) >> 2;    // column group of this warp
+        static_assert(BN % (32 * G) == 0, "column groups are whole 32-column chunks");
+        constexpr int kChunks = BN / (32 * G);       // 32-column chunks per warp
         static_assert(!Policy::kStoresG || kChunks % 2 == 0, "gradient-matrix slabs are 64 columns wide");
+        // with >= 3 warps per scheduler the TMEM load latency is hidden by the other warps; with 2 the
+        // next chunk's load is kept in flight in a second register buffer
+        constexpr bool kPingPong = (G <= 2) && (kChunks > 1);
         Policy pol;
         pol.kernel_begin(p);
         OutStage os;
@@ -665,13 +681,19 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
             const int c0 = half * kChunks * 32;  // first column of this warp's half
             // two register buffers: the TMEM load of chunk ch+1 is in flight while chunk ch is processed
-            uint32_t va[32], vb[32];
+            uint32_t va[32];
             __syncwarp();
             tmem_ld32(t_lane + c0, va);
-            if (kChunks == 1) {
-                tmem_ld_wait();
-                pol.chunk(p, c, ctx, 0, c0, va, cv + c0, os);
+            if constexpr (!kPingPong) {
+#pragma unroll 1
+                for (int ch = 0; ch < kChunks; ++ch) {
+                    tmem_ld_wait();
+                    pol.chunk(p, c, ctx, ch, c0 + ch * 32, va, cv + c0 + ch * 32, os);
+                    __syncwarp();
+                    if (ch + 1 < kChunks) tmem_ld32(t_lane + c0 + (ch + 1) * 32, va);
+                }
             } else {
+                uint32_t vb[32];
 #pragma unroll 1
                 for (int ch = 0; ch < kChunks; ch += 2) {
                     tmem_ld_wait();
@@ -690,23 +712,25 @@ __global__ void __launch_bounds__(kThreads, 1)
             pol.tile_end(p, c, ctx);
         }
         if (Policy::kStoresG) os.finish(lane);
-        pol.kernel_end(p, red);
+        pol.kernel_end(p, red, kEpiWarps);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
 // ------------------------------------------------------------------------------------ host
 static int pick_bn(int64_t rows, int64_t cols, bool stores_g) {
-    // widest tile that still yields at least ~one tile per SM; small problems are latency bound
+    // widest tile that still yields at least ~one tile per SM; small problems are latency bound.
+    // Gradient-matrix producers (heavy epilogue) use 128 x 192 tiles with 12 epilogue warps.
     const int64_t sms = sm_count();
     const int64_t rb = (rows + BM - 1) / BM;
+    if (stores_g) return rb * ((cols + 191) / 192) >= sms ? 192 : 128;
     if (rb * ((cols + 255) / 256) >= sms) return 256;
-    if (stores_g || rb * ((cols + 127) / 128) >= sms) return 128;
+    if (rb * ((cols + 127) / 128) >= sms) return 128;
     return 64;
 }
 
@@ -715,7 +739,7 @@ struct OutMatrix {  // optional fp16 gradient matrix drained by TMA stores
     int64_t ld = 0;
 };
 
-template <class Policy, int BN>
+template <class Policy, int BN, int G>
 static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                       const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
                       const OutMatrix& om, cudaStream_t st, const char* what) {
@@ -746,8 +770,8 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_x = rinv_x;
     c.rinv_y = rinv_y;
     c.scale = scale;
-    auto kern = sim_kernel<Policy, BN>;
-    constexpr int smem = SimSmem<BN, Policy::kStoresG>::kTotal;
+    auto kern = sim_kernel<Policy, BN, G>;
+    constexpr int smem = SimSmem<BN, G, Policy::kStoresG>::kTotal;
     static bool configured = false;  // per instantiation
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
@@ -755,11 +779,12 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
         configured = true;
     }
     const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid());
-    kern<<<grid, kThreads, smem, st>>>(tx, ty, to, c, pp);
+    kern<<<grid, sim_threads(G), smem, st>>>(tx, ty, to, c, pp);
     return check_launch(what);
 }
 
 static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
+static int g_dbg_flags = 0;  // bring-up knob (pb2_debug_flags)
 
 template <class Policy>
 static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
@@ -772,13 +797,19 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
     cudaStream_t st = (cudaStream_t)stream;
     int bn = force_bn ? force_bn : pick_bn(rows, cols, Policy::kStoresG);
     if (Policy::kStoresG && bn == 64) bn = 128;
-    if (bn == 256)
-        return launch_sim<Policy, 256>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
-    if (bn == 128)
-        return launch_sim<Policy, 128>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
-    if constexpr (!Policy::kStoresG)
-        return launch_sim<Policy, 64>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what);
-    return set_error(PB2_ERR_ARG, "%s: unsupported tile width", what);
+    if (!Policy::kStoresG && bn == 192) bn = 256;
+#define PB2_SIM(B, GG) \
+    launch_sim<Policy, B, GG>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
+    if constexpr (Policy::kStoresG) {
+        if (bn == 192) return PB2_SIM(192, 3);
+        if (bn == 256) return PB2_SIM(256, 2);
+        return PB2_SIM(128, 2);
+    } else {
+        if (bn == 256) return PB2_SIM(256, 2);
+        if (bn == 128) return PB2_SIM(128, 2);
+        return PB2_SIM(64, 2);
+    }
+#undef PB2_SIM
 }
 
 }  // namespace pb2
@@ -786,8 +817,12 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
 using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
+extern "C" int pb2_debug_flags(int flags) {
+    g_dbg_flags = flags;
+    return PB2_OK;
+}
 extern "C" int pb2_debug_force_bn(int bn) {
-    g_force_bn = (bn == 64 || bn == 128 || bn == 256) ? bn : 0;
+    g_force_bn = (bn == 64 || bn == 128 || bn == 192 || bn == 256) ? bn : 0;
     return PB2_OK;
 }
 
@@ -838,7 +873,7 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
                     "sim_hinge memset");
     if (rc) return rc;
     HingeParams pp{diag_row, diag_col, row_offset, col_offset, margin,   loss_partial,
-                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank};
+                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank, g_dbg_flags};
     OutMatrix om;
     om.ptr = gmat;
     om.ld = ld_g;

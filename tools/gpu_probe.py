@@ -215,10 +215,11 @@ def step_loss():
             print(f"{name} fwd+bwd n={n}: {ms:.3f} ms  {n * n / ms / 1e6:.2f} Gpairs/s  {6 * n * n * 512 / ms / 1e9:.1f} TFLOP/s(alg)")
 
 
-STEPS = {k[5:]: v for k, v in list(globals().items()) if k.startswith("step_")}
 
 
 def main():
+    global STEPS
+    STEPS = {k[5:]: v for k, v in list(globals().items()) if k.startswith("step_")}
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what != "all":
         STEPS[what]()
@@ -239,6 +240,40 @@ def main():
         with open(log) as f:
             txt = f.read()
         print(txt[-6000:])
+
+
+
+def step_hinge_perf():
+    """sim_hinge(+rank) on a 32768 x 32768 block for each tile configuration (pb2_debug_force_bn)."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = 32768
+    V, A = emb(n)
+    rv, _ = ops.row_norms(V)
+    ra, _ = ops.row_norms(A)
+    diag, thr = ops.sim_diag(A, V, ra, rv)
+    g, ld = ops.gmat_alloc(n, n, "cuda")
+    rc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    rk = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for flags in (0, 1, 2, 3):
+        lib.pb2_debug_flags(flags)
+        lib.pb2_debug_force_bn(256)
+        ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=10)
+        print(f"dbg flags={flags} bn=256 rank+G: {ms:.3f} ms", flush=True)
+    lib.pb2_debug_flags(0)
+    for bn in (128, 192, 256):
+        lib.pb2_debug_force_bn(bn)
+        for with_rank in (True, False):
+            fn = lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr if with_rank else None,
+                                       rank=rk if with_rank else None)
+            ms = _t(fn, iters=10)
+            print(f"sim_hinge bn={bn} rank={with_rank}: {ms:.3f} ms  {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, None, 0), iters=10)
+        print(f"sim_hinge bn={bn} no-G fwd only: {ms:.3f} ms  {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
+    lib.pb2_debug_force_bn(0)
+
 
 
 if __name__ == "__main__":

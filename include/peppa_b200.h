@@ -91,7 +91,8 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
  *     relu(zc) + relu(zr) summed = these partials + sum_j (margin - diag_col[j]) col_cnt[j]
  *     + sum_i (margin - diag_row[i]) row_cnt[i], completed by pb2_hinge_loss_terms
  *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
- * gmat may be NULL (forward only).  n_partials = capacity of loss_partial (>= pb2_sim_grid()).
+ * gmat may be NULL (forward only).  |n_partials| = capacity of loss_partial (>= pb2_sim_grid()); the buffer
+ * is cleared first unless n_partials is negative (the caller already did, see pb2_hinge_prep).
  * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
  * rank[i] += #{ j != i : s_ij >= pos_thr[i] } (loss and recall@k share one S pass). */
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
@@ -137,6 +138,21 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
                      const float* rinv_y, const int32_t* row_cnt, const int32_t* col_cnt, int64_t rows, int dim,
                      int64_t ldx, int64_t ldy, float coef_host, const float* coef_dev, float* grad_x,
                      int64_t ld_grad, void* stream);
+
+/* Fused small-batch training step (pig/models.py:262 at batch ~1k is launch bound): ONE launch before
+ * the similarity pass -- row norms of V and A, the diagonal score (pig/loss.py:43), fp16 normalised
+ * copies vh/ah ([n, dim], ld = dim) for pb2_grad_gemm, zeroed counts and partials -- and ONE launch
+ * after the gradient GEMMs: dV (rows of p_v) and dA (rows of p_a) through the normalisation Jacobian and
+ * the diagonal term, plus the scalar loss = coef * (sum partials + sum_i (margin - diag_i)(row_cnt_i +
+ * col_cnt_i)) (NaN when a row norm is zero).  Between them: pb2_sim_hinge with n_partials passed
+ * NEGATIVE (= "already zeroed", no memset) and two pb2_grad_gemm. */
+int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
+                   float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
+                   float* loss_partial, int n_partials, void* stream);
+int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim, int64_t ldv,
+                      int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag, const int32_t* row_cnt,
+                      const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,
+                      float* loss_out, float* d_v, float* d_a, void* stream);
 
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,

@@ -254,7 +254,14 @@ extern "C" int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int6
     if ((g_dtype != PB2_F16 && g_dtype != PB2_BF16) || (z_dtype != PB2_F16 && z_dtype != PB2_BF16))
         return set_error(PB2_ERR_ARG, "grad_gemm: operands must be fp16 or bf16");
     cudaStream_t st = (cudaStream_t)stream;
-    const int bn = dim % 256 == 0 ? 256 : (dim % 128 == 0 ? 128 : 64);
+    // widest output tile that divides dim and still gives about one tile per SM (small batches are
+    // latency bound: 1024 rows x 512 dims = 64 tiles of 128 x 64 instead of 16 of 128 x 256)
+    const int64_t m_rows = transpose ? g_cols : g_rows;
+    const int64_t rb = (m_rows + gg::BM - 1) / gg::BM;
+    const int64_t want = std::min<int64_t>(sm_count(), 64);
+    int bn = 64;
+    if (dim % 256 == 0 && rb * (dim / 256) >= want) bn = 256;
+    else if (dim % 128 == 0 && rb * (dim / 128) >= want) bn = 128;
     const int gf = g_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
     const int zf = z_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
 #define PB2_GG(T, B) \

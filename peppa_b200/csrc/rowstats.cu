@@ -186,6 +186,145 @@ __global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------- fused small-batch path
+// One launch before the similarity pass of a training step (pig/loss.py:33-39 at batch size ~1k,
+// where launches dominate): per row i norms of V_i and A_i, the diagonal score, the fp16 normalised
+// copies for the gradient GEMMs, and zeroing of the count / partial buffers.
+__global__ void __launch_bounds__(256)
+    hinge_prep_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ a, int64_t n, int dim,
+                      int64_t ldv, int64_t lda, float* __restrict__ rinv_v, float* __restrict__ rinv_a,
+                      float* __restrict__ diag, __half* __restrict__ vh, __half* __restrict__ ah,
+                      int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
+                      int n_partials) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_partials; i += (int64_t)gridDim.x * blockDim.x)
+        loss_partial[i] = 0.f;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const __nv_bfloat16* vr = v + r * ldv;
+        const __nv_bfloat16* ar = a + r * lda;
+        float sv = 0.f, sa = 0.f, dot = 0.f;
+        for (int d = lane * 8; d < dim; d += 256) {
+            float x[8], y[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(vr + d), x);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(ar + d), y);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sv = fmaf(x[e], x[e], sv);
+                sa = fmaf(y[e], y[e], sa);
+                dot = fmaf(x[e], y[e], dot);
+            }
+        }
+        sv = warp_sum(sv);
+        sa = warp_sum(sa);
+        dot = warp_sum(dot);
+        const float rv = 1.0f / sqrtf(sv), ra = 1.0f / sqrtf(sa);
+        if (lane == 0) {
+            rinv_v[r] = rv;
+            rinv_a[r] = ra;
+            diag[r] = __fmul_rn(__fmul_rn(dot, rv), ra);
+            row_cnt[r] = 0;
+            col_cnt[r] = 0;
+        }
+        for (int d = lane * 8; d < dim; d += 256) {
+            float x[8], y[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(vr + d), x);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(ar + d), y);
+            __half2 hx[4], hy[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                hx[e] = __floats2half2_rn(x[2 * e] * rv, x[2 * e + 1] * rv);
+                hy[e] = __floats2half2_rn(y[2 * e] * ra, y[2 * e + 1] * ra);
+            }
+            *reinterpret_cast<uint4*>(vh + r * dim + d) = *reinterpret_cast<const uint4*>(hx);
+            *reinterpret_cast<uint4*>(ah + r * dim + d) = *reinterpret_cast<const uint4*>(hy);
+        }
+    }
+}
+
+// One launch after the gradient GEMMs: rows [0, n) -> dV, rows [n, 2n) -> dA (normalisation Jacobian +
+// diagonal term, as hinge_finish_kernel), and block 0 finishes the scalar loss from the CTA partials
+// and the indicator counts (NaN if any row norm is zero, like the reference's 0/0).
+__global__ void __launch_bounds__(256)
+    hinge_finish2_kernel(const float* __restrict__ p_v, const float* __restrict__ p_a,
+                         const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ a, int64_t n, int dim,
+                         int64_t ldv, int64_t lda, const float* __restrict__ rinv_v, const float* __restrict__ rinv_a,
+                         const float* __restrict__ diag, const int32_t* __restrict__ row_cnt,
+                         const int32_t* __restrict__ col_cnt, const float* __restrict__ loss_partial, int n_partials,
+                         float margin, float coef, float* __restrict__ loss_out, float* __restrict__ d_v,
+                         float* __restrict__ d_a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t rr = warp; rr < 2 * n; rr += nwarps) {
+        const bool is_v = rr < n;
+        const int64_t r = is_v ? rr : rr - n;
+        const float* pr = (is_v ? p_v : p_a) + r * dim;
+        const __nv_bfloat16* xr = is_v ? v + r * ldv : a + r * lda;
+        const __nv_bfloat16* yr = is_v ? a + r * lda : v + r * ldv;
+        const float rx = is_v ? rinv_v[r] : rinv_a[r];
+        const float ry = is_v ? rinv_a[r] : rinv_v[r];
+        const float gd = -(float)(row_cnt[r] + col_cnt[r]) * ry;
+        float* out = (is_v ? d_v : d_a) + r * dim;
+        float dot = 0.f;
+        for (int d = lane * 8; d < dim; d += 256) {
+            float x[8], y[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), x);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), y);
+            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
+            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(gd, y[e], pv[e]), x[e] * rx, dot);
+        }
+        dot = warp_sum(dot);
+        for (int d = lane * 8; d < dim; d += 256) {
+            float x[8], y[8], o[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), x);
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), y);
+            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
+            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[e], pv[e]) - x[e] * rx * dot);
+            *reinterpret_cast<float4*>(out + d) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(out + d + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double sh[8];
+        __shared__ int sbad[8];
+        double acc = 0.0;
+        int bad = 0;
+        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += (double)loss_partial[i];
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            acc += (double)(margin - diag[i]) * (double)(row_cnt[i] + col_cnt[i]);
+            const float x = rinv_v[i], y = rinv_a[i];
+            bad |= !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (lane == 0) {
+            sh[threadIdx.x >> 5] = acc;
+            sbad[threadIdx.x >> 5] = bad;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            int b = 0;
+            for (int w = 0; w < 8; ++w) {
+                t += sh[w];
+                b |= sbad[w];
+            }
+            loss_out[0] = b ? __int_as_float(0x7fc00000) : (float)(t * (double)coef);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ hinge finish
 // One warp per row; the row (p, x, y) is held in registers for dim <= 1024, else re-read.
 __global__ void __launch_bounds__(256)
@@ -408,6 +547,38 @@ extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, con
         p, ld_p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim,
         ldx, ldy, coef_host, coef_dev, grad_x, ld_grad);
     return check_launch("hinge_finish");
+}
+
+extern "C" int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
+                              float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
+                              float* loss_partial, int n_partials, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!v || !a || !rinv_v || !rinv_a || !diag || !vh || !ah || !row_cnt || !col_cnt || !loss_partial)
+        return set_error(PB2_ERR_ARG, "hinge_prep: null");
+    if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(vh, dim, 2) || !vec_ok(ah, dim, 2))
+        return set_error(PB2_ERR_ARG, "hinge_prep: alignment");
+    hinge_prep_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
+        (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials);
+    return check_launch("hinge_prep");
+}
+
+extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim,
+                                 int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag,
+                                 const int32_t* row_cnt, const int32_t* col_cnt, const float* loss_partial,
+                                 int n_partials, float margin, float coef, float* loss_out, float* d_v, float* d_a,
+                                 void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!p_v || !p_a || !v || !a || !rinv_v || !rinv_a || !diag || !row_cnt || !col_cnt || !loss_partial || !loss_out ||
+        !d_v || !d_a)
+        return set_error(PB2_ERR_ARG, "hinge_finish2: null");
+    if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
+        !vec_ok(d_v, dim, 4) || !vec_ok(d_a, dim, 4))
+        return set_error(PB2_ERR_ARG, "hinge_finish2: alignment");
+    hinge_finish2_kernel<<<grid_for_warps(2 * n), 256, 0, (cudaStream_t)stream>>>(
+        p_v, p_a, (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt,
+        col_cnt, loss_partial, n_partials, margin, coef, loss_out, d_v, d_a);
+    return check_launch("hinge_finish2");
 }
 
 extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,

@@ -864,14 +864,18 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!diag_row || !diag_col || !loss_partial || !row_cnt || !col_cnt)
         return set_error(PB2_ERR_ARG, "sim_hinge: null");
+    const bool prezeroed = n_partials < 0;  // pb2_hinge_prep already cleared the partial buffer
+    if (prezeroed) n_partials = -n_partials;
     if (n_partials < pb2_sim_grid()) return set_error(PB2_ERR_ARG, "sim_hinge: loss_partial too small");
     int rc = check_gmat(gmat, ld_g, cols, "sim_hinge");
     if (rc) return rc;
     if ((pos_thr == nullptr) != (rank == nullptr))
         return set_error(PB2_ERR_ARG, "sim_hinge: pos_thr and rank go together");
-    rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
-                    "sim_hinge memset");
-    if (rc) return rc;
+    if (!prezeroed) {
+        rc = check_cuda(cudaMemsetAsync(loss_partial, 0, sizeof(float) * n_partials, (cudaStream_t)stream),
+                        "sim_hinge memset");
+        if (rc) return rc;
+    }
     HingeParams pp{diag_row, diag_col, row_offset, col_offset, margin,   loss_partial,
                    row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank, g_dbg_flags};
     OutMatrix om;

@@ -33,6 +33,11 @@ class _HingeFn(torch.autograd.Function):
         dev = vb.device
         n = vb.shape[0]
         need_grad = any(ctx.needs_input_grad[:2])
+        if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the five-launch fused step
+            loss, dV, dA = ops.hinge_step(vb, ab, margin)
+            ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
+            ctx.meta = (V.dtype, V.device, A.dtype, A.device)
+            return loss.to(V.device)
         rv, nv = ops.row_norms(vb)
         ra, na = ops.row_norms(ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43

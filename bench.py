@@ -221,8 +221,7 @@ def bench_train1024(args, device):
     import torch
     from peppa_b200.loss import TripletLoss
     n = 1024
-    a, v = synth_embeddings(n, 666, device)
-    a, v = a.float(), v.float()
+    a, v = synth_embeddings(n, 666, device)        # bf16 leaves, bf16 gradients (config 2: "1024 x 512-d bf16")
     mod = TripletLoss(MARGIN)
     vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
 

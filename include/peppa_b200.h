@@ -144,7 +144,8 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
  * copies vh/ah ([n, dim], ld = dim) for pb2_grad_gemm, zeroed counts and partials -- and ONE launch
  * after the gradient GEMMs: dV (rows of p_v) and dA (rows of p_a) through the normalisation Jacobian and
  * the diagonal term, plus the scalar loss = coef * (sum partials + sum_i (margin - diag_i)(row_cnt_i +
- * col_cnt_i)) (NaN when a row norm is zero).  Between them: pb2_sim_hinge with n_partials passed
+ * col_cnt_i)) (NaN when a row norm is zero); d_v / d_a are [n, dim] in out_dtype (PB2_F32/BF16/F16).
+ * Between them: pb2_sim_hinge with n_partials passed
  * NEGATIVE (= "already zeroed", no memset) and two pb2_grad_gemm. */
 int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
                    float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
@@ -152,7 +153,7 @@ int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv
 int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim, int64_t ldv,
                       int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag, const int32_t* row_cnt,
                       const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,
-                      float* loss_out, float* d_v, float* d_a, void* stream);
+                      float* loss_out, void* d_v, void* d_a, int out_dtype, void* stream);
 
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,

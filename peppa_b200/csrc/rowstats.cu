@@ -246,14 +246,37 @@ __global__ void __launch_bounds__(256)
 // One launch after the gradient GEMMs: rows [0, n) -> dV, rows [n, 2n) -> dA (normalisation Jacobian +
 // diagonal term, as hinge_finish_kernel), and block 0 finishes the scalar loss from the CTA partials
 // and the indicator counts (NaN if any row norm is zero, like the reference's 0/0).
+template <typename T>
+__device__ __forceinline__ void store8(T* dst, const float (&o)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* dst, const float (&o)[8]) {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* dst, const float (&o)[8]) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* dst, const float (&o)[8]) {
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+}
+
+template <typename TOut>
 __global__ void __launch_bounds__(256)
     hinge_finish2_kernel(const float* __restrict__ p_v, const float* __restrict__ p_a,
                          const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ a, int64_t n, int dim,
                          int64_t ldv, int64_t lda, const float* __restrict__ rinv_v, const float* __restrict__ rinv_a,
                          const float* __restrict__ diag, const int32_t* __restrict__ row_cnt,
                          const int32_t* __restrict__ col_cnt, const float* __restrict__ loss_partial, int n_partials,
-                         float margin, float coef, float* __restrict__ loss_out, float* __restrict__ d_v,
-                         float* __restrict__ d_a) {
+                         float margin, float coef, float* __restrict__ loss_out, TOut* __restrict__ d_v,
+                         TOut* __restrict__ d_a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(256)
         const float rx = is_v ? rinv_v[r] : rinv_a[r];
         const float ry = is_v ? rinv_a[r] : rinv_v[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * ry;
-        float* out = (is_v ? d_v : d_a) + r * dim;
+        TOut* out = (is_v ? d_v : d_a) + r * dim;
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
@@ -288,8 +311,7 @@ __global__ void __launch_bounds__(256)
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[e], pv[e]) - x[e] * rx * dot);
-            *reinterpret_cast<float4*>(out + d) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(out + d + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            store8<TOut>(out + d, o);
         }
     }
     if (blockIdx.x == 0) {
@@ -566,18 +588,25 @@ extern "C" int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, 
 extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim,
                                  int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag,
                                  const int32_t* row_cnt, const int32_t* col_cnt, const float* loss_partial,
-                                 int n_partials, float margin, float coef, float* loss_out, float* d_v, float* d_a,
-                                 void* stream) {
+                                 int n_partials, float margin, float coef, float* loss_out, void* d_v, void* d_a,
+                                 int out_dtype, void* stream) {
     if (n <= 0) return PB2_OK;
     if (!p_v || !p_a || !v || !a || !rinv_v || !rinv_a || !diag || !row_cnt || !col_cnt || !loss_partial || !loss_out ||
         !d_v || !d_a)
         return set_error(PB2_ERR_ARG, "hinge_finish2: null");
+    const int ob = out_dtype == PB2_F32 ? 4 : 2;
     if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
-        !vec_ok(d_v, dim, 4) || !vec_ok(d_a, dim, 4))
+        !vec_ok(d_v, dim, ob) || !vec_ok(d_a, dim, ob))
         return set_error(PB2_ERR_ARG, "hinge_finish2: alignment");
-    hinge_finish2_kernel<<<grid_for_warps(2 * n), 256, 0, (cudaStream_t)stream>>>(
-        p_v, p_a, (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt,
-        col_cnt, loss_partial, n_partials, margin, coef, loss_out, d_v, d_a);
+#define PB2_FIN2(T)                                                                                                \
+    hinge_finish2_kernel<T><<<grid_for_warps(2 * n), 256, 0, (cudaStream_t)stream>>>(                               \
+        p_v, p_a, (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, \
+        col_cnt, loss_partial, n_partials, margin, coef, loss_out, (T*)d_v, (T*)d_a)
+    if (out_dtype == PB2_F32) PB2_FIN2(float);
+    else if (out_dtype == PB2_BF16) PB2_FIN2(__nv_bfloat16);
+    else if (out_dtype == PB2_F16) PB2_FIN2(__half);
+    else return set_error(PB2_ERR_ARG, "hinge_finish2: unknown output dtype");
+#undef PB2_FIN2
     return check_launch("hinge_finish2");
 }
 

@@ -34,10 +34,13 @@ class _HingeFn(torch.autograd.Function):
         n = vb.shape[0]
         need_grad = any(ctx.needs_input_grad[:2])
         if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the five-launch fused step
-            loss, dV, dA = ops.hinge_step(vb, ab, margin)
-            ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
-            ctx.meta = (V.dtype, V.device, A.dtype, A.device)
+            same = V.dtype == A.dtype and V.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            loss, grads = ops.hinge_step(vb, ab, margin, V.dtype if same else torch.float32)
+            ctx.save_for_backward(grads)
+            ctx.fused = True
+            ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
             return loss.to(V.device)
+        ctx.fused = False
         rv, nv = ops.row_norms(vb)
         ra, na = ops.row_norms(ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
@@ -79,6 +82,14 @@ class _HingeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.fused:       # one scale kernel for both gradients, already in the inputs' dtype
+            (grads,) = ctx.saved_tensors
+            vd, vdev, ad, adev, dv_, da_ = ctx.meta
+            # a 0-d fp32 grad_output does not promote the product: one kernel, result in grads.dtype
+            g = grads * (grad_out if grad_out.device == grads.device else grad_out.to(grads.device))
+            gV = g[0][:, :dv_].to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
+            gA = g[1][:, :da_].to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
+            return gV, gA, None
         dV, dA = ctx.saved_tensors
         vd, vdev, ad, adev = ctx.meta
         go = grad_out.to(device=dV.device, dtype=torch.float32)

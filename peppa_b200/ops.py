@@ -217,9 +217,10 @@ def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
     return grad
 
 
-def hinge_step(vb, ab, margin):
+def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
     """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768) in five launches:
-    prep, fused similarity/hinge pass, two gradient GEMMs, finish.  Returns (loss 0-d fp32, dV, dA fp32)."""
+    prep, fused similarity/hinge pass, two gradient GEMMs, finish.  Returns (loss 0-d fp32, grads [2, n, d]
+    in ``grad_dtype``: dV then dA)."""
     n, d = vb.shape
     dev = vb.device
     lib = _cabi.lib()
@@ -231,7 +232,7 @@ def hinge_step(vb, ab, margin):
     halves = torch.empty(2, n, d, dtype=torch.float16, device=dev)
     g, ld = gmat_alloc(n, n, dev)
     pbuf = torch.empty(2, n, d, dtype=f32, device=dev)
-    grads = torch.empty(2, n, d, dtype=f32, device=dev)
+    grads = torch.empty(2, n, d, dtype=grad_dtype, device=dev)
     loss = torch.empty((), dtype=f32, device=dev)
     rv, ra, diag = stats[0], stats[1], stats[2]
     with torch.cuda.device(dev):
@@ -248,9 +249,9 @@ def hinge_step(vb, ab, margin):
               "grad_gemm")
         check(lib.pb2_hinge_finish2(_ptr(pbuf[0]), _ptr(pbuf[1]), _ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0),
                                     _ptr(rv), _ptr(ra), _ptr(diag), _ptr(cnts[0]), _ptr(cnts[1]), _ptr(part), n_part,
-                                    float(margin), 1.0 / float(n) ** 2, _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), st),
-              "hinge_finish2")
-    return loss, grads[0], grads[1]
+                                    float(margin), 1.0 / float(n) ** 2, _ptr(loss), _ptr(grads[0]), _ptr(grads[1]),
+                                    _DTYPE_CODE[grad_dtype], st), "hinge_finish2")
+    return loss, grads
 
 
 def sum_partials(part, alpha=1.0):

@@ -83,6 +83,13 @@ int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float*
                  const int64_t* pos_col, int64_t rows, int64_t cols, int64_t col_offset, int dim, int64_t ldq,
                  int64_t ldg, int32_t* rank, void* stream);
 
+/* pig/metrics.py:54-77 resampled recall from ONE score matrix: scores = pb2_sim_matrix(references,
+ * candidates) [G, G] fp32; idx = the n_samples x size subset draws (row-major int64, device);
+ * rank[s, j] = #{ c != j : fl32(1 - scores[ix_j, ix_c]) < fl32(1 - scores[ix_j, ix_j]) } (int32 [n_samples, size]).
+ * Replaces 500 small GEMMs + 50 000 argsort rows per evaluation call. */
+int pb2_subset_rank(const float* scores, int64_t ld, const int64_t* idx, int n_samples, int size, int32_t* rank,
+                    void* stream);
+
 /* pig/loss.py:28-48 TripletLoss / contrastive, forward pass fused with the gradient matrix.
  * For local rows i (global row id row_offset + i) and columns j (global id col_offset + j), i != j globally:
  *   zc = margin + s_ij - diag_col[j],  zr = margin + s_ij - diag_row[i]

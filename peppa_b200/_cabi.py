@@ -33,6 +33,7 @@ SIGNATURES = {
     "pb2_sim_diag": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
     "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i64, _i64, _p, _p],
+    "pb2_subset_rank": [_p, _i64, _p, _i, _i, _p, _p],
     "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],
     "pb2_sim_lse_parts": [_i64],
     "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _p, _p],

@@ -421,6 +421,33 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ------------------------------------------------------------------- resampled recall (f1)
+// pig/metrics.py:54-77 draws n_samples subsets of `size` clips and ranks each 100 x 100 sub-matrix with
+// its own GEMM + argsort loop.  Here the G x G score matrix is computed once (pb2_sim_matrix) and every
+// (sample, query) pair counts, inside its subset, the candidates strictly closer than its positive:
+// rank[s, j] = #{ c != j : fl32(1 - S[ix_j, ix_c]) < fl32(1 - S[ix_j, ix_j]) }.  One warp per (sample, query).
+__global__ void __launch_bounds__(256)
+    subset_rank_kernel(const float* __restrict__ S, int64_t ld, const int64_t* __restrict__ idx, int n_samples,
+                       int size, int32_t* __restrict__ rank) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t total = (int64_t)n_samples * size;
+    for (int64_t w = warp; w < total; w += nwarps) {
+        const int64_t s = w / size;
+        const int j = (int)(w % size);
+        const int64_t* ix = idx + s * size;
+        const float* row = S + ix[j] * ld;
+        const float dpos = __fsub_rn(1.0f, row[ix[j]]);
+        int cnt = 0;
+        for (int c = lane; c < size; c += 32)
+            cnt += (c != j && __fsub_rn(1.0f, row[ix[c]]) < dpos) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) rank[w] = cnt;
+    }
+}
+
 // ---------------------------------------------------------------------- contrastive(M) on a matrix
 // pass 1: one block per row: loss partial, indicator counts, off-diagonal gradient entries.
 __global__ void __launch_bounds__(256)
@@ -521,6 +548,15 @@ extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, con
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out,
         thr_out);
     return check_launch("pair_dot");
+}
+
+extern "C" int pb2_subset_rank(const float* scores, int64_t ld, const int64_t* idx, int n_samples, int size,
+                               int32_t* rank, void* stream) {
+    if (n_samples <= 0 || size <= 0) return PB2_OK;
+    if (!scores || !idx || !rank) return set_error(PB2_ERR_ARG, "subset_rank: null");
+    subset_rank_kernel<<<grid_for_warps((int64_t)n_samples * size), 256, 0, (cudaStream_t)stream>>>(scores, ld, idx, n_samples,
+                                                                                                 size, rank);
+    return check_launch("subset_rank");
 }
 
 extern "C" int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,

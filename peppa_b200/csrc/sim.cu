@@ -96,6 +96,14 @@ struct OutStage {
                 make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
         }
     }
+    // 32 fp32 of this thread's row = one whole 128-byte swizzled row (slab = one 32-column chunk)
+    __device__ __forceinline__ void write_f32(int lane, const float (&o)[32]) {
+        uint8_t* row = buf + (slab & 1u) * kOutSlabBytes + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(row + ((k ^ (lane & 7)) * 16)) =
+                make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
     __device__ __forceinline__ void begin_slab(int lane) {  // the slab buffer used two slabs ago must be drained
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
@@ -141,6 +149,7 @@ struct StorePolicy {
     };
     static constexpr int kColVecs = 1;
     static constexpr bool kStoresG = false;
+    static constexpr bool kStoresF32 = true;  // S tiles leave through the OutStage (fp32 boxes [32 x 32])
     float ri;
     __device__ void kernel_begin(const Params&) {}
     __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
@@ -149,32 +158,23 @@ struct StorePolicy {
     __device__ void tile_begin(const Params&, const SimCommon& c, const TileCtx& t) {
         ri = (t.row_valid ? (c.rinv_x ? c.rinv_x[t.row] : 1.f) : 0.f) * c.scale;
     }
-    __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
-                          const float* cv, OutStage&) {
-        if (!t.row_valid) return;
-        float* dst = p.out + t.row * p.ld + t.col0 + cbase;
-        const int nvalid = t.cols_valid - cbase;
-        if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage& os) {
+        if (cbase >= t.cols_valid) return;  // warp-uniform; TMA clips partially valid boxes itself
+        const int lane = threadIdx.x & 31;
+        float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = __uint_as_float(v[j]) * ri * cv[j];
-                o.y = __uint_as_float(v[j + 1]) * ri * cv[j + 1];
-                o.z = __uint_as_float(v[j + 2]) * ri * cv[j + 2];
-                o.w = __uint_as_float(v[j + 3]) * ri * cv[j + 3];
-                *reinterpret_cast<float4*>(dst + j) = o;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < nvalid) dst[j] = __uint_as_float(v[j]) * ri * cv[j];
-        }
+        for (int j = 0; j < 32; ++j) o[j] = __fmul_rn(__fmul_rn(__uint_as_float(v[j]), ri), cv[j]);
+        os.begin_slab(lane);
+        os.write_f32(lane, o);
+        os.end_slab(lane, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
     __device__ void kernel_end(const Params&, float*, int) {}
 };
 
 struct RankPolicy {
+    static constexpr bool kStoresF32 = false;
     struct Params {
         const float* pos_thr;  // rank_threshold(fl32(1 - s_pos)) per row (pb2_sim_diag / pb2_pair_dot)
         const int64_t* pos_col;
@@ -242,6 +242,7 @@ struct RankPolicy {
 // the diagonal tiles are visited): a gallery row that duplicates the positive then scores exactly
 // like it, as in the reference where both come out of one GEMM, and "strictly closer" stays strict.
 struct DiagPolicy {
+    static constexpr bool kStoresF32 = false;
     struct Params {
         float* out;   // s_k            (may be null)
         float* dist;  // fl32(1 - s_k)  (may be null)
@@ -306,6 +307,7 @@ struct HingeParams {
 constexpr float kBig = 1.329227995784916e36f;  // 2^120
 template <bool kRank>
 struct HingePolicyT {
+    static constexpr bool kStoresF32 = false;
     using Params = HingeParams;
     static constexpr int kColVecs = 3;  // rinv_y, thr_c = diag_col - margin, -pred(thr_c) * 2^120
     static constexpr bool kStoresG = true;
@@ -433,6 +435,7 @@ struct HingePolicyT {
 };
 
 struct LseRowPolicy {
+    static constexpr bool kStoresF32 = false;
     struct Params {
         float* part_max;
         float* part_sum;
@@ -484,6 +487,7 @@ struct LseRowPolicy {
 };
 
 struct LseGradPolicy {
+    static constexpr bool kStoresF32 = false;
     struct Params {
         const float* den_row;
         const float* den_col;
@@ -539,7 +543,7 @@ template <class Policy, int BN, int G>
 __global__ void __launch_bounds__(sim_threads(G), 1)
     sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                const __grid_constant__ CUtensorMap tm_out, const SimCommon c, const typename Policy::Params p) {
-    using L = SimSmem<BN, G, Policy::kStoresG>;
+    using L = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32>;
     constexpr int kEpiWarps = 4 * G;
     constexpr int kEpiThreads = kEpiWarps * 32;
     constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_y);
-        if (Policy::kStoresG) tma_prefetch_desc(&tm_out);
+        if (Policy::kStoresG || Policy::kStoresF32) tma_prefetch_desc(&tm_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < L::kStages; ++s) {
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             if (lane == 0) mbar_arrive(acc_empty + as);
             pol.tile_end(p, c, ctx);
         }
-        if (Policy::kStoresG) os.finish(lane);
+        if (Policy::kStoresG || Policy::kStoresF32) os.finish(lane);
         pol.kernel_end(p, red, kEpiWarps);
     }
     tc_fence_before();
@@ -751,6 +755,9 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     if (Policy::kStoresG && om.ptr) {
         rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
         if (rc) return rc;
+    } else if (Policy::kStoresF32 && om.ptr) {
+        rc = make_tmap_2d(&to, om.ptr, 4, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 4, 32, 32);
+        if (rc) return rc;
     } else {
         to = tx;  // never dereferenced
     }
@@ -771,7 +778,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_y = rinv_y;
     c.scale = scale;
     auto kern = sim_kernel<Policy, BN, G>;
-    constexpr int smem = SimSmem<BN, G, Policy::kStoresG>::kTotal;
+    constexpr int smem = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32>::kTotal;
     static bool configured = false;  // per instantiation
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
@@ -830,9 +837,14 @@ extern "C" int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x,
                               int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* out,
                               int64_t ld_out, void* stream) {
     if (!out && rows > 0 && cols > 0) return set_error(PB2_ERR_ARG, "sim_matrix: null output");
+    if (rows > 0 && cols > 0 && ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0 || ld_out < cols))
+        return set_error(PB2_ERR_ARG, "sim_matrix: out must be 16-byte aligned with ld_out %% 4 == 0, ld_out >= cols");
     StorePolicy::Params pp{out, ld_out};
+    OutMatrix om;
+    om.ptr = out;
+    om.ld = ld_out;
     return dispatch_sim<StorePolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
-                                     "sim_matrix", g_force_bn);
+                                     "sim_matrix", g_force_bn, om);
 }
 
 extern "C" int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim,

@@ -113,28 +113,40 @@ def triplet_accuracy(anchor, positive, negative, dim=1, discrete=True):
     return out.to(out_device)
 
 
+# One G x G score matrix serves every subset while it fits comfortably in HBM (fp32, 2^28 entries = 1 GiB).
+_RESAMPLE_MATRIX_LIMIT = 1 << 28
+
+
+def _resampled_ranks(candidates, references, size, n_samples):
+    """int32 [n_samples, size] ranks of each subset's positives; the subset draws consume the CPU
+    global generator exactly like the reference's loop (one randperm per sample, nothing else)."""
+    ix = torch.stack([sample_indices(candidates, size) for _ in range(n_samples)]) if n_samples > 0 else \
+        torch.empty(0, size, dtype=torch.int64)
+    g = len(candidates)
+    if g * g <= _RESAMPLE_MATRIX_LIMIT and n_samples > 0:
+        qb = ops.as_bf16_rows(references)
+        gb = ops.as_bf16_rows(candidates, device=qb.device)
+        rq, _ = ops.row_norms(qb)
+        rg, _ = ops.row_norms(gb)
+        scores = ops.sim_matrix(qb, gb, rq, rg)          # rows = references, as in pig/metrics.py:8
+        return ops.subset_rank(scores, ix.to(qb.device))
+    ranks = [_pair_ranks(candidates[i], references[i], None)[0] for i in ix]      # huge galleries: per subset
+    return torch.stack(ranks) if ranks else torch.empty(0, size, dtype=torch.int32)
+
+
 def resampled_recall(candidates, references, size=100, n_samples=100, n=1):
     assert len(candidates) == len(references)
     assert len(candidates) >= size
-    result = []
-    for i in range(n_samples):
-        ix = sample_indices(candidates, size)
-        X = candidates[ix]
-        Y = references[ix]
-        result.append(recall_at_n(X, Y, None, n=n))
-    return torch.stack(result)
+    rank = _resampled_ranks(candidates, references, size, n_samples)
+    return (rank < n).to(torch.float32).cpu()
 
 
 def resampled_recall_at_1_to_n(candidates, references, size=100, n_samples=100, N=1):
     assert len(candidates) == len(references)
     assert len(candidates) >= size
-    result = []
-    for i in range(n_samples):
-        ix = sample_indices(candidates, size)
-        X = candidates[ix]
-        Y = references[ix]
-        result.append(recall_at_1_to_n(X, Y, None, N=N))
-    return torch.stack(result)
+    rank = _resampled_ranks(candidates, references, size, n_samples)
+    ns = torch.arange(0, N + 1, device=rank.device, dtype=torch.int32).view(1, N + 1, 1)
+    return (rank.unsqueeze(1) < ns).to(torch.float32).cpu()      # [n_samples, N+1, size], row 0 == 0
 
 
 def sample_indices(x, size):

@@ -104,13 +104,15 @@ def sim_diag(x, y, rinv_x=None, rinv_y=None):
 
 
 def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
+    """fp32 [r, c] scores; the storage row pitch is padded to a multiple of 4 floats (16-byte rows for
+    the TMA stores), the returned tensor is the [:, :c] view."""
     r, c = x.shape[0], y.shape[0]
-    out = torch.empty(r, c, dtype=torch.float32, device=x.device)
+    ld = max(4, (c + 3) // 4 * 4)
+    buf = torch.empty(r, ld, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         check(_cabi.lib().pb2_sim_matrix(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0),
-                                         y.stride(0), float(scale), _ptr(out), out.stride(0) if r and c else c,
-                                         _stream(x.device)), "sim_matrix")
-    return out
+                                         y.stride(0), float(scale), _ptr(buf), ld, _stream(x.device)), "sim_matrix")
+    return buf[:, :c]
 
 
 def sim_rank(q, g, rinv_q, rinv_g, pos_thr, pos_col, col_offset=0, rank=None):
@@ -121,6 +123,16 @@ def sim_rank(q, g, rinv_q, rinv_g, pos_thr, pos_col, col_offset=0, rank=None):
         check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_thr), _ptr(pos_col), r, c,
                                        int(col_offset), q.shape[1], q.stride(0), g.stride(0), _ptr(rank),
                                        _stream(q.device)), "sim_rank")
+    return rank
+
+
+def subset_rank(scores, idx):
+    """scores [G, G] fp32 (rows = queries), idx [n_samples, size] int64 on the same device -> int32 ranks."""
+    n_samples, size = idx.shape
+    rank = torch.empty(n_samples, size, dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(_cabi.lib().pb2_subset_rank(_ptr(scores), scores.stride(0), _ptr(idx), n_samples, size, _ptr(rank),
+                                          _stream(scores.device)), "subset_rank")
     return rank
 
 

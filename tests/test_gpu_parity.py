@@ -274,3 +274,40 @@ def test_rank_ties_are_strict(pb):
     assert bool(((got == ranks) | near).all())
     fused = GalleryStep(n, 512).run(A.cuda().bfloat16(), V.cuda().bfloat16())["ranks"].cpu().long()
     assert torch.equal(fused, got)          # same thresholds, same two roundings: bit-identical counts
+
+
+def test_resampled_recall_paths_agree(pb):
+    """The one-matrix fast path (pb2_sim_matrix + pb2_subset_rank) and the per-subset path draw the same
+    subsets and give the same recall (up to near-ties, which the two arithmetic routes may order differently)."""
+    V, A = emb(700, 4.0, seed=21)
+    torch.manual_seed(7)
+    fast = pb.metrics.resampled_recall_at_1_to_n(V.cuda(), A.cuda(), size=100, n_samples=20, N=10)
+    old = pb.metrics._RESAMPLE_MATRIX_LIMIT
+    pb.metrics._RESAMPLE_MATRIX_LIMIT = 0
+    try:
+        torch.manual_seed(7)
+        slow = pb.metrics.resampled_recall_at_1_to_n(V.cuda(), A.cuda(), size=100, n_samples=20, N=10)
+    finally:
+        pb.metrics._RESAMPLE_MATRIX_LIMIT = old
+    assert fast.shape == slow.shape == (20, 11, 100)
+    assert int((fast != slow).any(dim=1).sum()) <= 4
+    torch.manual_seed(7)
+    ref = O.resampled_recall_at_1_to_n(V, A, size=100, n_samples=20, N=10)
+    assert int((fast != ref).any(dim=1).sum()) <= 4
+
+
+def test_cosine_matrix_odd_shapes_and_backward(pb):
+    g = torch.Generator().manual_seed(9)
+    U = torch.randn(130, 512, generator=g).bfloat16().float()
+    W = torch.randn(257, 512, generator=g).bfloat16().float()
+    M = pb.util.cosine_matrix(U.cuda(), W.cuda())
+    assert M.shape == (130, 257)
+    assert (M.cpu() - O.cosine_matrix(U, W)).abs().max() < 2e-6
+    u = U.cuda().requires_grad_(True)
+    w = W.cuda().requires_grad_(True)
+    T = torch.randn(130, 257, generator=g)
+    (pb.util.cosine_matrix(u, w) * T.cuda()).sum().backward()
+    ur = U.clone().requires_grad_(True)
+    wr = W.clone().requires_grad_(True)
+    (O.cosine_matrix(ur, wr) * T).sum().backward()
+    assert rel_err(u.grad.cpu(), ur.grad) < 2e-3 and rel_err(w.grad.cpu(), wr.grad) < 2e-3   # fp16 cast of dS

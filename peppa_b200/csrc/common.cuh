@@ -50,27 +50,31 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps IN HARDWARE until the phase completes (or ~the
+// hint elapses) instead of spinning -- the producer / MMA / loader warps share schedulers with epilogue
+// warps, and a busy poll loop steals their issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
     return done != 0;
 }
-// Bounded wait: a protocol bug (lost arrive, wrong phase) must trap, never hang the GPU.
-// ~4e9 cycles at ~1.9 GHz is a couple of seconds, far beyond any legitimate wait here.
+// Bounded wait: a protocol bug (lost arrive, wrong phase) must trap, never hang the GPU.  The clock is
+// only consulted every 256 failed (i.e. timed-out) tries; ~4e9 cycles is a couple of seconds.
 #ifndef PB2_WAIT_TIMEOUT_CYCLES
 #define PB2_WAIT_TIMEOUT_CYCLES 4000000000ll
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > PB2_WAIT_TIMEOUT_CYCLES) {
+        if ((++spins & 255u) == 0u && clock64() - t0 > PB2_WAIT_TIMEOUT_CYCLES) {
             printf("pb2: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
                    smem_u32(bar), parity);
             __trap();

@@ -276,5 +276,32 @@ def step_hinge_perf():
 
 
 
+
+def step_hinge_dim():
+    """Is the fused hinge pass MMA-bound or epilogue-bound?  Time it at D = 128 .. 1024 (same epilogue work)."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = 32768
+    for d in (128, 256, 512, 1024):
+        V, A = emb(n, d=d)
+        rv, _ = ops.row_norms(V)
+        ra, _ = ops.row_norms(A)
+        diag, thr = ops.sim_diag(A, V, ra, rv)
+        g, ld = ops.gmat_alloc(n, n, "cuda")
+        rc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        cc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        rk = torch.zeros(n, dtype=torch.int32, device="cuda")
+        idx = torch.arange(n, device="cuda")
+        for bn in (192, 256):
+            lib.pb2_debug_force_bn(bn)
+            ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=10)
+            print(f"D={d} bn={bn} hinge+rank+G: {ms:.3f} ms", flush=True)
+        lib.pb2_debug_force_bn(256)
+        ms = _t(lambda: ops.sim_rank(A, V, ra, rv, thr, idx), iters=10)
+        print(f"D={d} rank only: {ms:.3f} ms", flush=True)
+    lib.pb2_debug_force_bn(0)
+
+
 if __name__ == "__main__":
     main()

@@ -93,6 +93,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (GB) of one launch on a 32768 x 32768 block, from the committed
+    ncu --set full capture (profiles/r1_ncu_summary.json); None if unknown."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+    key = {"sim_hinge+rank": "r1_sim_hinge", "sim_hinge": "r1_sim_hinge", "grad_gemm": "r1_grad_gemm"}.get(kernel)
+    if not key or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f).get(key, {})
+
+    def gb(s):
+        v, u = s.split()[:2]
+        return float(v) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
+    try:
+        return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+    except (KeyError, ValueError):
+        return None
+
+
 def synth_embeddings(n, seed, device, alpha=4.0):
     """SURVEY 8(d) synthetic inputs: V = normalize(randn), A = normalize(alpha V + randn), bf16."""
     import torch
@@ -273,7 +292,8 @@ def bench_triplets1m(args, device):
     byt = t * (3 * DIM * 2 + 4)
     return {"workload": "triplets1m (config 4): triplet_accuracy, 2^20 triplets x 512 bf16", "triplets_per_s": t / ms * 1e3, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
-                         "frac": byt / ms / 1e6 / peaks()["hbm_gbs"], "traffic": None}}
+                         "frac": byt / ms / 1e6 / peaks()["hbm_gbs"], "traffic": 3.2286, "algorithmic": byt / 1e9,
+                         "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1_ncu_summary.json)"}}
 
 
 def main():
@@ -334,8 +354,9 @@ def main():
                    "parallelism": f"row-shard x{world}" + (" + NCCL all-gather/all-reduce/reduce-scatter" if world > 1 else "")},
         "frac_of_bf16_peak": 6.0 * res["pairs"] * DIM / (res["ms"] * 1e-3) / world / (pk["tf_sustained"] * 1e12),
         "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
-                     "launches": dom["launches"]},
+                     "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic(dom_name),
+                     "traffic_unit": "GB per launch (32768 x 32768 block, ncu --set full, profiles/r1_ncu_summary.json)",
+                     "peak_source": pk["source"] + " (sustained)", "launches": dom["launches"]},
         "kernels": {k: {"launches": v["launches"], "ms_total": v["ms"], "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None}
                     for k, v in res["kernels"].items()},
         "clocks": res["clocks"],

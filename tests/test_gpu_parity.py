@@ -311,3 +311,62 @@ def test_cosine_matrix_odd_shapes_and_backward(pb):
     wr = W.clone().requires_grad_(True)
     (O.cosine_matrix(ur, wr) * T).sum().backward()
     assert rel_err(u.grad.cpu(), ur.grad) < 2e-3 and rel_err(w.grad.cpu(), wr.grad) < 2e-3   # fp16 cast of dS
+
+
+def test_api_conformance_dtypes_layouts(pb):
+    """Inputs the reference accepts must keep working: fp16 / fp32 / bf16, non-contiguous views, CPU tensors,
+    an embedding size that is not a multiple of 64 (zero-padded internally), and the result types."""
+    g = torch.Generator().manual_seed(12)
+    V = torch.nn.functional.normalize(torch.randn(200, 300, generator=g), dim=1).bfloat16().float()
+    A = torch.nn.functional.normalize(2.0 * V + torch.randn(200, 300, generator=g), dim=1).bfloat16().float()
+    rl, rdv, rda = O.hinge_loss_and_grads(V, A, 0.2)
+    ranks, near = O.ranks_identity(V, A)
+    for make in (lambda x: x.cuda(), lambda x: x.cuda().half(), lambda x: x.cuda().bfloat16(),
+                 lambda x: x.cuda().t().contiguous().t(), lambda x: x):
+        v = make(V).requires_grad_(True)
+        a = make(A).requires_grad_(True)
+        loss = pb.loss.TripletLoss(0.2)(v, a)
+        loss.backward()
+        assert loss.device == v.device and v.grad.shape == (200, 300) and v.grad.dtype == v.dtype
+        tol = TOL if v.dtype == torch.float32 else 6e-3          # half-precision gradients are rounded to 2^-9 / 2^-11
+        assert rel_err(loss.float().cpu(), rl) < TOL
+        assert rel_err(v.grad.float().cpu(), rdv) < tol and rel_err(a.grad.float().cpu(), rda) < tol
+        rec = pb.metrics.recall_at_n(make(V), make(A), None, n=3)
+        assert bool((((ranks < 3).float() == rec) | near).all())
+    # triplet_accuracy: dim argument and broadcasting, like F.cosine_similarity
+    a3 = torch.randn(5, 7, 64, generator=g)
+    p3 = torch.randn(5, 7, 64, generator=g)
+    n3 = torch.randn(1, 7, 64, generator=g)
+    got = pb.metrics.triplet_accuracy(a3.cuda(), p3.cuda(), n3.cuda(), dim=2)
+    assert got.shape == (5, 7) and torch.equal(got.cpu(), O.triplet_accuracy(a3, p3, n3, dim=2))
+    got = pb.metrics.triplet_accuracy(a3.cuda(), p3.cuda(), n3.cuda(), dim=1, discrete=False)
+    assert got.shape == (5, 64)
+    assert (got.cpu() - O.triplet_accuracy(a3, p3, n3, dim=1, discrete=False)).abs().max() < 2e-6
+
+
+def test_milnce_k_candidates_not_silently_wrong(pb):
+    V, A = emb(16, 4.0)
+    with pytest.raises(NotImplementedError):
+        pb.loss.MILNCELoss()(V.cuda(), torch.cat([A, A]).cuda())
+
+
+def test_install_patches_a_pig_package(pb):
+    """peppa_b200.install() over a stand-in `pig` package: the hot-path names resolve to the B200 modules."""
+    import sys
+    import types
+
+    import peppa_b200
+    pig = types.ModuleType("pig_standin")
+    util = types.ModuleType("pig_standin.util")
+    util.cosine_matrix = lambda U, V: None
+    sys.modules["pig_standin"], sys.modules["pig_standin.util"] = pig, util
+    pig.util = util
+    try:
+        peppa_b200.install(pig)
+        assert pig.loss is pb.loss and pig.metrics is pb.metrics
+        assert sys.modules["pig_standin.util"].cosine_matrix is pb.util.cosine_matrix
+        V, A = emb(32, 4.0)
+        assert pig.loss.TripletLoss(0.2)(V.cuda(), A.cuda()).item() > 0
+    finally:
+        for k in [k for k in sys.modules if k.startswith("pig_standin")]:
+            del sys.modules[k]

@@ -324,17 +324,15 @@ template <bool kRank>
 struct HingePolicyT {
     static constexpr bool kStoresF32 = false;
     using Params = HingeParams;
-    static constexpr int kColVecs = 3;  // rinv_y, thr_c = diag_col - margin, -pred(thr_c) * 2^120
+    static constexpr int kColVecs = 2;  // rinv_y, -pred(thr_c) * 2^120 with thr_c = diag_col - margin
     static constexpr bool kStoresG = true;
     float ri, rbig, kbig;
     float2 loss2, rc2, rk2;
     int dcol;
     __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
     __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
-        const float thr = valid ? (p.diag_col[col] - p.margin) : PB2_INF;
         v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
-        v[1] = thr;
-        v[2] = valid ? -(nextafterf(thr, -PB2_INF) * kBig) : -PB2_INF;
+        v[1] = valid ? -(nextafterf(p.diag_col[col] - p.margin, -PB2_INF) * kBig) : -PB2_INF;
     }
     static constexpr int kRowVecs = 4;  // rinv_x, -pred(thr_r) * 2^120, -pred(pos_thr) * 2^120, diagonal column
     __device__ static void load_row(const Params& p, const SimCommon& c, int64_t row, bool valid, float* v) {
@@ -361,8 +359,7 @@ struct HingePolicyT {
     __device__ __forceinline__ void chunk_impl(const Params& p, const TileCtx& t, int ch, int cbase,
                                                const uint32_t (&v)[32], const float* cv, OutStage& os) {
         const float4* cv4 = reinterpret_cast<const float4*>(cv);
-        const float4* ct4 = reinterpret_cast<const float4*>(cv + kColVecStride);
-        const float4* cb4 = reinterpret_cast<const float4*>(cv + 2 * kColVecStride);
+        const float4* cb4 = reinterpret_cast<const float4*>(cv + kColVecStride);
         const float2 ri2 = make_float2(ri, ri);
         const int drel = dcol - cbase;                              // diagonal position inside this chunk
         const int nvalid = t.row_valid ? t.cols_valid - cbase : 0;  // valid columns of this row's chunk
@@ -375,14 +372,13 @@ struct HingePolicyT {
         float2 rca = make_float2(0.f, 0.f), rcb = make_float2(0.f, 0.f);
         // software pipelining: the three column-vector loads of group q+1 and the REDUX of group q are in
         // flight while group q's arithmetic issues (their latencies were the top stall reasons in ncu)
-        float4 c4 = cv4[0], t4 = ct4[0], b4 = cb4[0];
+        float4 c4 = cv4[0], b4 = cb4[0];
         uint32_t tot_prev = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            float4 nc4 = c4, nt4 = t4, nb4 = b4;
+            float4 nc4 = c4, nb4 = b4;
             if (q < 7) {
                 nc4 = cv4[q + 1];
-                nt4 = ct4[q + 1];
                 nb4 = cb4[q + 1];
             }
             float2 s01 = score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y);
@@ -407,25 +403,23 @@ struct HingePolicyT {
                 rka = __fadd2_rn(rka, make_float2(fma_sat(s01.x, kBig, kbig), fma_sat(s01.y, kBig, kbig)));
                 rkb = __fadd2_rn(rkb, make_float2(fma_sat(s23.x, kBig, kbig), fma_sat(s23.y, kBig, kbig)));
             }
-            // ALU pipe: byte-packed column counts (same test as ic, as a compare)
-            const uint32_t p0 = (s01.x >= t4.x) ? 0x1u : 0u, p1 = (s01.y >= t4.y) ? 0x100u : 0u;
-            const uint32_t p2 = (s23.x >= t4.z) ? 0x10000u : 0u, p3 = (s23.y >= t4.w) ? 0x1000000u : 0u;
-            const uint32_t pkq = (p0 | p1) | (p2 | p3);
-            // column counts over the warp's 32 rows (<= 32 per byte): lanes 4q..4q+3 keep group q
+            // column counts: the four 0/1 indicators packed into 6-bit fields of one exact fp32 integer
+            // (ic0 + 64 ic1 + 4096 ic2 + 262144 ic3 < 2^19), converted once and summed over the warp's
+            // 32 rows with REDUX (<= 32 per field); lanes 4q..4q+3 keep group q
+            const uint32_t pkq = __float2uint_rz(fmaf(fmaf(ic23.y, 64.f, ic23.x), 4096.f, fmaf(ic01.y, 64.f, ic01.x)));
             if (q > 0 && (lane >> 2) == q - 1) mine = tot_prev;  // consume the previous group's REDUX
             tot_prev = __reduce_add_sync(0xffffffffu, pkq);
             const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
             packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
             packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
             c4 = nc4;
-            t4 = nt4;
             b4 = nb4;
         }
         if ((lane >> 2) == 7) mine = tot_prev;
         loss2 = __fadd2_rn(loss2, __fadd2_rn(la, lb));
         rc2 = __fadd2_rn(rc2, __fadd2_rn(rca, rcb));
         if (kRank) rk2 = __fadd2_rn(rk2, __fadd2_rn(rka, rkb));
-        const int ccnt = (int)((mine >> ((lane & 3) * 8)) & 0xffu);
+        const int ccnt = (int)((mine >> ((lane & 3) * 6)) & 0x3fu);
         if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // 0 for out-of-range columns
         if (p.has_gmat) {
             if ((ch & 1) == 0) os.begin_slab(lane);

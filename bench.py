@@ -2,21 +2,25 @@
 """Benchmark of the contrastive-scoring hot path (BASELINE.json metric: similarity pairs/sec for
 loss fwd+bwd + recall@k at 1/2/4/8 B200, as a fraction of bf16 tensor-core peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Workload (``config.workload``): ``gallery`` (default) = BASELINE config 5, the only configuration the
-metric is quoted on at 1/2/4/8 GPUs and one that fits a single B200 (2 GiB of embeddings): a
-2^20 x 2^20 audio<->video gallery, one step = symmetric hinge loss forward + gradients (dA, dV)
-AND recall@1..10 from a single pass over the similarity matrix, rows sharded over the ranks
-(strong scaling: the gallery is fixed, each rank owns N/P rows).  ``train1024`` (config 2),
-``retrieval16k`` (config 3) and ``triplets1m`` (config 4) are measured too at N=1 and reported
-under ``other_workloads`` of the same JSON line (or as the main line with --workload).
+Workloads (``config.workload``):
+  gallery (default)  BASELINE config 5, the only configuration the metric is quoted on at 1/2/4/8 GPUs and
+                     one that fits a single B200 (2 GiB of embeddings): a 2^20 x 2^20 audio<->video gallery;
+                     one step = symmetric hinge loss forward + gradients (dA, dV) AND recall@1..10 from a
+                     single pass over the similarity matrix, rows sharded over the ranks (strong scaling).
+  train1024          config 2: TripletLoss fwd+bwd at batch 1024 x 512 bf16 through the public API.
+  retrieval16k       config 3: recall_at_1_to_n(N=10) on 16384 x 16384 through the public API.
+  triplets1m         config 4: triplet_accuracy on 2^20 triplets x 512 bf16 (HBM bound).
+The last three are single-GPU workloads; with the default workload they are also measured (N=1) and
+reported under ``other_workloads`` of the same JSON line.
 
-One JSON line on stdout (rank 0).  ``value`` is timed with device-resident inputs, ``e2e`` through
-the public API with pinned-host inputs copied in and the loss/recall read back every step.
+One JSON line on stdout (rank 0).  ``value`` is timed with device-resident inputs; ``e2e`` through the
+public API with pinned-host inputs copied in and the result read back every step.  ``roofline`` is the
+kernel with the largest summed device time, timed live with CUDA events around each of its launches.
 ``--impl reference`` times the CPU port of the reference (oracle/pig_oracle.py, torch-CPU, all host
-threads) on a bounded sample of the same workload; /root/reference is pure Python and does not
-exist on the GPU box, so the oracle port is the reference arm.
+threads) on a bounded sample of the same workload; /root/reference is pure Python and does not exist on
+the GPU box, so the oracle port is the reference arm.
 """
 from __future__ import annotations
 
@@ -35,6 +39,8 @@ if ROOT not in sys.path:
 DIM = 512
 MARGIN = 0.2
 TOP_N = 10
+METRIC = {"gallery": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "train1024": "similarity pairs/sec (loss fwd+bwd)",
+          "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)"}
 
 
 # ----------------------------------------------------------------------------------- helpers
@@ -47,6 +53,25 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (GB) of one launch, from the committed ncu --set full
+    captures (profiles/r1_ncu_summary.json: 32768 x 32768 blocks / 2^20 triplets); None if unknown."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
+    key = {"sim_hinge+rank": "r1_sim_hinge", "grad_gemm": "r1_grad_gemm", "triplet_score": "r1_triplet"}.get(kernel)
+    if not key or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f).get(key, {})
+
+    def gb(s):
+        v, u = s.split()[:2]
+        return float(v) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
+    try:
+        return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+    except (KeyError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -93,25 +118,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum (GB) of one launch on a 32768 x 32768 block, from the committed
-    ncu --set full capture (profiles/r1_ncu_summary.json); None if unknown."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
-    key = {"sim_hinge+rank": "r1_sim_hinge", "sim_hinge": "r1_sim_hinge", "grad_gemm": "r1_grad_gemm"}.get(kernel)
-    if not key or not os.path.exists(p):
-        return None
-    with open(p) as f:
-        d = json.load(f).get(key, {})
-
-    def gb(s):
-        v, u = s.split()[:2]
-        return float(v) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
-    try:
-        return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
-    except (KeyError, ValueError):
-        return None
-
-
 def synth_embeddings(n, seed, device, alpha=4.0):
     """SURVEY 8(d) synthetic inputs: V = normalize(randn), A = normalize(alpha V + randn), bf16."""
     import torch
@@ -136,45 +142,117 @@ def timed(fn, steps, warmup, sync):
     return e0.elapsed_time(e1) / steps
 
 
+def measure(fn, steps, warmup, sync, device, all_max=lambda x: x):
+    """Timed region of the ``value`` leg: K steps, clocks sampled, every instrumented kernel launch timed with
+    its own CUDA events (ops.EVENT_LOG), library launch counter read on both sides."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    for _ in range(warmup):
+        fn()
+    sync()
+    ops.EVENT_LOG = []
+    l0 = lib.pb2_launch_count()
+    with ClockSampler(device.index) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        sync()
+    launches = lib.pb2_launch_count() - l0
+    ms = all_max(e0.elapsed_time(e1) / steps)
+    log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    kern = {}
+    for name, work, s, e in log:
+        k = kern.setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+        k["launches"] += 1
+        k["ms"] += s.elapsed_time(e)
+        k["work"] += work
+    return {"ms": ms, "kernels": kern, "launches": launches, "clocks": clk.summary(), "out": out}
+
+
+def roofline_of(kern, bound):
+    """Dominant kernel (largest summed device time) against the measured peak of its bound."""
+    pk = peaks()
+    if not kern:
+        return None, {}
+    name, k = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    if bound == "hbm":
+        achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s", pk["source"]
+    else:
+        achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s", pk["source"] + " (sustained)"
+    roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": ncu_traffic(name), "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1_ncu_summary.json)",
+            "peak_source": src, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"]}
+    table = {n: {"launches": v["launches"], "ms_total": v["ms"],
+                 ("gbs" if bound == "hbm" else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)) if v["ms"] else None}
+             for n, v in kern.items()}
+    return roof, table
+
+
 # ------------------------------------------------------------------------- reference (CPU) arm
-def cpu_gallery_sample(n_s, steps, warmup):
-    """Reference path on a bounded sample: TripletLoss fwd+bwd + recall_at_1_to_n(N=10) on an
-    n_s x n_s sub-gallery with the port of pig/loss.py + pig/metrics.py (torch-CPU, all threads)."""
+def cpu_sample(workload, n_s, steps, warmup):
+    """The reference's algorithm (oracle port, torch-CPU, all host threads) on a bounded sample of the
+    workload; returns (metric value, seconds per step, description of the sample)."""
     import torch
     from oracle import pig_oracle as O
-    a, v = synth_embeddings(n_s, 666, "cpu")
-    a, v = a.float(), v.float()
+    if workload == "triplets1m":
+        t = n_s * 32
+        g = torch.Generator().manual_seed(666)
+        a, p, n = (torch.randn(t, DIM, generator=g).bfloat16().float() for _ in range(3))
+        step, units, what = (lambda: O.triplet_accuracy(a, p, n)), t, f"{t} triplets x {DIM} (fp32 values of the bf16 inputs)"
+    else:
+        if workload == "train1024":
+            n_s = 1024
+        a, v = synth_embeddings(n_s, 666, "cpu")
+        a, v = a.float(), v.float()
 
-    def step():
-        vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
-        O.triplet_loss(vv, aa, MARGIN).backward()
-        O.recall_at_1_to_n(v, a, torch.eye(n_s), N=TOP_N)
+        def loss_step():
+            vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
+            O.triplet_loss(vv, aa, MARGIN).backward()
 
+        def recall_step():
+            O.recall_at_1_to_n(v, a, torch.eye(n_s), N=TOP_N)
+
+        if workload == "train1024":
+            step, what = loss_step, "the full 1024 x 1024 batch, TripletLoss fwd+bwd"
+        elif workload == "retrieval16k":
+            step, what = recall_step, f"{n_s} x {n_s} sub-gallery, recall_at_1_to_n"
+        else:
+            step, what = (lambda: (loss_step(), recall_step())), f"{n_s} x {n_s} sub-gallery, TripletLoss fwd+bwd + recall_at_1_to_n"
+        units = n_s * n_s
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return n_s * n_s / dt, dt
+    return units / dt, dt, what
+
+
+def cpu_baseline(workload, n_s):
+    import torch
+    value, dt, what = cpu_sample(workload, n_s, 1, 1)
+    return {"value": value, "unit": "triplets/s" if workload == "triplets1m" else "pairs/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{what}; reference algorithm (oracle port); {dt:.3f} s per step; host has {os.cpu_count()} cpus"}
 
 
 def run_reference(args):
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    n_s = args.cpu_sample
-    value, dt = cpu_gallery_sample(n_s, args.steps, args.warmup)
+    value, dt, what = cpu_sample(args.workload, args.cpu_sample, args.steps, args.warmup)
+    unit = "triplets/s" if args.workload == "triplets1m" else "pairs/s"
     line = {
-        "impl": "reference", "metric": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "value": value, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "gallery", "gallery": args.gallery_n, "dim": DIM, "margin": MARGIN, "top_n": TOP_N,
-                   "note": "CPU port of pig.loss.TripletLoss fwd+bwd + pig.metrics.recall_at_1_to_n on a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{n_s} x {n_s} sub-gallery of the same synthetic embeddings; host has {os.cpu_count()} cpus"},
-        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC[args.workload], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "gallery" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "dim": DIM, "margin": MARGIN, "top_n": TOP_N,
+                   "note": "CPU port of the reference (pig.loss / pig.metrics algorithms) on a bounded sample: " + what},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{what}; host has {os.cpu_count()} cpus"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
@@ -183,7 +261,6 @@ def run_reference(args):
 # ------------------------------------------------------------------------------ GPU workloads
 def bench_gallery(args, rank, world, device, sync, all_max):
     import torch
-    from peppa_b200 import _cabi, ops
     from peppa_b200.gallery import GalleryStep
     n = args.gallery_n
     assert n % world == 0
@@ -191,34 +268,7 @@ def bench_gallery(args, rank, world, device, sync, all_max):
     a_dev, v_dev = synth_embeddings(nl, 666 + rank, device)
     a_host, v_host = a_dev.cpu().pin_memory(), v_dev.cpu().pin_memory()
     step = GalleryStep(nl, DIM, margin=MARGIN, top_n=TOP_N, rank=rank, world=world, device=device)
-    lib = _cabi.lib()
-
-    def run_dev():
-        return step.run(a_dev, v_dev)
-
-    # kernel-only timing with device-resident inputs, per-kernel CUDA events for the roofline
-    for _ in range(args.warmup):
-        run_dev()
-    sync()
-    ops.EVENT_LOG = []
-    launches0 = lib.pb2_launch_count()
-    with ClockSampler(device.index) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            out = run_dev()
-        e1.record()
-        sync()
-    launches = lib.pb2_launch_count() - launches0
-    ms = all_max(e0.elapsed_time(e1) / args.steps)
-    log, ops.EVENT_LOG = ops.EVENT_LOG, None
-    kern = {}
-    for name, flops, s, e in log:
-        k = kern.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0})
-        k["launches"] += 1
-        k["ms"] += s.elapsed_time(e)
-        k["flops"] += flops
-
+    m = measure(lambda: step.run(a_dev, v_dev), args.steps, args.warmup, sync, device, all_max)
     a_in, v_in = torch.empty_like(a_dev), torch.empty_like(v_dev)
 
     def run_e2e():
@@ -228,19 +278,28 @@ def bench_gallery(args, rank, world, device, sync, all_max):
         return o["loss"].item(), o["recall"].cpu()
 
     ms_e2e = all_max(timed(run_e2e, args.steps, 1, sync))
-    res = {"ms": ms, "ms_e2e": ms_e2e, "pairs": float(n) * float(n), "kernels": kern, "launches": launches * world,
-           "clocks": clk.summary(), "h2d": 2 * n * DIM * 2, "d2h": 4 + 4 * (TOP_N + 1), "loss": out["loss"].item(),
-           "recall10": out["recall"][TOP_N].item()}
-    return res
+    roof, table = roofline_of(m["kernels"], "tensor")
+    out = m["out"]
+    return {
+        "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
+        "launches": m["launches"] * world, "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4 + 4 * (TOP_N + 1),
+        "flops_per_unit": 6.0 * DIM, "scaling": "strong",
+        "check": {"loss": out["loss"].item(), "recall_at_10": out["recall"][TOP_N].item()},
+        "config": {"workload": f"gallery (BASELINE config 5): {n} x {n} audio-video gallery, hinge loss fwd+bwd + recall@1..10 from one "
+                               "similarity pass, rows sharded over ranks", "gallery": n, "dim": DIM, "margin": MARGIN, "top_n": TOP_N,
+                   "rows_per_gpu": nl, "l2": "per-step working set (embeddings, fp16 copies, gradient-matrix blocks of 2 GiB) far exceeds the "
+                                            "126 MB L2; no flush needed",
+                   "parallelism": f"row-shard x{world}" + (" + NCCL all-gather/all-reduce/reduce-scatter" if world > 1 else "")}}
 
 
-def bench_train1024(args, device):
-    """BASELINE config 2: TripletLoss fwd+bwd at batch 1024 x 512 through the public API
-    (peppa_b200.loss.TripletLoss + autograd), replayed as a CUDA graph (the step is launch bound)."""
+def bench_train1024(args, device, sync):
+    """Config 2: TripletLoss fwd+bwd at batch 1024 x 512 bf16 through peppa_b200.loss.TripletLoss + autograd.
+    The step is launch bound (5 library kernels + 2 torch kernels), so ``value`` replays it as a CUDA graph; the
+    per-kernel events and ``e2e`` run it eagerly."""
     import torch
     from peppa_b200.loss import TripletLoss
     n = 1024
-    a, v = synth_embeddings(n, 666, device)        # bf16 leaves, bf16 gradients (config 2: "1024 x 512-d bf16")
+    a, v = synth_embeddings(n, 666, device)
     mod = TripletLoss(MARGIN)
     vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
 
@@ -251,8 +310,8 @@ def bench_train1024(args, device):
         loss.backward()
         return loss
 
-    sync = torch.cuda.synchronize
-    eager = timed(step, 20, 5, sync)
+    steps, warm = max(args.steps, 50), max(args.warmup, 5)
+    m = measure(step, steps, warm, sync, device)
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -262,38 +321,96 @@ def bench_train1024(args, device):
     torch.cuda.current_stream().wait_stream(s)
     with torch.cuda.graph(g):
         loss = step()
-    graph = timed(g.replay, 50, 5, sync)
-    return {"workload": "train1024 (config 2): TripletLoss fwd+bwd, batch 1024 x 512", "pairs_per_s_graph": n * n / graph * 1e3,
-            "ms_graph": graph, "ms_eager": eager, "frac_of_bf16_peak": 6.0 * n * n * DIM / (graph * 1e-3) / (peaks()["tf_burst"] * 1e12),
-            "loss": loss.item()}
+    ms_graph = timed(g.replay, steps, warm, sync)
+    a_host, v_host = a.cpu().pin_memory(), v.cpu().pin_memory()
+
+    def run_e2e():
+        with torch.no_grad():
+            vv.copy_(v_host, non_blocking=True)
+            aa.copy_(a_host, non_blocking=True)
+        return step().item()
+
+    ms_e2e = timed(run_e2e, steps, warm, sync)
+    roof, table = roofline_of(m["kernels"], "tensor")
+    return {
+        "units": float(n) * n, "unit": "pairs/s", "ms": ms_graph, "ms_eager": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
+        "launches": m["launches"], "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4, "flops_per_unit": 6.0 * DIM, "scaling": "weak",
+        "check": {"loss": loss.item()}, "steps_used": steps,
+        "config": {"workload": "train1024 (BASELINE config 2): TripletLoss(0.2) fwd+bwd, batch 1024 x 512 bf16, public API, CUDA-graph replay",
+                   "batch": n, "dim": DIM, "margin": MARGIN,
+                   "l2": "4 MiB working set is L2 resident by nature of the workload (one training step re-reads its own batch)"}}
 
 
-def bench_retrieval16k(args, device):
+def bench_retrieval16k(args, device, sync):
     import torch
     from peppa_b200 import metrics
     n = 16384
     a, v = synth_embeddings(n, 666, device)
-    sync = torch.cuda.synchronize
-    ms = timed(lambda: metrics.recall_at_1_to_n(v, a, None, N=TOP_N), 10, 3, sync)
-    r = metrics.recall_at_1_to_n(v, a, None, N=TOP_N)
-    return {"workload": "retrieval16k (config 3): recall_at_1_to_n, 16384 x 16384, N=10, public API incl. D2H of the result",
-            "pairs_per_s": n * n / ms * 1e3, "ms": ms, "frac_of_bf16_peak": 2.0 * n * n * DIM / (ms * 1e-3) / (peaks()["tf_burst"] * 1e12),
-            "recall_at_10": r[TOP_N].mean().item()}
+    steps, warm = max(args.steps, 10), max(args.warmup, 3)
+    m = measure(lambda: metrics._pair_ranks(v, a, None)[0], steps, warm, sync, device)
+    a_host, v_host = a.cpu().pin_memory(), v.cpu().pin_memory()
+    a_in, v_in = torch.empty_like(a), torch.empty_like(v)
+
+    def run_e2e():
+        a_in.copy_(a_host, non_blocking=True)
+        v_in.copy_(v_host, non_blocking=True)
+        return metrics.recall_at_1_to_n(v_in, a_in, None, N=TOP_N)          # CPU float32 result like the reference
+
+    ms_e2e = timed(run_e2e, steps, warm, sync)
+    r = run_e2e()
+    roof, table = roofline_of(m["kernels"], "tensor")
+    return {
+        "units": float(n) * n, "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table, "launches": m["launches"],
+        "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4 * (TOP_N + 1) * n, "flops_per_unit": 2.0 * DIM, "scaling": "weak",
+        "check": {"recall_at_10": r[TOP_N].mean().item()}, "steps_used": steps,
+        "config": {"workload": "retrieval16k (BASELINE config 3): recall_at_1_to_n(N=10), 16384 audio x 16384 video, public API", "gallery": n,
+                   "dim": DIM, "top_n": TOP_N, "l2": "32 MiB of embeddings are L2 resident (as in the real evaluation, which ranks one gallery)"}}
 
 
-def bench_triplets1m(args, device):
+def bench_triplets1m(args, device, sync):
     import torch
-    from peppa_b200 import ops
+    from peppa_b200 import metrics, ops
     t = 1 << 20
     g = torch.Generator(device=device).manual_seed(666)
     a, p, n = (torch.randn(t, DIM, generator=g, device=device).bfloat16() for _ in range(3))
-    sync = torch.cuda.synchronize
-    ms = timed(lambda: ops.triplet_score(a, p, n), 20, 3, sync)     # 3.2 GB of inputs per call > 126 MB L2
-    byt = t * (3 * DIM * 2 + 4)
-    return {"workload": "triplets1m (config 4): triplet_accuracy, 2^20 triplets x 512 bf16", "triplets_per_s": t / ms * 1e3, "ms": ms,
-            "roofline": {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
-                         "frac": byt / ms / 1e6 / peaks()["hbm_gbs"], "traffic": 3.2286, "algorithmic": byt / 1e9,
-                         "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1_ncu_summary.json)"}}
+    steps, warm = max(args.steps, 20), max(args.warmup, 3)
+    m = measure(lambda: ops.triplet_score(a, p, n), steps, warm, sync, device)
+    hosts = [x.cpu().pin_memory() for x in (a, p, n)]
+    ins = [torch.empty_like(x) for x in (a, p, n)]
+
+    def run_e2e():
+        for d, h in zip(ins, hosts):
+            d.copy_(h, non_blocking=True)
+        return metrics.triplet_accuracy(*ins).float().mean().item()
+
+    ms_e2e = timed(run_e2e, 3, 1, sync)
+    roof, table = roofline_of(m["kernels"], "hbm")
+    return {
+        "units": float(t), "unit": "triplets/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table, "launches": m["launches"],
+        "clocks": m["clocks"], "h2d": 3 * t * DIM * 2, "d2h": 4, "flops_per_unit": None, "scaling": "weak",
+        "check": {"mean_accuracy": m["out"].mean().item()}, "steps_used": steps,
+        "config": {"workload": "triplets1m (BASELINE config 4): triplet_accuracy on 2^20 triplets x 512 bf16", "triplets": t, "dim": DIM,
+                   "bytes_per_triplet": 3 * DIM * 2 + 4, "l2": "3.2 GB of inputs per step exceed the 126 MB L2; no flush needed"}}
+
+
+def line_from(res, args, world, workload):
+    pk = peaks()
+    value = res["units"] / (res["ms"] * 1e-3)
+    line = {
+        "metric": METRIC[workload], "value": value, "unit": res["unit"], "n_gpus": world, "steps": res.get("steps_used", args.steps),
+        "warmup": args.warmup, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": res["config"], "roofline": res["roofline"], "kernels": res["kernels"],
+        "clocks": res["clocks"],
+        "e2e": {"value": res["units"] / (res["ms_e2e"] * 1e-3), "unit": res["unit"], "h2d_bytes_per_step": res["h2d"],
+                "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["ms_e2e"]},
+        "gpu_launches": res["launches"], "check": res["check"],
+    }
+    if res["flops_per_unit"]:
+        line["frac_of_bf16_peak"] = res["flops_per_unit"] * value / world / (pk["tf_sustained"] * 1e12)
+        line["frac_of_bf16_peak_note"] = "algorithmic flops (SURVEY 8d) per GPU / measured sustained cuBLAS bf16 rate"
+    if "ms_eager" in res:
+        line["ms_per_step_eager"] = res["ms_eager"]
+    return line
 
 
 def main():
@@ -302,7 +419,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gallery", choices=["gallery"])
+    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m"])
     ap.add_argument("--gallery-n", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-extras", action="store_true")
@@ -337,42 +454,25 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    res = bench_gallery(args, rank, world, device, sync, all_max)
-    pk = peaks()
-    value = res["pairs"] / (res["ms"] * 1e-3)
-    # dominant kernel = the one with the largest summed device time on rank 0
-    dom_name, dom = max(res["kernels"].items(), key=lambda kv: kv[1]["ms"])
-    achieved = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
-    line = {
-        "metric": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"gallery (BASELINE config 5): {args.gallery_n} x {args.gallery_n} audio-video gallery, hinge loss "
-                               "fwd+bwd + recall@1..10 from one similarity pass, rows sharded over ranks",
-                   "gallery": args.gallery_n, "dim": DIM, "margin": MARGIN, "top_n": TOP_N, "rows_per_gpu": args.gallery_n // world,
-                   "l2": "inputs (2 GiB bf16 + 4 GiB fp32 partials per step) exceed the 126 MB L2; no flush needed",
-                   "parallelism": f"row-shard x{world}" + (" + NCCL all-gather/all-reduce/reduce-scatter" if world > 1 else "")},
-        "frac_of_bf16_peak": 6.0 * res["pairs"] * DIM / (res["ms"] * 1e-3) / world / (pk["tf_sustained"] * 1e12),
-        "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"], "traffic": ncu_traffic(dom_name),
-                     "traffic_unit": "GB per launch (32768 x 32768 block, ncu --set full, profiles/r1_ncu_summary.json)",
-                     "peak_source": pk["source"] + " (sustained)", "launches": dom["launches"]},
-        "kernels": {k: {"launches": v["launches"], "ms_total": v["ms"], "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None}
-                    for k, v in res["kernels"].items()},
-        "clocks": res["clocks"],
-        "e2e": {"value": res["pairs"] / (res["ms_e2e"] * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": res["h2d"],
-                "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["ms_e2e"]},
-        "gpu_launches": res["launches"],
-        "check": {"loss": res["loss"], "recall_at_10": res["recall10"]},
-    }
+    single = {"train1024": bench_train1024, "retrieval16k": bench_retrieval16k, "triplets1m": bench_triplets1m}
+    if args.workload == "gallery":
+        line = line_from(bench_gallery(args, rank, world, device, sync, all_max), args, world, "gallery")
+    else:
+        # single-GPU workloads: every rank of a torchrun launch measures its own replica, rank 0 reports
+        line = line_from(single[args.workload](args, device, torch.cuda.synchronize), args, 1, args.workload)
+        line["n_gpus"] = world
+        line["value"] *= world
+        line["note"] = "replicas only: this workload does not shard; N independent replicas" if world > 1 else None
     if world == 1 and rank == 0:
-        import torch as _t
-        cpu_value, cpu_dt = cpu_gallery_sample(args.cpu_sample, 1, 1)
-        line["cpu_baseline"] = {"value": cpu_value, "unit": "pairs/s", "cores": _t.get_num_threads(), "kind": "port",
-                                "sample": f"{args.cpu_sample} x {args.cpu_sample} sub-gallery, reference algorithm (oracle port) fwd+bwd + "
-                                          f"recall_at_1_to_n; {cpu_dt:.2f} s per step; host has {os.cpu_count()} cpus"}
-        if not args.no_extras:
-            line["other_workloads"] = [bench_train1024(args, device), bench_retrieval16k(args, device), bench_triplets1m(args, device)]
+        line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample)
+        if args.workload == "gallery" and not args.no_extras:
+            line["other_workloads"] = []
+            for w, fn in single.items():
+                o = line_from(fn(args, device, torch.cuda.synchronize), args, 1, w)
+                line["other_workloads"].append({k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e",
+                                                                  "gpu_launches", "check") if k in o}
+                                               | ({"frac_of_bf16_peak": o["frac_of_bf16_peak"]} if "frac_of_bf16_peak" in o else {})
+                                               | ({"ms_per_step_eager": o["ms_per_step_eager"]} if "ms_per_step_eager" in o else {}))
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -252,9 +252,10 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
         check(lib.pb2_hinge_prep(_ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0), _ptr(rv), _ptr(ra), _ptr(diag),
                                  _ptr(halves[0]), _ptr(halves[1]), _ptr(cnts[0]), _ptr(cnts[1]), _ptr(part), n_part, st),
               "hinge_prep")
-        check(lib.pb2_sim_hinge(_ptr(vb), _ptr(ab), _ptr(rv), _ptr(ra), _ptr(diag), _ptr(diag), n, n, 0, 0, d, vb.stride(0),
-                                ab.stride(0), float(margin), _ptr(part), -n_part, _ptr(cnts[0]), _ptr(cnts[1]), _ptr(g), ld,
-                                _ptr(None), _ptr(None), st), "sim_hinge")
+        with _timed("sim_hinge", 2.0 * n * n * d, dev):
+            check(lib.pb2_sim_hinge(_ptr(vb), _ptr(ab), _ptr(rv), _ptr(ra), _ptr(diag), _ptr(diag), n, n, 0, 0, d,
+                                    vb.stride(0), ab.stride(0), float(margin), _ptr(part), -n_part, _ptr(cnts[0]),
+                                    _ptr(cnts[1]), _ptr(g), ld, _ptr(None), _ptr(None), st), "sim_hinge")
         check(lib.pb2_grad_gemm(_ptr(g), PB2_F16, n, n, ld, 0, _ptr(halves[1]), PB2_F16, d, d, 1.0, 0, _ptr(pbuf[0]), d, st),
               "grad_gemm")
         check(lib.pb2_grad_gemm(_ptr(g), PB2_F16, n, n, ld, 1, _ptr(halves[0]), PB2_F16, d, d, 1.0, 0, _ptr(pbuf[1]), d, st),
@@ -318,7 +319,7 @@ def triplet_score(anchor, positive, negative, ia=None, ip=None, in_=None, discre
     for m in (positive, negative):
         if m.shape[0] > 1 and m.stride(0) != ld:
             raise ValueError("triplet_score: operands must share a leading dimension")
-    with torch.cuda.device(anchor.device):
+    with torch.cuda.device(anchor.device), _timed("triplet_score", float(t) * (3 * d * anchor.element_size() + 4), anchor.device):
         check(_cabi.lib().pb2_triplet_score(_ptr(anchor), _ptr(positive), _ptr(negative), _ptr(ia), _ptr(ip), _ptr(in_), t, d,
                                             ld, code, int(bool(discrete)), _ptr(out), _stream(anchor.device)),
               "triplet_score")

@@ -162,6 +162,13 @@ int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const v
                       const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,
                       float* loss_out, void* d_v, void* d_a, int out_dtype, void* stream);
 
+/* The five launches above behind one call (one FFI crossing per training step): workspace is a 256-byte
+ * aligned device buffer of pb2_hinge_step_workspace(n, dim) bytes; n <= 32768 (one gradient-matrix block). */
+int64_t pb2_hinge_step_workspace(int64_t n, int dim);
+int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
+                   void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a, int out_dtype,
+                   void* stream);
+
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
                       float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);

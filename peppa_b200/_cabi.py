@@ -43,6 +43,8 @@ SIGNATURES = {
     "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
     "pb2_hinge_prep": [_p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
+    "pb2_hinge_step_workspace": [_i64, _i],
+    "pb2_hinge_step": [_p, _p, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],
     "pb2_rows_scale_f16": [_p, _p, _i64, _i, _i64, _p, _i64, _p],
     "pb2_milnce_finish": [_p, _i64, _p, _i64, _i, _i64, _f, _p, _p, _i64, _p],
     "pb2_sum_partials": [_p, _i, _f, _p, _p],
@@ -50,7 +52,7 @@ SIGNATURES = {
     "pb2_milnce_loss": [_p, _p, _p, _i64, _p, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
 }
-_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong}
+_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64}
 # test hooks, not part of the public header
 _DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_flags": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 

@@ -1,0 +1,80 @@
+// pb2_hinge_step: the whole TripletLoss forward + gradients of one training step (pig/models.py:262 ->
+// pig/loss.py:33-48 + autograd) as ONE C call = five kernel launches on the caller's stream:
+//   hinge_prep -> sim_hinge (tcgen05, fused loss/counts/gradient matrix) -> grad_gemm x2 -> hinge_finish2.
+// At batch ~1k the step is launch bound; one call keeps the host side to a single FFI crossing and the
+// scratch in one caller-provided workspace.
+#include <cuda_fp16.h>
+
+#include "host_util.h"
+#include "peppa_b200.h"
+
+namespace {
+constexpr int64_t kAlign = 256;
+int64_t up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+struct Layout {
+    int64_t rinv_v, rinv_a, diag, part, row_cnt, col_cnt, vh, ah, g, pv, pa, total, ld_g;
+    int n_part;
+};
+Layout layout(int64_t n, int dim) {
+    Layout L;
+    L.n_part = pb2_sim_grid();
+    L.ld_g = (n + 63) / 64 * 64;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t at = o;
+        o += up(bytes);
+        return at;
+    };
+    L.rinv_v = take(n * 4);
+    L.rinv_a = take(n * 4);
+    L.diag = take(n * 4);
+    L.part = take((int64_t)L.n_part * 4);
+    L.row_cnt = take(n * 4);
+    L.col_cnt = take(n * 4);
+    L.vh = take(n * dim * 2);
+    L.ah = take(n * dim * 2);
+    L.g = take(n * L.ld_g * 2);
+    L.pv = take(n * dim * 4);
+    L.pa = take(n * dim * 4);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+extern "C" int64_t pb2_hinge_step_workspace(int64_t n, int dim) { return n > 0 && dim > 0 ? layout(n, dim).total : 0; }
+
+extern "C" int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
+                              void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a,
+                              int out_dtype, void* stream) {
+    using pb2::set_error;
+    if (n <= 0) return set_error(PB2_ERR_ARG, "hinge_step: empty batch");
+    if (!v || !a || !workspace || !loss_out || !d_v || !d_a) return set_error(PB2_ERR_ARG, "hinge_step: null");
+    if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "hinge_step: dim must be a positive multiple of 64");
+    if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0)
+        return set_error(PB2_ERR_ARG, "hinge_step: workspace must be 256-byte aligned");
+    const Layout L = layout(n, dim);
+    if (workspace_bytes < L.total) return set_error(PB2_ERR_ARG, "hinge_step: workspace too small");
+    char* w = static_cast<char*>(workspace);
+    float* rinv_v = reinterpret_cast<float*>(w + L.rinv_v);
+    float* rinv_a = reinterpret_cast<float*>(w + L.rinv_a);
+    float* diag = reinterpret_cast<float*>(w + L.diag);
+    float* part = reinterpret_cast<float*>(w + L.part);
+    int32_t* row_cnt = reinterpret_cast<int32_t*>(w + L.row_cnt);
+    int32_t* col_cnt = reinterpret_cast<int32_t*>(w + L.col_cnt);
+    void* vh = w + L.vh;
+    void* ah = w + L.ah;
+    void* g = w + L.g;
+    float* pv = reinterpret_cast<float*>(w + L.pv);
+    float* pa = reinterpret_cast<float*>(w + L.pa);
+    int rc = pb2_hinge_prep(v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part, stream);
+    if (rc) return rc;
+    rc = pb2_sim_hinge(v, a, rinv_v, rinv_a, diag, diag, n, n, 0, 0, dim, ldv, lda, margin, part, -L.n_part, row_cnt,
+                       col_cnt, g, L.ld_g, nullptr, nullptr, stream);
+    if (rc) return rc;
+    rc = pb2_grad_gemm(g, PB2_F16, n, n, L.ld_g, 0, ah, PB2_F16, dim, dim, 1.0f, 0, pv, dim, stream);
+    if (rc) return rc;
+    rc = pb2_grad_gemm(g, PB2_F16, n, n, L.ld_g, 1, vh, PB2_F16, dim, dim, 1.0f, 0, pa, dim, stream);
+    if (rc) return rc;
+    return pb2_hinge_finish2(pv, pa, v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, part, L.n_part, margin,
+                             1.0f / ((float)n * (float)n), loss_out, d_v, d_a, out_dtype, stream);
+}

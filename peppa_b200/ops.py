@@ -229,41 +229,31 @@ def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
     return grad
 
 
+_STEP_WORKSPACE = {}      # (device, n, d) -> uint8 workspace, reused across steps (stream-ordered reuse)
+
+
 def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
-    """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768) in five launches:
-    prep, fused similarity/hinge pass, two gradient GEMMs, finish.  Returns (loss 0-d fp32, grads [2, n, d]
-    in ``grad_dtype``: dV then dA)."""
+    """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768): one C call, five
+    launches (prep, fused similarity/hinge pass, two gradient GEMMs, finish).  Returns (loss 0-d fp32,
+    grads [2, n, d] in ``grad_dtype``: dV then dA)."""
     n, d = vb.shape
     dev = vb.device
     lib = _cabi.lib()
-    f32, i32 = torch.float32, torch.int32
-    n_part = sim_grid(dev)
-    stats = torch.empty(3, n, dtype=f32, device=dev)              # rinv_v | rinv_a | diag
-    cnts = torch.empty(2, n, dtype=i32, device=dev)               # row_cnt | col_cnt
-    part = torch.empty(n_part, dtype=f32, device=dev)
-    halves = torch.empty(2, n, d, dtype=torch.float16, device=dev)
-    g, ld = gmat_alloc(n, n, dev)
-    pbuf = torch.empty(2, n, d, dtype=f32, device=dev)
+    key = (dev, n, d)
+    ws = _STEP_WORKSPACE.get(key)
+    if ws is None or torch.cuda.is_current_stream_capturing():
+        with torch.cuda.device(dev):
+            ws = torch.empty(int(lib.pb2_hinge_step_workspace(n, d)), dtype=torch.uint8, device=dev)
+        if not torch.cuda.is_current_stream_capturing():
+            if len(_STEP_WORKSPACE) > 8:
+                _STEP_WORKSPACE.clear()
+            _STEP_WORKSPACE[key] = ws
     grads = torch.empty(2, n, d, dtype=grad_dtype, device=dev)
-    loss = torch.empty((), dtype=f32, device=dev)
-    rv, ra, diag = stats[0], stats[1], stats[2]
-    with torch.cuda.device(dev):
-        st = _stream(dev)
-        check(lib.pb2_hinge_prep(_ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0), _ptr(rv), _ptr(ra), _ptr(diag),
-                                 _ptr(halves[0]), _ptr(halves[1]), _ptr(cnts[0]), _ptr(cnts[1]), _ptr(part), n_part, st),
-              "hinge_prep")
-        with _timed("sim_hinge", 2.0 * n * n * d, dev):
-            check(lib.pb2_sim_hinge(_ptr(vb), _ptr(ab), _ptr(rv), _ptr(ra), _ptr(diag), _ptr(diag), n, n, 0, 0, d,
-                                    vb.stride(0), ab.stride(0), float(margin), _ptr(part), -n_part, _ptr(cnts[0]),
-                                    _ptr(cnts[1]), _ptr(g), ld, _ptr(None), _ptr(None), st), "sim_hinge")
-        check(lib.pb2_grad_gemm(_ptr(g), PB2_F16, n, n, ld, 0, _ptr(halves[1]), PB2_F16, d, d, 1.0, 0, _ptr(pbuf[0]), d, st),
-              "grad_gemm")
-        check(lib.pb2_grad_gemm(_ptr(g), PB2_F16, n, n, ld, 1, _ptr(halves[0]), PB2_F16, d, d, 1.0, 0, _ptr(pbuf[1]), d, st),
-              "grad_gemm")
-        check(lib.pb2_hinge_finish2(_ptr(pbuf[0]), _ptr(pbuf[1]), _ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0),
-                                    _ptr(rv), _ptr(ra), _ptr(diag), _ptr(cnts[0]), _ptr(cnts[1]), _ptr(part), n_part,
-                                    float(margin), 1.0 / float(n) ** 2, _ptr(loss), _ptr(grads[0]), _ptr(grads[1]),
-                                    _DTYPE_CODE[grad_dtype], st), "hinge_finish2")
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("hinge_step (5 kernels)", 6.0 * n * n * d, dev):
+        check(lib.pb2_hinge_step(_ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws), ws.numel(),
+                                 _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), _DTYPE_CODE[grad_dtype], _stream(dev)),
+              "hinge_step")
     return loss, grads
 
 

@@ -88,6 +88,11 @@ class ClockSampler:
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (NVML init) contends with the CUDA driver for ~100 ms: let it finish and
+            # deliver its first sample BEFORE the timed region starts
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 2.0:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
         return self
@@ -104,7 +109,8 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[1:] if len(self.rows) > 2 else self.rows      # the first sample predates the timed region
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))

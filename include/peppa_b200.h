@@ -118,6 +118,10 @@ int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_x, const fl
 int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,
                   int accumulate, void* stream);
 
+/* out[i] = log sum_k exp(parts[k * n + i]) (natural log): the cross-rank merge of column log-sum-exp
+ * partials of a row-sharded gallery (each rank holds the LSE over its own rows). */
+int pb2_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream);
+
 /* MIL-NCE gradient matrix: gmat[i,j] = fp16( (exp(s_ij - den_row[i]) + exp(s_ij - den_col[j])) * 2^13 ). */
 int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* den_row,
                      const float* den_col, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,

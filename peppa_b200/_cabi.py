@@ -38,6 +38,7 @@ SIGNATURES = {
     "pb2_sim_lse_parts": [_i64],
     "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _p, _p],
     "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
+    "pb2_lse_combine": [_p, _i, _i64, _p, _p],
     "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_grad_gemm": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p],
     "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
@@ -54,7 +55,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64}
 # test hooks, not part of the public header
-_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_flags": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
+_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 
 _lib = None
 

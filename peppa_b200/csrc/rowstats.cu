@@ -124,6 +124,19 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
     lse[r] = v;
 }
 
+// out[i] = log sum_k exp(parts[k, i]) (natural log): merges per-rank column log-sum-exp partials
+__global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ parts, int n_parts, int64_t n,
+                                                          float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = kNegInf;
+    for (int k = 0; k < n_parts; ++k) m = fmaxf(m, parts[(int64_t)k * n + i]);
+    float s = 0.f;
+    if (m > kNegInf)
+        for (int k = 0; k < n_parts; ++k) s += expf(parts[(int64_t)k * n + i] - m);
+    out[i] = (m > kNegInf) ? m + logf(s) : kNegInf;
+}
+
 // fixed-order single-block sum -> deterministic
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ p, int n, float alpha,
                                                             float* __restrict__ out) {
@@ -566,6 +579,13 @@ extern "C" int pb2_lse_merge(const float* part_max, const float* part_sum, int n
     lse_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_max, part_sum, n_parts,
                                                                                       rows, lse, accumulate);
     return check_launch("lse_merge");
+}
+
+extern "C" int pb2_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!parts || !out || n_parts <= 0) return set_error(PB2_ERR_ARG, "lse_combine: bad arguments");
+    lse_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(parts, n_parts, n, out);
+    return check_launch("lse_combine");
 }
 
 extern "C" int pb2_sum_partials(const float* partials, int n, float alpha, float* out, void* stream) {

@@ -303,7 +303,6 @@ struct HingeParams {
     int has_gmat;
     const float* pos_thr;   // kRank only: rank threshold of the diagonal score
     int32_t* rank;          // kRank only
-    int dbg;                // bring-up knob (pb2_debug_flags): bit0 skip REDUX/col atomics, bit1 skip tmem wait cost probe
 };
 
 // kRank additionally counts, per row, the columns closer than the diagonal (recall@k of the same
@@ -863,7 +862,6 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
 }
 
 static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
-static int g_dbg_flags = 0;  // bring-up knob (pb2_debug_flags)
 
 template <class Policy>
 static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
@@ -896,10 +894,6 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
 using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
-extern "C" int pb2_debug_flags(int flags) {
-    g_dbg_flags = flags;
-    return PB2_OK;
-}
 extern "C" int pb2_debug_force_bn(int bn) {
     g_force_bn = (bn == 64 || bn == 128 || bn == 192 || bn == 256) ? bn : 0;
     return PB2_OK;
@@ -961,7 +955,7 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
         if (rc) return rc;
     }
     HingeParams pp{diag_row, diag_col, row_offset, col_offset, margin,   loss_partial,
-                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank, g_dbg_flags};
+                   row_cnt,  col_cnt,  gmat ? 1 : 0, pos_thr, rank};
     OutMatrix om;
     om.ptr = gmat;
     om.ld = ld_g;

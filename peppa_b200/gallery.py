@@ -15,6 +15,12 @@ columns are ALL video clips:
 The loss is symmetric in (V, A) (pig/loss.py:41-48 adds the row and the column hinge), so
 ``contrastive(cosine_matrix(A, V))`` equals the reference's ``TripletLoss(V, A)``; the gradients are
 returned under their own names.  With world_size == 1 no collective is issued.
+
+``loss="milnce"`` runs pig/loss.py:13-26 (MILNCELoss, K = 1, optional temperature) over the same sharding:
+row log-sum-exp of the local strip is complete locally; the column log-sum-exp is a partial per rank
+(over its own rows) and is merged across ranks (all-gather of the [N] partials + pb2_lse_combine); the
+backward recomputes the strip, writes the fp16 gradient-matrix blocks and reduce-scatters dV like the
+hinge path.  (No recall in this mode.)
 """
 from __future__ import annotations
 
@@ -34,7 +40,11 @@ class GalleryStep:
     None for the default group); ``world == 1`` needs no initialised process group at all."""
 
     def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
-                 group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None):
+                 group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None,
+                 loss: str = "hinge", temperature: float = 1.0):
+        if loss not in ("hinge", "milnce"):
+            raise ValueError("loss must be 'hinge' or 'milnce'")
+        self.loss, self.inv_tau = loss, 1.0 / float(temperature)
         # ``backend`` exists for the world_size-2 gloo tests of the orchestration on CPU boxes: they
         # inject an emulation of the kernel entry points built from the oracle.  The product never
         # passes it; the default is the CUDA ops module and there is no automatic selection.
@@ -78,6 +88,8 @@ class GalleryStep:
         (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
         ([top_n + 1] fp32: global recall@n, row 0 == 0) and the local int32 ``ranks``."""
         import torch.distributed as dist
+        if self.loss == "milnce":
+            return self._run_milnce(a_loc, v_loc)
         ops = self.ops
         nl, n, dev = self.n_local, self.n_total, self.device
         r0g = self.rank * nl                                  # global id of the first local row
@@ -135,4 +147,63 @@ class GalleryStep:
             p_v_loc = self.p_v_loc if self.world > 1 else self.p_v
             out["dA"] = ops.hinge_finish(self.p_a, a_loc, v_loc, ra, rv, self.row_cnt, cc, inv_n2)
             out["dV"] = ops.hinge_finish(p_v_loc, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
+        return out
+
+    def _run_milnce(self, a_loc, v_loc):
+        import torch.distributed as dist
+        ops = self.ops
+        nl, n, dev, inv_tau = self.n_local, self.n_total, self.device, self.inv_tau
+        r0g = self.rank * nl
+        if self.world > 1:
+            self._all_gather(self.v_full, v_loc)
+            v_full = self.v_full
+        else:
+            v_full = v_loc
+        rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
+        lse_row = lse_col = None
+        for (c0, c1) in cblocks:      # x = A_loc V^T / tau: rows complete locally
+            lse_row = ops.sim_lse_rows(a_loc, v_full[c0:c1], scale=inv_tau, lse=lse_row)
+        for (r0, r1) in rblocks:      # columns: log-sum-exp over THIS rank's rows only
+            lse_col = ops.sim_lse_rows(v_full, a_loc[r0:r1], scale=inv_tau, lse=lse_col)
+        if self.world > 1:
+            parts = torch.empty(self.world, n, dtype=torch.float32, device=dev)
+            self._all_gather(parts.view(-1), lse_col)
+            lse_col = ops.lse_combine(parts)                  # cross-rank merge of the column statistics
+            lse_row_full = torch.empty(n, dtype=torch.float32, device=dev)
+            self._all_gather(lse_row_full, lse_row)
+        else:
+            lse_row_full = lse_row
+        diag = ops.pair_dot(a_loc, v_loc)
+        if inv_tau != 1.0:
+            diag = diag * inv_tau
+        mean_loc, den_loc = ops.milnce_loss(lse_row, lse_col[r0g:r0g + nl].contiguous(), diag)
+        loss = mean_loc * float(nl)
+        if self.world > 1:
+            dist.all_reduce(loss, group=self.group)
+        out = {"loss": loss / float(n), "recall": None, "ranks": None, "dA": None, "dV": None}
+        if not self.with_grad:
+            return out
+        if self.world > 1:
+            _, den_full = ops.milnce_loss(lse_row_full, lse_col, torch.zeros(n, dtype=torch.float32, device=dev))
+        else:
+            den_full = den_loc
+        ah, vh = ops.rows_scale_f16(a_loc), ops.rows_scale_f16(v_full)
+        acc_a, acc_v = len(cblocks) > 1, len(rblocks) > 1
+        if acc_a:
+            self.p_a.zero_()
+        if acc_v:
+            self.p_v.zero_()
+        for (r0, r1) in rblocks:
+            for (c0, c1) in cblocks:
+                ops.sim_lse_grad(a_loc[r0:r1], v_full[c0:c1], den_loc[r0:r1], den_full[c0:c1], self.gmat, self.ld_g,
+                                 scale=inv_tau)
+                ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vh[c0:c1], transpose=False, out=self.p_a[r0:r1],
+                              accumulate=acc_a)
+                ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True, out=self.p_v[c0:c1],
+                              accumulate=acc_v)
+        if self.world > 1:
+            self._reduce_scatter(self.p_v_loc, self.p_v)
+        p_v_loc = self.p_v_loc if self.world > 1 else self.p_v
+        out["dA"] = ops.milnce_finish(self.p_a, v_loc, inv_tau / float(n))
+        out["dV"] = ops.milnce_finish(p_v_loc, a_loc, inv_tau / float(n))
         return out

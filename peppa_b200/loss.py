@@ -100,7 +100,7 @@ class _HingeFn(torch.autograd.Function):
 
 class _MilNceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, V, A):
+    def forward(ctx, V, A, inv_tau):
         if V.dim() != 2 or A.dim() != 2:
             raise RuntimeError("MILNCELoss expects 2-D V and A")
         if A.shape[0] != V.shape[0]:
@@ -115,9 +115,11 @@ class _MilNceFn(torch.autograd.Function):
         blocks = _blocks(n, _MAX_BLOCK)
         lse_row = lse_col = None
         for (c0, c1) in blocks:   # x = V A^T: row LSE over audio columns, column LSE = row LSE of A V^T
-            lse_row = ops.sim_lse_rows(vb, ab[c0:c1], lse=lse_row)
-            lse_col = ops.sim_lse_rows(ab, vb[c0:c1], lse=lse_col)
+            lse_row = ops.sim_lse_rows(vb, ab[c0:c1], scale=inv_tau, lse=lse_row)
+            lse_col = ops.sim_lse_rows(ab, vb[c0:c1], scale=inv_tau, lse=lse_col)
         diag = ops.pair_dot(vb, ab)
+        if inv_tau != 1.0:
+            diag = diag * inv_tau
         loss, den = ops.milnce_loss(lse_row, lse_col, diag)
         if need_grad:
             acc = len(blocks) > 1
@@ -128,11 +130,11 @@ class _MilNceFn(torch.autograd.Function):
             for (r0, r1) in blocks:
                 for (c0, c1) in blocks:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den[c0:c1], g, ld)
+                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den[c0:c1], g, ld, scale=inv_tau)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
-            dV = ops.milnce_finish(pv, ab, 1.0 / n)
-            dA = ops.milnce_finish(pa, vb, 1.0 / n)
+            dV = ops.milnce_finish(pv, ab, inv_tau / n)
+            dA = ops.milnce_finish(pa, vb, inv_tau / n)
             ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
             ctx.meta = (V.dtype, V.device, A.dtype, A.device)
         return loss.to(V.device)
@@ -144,15 +146,18 @@ class _MilNceFn(torch.autograd.Function):
         go = grad_out.to(device=dV.device, dtype=torch.float32)
         gV = (dV * go).to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
         gA = (dA * go).to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
-        return gV, gA
+        return gV, gA, None
 
 
 class MILNCELoss(torch.nn.Module):
     """The loss implemented is: log(pos/(2 * pos + neg)) = log(pos/(pos + neg/2)) - log(2)
-    (pig/loss.py:5-26; MIL-NCE of Miech et al. with one candidate per clip)."""
+    (pig/loss.py:5-26; MIL-NCE of Miech et al. with one candidate per clip).
 
-    def __init__(self):
+    ``temperature`` is an extension (default 1.0 = the reference, which has none): logits are divided by it."""
+
+    def __init__(self, temperature=1.0):
         super(MILNCELoss, self).__init__()
+        self.temperature = float(temperature)
 
     def forward(self, V, A):
         """Returns MIL-NCE loss.
@@ -160,7 +165,7 @@ class MILNCELoss(torch.nn.Module):
            V: Tensor of embeddings (e.g. video)
            A: Tensor of embeddings (e.g. audio)
         """
-        return _MilNceFn.apply(V, A)
+        return _MilNceFn.apply(V, A, 1.0 / self.temperature)
 
 
 class TripletLoss(torch.nn.Module):

@@ -179,6 +179,15 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
     return lse
 
 
+def lse_combine(parts):
+    """parts [P, n] fp32 natural-log partial LSEs -> [n] log-sum-exp over P."""
+    p_, n = parts.shape
+    out = torch.empty(n, dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        check(_cabi.lib().pb2_lse_combine(_ptr(parts), p_, n, _ptr(out), _stream(parts.device)), "lse_combine")
+    return out
+
+
 def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, scale=1.0):
     r, c = x.shape[0], y.shape[0]
     with torch.cuda.device(x.device):

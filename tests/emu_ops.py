@@ -24,6 +24,13 @@ def sim_diag(x, y, rinv_x=None, rinv_y=None):
     return s, 1.0 - s
 
 
+def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False, want_thr=False):
+    s = (x.float() * y.float()).sum(dim=1)
+    if rinv_x is not None:
+        s = s * rinv_x * rinv_y
+    return s
+
+
 def rows_scale_f16(x, rinv=None):
     xf = x.float()
     return (xf * rinv[:, None] if rinv is not None else xf).half()
@@ -76,3 +83,28 @@ def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_
     g = p + (-(row_cnt + col_cnt).float() * rinv_y)[:, None] * y.float()
     xh = x.float() * rinv_x[:, None]
     return coef_host * rinv_x[:, None] * (g - xh * (g * xh).sum(dim=1, keepdim=True))
+
+
+# ---- MIL-NCE entry points (natural-log statistics, fp16 gradient matrix scaled by 2^13) ---------------
+def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
+    s = torch.logsumexp((x.float() @ y.float().T) * scale, dim=1)
+    return s if lse is None else torch.logaddexp(lse, s)
+
+
+def lse_combine(parts):
+    return torch.logsumexp(parts, dim=0)
+
+
+def milnce_loss(lse_row, lse_col, diag):
+    den = torch.logaddexp(lse_row, lse_col)
+    return (den - diag).mean(), den
+
+
+def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, scale=1.0):
+    s = (x.float() @ y.float().T) * scale
+    r, c = s.shape
+    gmat[:r, :c] = ((torch.exp(s - den_row[:, None]) + torch.exp(s - den_col[None, :])) * 8192.0).half()
+
+
+def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
+    return coef_host * (p / 8192.0 - y.float())

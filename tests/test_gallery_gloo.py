@@ -21,6 +21,25 @@ def _emb(n, alpha, d=128, seed=666):
     return V.bfloat16(), A.bfloat16()
 
 
+def _worker_milnce(rank, world, port, n_local, block, outdir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu_ops
+        from peppa_b200.gallery import GalleryStep
+        V, A = _emb(n_local * world, 4.0)
+        sl = slice(rank * n_local, (rank + 1) * n_local)
+        step = GalleryStep(n_local, V.shape[1], rank=rank, world=world, device="cpu", block=block, backend=emu_ops,
+                           loss="milnce", temperature=0.5)
+        out = step.run(A[sl].contiguous(), V[sl].contiguous())
+        torch.save((rank, out["loss"].item(), out["dA"].clone(), out["dV"].clone()), os.path.join(outdir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, n_local, block, outdir):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
@@ -81,3 +100,31 @@ def test_two_rank_gallery_matches_single_process_oracle(n_local, block, tmp_path
     assert recall[0] == 0 and torch.equal(res[0][2], res[1][2])
     for k in (1, 5, 10):
         assert abs(recall[k].item() - (granks < k).float().mean().item()) < 1e-6
+
+
+@pytest.mark.parametrize("n_local,block", [(72, 32768), (64, 40)])
+def test_two_rank_milnce_gallery_matches_closed_form(n_local, block, tmp_path):
+    """Cross-rank merge of the column log-sum-exp partials (all-gather + pb2_lse_combine contract)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_milnce, args=(r, world, port, n_local, block, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(world)]
+    V, A = _emb(n_local * world, 4.0)
+    a = A.double().requires_grad_(True)
+    v = V.double().requires_grad_(True)
+    x = (a @ v.T) / 0.5                                    # rows = audio, columns = video, temperature 0.5
+    den = torch.logaddexp(torch.logsumexp(x, 1), torch.logsumexp(x, 0))
+    ref = (den - torch.diagonal(x)).mean()
+    ref.backward()
+    for r in res:
+        assert abs(r[1] - ref.item()) < 1e-5 * abs(ref.item())
+    gdA = torch.cat([r[2] for r in res]).double()
+    gdV = torch.cat([r[3] for r in res]).double()
+    assert (gdA - a.grad).abs().max() / a.grad.abs().max() < 2e-3      # fp16 gradient matrix of the emulation
+    assert (gdV - v.grad).abs().max() / v.grad.abs().max() < 2e-3

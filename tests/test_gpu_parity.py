@@ -370,3 +370,29 @@ def test_install_patches_a_pig_package(pb):
     finally:
         for k in [k for k in sys.modules if k.startswith("pig_standin")]:
             del sys.modules[k]
+
+
+def test_milnce_temperature_extension(pb):
+    """temperature defaults to the reference (none); with tau the logits are V A^T / tau."""
+    V, A = emb(512, 4.0)
+    tau = 0.25
+    loss, dV, dA = _grads(pb.loss.MILNCELoss(temperature=tau), V, A)
+    v = V.double().requires_grad_(True)
+    a = A.double().requires_grad_(True)
+    x = (v @ a.T) / tau
+    den = torch.logaddexp(torch.logsumexp(x, 1), torch.logsumexp(x, 0))
+    ref = (den - torch.diagonal(x)).mean()
+    ref.backward()
+    assert rel_err(loss, ref.detach()) < TOL and rel_err(dV, v.grad) < TOL and rel_err(dA, a.grad) < TOL
+
+
+@pytest.mark.parametrize("n,block", [(1024, 32768), (1100, 384)])
+def test_gallery_step_milnce_single_gpu(pb, n, block):
+    """GalleryStep(loss='milnce'): rows = audio, columns = video; equals MILNCELoss up to the (V, A) swap."""
+    from peppa_b200.gallery import GalleryStep
+    V, A = emb(n, 4.0)
+    out = GalleryStep(n, 512, block=block, loss="milnce").run(A.cuda().bfloat16(), V.cuda().bfloat16())
+    loss, dA, dV = O.milnce_loss_and_grads(A, V)           # closed form with rows = first argument
+    assert rel_err(out["loss"].cpu(), loss) < TOL
+    assert rel_err(out["dA"].cpu(), dA) < TOL and rel_err(out["dV"].cpu(), dV) < TOL
+    assert rel_err(out["loss"].cpu(), O.milnce_loss(V, A)) < TOL     # the loss itself is symmetric

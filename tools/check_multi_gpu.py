@@ -47,6 +47,19 @@ def main():
                   f"ranks identical {same_ranks} recall identical {same_recall} -> {'OK' if ok else 'MISMATCH'}", flush=True)
             assert ok
         dist.barrier()
+    # MIL-NCE over the same sharding: cross-rank merge of the column log-sum-exp partials
+    out = GalleryStep(nl, 512, rank=rank, world=world, device=dev, loss="milnce", temperature=0.5).run(A[sl].to(dev), V[sl].to(dev))
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = GalleryStep(n, 512, device=dev, loss="milnce", temperature=0.5).run(A.to(dev), V.to(dev))
+        rel = lambda x, r: ((x - r).abs().max() / r.abs().max()).item()  # noqa: E731
+        e_loss = abs(out["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item())
+        e_da, e_dv = rel(out["dA"], ref["dA"][sl]), rel(out["dV"], ref["dV"][sl])
+        ok = e_loss < 1e-5 and e_da < 1e-3 and e_dv < 1e-3
+        print(f"world={world} n={n} milnce: loss rel {e_loss:.2e} dA rel {e_da:.2e} dV rel {e_dv:.2e} -> {'OK' if ok else 'MISMATCH'}",
+              flush=True)
+        assert ok
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -257,12 +257,6 @@ def step_hinge_perf():
     rc = torch.zeros(n, dtype=torch.int32, device="cuda")
     cc = torch.zeros(n, dtype=torch.int32, device="cuda")
     rk = torch.zeros(n, dtype=torch.int32, device="cuda")
-    for flags in (0, 1, 2, 3):
-        lib.pb2_debug_flags(flags)
-        lib.pb2_debug_force_bn(256)
-        ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=10)
-        print(f"dbg flags={flags} bn=256 rank+G: {ms:.3f} ms", flush=True)
-    lib.pb2_debug_flags(0)
     for bn in (128, 192, 256):
         lib.pb2_debug_force_bn(bn)
         for with_rank in (True, False):

@@ -1,14 +1,15 @@
 // Backward GEMMs of the contrastive losses on the tensor cores:
-//     out[M, dim] (=|+=) alpha * op(G) * Z        G fp16 gradient matrix, Z bf16 embeddings
+//     out[M, dim] (=|+=) alpha * op(G) * Z        G fp16 gradient matrix, Z fp16 (normalised) embeddings
 // i.e. the autograd backward of torch.matmul in pig/util.py:13 / pig/loss.py:19
-// (dX = G Y, dY = G^T X).  G comes from the fused forward epilogue (sim.cu), already scaled
-// by the row/column norms, so both products use the raw bf16 embeddings.
+// (dX = G Y, dY = G^T X).  G comes from the fused forward epilogue (sim.cu).  tcgen05 kind::f16 cannot mix
+// an fp16 A with a bf16 B (illegal instruction, measured), so Z is an fp16 copy of the embeddings
+// (pb2_rows_scale_f16); both operand formats are runtime fields of the instruction descriptor.
 //
-// Operand layouts for tcgen05.mma (kind::f16, A = fp16, B = bf16, fp32 accumulate in TMEM):
+// Operand layouts for tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
 //   A = G   (transpose == 0): K-major, one TMA box [128 rows x 64 k] per stage.
 //   A = G^T (transpose != 0): MN-major, two TMA boxes [64 k x 64 m] per stage.
 //   B = Z^T always MN-major (Z is [K, dim] row-major): BN/64 TMA boxes [64 k x 64 n] per stage.
-// Same warp-specialised pipeline as sim.cu: TMA warp, MMA warp, 8 epilogue warps, 2 TMEM stages.
+// Same warp-specialised pipeline as sim.cu: 8 epilogue warps, MMA warp, TMA warp, 2 TMEM stages.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"

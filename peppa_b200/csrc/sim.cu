@@ -1,14 +1,16 @@
 // Kernels (a)/(b): the similarity matrix S = X * Y^T on the 5th-generation tensor cores with the
 // consumer of S fused into the epilogue, so S never reaches HBM.
 //
-//   warp 0      TMA producer: cp.async.bulk.tensor tiles of X [128 x 64] and Y [BN x 64] (bf16,
-//               128-byte swizzle) into a ring of shared-memory stages, mbarrier full/empty.
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) from the
-//               shared-memory descriptors into one of two TMEM accumulator stages.
-//   warp 2      TMEM allocator.
-//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time (thread == row; the load of chunk c+1 is in
-//               flight while chunk c is processed), row/column scales, the mode's reduction; the
-//               MMA of tile t+1 overlaps the epilogue of tile t (two TMEM accumulator stages).
+//   warps 0..4G-1   epilogue (G groups of 4 warps, one warp per TMEM lane quadrant and column group):
+//                   tcgen05.ld 32 columns at a time (thread == row; with G <= 2 the load of chunk c+1 is in
+//                   flight while chunk c is processed), row/column scales, the mode's reduction; the MMA of
+//                   tile t+1 overlaps the epilogue of tile t (two TMEM accumulator stages).
+//   warp 4G         vector loader: stages the next tile's per-column / per-row epilogue operands in shared
+//                   memory and hands them over with an mbarrier.
+//   warp 4G+1       MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) from the
+//                   shared-memory descriptors into one of two TMEM accumulator stages.
+//   warp 4G+2       TMA producer: cp.async.bulk.tensor tiles of X [128 x 64] and Y [BN x 64] (bf16, 128-byte
+//                   swizzle) into a ring of shared-memory stages, mbarrier full/empty; TMEM alloc/dealloc.
 //
 // Persistent: gridDim = #SMs, tiles walked in bands of 8 row blocks so that concurrently
 // running CTAs share X and Y tiles through L2.
@@ -20,7 +22,8 @@
 //           (optionally also the rank counts of the diagonal: loss and recall@k from one pass)
 //   LseRow  pig/loss.py:19-25  online row log-sum-exp partials
 //   LseGrad MIL-NCE gradient matrix from the merged row/column statistics
-// Gradient-matrix tiles leave the SM through per-warp swizzled staging buffers and TMA stores.
+//   Diag    paired scores s_kk through the same tensor-core arithmetic (only the diagonal tiles)
+// Gradient-matrix and score tiles leave the SM through per-warp swizzled staging buffers and TMA stores.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"

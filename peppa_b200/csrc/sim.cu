@@ -483,23 +483,39 @@ struct LseRowPolicy {
                           const float* cv, OutStage&) {
         const int nvalid = t.cols_valid - cbase;
         if (nvalid <= 0) return;
-        float x[32];
-        float cm = -PB2_INF;
+        const float4* cv4 = reinterpret_cast<const float4*>(cv);
+        const float2 ri2 = make_float2(ri, ri);
+        float2 x[16];
+        // logits of the chunk (packed FMUL2) and their maximum as a pairwise tree
+        float2 mx = make_float2(-PB2_INF, -PB2_INF);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            x[j] = (j < nvalid) ? __uint_as_float(v[j]) * ri * cv[j] : -PB2_INF;
-            cm = fmaxf(cm, x[j]);
+        for (int q = 0; q < 8; ++q) {
+            const float4 c4 = cv4[q];
+            x[2 * q] = score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y);
+            x[2 * q + 1] = score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w);
+            if (nvalid < 32) {  // warp-uniform: only the last column tile has a ragged chunk
+                if (4 * q + 0 >= nvalid) x[2 * q].x = -PB2_INF;
+                if (4 * q + 1 >= nvalid) x[2 * q].y = -PB2_INF;
+                if (4 * q + 2 >= nvalid) x[2 * q + 1].x = -PB2_INF;
+                if (4 * q + 3 >= nvalid) x[2 * q + 1].y = -PB2_INF;
+            }
+            mx.x = fmaxf(mx.x, fmaxf(x[2 * q].x, x[2 * q + 1].x));
+            mx.y = fmaxf(mx.y, fmaxf(x[2 * q].y, x[2 * q + 1].y));
         }
-        const float mn = fmaxf(m, cm);
+        const float mn = fmaxf(m, fmaxf(mx.x, mx.y));
         // mn == -inf only if every logit so far is -inf; keep the state untouched then
         if (mn > -PB2_INF) {
-            float a0 = s * ex2_approx(m - mn), a1 = 0.f;
+            const float2 neg = make_float2(-mn, -mn);
+            float a0 = s * ex2_approx(m - mn), a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                a0 += ex2_approx(x[j] - mn);
-                a1 += ex2_approx(x[j + 1] - mn);
+            for (int k = 0; k < 16; k += 2) {
+                const float2 d0 = __fadd2_rn(x[k], neg), d1 = __fadd2_rn(x[k + 1], neg);
+                a0 += ex2_approx(d0.x);
+                a1 += ex2_approx(d0.y);
+                a2 += ex2_approx(d1.x);
+                a3 += ex2_approx(d1.y);
             }
-            s = a0 + a1;
+            s = (a0 + a1) + (a2 + a3);
             m = mn;
         }
     }
@@ -537,15 +553,24 @@ struct LseGradPolicy {
     }
     __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
                           const float* cv, OutStage& os) {
-        const float* cd = cv + kColVecStride;
+        const float4* cv4 = reinterpret_cast<const float4*>(cv);
+        const float4* cd4 = reinterpret_cast<const float4*>(cv + kColVecStride);
+        const float2 ri2 = make_float2(ri, ri), dr2 = make_float2(drow, drow);
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            const float x0 = __uint_as_float(v[j]) * ri * cv[j], x1 = __uint_as_float(v[j + 1]) * ri * cv[j + 1];
-            const float g0 = ex2_approx(x0 + drow) + ex2_approx(x0 + cd[j]);
-            const float g1 = ex2_approx(x1 + drow) + ex2_approx(x1 + cd[j + 1]);
-            const __half2 h = __floats2half2_rn(g0, g1);
-            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int q = 0; q < 8; ++q) {
+            const float4 c4 = cv4[q], d4 = cd4[q];
+            const float2 x01 = score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y);
+            const float2 x23 = score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w);
+            const float2 r01 = __fadd2_rn(x01, dr2), r23 = __fadd2_rn(x23, dr2);
+            const float2 k01 = __fadd2_rn(x01, make_float2(d4.x, d4.y)), k23 = __fadd2_rn(x23, make_float2(d4.z, d4.w));
+            const float2 g01 = __fadd2_rn(make_float2(ex2_approx(r01.x), ex2_approx(r01.y)),
+                                          make_float2(ex2_approx(k01.x), ex2_approx(k01.y)));
+            const float2 g23 = __fadd2_rn(make_float2(ex2_approx(r23.x), ex2_approx(r23.y)),
+                                          make_float2(ex2_approx(k23.x), ex2_approx(k23.y)));
+            const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
+            packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+            packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
         }
         const int lane = lane_id();
         if ((ch & 1) == 0) os.begin_slab(lane);

@@ -445,6 +445,9 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    if local == 0:
+        from peppa_b200 import build as _build
+        _build.build()                  # no-op when the in-tree .so is current
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:

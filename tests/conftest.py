@@ -16,6 +16,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_library_is_current():
+    """The .so is git-ignored; (re)build it in-tree when it is missing or older than its sources (a no-op
+    otherwise: per-source hashes).  The product itself never builds or falls back -- it raises."""
+    from peppa_b200 import build
+    build.build()
+
+
 def pytest_collection_modifyitems(config, items):
     if torch.cuda.is_available():
         return

@@ -396,3 +396,44 @@ def test_gallery_step_milnce_single_gpu(pb, n, block):
     assert rel_err(out["loss"].cpu(), loss) < TOL
     assert rel_err(out["dA"].cpu(), dA) < TOL and rel_err(out["dV"].cpu(), dV) < TOL
     assert rel_err(out["loss"].cpu(), O.milnce_loss(V, A)) < TOL     # the loss itself is symmetric
+
+
+def test_blocked_loss_paths(pb):
+    """Batches larger than one gradient-matrix block walk blocks with accumulating gradient GEMMs; exercise
+    that code with a tiny block edge."""
+    old = pb.loss._MAX_BLOCK
+    pb.loss._MAX_BLOCK = 512
+    try:
+        V, A = emb(1200, 4.0)
+        for mod, ref in ((pb.loss.TripletLoss(0.2), lambda: O.hinge_loss_and_grads(V, A, 0.2)),
+                         (pb.loss.MILNCELoss(), lambda: O.milnce_loss_and_grads(V, A))):
+            loss, dV, dA = _grads(mod, V, A)
+            rl, rdv, rda = ref()
+            assert rel_err(loss, rl) < TOL and rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL
+    finally:
+        pb.loss._MAX_BLOCK = old
+
+
+def test_contrastive_matrix_backward(pb):
+    g = torch.Generator().manual_seed(4)
+    M = (torch.randn(193, 193, generator=g) * 0.2)
+    m = M.cuda().requires_grad_(True)
+    pb.loss.contrastive(m, margin=0.3).backward()
+    mr = M.clone().requires_grad_(True)
+    O.contrastive(mr, margin=0.3).backward()
+    assert rel_err(m.grad.cpu(), mr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("d,dtype", [(64, torch.bfloat16), (768, torch.bfloat16), (100, torch.float32), (512, torch.float16)])
+def test_triplet_kernel_shapes(pb, d, dtype):
+    """Vector paths (D a multiple of 32 lanes x 16 bytes), the generic path (odd D) and sliced, unaligned views."""
+    g = torch.Generator().manual_seed(d)
+    a, p, n = (torch.randn(777, d, generator=g).to(dtype) for _ in range(3))
+    ref = O.triplet_accuracy(a.float(), p.float(), n.float(), discrete=False)
+    got = pb.metrics.triplet_accuracy(a.cuda(), p.cuda(), n.cuda(), discrete=False).float().cpu()
+    assert (got - ref).abs().max() < (2e-6 if dtype == torch.float32 else 4e-3)       # result is cast to the input dtype
+    wide = torch.randn(777, d + 3, generator=g).to(dtype).cuda()
+    view = wide[:, 1:d + 1]                                                           # unaligned, strided rows
+    got = pb.metrics.triplet_accuracy(view, p.cuda(), n.cuda(), discrete=False).float().cpu()
+    ref = O.triplet_accuracy(view.float().cpu(), p.float(), n.float(), discrete=False)
+    assert (got - ref).abs().max() < (2e-6 if dtype == torch.float32 else 4e-3)

@@ -135,6 +135,16 @@ int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols,
                   const void* z, int z_dtype, int dim, int64_t ldz, float alpha, int accumulate, float* out,
                   int64_t ld_out, void* stream);
 
+/* The same product with a caller workspace (device, 256-byte aligned, pb2_grad_gemm_workspace() bytes, ZEROED
+ * once after allocation; the kernel leaves its flag area zero).  With it, shapes whose whole output tiles do
+ * not fill the last wave of SMs run stream-K: the contraction of a row block may be cut between two CTAs
+ * and is completed through the workspace in a fixed order (deterministic, no atomics on `out`).  One
+ * workspace serves one stream at a time.  workspace == NULL behaves like pb2_grad_gemm. */
+int64_t pb2_grad_gemm_workspace(void);
+int pb2_grad_gemm_ws(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose,
+                     const void* z, int z_dtype, int dim, int64_t ldz, float alpha, int accumulate, float* out,
+                     int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* out = fp16(x * rinv) (rinv == NULL: plain bf16 -> fp16 conversion): the embedding operand of
  * pb2_grad_gemm.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and fp16 holds every
  * normalised bf16 embedding value with 3 extra significand bits. */

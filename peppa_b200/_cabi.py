@@ -41,6 +41,8 @@ SIGNATURES = {
     "pb2_lse_combine": [_p, _i, _i64, _p, _p],
     "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_grad_gemm": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p],
+    "pb2_grad_gemm_workspace": [],
+    "pb2_grad_gemm_ws": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p, _i64, _p],
     "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
     "pb2_hinge_prep": [_p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
@@ -53,9 +55,10 @@ SIGNATURES = {
     "pb2_milnce_loss": [_p, _p, _p, _i64, _p, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
 }
-_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64}
+_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64,
+            "pb2_grad_gemm_workspace": C.c_int64}
 # test hooks, not part of the public header
-_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
+_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_gg_pair": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 
 _lib = None
 

@@ -10,6 +10,16 @@
 //   A = G^T (transpose != 0): MN-major, two TMA boxes [64 k x 64 m] per stage.
 //   B = Z^T always MN-major (Z is [K, dim] row-major): BN/64 TMA boxes [64 k x 64 n] per stage.
 // Same warp-specialised pipeline as sim.cu: 8 epilogue warps, MMA warp, TMA warp, 2 TMEM stages.
+//
+// Work decomposition.  A gradient-matrix block of 32768 x 32768 gives 256 x 2 output tiles of 128 x 256 with
+// 512 k-blocks each: 512 long tiles on 148 SMs = 3.46 waves, i.e. 13 % of the machine idles in the last
+// wave.  With a caller workspace the kernel therefore runs STREAM-K: the (row block, k-block) units are cut
+// into equal contiguous ranges, one per GROUP of n_cb CTAs (the CTAs of a group walk the same range for
+// the n_cb column tiles, so a G tile is still fetched from HBM once and hit in L2 by its neighbours).  A
+// row block cut between two groups is finished deterministically: the group holding its tail (always that
+// group's FIRST segment) parks the raw accumulators in the workspace and raises a flag; the group holding
+// its head (its LAST segment, reached ~a whole range later) adds them in its epilogue.  No atomics on the
+// output, fixed summation order, bit-reproducible.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
@@ -36,23 +46,58 @@ struct Args {
     // descriptor strides (bytes); runtime so the self-test can probe alternatives
     uint32_t mn_lbo, mn_sbo, mn_kstep;
     uint32_t idesc;
+    // stream-K (n_groups > 0): group g = blockIdx / n_cb owns units [total*g/n_groups, total*(g+1)/n_groups)
+    int n_groups;
+    uint32_t* flags;  // [grid] arrival counters, zero between launches
+    float4* parts;    // [grid][BN/4][128] raw accumulators of a CTA's tail segment
 };
 
-template <int BN>
+template <int BN, int kCtas>
 struct Smem {
     static constexpr int kABytes = BM * BK * 2;
-    static constexpr int kBBytes = (BN / 64) * kBoxBytes;
+    static constexpr int kBBytes = (BN / kCtas / 64) * kBoxBytes;  // a CTA of a pair stages half of B's columns
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
     static constexpr int kTileBytes = kStages * kStageBytes;
     static constexpr int kTotal = 1024 + kTileBytes + 256;
 };
 
-template <bool kTranspose, int BN>
+// Calls f(rb, cb, kb0, kb1) for every segment of this CTA (or CTA pair), in the same order for all warp
+// roles.  rb counts row blocks of BM * kCtas rows.
+template <int kCtas, class F>
+__device__ __forceinline__ void for_each_segment(const Args& a, F&& f) {
+    const int unit = (int)blockIdx.x / kCtas, n_units = (int)gridDim.x / kCtas;
+    if (a.n_groups > 0) {
+        const int g = unit / a.n_cb, cb = unit % a.n_cb;
+        if (g >= a.n_groups) return;
+        const int64_t total = (int64_t)a.n_rb * a.kblocks;
+        int64_t u = total * g / a.n_groups;
+        const int64_t u1 = total * (g + 1) / a.n_groups;
+        while (u < u1) {
+            const int rb = (int)(u / a.kblocks), kb0 = (int)(u % a.kblocks);
+            const int kb1 = (int)min((int64_t)a.kblocks, kb0 + (u1 - u));
+            f(rb, cb, kb0, kb1);
+            u += kb1 - kb0;
+        }
+    } else {
+        for (int64_t t = unit; t < a.n_tiles; t += n_units) f((int)(t / a.n_cb), (int)(t % a.n_cb), 0, a.kblocks);
+    }
+}
+
+// kCtas == 2: CTA pairs (cluster of 2) drive one tcgen05.mma.cta_group::2 of M = 256, N = BN per k-step;
+// each CTA stages its own 128 rows of A and BN/2 columns of B, accumulates its 128 x BN in its own TMEM
+// and runs its own epilogue.  See common.cuh for the protocol.
+template <bool kTranspose, int BN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
     grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z,
                      const Args a) {
-    using L = Smem<BN>;
+    using L = Smem<BN, kCtas>;
+    constexpr int BNL = BN / kCtas;  // B columns staged by this CTA
+    // BN == 512 (pairs only): the 128 x 512 fp32 accumulator is all of TMEM, one stage -- the epilogue is not
+    // overlapped, which costs ~1 % at the contraction lengths this variant is chosen for
+    constexpr int kAccStages = BN == 512 ? 1 : 2;
+    constexpr int kUmmaN = BN > 256 ? 256 : BN;  // N of one tcgen05.mma; BN == 512 issues two per k-step
+    static_assert(BN <= 256 || kCtas == 2, "512-wide tiles need CTA pairs");
     // 128-byte-swizzled TMA/UMMA tiles need 1024-byte alignment; the kernel has no static shared
     // memory, so the dynamic segment starts at the (aligned) base of the CTA's shared window.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -65,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
     if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tm_g);
         tma_prefetch_desc(&tm_z);
@@ -76,13 +122,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(acc_full + s, 1);
-            mbar_init(acc_empty + s, kEpiWarps);
+            mbar_init(acc_empty + s, kEpiWarps * kCtas);  // the leader's collects both CTAs' epilogues
         }
         fence_mbar_init();
     }
-    if (warp == kTmaWarp) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == kTmaWarp) {
+        if (kCtas == 2) tmem_alloc_pair(tmem_slot, kAccStages * BN);
+        else tmem_alloc(tmem_slot, kAccStages * BN);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (kCtas == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -90,42 +140,61 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-                const int rb = (int)(t / a.n_cb), cb = (int)(t % a.n_cb);
-                for (int kb = 0; kb < a.kblocks; ++kb) {
+            for_each_segment<kCtas>(a, [&](int rb, int cb, int kb0, int kb1) {
+                const int row0 = (rb * kCtas + (int)crank) * BM;
+                // this CTA's B columns: chunk q of 64 -> MMA q / (kUmmaN / kCtas / 64), half `crank` of its N
+                constexpr int kChunksPerMma = kUmmaN / kCtas / 64;
+                auto bcol = [&](int q) {
+                    return cb * BN + (q / kChunksPerMma) * kUmmaN + (int)crank * (kUmmaN / kCtas) + (q % kChunksPerMma) * 64;
+                };
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
-                    mbar_arrive_expect_tx(full + stage, L::kStageBytes);
-                    if (!kTranspose) {
-                        tma_load_2d(sa, &tm_g, full + stage, kb * BK, rb * BM, kEvictFirst);
-                    } else {
-                        tma_load_2d(sa, &tm_g, full + stage, rb * BM, kb * BK, kEvictFirst);
-                        tma_load_2d(sa + kBoxBytes, &tm_g, full + stage, rb * BM + 64, kb * BK, kEvictFirst);
-                    }
+                    if (kCtas == 1) {
+                        mbar_arrive_expect_tx(full + stage, L::kStageBytes);
+                        if (!kTranspose) {
+                            tma_load_2d(sa, &tm_g, full + stage, kb * BK, row0, kEvictFirst);
+                        } else {
+                            tma_load_2d(sa, &tm_g, full + stage, row0, kb * BK, kEvictFirst);
+                            tma_load_2d(sa + kBoxBytes, &tm_g, full + stage, row0 + 64, kb * BK, kEvictFirst);
+                        }
 #pragma unroll
-                    for (int cchunk = 0; cchunk < BN / 64; ++cchunk)
-                        tma_load_2d(sb + cchunk * kBoxBytes, &tm_z, full + stage, cb * BN + cchunk * 64, kb * BK,
-                                    kEvictLast);
+                        for (int cchunk = 0; cchunk < BNL / 64; ++cchunk)
+                            tma_load_2d(sb + cchunk * kBoxBytes, &tm_z, full + stage, bcol(cchunk), kb * BK, kEvictLast);
+                    } else {
+                        // both CTAs' bytes are counted on the leader's barrier
+                        if (crank == 0) mbar_arrive_expect_tx(full + stage, L::kStageBytes * kCtas);
+                        const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+                        if (!kTranspose) {
+                            tma_load_2d_pair(sa, &tm_g, lbar, kb * BK, row0, kEvictFirst);
+                        } else {
+                            tma_load_2d_pair(sa, &tm_g, lbar, row0, kb * BK, kEvictFirst);
+                            tma_load_2d_pair(sa + kBoxBytes, &tm_g, lbar, row0 + 64, kb * BK, kEvictFirst);
+                        }
+#pragma unroll
+                        for (int cchunk = 0; cchunk < BNL / 64; ++cchunk)
+                            tma_load_2d_pair(sb + cchunk * kBoxBytes, &tm_z, lbar, bcol(cchunk), kb * BK, kEvictLast);
+                    }
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-            }
+            });
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
+        if (lane == 0 && crank == 0) {
             const uint32_t idesc = a.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int64_t it = 0;
-            for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
-                const int as = (int)(it & 1);
-                mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);
+            for_each_segment<kCtas>(a, [&](int, int, int kb0, int kb1) {
+                const int as = (int)(it % kAccStages);
+                mbar_wait(acc_empty + as, (uint32_t)((it / kAccStages) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < a.kblocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -134,28 +203,52 @@ __global__ void __launch_bounds__(kThreads, 1)
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint64_t da = kTranspose ? make_smem_desc(sa + k * a.mn_kstep, a.mn_lbo, a.mn_sbo)
                                                        : make_smem_desc(sa + k * UK * 2, 16, 1024);
-                        const uint64_t db = make_smem_desc(sb + k * a.mn_kstep, a.mn_lbo, a.mn_sbo);
-                        umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+#pragma unroll
+                        for (int j = 0; j < BN / kUmmaN; ++j) {  // the B chunks of MMA j follow those of MMA j-1
+                            const uint64_t db = make_smem_desc(sb + j * (kUmmaN / kCtas / 64) * kBoxBytes + k * a.mn_kstep,
+                                                               a.mn_lbo, a.mn_sbo);
+                            if (kCtas == 2) umma_f16_pair(d_tmem + j * kUmmaN, da, db, idesc, acc);
+                            else umma_f16(d_tmem + j * kUmmaN, da, db, idesc, acc);
+                        }
                     }
-                    umma_commit(empty + stage);
+                    if (kCtas == 2) umma_commit_pair(empty + stage);
+                    else umma_commit(empty + stage);
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(acc_full + as);
-            }
+                if (kCtas == 2) umma_commit_pair(acc_full + as);
+                else umma_commit(acc_full + as);
+                ++it;
+            });
         }
     } else {
         const int quad = warp & 3;
         const int half = (warp - kEpiWarp0) >> 2;
         constexpr int kChunksPerHalf = BN / 64;
         int64_t it = 0;
-        for (int64_t t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
-            const int as = (int)(it & 1);
-            const int rb = (int)(t / a.n_cb), cb = (int)(t % a.n_cb);
-            const int64_t row = (int64_t)rb * BM + quad * 32 + lane;
-            mbar_wait(acc_full + as, (uint32_t)((it >> 1) & 1));
+        for_each_segment<kCtas>(a, [&](int rb, int cb, int kb0, int kb1) {
+            const int as = (int)(it % kAccStages);
+            const int64_t row = ((int64_t)rb * kCtas + crank) * BM + quad * 32 + lane;
+            // stream-K: a tail segment parks its accumulators; a head segment folds its neighbour's in
+            const bool park = kb0 > 0, fold = kb1 < a.kblocks;
+            const uint32_t peer = blockIdx.x + (uint32_t)(a.n_cb * kCtas);  // same tile slot, next group
+            if (fold) {
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    while (ld_acquire_u32(a.flags + peer) < (uint32_t)kEpiWarps) {
+                        __nanosleep(200);
+                        if (clock64() - t0 > PB2_WAIT_TIMEOUT_CYCLES) {
+                            printf("pb2: grad_gemm stream-K flag wait timed out (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            mbar_wait(acc_full + as, (uint32_t)((it / kAccStages) & 1));
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
@@ -164,6 +257,25 @@ __global__ void __launch_bounds__(kThreads, 1)
                 uint32_t v[32];
                 tmem_ld32(t_lane + cbase, v);
                 tmem_ld_wait();
+                if (park) {  // [BN/4][128] float4: consecutive lanes (rows) write consecutive 16 bytes
+                    float4* dst = a.parts + ((size_t)blockIdx.x * (BN / 4) + cbase / 4) * BM + quad * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j * BM] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    continue;
+                }
+                if (fold) {
+                    const float4* src = a.parts + ((size_t)peer * (BN / 4) + cbase / 4) * BM + quad * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 o = __ldcg(src + j * BM);
+                        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + o.x);
+                        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + o.y);
+                        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + o.z);
+                        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + o.w);
+                    }
+                }
                 if (row < a.m) {
                     float* dst = a.out + row * a.ld_out + (int64_t)cb * BN + cbase;
 #pragma unroll
@@ -183,22 +295,41 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + as);
-        }
+            if (lane == 0) {
+                if (kCtas == 2) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + as), 0));
+                else mbar_arrive(acc_empty + as);
+            }
+            if (park) {  // publish: every lane's stores, then one release-increment per warp
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) red_release_add_u32(a.flags + blockIdx.x, 1u);
+            }
+            if (fold) {  // all epilogue warps are past their reads of the peer's slot: re-arm its flag
+                named_bar_sync(1, kEpiWarps * 32);
+                if (warp == kEpiWarp0 && lane == 0) a.flags[peer] = 0u;
+            }
+            ++it;
+        });
     }
     tc_fence_before();
-    __syncthreads();
+    if (kCtas == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
+    else __syncthreads();
     if (warp == kTmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        if (kCtas == 2) tmem_dealloc_pair(tmem_base, kAccStages * BN);
+        else tmem_dealloc(tmem_base, kAccStages * BN);
     }
 }
 
 static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
 
-template <bool kTranspose, int BN>
+constexpr int64_t kFlagBytes = 1024;  // flags of up to 256 CTAs, then the parked accumulators
+static int64_t workspace_bytes() { return kFlagBytes + (int64_t)sm_count() * BM * 512 * 4; }
+
+template <bool kTranspose, int BN, int kCtas>
 static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int z_fmt,
-                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, cudaStream_t st) {
+                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, void* workspace,
+                  cudaStream_t st) {
     CUtensorMap tg, tz;
     const int64_t m = kTranspose ? g_cols : g_rows;
     const int64_t k = kTranspose ? g_rows : g_cols;
@@ -206,10 +337,11 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
     if (rc) return rc;
     rc = make_tmap_2d(&tz, z, 2, (uint64_t)k, (uint64_t)dim, (uint64_t)ldz * 2, 64, 64);
     if (rc) return rc;
+    constexpr int kRowsPerUnit = BM * kCtas;  // output rows of one CTA (pair) tile
     Args a;
     a.m = m;
     a.k = k;
-    a.n_rb = (int)((m + BM - 1) / BM);
+    a.n_rb = (int)((m + kRowsPerUnit - 1) / kRowsPerUnit);
     a.n_cb = dim / BN;
     a.n_tiles = (int64_t)a.n_rb * a.n_cb;
     a.kblocks = (int)((k + BK - 1) / BK);
@@ -220,19 +352,49 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
     a.mn_lbo = g_mn_lbo;
     a.mn_sbo = g_mn_sbo;
     a.mn_kstep = g_mn_kstep;
-    a.idesc = make_idesc(BM, BN, (uint32_t)g_fmt, (uint32_t)z_fmt, kTranspose ? kMajorMN : kMajorK, kMajorMN);
-    auto kern = grad_gemm_kernel<kTranspose, BN>;
-    constexpr int smem = Smem<BN>::kTotal;
+    a.idesc = make_idesc(kRowsPerUnit, BN > 256 ? 256 : BN, (uint32_t)g_fmt, (uint32_t)z_fmt, kTranspose ? kMajorMN : kMajorK, kMajorMN);
+    // stream-K when whole tiles would leave part of the machine idle in the last wave and every group's
+    // range spans at least one full tile (so a row block is cut at most once)
+    a.n_groups = 0;
+    a.flags = nullptr;
+    a.parts = nullptr;
+    const int units = sm_count() / kCtas;  // CTAs or CTA pairs the machine runs at once
+    if (workspace && a.n_cb <= units && units * kCtas <= 256) {
+        const int groups = units / a.n_cb;
+        const int64_t total = (int64_t)a.n_rb * a.kblocks;
+        if (a.n_tiles > units && a.n_tiles % units != 0 && total / groups >= a.kblocks) {
+            a.n_groups = groups;
+            a.flags = static_cast<uint32_t*>(workspace);
+            a.parts = reinterpret_cast<float4*>(static_cast<char*>(workspace) + kFlagBytes);
+        }
+    }
+    auto kern = grad_gemm_kernel<kTranspose, BN, kCtas>;
+    constexpr int smem = Smem<BN, kCtas>::kTotal;
     static bool configured = false;
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "grad_gemm");
         if (rc) return rc;
         configured = true;
     }
-    const int grid = (int)std::min<int64_t>(a.n_tiles, sm_count());
-    kern<<<grid, kThreads, smem, st>>>(tg, tz, a);
+    const int n_units = a.n_groups > 0 ? a.n_groups * a.n_cb : (int)std::min<int64_t>(a.n_tiles, units);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_units * kCtas));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = kCtas > 1 ? 1 : 0;
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, tg, tz, a), "grad_gemm launch");
+    if (rc) return rc;
     return check_launch("grad_gemm");
 }
+
+static int g_pair_mode = -1;  // test hook (pb2_debug_gg_pair): -1 = automatic, 0 = never, 1 = whenever legal
 
 }  // namespace gg
 }  // namespace pb2
@@ -246,10 +408,27 @@ extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep)
     return PB2_OK;
 }
 
+extern "C" int pb2_debug_gg_pair(int mode) {
+    gg::g_pair_mode = mode;
+    return PB2_OK;
+}
+
+extern "C" int64_t pb2_grad_gemm_workspace(void) { return gg::workspace_bytes(); }
+
 extern "C" int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g,
                              int transpose, const void* z, int z_dtype, int dim, int64_t ldz, float alpha,
                              int accumulate, float* out, int64_t ld_out, void* stream) {
+    return pb2_grad_gemm_ws(gmat, g_dtype, g_rows, g_cols, ld_g, transpose, z, z_dtype, dim, ldz, alpha, accumulate, out,
+                            ld_out, nullptr, 0, stream);
+}
+
+extern "C" int pb2_grad_gemm_ws(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g,
+                                int transpose, const void* z, int z_dtype, int dim, int64_t ldz, float alpha,
+                                int accumulate, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
     if (g_rows <= 0 || g_cols <= 0) return PB2_OK;
+    if (workspace && (workspace_bytes < gg::workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 255)))
+        return set_error(PB2_ERR_ARG, "grad_gemm: workspace must be 256-byte aligned and pb2_grad_gemm_workspace() bytes");
     if (!gmat || !z || !out) return set_error(PB2_ERR_ARG, "grad_gemm: null");
     if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "grad_gemm: dim must be a multiple of 64");
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0)
@@ -267,15 +446,29 @@ extern "C" int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int6
     else if (dim % 128 == 0 && rb * (dim / 128) >= want) bn = 128;
     const int gf = g_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
     const int zf = z_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
-#define PB2_GG(T, B) \
-    gg::launch<T, B>(gmat, gf, g_rows, g_cols, ld_g, z, zf, dim, ldz, alpha, accumulate, out, ld_out, st)
+#define PB2_GG(T, B, C) \
+    gg::launch<T, B, C>(gmat, gf, g_rows, g_cols, ld_g, z, zf, dim, ldz, alpha, accumulate, out, ld_out, workspace, st)
+    // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles per pair) once there are enough pair tiles to fill
+    // the machine: a third less operand traffic per SM than two independent 128 x 256 tiles
+    // g_pair_mode: -1 automatic, 0 never, 1 pairs of 256-wide tiles, 2 pairs of 512-wide tiles
+    const int64_t pair_rb = (m_rows + 2 * gg::BM - 1) / (2 * gg::BM);
+    const int64_t kblocks = ((transpose ? g_rows : g_cols) + gg::BK - 1) / gg::BK;
+    const bool pair = bn == 256 && (gg::g_pair_mode == 1 || (gg::g_pair_mode < 0 && pair_rb * (dim / 256) >= sm_count() / 2));
+    // a pair tile spanning 512 output columns reads each G tile once chip-wide and a third fewer operand bytes
+    // than two 256-wide tiles; its single TMEM stage exposes the epilogue, so only for long contractions
+    const bool wide = dim % 512 == 0 && bn == 256 &&
+                      (gg::g_pair_mode == 2 || (gg::g_pair_mode < 0 && pair_rb * (dim / 512) >= sm_count() / 2 && kblocks >= 128));
     if (transpose) {
-        if (bn == 256) return PB2_GG(true, 256);
-        if (bn == 128) return PB2_GG(true, 128);
-        return PB2_GG(true, 64);
+        if (wide) return PB2_GG(true, 512, 2);
+        if (pair) return PB2_GG(true, 256, 2);
+        if (bn == 256) return PB2_GG(true, 256, 1);
+        if (bn == 128) return PB2_GG(true, 128, 1);
+        return PB2_GG(true, 64, 1);
     }
-    if (bn == 256) return PB2_GG(false, 256);
-    if (bn == 128) return PB2_GG(false, 128);
-    return PB2_GG(false, 64);
+    if (wide) return PB2_GG(false, 512, 2);
+    if (pair) return PB2_GG(false, 256, 2);
+    if (bn == 256) return PB2_GG(false, 256, 1);
+    if (bn == 128) return PB2_GG(false, 128, 1);
+    return PB2_GG(false, 64, 1);
 #undef PB2_GG
 }

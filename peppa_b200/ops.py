@@ -196,16 +196,34 @@ def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, s
                                            _stream(x.device)), "sim_lse_grad")
 
 
-def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False):
+_GG_WORKSPACE = {}        # (device, stream) -> zero-initialised stream-K workspace of pb2_grad_gemm_ws
+
+
+def grad_gemm_workspace(device):
+    """Stream-K workspace for the current stream of ``device`` (allocated and zeroed once; the kernel
+    leaves its flag area zero, and reuse on one stream is stream-ordered)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _GG_WORKSPACE.get(key)
+    if ws is None:
+        with torch.cuda.device(device):
+            ws = torch.zeros(int(_cabi.lib().pb2_grad_gemm_workspace()), dtype=torch.uint8, device=device)
+        _GG_WORKSPACE[key] = ws
+    return ws
+
+
+def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False, stream_k=True):
     m = g_cols if transpose else g_rows
     d = z.shape[1]
     if out is None:
         out = torch.empty(m, d, dtype=torch.float32, device=z.device)
         accumulate = False
+    # small products are whole-tile anyway; skip the workspace (and its allocation under graph capture)
+    ws = grad_gemm_workspace(z.device) if stream_k and m * d > 148 * 128 * 256 else None
     with torch.cuda.device(z.device), _timed("grad_gemm", 2.0 * g_rows * g_cols * d, z.device):
-        check(_cabi.lib().pb2_grad_gemm(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g), int(bool(transpose)),
-                                        _ptr(z), _DTYPE_CODE[z.dtype], d, z.stride(0), float(alpha), int(bool(accumulate)),
-                                        _ptr(out), out.stride(0), _stream(z.device)), "grad_gemm")
+        check(_cabi.lib().pb2_grad_gemm_ws(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g),
+                                           int(bool(transpose)), _ptr(z), _DTYPE_CODE[z.dtype], d, z.stride(0),
+                                           float(alpha), int(bool(accumulate)), _ptr(out), out.stride(0), _ptr(ws),
+                                           ws.numel() if ws is not None else 0, _stream(z.device)), "grad_gemm")
     return out
 
 

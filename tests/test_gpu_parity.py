@@ -437,3 +437,27 @@ def test_triplet_kernel_shapes(pb, d, dtype):
     got = pb.metrics.triplet_accuracy(view, p.cuda(), n.cuda(), discrete=False).float().cpu()
     ref = O.triplet_accuracy(view.float().cpu(), p.float(), n.float(), discrete=False)
     assert (got - ref).abs().max() < (2e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("tr", [False, True])
+@pytest.mark.parametrize("r,c,d", [(20480, 2048, 512), (20000, 1000, 512), (9000, 4100, 256)])
+def test_grad_gemm_stream_k(pb, tr, r, c, d):
+    """The stream-K decomposition of pb2_grad_gemm_ws (row blocks cut between CTAs, completed through the
+    workspace) agrees with the whole-tile kernel and with fp64, and is bit-reproducible."""
+    from peppa_b200 import ops
+    torch.manual_seed(3)
+    gm, ld = ops.gmat_alloc(r, c, "cuda")
+    gm.zero_()
+    gm[:, :c] = torch.randint(0, 3, (r, c), device="cuda").half()
+    z = (torch.randn(r if tr else c, d, device="cuda") * 0.05).half()
+    tiles = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=False)
+    sk = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=True)
+    sk2 = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=True)
+    acc = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, out=torch.ones_like(sk), accumulate=True, alpha=0.5)
+    G = gm[:, :c].double()
+    ref = (G.T if tr else G) @ z.double()
+    scale = ref.abs().max()
+    assert ((tiles - ref).abs().max() / scale).item() < 1e-5
+    assert ((sk - ref).abs().max() / scale).item() < 1e-5
+    assert ((acc - (1 + 0.5 * ref)).abs().max() / scale).item() < 1e-5
+    assert torch.equal(sk, sk2)

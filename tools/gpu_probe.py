@@ -297,5 +297,66 @@ def step_hinge_dim():
     lib.pb2_debug_force_bn(0)
 
 
+def step_streamk():
+    """grad_gemm: CTA pairs (cta_group::2) on/off x stream-K on/off: agreement with fp64, determinism, sustained time."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    torch.manual_seed(0)
+    for tr in (False, True):
+        for (r, c, d) in [(20480, 2048, 512), (2048, 20480, 512), (20000, 1000, 512), (9000, 4100, 256), (40960, 640, 256)]:
+            gm, ld = ops.gmat_alloc(r, c, "cuda")
+            gm.zero_()
+            gm[:, :c] = torch.randint(0, 3, (r, c), device="cuda").half()
+            z = (torch.randn(r if tr else c, d, device="cuda") * 0.05).half()
+            ref = ((gm[:, :c].double().T if tr else gm[:, :c].double()) @ z.double())
+            for pair in (0, 1, 2):
+                lib.pb2_debug_gg_pair(pair)
+                a = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=False)
+                b = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=True)
+                b2 = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, stream_k=True)
+                base = torch.ones_like(a)
+                acc = ops.grad_gemm(gm, r, c, ld, z, transpose=tr, out=base, accumulate=True, alpha=0.5)
+                torch.cuda.synchronize()
+                e_a = ((a - ref).abs().max() / ref.abs().max()).item()
+                e_b = ((b - ref).abs().max() / ref.abs().max()).item()
+                e_acc = ((acc - (1 + 0.5 * ref)).abs().max() / ref.abs().max()).item()
+                print(f"T={tr} r={r} c={c} d={d} pair={pair}: tiles err {e_a:.2e}  stream-K err {e_b:.2e}  acc err {e_acc:.2e}  "
+                      f"deterministic {bool((b == b2).all())}", "OK" if max(e_a, e_b, e_acc) < 3e-5 else "MISMATCH", flush=True)
+    n = 32768
+    gm, ld = ops.gmat_alloc(n, n, "cuda")
+    gm.copy_(torch.randint(0, 3, (n, ld), device="cuda").half())
+    z = (torch.randn(n, 512, device="cuda") * 0.05).half()
+    out = torch.zeros(n, 512, device="cuda")
+    for pair in (0, 1, 2):
+        lib.pb2_debug_gg_pair(pair)
+        for tr in (False, True):
+            for sk in (False, True):
+                ms = _t(lambda: ops.grad_gemm(gm, n, n, ld, z, transpose=tr, out=out, accumulate=True, stream_k=sk), iters=300, warm=20)
+                print(f"grad_gemm 32768^2 pair={pair} T={tr} stream_k={sk}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s "
+                      f"(300 back to back)", flush=True)
+    lib.pb2_debug_gg_pair(-1)
+    # the library on the same products (fp16 in, fp32 accumulate, fp16 out): what 1 kW buys cuBLAS here
+    for tr in (False, True):
+        gmv = gm[:, :n]
+        fn = (lambda: torch.matmul(gmv.T, z)) if tr else (lambda: torch.matmul(gmv, z))
+        ms = _t(fn, iters=300, warm=20)
+        print(f"torch.matmul fp16 32768^2 x 512 T={tr}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s (300 back to back)", flush=True)
+    # burst: 3 launches after a 2 s pause (clocks not yet power-throttled)
+    import time
+    for pair in (0, 1, 2):
+        lib.pb2_debug_gg_pair(pair)
+        for sk in (False, True):
+            torch.cuda.synchronize()
+            time.sleep(2.0)
+            ms = _t(lambda: ops.grad_gemm(gm, n, n, ld, z, transpose=False, out=out, accumulate=True, stream_k=sk), iters=3, warm=1)
+            print(f"burst grad_gemm pair={pair} stream_k={sk}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
+    lib.pb2_debug_gg_pair(-1)
+    torch.cuda.synchronize()
+    time.sleep(2.0)
+    ms = _t(lambda: torch.matmul(gm[:, :n], z), iters=3, warm=1)
+    print(f"burst torch.matmul: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     main()

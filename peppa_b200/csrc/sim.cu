@@ -145,10 +145,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Largest float below a finite x (nextafterf(x, -inf)) without control flow: the vector-loader warp must
+// keep every global load of a tile in flight at once, and libdevice's nextafterf puts branches between them
+// (measured: twelve serialised round trips per tile, the loader -- not the MMA or the epilogue -- set the
+// tile period).  NaN stays NaN; -inf stays -inf.
+__device__ __forceinline__ float pred_f32(float x) {
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t down = (b & 0x7fffffffu) == 0u ? 0x80000001u : ((b >> 31) ? b + 1u : b - 1u);
+    return (x != x || x == -PB2_INF) ? x : __uint_as_float(down);
+}
 // s = fl32(fl32(v * ri) * cj) for two adjacent columns (packed FMUL2; same two roundings everywhere)
 __device__ __forceinline__ float2 score2(uint32_t v0, uint32_t v1, float2 ri2, float c0, float c1) {
     return __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(v0), __uint_as_float(v1)), ri2), make_float2(c0, c1));
 }
+
+// Vector-loader contract.  Each policy splits its per-column / per-row epilogue operands into
+//   fetch_*: global loads ONLY (predicated, no arithmetic on loaded values) into raw[] registers, and
+//   make_*:  the arithmetic that turns raw[] into the staged fp32 vectors.
+// The loader warp calls every fetch of a tile before the first make, so all of a tile's loads are in flight
+// together: one global round trip per tile instead of one per 32 columns.
+__device__ __forceinline__ uint32_t ldu(const float* p, int64_t i, bool pred, uint32_t dflt) {
+    return (pred && p) ? __float_as_uint(p[i]) : dflt;
+}
+constexpr uint32_t kOneBits = 0x3f800000u;
+constexpr int kMaxColRaw = 2, kMaxRowRaw = 4;
 
 // ------------------------------------------------------------------------------- epilogues
 // Each policy: Params (POD, kernel argument), kColVecs (per-column fp32 vectors staged in smem),
@@ -164,12 +184,18 @@ struct StorePolicy {
     static constexpr bool kStoresF32 = true;  // S tiles leave through the OutStage (fp32 boxes [32 x 32])
     float ri;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
+    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
     }
     static constexpr int kRowVecs = 1;
-    __device__ static void load_row(const Params&, const SimCommon& c, int64_t row, bool valid, float* v) {
-        v[0] = (valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) : 0.f) * c.scale;
+    __device__ static void fetch_row(const Params&, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+    }
+    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+        v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale;
     }
     __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) { ri = rv[0]; }
     __device__ void chunk(const Params&, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
@@ -201,15 +227,26 @@ struct RankPolicy {
     int pc;  // positive's column relative to the tile origin (may be out of range)
     int cnt;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
+    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
         // an out-of-range column must never count: NaN makes every comparison false
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : PB2_NAN;
+        v[0] = valid ? __uint_as_float(raw[0]) : PB2_NAN;
     }
     static constexpr int kRowVecs = 3;  // rinv_x * scale, rank threshold, positive's column (int bits)
-    __device__ static void load_row(const Params& p, const SimCommon& c, int64_t row, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) * c.scale : 0.f;
-        v[1] = valid ? p.pos_thr[row] : PB2_INF;  // s >= thr  <=>  fl32(1 - s) < fl32(1 - s_pos)
-        const int64_t rel = valid ? p.pos_col[row] - p.col_offset : -1;
+    __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+        raw[1] = ldu(p.pos_thr, row, valid, 0u);
+        const long long pc = valid ? p.pos_col[row] : -1ll;
+        raw[2] = (uint32_t)(unsigned long long)pc;
+        raw[3] = (uint32_t)((unsigned long long)pc >> 32);
+    }
+    __device__ static void make_row(const Params& p, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) * c.scale : 0.f;
+        v[1] = valid ? __uint_as_float(raw[1]) : PB2_INF;  // s >= thr  <=>  fl32(1 - s) < fl32(1 - s_pos)
+        const int64_t pc = (int64_t)(((unsigned long long)raw[3] << 32) | raw[2]);
+        const int64_t rel = valid ? pc - p.col_offset : -1;
         v[2] = __int_as_float((rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1);
     }
     __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx& t, const float* rv) {
@@ -268,12 +305,18 @@ struct DiagPolicy {
     static constexpr bool kStoresG = false;
     float ri;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
+    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
     }
     static constexpr int kRowVecs = 1;
-    __device__ static void load_row(const Params&, const SimCommon& c, int64_t row, bool valid, float* v) {
-        v[0] = (valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) : 0.f) * c.scale;
+    __device__ static void fetch_row(const Params&, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+    }
+    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+        v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale;
     }
     __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) { ri = rv[0]; }
     __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
@@ -332,16 +375,25 @@ struct HingePolicyT {
     float2 loss2, rc2, rk2;
     int dcol;
     __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
-    __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
-        v[1] = valid ? -(nextafterf(p.diag_col[col] - p.margin, -PB2_INF) * kBig) : -PB2_INF;
+    __device__ static void fetch_col(const Params& p, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+        raw[1] = ldu(p.diag_col, col, valid, 0u);
+    }
+    __device__ static void make_col(const Params& p, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+        v[1] = valid ? -(pred_f32(__uint_as_float(raw[1]) - p.margin) * kBig) : -PB2_INF;
     }
     static constexpr int kRowVecs = 4;  // rinv_x, -pred(thr_r) * 2^120, -pred(pos_thr) * 2^120, diagonal column
-    __device__ static void load_row(const Params& p, const SimCommon& c, int64_t row, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) : 0.f;
-        v[1] = valid ? -(nextafterf(p.diag_row[row] - p.margin, -PB2_INF) * kBig) : -PB2_INF;
+    __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+        raw[1] = ldu(p.diag_row, row, valid, 0u);
+        raw[2] = ldu(p.pos_thr, row, kRank && valid, 0u);
+    }
+    __device__ static void make_row(const Params& p, const SimCommon&, int64_t row, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+        v[1] = valid ? -(pred_f32(__uint_as_float(raw[1]) - p.margin) * kBig) : -PB2_INF;
         // [s >= pos_thr] as sat((s - pred(pos_thr)) * 2^120), like the hinge indicators
-        v[2] = (kRank && valid) ? -(nextafterf(p.pos_thr[row], -PB2_INF) * kBig) : -PB2_INF;
+        v[2] = (kRank && valid) ? -(pred_f32(__uint_as_float(raw[2])) * kBig) : -PB2_INF;
         const int64_t rel = valid ? (p.row_offset + row) - p.col_offset : -1;
         v[3] = __int_as_float((rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1);
     }
@@ -466,13 +518,19 @@ struct LseRowPolicy {
     static constexpr bool kStoresG = false;
     float ri, m, s;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void load_col(const Params&, const SimCommon& c, int64_t col, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
+    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
     }
     static constexpr int kRowVecs = 1;
-    __device__ static void load_row(const Params&, const SimCommon& c, int64_t row, bool valid, float* v) {
+    __device__ static void fetch_row(const Params&, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+    }
+    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
         // work in the log2 domain: t = s_ij * log2(e)
-        v[0] = (valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) : 0.f) * c.scale * 1.4426950408889634f;
+        v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale * 1.4426950408889634f;
     }
     __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) {
         ri = rv[0];
@@ -538,14 +596,22 @@ struct LseGradPolicy {
     static constexpr bool kStoresG = true;
     float ri, drow;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void load_col(const Params& p, const SimCommon& c, int64_t col, bool valid, float* v) {
-        v[0] = valid ? (c.rinv_y ? c.rinv_y[col] : 1.f) : 0.f;
-        v[1] = valid ? (13.0f - p.den_col[col] * 1.4426950408889634f) : -PB2_INF;
+    __device__ static void fetch_col(const Params& p, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+        raw[1] = ldu(p.den_col, col, valid, 0u);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+        v[1] = valid ? (13.0f - __uint_as_float(raw[1]) * 1.4426950408889634f) : -PB2_INF;
     }
     static constexpr int kRowVecs = 2;
-    __device__ static void load_row(const Params& p, const SimCommon& c, int64_t row, bool valid, float* v) {
-        v[0] = (valid ? (c.rinv_x ? c.rinv_x[row] : 1.f) : 0.f) * c.scale * 1.4426950408889634f;
-        v[1] = valid ? (13.0f - p.den_row[row] * 1.4426950408889634f) : -PB2_INF;
+    __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+        raw[1] = ldu(p.den_row, row, valid, 0u);
+    }
+    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+        v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale * 1.4426950408889634f;
+        v[1] = valid ? (13.0f - __uint_as_float(raw[1]) * 1.4426950408889634f) : -PB2_INF;
     }
     __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) {
         ri = rv[0];
@@ -713,32 +779,40 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);  // the epilogue is done with this buffer
             float* cv = colvec + as * (kMaxColVecs * kColVecStride);
             float* rv = rowvec + as * (kMaxRowVecs * BM);
-            // all global loads of the tile are issued before any is consumed (one warp, ~1 us of latency
-            // per dependent round trip otherwise)
+            // phase 1: every global load of the tile (fetch_* = loads only), phase 2: arithmetic + smem stores
             constexpr int kColIters = (BN + 31) / 32, kRowIters = BM / 32;
-            float tc[kColIters][kMaxColVecs], tr[kRowIters][kMaxRowVecs];
+            uint32_t rc[kColIters][kMaxColRaw], rr[kRowIters][kMaxRowRaw];
 #pragma unroll
             for (int i = 0; i < kColIters; ++i) {
                 const int col = lane + 32 * i;
-                Policy::load_col(p, c, col0 + col, col < BN && col0 + col < c.cols, tc[i]);
+                Policy::fetch_col(p, c, col0 + col, col < BN && col0 + col < c.cols, rc[i]);
             }
 #pragma unroll
             for (int i = 0; i < kRowIters; ++i) {
                 const int r = lane + 32 * i;
-                Policy::load_row(p, c, row0 + r, row0 + r < c.rows, tr[i]);
+                Policy::fetch_row(p, c, row0 + r, row0 + r < c.rows, rr[i]);
             }
+            // keep the two phases apart: neither the front end nor ptxas may sink a load to its use
+            asm volatile("" ::: "memory");
+            __syncwarp();
+            asm volatile("" ::: "memory");
 #pragma unroll
             for (int i = 0; i < kColIters; ++i) {
                 const int col = lane + 32 * i;
+                float tc[kMaxColVecs];
+                Policy::make_col(p, c, col < BN && col0 + col < c.cols, rc[i], tc);
                 if (col < BN) {
 #pragma unroll
-                    for (int k = 0; k < Policy::kColVecs; ++k) cv[k * kColVecStride + col] = tc[i][k];
+                    for (int k = 0; k < Policy::kColVecs; ++k) cv[k * kColVecStride + col] = tc[k];
                 }
             }
 #pragma unroll
             for (int i = 0; i < kRowIters; ++i) {
+                const int r = lane + 32 * i;
+                float tr[kMaxRowVecs];
+                Policy::make_row(p, c, row0 + r, row0 + r < c.rows, rr[i], tr);
 #pragma unroll
-                for (int k = 0; k < Policy::kRowVecs; ++k) rv[k * BM + lane + 32 * i] = tr[i][k];
+                for (int k = 0; k < Policy::kRowVecs; ++k) rv[k * BM + r] = tr[k];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(vec_full + as);

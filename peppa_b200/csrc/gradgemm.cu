@@ -186,8 +186,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else if (warp == kMmaWarp) {
         if (lane == 0 && crank == 0) {
             const uint32_t idesc = a.idesc;
+            // running descriptor low words (start address >> 4 | LBO); the high words are loop invariants
+            const uint64_t dk = make_smem_desc(smem_u32(smem), 16, 1024);               // K-major G tile
+            const uint64_t dm = make_smem_desc(smem_u32(smem), a.mn_lbo, a.mn_sbo);     // MN-major tiles
+            const uint32_t a_hi = (uint32_t)((kTranspose ? dm : dk) >> 32), b_hi = (uint32_t)(dm >> 32);
+            const uint32_t a_lo0 = (uint32_t)(kTranspose ? dm : dk), b_lo0 = (uint32_t)dm + (L::kABytes >> 4);
+            const uint32_t a_kstep = kTranspose ? (a.mn_kstep >> 4) : ((UK * 2) >> 4), b_kstep = a.mn_kstep >> 4;
+            constexpr uint32_t kStageLo = L::kStageBytes >> 4;
+            constexpr uint32_t kMmaBLo = ((kUmmaN / kCtas / 64) * kBoxBytes) >> 4;  // B chunks of MMA j follow those of j-1
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
             int64_t it = 0;
             for_each_segment<kCtas>(a, [&](int, int, int kb0, int kb1) {
                 const int as = (int)(it % kAccStages);
@@ -197,26 +205,28 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + L::kABytes;
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
-                        const uint64_t da = kTranspose ? make_smem_desc(sa + k * a.mn_kstep, a.mn_lbo, a.mn_sbo)
-                                                       : make_smem_desc(sa + k * UK * 2, 16, 1024);
                         const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
 #pragma unroll
-                        for (int j = 0; j < BN / kUmmaN; ++j) {  // the B chunks of MMA j follow those of MMA j-1
-                            const uint64_t db = make_smem_desc(sb + j * (kUmmaN / kCtas / 64) * kBoxBytes + k * a.mn_kstep,
-                                                               a.mn_lbo, a.mn_sbo);
-                            if (kCtas == 2) umma_f16_pair(d_tmem + j * kUmmaN, da, db, idesc, acc);
-                            else umma_f16(d_tmem + j * kUmmaN, da, db, idesc, acc);
+                        for (int j = 0; j < BN / kUmmaN; ++j) {
+                            if (kCtas == 2)
+                                umma_f16_pair_lohi(d_tmem + j * kUmmaN, a_lo + k * a_kstep, b_lo + j * kMmaBLo + k * b_kstep, a_hi,
+                                                   b_hi, idesc, acc);
+                            else
+                                umma_f16_pair_lohi_1(d_tmem + j * kUmmaN, a_lo + k * a_kstep, b_lo + j * kMmaBLo + k * b_kstep,
+                                                     a_hi, b_hi, idesc, acc);
                         }
                     }
                     if (kCtas == 2) umma_commit_pair(empty + stage);
                     else umma_commit(empty + stage);
+                    a_lo += kStageLo;
+                    b_lo += kStageLo;
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
+                        a_lo = a_lo0;
+                        b_lo = b_lo0;
                     }
                 }
                 if (kCtas == 2) umma_commit_pair(acc_full + as);

@@ -95,6 +95,7 @@ struct OutStage {
     const CUtensorMap* tmap;  // gradient matrix [rows, cols] fp16, box [32 x 64]
     uint32_t slab;            // running slab counter of this warp
     uint32_t mask;            // nbuf - 1 (1: double buffered, 0: one slab per tile and warp)
+    bool skip_store;          // measurement hook (pb2_debug_force_bn bit 16): stage but do not store
     // 16 fp16 (two uint4) of this thread's row, chunk parity cp (0: columns 0-31, 1: columns 32-63)
     __device__ __forceinline__ void write(int lane, int cp, const uint32_t (&packed)[16]) {
         uint8_t* row = buf + (slab & mask) * kOutSlabBytes + lane * 128;
@@ -124,7 +125,7 @@ struct OutStage {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_2d(tmap, buf + (slab & mask) * kOutSlabBytes, col, row);
+            if (!skip_store) tma_store_2d(tmap, buf + (slab & mask) * kOutSlabBytes, col, row);
             tma_store_commit();
         }
         ++slab;
@@ -138,6 +139,14 @@ struct OutStage {
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
     float d;
     asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// [a >= b] as an exact 1.0f / 0.0f from ONE ALU-pipe instruction (FSET.BF): the sub-partition issues one
+// FMA-pipe and one ALU-pipe instruction every other cycle each (tools/ubench/pipes.cu), so the epilogue
+// splits its indicators between fma_sat (FMA pipe) and this.
+__device__ __forceinline__ float fset_ge(float a, float b) {
+    float d;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -371,7 +380,7 @@ struct HingePolicyT {
     using Params = HingeParams;
     static constexpr int kColVecs = 2;  // rinv_y, -pred(thr_c) * 2^120 with thr_c = diag_col - margin
     static constexpr bool kStoresG = true;
-    float ri, rbig, kbig;
+    float ri, thr_r, thr_k;
     float2 loss2, rc2, rk2;
     int dcol;
     __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
@@ -383,7 +392,7 @@ struct HingePolicyT {
         v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
         v[1] = valid ? -(pred_f32(__uint_as_float(raw[1]) - p.margin) * kBig) : -PB2_INF;
     }
-    static constexpr int kRowVecs = 4;  // rinv_x, -pred(thr_r) * 2^120, -pred(pos_thr) * 2^120, diagonal column
+    static constexpr int kRowVecs = 4;  // rinv_x, thr_r = diag_row - margin, pos_thr, diagonal column
     __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
         raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
         raw[1] = ldu(p.diag_row, row, valid, 0u);
@@ -391,9 +400,9 @@ struct HingePolicyT {
     }
     __device__ static void make_row(const Params& p, const SimCommon&, int64_t row, bool valid, const uint32_t* raw, float* v) {
         v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
-        v[1] = valid ? -(pred_f32(__uint_as_float(raw[1]) - p.margin) * kBig) : -PB2_INF;
-        // [s >= pos_thr] as sat((s - pred(pos_thr)) * 2^120), like the hinge indicators
-        v[2] = (kRank && valid) ? -(pred_f32(__uint_as_float(raw[2])) * kBig) : -PB2_INF;
+        // per-row thresholds are compared on the ALU pipe (fset_ge); an invalid row never fires
+        v[1] = valid ? __uint_as_float(raw[1]) - p.margin : PB2_INF;
+        v[2] = (kRank && valid) ? __uint_as_float(raw[2]) : PB2_INF;
         const int64_t rel = valid ? (p.row_offset + row) - p.col_offset : -1;
         v[3] = __int_as_float((rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1);
     }
@@ -401,8 +410,8 @@ struct HingePolicyT {
         rc2 = make_float2(0.f, 0.f);
         rk2 = make_float2(0.f, 0.f);
         ri = rv[0];
-        rbig = rv[128];
-        kbig = rv[256];
+        thr_r = rv[128];
+        thr_k = rv[256];
         const int g = __float_as_int(rv[384]);
         const int64_t rel = (int64_t)g - t.col0;
         dcol = (g >= 0 && rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
@@ -446,16 +455,16 @@ struct HingePolicyT {
             // FMA pipe: indicators as exact 0/1 floats
             const float2 ic01 = make_float2(fma_sat(s01.x, kBig, b4.x), fma_sat(s01.y, kBig, b4.y));
             const float2 ic23 = make_float2(fma_sat(s23.x, kBig, b4.z), fma_sat(s23.y, kBig, b4.w));
-            const float2 ir01 = make_float2(fma_sat(s01.x, kBig, rbig), fma_sat(s01.y, kBig, rbig));
-            const float2 ir23 = make_float2(fma_sat(s23.x, kBig, rbig), fma_sat(s23.y, kBig, rbig));
+            const float2 ir01 = make_float2(fset_ge(s01.x, thr_r), fset_ge(s01.y, thr_r));  // ALU pipe
+            const float2 ir23 = make_float2(fset_ge(s23.x, thr_r), fset_ge(s23.y, thr_r));
             const float2 g01 = __fadd2_rn(ic01, ir01), g23 = __fadd2_rn(ic23, ir23);
             la = __ffma2_rn(g01, s01, la);
             lb = __ffma2_rn(g23, s23, lb);
             rca = __fadd2_rn(rca, ir01);
             rcb = __fadd2_rn(rcb, ir23);
             if (kRank) {
-                rka = __fadd2_rn(rka, make_float2(fma_sat(s01.x, kBig, kbig), fma_sat(s01.y, kBig, kbig)));
-                rkb = __fadd2_rn(rkb, make_float2(fma_sat(s23.x, kBig, kbig), fma_sat(s23.y, kBig, kbig)));
+                rka = __fadd2_rn(rka, make_float2(fset_ge(s01.x, thr_k), fset_ge(s01.y, thr_k)));
+                rkb = __fadd2_rn(rkb, make_float2(fset_ge(s23.x, thr_k), fset_ge(s23.y, thr_k)));
             }
             // column counts: the four 0/1 indicators packed into 6-bit fields of one exact fp32 integer
             // (ic0 + 64 ic1 + 4096 ic2 + 262144 ic3 < 2^19), converted once and summed over the warp's
@@ -740,8 +749,13 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         // ====================================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+            // K-major 128B-swizzled operands: descriptor = {start >> 4 | LBO 16 B, SBO 1024 B | version | swizzle}.
+            // Only the start address changes, linearly: one running low word, adds instead of rebuilds.
+            const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+            constexpr uint32_t kStageLo = L::kStageBytes >> 4, kYLo = (BM * BK * 2) >> 4, kKLo = (UK * 2) >> 4;
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, lo = lo0;
             int64_t it = 0;
             for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
                 const int as = (int)(it & 1);
@@ -751,18 +765,15 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                 for (int kb = 0; kb < c.kblocks; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t sx = smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sy = sx + BM * BK * 2;
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k) {
-                        const uint64_t da = make_smem_desc(sx + k * UK * 2, 16, 1024);
-                        const uint64_t db = make_smem_desc(sy + k * UK * 2, 16, 1024);
-                        umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_f16_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(empty + stage);  // stage reusable once these MMAs have read it
+                    lo += kStageLo;
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
+                        lo = lo0;
                     }
                 }
                 umma_commit(acc_full + as);  // accumulator complete -> epilogue
@@ -834,6 +845,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         os.tmap = &tm_out;
         os.slab = 0;
         os.mask = L::kOutBufs - 1;
+        os.skip_store = c.diag_only < 0;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
             const int as = (int)(it & 1);
@@ -898,6 +910,8 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
 }
 
 // ------------------------------------------------------------------------------------ host
+static int g_skip_store = 0;  // measurement hook: pb2_debug_force_bn(bn | 0x10000)
+
 static int pick_bn(int64_t rows, int64_t cols, bool stores_g) {
     // widest tile that still yields at least ~one tile per SM; small problems are latency bound.
     // (128 x 192 tiles with 12 epilogue warps exist for the gradient-matrix producers -- force_bn 192 --
@@ -941,7 +955,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.n_rb = (int)((rows + BM - 1) / BM);
     c.n_cb = (int)((cols + BN - 1) / BN);
     c.n_tiles = (int64_t)c.n_rb * c.n_cb;
-    c.diag_only = 0;
+    c.diag_only = g_skip_store ? -1 : 0;
     if (std::is_same<Policy, DiagPolicy>::value) {  // paired rows: only the diagonal tiles
         c.diag_only = 1;
         c.n_cb = 0;
@@ -997,6 +1011,8 @@ using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
 extern "C" int pb2_debug_force_bn(int bn) {
+    g_skip_store = (bn >> 16) & 1;
+    bn &= 0xffff;
     g_force_bn = (bn == 64 || bn == 128 || bn == 192 || bn == 256) ? bn : 0;
     return PB2_OK;
 }

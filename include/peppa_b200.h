@@ -187,6 +187,14 @@ int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, int64_t ldv
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
                       float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);
 
+/* MIL-NCE finish with K candidates per clip (pig/loss.py:19-25, x viewed as [N, N, K]):
+ *   grad_x[r] = coef * ( p_r * 2^-13 - sum_{k < group} w[r*group + k] * y[(r*group + k) / y_div] ),
+ * w = softmax over the K paired logits of a clip.  Video side: group = K, y_div = 1, y = audio rows;
+ * audio side: group = 1, y_div = K, y = video rows. */
+int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, const float* w, int64_t rows, int group, int y_div,
+                        int dim, int64_t ldy, float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
+                        void* stream);
+
 /* out[0] (=|+=) alpha * ( sum_k partials[k] + sum_k (margin - diag[k]) * cnt[k] ); either group may be
  * NULL.  Completes the hinge loss from pb2_sim_hinge's partials and indicator counts (double
  * accumulation, fixed order: deterministic). */
@@ -206,6 +214,17 @@ int pb2_milnce_loss(const float* lse_row, const float* lse_col, const float* dia
  * floats followed by 2*n int32 of scratch for the indicator counts. */
 int pb2_contrastive_matrix(const float* m, int64_t n, int64_t ld, float margin, float* loss_partial, int n_partials,
                            float* grad_m, int64_t ld_grad, float coef_host, const float* coef_dev, void* stream);
+
+/* ---- encoder tail: nn.Linear(n_in, n_out) followed by F.normalize(p=2, dim=1), the last
+ * two stages of both reference encoders (pig/models.py:96-109, :130-150), as one tcgen05 kernel.
+ *   y = x W^T + bias  (x [rows, n_in] bf16, W [n_out, n_in] bf16 in nn.Linear layout, bias fp32 or NULL)
+ *   out = bf16( y / max(||y||, eps) )   [rows, n_out], n_out % 64 == 0, n_out <= 512, n_in % 64 == 0
+ *   rinv[r] = 1 / ||out_r||  (of the ROUNDED row: what pb2_sim_* take as rinv_x / rinv_y; optional)
+ *   norm[r] = ||y_r||        (for the backward's normalisation Jacobian; optional)
+ * y itself never reaches HBM: one CTA holds all n_out features of its 128 rows in TMEM. */
+int pb2_project_normalize(const void* x, const void* w, const float* bias, int64_t rows, int n_in, int n_out,
+                          int64_t ldx, int64_t ldw, float eps, void* out, int64_t ld_out, float* rinv, float* norm,
+                          void* stream);
 
 /* number of CTAs the persistent similarity kernels launch on the current device */
 int pb2_sim_grid(void);

@@ -52,10 +52,31 @@ def bits(x):
     return x.bfloat16().view(torch.int16).numpy().view(np.uint16)
 
 
+def milnce_k_fixtures(pig):
+    """MILNCELoss with K = len(A) / len(V) > 1 audio candidates per video (pig/loss.py:19-25 views the
+    logits as [N, N, K]); forward value and autograd gradients of the reference itself."""
+    for n, k, alpha in [(16, 3, 4.0), (40, 2, 0.5)]:
+        V, _ = embeddings(n, alpha, seed=23)
+        g = torch.Generator().manual_seed(29)
+        # candidate k of clip i: a noisy copy of the clip's video embedding (un-normalised scale ~3 so that
+        # the K paired logits differ visibly)
+        A = (3.0 * V.repeat_interleave(k, dim=0) + torch.randn(n * k, V.shape[1], generator=g)).bfloat16().float()
+        V = (3.0 * V).bfloat16().float()
+        v = V.clone().requires_grad_(True)
+        a = A.clone().requires_grad_(True)
+        loss = pig.loss.MILNCELoss()(v, a)
+        loss.backward()
+        np.savez_compressed(os.path.join(OUT, f"milnce_n{n}_k{k}.npz"), V=bits(V), A=bits(A), k=np.int64(k),
+                            loss=loss.detach().numpy(), dV=v.grad.numpy(), dA=a.grad.numpy())
+
+
 def main():
     pig = _import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed summation order for the fixtures
+    milnce_k_fixtures(pig)
+    if len(sys.argv) > 1 and sys.argv[1] == "milnce_k":
+        return
 
     # ---- loss + recall fixtures ------------------------------------------------------
     for n, alpha in [(8, 4.0), (8, 0.5), (64, 4.0), (100, 0.5), (257, 4.0)]:

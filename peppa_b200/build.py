@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libpeppa_b200.so")
 SELFTEST = os.path.join(CSRC, "pb2_selftest")
 
-LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu"]
+LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v",

@@ -434,6 +434,40 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// MIL-NCE with K candidates per clip (pig/loss.py:19-25 views x as [N, N, K]): the positive term of row r
+// is sum_k w[r * group + k] * y[(r * group + k) / y_div] with w = softmax_k of the K paired logits.
+//   video side: group = K, y_div = 1 (the clip's K audio rows);  audio side: group = 1, y_div = K (its video).
+__global__ void __launch_bounds__(256)
+    milnce_finish_k_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ y,
+                           const float* __restrict__ w, int64_t rows, int group, int y_div, int dim, int64_t ldy,
+                           float coef_host, const float* __restrict__ coef_dev, float* __restrict__ grad,
+                           int64_t ld_grad) {
+    const float coef = coef_host * (coef_dev ? coef_dev[0] : 1.f);
+    const int vec_per_row = dim / 8;
+    const int64_t total = rows * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int d = (int)(i % vec_per_row) * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < group; ++k) {
+            const int64_t c = r * group + k;
+            float b[8];
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(y + (c / y_div) * ldy + d), b);
+            const float wk = w[c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(wk, b[j], acc[j]);
+        }
+        const float4 p0 = *reinterpret_cast<const float4*>(p + r * ld_p + d);
+        const float4 p1 = *reinterpret_cast<const float4*>(p + r * ld_p + d + 4);
+        const float s = 1.0f / 8192.0f;
+        float* gr = grad + r * ld_grad + d;
+        *reinterpret_cast<float4*>(gr) = make_float4(coef * (p0.x * s - acc[0]), coef * (p0.y * s - acc[1]),
+                                                     coef * (p0.z * s - acc[2]), coef * (p0.w * s - acc[3]));
+        *reinterpret_cast<float4*>(gr + 4) = make_float4(coef * (p1.x * s - acc[4]), coef * (p1.y * s - acc[5]),
+                                                         coef * (p1.z * s - acc[6]), coef * (p1.w * s - acc[7]));
+    }
+}
+
 // ------------------------------------------------------------------- resampled recall (f1)
 // pig/metrics.py:54-77 draws n_samples subsets of `size` clips and ranks each 100 x 100 sub-matrix with
 // its own GEMM + argsort loop.  Here the G x G score matrix is computed once (pb2_sim_matrix) and every
@@ -678,6 +712,21 @@ extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, in
     milnce_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const __nv_bfloat16*)y, rows, dim, ldy,
                                                                 coef_host, coef_dev, grad_x, ld_grad);
     return check_launch("milnce_finish");
+}
+
+extern "C" int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, const float* w, int64_t rows, int group,
+                                   int y_div, int dim, int64_t ldy, float coef_host, const float* coef_dev,
+                                   float* grad_x, int64_t ld_grad, void* stream) {
+    if (rows <= 0) return PB2_OK;
+    if (!p || !y || !w || !grad_x) return set_error(PB2_ERR_ARG, "milnce_finish_k: null");
+    if (group < 1 || y_div < 1) return set_error(PB2_ERR_ARG, "milnce_finish_k: group and y_div must be >= 1");
+    if (dim % 8 != 0 || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "milnce_finish_k: alignment");
+    const int64_t total = rows * (dim / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    milnce_finish_k_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const __nv_bfloat16*)y, w, rows, group, y_div,
+                                                                  dim, ldy, coef_host, coef_dev, grad_x, ld_grad);
+    return check_launch("milnce_finish_k");
 }
 
 extern "C" int pb2_contrastive_matrix(const float* m, int64_t n, int64_t ld, float margin, float* loss_partial,

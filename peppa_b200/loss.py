@@ -99,42 +99,66 @@ class _HingeFn(torch.autograd.Function):
 
 
 class _MilNceFn(torch.autograd.Function):
+    """pig/loss.py:13-26.  x = V A^T / tau is viewed as [N, N, K] with K = len(A) / len(V) candidates per
+    clip (audio rows i*K .. i*K+K-1 belong to video i):
+        num_i = LSE_k x[i, i, k]
+        den_i = LSE( x[i, :, :]  U  x[:, i, :] ) = logaddexp(row LSE of video i, LSE_k column LSE of audio i*K+k)
+        loss  = mean_i (den_i - num_i)
+    Neither x nor its [N, 2NK] concatenation is materialised: two fused row-LSE passes give the statistics,
+    the backward recomputes x tile by tile into the fp16 gradient matrix
+        G[i, c] = exp(x_ic - den_i) + exp(x_ic - den_{c // K})      (the diagonal softmax term is rank-K)."""
+
     @staticmethod
     def forward(ctx, V, A, inv_tau):
         if V.dim() != 2 or A.dim() != 2:
             raise RuntimeError("MILNCELoss expects 2-D V and A")
-        if A.shape[0] != V.shape[0]:
-            raise NotImplementedError(
-                "MILNCELoss with K = len(A) / len(V) > 1 candidates per video is not implemented by the fused "
-                "path (the reference repo only ever uses K == 1)")
+        n = V.shape[0]
+        if n == 0 or A.shape[0] % n != 0 or A.shape[0] == 0:   # the reference's x.view(N, N, -1) fails the same way
+            raise RuntimeError(f"shape '[{n}, {n}, -1]' is invalid for input of size {n * A.shape[0]}")
+        k = A.shape[0] // n
         vb = ops.as_bf16_rows(V)
         ab = ops.as_bf16_rows(A, device=vb.device)
         dev = vb.device
-        n = vb.shape[0]
+        nk = n * k
         need_grad = any(ctx.needs_input_grad)
-        blocks = _blocks(n, _MAX_BLOCK)
+        vblocks, ablocks = _blocks(n, _MAX_BLOCK), _blocks(nk, _MAX_BLOCK)
         lse_row = lse_col = None
-        for (c0, c1) in blocks:   # x = V A^T: row LSE over audio columns, column LSE = row LSE of A V^T
+        for (c0, c1) in ablocks:   # rows = videos, columns = audio candidates
             lse_row = ops.sim_lse_rows(vb, ab[c0:c1], scale=inv_tau, lse=lse_row)
+        for (c0, c1) in vblocks:   # LSE over videos for every audio candidate = row LSE of A V^T
             lse_col = ops.sim_lse_rows(ab, vb[c0:c1], scale=inv_tau, lse=lse_col)
-        diag = ops.pair_dot(vb, ab)
-        if inv_tau != 1.0:
-            diag = diag * inv_tau
-        loss, den = ops.milnce_loss(lse_row, lse_col, diag)
+        if k == 1:
+            diag = ops.pair_dot(vb, ab)
+            if inv_tau != 1.0:
+                diag = diag * inv_tau
+            loss, den = ops.milnce_loss(lse_row, lse_col, diag)
+            den_a, w = den, None
+        else:
+            iv = torch.arange(n, device=dev, dtype=torch.int64).repeat_interleave(k)
+            pos = ops.pair_dot(vb, ab, ix=iv) * inv_tau                      # x[i, i, k], [N*K]
+            num = ops.lse_combine(pos.view(n, k).t().contiguous())           # LSE over the K candidates
+            col_grp = ops.lse_combine(lse_col.view(n, k).t().contiguous())   # x[:, i, :] merged over k
+            loss, den = ops.milnce_loss(lse_row, col_grp, num)
+            den_a = den.repeat_interleave(k)                                 # den of the clip an audio row belongs to
+            w = torch.exp(pos - num.repeat_interleave(k)).contiguous()       # softmax_k of the paired logits
         if need_grad:
-            acc = len(blocks) > 1
+            acc_v, acc_a = len(ablocks) > 1, len(vblocks) > 1
             vh, ah = ops.rows_scale_f16(vb), ops.rows_scale_f16(ab)
-            pv = torch.zeros(n, vb.shape[1], dtype=torch.float32, device=dev) if acc else \
-                torch.empty(n, vb.shape[1], dtype=torch.float32, device=dev)
-            pa = torch.zeros_like(pv) if acc else torch.empty_like(pv)
-            for (r0, r1) in blocks:
-                for (c0, c1) in blocks:
+            d = vb.shape[1]
+            pv = (torch.zeros if acc_v else torch.empty)(n, d, dtype=torch.float32, device=dev)
+            pa = (torch.zeros if acc_a else torch.empty)(nk, d, dtype=torch.float32, device=dev)
+            for (r0, r1) in vblocks:
+                for (c0, c1) in ablocks:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den[c0:c1], g, ld, scale=inv_tau)
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc)
-                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc)
-            dV = ops.milnce_finish(pv, ab, inv_tau / n)
-            dA = ops.milnce_finish(pa, vb, inv_tau / n)
+                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den_a[c0:c1], g, ld, scale=inv_tau)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc_v)
+                    ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc_a)
+            if k == 1:
+                dV = ops.milnce_finish(pv, ab, inv_tau / n)
+                dA = ops.milnce_finish(pa, vb, inv_tau / n)
+            else:
+                dV = ops.milnce_finish_k(pv, ab, w, n, k, 1, inv_tau / n)
+                dA = ops.milnce_finish_k(pa, vb, w, nk, 1, k, inv_tau / n)
             ctx.save_for_backward(dV[:, :V.shape[1]], dA[:, :A.shape[1]])
             ctx.meta = (V.dtype, V.device, A.dtype, A.device)
         return loss.to(V.device)
@@ -151,7 +175,7 @@ class _MilNceFn(torch.autograd.Function):
 
 class MILNCELoss(torch.nn.Module):
     """The loss implemented is: log(pos/(2 * pos + neg)) = log(pos/(pos + neg/2)) - log(2)
-    (pig/loss.py:5-26; MIL-NCE of Miech et al. with one candidate per clip).
+    (pig/loss.py:5-26; MIL-NCE of Miech et al.; K = len(A) / len(V) candidates per clip, K = 1 in the reference repo).
 
     ``temperature`` is an extension (default 1.0 = the reference, which has none): logits are divided by it."""
 

@@ -256,6 +256,33 @@ def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
     return grad
 
 
+def milnce_finish_k(p, y, w, rows, group, y_div, coef_host=1.0):
+    """MIL-NCE finish with K candidates per clip: see pb2_milnce_finish_k."""
+    d = y.shape[1]
+    grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        check(_cabi.lib().pb2_milnce_finish_k(_ptr(p), p.stride(0), _ptr(y), _ptr(w), rows, int(group), int(y_div), d,
+                                              y.stride(0), float(coef_host), _ptr(None), _ptr(grad), grad.stride(0),
+                                              _stream(y.device)), "milnce_finish_k")
+    return grad
+
+
+def project_normalize(x_bf16, w_bf16, bias=None, eps=1e-12):
+    """bf16( normalize(x W^T + b) ) with the fp32 1/||row|| of the rounded rows and ||y||: the encoder tail
+    (pig/models.py:96-109, :130-150) in one launch.  x [rows, n_in], W [n_out, n_in] (nn.Linear layout)."""
+    rows, n_in = x_bf16.shape
+    n_out = w_bf16.shape[0]
+    dev = x_bf16.device
+    out = torch.empty(rows, n_out, dtype=torch.bfloat16, device=dev)
+    rinv = torch.empty(rows, dtype=torch.float32, device=dev)
+    norm = torch.empty(rows, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("project_normalize", 2.0 * rows * n_in * n_out, dev):
+        check(_cabi.lib().pb2_project_normalize(_ptr(x_bf16), _ptr(w_bf16), _ptr(bias), rows, n_in, n_out, x_bf16.stride(0),
+                                                w_bf16.stride(0), float(eps), _ptr(out), out.stride(0) if rows else n_out,
+                                                _ptr(rinv), _ptr(norm), _stream(dev)), "project_normalize")
+    return out, rinv, norm
+
+
 _STEP_WORKSPACE = {}      # (device, n, d) -> uint8 workspace, reused across steps (stream-ordered reuse)
 
 

@@ -344,10 +344,34 @@ def test_api_conformance_dtypes_layouts(pb):
     assert (got.cpu() - O.triplet_accuracy(a3, p3, n3, dim=1, discrete=False)).abs().max() < 2e-6
 
 
-def test_milnce_k_candidates_not_silently_wrong(pb):
-    V, A = emb(16, 4.0)
-    with pytest.raises(NotImplementedError):
-        pb.loss.MILNCELoss()(V.cuda(), torch.cat([A, A]).cuda())
+@pytest.mark.parametrize("name", golden_files("milnce_n"))
+def test_milnce_k_candidates_golden(pb, name):
+    """MILNCELoss with K = len(A) / len(V) > 1 candidates per video against the reference's own outputs."""
+    g = load_golden(name)
+    v = g["V"].cuda().requires_grad_(True)
+    a = g["A"].cuda().requires_grad_(True)
+    loss = pb.loss.MILNCELoss()(v, a)
+    loss.backward()
+    assert rel_err(loss, g["loss"]) < 1e-3
+    assert rel_err(v.grad, g["dV"]) < 1e-3 and rel_err(a.grad, g["dA"]) < 1e-3
+
+
+def test_milnce_k_candidates_oracle_and_errors(pb):
+    from oracle import pig_oracle as O
+    gen = torch.Generator().manual_seed(5)
+    n, k = 600, 4
+    V = (2.0 * torch.nn.functional.normalize(torch.randn(n, 512, generator=gen), dim=1)).bfloat16().float()
+    A = (2.0 * V.repeat_interleave(k, dim=0) + 0.5 * torch.randn(n * k, 512, generator=gen)).bfloat16().float()
+    v0, a0 = V.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    ref = O.milnce_loss(v0, a0)
+    ref.backward()
+    v, a = V.cuda().requires_grad_(True), A.cuda().requires_grad_(True)
+    loss = pb.loss.MILNCELoss()(v, a)
+    loss.backward()
+    assert rel_err(loss, ref.detach()) < 1e-3
+    assert rel_err(v.grad, v0.grad) < 1e-3 and rel_err(a.grad, a0.grad) < 1e-3
+    with pytest.raises(RuntimeError, match="invalid for input of size"):     # the reference's view() error
+        pb.loss.MILNCELoss()(V.cuda(), A[:n * k - 1].cuda())
 
 
 def test_install_patches_a_pig_package(pb):
@@ -461,3 +485,57 @@ def test_grad_gemm_stream_k(pb, tr, r, c, d):
     assert ((sk - ref).abs().max() / scale).item() < 1e-5
     assert ((acc - (1 + 0.5 * ref)).abs().max() / scale).item() < 1e-5
     assert torch.equal(sk, sk2)
+
+
+@pytest.mark.parametrize("rows,n_in,n_out,bias", [(1000, 512, 512, True), (5, 512, 512, False), (300, 28, 512, True),
+                                                  (4096, 768, 256, True), (129, 512, 64, True), (2000, 1024, 384, True)])
+def test_encoder_tail_project_normalize(pb, rows, n_in, n_out, bias):
+    """nn.Linear + F.normalize of the reference encoders (pig/models.py:96-109, :130-150) as one
+    tcgen05 kernel; bf16 operands, fp32 accumulate, bf16 output.  Tolerances: the output is the bf16 rounding of
+    the fp32 result (2^-8 of the largest component); rinv / norm are fp32 statistics."""
+    from peppa_b200 import encoder
+    g = torch.Generator().manual_seed(rows + n_in)
+    x = torch.randn(rows, n_in, generator=g).bfloat16().float()
+    lin = torch.nn.Linear(n_in, n_out, bias=bias)
+    with torch.no_grad():
+        lin.weight.copy_(lin.weight.bfloat16().float())
+    ref_in = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.normalize(lin(ref_in), p=2, dim=1)
+    mod = encoder.ProjectNormalize.from_linear(lin).cuda()
+    xin = x.cuda().requires_grad_(True)
+    out, rinv = mod(xin, return_rinv=True)
+    assert out.dtype == torch.bfloat16 and out.shape == (rows, n_out) and rinv.shape == (rows,)
+    assert (out.float().cpu() - ref.detach()).abs().max().item() <= 2.0 ** -8 * ref.detach().abs().max().item() + 1e-6
+    assert rel_err(rinv, 1.0 / out.float().norm(dim=1)) < 1e-5
+    # backward through the normalisation Jacobian and the projection
+    w = torch.randn(rows, n_out, generator=g)
+    (ref * w).sum().backward()
+    (out.float() * w.cuda()).sum().backward()
+    assert rel_err(xin.grad, ref_in.grad) < 2e-2
+    assert rel_err(mod.weight.grad, lin.weight.grad) < 2e-2
+    if bias:
+        assert rel_err(mod.bias.grad, lin.bias.grad) < 2e-2
+
+
+def test_encoder_tail_feeds_the_loss(pb):
+    """The tail's (bf16 rows, rinv) pair is what the scoring kernels consume: TripletLoss on the fused
+    embeddings equals the reference pipeline project -> normalize -> TripletLoss on the same bf16 weights."""
+    from oracle import pig_oracle as O
+    from peppa_b200 import encoder
+    g = torch.Generator().manual_seed(3)
+    n = 384
+    fv, fa = torch.randn(n, 512, generator=g).bfloat16().float(), torch.randn(n, 512, generator=g).bfloat16().float()
+    fa = (fa + 0.5 * fv).bfloat16().float()        # weakly related pairs: a non-trivial hinge loss
+    pv, pa = torch.nn.Linear(512, 512), torch.nn.Linear(512, 512)
+    with torch.no_grad():
+        pa.weight.copy_(pv.weight)
+        pa.bias.copy_(pv.bias)
+        for m in (pv, pa):
+            m.weight.copy_(m.weight.bfloat16().float())
+    V = torch.nn.functional.normalize(pv(fv), dim=1)
+    A = torch.nn.functional.normalize(pa(fa), dim=1)
+    ref = O.triplet_loss(V.detach(), A.detach(), 0.2)
+    ev = encoder.ProjectNormalize.from_linear(pv).cuda()(fv.cuda())
+    ea = encoder.ProjectNormalize.from_linear(pa).cuda()(fa.cuda())
+    got = pb.loss.TripletLoss(0.2)(ev, ea)
+    assert ref.item() > 1e-3 and rel_err(got, ref) < 5e-3     # embeddings are bf16-rounded before the loss

@@ -112,3 +112,17 @@ def test_triplet_sampler_and_scores_match_reference():
     sc = O.score_triplets(g["V"], g["A"], dur, n_samples=5)
     assert torch.equal(sc["accuracy"], g["score_accuracy"]) and torch.equal(sc["duration"], g["score_duration"])
     assert "NameError" in str(g["head_error"])      # the reference's own score_triplets is broken at HEAD
+
+
+@pytest.mark.parametrize("name", golden_files("milnce_n"))
+def test_milnce_k_candidates_bit_exact(name):
+    """MILNCELoss with K > 1 audio candidates per video (pig/loss.py:19-25): oracle == reference, bit for bit."""
+    g = load_golden(name)
+    v = g["V"].clone().requires_grad_(True)
+    a = g["A"].clone().requires_grad_(True)
+    torch.set_num_threads(1)
+    loss = O.milnce_loss(v, a)
+    loss.backward()
+    assert a.shape[0] == int(g["k"]) * v.shape[0]
+    assert np.array_equal(loss.detach().numpy(), g["loss"])
+    assert torch.equal(v.grad, g["dV"]) and torch.equal(a.grad, g["dA"])

@@ -40,7 +40,11 @@ DIM = 512
 MARGIN = 0.2
 TOP_N = 10
 METRIC = {"gallery": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "train1024": "similarity pairs/sec (loss fwd+bwd)",
-          "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)"}
+          "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)",
+          "encoder_tail": "rows/sec (Linear 512x512 + L2-normalise + bf16 + rinv)"}
+
+
+UNIT = {"triplets1m": "triplets/s", "encoder_tail": "rows/s"}
 
 
 # ----------------------------------------------------------------------------------- helpers
@@ -203,7 +207,14 @@ def cpu_sample(workload, n_s, steps, warmup):
     workload; returns (metric value, seconds per step, description of the sample)."""
     import torch
     from oracle import pig_oracle as O
-    if workload == "triplets1m":
+    if workload == "encoder_tail":
+        t = n_s * 16
+        g = torch.Generator().manual_seed(666)
+        x = torch.randn(t, DIM, generator=g).bfloat16().float()
+        lin = torch.nn.Linear(DIM, DIM)
+        step, units = (lambda: torch.nn.functional.normalize(lin(x), p=2, dim=1)), t
+        what = f"{t} rows: nn.Linear(512, 512) + F.normalize (pig/models.py:105-109), torch-CPU fp32"
+    elif workload == "triplets1m":
         t = n_s * 32
         g = torch.Generator().manual_seed(666)
         a, p, n = (torch.randn(t, DIM, generator=g).bfloat16().float() for _ in range(3))
@@ -240,7 +251,7 @@ def cpu_sample(workload, n_s, steps, warmup):
 def cpu_baseline(workload, n_s):
     import torch
     value, dt, what = cpu_sample(workload, n_s, 1, 1)
-    return {"value": value, "unit": "triplets/s" if workload == "triplets1m" else "pairs/s", "cores": torch.get_num_threads(),
+    return {"value": value, "unit": UNIT.get(workload, "pairs/s"), "cores": torch.get_num_threads(),
             "kind": "port", "sample": f"{what}; reference algorithm (oracle port); {dt:.3f} s per step; host has {os.cpu_count()} cpus"}
 
 
@@ -249,7 +260,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     value, dt, what = cpu_sample(args.workload, args.cpu_sample, args.steps, args.warmup)
-    unit = "triplets/s" if args.workload == "triplets1m" else "pairs/s"
+    unit = UNIT.get(args.workload, "pairs/s")
     line = {
         "impl": "reference", "metric": METRIC[args.workload], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -402,6 +413,38 @@ def bench_triplets1m(args, device, sync):
                    "bytes_per_triplet": 3 * DIM * 2 + 4, "l2": "3.2 GB of inputs per step exceed the 126 MB L2; no flush needed"}}
 
 
+def bench_encoder_tail(args, device, sync):
+    """Linear(512, 512) + L2-normalise + bf16 + rinv for 2^20 rows (one modality of the
+    gallery), fused in one tcgen05 kernel (pig/models.py:96-109, :130-150)."""
+    import torch
+    from peppa_b200 import encoder, ops
+    n = 1 << 20
+    g = torch.Generator(device=device).manual_seed(666)
+    x = torch.randn(n, DIM, generator=g, device=device).bfloat16()
+    w = (torch.randn(DIM, DIM, generator=g, device=device) / DIM ** 0.5).bfloat16()
+    b = torch.randn(DIM, generator=g, device=device) * 0.1
+    steps, warm = max(args.steps, 20), max(args.warmup, 3)
+    m = measure(lambda: ops.project_normalize(x, w, b)[1], steps, warm, sync, device)
+    host = x.cpu().pin_memory()
+    xin = torch.empty_like(x)
+    mod = encoder.ProjectNormalize(DIM, DIM).to(device)
+
+    def run_e2e():
+        xin.copy_(host, non_blocking=True)
+        out, rinv = mod(xin, return_rinv=True)
+        return rinv.sum().item()
+
+    ms_e2e = timed(run_e2e, 3, 1, sync)
+    roof, table = roofline_of(m["kernels"], "tensor")
+    return {
+        "units": float(n), "unit": "rows/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table, "launches": m["launches"],
+        "clocks": m["clocks"], "h2d": n * DIM * 2, "d2h": 4, "flops_per_unit": 2.0 * DIM * DIM, "scaling": "weak",
+        "check": {"mean_rinv": m["out"].mean().item()}, "steps_used": steps,
+        "config": {"workload": "encoder_tail (SURVEY 8f row 3): Linear(512,512) + L2-normalise + bf16 + rinv, 2^20 rows", "rows": n,
+                   "dim": DIM, "hbm_bytes_per_row": 2 * DIM * 2 + 8,
+                   "l2": "1 GiB in + 1 GiB out per step exceed the 126 MB L2; the 512 KiB weight is L2 resident by design"}}
+
+
 def line_from(res, args, world, workload):
     pk = peaks()
     value = res["units"] / (res["ms"] * 1e-3)
@@ -428,7 +471,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m"])
+    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail"])
     ap.add_argument("--gallery-n", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-extras", action="store_true")
@@ -466,7 +509,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    single = {"train1024": bench_train1024, "retrieval16k": bench_retrieval16k, "triplets1m": bench_triplets1m}
+    single = {"train1024": bench_train1024, "retrieval16k": bench_retrieval16k, "triplets1m": bench_triplets1m,
+              "encoder_tail": bench_encoder_tail}
     if args.workload == "gallery":
         line = line_from(bench_gallery(args, rank, world, device, sync, all_max), args, world, "gallery")
     else:

@@ -145,6 +145,14 @@ int pb2_grad_gemm_ws(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_co
                      const void* z, int z_dtype, int dim, int64_t ldz, float alpha, int accumulate, float* out,
                      int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Both backward products of one gradient-matrix block in ONE launch (a batch-1k training step is launch
+ * bound): out0[g_rows, dim] = alpha * G * Z0 (Z0 is [g_cols, dim]) and out1[g_cols, dim] = alpha * G^T * Z1
+ * (Z1 is [g_rows, dim]).  Used when every 128 x 64 tile of both products fits the machine at once; larger
+ * shapes run as two pb2_grad_gemm launches. */
+int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
+                       const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
+                       float* out1, int64_t ld_out0, int64_t ld_out1, void* stream);
+
 /* out = fp16(x * rinv) (rinv == NULL: plain bf16 -> fp16 conversion): the embedding operand of
  * pb2_grad_gemm.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and fp16 holds every
  * normalised bf16 embedding value with 3 extra significand bits. */

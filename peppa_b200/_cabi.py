@@ -43,6 +43,7 @@ SIGNATURES = {
     "pb2_grad_gemm": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p],
     "pb2_grad_gemm_workspace": [],
     "pb2_grad_gemm_ws": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p, _i64, _p],
+    "pb2_grad_gemm_dual": [_p, _i, _i64, _i64, _i64, _p, _p, _i, _i, _i64, _i64, _f, _p, _p, _i64, _i64, _p],
     "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
     "pb2_hinge_prep": [_p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],

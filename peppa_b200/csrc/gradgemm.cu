@@ -65,8 +65,8 @@ struct Smem {
 // Calls f(rb, cb, kb0, kb1) for every segment of this CTA (or CTA pair), in the same order for all warp
 // roles.  rb counts row blocks of BM * kCtas rows.
 template <int kCtas, class F>
-__device__ __forceinline__ void for_each_segment(const Args& a, F&& f) {
-    const int unit = (int)blockIdx.x / kCtas, n_units = (int)gridDim.x / kCtas;
+__device__ __forceinline__ void for_each_segment(const Args& a, int block, int nblocks, F&& f) {
+    const int unit = block / kCtas, n_units = nblocks / kCtas;
     if (a.n_groups > 0) {
         const int g = unit / a.n_cb, cb = unit % a.n_cb;
         if (g >= a.n_groups) return;
@@ -87,10 +87,10 @@ __device__ __forceinline__ void for_each_segment(const Args& a, F&& f) {
 // kCtas == 2: CTA pairs (cluster of 2) drive one tcgen05.mma.cta_group::2 of M = 256, N = BN per k-step;
 // each CTA stages its own 128 rows of A and BN/2 columns of B, accumulates its 128 x BN in its own TMEM
 // and runs its own epilogue.  See common.cuh for the protocol.
+// `block` of `nblocks`: this CTA's index within ITS product (the dual launch runs two products in one grid).
 template <bool kTranspose, int BN, int kCtas>
-__global__ void __launch_bounds__(kThreads, 1)
-    grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z,
-                     const Args a) {
+__device__ __forceinline__ void gg_body(const CUtensorMap& tm_g, const CUtensorMap& tm_z, const Args& a, const int block,
+                                        const int nblocks) {
     using L = Smem<BN, kCtas>;
     constexpr int BNL = BN / kCtas;  // B columns staged by this CTA
     // BN == 512 (pairs only): the 128 x 512 fp32 accumulator is all of TMEM, one stage -- the epilogue is not
@@ -130,17 +130,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (kCtas == 2) tmem_alloc_pair(tmem_slot, kAccStages * BN);
         else tmem_alloc(tmem_slot, kAccStages * BN);
     }
+    pdl_launch_dependents();
     tc_fence_before();
     if (kCtas == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == kTmaWarp) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for_each_segment<kCtas>(a, [&](int rb, int cb, int kb0, int kb1) {
+            for_each_segment<kCtas>(a, block, nblocks, [&](int rb, int cb, int kb0, int kb1) {
                 const int row0 = (rb * kCtas + (int)crank) * BM;
                 // this CTA's B columns: chunk q of 64 -> MMA q / (kUmmaN / kCtas / 64), half `crank` of its N
                 constexpr int kChunksPerMma = kUmmaN / kCtas / 64;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             int stage = 0;
             uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
             int64_t it = 0;
-            for_each_segment<kCtas>(a, [&](int, int, int kb0, int kb1) {
+            for_each_segment<kCtas>(a, block, nblocks, [&](int, int, int kb0, int kb1) {
                 const int as = (int)(it % kAccStages);
                 mbar_wait(acc_empty + as, (uint32_t)((it / kAccStages) & 1) ^ 1);
                 tc_fence_after();
@@ -239,19 +241,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int half = (warp - kEpiWarp0) >> 2;
         constexpr int kChunksPerHalf = BN / 64;
         int64_t it = 0;
-        for_each_segment<kCtas>(a, [&](int rb, int cb, int kb0, int kb1) {
+        for_each_segment<kCtas>(a, block, nblocks, [&](int rb, int cb, int kb0, int kb1) {
             const int as = (int)(it % kAccStages);
             const int64_t row = ((int64_t)rb * kCtas + crank) * BM + quad * 32 + lane;
             // stream-K: a tail segment parks its accumulators; a head segment folds its neighbour's in
             const bool park = kb0 > 0, fold = kb1 < a.kblocks;
-            const uint32_t peer = blockIdx.x + (uint32_t)(a.n_cb * kCtas);  // same tile slot, next group
+            const uint32_t peer = (uint32_t)block + (uint32_t)(a.n_cb * kCtas);  // same tile slot, next group
             if (fold) {
                 if (lane == 0) {
                     const long long t0 = clock64();
                     while (ld_acquire_u32(a.flags + peer) < (uint32_t)kEpiWarps) {
                         __nanosleep(200);
                         if (clock64() - t0 > PB2_WAIT_TIMEOUT_CYCLES) {
-                            printf("pb2: grad_gemm stream-K flag wait timed out (block %d)\n", blockIdx.x);
+                            printf("pb2: grad_gemm stream-K flag wait timed out (block %d)\n", block);
                             __trap();
                         }
                     }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tmem_ld32(t_lane + cbase, v);
                 tmem_ld_wait();
                 if (park) {  // [BN/4][128] float4: consecutive lanes (rows) write consecutive 16 bytes
-                    float4* dst = a.parts + ((size_t)blockIdx.x * (BN / 4) + cbase / 4) * BM + quad * 32 + lane;
+                    float4* dst = a.parts + ((size_t)block * (BN / 4) + cbase / 4) * BM + quad * 32 + lane;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         dst[j * BM] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (park) {  // publish: every lane's stores, then one release-increment per warp
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) red_release_add_u32(a.flags + blockIdx.x, 1u);
+                if (lane == 0) red_release_add_u32(a.flags + block, 1u);
             }
             if (fold) {  // all epilogue warps are past their reads of the peer's slot: re-arm its flag
                 named_bar_sync(1, kEpiWarps * 32);
@@ -331,24 +333,43 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
+template <bool kTranspose, int BN, int kCtas>
+__global__ void __launch_bounds__(kThreads, 1)
+    grad_gemm_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z,
+                     const Args a) {
+    gg_body<kTranspose, BN, kCtas>(tm_g, tm_z, a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Both backward products of one gradient-matrix block in ONE launch: CTAs [0, n0) compute out0 = G Z0, the
+// rest out1 = G^T Z1.  A batch-1k training step is launch bound (each of these GEMMs is ~64 short tiles), and
+// the two products are independent, so they share a grid instead of queueing behind each other.
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    grad_gemm_dual_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_z0,
+                          const __grid_constant__ CUtensorMap tm_g1, const __grid_constant__ CUtensorMap tm_z1, const Args a0,
+                          const Args a1, const int n0) {
+    if ((int)blockIdx.x < n0) gg_body<false, BN, 1>(tm_g0, tm_z0, a0, (int)blockIdx.x, n0);
+    else gg_body<true, BN, 1>(tm_g1, tm_z1, a1, (int)blockIdx.x - n0, (int)gridDim.x - n0);
+}
+
 static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
 
 constexpr int64_t kFlagBytes = 1024;  // flags of up to 256 CTAs, then the parked accumulators
 static int64_t workspace_bytes() { return kFlagBytes + (int64_t)sm_count() * BM * 512 * 4; }
 
+// Tensor maps and kernel arguments of one product (no stream-K decision yet).
 template <bool kTranspose, int BN, int kCtas>
-static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int z_fmt,
-                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, void* workspace,
-                  cudaStream_t st) {
-    CUtensorMap tg, tz;
+static int prepare(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int z_fmt, int dim,
+                   int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, CUtensorMap* tg, CUtensorMap* tz,
+                   Args* pa) {
     const int64_t m = kTranspose ? g_cols : g_rows;
     const int64_t k = kTranspose ? g_rows : g_cols;
-    int rc = make_tmap_2d(&tg, g, 2, (uint64_t)g_rows, (uint64_t)g_cols, (uint64_t)ld_g * 2, kTranspose ? 64 : BM, 64);
+    int rc = make_tmap_2d(tg, g, 2, (uint64_t)g_rows, (uint64_t)g_cols, (uint64_t)ld_g * 2, kTranspose ? 64 : BM, 64);
     if (rc) return rc;
-    rc = make_tmap_2d(&tz, z, 2, (uint64_t)k, (uint64_t)dim, (uint64_t)ldz * 2, 64, 64);
+    rc = make_tmap_2d(tz, z, 2, (uint64_t)k, (uint64_t)dim, (uint64_t)ldz * 2, 64, 64);
     if (rc) return rc;
     constexpr int kRowsPerUnit = BM * kCtas;  // output rows of one CTA (pair) tile
-    Args a;
+    Args& a = *pa;
     a.m = m;
     a.k = k;
     a.n_rb = (int)((m + kRowsPerUnit - 1) / kRowsPerUnit);
@@ -363,11 +384,23 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
     a.mn_sbo = g_mn_sbo;
     a.mn_kstep = g_mn_kstep;
     a.idesc = make_idesc(kRowsPerUnit, BN > 256 ? 256 : BN, (uint32_t)g_fmt, (uint32_t)z_fmt, kTranspose ? kMajorMN : kMajorK, kMajorMN);
-    // stream-K when whole tiles would leave part of the machine idle in the last wave and every group's
-    // range spans at least one full tile (so a row block is cut at most once)
     a.n_groups = 0;
     a.flags = nullptr;
     a.parts = nullptr;
+    return PB2_OK;
+}
+
+template <bool kTranspose, int BN, int kCtas>
+static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int z_fmt,
+                  int dim, int64_t ldz, float alpha, int accumulate, float* out, int64_t ld_out, void* workspace,
+                  cudaStream_t st) {
+    CUtensorMap tg, tz;
+    Args a;
+    int rc = prepare<kTranspose, BN, kCtas>(g, g_fmt, g_rows, g_cols, ld_g, z, z_fmt, dim, ldz, alpha, accumulate, out, ld_out,
+                                            &tg, &tz, &a);
+    if (rc) return rc;
+    // stream-K when whole tiles would leave part of the machine idle in the last wave and every group's
+    // range spans at least one full tile (so a row block is cut at most once)
     const int units = sm_count() / kCtas;  // CTAs or CTA pairs the machine runs at once
     if (workspace && a.n_cb <= units && units * kCtas <= 256) {
         const int groups = units / a.n_cb;
@@ -387,21 +420,36 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
         configured = true;
     }
     const int n_units = a.n_groups > 0 ? a.n_groups * a.n_cb : (int)std::min<int64_t>(a.n_tiles, units);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_units * kCtas));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = kCtas > 1 ? 1 : 0;
-    rc = check_cuda(cudaLaunchKernelEx(&cfg, kern, tg, tz, a), "grad_gemm launch");
+    rc = check_cuda(launch_ex(kern, (unsigned)(n_units * kCtas), (unsigned)kThreads, (size_t)smem, st, kCtas, tg, tz, a),
+                    "grad_gemm launch");
     if (rc) return rc;
     return check_launch("grad_gemm");
+}
+
+// out0 = G Z0 and out1 = G^T Z1 in one grid (every tile of both products resident at once).
+template <int BN>
+static int launch_dual(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0, const void* z1,
+                       int z_fmt, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0, float* out1, int64_t ld_out0,
+                       int64_t ld_out1, cudaStream_t st) {
+    CUtensorMap tg0, tz0, tg1, tz1;
+    Args a0, a1;
+    int rc = prepare<false, BN, 1>(g, g_fmt, g_rows, g_cols, ld_g, z0, z_fmt, dim, ldz0, alpha, 0, out0, ld_out0, &tg0, &tz0, &a0);
+    if (rc) return rc;
+    rc = prepare<true, BN, 1>(g, g_fmt, g_rows, g_cols, ld_g, z1, z_fmt, dim, ldz1, alpha, 0, out1, ld_out1, &tg1, &tz1, &a1);
+    if (rc) return rc;
+    auto kern = grad_gemm_dual_kernel<BN>;
+    constexpr int smem = Smem<BN, 1>::kTotal;
+    static bool configured = false;
+    if (!configured) {
+        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "grad_gemm_dual");
+        if (rc) return rc;
+        configured = true;
+    }
+    const int n0 = (int)a0.n_tiles, n1 = (int)a1.n_tiles;
+    rc = check_cuda(launch_ex(kern, (unsigned)(n0 + n1), (unsigned)kThreads, (size_t)smem, st, 1, tg0, tz0, tg1, tz1, a0, a1, n0),
+                    "grad_gemm_dual launch");
+    if (rc) return rc;
+    return check_launch("grad_gemm_dual");
 }
 
 static int g_pair_mode = -1;  // test hook (pb2_debug_gg_pair): -1 = automatic, 0 = never, 1 = whenever legal
@@ -421,6 +469,26 @@ extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep)
 extern "C" int pb2_debug_gg_pair(int mode) {
     gg::g_pair_mode = mode;
     return PB2_OK;
+}
+
+extern "C" int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
+                                  const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
+                                  float* out1, int64_t ld_out0, int64_t ld_out1, void* stream) {
+    if (g_rows <= 0 || g_cols <= 0) return PB2_OK;
+    if (!gmat || !z0 || !z1 || !out0 || !out1) return set_error(PB2_ERR_ARG, "grad_gemm_dual: null");
+    // one wave: every 128 x 64 tile of both products gets its own CTA; otherwise two ordinary launches
+    const int64_t tiles = ((g_rows + gg::BM - 1) / gg::BM + (g_cols + gg::BM - 1) / gg::BM) * (dim / 64);
+    const bool ok16 = (g_dtype == PB2_F16 || g_dtype == PB2_BF16) && (z_dtype == PB2_F16 || z_dtype == PB2_BF16);
+    if (dim <= 0 || dim % 64 != 0 || tiles > sm_count() || !ok16 || (reinterpret_cast<uintptr_t>(out0) & 15) ||
+        (reinterpret_cast<uintptr_t>(out1) & 15) || ld_out0 % 4 != 0 || ld_out1 % 4 != 0) {
+        int rc = pb2_grad_gemm(gmat, g_dtype, g_rows, g_cols, ld_g, 0, z0, z_dtype, dim, ldz0, alpha, 0, out0, ld_out0, stream);
+        if (rc) return rc;
+        return pb2_grad_gemm(gmat, g_dtype, g_rows, g_cols, ld_g, 1, z1, z_dtype, dim, ldz1, alpha, 0, out1, ld_out1, stream);
+    }
+    const int gf = g_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
+    const int zf = z_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
+    return gg::launch_dual<64>(gmat, gf, g_rows, g_cols, ld_g, z0, z1, zf, dim, ldz0, ldz1, alpha, out0, out1, ld_out0, ld_out1,
+                               (cudaStream_t)stream);
 }
 
 extern "C" int64_t pb2_grad_gemm_workspace(void) { return gg::workspace_bytes(); }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <utility>
 
 namespace pb2 {
 
@@ -18,5 +19,43 @@ int sm_count();                                     // SMs of the current device
 // `rows`, row pitch `ld_bytes`; box = box_cols x box_rows elements; out-of-bounds reads give 0.
 int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols);
+
+// Launch helper: optional thread-block cluster, and -- while a PdlScope is alive on this thread -- the
+// programmatic-stream-serialization attribute (programmatic dependent launch): the kernel may start while its
+// predecessor in the stream drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and
+// blocks in griddepcontrol.wait (pdl_wait() in common.cuh) until the predecessor's memory is visible.  Every
+// kernel launched through here calls pdl_wait() before it touches global memory.
+extern thread_local int g_pdl_depth;
+struct PdlScope {
+    PdlScope() { ++g_pdl_depth; }
+    ~PdlScope() { --g_pdl_depth; }
+};
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, int cluster,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (g_pdl_depth > 0) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 }  // namespace pb2

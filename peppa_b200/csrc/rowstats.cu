@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(256)
                       float* __restrict__ diag, __half* __restrict__ vh, __half* __restrict__ ah,
                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
                       int n_partials) {
+    pdl_launch_dependents();
+    pdl_wait();  // the workspace may still be read by the previous step's kernels
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -290,6 +292,8 @@ __global__ void __launch_bounds__(256)
                          const int32_t* __restrict__ col_cnt, const float* __restrict__ loss_partial, int n_partials,
                          float margin, float coef, float* __restrict__ loss_out, TOut* __restrict__ d_v,
                          TOut* __restrict__ d_a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -669,9 +673,11 @@ extern "C" int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, 
         return set_error(PB2_ERR_ARG, "hinge_prep: null");
     if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(vh, dim, 2) || !vec_ok(ah, dim, 2))
         return set_error(PB2_ERR_ARG, "hinge_prep: alignment");
-    hinge_prep_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
-        (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials);
+    int rc = check_cuda(launch_ex(hinge_prep_kernel, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream, 1,
+                                  (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag,
+                                  (__half*)vh, (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials),
+                        "hinge_prep");
+    if (rc) return rc;
     return check_launch("hinge_prep");
 }
 
@@ -688,15 +694,18 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
     if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
         !vec_ok(d_v, dim, ob) || !vec_ok(d_a, dim, ob))
         return set_error(PB2_ERR_ARG, "hinge_finish2: alignment");
-#define PB2_FIN2(T)                                                                                                \
-    hinge_finish2_kernel<T><<<grid_for_warps(2 * n), 256, 0, (cudaStream_t)stream>>>(                               \
-        p_v, p_a, (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, \
-        col_cnt, loss_partial, n_partials, margin, coef, loss_out, (T*)d_v, (T*)d_a)
+    cudaError_t e;
+#define PB2_FIN2(T)                                                                                                       \
+    e = launch_ex(hinge_finish2_kernel<T>, (unsigned)grid_for_warps(2 * n), 256u, (size_t)0, (cudaStream_t)stream, 1, p_v, p_a, \
+                  (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt,  \
+                  loss_partial, n_partials, margin, coef, loss_out, (T*)d_v, (T*)d_a)
     if (out_dtype == PB2_F32) PB2_FIN2(float);
     else if (out_dtype == PB2_BF16) PB2_FIN2(__nv_bfloat16);
     else if (out_dtype == PB2_F16) PB2_FIN2(__half);
     else return set_error(PB2_ERR_ARG, "hinge_finish2: unknown output dtype");
 #undef PB2_FIN2
+    int rc = check_cuda(e, "hinge_finish2");
+    if (rc) return rc;
     return check_launch("hinge_finish2");
 }
 

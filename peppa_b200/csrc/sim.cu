@@ -95,9 +95,10 @@ struct OutStage {
     const CUtensorMap* tmap;  // gradient matrix [rows, cols] fp16, box [32 x 64]
     uint32_t slab;            // running slab counter of this warp
     uint32_t mask;            // nbuf - 1 (1: double buffered, 0: one slab per tile and warp)
-    bool skip_store;          // measurement hook (pb2_debug_force_bn bit 16): stage but do not store
+    int skip;                 // measurement hooks (pb2_debug_force_bn bits 16..18): 1 no TMA store, 2 no STS, 4 no fence
     // 16 fp16 (two uint4) of this thread's row, chunk parity cp (0: columns 0-31, 1: columns 32-63)
     __device__ __forceinline__ void write(int lane, int cp, const uint32_t (&packed)[16]) {
+        if (skip & 2) return;
         uint8_t* row = buf + (slab & mask) * kOutSlabBytes + lane * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -122,10 +123,10 @@ struct OutStage {
         __syncwarp();
     }
     __device__ __forceinline__ void end_slab(int lane, int32_t col, int32_t row) {
-        fence_proxy_async_smem();
+        if (!(skip & 4)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            if (!skip_store) tma_store_2d(tmap, buf + (slab & mask) * kOutSlabBytes, col, row);
+            if (!(skip & 1)) tma_store_2d(tmap, buf + (slab & mask) * kOutSlabBytes, col, row);
             tma_store_commit();
         }
         ++slab;
@@ -718,10 +719,12 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         fence_mbar_init();
     }
     if (warp == kTmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == kTmaWarp) {
         // ===================================================================== TMA producer
@@ -845,7 +848,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         os.tmap = &tm_out;
         os.slab = 0;
         os.mask = L::kOutBufs - 1;
-        os.skip_store = c.diag_only < 0;
+        os.skip = c.diag_only < 0 ? -c.diag_only : 0;
         int64_t it = 0;
         for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
             const int as = (int)(it & 1);
@@ -955,7 +958,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.n_rb = (int)((rows + BM - 1) / BM);
     c.n_cb = (int)((cols + BN - 1) / BN);
     c.n_tiles = (int64_t)c.n_rb * c.n_cb;
-    c.diag_only = g_skip_store ? -1 : 0;
+    c.diag_only = -g_skip_store;
     if (std::is_same<Policy, DiagPolicy>::value) {  // paired rows: only the diagonal tiles
         c.diag_only = 1;
         c.n_cb = 0;
@@ -973,7 +976,8 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
         configured = true;
     }
     const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid());
-    kern<<<grid, sim_threads(G), smem, st>>>(tx, ty, to, c, pp);
+    rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, 1, tx, ty, to, c, pp), what);
+    if (rc) return rc;
     return check_launch(what);
 }
 
@@ -1011,7 +1015,7 @@ using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
 extern "C" int pb2_debug_force_bn(int bn) {
-    g_skip_store = (bn >> 16) & 1;
+    g_skip_store = (bn >> 16) & 7;
     bn &= 0xffff;
     g_force_bn = (bn == 64 || bn == 128 || bn == 192 || bn == 256) ? bn : 0;
     return PB2_OK;

@@ -1,6 +1,7 @@
 // pb2_hinge_step: the whole TripletLoss forward + gradients of one training step (pig/models.py:262 ->
-// pig/loss.py:33-48 + autograd) as ONE C call = five kernel launches on the caller's stream:
-//   hinge_prep -> sim_hinge (tcgen05, fused loss/counts/gradient matrix) -> grad_gemm x2 -> hinge_finish2.
+// pig/loss.py:33-48 + autograd) as ONE C call = four kernel launches on the caller's stream:
+//   hinge_prep -> sim_hinge (tcgen05, fused loss/counts/gradient matrix) -> grad_gemm_dual (both backward
+//   products in one grid) -> hinge_finish2, chained with programmatic dependent launch.
 // At batch ~1k the step is launch bound; one call keeps the host side to a single FFI crossing and the
 // scratch in one caller-provided workspace.
 #include <cuda_fp16.h>
@@ -66,14 +67,16 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, 
     void* g = w + L.g;
     float* pv = reinterpret_cast<float*>(w + L.pv);
     float* pa = reinterpret_cast<float*>(w + L.pa);
+    // programmatic dependent launch between the four kernels: each one's prologue (barrier init, TMEM
+    // allocation, descriptor prefetch) overlaps its predecessor's tail
+    pb2::PdlScope pdl;
     int rc = pb2_hinge_prep(v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part, stream);
     if (rc) return rc;
     rc = pb2_sim_hinge(v, a, rinv_v, rinv_a, diag, diag, n, n, 0, 0, dim, ldv, lda, margin, part, -L.n_part, row_cnt,
                        col_cnt, g, L.ld_g, nullptr, nullptr, stream);
     if (rc) return rc;
-    rc = pb2_grad_gemm(g, PB2_F16, n, n, L.ld_g, 0, ah, PB2_F16, dim, dim, 1.0f, 0, pv, dim, stream);
-    if (rc) return rc;
-    rc = pb2_grad_gemm(g, PB2_F16, n, n, L.ld_g, 1, vh, PB2_F16, dim, dim, 1.0f, 0, pa, dim, stream);
+    // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
+    rc = pb2_grad_gemm_dual(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, pv, pa, dim, dim, stream);
     if (rc) return rc;
     return pb2_hinge_finish2(pv, pa, v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, part, L.n_part, margin,
                              1.0f / ((float)n * (float)n), loss_out, d_v, d_a, out_dtype, stream);

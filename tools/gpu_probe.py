@@ -266,9 +266,11 @@ def step_hinge_perf():
             print(f"sim_hinge bn={bn} rank={with_rank}: {ms:.3f} ms  {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
         ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, None, 0), iters=10)
         print(f"sim_hinge bn={bn} no-G fwd only: {ms:.3f} ms  {2 * n * n * 512 / ms / 1e9:.1f} TFLOP/s", flush=True)
-    lib.pb2_debug_force_bn(256 | 0x10000)   # stage the gradient-matrix tiles but skip the TMA stores
-    ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=10)
-    print(f"sim_hinge bn=256 rank=True, G staged but not stored: {ms:.3f} ms", flush=True)
+    for bits, what in ((0, "baseline"), (1, "no TMA store"), (3, "no TMA store, no STS"), (7, "no TMA store, no STS, no fence"),
+                       (4, "no proxy fence (stores race: timing only)"), (0, "baseline again")):
+        lib.pb2_debug_force_bn(256 | (bits << 16))
+        ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=200, warm=20)
+        print(f"sim_hinge bn=256 rank=True [{what}]: {ms:.3f} ms (200 back to back)", flush=True)
     lib.pb2_debug_force_bn(0)
 
 

@@ -61,20 +61,25 @@ def peaks():
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum (GB) of one launch, from the committed ncu --set full
-    captures (profiles/r1_ncu_summary.json: 32768 x 32768 blocks / 2^20 triplets); None if unknown."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_summary.json")
-    key = {"sim_hinge+rank": "r1_sim_hinge", "grad_gemm": "r1_grad_gemm", "triplet_score": "r1_triplet"}.get(kernel)
-    if not key or not os.path.exists(p):
-        return None
-    with open(p) as f:
-        d = json.load(f).get(key, {})
-
+    captures (profiles/r1b_ncu_summary.json: the kernels of a 32768 x 32768 gallery block;
+    profiles/r1_ncu_summary.json: 2^20 triplets); None if unknown."""
     def gb(s):
         v, u = s.split()[:2]
         return float(v) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
+
     try:
+        if kernel in ("sim_hinge+rank", "grad_gemm"):
+            with open(os.path.join(ROOT, "profiles", "r1b_ncu_summary.json")) as f:
+                ks = json.load(f)["r1b_gallery_kernels.ncu-rep"]
+            want = "HingePolicyT" if kernel == "sim_hinge+rank" else "grad_gemm_kernel<0, 512, 2>"
+            d = next(k for k in ks if want in k["kernel"])
+        elif kernel == "triplet_score":
+            with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+                d = json.load(f)["r1_triplet"]
+        else:
+            return None
         return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
-    except (KeyError, ValueError):
+    except (OSError, KeyError, ValueError, StopIteration):
         return None
 
 
@@ -193,7 +198,7 @@ def roofline_of(kern, bound):
     else:
         achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s", pk["source"] + " (sustained)"
     roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": ncu_traffic(name), "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1_ncu_summary.json)",
+            "traffic": ncu_traffic(name), "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1b_ncu_summary.json / r1_ncu_summary.json)",
             "peak_source": src, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"]}
     table = {n: {"launches": v["launches"], "ms_total": v["ms"],
                  ("gbs" if bound == "hbm" else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)) if v["ms"] else None}

@@ -658,9 +658,9 @@ struct LseGradPolicy {
 };
 
 // ---------------------------------------------------------------------------------- kernel
-template <int BN, int G, bool kOut>
+template <int BN, int G, bool kOut, int kCtas>
 struct SimSmem {
-    static constexpr int kStageBytes = (BM + BN) * BK * 2;
+    static constexpr int kStageBytes = (BM + BN / kCtas) * BK * 2;  // a CTA of a pair stages half of Y's rows
     // shared memory not spent on staging goes to the TMA pipeline: bytes in flight bound the MMA rate
     static constexpr int kOutBufs = G >= 3 ? 1 : 2;  // G >= 3: one 64-column slab per warp and tile
     static constexpr int kOutBytes = kOut ? 4 * G * kOutBufs * kOutSlabBytes : 0;
@@ -673,11 +673,15 @@ struct SimSmem {
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
 
-template <class Policy, int BN, int G>
+// kCtas == 2: CTA pairs (cluster of 2, tcgen05 cta_group::2).  One MMA of M = 256 covers the 128 rows of
+// each CTA; each CTA stages its own X rows and HALF of the tile's Y rows, accumulates S[its 128 rows, BN]
+// in its own TMEM and runs its own loader and epilogue.  A third less operand traffic (L2 -> smem and
+// smem -> tensor core) per SM than two independent 128 x BN tiles; see common.cuh for the protocol.
+template <class Policy, int BN, int G, int kCtas>
 __global__ void __launch_bounds__(sim_threads(G), 1)
     sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                const __grid_constant__ CUtensorMap tm_out, const SimCommon c, const typename Policy::Params p) {
-    using L = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32>;
+    using L = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32, kCtas>;
     constexpr int kEpiWarps = 4 * G;
     constexpr int kEpiThreads = kEpiWarps * 32;
     constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
@@ -693,13 +697,16 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     uint64_t* acc_full = bars + 2 * L::kStages;  // [2]
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint64_t* vec_full = acc_empty + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vec_full + 2);
+    uint64_t* vec_empty = vec_full + 2;          // [2] the epilogue is done with a vector buffer (CTA-local)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vec_empty + 2);
     float* rowvec = colvec + 2 * kMaxColVecs * kColVecStride;  // [acc stage][vec][128]
     float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [kMaxEpiWarps]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr int kLoaderWarp = 4 * G, kMmaWarp = 4 * G + 1, kTmaWarp = 4 * G + 2;
+    const uint32_t crank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+    const int64_t unit0 = blockIdx.x / kCtas, n_units = gridDim.x / kCtas;  // tiles are dealt to CTAs / CTA pairs
 
     if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -713,15 +720,20 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full + a, 1);
-            mbar_init(acc_empty + a, kEpiWarps);
+            mbar_init(acc_empty + a, kEpiWarps * kCtas);  // the leader's collects both CTAs' epilogues
             mbar_init(vec_full + a, 1);
+            mbar_init(vec_empty + a, kEpiWarps);
         }
         fence_mbar_init();
     }
-    if (warp == kTmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kTmaWarp) {
+        if (kCtas == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
+    }
     pdl_launch_dependents();
     tc_fence_before();
-    __syncthreads();
+    if (kCtas == 2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
@@ -731,16 +743,24 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            for (int64_t t = unit0; t < c.n_tiles; t += n_units) {
                 int rb, cb;
                 tile_coords(t, c.n_rb, c.n_cb, rb, cb);
+                const int xrow = (rb * kCtas + (int)crank) * BM, yrow = cb * BN + (int)crank * (BN / kCtas);
                 for (int kb = 0; kb < c.kblocks; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sx = smem + stage * L::kStageBytes;
                     uint8_t* sy = sx + BM * BK * 2;
-                    mbar_arrive_expect_tx(full + stage, L::kStageBytes);
-                    tma_load_2d(sx, &tm_x, full + stage, kb * BK, rb * BM, kEvictNormal);
-                    tma_load_2d(sy, &tm_y, full + stage, kb * BK, cb * BN, kEvictNormal);
+                    if (kCtas == 1) {
+                        mbar_arrive_expect_tx(full + stage, L::kStageBytes);
+                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, kEvictNormal);
+                        tma_load_2d(sy, &tm_y, full + stage, kb * BK, yrow, kEvictNormal);
+                    } else {  // both CTAs' bytes are counted on the leader's barrier
+                        if (crank == 0) mbar_arrive_expect_tx(full + stage, L::kStageBytes * kCtas);
+                        const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+                        tma_load_2d_pair(sx, &tm_x, lbar, kb * BK, xrow, kEvictNormal);
+                        tma_load_2d_pair(sy, &tm_y, lbar, kb * BK, yrow, kEvictNormal);
+                    }
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -750,8 +770,8 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         }
     } else if (warp == kMmaWarp) {
         // ====================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = make_idesc(BM * kCtas, BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
             // K-major 128B-swizzled operands: descriptor = {start >> 4 | LBO 16 B, SBO 1024 B | version | swizzle}.
             // Only the start address changes, linearly: one running low word, adds instead of rebuilds.
             const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
@@ -760,7 +780,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             int stage = 0;
             uint32_t phase = 0, lo = lo0;
             int64_t it = 0;
-            for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
+            for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
                 const int as = (int)(it & 1);
                 mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -769,9 +789,14 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k)
-                        umma_f16_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(empty + stage);  // stage reusable once these MMAs have read it
+                    for (int k = 0; k < BK / UK; ++k) {
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        if (kCtas == 2) umma_f16_pair_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, desc_hi, idesc, acc);
+                        else umma_f16_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, idesc, acc);
+                    }
+                    // stage reusable (in both CTAs of a pair) once these MMAs have read it
+                    if (kCtas == 2) umma_commit_pair(empty + stage);
+                    else umma_commit(empty + stage);
                     lo += kStageLo;
                     if (++stage == L::kStages) {
                         stage = 0;
@@ -779,18 +804,19 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                         lo = lo0;
                     }
                 }
-                umma_commit(acc_full + as);  // accumulator complete -> epilogue
+                if (kCtas == 2) umma_commit_pair(acc_full + as);  // accumulator complete -> both epilogues
+                else umma_commit(acc_full + as);
             }
         }
     } else if (warp == kLoaderWarp) {
         // ============================ vector loader: per-column and per-row epilogue operands -> smem
         int64_t it = 0;
-        for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
+        for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
             const int as = (int)(it & 1);
             int rb, cb;
             tile_coords(t, c.n_rb, c.n_cb, rb, cb);
-            const int64_t row0 = (int64_t)rb * BM, col0 = (int64_t)cb * BN;
-            mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);  // the epilogue is done with this buffer
+            const int64_t row0 = ((int64_t)rb * kCtas + crank) * BM, col0 = (int64_t)cb * BN;
+            mbar_wait(vec_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);  // the epilogue is done with this buffer
             float* cv = colvec + as * (kMaxColVecs * kColVecStride);
             float* rv = rowvec + as * (kMaxRowVecs * BM);
             // phase 1: every global load of the tile (fetch_* = loads only), phase 2: arithmetic + smem stores
@@ -850,12 +876,12 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         os.mask = L::kOutBufs - 1;
         os.skip = c.diag_only < 0 ? -c.diag_only : 0;
         int64_t it = 0;
-        for (int64_t t = blockIdx.x; t < c.n_tiles; t += gridDim.x, ++it) {
+        for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
             const int as = (int)(it & 1);
             int rb, cb;
             tile_coords(t, c.n_rb, c.n_cb, rb, cb);
             TileCtx ctx;
-            ctx.row0 = (int64_t)rb * BM;
+            ctx.row0 = ((int64_t)rb * kCtas + crank) * BM;
             ctx.col0 = (int64_t)cb * BN;
             ctx.row = ctx.row0 + quad * 32 + lane;
             ctx.row_valid = ctx.row < c.rows;
@@ -898,17 +924,23 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + as);
+            if (lane == 0) {
+                mbar_arrive(vec_empty + as);  // the loader may restage this buffer
+                if (kCtas == 2) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + as), 0));  // the leader's MMA warp
+                else mbar_arrive(acc_empty + as);
+            }
             pol.tile_end(p, c, ctx);
         }
         if (Policy::kStoresG || Policy::kStoresF32) os.finish(lane);
         pol.kernel_end(p, red, kEpiWarps);
     }
     tc_fence_before();
-    __syncthreads();
+    if (kCtas == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
+    else __syncthreads();
     if (warp == kTmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (kCtas == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -933,14 +965,14 @@ struct OutMatrix {  // optional fp16 gradient matrix drained by TMA stores
     int64_t ld = 0;
 };
 
-template <class Policy, int BN, int G>
+template <class Policy, int BN, int G, int kCtas>
 static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                       const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
                       const OutMatrix& om, cudaStream_t st, const char* what) {
     CUtensorMap tx, ty, to;
     int rc = make_tmap_2d(&tx, x, 2, (uint64_t)rows, (uint64_t)dim, (uint64_t)ldx * 2, BM, BK);
     if (rc) return rc;
-    rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN, BK);
+    rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN / kCtas, BK);
     if (rc) return rc;
     if (Policy::kStoresG && om.ptr) {
         rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
@@ -955,7 +987,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rows = rows;
     c.cols = cols;
     c.kblocks = dim / BK;
-    c.n_rb = (int)((rows + BM - 1) / BM);
+    c.n_rb = (int)((rows + BM * kCtas - 1) / (BM * kCtas));  // row blocks of a CTA (pair) tile
     c.n_cb = (int)((cols + BN - 1) / BN);
     c.n_tiles = (int64_t)c.n_rb * c.n_cb;
     c.diag_only = -g_skip_store;
@@ -967,21 +999,27 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_x = rinv_x;
     c.rinv_y = rinv_y;
     c.scale = scale;
-    auto kern = sim_kernel<Policy, BN, G>;
-    constexpr int smem = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32>::kTotal;
+    auto kern = sim_kernel<Policy, BN, G, kCtas>;
+    constexpr int smem = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32, kCtas>::kTotal;
     static bool configured = false;  // per instantiation
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
         if (rc) return rc;
         configured = true;
     }
-    const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid());
-    rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, 1, tx, ty, to, c, pp), what);
+    const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid() / kCtas) * kCtas;
+    rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, kCtas, tx, ty, to, c, pp), what);
     if (rc) return rc;
     return check_launch(what);
 }
 
 static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
+// pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, anything else = independent CTAs.  Pairs are
+// correct (tools/gpu_probe.py simpair: identical counts / ranks) but measured SLOWER here -- hinge pass 1.34 vs
+// 1.23 ms, rank pass 0.843 vs 0.827 ms per 32768^2 block, sustained: a pair's MMA for tile t+2 waits for BOTH
+// CTAs' epilogues of tile t, and these kernels are bound by their epilogues, not by operand traffic (unlike the
+// gradient GEMM, whose gain came from the 512-wide pair tile reading G once).  Kept as a measured option.
+static int g_sim_pair = 0;
 
 template <class Policy>
 static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
@@ -995,16 +1033,21 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
     int bn = force_bn ? force_bn : pick_bn(rows, cols, Policy::kStoresG);
     if (Policy::kStoresG && bn == 64) bn = 128;
     if (!Policy::kStoresG && bn == 192) bn = 256;
-#define PB2_SIM(B, GG) \
-    launch_sim<Policy, B, GG>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
-    if constexpr (Policy::kStoresG) {
-        if (bn == 192) return PB2_SIM(192, 3);
-        if (bn == 256) return PB2_SIM(256, 2);
-        return PB2_SIM(128, 2);
+#define PB2_SIM(B, GG, CC) \
+    launch_sim<Policy, B, GG, CC>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
+    const bool pair = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 1;
+    if constexpr (std::is_same<Policy, DiagPolicy>::value) {
+        return PB2_SIM(128, 2, 1);
+    } else if constexpr (Policy::kStoresG) {
+        if (bn == 192) return PB2_SIM(192, 3, 1);
+        if (pair) return PB2_SIM(256, 2, 2);
+        if (bn == 256) return PB2_SIM(256, 2, 1);
+        return PB2_SIM(128, 2, 1);
     } else {
-        if (bn == 256) return PB2_SIM(256, 2);
-        if (bn == 128) return PB2_SIM(128, 2);
-        return PB2_SIM(64, 2);
+        if (pair) return PB2_SIM(256, 2, 2);
+        if (bn == 256) return PB2_SIM(256, 2, 1);
+        if (bn == 128) return PB2_SIM(128, 2, 1);
+        return PB2_SIM(64, 2, 1);
     }
 #undef PB2_SIM
 }
@@ -1014,6 +1057,10 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
 using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
+extern "C" int pb2_debug_sim_pair(int mode) {
+    g_sim_pair = mode;
+    return PB2_OK;
+}
 extern "C" int pb2_debug_force_bn(int bn) {
     g_skip_store = (bn >> 16) & 7;
     bn &= 0xffff;

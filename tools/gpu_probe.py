@@ -302,6 +302,39 @@ def step_hinge_dim():
     lib.pb2_debug_force_bn(0)
 
 
+def step_simpair():
+    """Similarity kernels on CTA pairs (cta_group::2) vs independent 128 x 256 tiles: same results, sustained time."""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = 32768
+    V, A = emb(n)
+    rv, _ = ops.row_norms(V)
+    ra, _ = ops.row_norms(A)
+    diag, thr = ops.sim_diag(A, V, ra, rv)
+    g, ld = ops.gmat_alloc(n, n, "cuda")
+    idx = torch.arange(n, device="cuda")
+    res = {}
+    for pair in (0, 1):
+        lib.pb2_debug_sim_pair(pair)
+        rc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        cc = torch.zeros(n, dtype=torch.int32, device="cuda")
+        rk = torch.zeros(n, dtype=torch.int32, device="cuda")
+        part = ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk)
+        rk2 = ops.sim_rank(A, V, ra, rv, thr, idx)
+        torch.cuda.synchronize()
+        res[pair] = (rc.clone(), cc.clone(), rk.clone(), rk2.clone(), part.double().sum().item(), g[:, :n].float().sum().item())
+        ms_h = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk), iters=200, warm=20)
+        ms_r = _t(lambda: ops.sim_rank(A, V, ra, rv, thr, idx, rank=rk2), iters=200, warm=20)
+        print(f"pair={pair}: hinge+rank+G {ms_h:.3f} ms ({2 * n * n * 512 / ms_h / 1e9:.0f} TF/s)   rank only {ms_r:.3f} ms "
+              f"({2 * n * n * 512 / ms_r / 1e9:.0f} TF/s)   (200 back to back)", flush=True)
+    a, b = res[0], res[1]
+    print("row counts equal", torch.equal(a[0], b[0]), "col counts equal", torch.equal(a[1], b[1]), "hinge ranks equal",
+          torch.equal(a[2], b[2]), "rank-kernel ranks equal", torch.equal(a[3], b[3]), "loss partial sums", a[4], b[4],
+          "G sums", a[5], b[5], flush=True)
+    lib.pb2_debug_sim_pair(0)
+
+
 def step_streamk():
     """grad_gemm: CTA pairs (cta_group::2) on/off x stream-K on/off: agreement with fp64, determinism, sustained time."""
     import torch

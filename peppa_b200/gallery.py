@@ -8,8 +8,11 @@ columns are ALL video clips:
   1. all-gather the video block (bf16), its row norms and the diagonal scores  (NCCL over NVLink)
   2. fused tcgen05 pass over the [N/P x N] strip: hinge loss partials, indicator counts, rank
      counts of the diagonal, and the fp16 gradient-matrix block           (pb2_sim_hinge + rank)
-  3. gradient GEMMs: dA rows are complete locally; dV partials are [N, D] per rank
-  4. all-reduce the column counts (int32) and the scalar loss; reduce-scatter the dV partials
+  3. gradient GEMMs: dA rows are complete locally; dV partials are [N, D] per rank.  The strip is walked
+     column block by column block, and as soon as a column block's dV partial is complete it is reduced
+     to the rank that owns those video rows (asynchronously, on NCCL's stream, while the next column
+     block computes): the 2 GiB reduce-scatter of a 2^20 gallery hides behind the tensor work
+  4. all-reduce the column counts (int32) and the scalar loss
   5. normalisation Jacobian (pb2_hinge_finish) on the local rows
 
 The loss is symmetric in (V, A) (pig/loss.py:41-48 adds the row and the column hinge), so
@@ -83,6 +86,19 @@ class GalleryStep:
         else:
             dist.reduce_scatter_tensor(out, full, group=self.group)
 
+    def _reduce_to_owners(self, full, c0, c1):
+        """Start the reduction of rows [c0, c1) of a [N, D] partial to the rank(s) owning them; the owner's
+        rows are summed in place.  Returns the pending work handles."""
+        import torch.distributed as dist
+        works, a = [], c0
+        while a < c1:
+            owner = a // self.n_local
+            b = min(c1, (owner + 1) * self.n_local)
+            dst = dist.get_global_rank(self.group, owner) if self.group is not None else owner
+            works.append(dist.reduce(full[a:b], dst=dst, group=self.group, async_op=True))
+            a = b
+        return works
+
     def run(self, a_loc: torch.Tensor, v_loc: torch.Tensor):
         """a_loc, v_loc: [n_local, dim] bf16 on this rank's GPU.  Returns a dict with the global loss
         (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
@@ -116,8 +132,9 @@ class GalleryStep:
                 self.p_a.zero_()
             if acc_v:
                 self.p_v.zero_()
-        for (r0, r1) in rblocks:
-            for (c0, c1) in cblocks:
+        pending = []
+        for (c0, c1) in cblocks:            # column blocks outermost: a block's dV partial completes early
+            for (r0, r1) in rblocks:
                 part = ops.sim_hinge(a_loc[r0:r1], v_full[c0:c1], ra[r0:r1], rv_full[c0:c1], diag[r0:r1],
                                      diag_full[c0:c1], self.margin, self.row_cnt[r0:r1], self.col_cnt[c0:c1],
                                      self.gmat if self.with_grad else None, self.ld_g if self.with_grad else 0,
@@ -129,6 +146,8 @@ class GalleryStep:
                                   out=self.p_a[r0:r1], accumulate=acc_a)
                     ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True,
                                   out=self.p_v[c0:c1], accumulate=acc_v)
+            if self.with_grad and self.world > 1:
+                pending += self._reduce_to_owners(self.p_v, c0, c1)
         ops.hinge_loss_terms(loss, diag=diag, cnt=self.row_cnt, margin=self.margin)      # local rows' term
         hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
         hits = hits.sum(dim=1).to(torch.float32)
@@ -136,15 +155,15 @@ class GalleryStep:
             dist.all_reduce(self.col_cnt, group=self.group)
             dist.all_reduce(loss, group=self.group)
             dist.all_reduce(hits, group=self.group)
-            if self.with_grad:
-                self._reduce_scatter(self.p_v_loc, self.p_v)
+            for w in pending:
+                w.wait()
         # column term from the merged counts (identical on every rank, added once after the all-reduce)
         ops.hinge_loss_terms(loss, diag=diag_full, cnt=self.col_cnt, margin=self.margin)
         inv_n2 = 1.0 / float(n) ** 2
         out = {"loss": loss * inv_n2, "recall": hits / float(n), "ranks": self.ranks, "dA": None, "dV": None}
         if self.with_grad:
             cc = self.col_cnt[r0g:r0g + nl]
-            p_v_loc = self.p_v_loc if self.world > 1 else self.p_v
+            p_v_loc = self.p_v[r0g:r0g + nl]      # this rank's rows: complete locally (world 1) or reduced in place
             out["dA"] = ops.hinge_finish(self.p_a, a_loc, v_loc, ra, rv, self.row_cnt, cc, inv_n2)
             out["dV"] = ops.hinge_finish(p_v_loc, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
         return out

@@ -9,10 +9,12 @@
 //   rinv = 1 / ||out||       norm = ||y||  (the backward's normalisation Jacobian needs it)
 //
 // One CTA owns 128 rows and ALL n_out <= 512 output features: the 128 x 512 fp32 accumulator is the whole
-// of TMEM, so the row norm is complete inside the CTA and y never exists in HBM.  x tiles [128 x 64] and
-// W tiles [n_out x 64] stream through a two-stage TMA ring; one thread issues the MMAs (two of N <= 256
-// per k-step); four epilogue warps (thread == row) read the accumulator twice -- sum of squares, then
-// scale / round / stage -- and the bf16 tile leaves through swizzled slabs and TMA stores.
+// of TMEM, so the row norm is complete inside the CTA and y never exists in HBM.  CTAs work in pairs
+// (tcgen05 cta_group::2): x tiles [128 x 64] per CTA and W tiles [n_out x 64] split between the two CTAs
+// stream through a three-stage TMA ring; the leader's thread issues the MMAs (two of M = 256, N <= 256
+// per k-step); eight epilogue warps (thread == row, two column halves per TMEM lane quadrant) read the
+// accumulator twice -- sum of squares, then scale / round / stage -- with packed fp32 math, and the bf16
+// tile leaves through swizzled slabs and TMA stores.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
@@ -21,17 +23,23 @@ namespace pb2 {
 namespace proj {
 
 constexpr int BM = 128, BK = 64, UK = 16;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kTmaWarp = 5;
-constexpr int kThreads = 6 * 32;
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kTmaWarp = 9;  // two epilogue warps per TMEM lane quadrant (column halves)
+constexpr int kThreads = 10 * 32;
 constexpr int kMaxOut = 512;
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 spans the 128 rows of both CTAs; each CTA
+// stages its own x rows and HALF of W's rows for each of the two MMAs of a k-step, so a stage is 48 KiB instead
+// of 80 and W crosses L2 -> SM once per pair (the kernel was bound by that traffic, not by the tensor pipe).
 constexpr int kXBytes = BM * BK * 2;           // 16 KiB
-constexpr int kWBytes = kMaxOut * BK * 2;      // 64 KiB (rows beyond n_out are zero-filled by TMA)
+constexpr int kWHalf = 128 * BK * 2;           // 16 KiB: this CTA's rows of one MMA's W tile (N <= 256 per MMA)
+constexpr int kWBytes = 2 * kWHalf;
 constexpr int kStageBytes = kXBytes + kWBytes;
-constexpr int kStages = 2;
+constexpr int kStages = 3;
+constexpr int kWBox = 32;                      // W rows per TMA box
 constexpr int kSlabBytes = 32 * 64 * 2;        // one warp's [32 rows x 64 bf16] staging slab
 constexpr int kOutBytes = kEpiWarps * 2 * kSlabBytes;
-constexpr int kBiasBytes = kMaxOut * 4;
-constexpr int kSmem = kStages * kStageBytes + kOutBytes + kBiasBytes + 256;
+constexpr int kBiasBytes = 0;                   // the bias is read through L1 (broadcast loads): shared memory is full
+constexpr int kRedBytes = 2 * 2 * BM * 4;      // per-row partial sums of the two column halves: [ss | q][half][row]
+constexpr int kSmem = kStages * kStageBytes + kOutBytes + kBiasBytes + kRedBytes + 256;
 
 struct Args {
     int64_t rows;
@@ -55,7 +63,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* out_stage = smem + kStages * kStageBytes;
     float* bias_s = reinterpret_cast<float*>(out_stage + kOutBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
+    float* red_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_s) + kRedBytes);
     uint64_t* full = bars;                // [kStages]
     uint64_t* empty = bars + kStages;     // [kStages]
     uint64_t* acc_full = empty + kStages;
@@ -63,7 +72,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_tiles = (a.rows + BM - 1) / BM;
+    const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+    const int64_t n_tiles = (a.rows + 2 * BM - 1) / (2 * BM);  // pair tiles of 256 rows
+    const int64_t unit0 = blockIdx.x / 2, n_units = gridDim.x / 2;
     if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_w);
@@ -75,13 +86,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_init(empty + s, 1);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, kEpiWarps);
+        mbar_init(acc_empty, 2 * kEpiWarps);  // the leader's collects both CTAs' epilogues
         fence_mbar_init();
     }
-    if (warp == kTmaWarp) tmem_alloc(tmem_slot, 512);
-    for (int i = threadIdx.x; i < kMaxOut; i += kThreads) bias_s[i] = (a.bias && i < a.n_out) ? a.bias[i] : 0.f;
+    if (warp == kTmaWarp) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n1 = a.n_out > 256 ? 256 : a.n_out, n2 = a.n_out - n1;  // N of the two MMAs of a k-step
@@ -90,15 +100,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int h1 = n1 / 2, h2 = n2 / 2;  // this CTA's W rows per MMA
+            for (int64_t t = unit0; t < n_tiles; t += n_units) {
+                const int32_t xrow = (int32_t)((t * 2 + crank) * BM);
                 for (int kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sx = smem + stage * kStageBytes;
                     uint8_t* sw = sx + kXBytes;
-                    mbar_arrive_expect_tx(full + stage, a.tx_bytes);
-                    tma_load_2d(sx, &tm_x, full + stage, kb * BK, (int32_t)(t * BM), kEvictFirst);
-                    tma_load_2d(sw, &tm_w, full + stage, kb * BK, 0, kEvictLast);
-                    if (n2 > 0) tma_load_2d(sw + kWBytes / 2, &tm_w, full + stage, kb * BK, 256, kEvictLast);
+                    if (crank == 0) mbar_arrive_expect_tx(full + stage, a.tx_bytes);  // both CTAs' bytes
+                    const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+                    tma_load_2d_pair(sx, &tm_x, lbar, kb * BK, xrow, kEvictFirst);
+                    for (int r0 = 0; r0 < h1; r0 += kWBox)
+                        tma_load_2d_pair(sw + r0 * (BK * 2), &tm_w, lbar, kb * BK, (int32_t)crank * h1 + r0, kEvictLast);
+                    for (int r0 = 0; r0 < h2; r0 += kWBox)
+                        tma_load_2d_pair(sw + kWHalf + r0 * (BK * 2), &tm_w, lbar, kb * BK, 256 + (int32_t)crank * h2 + r0, kEvictLast);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -107,17 +122,17 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            const uint32_t idesc1 = make_idesc(BM, (uint32_t)n1, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
-            const uint32_t idesc2 = n2 > 0 ? make_idesc(BM, (uint32_t)n2, kFmtBF16, kFmtBF16, kMajorK, kMajorK) : 0u;
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc1 = make_idesc(2 * BM, (uint32_t)n1, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+            const uint32_t idesc2 = n2 > 0 ? make_idesc(2 * BM, (uint32_t)n2, kFmtBF16, kFmtBF16, kMajorK, kMajorK) : 0u;
             const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
             const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
-            constexpr uint32_t kStageLo = kStageBytes >> 4, kWLo = kXBytes >> 4, kW2Lo = (kXBytes + kWBytes / 2) >> 4,
+            constexpr uint32_t kStageLo = kStageBytes >> 4, kWLo = kXBytes >> 4, kW2Lo = (kXBytes + kWHalf) >> 4,
                                kKLo = (UK * 2) >> 4;
             int stage = 0;
             uint32_t phase = 0, lo = lo0;
             int64_t it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
                 mbar_wait(acc_empty, (uint32_t)(it & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < a.kblocks; ++kb) {
@@ -126,10 +141,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        umma_f16_lohi(tmem_base, lo + k * kKLo, lo + kWLo + k * kKLo, desc_hi, idesc1, acc);
-                        if (n2 > 0) umma_f16_lohi(tmem_base + 256, lo + k * kKLo, lo + kW2Lo + k * kKLo, desc_hi, idesc2, acc);
+                        umma_f16_pair_lohi(tmem_base, lo + k * kKLo, lo + kWLo + k * kKLo, desc_hi, desc_hi, idesc1, acc);
+                        if (n2 > 0)
+                            umma_f16_pair_lohi(tmem_base + 256, lo + k * kKLo, lo + kW2Lo + k * kKLo, desc_hi, desc_hi, idesc2, acc);
                     }
-                    umma_commit(empty + stage);
+                    umma_commit_pair(empty + stage);
                     lo += kStageLo;
                     if (++stage == kStages) {
                         stage = 0;
@@ -137,72 +153,85 @@ __global__ void __launch_bounds__(kThreads, 1)
                         lo = lo0;
                     }
                 }
-                umma_commit(acc_full);
+                umma_commit_pair(acc_full);
             }
         }
     } else {
-        // ===== epilogue: thread == row, two passes over the 128 x n_out accumulator
-        const int quad = warp & 3;
+        // ===== epilogue: thread == row; warps 0-3 take the first half of the 32-column chunks, warps 4-7 the
+        // second; two passes over the accumulator (sum of squares, then scale / round / stage), the halves'
+        // per-row partial sums meet in shared memory in a fixed order (deterministic)
+        const int quad = warp & 3, half = warp >> 2;
         uint8_t* slab = out_stage + warp * 2 * kSlabBytes;
         uint32_t n_slab = 0;
         const int n_chunks = a.n_out / 32;
+        const int ch0 = half == 0 ? 0 : (n_chunks + 1) / 2 / 2 * 2;           // even split point (slabs are 2 chunks)
+        const int ch1 = half == 0 ? (n_chunks + 1) / 2 / 2 * 2 : n_chunks;
+        const int r = quad * 32 + lane;
+        const bool has_bias = a.bias != nullptr;
         int64_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-            const int64_t row = t * BM + quad * 32 + lane;
+        for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+            const int64_t row0 = (t * 2 + crank) * BM, row = row0 + r;
             mbar_wait(acc_full, (uint32_t)(it & 1));
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-            float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            float2 ssa = make_float2(0.f, 0.f), ssb = make_float2(0.f, 0.f);
+            for (int ch = ch0; ch < ch1; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(t_lane + ch * 32, v);
                 tmem_ld_wait();
-                const float* b = bias_s + ch * 32;
+                const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float y0 = __uint_as_float(v[j]) + b[j], y1 = __uint_as_float(v[j + 1]) + b[j + 1];
-                    const float y2 = __uint_as_float(v[j + 2]) + b[j + 2], y3 = __uint_as_float(v[j + 3]) + b[j + 3];
-                    ss0 = fmaf(y0, y0, ss0);
-                    ss1 = fmaf(y1, y1, ss1);
-                    ss2 = fmaf(y2, y2, ss2);
-                    ss3 = fmaf(y3, y3, ss3);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float2 y01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+                    const float2 y23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
+                    ssa = __ffma2_rn(y01, y01, ssa);
+                    ssb = __ffma2_rn(y23, y23, ssb);
                 }
             }
-            const float nrm = sqrtf((ss0 + ss1) + (ss2 + ss3));
+            red_s[half * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+            named_bar_sync(1, kEpiWarps * 32);
+            const float nrm = sqrtf(red_s[r] + red_s[BM + r]);
             const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
-            float q0 = 0.f, q1 = 0.f;
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            const float2 sc2 = make_float2(scale, scale);
+            float2 qa = make_float2(0.f, 0.f);
+            for (int ch = ch0; ch < ch1; ++ch) {
                 uint32_t v[32];
                 tmem_ld32(t_lane + ch * 32, v);
                 tmem_ld_wait();
-                const float* b = bias_s + ch * 32;
+                const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
                 uint32_t packed[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float e0 = (__uint_as_float(v[j]) + b[j]) * scale, e1 = (__uint_as_float(v[j + 1]) + b[j + 1]) * scale;
-                    const uint32_t pk = pack_bf16(e0, e1);
-                    packed[j >> 1] = pk;
-                    const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
-                    q0 = fmaf(r0, r0, q0);
-                    q1 = fmaf(r1, r1, q1);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float2 e01 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y)), sc2);
+                    const float2 e23 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w)), sc2);
+                    const uint32_t p0 = pack_bf16(e01.x, e01.y), p1 = pack_bf16(e23.x, e23.y);
+                    packed[2 * j] = p0;
+                    packed[2 * j + 1] = p1;
+                    const float2 r01 = make_float2(__uint_as_float(p0 << 16), __uint_as_float(p0 & 0xffff0000u));
+                    const float2 r23 = make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+                    qa = __ffma2_rn(r01, r01, qa);
+                    qa = __ffma2_rn(r23, r23, qa);
                 }
+                const int cp = (ch - ch0) & 1;
                 uint8_t* sl = slab + (n_slab & 1) * kSlabBytes;
-                if ((ch & 1) == 0) {  // the slab about to be rewritten must have been read by its TMA store
+                if (cp == 0) {  // the slab about to be rewritten must have been read by its TMA store
                     if (lane == 0) tma_store_wait_read<1>();
                     __syncwarp();
                 }
                 uint8_t* srow = sl + lane * 128;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int c16 = ((ch & 1) * 4 + k) ^ (lane & 7);  // 128-byte swizzle
+                    const int c16 = (cp * 4 + k) ^ (lane & 7);  // 128-byte swizzle
                     *reinterpret_cast<uint4*>(srow + c16 * 16) =
                         make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
                 }
-                if (ch & 1) {
+                if (cp) {
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tm_out, sl, (ch - 1) * 32, (int32_t)(t * BM + quad * 32));
+                        tma_store_2d(&tm_out, sl, (ch - 1) * 32, (int32_t)(row0 + quad * 32));
                         tma_store_commit();
                     }
                     ++n_slab;
@@ -210,9 +239,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-            if (row < a.rows) {
-                if (a.rinv) a.rinv[row] = 1.0f / sqrtf(q0 + q1);  // no epsilon: the scoring kernels' convention
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty), 0));  // the leader's MMA warp
+            red_s[2 * BM + half * BM + r] = qa.x + qa.y;
+            named_bar_sync(1, kEpiWarps * 32);
+            if (half == 0 && row < a.rows) {
+                if (a.rinv) a.rinv[row] = 1.0f / sqrtf(red_s[2 * BM + r] + red_s[3 * BM + r]);  // no epsilon: the scoring kernels' convention
                 if (a.norm) a.norm[row] = nrm;
             }
         }
@@ -220,10 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
     if (warp == kTmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -240,12 +271,12 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
     if (n_in <= 0 || n_in % 64 != 0) return set_error(PB2_ERR_ARG, "project_normalize: n_in must be a positive multiple of 64");
     if (n_out <= 0 || n_out % 64 != 0 || n_out > proj::kMaxOut)
         return set_error(PB2_ERR_ARG, "project_normalize: n_out must be a multiple of 64, at most 512");
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return set_error(PB2_ERR_ARG, "project_normalize: bias must be 16-byte aligned");
     if (ld_out % 8 != 0 || ld_out < n_out) return set_error(PB2_ERR_ARG, "project_normalize: ld_out %% 8 == 0, >= n_out");
     CUtensorMap tx, tw, to;
     int rc = make_tmap_2d(&tx, x, 2, (uint64_t)rows, (uint64_t)n_in, (uint64_t)ldx * 2, proj::BM, proj::BK);
     if (rc) return rc;
-    const int w_box = n_out < 256 ? n_out : 256;  // W rows per TMA box (a second box covers rows 256..511)
-    rc = make_tmap_2d(&tw, w, 2, (uint64_t)n_out, (uint64_t)n_in, (uint64_t)ldw * 2, (uint32_t)w_box, proj::BK);
+    rc = make_tmap_2d(&tw, w, 2, (uint64_t)n_out, (uint64_t)n_in, (uint64_t)ldw * 2, proj::kWBox, proj::BK);
     if (rc) return rc;
     rc = make_tmap_2d(&to, out, 2, (uint64_t)rows, (uint64_t)n_out, (uint64_t)ld_out * 2, 32, 64);
     if (rc) return rc;
@@ -253,7 +284,7 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
     a.rows = rows;
     a.n_out = n_out;
     a.kblocks = n_in / proj::BK;
-    a.tx_bytes = (uint32_t)(proj::kXBytes + w_box * proj::BK * 2 * (n_out > 256 ? 2 : 1));
+    a.tx_bytes = (uint32_t)(2 * proj::kXBytes + n_out * proj::BK * 2);  // both CTAs: two x tiles + all W rows once
     a.bias = bias;
     a.eps = eps;
     a.rinv = rinv;
@@ -266,8 +297,11 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
         if (rc) return rc;
         configured = true;
     }
-    const int64_t n_tiles = (rows + proj::BM - 1) / proj::BM;
-    const int grid = (int)std::min<int64_t>(n_tiles, sm_count());
-    proj::project_normalize_kernel<<<grid, proj::kThreads, proj::kSmem, (cudaStream_t)stream>>>(tx, tw, to, a);
+    const int64_t n_tiles = (rows + 2 * proj::BM - 1) / (2 * proj::BM);
+    const int grid = 2 * (int)std::min<int64_t>(n_tiles, sm_count() / 2);
+    rc = check_cuda(launch_ex(proj::project_normalize_kernel, (unsigned)grid, (unsigned)proj::kThreads, (size_t)proj::kSmem,
+                              (cudaStream_t)stream, 2, tx, tw, to, a),
+                    "project_normalize launch");
+    if (rc) return rc;
     return check_launch("project_normalize");
 }

@@ -574,3 +574,62 @@ def test_embedding_store_scoring(pb, tmp_path):
     assert (row["recall_jitter"].cpu() != ref_jit).float().mean().item() < 2e-3
     assert torch.allclose(torch.as_tensor(row["triplet_acc"]).float().cpu(), torch.as_tensor(ref_acc).float(), atol=2e-3)
     assert torch.equal(row["recall_at_10_fixed"], row["recall_fixed"][:, 10, :])
+
+
+def test_gallery_131k_properties(pb):
+    """C5-shaped gallery at 2^17 clips (4 x 4 gradient-matrix blocks: the stream-K / CTA-pair gradient GEMMs and the
+    blocked hinge pass exactly as in the 2^20 bench), checked through size-independent properties -- the reference
+    cannot run it (N^2 fp32 = 64 GiB) -- plus exact ranks and gradient rows on random subsets against the oracle."""
+    from peppa_b200.gallery import GalleryStep
+    n = 1 << 17
+    g = torch.Generator(device="cuda").manual_seed(666)
+    V = torch.nn.functional.normalize(torch.randn(n, 512, generator=g, device="cuda"), dim=1)
+    A = torch.nn.functional.normalize(2.0 * V + torch.randn(n, 512, generator=g, device="cuda"), dim=1).bfloat16()
+    V = V.bfloat16()
+    step = GalleryStep(n, 512, margin=0.2, top_n=10)
+    out = step.run(A, V)
+    loss, dA, dV, ranks = out["loss"].item(), out["dA"].clone(), out["dV"].clone(), out["ranks"].clone()
+    # (1) the normalisation Jacobian makes every gradient row orthogonal to its input row
+    for grad, x in ((dA, A), (dV, V)):
+        dots = (grad.double() * x.double()).sum(1).abs().max().item()
+        assert dots < 1e-4 * grad.double().norm(dim=1).max().item()
+    # (2) recall is the histogram of the ranks; monotone in n
+    rec = out["recall"].cpu()
+    assert rec[0] == 0 and bool((rec[1:] >= rec[:-1]).all())
+    for k in (1, 5, 10):
+        assert abs(rec[k].item() - (ranks < k).float().mean().item()) < 1e-6
+    # (3) the loss is symmetric in the roles of the two modalities (pig/loss.py:41-48 adds both directions)
+    swapped = step.run(V, A)
+    assert abs(swapped["loss"].item() - loss) < 1e-6 * abs(loss)
+    assert rel_err(swapped["dA"], dV) < 1e-5 and rel_err(swapped["dV"], dA) < 1e-5
+    # (4) permuting the clips permutes ranks and gradient rows (near-ties may move a rank)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(3)).cuda()
+    p = step.run(A[perm].contiguous(), V[perm].contiguous())
+    assert abs(p["loss"].item() - loss) < 1e-6 * abs(loss)
+    assert int((p["ranks"] != ranks[perm]).sum()) <= 8
+    assert rel_err(p["dA"], dA[perm]) < 1e-5
+    # (5) deterministic
+    again = step.run(A, V)
+    assert torch.equal(again["dA"], dA) and torch.equal(again["dV"], dV) and again["loss"].item() == loss
+    # (6) exact ranks of 256 random queries against the oracle formulation, and their gradient rows in fp64
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:256].cuda()
+    Af, Vf = A.double(), V.double()
+    Ah, Vh = Af / Af.norm(dim=1, keepdim=True), Vf / Vf.norm(dim=1, keepdim=True)
+    S = (Ah[rows].float() @ Vh.float().T)
+    d = 1 - S
+    pos = d[torch.arange(256, device="cuda"), rows].unsqueeze(1)
+    want = (d < pos).sum(1)
+    near = ((d - pos).abs() <= 1e-6).sum(1) > 1
+    assert bool(((ranks[rows].long() == want) | near).all())
+    diag = (Ah * Vh).sum(1)
+    S64 = Ah[rows] @ Vh.T                                                    # [256, n] rows of the score matrix
+    ir = (0.2 + S64 - diag[rows].unsqueeze(1)) >= 0                          # row hinge active
+    ic = (0.2 + S64 - diag.unsqueeze(0)) >= 0                                # column hinge active
+    G = ir.double() + ic.double()
+    G[torch.arange(256, device="cuda"), rows] = 0
+    # diagonal term: -(row count + column count); the column count of a sampled clip needs its whole column
+    col_cnt = ((0.2 + (Ah @ Vh[rows].T) - diag[rows].unsqueeze(0)) >= 0).sum(0) - 1
+    row_cnt = ir.sum(1) - 1
+    gA = G @ Vh - (row_cnt + col_cnt).double().unsqueeze(1) * Vh[rows]
+    gA = (gA - Ah[rows] * (gA * Ah[rows]).sum(1, keepdim=True)) / Af[rows].norm(dim=1, keepdim=True) / float(n) ** 2
+    assert rel_err(dA[rows], gA) < TOL

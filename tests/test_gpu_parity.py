@@ -464,7 +464,8 @@ def test_triplet_kernel_shapes(pb, d, dtype):
 
 
 @pytest.mark.parametrize("tr", [False, True])
-@pytest.mark.parametrize("r,c,d", [(20480, 2048, 512), (20000, 1000, 512), (9000, 4100, 256)])
+@pytest.mark.parametrize("r,c,d", [(20480, 2048, 512), (20000, 1000, 512), (9000, 4100, 256), (19000, 19000, 768),
+                                   (19200, 19200, 1024), (300, 40000, 512)])
 def test_grad_gemm_stream_k(pb, tr, r, c, d):
     """The stream-K decomposition of pb2_grad_gemm_ws (row blocks cut between CTAs, completed through the
     workspace) agrees with the whole-tile kernel and with fp64, and is bit-reproducible."""
@@ -481,9 +482,10 @@ def test_grad_gemm_stream_k(pb, tr, r, c, d):
     G = gm[:, :c].double()
     ref = (G.T if tr else G) @ z.double()
     scale = ref.abs().max()
-    assert ((tiles - ref).abs().max() / scale).item() < 1e-5
-    assert ((sk - ref).abs().max() / scale).item() < 1e-5
-    assert ((acc - (1 + 0.5 * ref)).abs().max() / scale).item() < 1e-5
+    tol = 1e-5 * max(1.0, ((r if tr else c) / 4096.0) ** 0.5)      # fp32 accumulation over the contraction length
+    assert ((tiles - ref).abs().max() / scale).item() < tol
+    assert ((sk - ref).abs().max() / scale).item() < tol
+    assert ((acc - (1 + 0.5 * ref)).abs().max() / scale).item() < tol
     assert torch.equal(sk, sk2)
 
 

@@ -171,7 +171,7 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
     accumulate = lse is not None
     if lse is None:
         lse = torch.empty(r, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("sim_lse_rows", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
         check(lib.pb2_sim_lse_rows(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0), y.stride(0),
                                    float(scale), _ptr(pmax), _ptr(psum), st), "sim_lse_rows")
@@ -190,7 +190,7 @@ def lse_combine(parts):
 
 def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, scale=1.0):
     r, c = x.shape[0], y.shape[0]
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("sim_lse_grad", 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_lse_grad(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(den_row), _ptr(den_col), r, c,
                                            x.shape[1], x.stride(0), y.stride(0), float(scale), _ptr(gmat), int(ld_g),
                                            _stream(x.device)), "sim_lse_grad")

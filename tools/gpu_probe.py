@@ -335,6 +335,37 @@ def step_simpair():
     lib.pb2_debug_sim_pair(0)
 
 
+def step_milnce_perf():
+    """MIL-NCE gallery step (pig/loss.py:13-26 fwd+bwd, K = 1) on a 65536-clip gallery: time per kernel."""
+    import torch
+    from peppa_b200 import ops
+    from peppa_b200.gallery import GalleryStep
+    n = 65536
+    V, A = emb(n)
+    step = GalleryStep(n, 512, loss="milnce", temperature=0.07)
+    for _ in range(2):
+        out = step.run(A, V)
+    torch.cuda.synchronize()
+    ops.EVENT_LOG = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        out = step.run(A, V)
+    e1.record()
+    torch.cuda.synchronize()
+    log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    agg = {}
+    for name, work, s, e in log:
+        k = agg.setdefault(name, [0, 0.0, 0.0])
+        k[0] += 1
+        k[1] += s.elapsed_time(e)
+        k[2] += work
+    ms = e0.elapsed_time(e1) / 3
+    print(f"milnce gallery {n}: {ms:.2f} ms/step  {n * n / ms / 1e6:.1f} Gpairs/s  loss {out['loss'].item():.5f}")
+    for name, (cnt, t, w) in agg.items():
+        print(f"  {name}: {cnt} launches, {t / cnt:.3f} ms avg, {w / t / 1e9:.0f} TF/s")
+
+
 def step_streamk():
     """grad_gemm: CTA pairs (cta_group::2) on/off x stream-K on/off: agreement with fp64, determinism, sustained time."""
     import torch

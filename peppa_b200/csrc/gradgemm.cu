@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
+static int g_units_cap = 0;
 
 constexpr int64_t kFlagBytes = 1024;  // flags of up to 256 CTAs, then the parked accumulators
 static int64_t workspace_bytes() { return kFlagBytes + (int64_t)sm_count() * BM * 512 * 4; }
@@ -401,7 +402,8 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
     if (rc) return rc;
     // stream-K when whole tiles would leave part of the machine idle in the last wave and every group's
     // range spans at least one full tile (so a row block is cut at most once)
-    const int units = sm_count() / kCtas;  // CTAs or CTA pairs the machine runs at once
+    int units = sm_count() / kCtas;  // CTAs or CTA pairs the machine runs at once
+    if (g_units_cap > 0 && g_units_cap < units) units = g_units_cap;  // measurement hook (pb2_debug_gg_units)
     if (workspace && a.n_cb <= units && units * kCtas <= 256) {
         const int groups = units / a.n_cb;
         const int64_t total = (int64_t)a.n_rb * a.kblocks;
@@ -466,6 +468,10 @@ extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep)
     return PB2_OK;
 }
 
+extern "C" int pb2_debug_gg_units(int cap) {
+    gg::g_units_cap = cap;
+    return PB2_OK;
+}
 extern "C" int pb2_debug_gg_pair(int mode) {
     gg::g_pair_mode = mode;
     return PB2_OK;

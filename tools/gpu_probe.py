@@ -366,6 +366,27 @@ def step_milnce_perf():
         print(f"  {name}: {cnt} launches, {t / cnt:.3f} ms avg, {w / t / 1e9:.0f} TF/s")
 
 
+def step_gg_units():
+    """Gradient GEMM (CTA pairs, 512-wide, stream-K) on fewer SM pairs: cuBLAS's own kernel runs 33 clusters of 4
+    (132 of 148 SMs) and is ahead under the power cap -- does leaving SMs idle help ours?"""
+    import torch
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = 32768
+    gm, ld = ops.gmat_alloc(n, n, "cuda")
+    gm.copy_(torch.randint(0, 3, (n, ld), device="cuda").half())
+    z = (torch.randn(n, 512, device="cuda") * 0.05).half()
+    out = torch.zeros(n, 512, device="cuda")
+    for cap in (74, 70, 66, 62, 56, 74):
+        lib.pb2_debug_gg_units(cap)
+        for tr in (False, True):
+            ms = _t(lambda: ops.grad_gemm(gm, n, n, ld, z, transpose=tr, out=out, accumulate=True), iters=300, warm=20)
+            print(f"pairs={cap} T={tr}: {ms:.3f} ms {2 * n * n * 512 / ms / 1e9:.0f} TF/s (300 back to back)", flush=True)
+    lib.pb2_debug_gg_units(0)
+    ms = _t(lambda: torch.matmul(gm[:, :n], z), iters=300, warm=20)
+    print(f"torch.matmul: {ms:.3f} ms", flush=True)
+
+
 def step_streamk():
     """grad_gemm: CTA pairs (cta_group::2) on/off x stream-K on/off: agreement with fp64, determinism, sustained time."""
     import torch

@@ -62,3 +62,29 @@ def test_sampler_matches_golden_without_device():
         assert np.array_equal(np.array(pos), g["draws"][k, 0].numpy())
         assert np.array_equal(np.array(neg), g["draws"][k, 1].numpy())
     assert triplet.pairs([1, 2, 3, 4, 5]) == [[1, 2], [3, 4]] and triplet.pairs([1]) == []
+
+
+def test_encoder_tail_module_is_state_dict_compatible_with_linear():
+    """ProjectNormalize keeps nn.Linear's parameters (pig/models.py:96-98 `self.project = nn.Linear(...)`), so a
+    checkpoint's `project.*` tensors load unchanged; without CUDA the forward raises (no CPU fallback)."""
+    from peppa_b200 import encoder
+    lin = torch.nn.Linear(28, 512)
+    mod = encoder.ProjectNormalize.from_linear(lin)
+    assert set(mod.state_dict()) == set(lin.state_dict()) == {"weight", "bias"}
+    assert torch.equal(mod.weight, lin.weight) and torch.equal(mod.bias, lin.bias)
+    nb = encoder.ProjectNormalize(512, 256, bias=False)
+    assert nb.bias is None and nb.weight.shape == (256, 512)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            mod(torch.randn(4, 28))
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        encoder.project_normalize(torch.randn(4, 64), torch.randn(100, 64))
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    null = C.c_void_p(0)
+    assert lib.pb2_project_normalize(null, null, null, 8, 512, 512, 512, 512, 1e-12, null, 512, null, null, null) == 1
+    assert lib.pb2_project_normalize(null, null, null, 0, 512, 512, 512, 512, 1e-12, null, 512, null, null, null) == 0
+    assert lib.pb2_grad_gemm_dual(null, 1, 8, 8, 64, null, null, 1, 512, 512, 512, 1.0, null, null, 512, 512, null) == 1
+    assert lib.pb2_milnce_finish_k(null, 512, null, null, 8, 2, 1, 512, 512, 1.0, null, null, 512, null) == 1
+    assert lib.pb2_grad_gemm_workspace() >= 148 * 128 * 512 * 4

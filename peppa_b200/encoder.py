@@ -41,6 +41,8 @@ class _ProjectNormalizeFn(torch.autograd.Function):
         out, rinv, norm = ops.project_normalize(xb, wb, b, eps)
         ctx.save_for_backward(xb, wb, out, norm)
         ctx.meta = (x.dtype, x.device, x.shape[1], weight.dtype, weight.device, bias is not None and bias.dtype, eps)
+        if x.device != out.device:          # results follow the input's device, like the loss / metric drop-ins
+            out, rinv = out.to(x.device), rinv.to(x.device)
         ctx.mark_non_differentiable(rinv)
         return out, rinv
 
@@ -48,7 +50,7 @@ class _ProjectNormalizeFn(torch.autograd.Function):
     def backward(ctx, g_out, _g_rinv):
         xb, wb, out, norm = ctx.saved_tensors
         xd, xdev, n_in, wd, wdev, bd, eps = ctx.meta
-        g = g_out.to(device=out.device, dtype=torch.float32)
+        g = g_out.to(device=out.device, dtype=torch.float32)      # `out` was saved on the GPU
         e = out.float()
         # Jacobian of y -> y / max(||y||, eps):  (g - e <g, e>) / ||y||
         dy = (g - e * (g * e).sum(dim=1, keepdim=True)) / norm.clamp_min(eps).unsqueeze(1)
@@ -58,7 +60,7 @@ class _ProjectNormalizeFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = (dy.t() @ xb.float())[:, :n_in].to(device=wdev, dtype=wd)
         if ctx.needs_input_grad[2]:
-            gb = dy.sum(dim=0).to(dtype=bd)
+            gb = dy.sum(dim=0).to(device=wdev, dtype=bd)
         return gx, gw, gb, None
 
 

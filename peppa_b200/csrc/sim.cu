@@ -658,9 +658,12 @@ struct LseGradPolicy {
 };
 
 // ---------------------------------------------------------------------------------- kernel
+// kCtas: 1 = independent CTAs; 2 = CTA pairs sharing one MMA (cta_group::2); 3 = clusters of 2 whose CTAs take
+// the tiles (rb, cb) and (rb + 1, cb), run independent MMAs and share the Y tile: each loads half of it and
+// multicasts that half to both (a third fewer L2 lookups, no coupling through the accumulators).
 template <int BN, int G, bool kOut, int kCtas>
 struct SimSmem {
-    static constexpr int kStageBytes = (BM + BN / kCtas) * BK * 2;  // a CTA of a pair stages half of Y's rows
+    static constexpr int kStageBytes = (BM + (kCtas == 2 ? BN / 2 : BN)) * BK * 2;  // a pair CTA stages half of Y
     // shared memory not spent on staging goes to the TMA pipeline: bytes in flight bound the MMA rate
     static constexpr int kOutBufs = G >= 3 ? 1 : 2;  // G >= 3: one 64-column slab per warp and tile
     static constexpr int kOutBytes = kOut ? 4 * G * kOutBufs * kOutSlabBytes : 0;
@@ -705,8 +708,11 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr int kLoaderWarp = 4 * G, kMmaWarp = 4 * G + 1, kTmaWarp = 4 * G + 2;
-    const uint32_t crank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
-    const int64_t unit0 = blockIdx.x / kCtas, n_units = gridDim.x / kCtas;  // tiles are dealt to CTAs / CTA pairs
+    constexpr int kCluster = kCtas >= 2 ? 2 : 1;    // CTAs per cluster
+    constexpr bool kSharedMma = kCtas == 2;         // one M = 256 MMA per pair
+    constexpr bool kMcast = kCtas == 3;             // independent MMAs, Y tile multicast
+    const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;  // pairs: 0 = leader (issues the MMAs)
+    const int64_t unit0 = blockIdx.x / kCluster, n_units = gridDim.x / kCluster;  // tiles are dealt to CTAs / clusters
 
     if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -716,23 +722,23 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < L::kStages; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, kMcast ? 2 : 1);  // multicast: a stage is refilled once BOTH CTAs' MMAs have read it
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full + a, 1);
-            mbar_init(acc_empty + a, kEpiWarps * kCtas);  // the leader's collects both CTAs' epilogues
+            mbar_init(acc_empty + a, kEpiWarps * (kSharedMma ? 2 : 1));  // a pair leader's collects both CTAs' epilogues
             mbar_init(vec_full + a, 1);
             mbar_init(vec_empty + a, kEpiWarps);
         }
         fence_mbar_init();
     }
     if (warp == kTmaWarp) {
-        if (kCtas == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+        if (kSharedMma) tmem_alloc_pair(tmem_slot, kTmemCols);
         else tmem_alloc(tmem_slot, kTmemCols);
     }
     pdl_launch_dependents();
     tc_fence_before();
-    if (kCtas == 2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
+    if (kCluster == 2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             for (int64_t t = unit0; t < c.n_tiles; t += n_units) {
                 int rb, cb;
                 tile_coords(t, c.n_rb, c.n_cb, rb, cb);
-                const int xrow = (rb * kCtas + (int)crank) * BM, yrow = cb * BN + (int)crank * (BN / kCtas);
+                const int xrow = (rb * kCluster + (int)crank) * BM, yrow = cb * BN + (int)crank * (BN / kCluster);
                 for (int kb = 0; kb < c.kblocks; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sx = smem + stage * L::kStageBytes;
@@ -755,6 +761,11 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                         mbar_arrive_expect_tx(full + stage, L::kStageBytes);
                         tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, kEvictNormal);
                         tma_load_2d(sy, &tm_y, full + stage, kb * BK, yrow, kEvictNormal);
+                    } else if (kMcast) {  // own X tile; this CTA's half of the Y tile lands in both CTAs
+                        mbar_arrive_expect_tx(full + stage, L::kStageBytes);  // X + both halves of Y arrive here
+                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, kEvictNormal);
+                        tma_load_2d_mcast(sy + crank * (BN / 2) * BK * 2, &tm_y, full + stage, kb * BK, yrow, (uint16_t)3,
+                                          kEvictNormal);
                     } else {  // both CTAs' bytes are counted on the leader's barrier
                         if (crank == 0) mbar_arrive_expect_tx(full + stage, L::kStageBytes * kCtas);
                         const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
@@ -770,8 +781,8 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         }
     } else if (warp == kMmaWarp) {
         // ====================================================================== MMA issuer
-        if (lane == 0 && crank == 0) {
-            constexpr uint32_t idesc = make_idesc(BM * kCtas, BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+        if (lane == 0 && (crank == 0 || !kSharedMma)) {
+            constexpr uint32_t idesc = make_idesc(BM * (kSharedMma ? 2 : 1), BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
             // K-major 128B-swizzled operands: descriptor = {start >> 4 | LBO 16 B, SBO 1024 B | version | swizzle}.
             // Only the start address changes, linearly: one running low word, adds instead of rebuilds.
             const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
@@ -791,11 +802,12 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        if (kCtas == 2) umma_f16_pair_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, desc_hi, idesc, acc);
+                        if (kSharedMma) umma_f16_pair_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, desc_hi, idesc, acc);
                         else umma_f16_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, idesc, acc);
                     }
-                    // stage reusable (in both CTAs of a pair) once these MMAs have read it
-                    if (kCtas == 2) umma_commit_pair(empty + stage);
+                    // stage reusable (in both CTAs of a cluster) once these MMAs have read it
+                    if (kSharedMma) umma_commit_pair(empty + stage);
+                    else if (kMcast) umma_commit_mcast(empty + stage, (uint16_t)3);
                     else umma_commit(empty + stage);
                     lo += kStageLo;
                     if (++stage == L::kStages) {
@@ -804,7 +816,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                         lo = lo0;
                     }
                 }
-                if (kCtas == 2) umma_commit_pair(acc_full + as);  // accumulator complete -> both epilogues
+                if (kSharedMma) umma_commit_pair(acc_full + as);  // accumulator complete -> both epilogues
                 else umma_commit(acc_full + as);
             }
         }
@@ -815,7 +827,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             const int as = (int)(it & 1);
             int rb, cb;
             tile_coords(t, c.n_rb, c.n_cb, rb, cb);
-            const int64_t row0 = ((int64_t)rb * kCtas + crank) * BM, col0 = (int64_t)cb * BN;
+            const int64_t row0 = ((int64_t)rb * kCluster + crank) * BM, col0 = (int64_t)cb * BN;
             mbar_wait(vec_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);  // the epilogue is done with this buffer
             float* cv = colvec + as * (kMaxColVecs * kColVecStride);
             float* rv = rowvec + as * (kMaxRowVecs * BM);
@@ -881,7 +893,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             int rb, cb;
             tile_coords(t, c.n_rb, c.n_cb, rb, cb);
             TileCtx ctx;
-            ctx.row0 = ((int64_t)rb * kCtas + crank) * BM;
+            ctx.row0 = ((int64_t)rb * kCluster + crank) * BM;
             ctx.col0 = (int64_t)cb * BN;
             ctx.row = ctx.row0 + quad * 32 + lane;
             ctx.row_valid = ctx.row < c.rows;
@@ -926,7 +938,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(vec_empty + as);  // the loader may restage this buffer
-                if (kCtas == 2) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + as), 0));  // the leader's MMA warp
+                if (kSharedMma) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + as), 0));  // the leader's MMA warp
                 else mbar_arrive(acc_empty + as);
             }
             pol.tile_end(p, c, ctx);
@@ -935,11 +947,11 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         pol.kernel_end(p, red, kEpiWarps);
     }
     tc_fence_before();
-    if (kCtas == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
+    if (kCluster == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
     else __syncthreads();
     if (warp == kTmaWarp) {
         tc_fence_after();
-        if (kCtas == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        if (kSharedMma) tmem_dealloc_pair(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
@@ -972,7 +984,8 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     CUtensorMap tx, ty, to;
     int rc = make_tmap_2d(&tx, x, 2, (uint64_t)rows, (uint64_t)dim, (uint64_t)ldx * 2, BM, BK);
     if (rc) return rc;
-    rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN / kCtas, BK);
+    constexpr int kCluster = kCtas >= 2 ? 2 : 1;
+    rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN / kCluster, BK);
     if (rc) return rc;
     if (Policy::kStoresG && om.ptr) {
         rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
@@ -987,7 +1000,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rows = rows;
     c.cols = cols;
     c.kblocks = dim / BK;
-    c.n_rb = (int)((rows + BM * kCtas - 1) / (BM * kCtas));  // row blocks of a CTA (pair) tile
+    c.n_rb = (int)((rows + BM * kCluster - 1) / (BM * kCluster));  // row blocks of a CTA (cluster) tile
     c.n_cb = (int)((cols + BN - 1) / BN);
     c.n_tiles = (int64_t)c.n_rb * c.n_cb;
     c.diag_only = -g_skip_store;
@@ -1007,8 +1020,8 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
         if (rc) return rc;
         configured = true;
     }
-    const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid() / kCtas) * kCtas;
-    rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, kCtas, tx, ty, to, c, pp), what);
+    const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid() / kCluster) * kCluster;
+    rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, kCluster, tx, ty, to, c, pp), what);
     if (rc) return rc;
     return check_launch(what);
 }
@@ -1018,7 +1031,8 @@ static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
 // correct (tools/gpu_probe.py simpair: identical counts / ranks) but measured SLOWER here -- hinge pass 1.34 vs
 // 1.23 ms, rank pass 0.843 vs 0.827 ms per 32768^2 block, sustained: a pair's MMA for tile t+2 waits for BOTH
 // CTAs' epilogues of tile t, and these kernels are bound by their epilogues, not by operand traffic (unlike the
-// gradient GEMM, whose gain came from the 512-wide pair tile reading G once).  Kept as a measured option.
+// gradient GEMM, whose gain came from the 512-wide pair tile reading G once).  2 = clusters of 2 with independent
+// MMAs and a multicast Y tile: within noise of independent CTAs (1.25 ms / 0.794 ms).  Kept as measured options.
 static int g_sim_pair = 0;
 
 template <class Policy>
@@ -1036,14 +1050,17 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
 #define PB2_SIM(B, GG, CC) \
     launch_sim<Policy, B, GG, CC>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
     const bool pair = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 1;
+    const bool mcast = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 2;
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
         return PB2_SIM(128, 2, 1);
     } else if constexpr (Policy::kStoresG) {
         if (bn == 192) return PB2_SIM(192, 3, 1);
+        if (mcast) return PB2_SIM(256, 2, 3);
         if (pair) return PB2_SIM(256, 2, 2);
         if (bn == 256) return PB2_SIM(256, 2, 1);
         return PB2_SIM(128, 2, 1);
     } else {
+        if (mcast) return PB2_SIM(256, 2, 3);
         if (pair) return PB2_SIM(256, 2, 2);
         if (bn == 256) return PB2_SIM(256, 2, 1);
         if (bn == 128) return PB2_SIM(128, 2, 1);

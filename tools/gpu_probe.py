@@ -315,7 +315,7 @@ def step_simpair():
     g, ld = ops.gmat_alloc(n, n, "cuda")
     idx = torch.arange(n, device="cuda")
     res = {}
-    for pair in (0, 1):
+    for pair in (0, 1, 2, 0):      # 0 independent CTAs, 1 shared-MMA pairs, 2 clusters of 2 with Y multicast
         lib.pb2_debug_sim_pair(pair)
         rc = torch.zeros(n, dtype=torch.int32, device="cuda")
         cc = torch.zeros(n, dtype=torch.int32, device="cuda")
@@ -328,10 +328,11 @@ def step_simpair():
         ms_r = _t(lambda: ops.sim_rank(A, V, ra, rv, thr, idx, rank=rk2), iters=200, warm=20)
         print(f"pair={pair}: hinge+rank+G {ms_h:.3f} ms ({2 * n * n * 512 / ms_h / 1e9:.0f} TF/s)   rank only {ms_r:.3f} ms "
               f"({2 * n * n * 512 / ms_r / 1e9:.0f} TF/s)   (200 back to back)", flush=True)
-    a, b = res[0], res[1]
-    print("row counts equal", torch.equal(a[0], b[0]), "col counts equal", torch.equal(a[1], b[1]), "hinge ranks equal",
-          torch.equal(a[2], b[2]), "rank-kernel ranks equal", torch.equal(a[3], b[3]), "loss partial sums", a[4], b[4],
-          "G sums", a[5], b[5], flush=True)
+    for m in (1, 2):
+        a, b = res[0], res[m]
+        print(f"mode {m} vs 0: row counts equal", torch.equal(a[0], b[0]), "col counts equal", torch.equal(a[1], b[1]),
+              "hinge ranks equal", torch.equal(a[2], b[2]), "rank-kernel ranks equal", torch.equal(a[3], b[3]),
+              "loss partial sums", a[4], b[4], "G sums", a[5], b[5], flush=True)
     lib.pb2_debug_sim_pair(0)
 
 

@@ -635,3 +635,9 @@ def test_gallery_131k_properties(pb):
     gA = G @ Vh - (row_cnt + col_cnt).double().unsqueeze(1) * Vh[rows]
     gA = (gA - Ah[rows] * (gA * Ah[rows]).sum(1, keepdim=True)) / Af[rows].norm(dim=1, keepdim=True) / float(n) ** 2
     assert rel_err(dA[rows], gA) < TOL
+
+
+def test_graft_entry_smoke(pb):
+    """The driver's smoke(): one small invocation of the hot path on cuda:0 checked against the oracle."""
+    import __graft_entry__ as entry
+    entry.smoke()

@@ -57,7 +57,8 @@ def _pair_ranks(candidates, references, correct):
     else:                           # several targets per row: one query copy per (row, target) pair
         q, rq_p = qb[rows].contiguous(), rq[rows].contiguous()
     # the target's own score comes from the same tensor-core arithmetic as every candidate's
-    identity = counts is None and cols.numel() == gb.shape[0] and bool((cols == rows).all())
+    # (``correct=None`` hands back one index tensor for rows and columns: no device round trip to find that out)
+    identity = counts is None and cols.numel() == gb.shape[0] and (cols is rows or bool((cols == rows).all()))
     tgt, rt = (gb, rg) if identity else (gb[cols].contiguous(), rg[cols].contiguous())
     _, pos_thr = ops.sim_diag(q, tgt, rq_p, rt)
     rank = ops.sim_rank(q, gb, rq_p, rg, pos_thr, cols)

@@ -85,6 +85,7 @@ struct TileCtx {
     int cols_valid;  // number of valid columns in this tile (<= BN)
     int cb;          // column-block index
     int half;        // which column group of the tile this warp covers
+    int warp_cols;   // columns of the tile one epilogue warp covers (BN / G)
     int quad;        // TMEM lane quadrant of this warp (rows quad*32 .. +31 of the tile)
 };
 
@@ -589,9 +590,19 @@ struct LseRowPolicy {
     }
     __device__ void tile_end(const Params& p, const SimCommon& c, const TileCtx& t) {
         if (!t.row_valid) return;
-        const int64_t slot = ((int64_t)t.cb * 2 + t.half) * c.rows + t.row;
-        p.part_max[slot] = m;
-        p.part_sum[slot] = s;
+        // partial layout: two slots per 128 columns (pb2_sim_lse_parts).  A warp of a 128-wide tile covers 64
+        // columns = one slot; a warp of a 256-wide tile covers 128 columns = a slot pair (second one empty).
+        if (t.warp_cols == 64) {
+            const int64_t slot = ((int64_t)t.cb * 2 + t.half) * c.rows + t.row;
+            p.part_max[slot] = m;
+            p.part_sum[slot] = s;
+        } else if (((int64_t)t.cb * 2 + t.half) * 128 < c.cols) {  // a 128-column unit past the last column has no slots
+            const int64_t slot = ((int64_t)t.cb * 4 + t.half * 2) * c.rows + t.row;
+            p.part_max[slot] = m;
+            p.part_sum[slot] = s;
+            p.part_max[slot + c.rows] = -PB2_INF;
+            p.part_sum[slot + c.rows] = 0.f;
+        }
     }
     __device__ void kernel_end(const Params&, float*, int) {}
 };
@@ -900,6 +911,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             ctx.cols_valid = (int)min((int64_t)BN, c.cols - ctx.col0);
             ctx.cb = cb;
             ctx.half = half;
+            ctx.warp_cols = kChunks * 32;
             ctx.quad = quad;
             const float* cv = colvec + as * (kMaxColVecs * kColVecStride);
             mbar_wait(vec_full + as, (uint32_t)((it >> 1) & 1));  // operands staged by the loader warp
@@ -1160,8 +1172,10 @@ extern "C" int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_
                                 float* part_sum, void* stream) {
     if (rows > 0 && cols > 0 && (!part_max || !part_sum)) return set_error(PB2_ERR_ARG, "sim_lse_rows: null");
     LseRowPolicy::Params pp{part_max, part_sum};
+    // 256-wide tiles once they fill the machine (the partial layout is the 128-column one either way)
+    const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
     return dispatch_sim<LseRowPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
-                                      "sim_lse_rows", 128);
+                                      "sim_lse_rows", bn);
 }
 
 extern "C" int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const float* rinv_y,

@@ -41,7 +41,8 @@ MARGIN = 0.2
 TOP_N = 10
 METRIC = {"gallery": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "train1024": "similarity pairs/sec (loss fwd+bwd)",
           "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)",
-          "encoder_tail": "rows/sec (Linear 512x512 + L2-normalise + bf16 + rinv)"}
+          "encoder_tail": "rows/sec (Linear 512x512 + L2-normalise + bf16 + rinv)",
+          "milnce64k": "similarity pairs/sec (MIL-NCE loss fwd+bwd)"}
 
 
 UNIT = {"triplets1m": "triplets/s", "encoder_tail": "rows/s"}
@@ -212,7 +213,15 @@ def cpu_sample(workload, n_s, steps, warmup):
     workload; returns (metric value, seconds per step, description of the sample)."""
     import torch
     from oracle import pig_oracle as O
-    if workload == "encoder_tail":
+    if workload == "milnce64k":
+        a, v = synth_embeddings(n_s, 666, "cpu")
+        a, v = a.float(), v.float()
+
+        def step():
+            vv, aa = (v / 0.07).clone().requires_grad_(True), a.clone().requires_grad_(True)
+            O.milnce_loss(aa, vv).backward()
+        units, what = n_s * n_s, f"{n_s} x {n_s} sub-gallery, MILNCELoss fwd+bwd (logits / 0.07)"
+    elif workload == "encoder_tail":
         t = n_s * 16
         g = torch.Generator().manual_seed(666)
         x = torch.randn(t, DIM, generator=g).bfloat16().float()
@@ -312,6 +321,36 @@ def bench_gallery(args, rank, world, device, sync, all_max):
                    "rows_per_gpu": nl, "l2": "per-step working set (embeddings, fp16 copies, gradient-matrix blocks of 2 GiB) far exceeds the "
                                             "126 MB L2; no flush needed",
                    "parallelism": f"row-shard x{world}" + (" + NCCL all-gather/all-reduce/reduce-scatter" if world > 1 else "")}}
+
+
+def bench_milnce64k(args, device, sync):
+    """North-star kernel (a): MIL-NCE (pig/loss.py:13-26) forward + backward over a 65536-clip gallery with a
+    temperature -- tensor-core logits with online row and column log-sum-exp (the N x N logits never reach HBM)
+    and the fused backward (recomputed logits -> fp16 gradient matrix -> two tensor-core GEMMs)."""
+    import torch
+    from peppa_b200.gallery import GalleryStep
+    n = 65536
+    a_dev, v_dev = synth_embeddings(n, 666, device)
+    a_host, v_host = a_dev.cpu().pin_memory(), v_dev.cpu().pin_memory()
+    step = GalleryStep(n, DIM, device=device, loss="milnce", temperature=0.07)
+    steps, warm = max(args.steps, 5), max(args.warmup, 3)
+    m = measure(lambda: step.run(a_dev, v_dev), steps, warm, sync, device)
+    a_in, v_in = torch.empty_like(a_dev), torch.empty_like(v_dev)
+
+    def run_e2e():
+        a_in.copy_(a_host, non_blocking=True)
+        v_in.copy_(v_host, non_blocking=True)
+        return step.run(a_in, v_in)["loss"].item()
+
+    ms_e2e = timed(run_e2e, 3, 1, sync)
+    roof, table = roofline_of(m["kernels"], "tensor")
+    return {
+        "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
+        "launches": m["launches"], "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4, "flops_per_unit": 6.0 * DIM,
+        "scaling": "weak", "check": {"loss": m["out"]["loss"].item()}, "steps_used": steps,
+        "config": {"workload": "milnce64k (north-star kernel a): MILNCELoss fwd+bwd, 65536 x 65536 logits, temperature 0.07, online "
+                               "row + column log-sum-exp, fused backward", "gallery": n, "dim": DIM, "temperature": 0.07,
+                   "l2": "2 GiB gradient-matrix blocks and 128 MiB of embeddings per step exceed the 126 MB L2; no flush needed"}}
 
 
 def bench_train1024(args, device, sync):
@@ -497,7 +536,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail"])
+    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail", "milnce64k"])
     ap.add_argument("--gallery-n", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-extras", action="store_true")
@@ -536,7 +575,7 @@ def main():
         return t.item()
 
     single = {"train1024": bench_train1024, "retrieval16k": bench_retrieval16k, "triplets1m": bench_triplets1m,
-              "encoder_tail": bench_encoder_tail}
+              "encoder_tail": bench_encoder_tail, "milnce64k": bench_milnce64k}
     if args.workload == "gallery":
         line = line_from(bench_gallery(args, rank, world, device, sync, all_max), args, world, "gallery")
     else:

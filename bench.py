@@ -264,15 +264,25 @@ def cpu_sample(workload, n_s, steps, warmup):
 
 def cpu_baseline(workload, n_s):
     import torch
+    _all_host_threads()
     value, dt, what = cpu_sample(workload, n_s, 1, 1)
     return {"value": value, "unit": UNIT.get(workload, "pairs/s"), "cores": torch.get_num_threads(),
             "kind": "port", "sample": f"{what}; reference algorithm (oracle port); {dt:.3f} s per step; host has {os.cpu_count()} cpus"}
+
+
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
 
 
 def run_reference(args):
     import torch
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
+    _all_host_threads()
     value, dt, what = cpu_sample(args.workload, args.cpu_sample, args.steps, args.warmup)
     unit = UNIT.get(args.workload, "pairs/s")
     line = {

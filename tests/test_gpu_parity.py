@@ -519,6 +519,27 @@ def test_encoder_tail_project_normalize(pb, rows, n_in, n_out, bias):
         assert rel_err(mod.bias.grad, lin.bias.grad) < 2e-2
 
 
+def test_encoder_tail_column_split_variant(pb):
+    """The column-split kernel (pair of CTAs on the same rows, row statistics exchanged through distributed shared
+    memory with st.async) gives the same embeddings as the default row-split kernel."""
+    from peppa_b200 import _cabi, ops
+    g = torch.Generator().manual_seed(11)
+    for rows, n_in, n_out in ((3000, 512, 512), (129, 256, 128), (2000, 1024, 384)):
+        x = torch.randn(rows, n_in, generator=g).bfloat16().cuda()
+        w = (torch.randn(n_out, n_in, generator=g) / n_in ** 0.5).bfloat16().cuda()
+        b = torch.randn(n_out, generator=g).cuda()
+        _cabi.lib().pb2_debug_proj_variant(2)
+        try:
+            o2, r2, m2 = ops.project_normalize(x, w, b)
+            torch.cuda.synchronize()
+        finally:
+            _cabi.lib().pb2_debug_proj_variant(0)
+        o1, r1, m1 = ops.project_normalize(x, w, b)
+        assert (o1.float() - o2.float()).abs().max().item() <= 2.0 ** -8 * o1.float().abs().max().item()
+        assert rel_err(r2, 1.0 / o2.float().norm(dim=1)) < 1e-5       # rinv belongs to ITS rounded rows
+        assert rel_err(m2, m1) < 1e-5 and rel_err(r2, r1) < 1e-3
+
+
 def test_encoder_tail_feeds_the_loss(pb):
     """The tail's (bf16 rows, rinv) pair is what the scoring kernels consume: TripletLoss on the fused
     embeddings equals the reference pipeline project -> normalize -> TripletLoss on the same bf16 weights."""

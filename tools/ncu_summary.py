@@ -31,12 +31,13 @@ def raw(rep):
 
 
 def stalls(rep):
+    """Warp-stall sampling per captured kernel (the CSV source page prints every kernel's section twice)."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    per_kernel, cur, hdr = [], None, None
+    sections, cur, hdr = [], None, None
     for row in csv.reader(out.splitlines()):
         if row and row[0] == "Kernel Name":
-            cur = Counter()
-            per_kernel.append(cur)
+            cur = (row[1], Counter())
+            sections.append(cur)
             hdr = None
         elif row and row[0] == "Address":
             hdr = row
@@ -44,11 +45,13 @@ def stalls(rep):
             for h, v in zip(hdr, row):
                 if h.startswith("stall_") and "Not Issued" not in h:
                     try:
-                        cur[h[6:]] += int(v)
+                        cur[1][h[6:]] += int(v)
                     except ValueError:
                         pass
     res = []
-    for c in per_kernel:
+    for i, (name, c) in enumerate(sections):
+        if i > 0 and sections[i - 1][0] == name and sections[i - 1][1] == c:
+            continue                                  # the duplicate of the previous section
         tot = sum(c.values()) or 1
         res.append({k: round(100.0 * v / tot, 1) for k, v in c.most_common(6)})
     return res
@@ -58,8 +61,9 @@ def main():
     out = {}
     for rep in sys.argv[2:]:
         ks, st = raw(rep), stalls(rep)
-        if len(ks) == 1 and len(st) == 1:      # the source page does not separate same-named template instances
-            ks[0]["warp_stall_samples_pct"] = st[0]
+        if len(ks) == len(st):
+            for k, x in zip(ks, st):
+                k["warp_stall_samples_pct_all_warps"] = x
         out[rep.split("/")[-1]] = ks
     with open(sys.argv[1], "w") as f:
         json.dump(out, f, indent=1)

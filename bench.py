@@ -42,7 +42,8 @@ TOP_N = 10
 METRIC = {"gallery": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "train1024": "similarity pairs/sec (loss fwd+bwd)",
           "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)",
           "encoder_tail": "rows/sec (Linear 512x512 + L2-normalise + bf16 + rinv)",
-          "milnce64k": "similarity pairs/sec (MIL-NCE loss fwd+bwd)"}
+          "milnce64k": "similarity pairs/sec (MIL-NCE loss fwd+bwd)",
+          "eval1467": "subset pairs/sec (500 x recall@1..10 over 100-clip subsets + 500 triplet resamples)"}
 
 
 UNIT = {"triplets1m": "triplets/s", "encoder_tail": "rows/s"}
@@ -213,7 +214,21 @@ def cpu_sample(workload, n_s, steps, warmup):
     workload; returns (metric value, seconds per step, description of the sample)."""
     import torch
     from oracle import pig_oracle as O
-    if workload == "milnce64k":
+    if workload == "eval1467":
+        import random
+        a, v = synth_embeddings(1467, 666, "cpu")
+        a, v = a.float(), v.float()
+        gd = torch.Generator().manual_seed(5)
+        dur = torch.randint(20, 60, (1467,), generator=gd).float() / 10.0
+        n_smp = 50                                             # a tenth of the evaluation's 500 samples (bounded CPU time)
+
+        def step():
+            torch.manual_seed(666)
+            random.seed(666)
+            O.resampled_recall_at_1_to_n(v, a, size=100, n_samples=n_smp, N=10)
+            O.score_triplets(v, a, dur, n_samples=n_smp)
+        units, what = n_smp * 100.0 * 100.0, f"{n_smp} of the 500 subsets / resamples on the 1467-clip gallery"
+    elif workload == "milnce64k":
         a, v = synth_embeddings(n_s, 666, "cpu")
         a, v = a.float(), v.float()
 
@@ -361,6 +376,53 @@ def bench_milnce64k(args, device, sync):
         "config": {"workload": "milnce64k (north-star kernel a): MILNCELoss fwd+bwd, 65536 x 65536 logits, temperature 0.07, online "
                                "row + column log-sum-exp, fused backward", "gallery": n, "dim": DIM, "temperature": 0.07,
                    "l2": "2 GiB gradient-matrix blocks and 128 MiB of embeddings per step exceed the 126 MB L2; no flush needed"}}
+
+
+def bench_eval1467(args, device, sync):
+    """The reference's evaluation call (pig/evaluation.py:159, pig/models.py:297-303): recall@1..10 over 500 random
+    100-clip subsets of a validation gallery of 1467 clips (results/data_statistics.csv), plus score_triplets with
+    500 duration-matched resamples (pig/models.py:311-317) -- 25.4 s + seconds on the CPU."""
+    import random
+
+    import torch
+    from peppa_b200 import metrics, triplet
+    n = 1467
+    a, v = synth_embeddings(n, 666, device)
+    g = torch.Generator().manual_seed(5)
+    dur = torch.randint(20, 60, (n,), generator=g).float() / 10.0
+
+    def step():
+        torch.manual_seed(666)
+        random.seed(666)
+        rec = metrics.resampled_recall_at_1_to_n(v, a, size=100, n_samples=500, N=10)
+        acc = triplet.score_triplets(v, a, dur, n_samples=500)["accuracy"]
+        return rec, acc
+
+    steps, warm = max(args.steps, 5), max(args.warmup, 3)
+    m = measure(step, steps, warm, sync, device)
+    a_host, v_host = a.cpu().pin_memory(), v.cpu().pin_memory()
+    a_in, v_in = torch.empty_like(a), torch.empty_like(v)
+
+    def run_e2e():
+        a_in.copy_(a_host, non_blocking=True)
+        v_in.copy_(v_host, non_blocking=True)
+        torch.manual_seed(666)
+        random.seed(666)
+        rec = metrics.resampled_recall_at_1_to_n(v_in, a_in, size=100, n_samples=500, N=10)
+        return rec.mean().item(), triplet.score_triplets(v_in, a_in, dur, n_samples=500)["accuracy"]
+
+    ms_e2e = timed(run_e2e, 3, 1, sync)
+    rec, acc = m["out"]
+    pairs = 500.0 * 100 * 100
+    return {
+        "units": pairs, "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": None, "kernels": {}, "launches": m["launches"],
+        "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 500 * 11 * 100 * 4 + 500 * 4, "flops_per_unit": None, "scaling": "weak",
+        "check": {"recall_at_10": rec[:, 10, :].mean().item(), "triplet_acc": float(torch.as_tensor(acc).float().mean())},
+        "steps_used": steps,
+        "config": {"workload": "eval1467 (SURVEY 8f rows 1-2): resampled_recall_at_1_to_n(size=100, n_samples=500, N=10) + "
+                               "score_triplets(n_samples=500) on a 1467-clip gallery, public API; host-side: the reference's RNG draws "
+                               "(500 randperm, 500 duration-matched pairings)", "gallery": n, "dim": DIM,
+                   "l2": "latency / host bound: the whole gallery is 1.5 MB"}}
 
 
 def bench_train1024(args, device, sync):
@@ -546,7 +608,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail", "milnce64k"])
+    ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail", "milnce64k", "eval1467"])
     ap.add_argument("--gallery-n", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-extras", action="store_true")
@@ -585,7 +647,7 @@ def main():
         return t.item()
 
     single = {"train1024": bench_train1024, "retrieval16k": bench_retrieval16k, "triplets1m": bench_triplets1m,
-              "encoder_tail": bench_encoder_tail, "milnce64k": bench_milnce64k}
+              "encoder_tail": bench_encoder_tail, "milnce64k": bench_milnce64k, "eval1467": bench_eval1467}
     if args.workload == "gallery":
         line = line_from(bench_gallery(args, rank, world, device, sync, all_max), args, world, "gallery")
     else:

@@ -136,6 +136,17 @@ struct OutStage {
         if (lane == 0) tma_store_wait_all<0>();
         __syncwarp();
     }
+    // One 32-column chunk (16 packed fp16 pairs per thread) of this warp's share of a gradient-matrix tile: two
+    // chunks fill a 64-column slab, which is fenced and handed to a TMA store while the next slab is written.
+    // Measured and dropped (32768^2 block, 200 launches back to back, same board): staging both slabs of a 256-wide
+    // tile and synchronising once per tile 1.27 -> 1.33 ms (the drain wait then follows the stores immediately; it
+    // needs a second pair of slabs); draining the slab with LDS + whole-line STG instead of the proxy fence + TMA
+    // store 1.28 -> 1.44 ms.
+    __device__ __forceinline__ void stage(int lane, int ch, const uint32_t (&packed)[16], int32_t col_of_chunk, int32_t row) {
+        if ((ch & 1) == 0) begin_slab(lane);
+        write(lane, ch & 1, packed);
+        if (ch & 1) end_slab(lane, col_of_chunk - 32, row);
+    }
 };
 
 __device__ __forceinline__ float fma_sat(float a, float b, float c) {
@@ -375,6 +386,12 @@ struct HingeParams {
 // There is no per-element z = margin + s - d: fl32(s + c) >= 0  <=>  s >= -c exactly, and
 // sum relu(z) = sum g*s + sum_j (m - d_j) col_cnt[j] + sum_i (m - d_i) row_cnt[i] is completed from the
 // counts afterwards (pb2_hinge_loss_terms).  Column counts are summed over the warp's rows with REDUX.
+#ifndef PB2_HINGE_KO
+#define PB2_HINGE_KO 0  // knock-out timing builds (wrong results): 1 no column counts, 2 no loss sum, 4 no row counts
+#endif
+#ifndef PB2_HINGE_PIPES
+#define PB2_HINGE_PIPES 0  // measurement builds: bit 0 column indicator on the ALU pipe, bits 1 / 2 row / rank indicator on the FMA pipe
+#endif
 constexpr float kBig = 1.329227995784916e36f;  // 2^120
 template <bool kRank>
 struct HingePolicyT {
@@ -382,7 +399,7 @@ struct HingePolicyT {
     using Params = HingeParams;
     static constexpr int kColVecs = 2;  // rinv_y, -pred(thr_c) * 2^120 with thr_c = diag_col - margin
     static constexpr bool kStoresG = true;
-    float ri, thr_r, thr_k;
+    float ri, thr_r, thr_k, cr_r, cr_k;
     float2 loss2, rc2, rk2;
     int dcol;
     __device__ void kernel_begin(const Params&) { loss2 = make_float2(0.f, 0.f); }
@@ -392,7 +409,11 @@ struct HingePolicyT {
     }
     __device__ static void make_col(const Params& p, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
         v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+#if PB2_HINGE_PIPES & 1
+        v[1] = valid ? __uint_as_float(raw[1]) - p.margin : PB2_INF;
+#else
         v[1] = valid ? -(pred_f32(__uint_as_float(raw[1]) - p.margin) * kBig) : -PB2_INF;
+#endif
     }
     static constexpr int kRowVecs = 4;  // rinv_x, thr_r = diag_row - margin, pos_thr, diagonal column
     __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
@@ -414,6 +435,10 @@ struct HingePolicyT {
         ri = rv[0];
         thr_r = rv[128];
         thr_k = rv[256];
+#if PB2_HINGE_PIPES & 6
+        cr_r = -(pred_f32(thr_r) * kBig);
+        cr_k = -(pred_f32(thr_k) * kBig);
+#endif
         const int g = __float_as_int(rv[384]);
         const int64_t rel = (int64_t)g - t.col0;
         dcol = (g >= 0 && rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
@@ -438,7 +463,7 @@ struct HingePolicyT {
         // software pipelining: the three column-vector loads of group q+1 and the REDUX of group q are in
         // flight while group q's arithmetic issues (their latencies were the top stall reasons in ncu)
         float4 c4 = cv4[0], b4 = cb4[0];
-        uint32_t tot_prev = 0;
+        uint32_t tot[8], pk_prev = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             float4 nc4 = c4, nb4 = b4;
@@ -455,41 +480,75 @@ struct HingePolicyT {
                 if (4 * q + 3 == drel || 4 * q + 3 >= nvalid) s23.y = kMasked;
             }
             // FMA pipe: indicators as exact 0/1 floats
+#if PB2_HINGE_PIPES & 1
+            const float2 ic01 = make_float2(fset_ge(s01.x, b4.x), fset_ge(s01.y, b4.y));
+            const float2 ic23 = make_float2(fset_ge(s23.x, b4.z), fset_ge(s23.y, b4.w));
+#else
             const float2 ic01 = make_float2(fma_sat(s01.x, kBig, b4.x), fma_sat(s01.y, kBig, b4.y));
             const float2 ic23 = make_float2(fma_sat(s23.x, kBig, b4.z), fma_sat(s23.y, kBig, b4.w));
+#endif
+#if PB2_HINGE_PIPES & 2
+            const float2 ir01 = make_float2(fma_sat(s01.x, kBig, cr_r), fma_sat(s01.y, kBig, cr_r));
+            const float2 ir23 = make_float2(fma_sat(s23.x, kBig, cr_r), fma_sat(s23.y, kBig, cr_r));
+#else
             const float2 ir01 = make_float2(fset_ge(s01.x, thr_r), fset_ge(s01.y, thr_r));  // ALU pipe
             const float2 ir23 = make_float2(fset_ge(s23.x, thr_r), fset_ge(s23.y, thr_r));
+#endif
             const float2 g01 = __fadd2_rn(ic01, ir01), g23 = __fadd2_rn(ic23, ir23);
+#if !(PB2_HINGE_KO & 2)
             la = __ffma2_rn(g01, s01, la);
             lb = __ffma2_rn(g23, s23, lb);
+#endif
+#if !(PB2_HINGE_KO & 4)
             rca = __fadd2_rn(rca, ir01);
             rcb = __fadd2_rn(rcb, ir23);
+#endif
             if (kRank) {
+#if PB2_HINGE_PIPES & 4
+                rka = __fadd2_rn(rka, make_float2(fma_sat(s01.x, kBig, cr_k), fma_sat(s01.y, kBig, cr_k)));
+                rkb = __fadd2_rn(rkb, make_float2(fma_sat(s23.x, kBig, cr_k), fma_sat(s23.y, kBig, cr_k)));
+#else
                 rka = __fadd2_rn(rka, make_float2(fset_ge(s01.x, thr_k), fset_ge(s01.y, thr_k)));
                 rkb = __fadd2_rn(rkb, make_float2(fset_ge(s23.x, thr_k), fset_ge(s23.y, thr_k)));
+#endif
             }
             // column counts: the four 0/1 indicators packed into 6-bit fields of one exact fp32 integer
             // (ic0 + 64 ic1 + 4096 ic2 + 262144 ic3 < 2^19), converted once and summed over the warp's
             // 32 rows with REDUX (<= 32 per field); lanes 4q..4q+3 keep group q
+            // the conversion of group q is in flight while group q-1 is reduced (F2I and REDUX latencies overlap the
+            // next group's arithmetic); the totals are warp-uniform and picked per lane after the loop
+#if PB2_HINGE_KO & 1
+            if (q > 0) tot[q - 1] = 0;
+#else
             const uint32_t pkq = __float2uint_rz(fmaf(fmaf(ic23.y, 64.f, ic23.x), 4096.f, fmaf(ic01.y, 64.f, ic01.x)));
-            if (q > 0 && (lane >> 2) == q - 1) mine = tot_prev;  // consume the previous group's REDUX
-            tot_prev = __reduce_add_sync(0xffffffffu, pkq);
+            if (q > 0) tot[q - 1] = __reduce_add_sync(0xffffffffu, pk_prev);
+            pk_prev = pkq;
+#endif
             const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
             packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
             packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
             c4 = nc4;
             b4 = nb4;
         }
-        if ((lane >> 2) == 7) mine = tot_prev;
+#if PB2_HINGE_KO & 1
+        tot[7] = pk_prev;
+#else
+        tot[7] = __reduce_add_sync(0xffffffffu, pk_prev);
+#endif
+        {   // lane L keeps group L >> 2: a three-level select on the lane's bits 2..4 (7 SEL, no per-group predicates)
+            const bool b0 = lane & 4, b1 = lane & 8, b2 = lane & 16;
+            const uint32_t a0 = b0 ? tot[1] : tot[0], a1 = b0 ? tot[3] : tot[2];
+            const uint32_t a2 = b0 ? tot[5] : tot[4], a3 = b0 ? tot[7] : tot[6];
+            const uint32_t e0 = b1 ? a1 : a0, e1 = b1 ? a3 : a2;
+            mine = b2 ? e1 : e0;
+        }
         loss2 = __fadd2_rn(loss2, __fadd2_rn(la, lb));
         rc2 = __fadd2_rn(rc2, __fadd2_rn(rca, rcb));
         if (kRank) rk2 = __fadd2_rn(rk2, __fadd2_rn(rka, rkb));
         const int ccnt = (int)((mine >> ((lane & 3) * 6)) & 0x3fu);
         if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // 0 for out-of-range columns
         if (p.has_gmat) {
-            if ((ch & 1) == 0) os.begin_slab(lane);
-            os.write(lane, ch & 1, packed);
-            if (ch & 1) os.end_slab(lane, (int32_t)(t.col0 + cbase - 32), (int32_t)(t.row0 + t.quad * 32));
+            os.stage(lane, ch, packed, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
         }
     }
     __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
@@ -660,9 +719,7 @@ struct LseGradPolicy {
             packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
         }
         const int lane = lane_id();
-        if ((ch & 1) == 0) os.begin_slab(lane);
-        os.write(lane, ch & 1, packed);
-        if (ch & 1) os.end_slab(lane, (int32_t)(t.col0 + cbase - 32), (int32_t)(t.row0 + t.quad * 32));
+        os.stage(lane, ch, packed, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
     }
     __device__ void tile_end(const Params&, const SimCommon&, const TileCtx&) {}
     __device__ void kernel_end(const Params&, float*, int) {}
@@ -681,7 +738,12 @@ struct SimSmem {
     static constexpr int kColVecBytes = 2 * kMaxColVecs * kColVecStride * 4 + 2 * kMaxRowVecs * BM * 4;  // col + row vectors
     static constexpr int kBarBytes = 512;
     static constexpr int kBudget = 227 * 1024 - kOutBytes - kColVecBytes - kBarBytes;
-    static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+    static constexpr int kFit = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+#ifdef PB2_STAGE_CAP  // measurement builds: how much of the tile period is TMA bytes in flight?
+    static constexpr int kStages = kFit > PB2_STAGE_CAP ? PB2_STAGE_CAP : kFit;
+#else
+    static constexpr int kStages = kFit;
+#endif
     static constexpr int kTileBytes = kStages * kStageBytes;
     static constexpr int kTotal = kTileBytes + kOutBytes + kColVecBytes + kBarBytes;
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");

@@ -951,7 +951,11 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         static_assert(!Policy::kStoresG || kChunks % 2 == 0, "gradient-matrix slabs are 64 columns wide");
         // with >= 3 warps per scheduler the TMEM load latency is hidden by the other warps; with 2 the
         // next chunk's load is kept in flight in a second register buffer
+#ifdef PB2_NO_PINGPONG  // measurement builds: one TMEM register buffer (32 fewer live registers)
+        constexpr bool kPingPong = false;
+#else
         constexpr bool kPingPong = (G <= 2) && (kChunks > 1);
+#endif
         Policy pol;
         pol.kernel_begin(p);
         OutStage os;
@@ -1131,7 +1135,11 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
         if (bn == 192) return PB2_SIM(192, 3, 1);
         if (mcast) return PB2_SIM(256, 2, 3);
         if (pair) return PB2_SIM(256, 2, 2);
+#ifdef PB2_HINGE_G4  // measurement builds: four column groups (16 epilogue warps, 64 columns each) on 256-wide tiles
+        if (bn == 256) return PB2_SIM(256, 4, 1);
+#else
         if (bn == 256) return PB2_SIM(256, 2, 1);
+#endif
         return PB2_SIM(128, 2, 1);
     } else {
         if (mcast) return PB2_SIM(256, 2, 3);

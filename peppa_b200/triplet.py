@@ -58,23 +58,64 @@ def _duration_keys(duration):
     return [duration[i] for i in range(len(duration))]
 
 
+_FAST_SAMPLE2 = None
+
+
+def _sample2_is_two_randbelow():
+    """``random.sample(p, 2)`` on a pair is, in CPython, ``j = _randbelow(2); _randbelow(1)`` -> ``[p[j], p[1 - j]]``
+    with ``_randbelow(n)`` = rejection sampling on ``getrandbits(n.bit_length())``.  Checked once against the
+    interpreter that is running (results and generator state over 256 draws on private generators); if it ever
+    stops holding, the sampler below keeps calling ``random.sample`` itself."""
+    global _FAST_SAMPLE2
+    if _FAST_SAMPLE2 is None:
+        a, b = random.Random(20211), random.Random(20211)
+        ok = True
+        for i in range(256):
+            p = [2 * i, 2 * i + 1]
+            r = b.getrandbits(2)
+            while r >= 2:
+                r = b.getrandbits(2)
+            q = b.getrandbits(1)
+            while q:
+                q = b.getrandbits(1)
+            ok = ok and a.sample(p, 2) == [p[r], p[1 - r]]
+        _FAST_SAMPLE2 = bool(ok and a.getstate() == b.getstate())
+    return _FAST_SAMPLE2
+
+
 def _sampled_index_pairs(duration, n_samples):
     """``n_samples`` draws of ``zip(*_triplets(range(len(duration)), lambda idx: duration[idx]))`` as two int64
     tensors [n_samples, pairs].  Sorting and grouping by duration consume no randomness, so they are done once; the
-    per-group ``shuffled`` / ``random.sample`` calls run in the reference's order (pig/triplet.py:99-104), one sample
-    after the other, so seeded runs draw identical triplets."""
+    per-group ``shuffled`` / ``random.sample`` draws run in the reference's order (pig/triplet.py:99-104), one sample
+    after the other, on the global ``random`` generator, so seeded runs draw identical triplets and leave the
+    generator in the same state."""
     keys = _duration_keys(duration)
     groups = [list(items) for _, items in grouped(range(len(keys)), key=keys.__getitem__)]
     if n_samples > 0 and not any(len(items) > 1 for items in groups):
         pos_idx, neg_idx = zip(*[])      # no two clips share a duration: the reference's unpack raises ValueError
     pos, neg = [], []
-    sample = random.sample
-    for i in range(n_samples):
-        for items in groups:
-            for p in pairs(shuffled(items)):
-                target, distractor = sample(p, 2)
-                pos.append(target)
-                neg.append(distractor)
+    if _sample2_is_two_randbelow():
+        getrandbits = random.getrandbits
+        for i in range(n_samples):
+            for items in groups:
+                xs = shuffled(items)
+                for k in range(0, len(xs) - 1, 2):          # pairs(xs), random.sample(pair, 2) unrolled
+                    r = getrandbits(2)
+                    while r >= 2:
+                        r = getrandbits(2)
+                    q = getrandbits(1)
+                    while q:
+                        q = getrandbits(1)
+                    pos.append(xs[k + r])
+                    neg.append(xs[k + 1 - r])
+    else:
+        sample = random.sample
+        for i in range(n_samples):
+            for items in groups:
+                for p in pairs(shuffled(items)):
+                    target, distractor = sample(p, 2)
+                    pos.append(target)
+                    neg.append(distractor)
     per_sample = sum(len(items) // 2 for items in groups)
     return (torch.tensor(pos, dtype=torch.int64).view(n_samples, per_sample),
             torch.tensor(neg, dtype=torch.int64).view(n_samples, per_sample))

@@ -65,14 +65,18 @@ def test_sampler_matches_golden_without_device():
     # the batched sampler behind score_triplets / comparative_score_triplets (grouping hoisted out of the sample
     # loop, plain-number keys) draws the same triplets from the same seed
     random.seed(666)
-    pos, neg = triplet._sampled_index_pairs(dur, 5)
-    assert pos.dtype == torch.int64 and tuple(pos.shape) == tuple(g["draws"][:, 0].shape)
-    assert torch.equal(pos, g["draws"][:, 0].to(torch.int64)) and torch.equal(neg, g["draws"][:, 1].to(torch.int64))
-    state = random.getstate()
-    random.seed(666)
     for k in range(5):
         list(triplet._triplets(range(len(dur)), lambda i: dur[i]))
-    assert random.getstate() == state               # and leaves the generator where the reference's loop leaves it
+    state = random.getstate()
+    assert triplet._sample2_is_two_randbelow()      # CPython's sample(pair, 2) is the two rejection draws it unrolls
+    for fast in (True, False):                      # ... and the plain random.sample path it falls back to otherwise
+        triplet._FAST_SAMPLE2 = fast
+        random.seed(666)
+        pos, neg = triplet._sampled_index_pairs(dur, 5)
+        assert pos.dtype == torch.int64 and tuple(pos.shape) == tuple(g["draws"][:, 0].shape)
+        assert torch.equal(pos, g["draws"][:, 0].to(torch.int64)) and torch.equal(neg, g["draws"][:, 1].to(torch.int64))
+        assert random.getstate() == state           # leaves the generator where the reference's loop leaves it
+    triplet._FAST_SAMPLE2 = None
 
 
 def test_encoder_tail_module_is_state_dict_compatible_with_linear():

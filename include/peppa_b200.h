@@ -118,6 +118,20 @@ int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_x, const fl
 int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,
                   int accumulate, void* stream);
 
+/* pig/loss.py:13-26 MILNCELoss, both directions of the log-sum-exp from ONE pass over the logits
+ * (x = V A^T is both `x` and `x.permute(1,0,2)` of pig/loss.py:23): for logits with a known bound,
+ * |scale * <x_i, y_j>| <= bound and bound * log2(e) <= 60, accumulate e_ij = 2^(logit_ij * log2(e) - M),
+ * M = bound * log2(e), into row sums (row_part_sum: [pb2_sim_lse_parts(cols), rows]) and column sums
+ * (col_part_sum: [pb2_sim_lse_col_parts(rows), cols], one partial per 32 rows, fixed order, no atomics).
+ * pb2_lse_merge_const folds partials [n_parts, n] into lse[n] = (M + log2 sum_k part[k, i]) * ln 2
+ * (log-added into lse when accumulate != 0).  Unbounded logits: pb2_sim_lse_rows twice. */
+int pb2_sim_lse_col_parts(int64_t rows);
+int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                     int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float bound,
+                     float* row_part_sum, float* col_part_sum, void* stream);
+int pb2_lse_merge_const(const float* part_sum, int n_parts, int64_t n, float bound, float* lse, int accumulate,
+                        void* stream);
+
 /* out[i] = log sum_k exp(parts[k * n + i]) (natural log): the cross-rank merge of column log-sum-exp
  * partials of a row-sharded gallery (each rank holds the LSE over its own rows). */
 int pb2_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream);

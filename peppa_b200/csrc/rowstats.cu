@@ -124,6 +124,31 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
     lse[r] = v;
 }
 
+// partial sums of 2^(t - M) with one shift M for every partial (pb2_sim_lse_both): lse = (M + log2 sum) ln 2
+__global__ void __launch_bounds__(256) lse_merge_const_kernel(const float* __restrict__ psum, int n_parts, int64_t n,
+                                                              float shift, float* __restrict__ lse, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // four independent chains in a fixed order (the partial count is a multiple of 4 for the column layout)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= n_parts; k += 4) {
+        s0 += psum[(int64_t)k * n + i];
+        s1 += psum[(int64_t)(k + 1) * n + i];
+        s2 += psum[(int64_t)(k + 2) * n + i];
+        s3 += psum[(int64_t)(k + 3) * n + i];
+    }
+    for (; k < n_parts; ++k) s0 += psum[(int64_t)k * n + i];
+    const float s = (s0 + s1) + (s2 + s3);
+    float v = (s > 0.f) ? (shift + log2f(s)) * kLn2 : (s == 0.f ? kNegInf : s);  // NaN / inf propagate
+    if (accumulate) {
+        const float o = lse[i];
+        const float hi = fmaxf(o, v), lo = fminf(o, v);
+        v = (v != v) ? v : ((hi > kNegInf) ? hi + log1pf(expf(lo - hi)) : kNegInf);
+    }
+    lse[i] = v;
+}
+
 // out[i] = log sum_k exp(parts[k, i]) (natural log): merges per-rank column log-sum-exp partials
 __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ parts, int n_parts, int64_t n,
                                                           float* __restrict__ out) {
@@ -617,6 +642,15 @@ extern "C" int pb2_lse_merge(const float* part_max, const float* part_sum, int n
     lse_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_max, part_sum, n_parts,
                                                                                       rows, lse, accumulate);
     return check_launch("lse_merge");
+}
+
+extern "C" int pb2_lse_merge_const(const float* part_sum, int n_parts, int64_t n, float bound, float* lse,
+                                   int accumulate, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!part_sum || !lse || n_parts <= 0) return set_error(PB2_ERR_ARG, "lse_merge_const: bad arguments");
+    lse_merge_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        part_sum, n_parts, n, bound * 1.4426950408889634f, lse, accumulate);
+    return check_launch("lse_merge_const");
 }
 
 extern "C" int pb2_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream) {

@@ -666,6 +666,118 @@ struct LseRowPolicy {
     __device__ void kernel_end(const Params&, float*, int) {}
 };
 
+// Row AND column log-sum-exp statistics from ONE pass over S (north-star kernel (a)), for logits with a known bound:
+// with |scale * <x_i, y_j>| <= bound, e_ij = 2^(t_ij - M) (t = logit * log2 e, M = bound * log2 e) never overflows and
+// keeps full relative precision while 2 M stays far below the fp32 exponent range (the host refuses M > 60), so the
+// row sums and the column sums are plain sums of the SAME exponentials: one ex2 per element instead of two passes with
+// running maxima.  A thread owns a row, so its row sum is a register; the column sums of a 32 x 32 chunk go through
+// the warp's staging slab (one swizzled 128-byte row per thread, read back eight rows x four columns per thread,
+// two shuffles) and leave as one fp32 per (32-row group, column): fixed order, no atomics, bit-reproducible.
+// Partials: row sums in the layout of pb2_sim_lse_parts (per 128 columns), column sums [4 * row blocks, cols];
+// both are merged by pb2_lse_merge_const.
+struct LseBothPolicy {
+    static constexpr bool kStoresF32 = false;
+    static constexpr bool kStoresG = false;
+    static constexpr bool kUsesStage = true;
+    struct Params {
+        float* row_part_sum;  // [pb2_sim_lse_parts(cols), rows]
+        float* col_part_sum;  // [pb2_sim_lse_col_parts(rows), cols]
+        float shift;          // M: log2-domain upper bound of the logits
+    };
+    static constexpr int kColVecs = 1;
+    float ri, s;
+    __device__ void kernel_begin(const Params&) {}
+    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+    }
+    __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
+        v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+    }
+    static constexpr int kRowVecs = 1;
+    __device__ static void fetch_row(const Params&, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+        raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+    }
+    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+        v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale * 1.4426950408889634f;  // log2 domain
+    }
+    __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) {
+        ri = rv[0];
+        s = 0.f;
+    }
+    __device__ void chunk(const Params& p, const SimCommon& c, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
+                          const float* cv, OutStage& os) {
+        const int nvalid = t.cols_valid - cbase;
+        if (nvalid <= 0) return;  // warp-uniform
+        const float4* cv4 = reinterpret_cast<const float4*>(cv);
+        const float2 ri2 = make_float2(ri, ri);
+        const float2 neg = make_float2(-p.shift, -p.shift);
+        float e[32];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 c4 = cv4[q];
+            const float2 d0 = __fadd2_rn(score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y), neg);
+            const float2 d1 = __fadd2_rn(score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w), neg);
+            e[4 * q + 0] = ex2_approx(d0.x);
+            e[4 * q + 1] = ex2_approx(d0.y);
+            e[4 * q + 2] = ex2_approx(d1.x);
+            e[4 * q + 3] = ex2_approx(d1.y);
+            if (nvalid < 32 || !t.row_valid) {  // ragged last column tile / rows past the end add nothing
+                if (4 * q + 0 >= nvalid || !t.row_valid) e[4 * q + 0] = 0.f;
+                if (4 * q + 1 >= nvalid || !t.row_valid) e[4 * q + 1] = 0.f;
+                if (4 * q + 2 >= nvalid || !t.row_valid) e[4 * q + 2] = 0.f;
+                if (4 * q + 3 >= nvalid || !t.row_valid) e[4 * q + 3] = 0.f;
+            }
+            a0 += e[4 * q + 0];
+            a1 += e[4 * q + 1];
+            a2 += e[4 * q + 2];
+            a3 += e[4 * q + 3];
+        }
+        s += (a0 + a1) + (a2 + a3);
+        // column sums over this warp's 32 rows: transpose through the slab
+        const int lane = lane_id();
+        os.write_f32(lane, e);
+        __syncwarp();
+        const uint8_t* sl = os.buf + (os.slab & os.mask) * kOutSlabBytes;
+        const int c16 = lane & 7, rg = lane >> 3;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // rows rg*8 + k (row % 8 == k), columns 4*c16 .. 4*c16+3
+            const float4 w = *reinterpret_cast<const float4*>(sl + (rg * 8 + k) * 128 + ((c16 ^ k) * 16));
+            acc.x += w.x;
+            acc.y += w.y;
+            acc.z += w.z;
+            acc.w += w.w;
+        }
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+        }
+        const float mine = rg == 0 ? acc.x : (rg == 1 ? acc.y : (rg == 2 ? acc.z : acc.w));
+        const int col = c16 * 4 + rg;  // the 32 lanes cover the chunk's 32 columns once
+        if (col < nvalid) {
+            const int64_t part = (t.row0 >> 7) * 4 + t.quad;
+            p.col_part_sum[part * c.cols + t.col0 + cbase + col] = mine;
+        }
+        ++os.slab;  // the next chunk stages into the other slab while stragglers still read this one
+    }
+    __device__ void tile_end(const Params& p, const SimCommon& c, const TileCtx& t) {
+        if (!t.row_valid) return;
+        // row-sum partials: two slots per 128 columns like LseRowPolicy (pb2_sim_lse_parts)
+        if (t.warp_cols == 64) {
+            p.row_part_sum[((int64_t)t.cb * 2 + t.half) * c.rows + t.row] = s;
+        } else if (((int64_t)t.cb * 2 + t.half) * 128 < c.cols) {
+            const int64_t slot = ((int64_t)t.cb * 4 + t.half * 2) * c.rows + t.row;
+            p.row_part_sum[slot] = s;
+            p.row_part_sum[slot + c.rows] = 0.f;
+        }
+    }
+    __device__ void kernel_end(const Params&, float*, int) {}
+};
+
 struct LseGradPolicy {
     static constexpr bool kStoresF32 = false;
     struct Params {
@@ -729,6 +841,12 @@ struct LseGradPolicy {
 // kCtas: 1 = independent CTAs; 2 = CTA pairs sharing one MMA (cta_group::2); 3 = clusters of 2 whose CTAs take
 // the tiles (rb, cb) and (rb + 1, cb), run independent MMAs and share the Y tile: each loads half of it and
 // multicasts that half to both (a third fewer L2 lookups, no coupling through the accumulators).
+// does the policy need the per-warp staging slabs (gradient-matrix / fp32 output tiles, or the column-sum transpose)?
+template <class P, class = void>
+struct uses_stage : std::integral_constant<bool, P::kStoresG || P::kStoresF32> {};
+template <class P>
+struct uses_stage<P, typename std::enable_if<P::kUsesStage>::type> : std::true_type {};
+
 template <int BN, int G, bool kOut, int kCtas>
 struct SimSmem {
     static constexpr int kStageBytes = (BM + (kCtas == 2 ? BN / 2 : BN)) * BK * 2;  // a pair CTA stages half of Y
@@ -757,7 +875,7 @@ template <class Policy, int BN, int G, int kCtas>
 __global__ void __launch_bounds__(sim_threads(G), 1)
     sim_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                const __grid_constant__ CUtensorMap tm_out, const SimCommon c, const typename Policy::Params p) {
-    using L = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32, kCtas>;
+    using L = SimSmem<BN, G, uses_stage<Policy>::value, kCtas>;
     constexpr int kEpiWarps = 4 * G;
     constexpr int kEpiThreads = kEpiWarps * 32;
     constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);  // power of two >= 2 * BN
@@ -1091,7 +1209,7 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_y = rinv_y;
     c.scale = scale;
     auto kern = sim_kernel<Policy, BN, G, kCtas>;
-    constexpr int smem = SimSmem<BN, G, Policy::kStoresG || Policy::kStoresF32, kCtas>::kTotal;
+    constexpr int smem = SimSmem<BN, G, uses_stage<Policy>::value, kCtas>::kTotal;
     static bool configured = false;  // per instantiation
     if (!configured) {
         rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
@@ -1232,6 +1350,21 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
                                                 "sim_hinge+rank", g_force_bn, om);
     return dispatch_sim<HingePolicyT<false>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
                                              "sim_hinge", g_force_bn, om);
+}
+
+extern "C" int pb2_sim_lse_col_parts(int64_t rows) { return (int)((rows + BM - 1) / BM) * 4; }
+
+extern "C" int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                                int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float bound,
+                                float* row_part_sum, float* col_part_sum, void* stream) {
+    if (rows > 0 && cols > 0 && (!row_part_sum || !col_part_sum)) return set_error(PB2_ERR_ARG, "sim_lse_both: null");
+    const float shift = bound * 1.4426950408889634f;
+    if (!(bound >= 0.f) || !(shift <= 60.f))
+        return set_error(PB2_ERR_ARG, "sim_lse_both: needs 0 <= bound and bound * log2(e) <= 60 (use the two-pass path)");
+    LseBothPolicy::Params pp{row_part_sum, col_part_sum, shift};
+    const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
+    return dispatch_sim<LseBothPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+                                       "sim_lse_both", bn);
 }
 
 // LSE partial layout is fixed to the 128-column tile so the caller can size buffers up front.

@@ -44,10 +44,13 @@ class GalleryStep:
 
     def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
                  group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None,
-                 loss: str = "hinge", temperature: float = 1.0):
+                 loss: str = "hinge", temperature: float = 1.0, logit_bound=None):
         if loss not in ("hinge", "milnce"):
             raise ValueError("loss must be 'hinge' or 'milnce'")
         self.loss, self.inv_tau = loss, 1.0 / float(temperature)
+        # MIL-NCE: a known bound on |logit| (e.g. 1 / temperature for unit-norm embeddings) skips the per-step device
+        # round trip that otherwise derives it from the row norms; float("inf") forces the two-pass log-sum-exp
+        self.logit_bound = None if logit_bound is None else float(logit_bound)
         # ``backend`` exists for the world_size-2 gloo tests of the orchestration on CPU boxes: they
         # inject an emulation of the kernel entry points built from the oracle.  The product never
         # passes it; the default is the CUDA ops module and there is no automatic selection.
@@ -180,10 +183,20 @@ class GalleryStep:
             v_full = v_loc
         rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
         lse_row = lse_col = None
-        for (c0, c1) in cblocks:      # x = A_loc V^T / tau: rows complete locally
-            lse_row = ops.sim_lse_rows(a_loc, v_full[c0:c1], scale=inv_tau, lse=lse_row)
-        for (r0, r1) in rblocks:      # columns: log-sum-exp over THIS rank's rows only
-            lse_col = ops.sim_lse_rows(v_full, a_loc[r0:r1], scale=inv_tau, lse=lse_col)
+        bound = self.logit_bound if self.logit_bound is not None else ops.logit_bound(a_loc, v_full, inv_tau)
+        if bound <= ops.LSE_BOTH_MAX_BOUND:
+            # bounded logits: rows (complete locally) and columns (over THIS rank's rows) from one pass per block
+            lse_row = torch.full((nl,), float("-inf"), dtype=torch.float32, device=dev)
+            lse_col = torch.full((n,), float("-inf"), dtype=torch.float32, device=dev)
+            for (r0, r1) in rblocks:
+                for (c0, c1) in cblocks:
+                    ops.sim_lse_both(a_loc[r0:r1], v_full[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1],
+                                     lse_col=lse_col[c0:c1])
+        else:
+            for (c0, c1) in cblocks:      # x = A_loc V^T / tau: rows complete locally
+                lse_row = ops.sim_lse_rows(a_loc, v_full[c0:c1], scale=inv_tau, lse=lse_row)
+            for (r0, r1) in rblocks:      # columns: log-sum-exp over THIS rank's rows only
+                lse_col = ops.sim_lse_rows(v_full, a_loc[r0:r1], scale=inv_tau, lse=lse_col)
         if self.world > 1:
             parts = torch.empty(self.world, n, dtype=torch.float32, device=dev)
             self._all_gather(parts.view(-1), lse_col)

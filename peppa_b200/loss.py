@@ -17,6 +17,8 @@ from .util import cosine_matrix  # noqa: F401  (pig/loss.py re-exports its own c
 # Largest gradient-matrix block kept in HBM at once (rows x cols fp16).  Bigger problems are
 # walked block by block with accumulating gradient GEMMs.
 _MAX_BLOCK = 32768
+# MIL-NCE problems from this many logits on take the one-pass row + column log-sum-exp (pb2_sim_lse_both)
+_LSE_BOTH_MIN_PAIRS = 1 << 26
 
 
 def _blocks(n, step):
@@ -123,10 +125,20 @@ class _MilNceFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         vblocks, ablocks = _blocks(n, _MAX_BLOCK), _blocks(nk, _MAX_BLOCK)
         lse_row = lse_col = None
-        for (c0, c1) in ablocks:   # rows = videos, columns = audio candidates
-            lse_row = ops.sim_lse_rows(vb, ab[c0:c1], scale=inv_tau, lse=lse_row)
-        for (c0, c1) in vblocks:   # LSE over videos for every audio candidate = row LSE of A V^T
-            lse_col = ops.sim_lse_rows(ab, vb[c0:c1], scale=inv_tau, lse=lse_col)
+        # large problems: both directions of the log-sum-exp from ONE pass over the logits when they are bounded
+        # (one device round trip for the bound; below _LSE_BOTH_MIN_PAIRS the two passes cost less than that)
+        bound = ops.logit_bound(vb, ab, inv_tau) if n * nk >= _LSE_BOTH_MIN_PAIRS else None
+        if bound is not None and bound <= ops.LSE_BOTH_MAX_BOUND:
+            lse_row = torch.full((n,), float("-inf"), dtype=torch.float32, device=dev)
+            lse_col = torch.full((nk,), float("-inf"), dtype=torch.float32, device=dev)
+            for (r0, r1) in vblocks:
+                for (c0, c1) in ablocks:
+                    ops.sim_lse_both(vb[r0:r1], ab[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1], lse_col=lse_col[c0:c1])
+        else:
+            for (c0, c1) in ablocks:   # rows = videos, columns = audio candidates
+                lse_row = ops.sim_lse_rows(vb, ab[c0:c1], scale=inv_tau, lse=lse_row)
+            for (c0, c1) in vblocks:   # LSE over videos for every audio candidate = row LSE of A V^T
+                lse_col = ops.sim_lse_rows(ab, vb[c0:c1], scale=inv_tau, lse=lse_col)
         if k == 1:
             diag = ops.pair_dot(vb, ab)
             if inv_tau != 1.0:

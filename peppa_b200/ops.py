@@ -179,6 +179,42 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
     return lse
 
 
+LSE_BOTH_MAX_BOUND = 60.0 / 1.4426950408889634     # pb2_sim_lse_both refuses bound * log2(e) > 60
+
+
+def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None):
+    """Row AND column log-sum-exp of s = scale * <x_i, y_j> from one pass, for |s| <= ``bound``.
+
+    Returns (lse_row [rows], lse_col [cols]); tensors passed in are log-added into (blocks of a larger matrix:
+    ``lse_row[r0:r1]`` over the column blocks, ``lse_col[c0:c1]`` over the row blocks)."""
+    r, c = x.shape[0], y.shape[0]
+    lib = _cabi.lib()
+    prow = torch.empty(int(lib.pb2_sim_lse_parts(c)), r, dtype=torch.float32, device=x.device)
+    pcol = torch.empty(int(lib.pb2_sim_lse_col_parts(r)), c, dtype=torch.float32, device=x.device)
+    acc_row, acc_col = lse_row is not None, lse_col is not None
+    if lse_row is None:
+        lse_row = torch.empty(r, dtype=torch.float32, device=x.device)
+    if lse_col is None:
+        lse_col = torch.empty(c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _timed("sim_lse_both", 2.0 * r * c * x.shape[1], x.device):
+        st = _stream(x.device)
+        check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0), y.stride(0),
+                                   float(scale), float(bound), _ptr(prow), _ptr(pcol), st), "sim_lse_both")
+        check(lib.pb2_lse_merge_const(_ptr(prow), prow.shape[0], r, float(bound), _ptr(lse_row), int(acc_row), st),
+              "lse_merge_const")
+        check(lib.pb2_lse_merge_const(_ptr(pcol), pcol.shape[0], c, float(bound), _ptr(lse_col), int(acc_col), st),
+              "lse_merge_const")
+    return lse_row, lse_col
+
+
+def logit_bound(x_bf16, y_bf16, scale=1.0):
+    """max_i ||x_i|| * max_j ||y_j|| * |scale| (Cauchy-Schwarz, with a 1e-4 margin for the fp32 accumulation), as a
+    Python float: ONE device round trip.  NaN / inf norms give NaN / inf, which no caller accepts as a bound."""
+    _, nx = row_norms(x_bf16)
+    _, ny = row_norms(y_bf16)
+    return float(nx.max() * ny.max()) * abs(float(scale)) * 1.0001
+
+
 def lse_combine(parts):
     """parts [P, n] fp32 natural-log partial LSEs -> [n] log-sum-exp over P."""
     p_, n = parts.shape

@@ -91,6 +91,31 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
     return s if lse is None else torch.logaddexp(lse, s)
 
 
+LSE_BOTH_MAX_BOUND = 60.0 / 1.4426950408889634
+
+
+def logit_bound(x, y, scale=1.0):
+    return float(torch.linalg.vector_norm(x.float(), dim=1).max() * torch.linalg.vector_norm(y.float(), dim=1).max()) \
+        * abs(float(scale)) * 1.0001
+
+
+def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None):
+    s = (x.float() @ y.float().T) * scale
+    assert float(s.abs().max()) <= bound
+    e = torch.exp2(s * 1.4426950408889634 - bound * 1.4426950408889634)      # the kernel's fixed-shift sums
+    row = (bound * 1.4426950408889634 + torch.log2(e.sum(dim=1))) * 0.6931471805599453
+    col = (bound * 1.4426950408889634 + torch.log2(e.sum(dim=0))) * 0.6931471805599453
+    if lse_row is None:
+        lse_row = row
+    else:
+        lse_row.copy_(torch.logaddexp(lse_row, row))
+    if lse_col is None:
+        lse_col = col
+    else:
+        lse_col.copy_(torch.logaddexp(lse_col, col))
+    return lse_row, lse_col
+
+
 def lse_combine(parts):
     return torch.logsumexp(parts, dim=0)
 

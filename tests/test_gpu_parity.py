@@ -422,6 +422,69 @@ def test_gallery_step_milnce_single_gpu(pb, n, block):
     assert rel_err(out["loss"].cpu(), O.milnce_loss(V, A)) < TOL     # the loss itself is symmetric
 
 
+@pytest.mark.parametrize("r,c,d,scale", [(1000, 1500, 512, 1.0), (300, 70, 64, 14.0), (4096, 4100, 256, 5.0), (129, 33, 512, 1.0 / 0.07)])
+def test_sim_lse_both_against_fp64(pb, r, c, d, scale):
+    """One pass over the logits gives both directions of the log-sum-exp (pig/loss.py:23-25: x and x.permute(1,0,2)):
+    against fp64, against the two-pass kernels, block-wise accumulation, bit-reproducible, bound refusal."""
+    from peppa_b200 import ops
+    g = torch.Generator().manual_seed(r * 7 + c)
+    X = torch.nn.functional.normalize(torch.randn(r, d, generator=g), dim=1).bfloat16()
+    Y = torch.nn.functional.normalize(0.5 * X[torch.arange(c) % r].float() + torch.randn(c, d, generator=g), dim=1).bfloat16()
+    xb, yb = X.cuda(), Y.cuda()
+    bound = ops.logit_bound(xb, yb, scale)
+    assert scale * 0.99 < bound < scale * 1.02                       # unit-norm rows up to bf16 rounding
+    lr, lc = ops.sim_lse_both(xb, yb, bound, scale=scale)
+    S = (X.double() @ Y.double().T) * scale
+    assert (lr.cpu().double() - torch.logsumexp(S, 1)).abs().max() < 1e-4
+    assert (lc.cpu().double() - torch.logsumexp(S, 0)).abs().max() < 1e-4
+    assert (lr - ops.sim_lse_rows(xb, yb, scale=scale)).abs().max() < 1e-4
+    assert (lc - ops.sim_lse_rows(yb, xb, scale=scale)).abs().max() < 1e-4
+    lr2, lc2 = ops.sim_lse_both(xb, yb, bound, scale=scale)
+    assert torch.equal(lr, lr2) and torch.equal(lc, lc2)             # fixed summation order, no atomics
+    ar = torch.full((r,), float("-inf"), device="cuda")
+    ac = torch.full((c,), float("-inf"), device="cuda")
+    rh, chf = r // 2 + 3, c // 3 + 1
+    for (r0, r1) in ((0, rh), (rh, r)):
+        for (c0, c1) in ((0, chf), (chf, c)):
+            ops.sim_lse_both(xb[r0:r1], yb[c0:c1], bound, scale=scale, lse_row=ar[r0:r1], lse_col=ac[c0:c1])
+    assert (ar - lr).abs().max() < 1e-5 and (ac - lc).abs().max() < 1e-5
+    with pytest.raises(RuntimeError):
+        ops.sim_lse_both(xb, yb, 100.0, scale=scale)                 # 2^(-2 * 144) would underflow: refused
+
+
+def test_milnce_one_pass_statistics_path(pb):
+    """MILNCELoss takes the one-pass row + column statistics from 2^26 logits on when the logits are bounded;
+    force it at a small size (ragged blocks), and check that unbounded logits keep the two-pass kernels."""
+    old = pb.loss._MAX_BLOCK, pb.loss._LSE_BOTH_MIN_PAIRS
+    pb.loss._MAX_BLOCK, pb.loss._LSE_BOTH_MIN_PAIRS = 512, 0
+    try:
+        V, A = emb(1200, 4.0)
+        for tau in (1.0, 0.07):
+            loss, dV, dA = _grads(pb.loss.MILNCELoss(temperature=tau), V, A)
+            v = V.double().requires_grad_(True)
+            a = A.double().requires_grad_(True)
+            x = (v @ a.T) / tau
+            ref = (torch.logaddexp(torch.logsumexp(x, 1), torch.logsumexp(x, 0)) - torch.diagonal(x)).mean()
+            ref.backward()
+            assert rel_err(loss, ref.detach()) < TOL and rel_err(dV, v.grad) < TOL and rel_err(dA, a.grad) < TOL
+        from peppa_b200 import ops
+        calls = []
+        orig = ops.sim_lse_both
+        ops.sim_lse_both = lambda *a_, **k: calls.append(1) or orig(*a_, **k)
+        try:
+            Vs, As = (V * 8.0).bfloat16().float(), (A * 8.0).bfloat16().float()      # |logit| up to 64 > 41.6
+            loss, dV, dA = _grads(pb.loss.MILNCELoss(), Vs, As)
+            assert not calls
+            rl, rdv, rda = O.milnce_loss_and_grads(Vs, As)
+            assert rel_err(loss, rl) < TOL and rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL
+            _grads(pb.loss.MILNCELoss(), V, A)
+            assert calls
+        finally:
+            ops.sim_lse_both = orig
+    finally:
+        pb.loss._MAX_BLOCK, pb.loss._LSE_BOTH_MIN_PAIRS = old
+
+
 def test_blocked_loss_paths(pb):
     """Batches larger than one gradient-matrix block walk blocks with accumulating gradient GEMMs; exercise
     that code with a tiny block edge."""

@@ -1,6 +1,6 @@
 """A/B timing of the fused similarity passes between two builds of the library.
 
-    python tools/ab_hinge.py [path/to/other_lib.so] [what ...]     what in {hinge, rank, hinge_nog}; default hinge
+    python tools/ab_hinge.py [path/to/other_lib.so] [what ...]     what in {hinge, rank, hinge_nog, lse}; default hinge
 
 Loads the given library instead of the in-tree one (measurement only: the product always loads
 peppa_b200/csrc/libpeppa_b200.so), runs the pass on a 32768 x 32768 block 200 times back to back and prints the
@@ -46,6 +46,13 @@ def main():
         for rep in range(2):
             ms = _t(lambda: ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, None, 0, pos_thr=thr, rank=rk), iters=200, warm=20)
             print(f"{name} hinge+rank, no G 32768^2: {ms:.4f} ms  {flops / ms / 1e9:.1f} TF/s", flush=True)
+    if "lse" in what:
+        bound = ops.logit_bound(A, V, 1.0 / 0.07)
+        for rep in range(2):
+            ms = _t(lambda: ops.sim_lse_both(A, V, bound, scale=1.0 / 0.07), iters=100, warm=10)
+            print(f"{name} lse_both 32768^2: {ms:.4f} ms  {flops / ms / 1e9:.1f} TF/s", flush=True)
+            ms = _t(lambda: ops.sim_lse_rows(A, V, scale=1.0 / 0.07), iters=100, warm=10)
+            print(f"{name} lse_rows (one direction) 32768^2: {ms:.4f} ms  {flops / ms / 1e9:.1f} TF/s", flush=True)
     if "rank" in what:
         for rep in range(2):
             ms = _t(lambda: ops.sim_rank(A, V, ra, rv, thr, idx), iters=200, warm=20)

@@ -708,11 +708,19 @@ struct LseBothPolicy {
                           const float* cv, OutStage& os) {
         const int nvalid = t.cols_valid - cbase;
         if (nvalid <= 0) return;  // warp-uniform
+        // kSlow: ragged last column tile, or rows past the end in this warp (those elements add nothing)
+        if (__any_sync(0xffffffffu, nvalid < 32 || !t.row_valid)) chunk_impl<true>(p, c, t, cbase, v, cv, os);
+        else chunk_impl<false>(p, c, t, cbase, v, cv, os);
+    }
+    template <bool kSlow>
+    __device__ __forceinline__ void chunk_impl(const Params& p, const SimCommon& c, const TileCtx& t, int cbase,
+                                               const uint32_t (&v)[32], const float* cv, OutStage& os) {
+        const int nvalid = t.cols_valid - cbase;
         const float4* cv4 = reinterpret_cast<const float4*>(cv);
         const float2 ri2 = make_float2(ri, ri);
         const float2 neg = make_float2(-p.shift, -p.shift);
         float e[32];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float4 c4 = cv4[q];
@@ -722,33 +730,30 @@ struct LseBothPolicy {
             e[4 * q + 1] = ex2_approx(d0.y);
             e[4 * q + 2] = ex2_approx(d1.x);
             e[4 * q + 3] = ex2_approx(d1.y);
-            if (nvalid < 32 || !t.row_valid) {  // ragged last column tile / rows past the end add nothing
+            if (kSlow) {
                 if (4 * q + 0 >= nvalid || !t.row_valid) e[4 * q + 0] = 0.f;
                 if (4 * q + 1 >= nvalid || !t.row_valid) e[4 * q + 1] = 0.f;
                 if (4 * q + 2 >= nvalid || !t.row_valid) e[4 * q + 2] = 0.f;
                 if (4 * q + 3 >= nvalid || !t.row_valid) e[4 * q + 3] = 0.f;
             }
-            a0 += e[4 * q + 0];
-            a1 += e[4 * q + 1];
-            a2 += e[4 * q + 2];
-            a3 += e[4 * q + 3];
+            a01 = __fadd2_rn(a01, make_float2(e[4 * q + 0], e[4 * q + 1]));
+            a23 = __fadd2_rn(a23, make_float2(e[4 * q + 2], e[4 * q + 3]));
         }
-        s += (a0 + a1) + (a2 + a3);
+        s += (a01.x + a01.y) + (a23.x + a23.y);
         // column sums over this warp's 32 rows: transpose through the slab
         const int lane = lane_id();
         os.write_f32(lane, e);
         __syncwarp();
         const uint8_t* sl = os.buf + (os.slab & os.mask) * kOutSlabBytes;
         const int c16 = lane & 7, rg = lane >> 3;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 axy = make_float2(0.f, 0.f), azw = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // rows rg*8 + k (row % 8 == k), columns 4*c16 .. 4*c16+3
             const float4 w = *reinterpret_cast<const float4*>(sl + (rg * 8 + k) * 128 + ((c16 ^ k) * 16));
-            acc.x += w.x;
-            acc.y += w.y;
-            acc.z += w.z;
-            acc.w += w.w;
+            axy = __fadd2_rn(axy, make_float2(w.x, w.y));
+            azw = __fadd2_rn(azw, make_float2(w.z, w.w));
         }
+        float4 acc = make_float4(axy.x, axy.y, azw.x, azw.y);
 #pragma unroll
         for (int off = 8; off <= 16; off <<= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
@@ -758,7 +763,7 @@ struct LseBothPolicy {
         }
         const float mine = rg == 0 ? acc.x : (rg == 1 ? acc.y : (rg == 2 ? acc.z : acc.w));
         const int col = c16 * 4 + rg;  // the 32 lanes cover the chunk's 32 columns once
-        if (col < nvalid) {
+        if (!kSlow || col < nvalid) {
             const int64_t part = (t.row0 >> 7) * 4 + t.quad;
             p.col_part_sum[part * c.cols + t.col0 + cbase + col] = mine;
         }

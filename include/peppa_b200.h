@@ -173,6 +173,12 @@ int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_
 int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, int dim, int64_t ld, void* out, int64_t ld_out,
                        void* stream);
 
+/* y0 = x0 * coef[0], y1 = x1 * coef[0] (coef on the device; dtype PB2_BF16 / PB2_F16 / PB2_F32; n_elems per
+ * array, whole 16-byte vectors): the backward of pig/loss.py's scalar losses, whose gradients are produced in the
+ * forward -- autograd's grad_output arrives as a device scalar, and both gradients are scaled in one launch. */
+int pb2_scale_pair(const void* x0, const void* x1, int64_t n_elems, int dtype, const float* coef, void* y0, void* y1,
+                   void* stream);
+
 /* Hinge finish (SURVEY 8a'): g_i = p_i + gdiag_i * rinv_y[i] * y_i,  gdiag_i = -(row_cnt[i] + col_cnt[i]),
  * p = G * Yhat from pb2_grad_gemm; grad_x[i] = coef * rinv_x[i] * (g_i - xhat_i <g_i, xhat_i>),
  * xhat = x * rinv_x (the Jacobian of the row normalisation in pig/util.py:11-12).

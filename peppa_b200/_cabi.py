@@ -53,6 +53,7 @@ SIGNATURES = {
     "pb2_hinge_step_workspace": [_i64, _i],
     "pb2_hinge_step": [_p, _p, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],
     "pb2_rows_scale_f16": [_p, _p, _i64, _i, _i64, _p, _i64, _p],
+    "pb2_scale_pair": [_p, _p, _i64, _i, _p, _p, _p, _p],
     "pb2_milnce_finish": [_p, _i64, _p, _i64, _i, _i64, _f, _p, _p, _i64, _p],
     "pb2_milnce_finish_k": [_p, _i64, _p, _p, _i64, _i, _i, _i, _i64, _f, _p, _p, _i64, _p],
     "pb2_project_normalize": [_p, _p, _p, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p],

@@ -71,6 +71,26 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// y0 = x0 * c, y1 = x1 * c with c read on the device: the backward of a scalar loss whose gradients were produced in
+// the forward (autograd hands grad_output over as a device scalar).  One launch for both gradients, 16-byte vectors.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    scale_pair_kernel(const T* __restrict__ x0, const T* __restrict__ x1, int64_t n_vec, const float* __restrict__ coef,
+                      T* __restrict__ y0, T* __restrict__ y1) {
+    constexpr int kPer = 16 / sizeof(T);
+    const float c = *coef;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool second = i >= n_vec;
+        const int64_t k = second ? i - n_vec : i;
+        const uint4 raw = *reinterpret_cast<const uint4*>((second ? x1 : x0) + k * kPer);
+        T v[kPer];
+        *reinterpret_cast<uint4*>(v) = raw;
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) v[e] = (T)((float)v[e] * c);
+        *reinterpret_cast<uint4*>((second ? y1 : y0) + k * kPer) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 // ----------------------------------------------------------------------------------- pair dot
 __global__ void __launch_bounds__(256)
     pair_dot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
@@ -612,6 +632,28 @@ extern "C" int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, i
     rows_scale_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rinv, n, dim, ld,
                                                                   (__half*)out, ld_out);
     return check_launch("rows_scale_f16");
+}
+
+extern "C" int pb2_scale_pair(const void* x0, const void* x1, int64_t n_elems, int dtype, const float* coef,
+                              void* y0, void* y1, void* stream) {
+    if (n_elems <= 0) return PB2_OK;
+    const int es = dtype == PB2_F32 ? 4 : 2;
+    auto ok = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!ok(x0) || !ok(x1) || !ok(y0) || !ok(y1) || !coef || (n_elems * es) % 16 != 0 ||
+        (dtype != PB2_F32 && dtype != PB2_BF16 && dtype != PB2_F16))
+        return set_error(PB2_ERR_ARG, "scale_pair: need 16-byte aligned bf16 / fp16 / fp32 arrays of whole 16-byte vectors");
+    const int64_t n_vec = n_elems * es / 16;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((2 * n_vec + 255) / 256, (int64_t)sm_count() * 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PB2_F32)
+        scale_pair_kernel<float><<<grid, 256, 0, st>>>((const float*)x0, (const float*)x1, n_vec, coef, (float*)y0, (float*)y1);
+    else if (dtype == PB2_BF16)
+        scale_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, n_vec, coef,
+                                                               (__nv_bfloat16*)y0, (__nv_bfloat16*)y1);
+    else
+        scale_pair_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x0, (const __half*)x1, n_vec, coef, (__half*)y0,
+                                                        (__half*)y1);
+    return check_launch("scale_pair");
 }
 
 extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,

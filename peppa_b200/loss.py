@@ -87,10 +87,11 @@ class _HingeFn(torch.autograd.Function):
         if ctx.fused:       # one scale kernel for both gradients, already in the inputs' dtype
             (grads,) = ctx.saved_tensors
             vd, vdev, ad, adev, dv_, da_ = ctx.meta
-            # a 0-d fp32 grad_output does not promote the product: one kernel, result in grads.dtype
-            g = grads * (grad_out if grad_out.device == grads.device else grad_out.to(grads.device))
-            gV = g[0][:, :dv_].to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
-            gA = g[1][:, :da_].to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
+            go = grad_out.detach().to(device=grads.device, dtype=torch.float32)
+            # two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy
+            g0, g1 = ops.scale_pair(grads[0], grads[1], go)
+            gV = g0[:, :dv_].to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
+            gA = g1[:, :da_].to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
             return gV, gA, None
         dV, dA = ctx.saved_tensors
         vd, vdev, ad, adev = ctx.meta

@@ -347,6 +347,16 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
     return loss, grads
 
 
+def scale_pair(x0, x1, coef):
+    """(x0 * coef, x1 * coef) for a 0-d fp32 device tensor ``coef``: one launch, fresh contiguous results."""
+    assert x0.dtype == x1.dtype and x0.shape == x1.shape and x0.is_contiguous() and x1.is_contiguous()
+    y0, y1 = torch.empty_like(x0), torch.empty_like(x1)
+    with torch.cuda.device(x0.device):
+        check(_cabi.lib().pb2_scale_pair(_ptr(x0), _ptr(x1), x0.numel(), _DTYPE_CODE[x0.dtype], _ptr(coef), _ptr(y0), _ptr(y1),
+                                         _stream(x0.device)), "scale_pair")
+    return y0, y1
+
+
 def sum_partials(part, alpha=1.0):
     out = torch.empty((), dtype=torch.float32, device=part.device)
     with torch.cuda.device(part.device):

@@ -145,13 +145,26 @@ __global__ void __launch_bounds__(256) lse_merge_kernel(const float* __restrict_
 }
 
 // partial sums of 2^(t - M) with one shift M for every partial (pb2_sim_lse_both): lse = (M + log2 sum) ln 2
-__global__ void __launch_bounds__(256) lse_merge_const_kernel(const float* __restrict__ psum, int n_parts, int64_t n,
+__global__ void __launch_bounds__(64) lse_merge_const_kernel(const float* __restrict__ psum, int n_parts, int64_t n,
                                                               float shift, float* __restrict__ lse, int accumulate) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // four independent chains in a fixed order (the partial count is a multiple of 4 for the column layout)
+    // four chains in a fixed order; sixteen loads in flight per thread (a 32768-wide merge has only 128 CTAs, so
+    // the bandwidth has to come from memory-level parallelism inside the thread)
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int k = 0;
+    for (; k + 16 <= n_parts; k += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(psum + (int64_t)(k + u) * n + i);
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) {
+            s0 += v[u];
+            s1 += v[u + 1];
+            s2 += v[u + 2];
+            s3 += v[u + 3];
+        }
+    }
     for (; k + 4 <= n_parts; k += 4) {
         s0 += psum[(int64_t)k * n + i];
         s1 += psum[(int64_t)(k + 1) * n + i];
@@ -690,7 +703,7 @@ extern "C" int pb2_lse_merge_const(const float* part_sum, int n_parts, int64_t n
                                    int accumulate, void* stream) {
     if (n <= 0) return PB2_OK;
     if (!part_sum || !lse || n_parts <= 0) return set_error(PB2_ERR_ARG, "lse_merge_const: bad arguments");
-    lse_merge_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    lse_merge_const_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
         part_sum, n_parts, n, bound * 1.4426950408889634f, lse, accumulate);
     return check_launch("lse_merge_const");
 }

@@ -4,8 +4,9 @@ The duration-matched sampler stays in Python and consumes ``random`` in exactly 
 order (seeded runs draw identical triplets), with the duration grouping hoisted out of the sample loop
 (SURVEY 8f row 2); the arithmetic of *all* samples runs in one launch of the fused gather + cosine-gap
 kernel, so ``audio[pos]``, ``video[pos]``, ``video[neg]`` are never materialised.
-``TripletScorer`` (pig/triplet.py:31-61) is the encode-side caller and is out of scope: it needs the
-dataset and Lightning; its ``_score`` is ``score_triplets`` below.
+``TripletScorer`` (pig/triplet.py:31-61) is the encode-side caller: the class below keeps its interface and
+imports the dataset (``pig.data``) and Lightning only when it is used -- the encoders and the data pipeline are
+not part of this package; its ``_score`` is ``score_triplets`` below.
 """
 from __future__ import annotations
 
@@ -31,6 +32,36 @@ class TripletBatch:
     anchor: ...
     positive: ...
     negative: ...
+
+
+class TripletScorer:
+    """pig/triplet.py:31-61 with the same constructor, ``_encode`` / ``_score`` / ``evaluate``.  The dataset and the
+    trainer are the reference's own (``pig.data.PeppaPigDataset``, ``pig.data.grouped_loader``, ``pl.Trainer``),
+    imported on use; only the scoring runs here."""
+
+    def __init__(self, fragment_type, split=['val'], target_size=(180, 100), audio_sample_rate=44100, scrambled_video=False):
+        from pig.data import PeppaPigDataset      # the reference's data pipeline (not part of this package)
+        self.dataset = PeppaPigDataset(target_size=target_size, split=split, fragment_type=fragment_type, duration=None,
+                                       audio_sample_rate=audio_sample_rate, scrambled_video=scrambled_video)
+
+    def _encode(self, model, trainer, batch_size):
+        """Encode the whole split once (batches grouped by audio duration, like pig/triplet.py:44-51)."""
+        import pig.data as data
+        loader = data.grouped_loader(self.dataset, lambda clip: clip.audio_duration, data.collate, batch_size=batch_size)
+        encoded = list(trainer.predict(model, loader))
+        self._audio = torch.cat([b.audio for b in encoded])
+        self._video = torch.cat([b.video for b in encoded])
+        self._duration = torch.cat([b.audio_duration for b in encoded])
+
+    def _score(self, n_samples=100):
+        return score_triplets(self._video, self._audio, self._duration, n_samples=n_samples)
+
+    def evaluate(self, model, batch_size, n_samples=100, trainer=None):
+        if trainer is None:                       # pig/triplet.py:58-59
+            from pytorch_lightning import Trainer
+            trainer = Trainer(gpus=1, logger=False)
+        self._encode(model, trainer, batch_size)
+        return self._score(n_samples=n_samples)
 
 
 def _gather_scores(audio_b, video_b, pos_idx, neg_idx, discrete):

@@ -103,3 +103,43 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_grad_gemm_dual(null, 1, 8, 8, 64, null, null, 1, 512, 512, 512, 1.0, null, null, 512, 512, null) == 1
     assert lib.pb2_milnce_finish_k(null, 512, null, null, 8, 2, 1, 512, 512, 1.0, null, null, 512, null) == 1
     assert lib.pb2_grad_gemm_workspace() >= 148 * 128 * 512 * 4
+
+
+def test_triplet_scorer_keeps_the_reference_interface(monkeypatch):
+    """TripletScorer (pig/triplet.py:31-61): constructor arguments go to the reference's own dataset class, _encode
+    concatenates what trainer.predict yields; pig.data and Lightning are imported only on use."""
+    import sys
+    import types
+
+    from peppa_b200 import triplet
+    seen = {}
+
+    class FakeDataset:
+        def __init__(self, **kw):
+            seen.update(kw)
+
+    data = types.ModuleType("pig.data")
+    data.PeppaPigDataset = FakeDataset
+    data.collate = object()
+    data.grouped_loader = lambda ds, key, collate, batch_size: [("loader", ds, batch_size)]
+    pig = types.ModuleType("pig")
+    pig.data = data
+    monkeypatch.setitem(sys.modules, "pig", pig)
+    monkeypatch.setitem(sys.modules, "pig.data", data)
+    sc = triplet.TripletScorer("dialog", split=["val"], target_size=(90, 50), scrambled_video=True)
+    assert seen == dict(target_size=(90, 50), split=["val"], fragment_type="dialog", duration=None, audio_sample_rate=44100,
+                        scrambled_video=True)
+
+    class Batch:
+        def __init__(self, k):
+            self.audio, self.video = torch.full((2, 4), float(k)), torch.full((2, 4), float(-k))
+            self.audio_duration = torch.tensor([1.0 * k, 2.0 * k])
+
+    class Trainer:
+        def predict(self, model, loader):
+            assert loader[0][0] == "loader" and loader[0][2] == 8
+            return [Batch(1), Batch(2)]
+
+    sc._encode(model=None, trainer=Trainer(), batch_size=8)
+    assert tuple(sc._audio.shape) == (4, 4) and torch.equal(sc._duration, torch.tensor([1.0, 2.0, 2.0, 4.0]))
+    assert torch.equal(sc._video, -sc._audio)

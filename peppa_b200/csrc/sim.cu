@@ -91,6 +91,18 @@ struct TileCtx {
 
 // Per-warp output staging for gradient-matrix tiles: two 4 KiB slabs, 128-byte swizzled, each
 // written by the warp's 32 threads (one 128-byte row per thread) and drained by a TMA store.
+// Output tiles (gradient matrix, score matrix) leave with an evict-first L2 hint: a 2 GiB block streams through the
+// 126 MB L2 on its way to HBM and otherwise keeps evicting the 64 MB of operands every CTA re-reads (measured on the
+// hinge pass, 32768^2 block: 1.249 -> 1.219 ms sustained, 1.211 -> 1.159 ms for the first 200 launches; operand
+// loads with an evict-last hint on top (2): no further change).  0 = no hint (measurement builds).
+#ifndef PB2_G_STORE_HINT
+#define PB2_G_STORE_HINT 1
+#endif
+#if PB2_G_STORE_HINT >= 2
+#define PB2_OPERAND_POLICY kEvictLast
+#else
+#define PB2_OPERAND_POLICY kEvictNormal
+#endif
 struct OutStage {
     uint8_t* buf;             // this warp's nbuf * kOutSlabBytes
     const CUtensorMap* tmap;  // gradient matrix [rows, cols] fp16, box [32 x 64]
@@ -127,7 +139,11 @@ struct OutStage {
         if (!(skip & 4)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
+#if PB2_G_STORE_HINT
+            if (!(skip & 1)) tma_store_2d_hint(tmap, buf + (slab & mask) * kOutSlabBytes, col, row, kEvictFirst);
+#else
             if (!(skip & 1)) tma_store_2d(tmap, buf + (slab & mask) * kOutSlabBytes, col, row);
+#endif
             tma_store_commit();
         }
         ++slab;
@@ -955,18 +971,18 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                     uint8_t* sy = sx + BM * BK * 2;
                     if (kCtas == 1) {
                         mbar_arrive_expect_tx(full + stage, L::kStageBytes);
-                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, kEvictNormal);
-                        tma_load_2d(sy, &tm_y, full + stage, kb * BK, yrow, kEvictNormal);
+                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, PB2_OPERAND_POLICY);
+                        tma_load_2d(sy, &tm_y, full + stage, kb * BK, yrow, PB2_OPERAND_POLICY);
                     } else if (kMcast) {  // own X tile; this CTA's half of the Y tile lands in both CTAs
                         mbar_arrive_expect_tx(full + stage, L::kStageBytes);  // X + both halves of Y arrive here
-                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, kEvictNormal);
+                        tma_load_2d(sx, &tm_x, full + stage, kb * BK, xrow, PB2_OPERAND_POLICY);
                         tma_load_2d_mcast(sy + crank * (BN / 2) * BK * 2, &tm_y, full + stage, kb * BK, yrow, (uint16_t)3,
-                                          kEvictNormal);
+                                          PB2_OPERAND_POLICY);
                     } else {  // both CTAs' bytes are counted on the leader's barrier
                         if (crank == 0) mbar_arrive_expect_tx(full + stage, L::kStageBytes * kCtas);
                         const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
-                        tma_load_2d_pair(sx, &tm_x, lbar, kb * BK, xrow, kEvictNormal);
-                        tma_load_2d_pair(sy, &tm_y, lbar, kb * BK, yrow, kEvictNormal);
+                        tma_load_2d_pair(sx, &tm_x, lbar, kb * BK, xrow, PB2_OPERAND_POLICY);
+                        tma_load_2d_pair(sy, &tm_y, lbar, kb * BK, yrow, PB2_OPERAND_POLICY);
                     }
                     if (++stage == L::kStages) {
                         stage = 0;

@@ -1244,13 +1244,18 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
 }
 
 static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
-// pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, anything else = independent CTAs.  Pairs are
+// pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, 2 = multicast clusters, 0 = independent CTAs, -1 = default.  Pairs are
 // correct (tools/gpu_probe.py simpair: identical counts / ranks) but measured SLOWER here -- hinge pass 1.34 vs
 // 1.23 ms, rank pass 0.843 vs 0.827 ms per 32768^2 block, sustained: a pair's MMA for tile t+2 waits for BOTH
 // CTAs' epilogues of tile t, and these kernels are bound by their epilogues, not by operand traffic (unlike the
 // gradient GEMM, whose gain came from the 512-wide pair tile reading G once).  2 = clusters of 2 with independent
 // MMAs and a multicast Y tile: within noise of independent CTAs (1.25 ms / 0.794 ms).  Kept as measured options.
-static int g_sim_pair = 0;
+// -1 (default) = 0.  Third session, alternating builds on one board: back to back on a 32768^2 block the multicast
+// clusters are 2-3 % faster for the passes without an output tile (rank 0.836 -> 0.816-0.825 ms, one-pass
+// log-sum-exp 1.104-1.112 -> 1.055-1.084 ms) and slower with one (hinge + gradient matrix 1.216 -> 1.245 ms); inside
+// the real steps, where these passes alternate with the gradient GEMMs, they lose (65536-clip MIL-NCE step 16.0-16.9
+// -> 16.4-17.7 ms, 16384^2 recall call 0.38-0.41 -> 0.41-0.43 ms; tools/ab_milnce.py), so independent CTAs stay.
+static int g_sim_pair = -1;
 
 template <class Policy>
 static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,

@@ -452,6 +452,35 @@ def test_sim_lse_both_against_fp64(pb, r, c, d, scale):
         ops.sim_lse_both(xb, yb, 100.0, scale=scale)                 # 2^(-2 * 144) would underflow: refused
 
 
+def test_multicast_clusters_match_independent_ctas(pb):
+    """The cluster variants of the rank and log-sum-exp passes (two CTAs sharing a multicast gallery tile; CTA pairs
+    on one MMA) are measured options (default: independent CTAs); their results are bit-identical, also with an odd
+    trailing row block."""
+    from peppa_b200 import _cabi, ops
+    lib = _cabi.lib()
+    n = 33 * 128 + 5
+    V, A = emb(n, 4.0)
+    vb, ab = V.cuda().bfloat16(), A.cuda().bfloat16()
+    rv, _ = ops.row_norms(vb)
+    ra, _ = ops.row_norms(ab)
+    _, thr = ops.sim_diag(ab, vb, ra, rv)
+    idx = torch.arange(n, device="cuda")
+    bound = ops.logit_bound(ab, vb, 4.0)
+    res = {}
+    try:
+        for mode in (0, 2, 1):
+            lib.pb2_debug_sim_pair(mode)
+            res[mode] = (ops.sim_rank(ab, vb, ra, rv, thr, idx), *ops.sim_lse_both(ab, vb, bound, scale=4.0),
+                         ops.sim_lse_rows(ab, vb, scale=4.0))
+    finally:
+        lib.pb2_debug_sim_pair(-1)
+    for mode in (2, 1):
+        for x, y in zip(res[0], res[mode]):
+            assert torch.equal(x, y)
+    ranks, near = O.ranks_identity(V, A)
+    assert bool(((res[2][0].cpu() == ranks) | near).all())
+
+
 def test_milnce_one_pass_statistics_path(pb):
     """MILNCELoss takes the one-pass row + column statistics from 2^26 logits on when the logits are bounded;
     force it at a small size (ragged blocks), and check that unbounded logits keep the two-pass kernels."""

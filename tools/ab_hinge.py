@@ -19,10 +19,16 @@ def main():
     args = sys.argv[1:]
     if args and args[0].endswith(".so"):
         _cabi.LIB_PATH = os.path.abspath(args.pop(0))
+    pair = -1
+    for a_ in list(args):
+        if a_.startswith("pair="):          # pb2_debug_sim_pair: 0 = independent CTAs, 1 = CTA pairs, 2 = multicast clusters (default -1: per policy)
+            pair = int(a_[5:])
+            args.remove(a_)
     what = args or ["hinge"]
     from peppa_b200 import ops
     from gpu_probe import _t, emb
-    name = os.path.basename(_cabi.LIB_PATH)
+    name = os.path.basename(_cabi.LIB_PATH) + (f" pair={pair}" if pair >= 0 else "")
+    _cabi.lib().pb2_debug_sim_pair(pair)
     n = 32768
     V, A = emb(n)
     rv, _ = ops.row_norms(V)

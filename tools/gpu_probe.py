@@ -333,7 +333,7 @@ def step_simpair():
         print(f"mode {m} vs 0: row counts equal", torch.equal(a[0], b[0]), "col counts equal", torch.equal(a[1], b[1]),
               "hinge ranks equal", torch.equal(a[2], b[2]), "rank-kernel ranks equal", torch.equal(a[3], b[3]),
               "loss partial sums", a[4], b[4], "G sums", a[5], b[5], flush=True)
-    lib.pb2_debug_sim_pair(0)
+    lib.pb2_debug_sim_pair(-1)
 
 
 def step_milnce_perf():

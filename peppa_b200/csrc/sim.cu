@@ -91,12 +91,13 @@ struct TileCtx {
 
 // Per-warp output staging for gradient-matrix tiles: two 4 KiB slabs, 128-byte swizzled, each
 // written by the warp's 32 threads (one 128-byte row per thread) and drained by a TMA store.
-// Output tiles (gradient matrix, score matrix) leave with an evict-first L2 hint: a 2 GiB block streams through the
-// 126 MB L2 on its way to HBM and otherwise keeps evicting the 64 MB of operands every CTA re-reads (measured on the
-// hinge pass, 32768^2 block: 1.249 -> 1.219 ms sustained, 1.211 -> 1.159 ms for the first 200 launches; operand
-// loads with an evict-last hint on top (2): no further change).  0 = no hint (measurement builds).
+// PB2_G_STORE_HINT (measurement builds): 1 = output tiles leave with an evict-first L2 hint, 2 = and operand loads
+// evict-last.  Back to back on a 32768^2 block the hint is worth 2.5 % (hinge pass 1.249 -> 1.219 ms sustained: the
+// 2 GiB block no longer evicts the 64 MB of operands the next launch re-reads); inside the real gallery step, where
+// the gradient GEMMs stream 4 GiB through L2 between two hinge passes anyway, it is neutral (131072-clip step, two
+// builds alternating in one call: 47.3 ms without, 47.6 ms with; tools/ab_gallery.py), so the default stays plain.
 #ifndef PB2_G_STORE_HINT
-#define PB2_G_STORE_HINT 1
+#define PB2_G_STORE_HINT 0
 #endif
 #if PB2_G_STORE_HINT >= 2
 #define PB2_OPERAND_POLICY kEvictLast

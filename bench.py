@@ -310,7 +310,7 @@ def run_reference(args):
                          "sample": f"{what}; host has {os.cpu_count()} cpus"},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -602,6 +602,15 @@ def line_from(res, args, world, workload):
     return line
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -613,6 +622,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON record: libraries that print there (NCCL writes its version line to
+    # stdout when NCCL_DEBUG is set on the box) are sent to stderr, and emit() below writes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -667,7 +682,7 @@ def main():
                                                | ({"frac_of_bf16_peak": o["frac_of_bf16_peak"]} if "frac_of_bf16_peak" in o else {})
                                                | ({"ms_per_step_eager": o["ms_per_step_eager"]} if "ms_per_step_eager" in o else {}))
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

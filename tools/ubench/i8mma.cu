@@ -35,6 +35,9 @@ __device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t da, uint64_t db, u
 }
 
 // reps == 0: one product, D written to out (correctness).  reps > 0: reps x 4 MMAs back to back (issue rate).
+// reps < 0: correctness with B given TRANSPOSED, bt [K = 128][N = 128] row-major, and read MN-major (the layout of the
+// embedding operand of the gradient GEMMs): 128 k-rows of 128 bytes, 128B swizzle on (k-row % 8), descriptor SBO =
+// 1024 (8 k-rows), 32 k-rows = 4096 bytes per instruction, B-major bit set; -reps - 1 = LBO >> 4 to try.
 template <bool kI8>
 __global__ void __launch_bounds__(128, 1) probe(const uint8_t* a, const uint8_t* b, int32_t* out, int reps) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -60,17 +63,26 @@ __global__ void __launch_bounds__(128, 1) probe(const uint8_t* a, const uint8_t*
     tc_fence_after();
     const uint32_t tmem = *slot;
     if (tid == 0) {
-        const uint32_t idesc = kI8 ? idesc_of(2, 0, 1, 128, 128) : idesc_of(1, 1, 1, 128, 128);
-        const uint64_t da = make_smem_desc(smem_u32(sa), 16, 1024), db = make_smem_desc(smem_u32(sb), 16, 1024);
-        const int n = reps > 0 ? reps : 1;
-        for (int it = 0; it < n; ++it)
+        uint32_t idesc = kI8 ? idesc_of(2, 0, 1, 128, 128) : idesc_of(1, 1, 1, 128, 128);
+        const uint64_t da = make_smem_desc(smem_u32(sa), 16, 1024);
+        if (reps < 0) {
+            idesc |= 1u << 16;  // B is MN-major
+            const uint32_t code = (uint32_t)(-reps - 1);  // (LBO >> 4) * 4096 + (SBO >> 4)
+            const uint64_t db = make_smem_desc(smem_u32(sb), (code >> 12) << 4, (code & 4095u) << 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma<kI8>(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);  // +32 bytes per step
+            for (int k = 0; k < 4; ++k) mma<kI8>(tmem, da + 2 * k, db + 256 * k, idesc, k != 0 ? 1u : 0u);  // +32 k-rows per step
+        } else {
+            const uint64_t db = make_smem_desc(smem_u32(sb), 16, 1024);
+            const int n = reps > 0 ? reps : 1;
+            for (int it = 0; it < n; ++it)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma<kI8>(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);  // +32 bytes per step
+        }
         umma_commit(bar);
     }
     mbar_wait(bar, 0);
     tc_fence_after();
-    if (reps == 0) {
+    if (reps <= 0) {
         for (int ch = 0; ch < 4; ++ch) {
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
@@ -115,6 +127,36 @@ int main() {
         }
     printf("kind::i8 u8 x s8 -> s32, 128 x 128 x 128, K-major 128B swizzle: %ld mismatches (D[0][0..3] = %d %d %d %d)\n", bad, ho[0], ho[1],
            ho[2], ho[3]);
+    // B transposed in memory, read MN-major
+    std::vector<uint8_t> hbt(128 * 128);
+    for (int k = 0; k < 128; ++k)
+        for (int j = 0; j < 128; ++j) hbt[k * 128 + j] = hb[j * 128 + k];
+    uint8_t* dbt;
+    cudaMalloc(&dbt, hbt.size());
+    cudaMemcpy(dbt, hbt.data(), hbt.size(), cudaMemcpyHostToDevice);
+    // (LBO, SBO) candidates in bytes: with one 128-element MN chunk the stride between 8-k-row groups (1024 B) is
+    // the one that matters; which field carries it is what the sweep answers
+    // (measured: SBO = 1024 is exact for every LBO; SBO = 16 gives 16378 mismatches; SBO = 4096 walks out of the tile)
+    const int cand[][2] = {{16, 1024}, {1024, 1024}, {4096, 1024}, {16384, 1024}};
+    for (auto& c2 : cand) {
+        const int lbo = c2[0] >> 4, sbo = c2[1] >> 4;
+        cudaMemset(dout, 0xff, 128 * 128 * 4);
+        probe<true><<<1, 128, smem>>>(da, dbt, dout, -(lbo * 4096 + sbo) - 1);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            printf("MN-major B probe (LBO %d, SBO %d) failed: %s\n", lbo << 4, sbo << 4, cudaGetErrorString(e));
+            return 1;
+        }
+        cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost);
+        long badt = 0;
+        for (int i = 0; i < 128; ++i)
+            for (int j = 0; j < 128; ++j) {
+                int32_t ref = 0;
+                for (int k = 0; k < 128; ++k) ref += (int32_t)ha[i * 128 + k] * (int32_t)(int8_t)hb[j * 128 + k];
+                badt += ref != ho[i * 128 + j];
+            }
+        printf("kind::i8, B [K][N] read MN-major (+4096 B per K = 32; LBO %5d, SBO %5d): %ld mismatches\n", lbo << 4, sbo << 4, badt);
+    }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaEvent_t t0, t1;

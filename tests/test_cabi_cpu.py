@@ -143,3 +143,21 @@ def test_triplet_scorer_keeps_the_reference_interface(monkeypatch):
     sc._encode(model=None, trainer=Trainer(), batch_size=8)
     assert tuple(sc._audio.shape) == (4, 4) and torch.equal(sc._duration, torch.tensor([1.0, 2.0, 2.0, 4.0]))
     assert torch.equal(sc._video, -sc._audio)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: exactly ONE line on stdout, the JSON record (anything a library prints goes to stderr).
+    The reference arm is CPU-only, so the contract is checked here on a small bounded sample."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "train1024",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["value"] > 0 and rec["unit"] == "pairs/s"
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0

@@ -103,6 +103,17 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_grad_gemm_dual(null, 1, 8, 8, 64, null, null, 1, 512, 512, 512, 1.0, null, null, 512, 512, null) == 1
     assert lib.pb2_milnce_finish_k(null, 512, null, null, 8, 2, 1, 512, 512, 1.0, null, null, 512, null) == 1
     assert lib.pb2_grad_gemm_workspace() >= 148 * 128 * 512 * 4
+    # one-pass log-sum-exp: null partials and a bound whose shift would underflow fp32 are refused before any launch
+    one = C.c_void_p(256)
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, 1.0, null, null, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, 100.0, one, one, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, -1.0, one, one, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 0, 8, 512, 512, 512, 1.0, 1.0, null, null, null) == 0
+    assert lib.pb2_sim_lse_col_parts(1000) == 32 and lib.pb2_sim_lse_col_parts(128) == 4
+    assert lib.pb2_lse_merge_const(null, 4, 8, 1.0, null, 0, null) == 1 and lib.pb2_lse_merge_const(null, 4, 0, 1.0, null, 0, null) == 0
+    assert lib.pb2_scale_pair(null, null, 64, 0, null, null, null, null) == 1
+    assert lib.pb2_scale_pair(one, one, 63, 2, one, one, one, null) == 1        # not whole 16-byte vectors
+    assert lib.pb2_scale_pair(null, null, 0, 0, null, null, null, null) == 0
 
 
 def test_triplet_scorer_keeps_the_reference_interface(monkeypatch):

@@ -62,27 +62,27 @@ def peaks():
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum (GB) of one launch, from the committed ncu --set full
-    captures (profiles/r1b_ncu_summary.json: the kernels of a 32768 x 32768 gallery block;
-    profiles/r1_ncu_summary.json: 2^20 triplets); None if unknown."""
+    """(GB per launch, source) -- dram__bytes_read.sum + dram__bytes_write.sum of one launch of ``kernel``.  ncu
+    cannot run inside the timed bench (it replays every kernel ~40 times), so the figure comes from the committed
+    ``ncu --set full`` capture of the same kernel on the same shape; the source string names the file and its
+    capture date so a stale number is visible as such.  (None, None) if there is no capture."""
     def gb(s):
         v, u = s.split()[:2]
         return float(v) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[u]
 
     try:
-        if kernel in ("sim_hinge+rank", "grad_gemm"):
-            with open(os.path.join(ROOT, "profiles", "r1b_ncu_summary.json")) as f:
-                ks = json.load(f)["r1b_gallery_kernels.ncu-rep"]
-            want = "HingePolicyT" if kernel == "sim_hinge+rank" else "grad_gemm_kernel<0, 512, 2>"
-            d = next(k for k in ks if want in k["kernel"])
-        elif kernel == "triplet_score":
-            with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
-                d = json.load(f)["r1_triplet"]
-        else:
-            return None
-        return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
-    except (OSError, KeyError, ValueError, StopIteration):
-        return None
+        with open(os.path.join(ROOT, "profiles", "traffic_index.json")) as f:
+            idx = json.load(f)
+        e = idx.get(kernel)
+        if not e:
+            return None, None
+        with open(os.path.join(ROOT, "profiles", e["file"])) as f:
+            d = json.load(f)
+        for key in e["path"]:
+            d = next(k for k in d if e["match"] in k["kernel"]) if key == "*" else d[key]
+        return gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"]), f"profiles/{e['file']} ({e['captured']}; {e['shape']})"
+    except (OSError, KeyError, ValueError, StopIteration, TypeError):
+        return None, None
 
 
 class ClockSampler:
@@ -189,18 +189,27 @@ def measure(fn, steps, warmup, sync, device, all_max=lambda x: x):
     return {"ms": ms, "kernels": kern, "launches": launches, "clocks": clk.summary(), "out": out}
 
 
-def roofline_of(kern, bound):
-    """Dominant kernel (largest summed device time) against the measured peak of its bound."""
+def roofline_of(kern, bound, step_ms=None):
+    """Dominant kernel (largest summed device time) against the measured peak of its bound.  Tensor-bound kernels
+    are divided by the BURST cuBLAS figure when they run alone in a short step (the step lasts under 50 ms: the
+    board has not reached its power cap) and by the SUSTAINED one inside a long step; both fractions are reported."""
     pk = peaks()
     if not kern:
         return None, {}
     name, k = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    extra = {}
     if bound == "hbm":
         achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s", pk["source"]
     else:
-        achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e12, pk["tf_sustained"], "TFLOP/s", pk["source"] + " (sustained)"
-    roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": ncu_traffic(name), "traffic_unit": "GB per launch (ncu dram read+write, profiles/r1b_ncu_summary.json / r1_ncu_summary.json)",
+        achieved, unit = k["work"] / (k["ms"] * 1e-3) / 1e12, "TFLOP/s"
+        burst = step_ms is not None and step_ms < 50.0
+        peak, src = (pk["tf_burst"], pk["source"] + " (burst: kernel timed in a short step)") if burst else \
+            (pk["tf_sustained"], pk["source"] + " (sustained: kernel timed inside a long step)")
+        extra = {"frac_of_burst": achieved / pk["tf_burst"], "frac_of_sustained": achieved / pk["tf_sustained"]}
+    traffic, traffic_src = ncu_traffic(name)
+    roof = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, **extra,
+            "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
+            "traffic_source": traffic_src,
             "peak_source": src, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"]}
     table = {n: {"launches": v["launches"], "ms_total": v["ms"],
                  ("gbs" if bound == "hbm" else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)) if v["ms"] else None}
@@ -277,12 +286,21 @@ def cpu_sample(workload, n_s, steps, warmup):
     return units / dt, dt, what
 
 
-def cpu_baseline(workload, n_s):
+def cpu_baseline(workload, n_s, gallery_n=None):
+    """The reference's algorithm on the box's host cores, ONE step of a bounded sample (no warm-up: the step is tens of
+    seconds of torch-CPU work).  For the gallery the sample is a 16384-clip sub-gallery; the full
+    problem cannot exist on a host (N^2 fp32 = 4 TiB), so its time is given as an explicitly labelled ~N^2
+    extrapolation of the measured sample."""
     import torch
     _all_host_threads()
-    value, dt, what = cpu_sample(workload, n_s, 1, 1)
-    return {"value": value, "unit": UNIT.get(workload, "pairs/s"), "cores": torch.get_num_threads(),
-            "kind": "port", "sample": f"{what}; reference algorithm (oracle port); {dt:.3f} s per step; host has {os.cpu_count()} cpus"}
+    value, dt, what = cpu_sample(workload, n_s, 1, 0)
+    out = {"value": value, "unit": UNIT.get(workload, "pairs/s"), "cores": torch.get_num_threads(),
+           "kind": "port", "sample": f"{what}; reference algorithm (oracle port); {dt:.3f} s per step; host has {os.cpu_count()} cpus"}
+    if workload == "gallery" and gallery_n:
+        out["extrapolated"] = {"what": f"EXTRAPOLATION, not a measurement: one {gallery_n} x {gallery_n} step at the measured pairs/s "
+                                       f"(cost ~ N^2; the reference's N x N fp32 temporaries would need {gallery_n * gallery_n * 4 / 2**40:.0f} TiB)",
+                               "seconds_per_step": float(gallery_n) ** 2 / value}
+    return out
 
 
 def _all_host_threads():
@@ -298,7 +316,12 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     _all_host_threads()
-    value, dt, what = cpu_sample(args.workload, args.cpu_sample, args.steps, args.warmup)
+    # bounded so that the whole --steps K --warmup W run ends within a few minutes: a 16384-clip sample costs ~20-40 s a step
+    n_s = args.cpu_sample
+    if args.workload == "gallery" and n_s == 0:
+        calls = args.steps + args.warmup
+        n_s = 16384 if calls <= 4 else (8192 if calls <= 12 else 4096)
+    value, dt, what = cpu_sample(args.workload, n_s or 4096, args.steps, args.warmup)
     unit = UNIT.get(args.workload, "pairs/s")
     line = {
         "impl": "reference", "metric": METRIC[args.workload], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
@@ -315,13 +338,54 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU workloads
+def rank_hash_terms(ranks, first_global_row=0):
+    """Order-independent 64-bit fingerprint of (global row id, rank) pairs: the terms (rank_i + 1) * odd
+    multiplier(i), summed with int64 wrap-around by the caller.  Row-sharded runs add their local sums (wrap-around
+    addition is associative and commutative), so 1, 2, 4 and 8 GPUs print the same number iff every rank of every
+    row agrees."""
+    import torch
+    r = ranks.to(torch.int64)
+    i = torch.arange(r.numel(), device=r.device, dtype=torch.int64) + int(first_global_row)
+    mult = (i * -7046029254386353131 + 7146057691288625177) | 1         # multiplicative hash constants, wraps mod 2^64
+    return (r + 1) * mult
+
+
+def verify_gallery(out, a_all, v_all, rank, world, n_rows=64):
+    """Outside the timed region: ``n_rows`` seeded global rows of the step's result against the blockwise restatement
+    of the reference's formulas (oracle/blockwise.py; plain torch on this GPU, never this repo's kernels) -- exact
+    ranks against the WHOLE gallery (identical outside a 1e-6 near-tie, inside the tie window otherwise), and the
+    dA / dV rows against the fp64 closed form.  Every rank checks the sampled rows it owns."""
+    import torch
+    from oracle import blockwise as B
+    n = a_all.shape[0]
+    nl = n // world
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(2026))[:n_rows].to(a_all.device)
+    mine = rows[(rows >= rank * nl) & (rows < (rank + 1) * nl)]
+    res = {"rows": 0, "rank_mismatch": 0, "near_tie_rows": 0, "dA_rel_err": 0.0, "dV_rel_err": 0.0}
+    if mine.numel():
+        loc = mine - rank * nl
+        want, near, lo, hi = B.sampled_rank_bounds(v_all, a_all, mine)
+        got = out["ranks"][loc].long()
+        bad = ((got != want) & ~near) | (got < lo) | (got > hi)
+        res.update(rows=int(mine.numel()), rank_mismatch=int(bad.sum()), near_tie_rows=int(near.sum()))
+        if out["dA"] is not None:
+            rel = lambda x, r: ((x.double() - r).abs().max() / r.abs().max()).item()  # noqa: E731
+            res["dA_rel_err"] = rel(out["dA"][loc], B.hinge_grad_rows(a_all, v_all, mine, MARGIN))
+            res["dV_rel_err"] = rel(out["dV"][loc], B.hinge_grad_rows(v_all, a_all, mine, MARGIN))
+    return res
+
+
 def bench_gallery(args, rank, world, device, sync, all_max):
     import torch
+    import torch.distributed as dist
     from peppa_b200.gallery import GalleryStep
     n = args.gallery_n
     assert n % world == 0
     nl = n // world
-    a_dev, v_dev = synth_embeddings(nl, 666 + rank, device)
+    # ONE global seed: every world size scores the SAME gallery (each rank generates it and keeps its row block),
+    # so the check block below is comparable across the N = 1, 2, 4, 8 lines of a scaling run
+    a_all, v_all = synth_embeddings(n, 666, device)
+    a_dev, v_dev = (a_all, v_all) if world == 1 else (a_all[rank * nl:(rank + 1) * nl].clone(), v_all[rank * nl:(rank + 1) * nl].clone())
     a_host, v_host = a_dev.cpu().pin_memory(), v_dev.cpu().pin_memory()
     step = GalleryStep(nl, DIM, margin=MARGIN, top_n=TOP_N, rank=rank, world=world, device=device)
     m = measure(lambda: step.run(a_dev, v_dev), args.steps, args.warmup, sync, device, all_max)
@@ -333,14 +397,39 @@ def bench_gallery(args, rank, world, device, sync, all_max):
         o = step.run(a_in, v_in)
         return o["loss"].item(), o["recall"].cpu()
 
-    ms_e2e = all_max(timed(run_e2e, args.steps, 1, sync))
-    roof, table = roofline_of(m["kernels"], "tensor")
+    # the end-to-end leg repeats the same seconds-long step with the copies inside the timed region: 3-5 steps
+    # resolve it to well under a percent, and the whole default run has to finish within minutes
+    ms_e2e = all_max(timed(run_e2e, max(3, min(args.steps, 5)), 1, sync))
+    roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
     out = m["out"]
+    # ---- check block (outside the timed region): world-size independent by construction
+    sums = torch.stack([rank_hash_terms(out["ranks"], rank * nl).sum(),
+                        (out["ranks"].to(torch.int64) * 0 + 1).sum()])                     # [hash, rows]
+    grad_sums = torch.stack([out["dA"].double().abs().sum(), out["dV"].double().abs().sum()])
+    ver = verify_gallery(out, a_all, v_all, rank, world)
+    vt = torch.tensor([ver["rows"], ver["rank_mismatch"], ver["near_tie_rows"]], dtype=torch.int64, device=device)
+    ve = torch.tensor([ver["dA_rel_err"], ver["dV_rel_err"]], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(sums)                   # int64 wrap-around sum
+        dist.all_reduce(grad_sums)
+        dist.all_reduce(vt)
+        dist.all_reduce(ve, op=dist.ReduceOp.MAX)
+    verified = {"rows": int(vt[0]), "rank_mismatches_outside_1e-6_ties": int(vt[1]), "near_tie_rows": int(vt[2]),
+                "dA_rows_max_rel_err": float(ve[0]), "dV_rows_max_rel_err": float(ve[1]),
+                "checker": "oracle/blockwise.py (reference formulas, torch fp32 ranks / fp64 gradients on the GPU), 64 seeded rows "
+                           "against the whole gallery, outside the timed region",
+                "ok": bool(int(vt[0]) == 64 and int(vt[1]) == 0 and float(ve[0]) < 1e-3 and float(ve[1]) < 1e-3)}
+    rec = out["recall"]
+    check = {"loss": out["loss"].item(), "recall_at_1": rec[1].item(), "recall_at_5": rec[5].item(), "recall_at_10": rec[TOP_N].item(),
+             "rank_hash": f"{int(sums[0]) & 0xFFFFFFFFFFFFFFFF:016x}", "rows_hashed": int(sums[1]),
+             "dA_abs_sum": float(grad_sums[0]), "dV_abs_sum": float(grad_sums[1]), "verified": verified,
+             "note": "one global seed: loss / recall / rank_hash are the same numbers at every --gpus N (rank_hash bit for bit; "
+                     "loss and the gradient sums to fp32 summation order)"}
     return {
         "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
         "launches": m["launches"] * world, "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4 + 4 * (TOP_N + 1),
         "flops_per_unit": 6.0 * DIM, "scaling": "strong",
-        "check": {"loss": out["loss"].item(), "recall_at_10": out["recall"][TOP_N].item()},
+        "check": check,
         "config": {"workload": f"gallery (BASELINE config 5): {n} x {n} audio-video gallery, hinge loss fwd+bwd + recall@1..10 from one "
                                "similarity pass, rows sharded over ranks", "gallery": n, "dim": DIM, "margin": MARGIN, "top_n": TOP_N,
                    "rows_per_gpu": nl, "l2": "per-step working set (embeddings, fp16 copies, gradient-matrix blocks of 2 GiB) far exceeds the "
@@ -368,7 +457,7 @@ def bench_milnce64k(args, device, sync):
         return step.run(a_in, v_in)["loss"].item()
 
     ms_e2e = timed(run_e2e, 3, 1, sync)
-    roof, table = roofline_of(m["kernels"], "tensor")
+    roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
     return {
         "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
         "launches": m["launches"], "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4, "flops_per_unit": 6.0 * DIM,
@@ -484,7 +573,7 @@ def bench_train1024(args, device, sync):
 
     ms_e2e = timed(run_e2e, steps, warm, sync)
     assert abs(run_e2e() - loss.item()) < 1e-6
-    roof, table = roofline_of(m["kernels"], "tensor")
+    roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
     return {
         "units": float(n) * n, "unit": "pairs/s", "ms": ms_graph, "ms_eager": m["ms"], "ms_e2e": ms_e2e, "ms_e2e_eager": ms_e2e_eager,
         "roofline": roof, "kernels": table,
@@ -512,7 +601,7 @@ def bench_retrieval16k(args, device, sync):
 
     ms_e2e = timed(run_e2e, steps, warm, sync)
     r = run_e2e()
-    roof, table = roofline_of(m["kernels"], "tensor")
+    roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
     return {
         "units": float(n) * n, "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table, "launches": m["launches"],
         "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4 * (TOP_N + 1) * n, "flops_per_unit": 2.0 * DIM, "scaling": "weak",
@@ -569,7 +658,7 @@ def bench_encoder_tail(args, device, sync):
         return rinv.sum().item()
 
     ms_e2e = timed(run_e2e, 3, 1, sync)
-    roof, table = roofline_of(m["kernels"], "tensor")
+    roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
     return {
         "units": float(n), "unit": "rows/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table, "launches": m["launches"],
         "clocks": m["clocks"], "h2d": n * DIM * 2, "d2h": 4, "flops_per_unit": 2.0 * DIM * DIM, "scaling": "weak",
@@ -577,6 +666,59 @@ def bench_encoder_tail(args, device, sync):
         "config": {"workload": "encoder_tail (SURVEY 8f row 3): Linear(512,512) + L2-normalise + bf16 + rinv, 2^20 rows", "rows": n,
                    "dim": DIM, "hbm_bytes_per_row": 2 * DIM * 2 + 8,
                    "l2": "1 GiB in + 1 GiB out per step exceed the 126 MB L2; the 512 KiB weight is L2 resident by design"}}
+
+
+def gpu_eager_baselines(device):
+    """The reference's OWN GPU path -- its ATen / cuBLAS calls, i.e. the oracle port's functions run on cuda tensors
+    ("that cuBLAS-based eager path is the bar to beat") -- timed beside ours for config 2, config 3 and a
+    32768^2 loss.  fp32 inputs as the reference's code sees them without AMP, and under fp16 autocast as Lightning's
+    ``precision: 16`` (hparams_base.yaml:45) runs it.  A reported baseline; nothing here is on the product path."""
+    import torch
+    from oracle import pig_oracle as O
+    out = []
+
+    def timeit(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for n, steps in ((1024, 50), (32768, 3)):
+        a, v = synth_embeddings(n, 666, device)
+        a, v = a.float(), v.float()
+
+        def loss_step(amp):
+            vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                loss = O.triplet_loss(vv, aa, MARGIN)
+            loss.backward()
+        for amp in (False, True):
+            try:
+                ms = timeit(lambda: loss_step(amp), steps, 2)
+                out.append({"what": f"reference TripletLoss fwd+bwd (oracle port on cuda: torch.matmul / clamp / autograd), {n} x {n}, "
+                                    + ("fp16 autocast (precision: 16)" if amp else "fp32"),
+                            "ms_per_step": ms, "value": float(n) * n / (ms * 1e-3), "unit": "pairs/s"})
+            except RuntimeError as e:      # e.g. out of memory at 32768^2 under a crowded GPU
+                out.append({"what": f"reference TripletLoss {n} x {n} amp={amp}", "error": str(e)[:200]})
+        del a, v
+        torch.cuda.empty_cache()
+    n = 16384
+    a, v = synth_embeddings(n, 666, device)
+    a, v = a.float(), v.float()
+    eye = torch.eye(n, device=device)
+    t0 = time.perf_counter()
+    O.recall_at_1_to_n(v, a, eye, N=TOP_N)          # the per-row argsort + .item() loop of pig/metrics.py:23-40, on the GPU
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out.append({"what": f"reference recall_at_1_to_n(N=10) (oracle port on cuda: matmul + per-row argsort loop with .item() syncs), {n} x {n}",
+                "ms_per_step": dt * 1e3, "value": float(n) * n / dt, "unit": "pairs/s"})
+    return out
 
 
 def line_from(res, args, world, workload):
@@ -592,8 +734,12 @@ def line_from(res, args, world, workload):
         "gpu_launches": res["launches"], "check": res["check"],
     }
     if res["flops_per_unit"]:
-        line["frac_of_bf16_peak"] = res["flops_per_unit"] * value / world / (pk["tf_sustained"] * 1e12)
-        line["frac_of_bf16_peak_note"] = "algorithmic flops (SURVEY 8d) per GPU / measured sustained cuBLAS bf16 rate"
+        tf = res["flops_per_unit"] * value / world / 1e12
+        line["frac_of_bf16_peak"] = tf / pk["tf_sustained"]
+        line["frac_of_bf16_peak_burst"] = tf / pk["tf_burst"]
+        line["frac_of_bf16_peak_note"] = (f"algorithmic flops (SURVEY 8d) per GPU = {tf:.1f} TFLOP/s over the measured cuBLAS bf16 rates: "
+                                          f"sustained {pk['tf_sustained']} (frac_of_bf16_peak: the step runs for seconds at the power cap) "
+                                          f"and burst {pk['tf_burst']} (frac_of_bf16_peak_burst)")
     if "ms_eager" in res:
         line["ms_per_step_eager"] = res["ms_eager"]
     if "ms_e2e_eager" in res:
@@ -619,7 +765,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gallery", choices=["gallery", "train1024", "retrieval16k", "triplets1m", "encoder_tail", "milnce64k", "eval1467"])
     ap.add_argument("--gallery-n", type=int, default=1 << 20)
-    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="clips in the CPU arm's sub-gallery (0 = automatic: 16384 for cpu_baseline and short reference runs, "
+                         "smaller when --steps + --warmup would otherwise take more than a few minutes)")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON record: libraries that print there (NCCL writes its version line to
@@ -672,8 +820,10 @@ def main():
         line["value"] *= world
         line["note"] = "replicas only: this workload does not shard; N independent replicas" if world > 1 else None
     if world == 1 and rank == 0:
-        line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample)
+        line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_sample or (16384 if args.workload == "gallery" else 4096),
+                                            args.gallery_n if args.workload == "gallery" else None)
         if args.workload == "gallery" and not args.no_extras:
+            line["gpu_eager_baseline"] = gpu_eager_baselines(device)
             line["other_workloads"] = []
             for w, fn in single.items():
                 o = line_from(fn(args, device, torch.cuda.synchronize), args, 1, w)

@@ -5,9 +5,12 @@
  * peppa_b200/ keep those signatures and call ONLY the entry points declared here (ctypes, see
  * INTEGRATION.md).  Plain pointers and sizes; no torch types.  All pointers are DEVICE
  * pointers unless stated otherwise; matrices are row-major with an element leading
- * dimension `ld*`; embedding operands of the tensor-core kernels are bf16, 16-byte aligned,
- * with dim % 64 == 0 (the Python side zero-pads otherwise; zero padding changes neither dot
- * products nor norms).  Every call only ENQUEUES work on `stream` (a cudaStream_t) and
+ * dimension `ld*`.  Embedding rows may be bf16, fp16 or fp32 (`dtype`, a PB2_* code: the reference's
+ * callers hand over fp32 tensors, fp16 under Lightning's `precision: 16` -- hparams_base.yaml:45,
+ * pig/evaluation.py:70 -- or bf16): the row-wise kernels read the true values; the tensor-core kernels
+ * (pb2_sim_*) take bf16 or fp16 operands natively and fp32 rows as their split-bf16 pair (pb2_split_bf16:
+ * contraction length 3 dim).  Operands are 16-byte aligned with dim % 64 == 0 (the Python side zero-pads
+ * otherwise; zero padding changes neither dot products nor norms).  Every call only ENQUEUES work on `stream` (a cudaStream_t) and
  * returns a status: 0 = ok, non-zero = error, message via pb2_last_error().  Re-entrant; no
  * global state besides a cached driver entry point and per-device SM counts.
  */
@@ -19,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PB2_VERSION 1
+#define PB2_VERSION 2
 
 #define PB2_OK 0
 #define PB2_ERR_ARG 1
@@ -46,15 +49,21 @@ int pb2_triplet_score(const void* anchor, const void* positive, const void* nega
 
 /* ---- row statistics: replaces U.norm(2, dim=1, keepdim=True) of pig/util.py:11-12.
  * rinv[i] = 1/||x_i||_2 (no epsilon: a zero row gives +inf and NaN scores, like the reference),
- * norm[i] = ||x_i||_2; either output may be NULL.  x is bf16. */
-int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream);
+ * norm[i] = ||x_i||_2; either output may be NULL.  x is bf16 / fp16 / fp32 (dtype). */
+int pb2_row_norms(const void* x, int dtype, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream);
+
+/* Split-bf16 tensor-core operand of an fp32 matrix x [n, dim]: hi = bf16(x), lo = bf16(x - hi);
+ * out [n, 3 dim] bf16 = [hi | lo | hi] (side 0, the X operand) or [hi | hi | lo] (side 1, the Y operand), so that
+ * ONE pb2_sim_* call with dim' = 3 dim accumulates <hi_x,hi_y> + <lo_x,hi_y> + <hi_x,lo_y> in fp32 (~2^-17
+ * relative per product: the matmul of pig/util.py:13 on fp32 inputs without rounding them to bf16). */
+int pb2_split_bf16(const float* x, int64_t n, int dim, int64_t ld, int side, void* out, int64_t ld_out, void* stream);
 
 /* out[k] = <x[ix[k]], y[iy[k]]> * sx * sy with sx = rinv_x[ix[k]] (1 if rinv_x == NULL), same
  * for sy; ix / iy NULL = k.  The diagonal M_ii of pig/loss.py:43 and the positive's score of
  * pig/metrics.py:8-20.  dist_out (optional) = fl32(1 - out[k]); thr_out (optional) = the rank
  * threshold t_k: for every float s,  s >= t_k  <=>  fl32(1 - s) < dist_out[k]  (what pb2_sim_rank takes).
  * CUDA-core fp32 arithmetic: use it for the hinge diagonal; for ranking prefer pb2_sim_diag. */
-int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
+int pb2_pair_dot(const void* x, const void* y, int dtype, const int64_t* ix, const int64_t* iy, const float* rinv_x,
                  const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out, float* dist_out,
                  float* thr_out, void* stream);
 
@@ -62,17 +71,18 @@ int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t*
  * passes (only the diagonal tiles are visited), so that a gallery row duplicating the positive scores
  * bit-identically to it -- as in the reference, where positive and candidates come out of one GEMM
  * (pig/metrics.py:8) -- and "strictly closer" stays strict.  Outputs as pb2_pair_dot (each optional). */
-int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim,
+int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim, int dtype,
                  int64_t ldx, int64_t ldy, float* out, float* dist_out, float* thr_out, void* stream);
 
-/* ---- (a)/(b) similarity kernels: S = X * Y^T on the tcgen05 tensor cores (bf16 in, fp32
+/* ---- (a)/(b) similarity kernels: S = X * Y^T on the tcgen05 tensor cores (X and Y both bf16 or both fp16
+ * -- `dtype` = PB2_BF16 / PB2_F16, kind::f16 takes either natively; fp32 rows via pb2_split_bf16 -- fp32
  * accumulate in TMEM), epilogue fused per entry point; S itself reaches HBM only in
  * pb2_sim_matrix.  X is [rows, dim], Y is [cols, dim]; s_ij = <x_i,y_j> * rinv_x[i] * rinv_y[j]
  * * scale (rinv_* == NULL means 1). */
 
 /* pig/util.py:9-13 cosine_matrix (and the raw V A^T of pig/loss.py:19): out is fp32 [rows, cols]. */
 int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                   int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* out, int64_t ld_out,
+                   int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float* out, int64_t ld_out,
                    void* stream);
 
 /* pig/metrics.py:7-40 with one target per query row: rank[i] += #{ j != pos_col[i] : s_ij >= pos_thr[i] }
@@ -80,7 +90,7 @@ int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x, const floa
  * must be zeroed by the caller; column indices are offset by col_offset (sharded galleries).
  * No sort, no N x N store. */
 int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g, const float* pos_thr,
-                 const int64_t* pos_col, int64_t rows, int64_t cols, int64_t col_offset, int dim, int64_t ldq,
+                 const int64_t* pos_col, int64_t rows, int64_t cols, int64_t col_offset, int dim, int dtype, int64_t ldq,
                  int64_t ldg, int32_t* rank, void* stream);
 
 /* pig/metrics.py:54-77 resampled recall from ONE score matrix: scores = pb2_sim_matrix(references,
@@ -103,7 +113,7 @@ int pb2_subset_rank(const float* scores, int64_t ld, const int64_t* idx, int n_s
  * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
  * rank[i] += #{ j != i : s_ij >= pos_thr[i] } (loss and recall@k share one S pass). */
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
-                  const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim,
+                  const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim, int dtype,
                   int64_t ldx, int64_t ldy, float margin, float* loss_partial, int n_partials, int32_t* row_cnt,
                   int32_t* col_cnt, void* gmat, int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream);
 
@@ -113,7 +123,7 @@ int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float
  * (natural log).  Column LSE = the same call with X and Y swapped. */
 int pb2_sim_lse_parts(int64_t cols);
 int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                     int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* part_max, float* part_sum,
+                     int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float* part_max, float* part_sum,
                      void* stream);
 int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int64_t rows, float* lse,
                   int accumulate, void* stream);
@@ -127,7 +137,7 @@ int pb2_lse_merge(const float* part_max, const float* part_sum, int n_parts, int
  * (log-added into lse when accumulate != 0).  Unbounded logits: pb2_sim_lse_rows twice. */
 int pb2_sim_lse_col_parts(int64_t rows);
 int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                     int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float bound,
+                     int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float bound,
                      float* row_part_sum, float* col_part_sum, void* stream);
 int pb2_lse_merge_const(const float* part_sum, int n_parts, int64_t n, float bound, float* lse, int accumulate,
                         void* stream);
@@ -138,7 +148,7 @@ int pb2_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void
 
 /* MIL-NCE gradient matrix: gmat[i,j] = fp16( (exp(s_ij - den_row[i]) + exp(s_ij - den_col[j])) * 2^13 ). */
 int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* den_row,
-                     const float* den_col, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
+                     const float* den_col, int64_t rows, int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy,
                      float scale, void* gmat, int64_t ld_g, void* stream);
 
 /* ---- backward GEMMs on the tensor cores: out[M, dim] (=|+=) alpha * op(G) * Z with G [g_rows, g_cols]
@@ -167,23 +177,24 @@ int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_
                        const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
                        float* out1, int64_t ld_out0, int64_t ld_out1, void* stream);
 
-/* out = fp16(x * rinv) (rinv == NULL: plain bf16 -> fp16 conversion): the embedding operand of
- * pb2_grad_gemm.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and fp16 holds every
+/* out = fp16(x * rinv) (rinv == NULL: plain conversion to fp16; x bf16 / fp16 / fp32): the embedding operand
+ * of pb2_grad_gemm.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, and fp16 holds every
  * normalised bf16 embedding value with 3 extra significand bits. */
-int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, int dim, int64_t ld, void* out, int64_t ld_out,
-                       void* stream);
+int pb2_rows_scale_f16(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
+                       int64_t ld_out, void* stream);
 
-/* y0 = x0 * coef[0], y1 = x1 * coef[0] (coef on the device; dtype PB2_BF16 / PB2_F16 / PB2_F32; n_elems per
- * array, whole 16-byte vectors): the backward of pig/loss.py's scalar losses, whose gradients are produced in the
- * forward -- autograd's grad_output arrives as a device scalar, and both gradients are scaled in one launch. */
-int pb2_scale_pair(const void* x0, const void* x1, int64_t n_elems, int dtype, const float* coef, void* y0, void* y1,
-                   void* stream);
+/* y0 = T(x0 * coef[0]), y1 = T(x1 * coef[0]) (x fp32, coef on the device; T = out_dtype PB2_BF16 / PB2_F16 /
+ * PB2_F32; n_elems per array, whole 16-byte output vectors): the backward of pig/loss.py's scalar losses, whose
+ * gradients are produced in the forward and kept in fp32 -- autograd's grad_output (e.g. a GradScaler's 65536
+ * under pig's `precision: 16`, hparams_base.yaml:45) is applied BEFORE the rounding to the inputs' dtype. */
+int pb2_scale_pair(const float* x0, const float* x1, int64_t n_elems, int out_dtype, const float* coef, void* y0,
+                   void* y1, void* stream);
 
 /* Hinge finish (SURVEY 8a'): g_i = p_i + gdiag_i * rinv_y[i] * y_i,  gdiag_i = -(row_cnt[i] + col_cnt[i]),
  * p = G * Yhat from pb2_grad_gemm; grad_x[i] = coef * rinv_x[i] * (g_i - xhat_i <g_i, xhat_i>),
  * xhat = x * rinv_x (the Jacobian of the row normalisation in pig/util.py:11-12).
  * coef_dev (device scalar, may be NULL = 1) * coef_host multiplies the result. */
-int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
+int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, int dtype, const float* rinv_x,
                      const float* rinv_y, const int32_t* row_cnt, const int32_t* col_cnt, int64_t rows, int dim,
                      int64_t ldx, int64_t ldy, float coef_host, const float* coef_dev, float* grad_x,
                      int64_t ld_grad, void* stream);
@@ -195,31 +206,34 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
  * the diagonal term, plus the scalar loss = coef * (sum partials + sum_i (margin - diag_i)(row_cnt_i +
  * col_cnt_i)) (NaN when a row norm is zero); d_v / d_a are [n, dim] in out_dtype (PB2_F32/BF16/F16).
  * Between them: pb2_sim_hinge with n_partials passed
- * NEGATIVE (= "already zeroed", no memset) and two pb2_grad_gemm. */
-int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
+ * NEGATIVE (= "already zeroed", no memset) and two pb2_grad_gemm.  v / a are bf16 / fp16 / fp32 rows (dtype);
+ * for fp32 rows pb2_hinge_prep also writes their split-bf16 tensor-core operands v_split / a_split
+ * ([n, 3 dim] bf16, see pb2_split_bf16; NULL otherwise). */
+int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
                    float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
-                   float* loss_partial, int n_partials, void* stream);
-int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim, int64_t ldv,
+                   float* loss_partial, int n_partials, void* v_split, void* a_split, void* stream);
+int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv,
                       int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag, const int32_t* row_cnt,
                       const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,
                       float* loss_out, void* d_v, void* d_a, int out_dtype, void* stream);
 
 /* The five launches above behind one call (one FFI crossing per training step): workspace is a 256-byte
- * aligned device buffer of pb2_hinge_step_workspace(n, dim) bytes; n <= 32768 (one gradient-matrix block). */
-int64_t pb2_hinge_step_workspace(int64_t n, int dim);
-int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
+ * aligned device buffer of pb2_hinge_step_workspace(n, dim, in_dtype) bytes; n <= 32768 (one gradient-matrix
+ * block); v / a are bf16 / fp16 / fp32 rows (in_dtype). */
+int64_t pb2_hinge_step_workspace(int64_t n, int dim, int in_dtype);
+int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                    void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a, int out_dtype,
                    void* stream);
 
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
-int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
+int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int dtype, int64_t rows, int dim, int64_t ldy,
                       float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);
 
 /* MIL-NCE finish with K candidates per clip (pig/loss.py:19-25, x viewed as [N, N, K]):
  *   grad_x[r] = coef * ( p_r * 2^-13 - sum_{k < group} w[r*group + k] * y[(r*group + k) / y_div] ),
  * w = softmax over the K paired logits of a clip.  Video side: group = K, y_div = 1, y = audio rows;
  * audio side: group = 1, y_div = K, y = video rows. */
-int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, const float* w, int64_t rows, int group, int y_div,
+int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, int dtype, const float* w, int64_t rows, int group, int y_div,
                         int dim, int64_t ldy, float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
                         void* stream);
 

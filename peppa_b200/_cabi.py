@@ -12,6 +12,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpeppa_b200.so")
+MEASURE_LIB_PATH = os.path.join(_HERE, "csrc", "libpeppa_b200_measure.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "peppa_b200.h")
 
 PB2_BF16, PB2_F16, PB2_F32 = 0, 1, 2
@@ -28,34 +29,35 @@ SIGNATURES = {
     "pb2_launch_count": [],
     "pb2_sim_grid": [],
     "pb2_triplet_score": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i, _i, _p, _p],
-    "pb2_row_norms": [_p, _i64, _i, _i64, _p, _p, _p],
-    "pb2_pair_dot": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
-    "pb2_sim_diag": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
-    "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
-    "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i64, _i64, _p, _p],
+    "pb2_row_norms": [_p, _i, _i64, _i, _i64, _p, _p, _p],
+    "pb2_split_bf16": [_p, _i64, _i, _i64, _i, _p, _i64, _p],
+    "pb2_pair_dot": [_p, _p, _i, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
+    "pb2_sim_diag": [_p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _p],
+    "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p],
+    "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i64, _i64, _p, _p],
     "pb2_subset_rank": [_p, _i64, _p, _i, _i, _p, _p],
-    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],
+    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],
     "pb2_sim_lse_parts": [_i64],
-    "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _p, _p],
+    "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _p, _p],
     "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
     "pb2_sim_lse_col_parts": [_i64],
-    "pb2_sim_lse_both": [_p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _f, _p, _p, _p],
+    "pb2_sim_lse_both": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _f, _p, _p, _p],
     "pb2_lse_merge_const": [_p, _i, _i64, _f, _p, _i, _p],
     "pb2_lse_combine": [_p, _i, _i64, _p, _p],
-    "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i64, _i64, _f, _p, _i64, _p],
+    "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_grad_gemm": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p],
     "pb2_grad_gemm_workspace": [],
     "pb2_grad_gemm_ws": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p, _i64, _p],
     "pb2_grad_gemm_dual": [_p, _i, _i64, _i64, _i64, _p, _p, _i, _i, _i64, _i64, _f, _p, _p, _i64, _i64, _p],
-    "pb2_hinge_finish": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
-    "pb2_hinge_prep": [_p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
-    "pb2_hinge_finish2": [_p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
-    "pb2_hinge_step_workspace": [_i64, _i],
-    "pb2_hinge_step": [_p, _p, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],
-    "pb2_rows_scale_f16": [_p, _p, _i64, _i, _i64, _p, _i64, _p],
+    "pb2_hinge_finish": [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
+    "pb2_hinge_prep": [_p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    "pb2_hinge_finish2": [_p, _p, _p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
+    "pb2_hinge_step_workspace": [_i64, _i, _i],
+    "pb2_hinge_step": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],
+    "pb2_rows_scale_f16": [_p, _i, _p, _i64, _i, _i64, _p, _i64, _p],
     "pb2_scale_pair": [_p, _p, _i64, _i, _p, _p, _p, _p],
-    "pb2_milnce_finish": [_p, _i64, _p, _i64, _i, _i64, _f, _p, _p, _i64, _p],
-    "pb2_milnce_finish_k": [_p, _i64, _p, _p, _i64, _i, _i, _i, _i64, _f, _p, _p, _i64, _p],
+    "pb2_milnce_finish": [_p, _i64, _p, _i, _i64, _i, _i64, _f, _p, _p, _i64, _p],
+    "pb2_milnce_finish_k": [_p, _i64, _p, _i, _p, _i64, _i, _i, _i, _i64, _f, _p, _p, _i64, _p],
     "pb2_project_normalize": [_p, _p, _p, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p],
     "pb2_sum_partials": [_p, _i, _f, _p, _p],
     "pb2_hinge_loss_terms": [_p, _i, _p, _p, _i64, _f, _f, _p, _i, _p],
@@ -64,7 +66,8 @@ SIGNATURES = {
 }
 _RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64,
             "pb2_grad_gemm_workspace": C.c_int64}
-# test hooks, not part of the public header
+# selectors / knock-outs of the MEASUREMENT build only (libpeppa_b200_measure.so, -DPB2_MEASURE): not in the public
+# header and not exported by the product library
 _DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_gg_pair": [_i], "pb2_debug_proj_variant": [_i], "pb2_debug_gg_units": [_i], "pb2_debug_sim_pair": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 
 _lib = None
@@ -86,13 +89,39 @@ def lib():
         raise RuntimeError(
             f"peppa_b200: native library not built ({LIB_PATH} missing). Run `python -m peppa_b200.build` "
             "(or __graft_entry__.build()). There is no CPU fallback.")
-    handle = C.CDLL(LIB_PATH)
-    for name, args in {**SIGNATURES, **_DEBUG}.items():
+    _lib = _bind(C.CDLL(LIB_PATH), SIGNATURES)
+    return _lib
+
+
+def _bind(handle, table):
+    for name, args in table.items():
         fn = getattr(handle, name)  # AttributeError if the export is missing
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
-    _lib = handle
     return handle
+
+
+_measure = None
+
+
+class measurement_library:
+    """``with measurement_library() as lib:`` routes every ``lib()`` call of this process through the measurement
+    build (same kernels plus the ``pb2_debug_*`` selectors) for the duration of the block.  For tools/ and the
+    variant tests only; the product path never enters it."""
+
+    def __enter__(self):
+        global _lib, _measure
+        if _measure is None:
+            if not os.path.exists(MEASURE_LIB_PATH):
+                raise RuntimeError(f"peppa_b200: measurement library not built ({MEASURE_LIB_PATH}); run `python -m peppa_b200.build`")
+            _measure = _bind(C.CDLL(MEASURE_LIB_PATH), {**SIGNATURES, **_DEBUG})
+        self._saved = lib()
+        _lib = _measure
+        return _measure
+
+    def __exit__(self, *a):
+        global _lib
+        _lib = self._saved
 
 
 class Pb2Error(RuntimeError):
@@ -103,3 +132,8 @@ def check(status: int, what: str = ""):
     if status != 0:
         msg = lib().pb2_last_error()
         raise Pb2Error(f"peppa_b200 {what} failed (status {status}): {msg.decode() if msg else ''}")
+
+
+def use_measurement_library():
+    """Switch this process to the measurement build for good (tools/ scripts call this first)."""
+    return measurement_library().__enter__()

@@ -1,8 +1,10 @@
-"""Build the C-ABI shared library (and the stand-alone self-test) in-tree with nvcc for sm_100a.
+"""Build the C-ABI shared library in-tree with nvcc for sm_100a.
 
-``python -m peppa_b200.build`` or ``peppa_b200.build.build()``.  The outputs
-(``peppa_b200/csrc/libpeppa_b200.so``, ``peppa_b200/csrc/pb2_selftest``) are git-ignored but travel
-to the GPU box with the repo snapshot.  nvcc cross-compiles without a GPU.
+``python -m peppa_b200.build`` or ``peppa_b200.build.build()``.  Two libraries come out of the same sources:
+``peppa_b200/csrc/libpeppa_b200.so`` (the product: no debug exports, no mutable global state) and
+``peppa_b200/csrc/libpeppa_b200_measure.so`` (``-DPB2_MEASURE``: the ``pb2_debug_*`` tile-shape / cluster-variant
+selectors and knock-out switches used by ``tools/`` and the variant tests).  Both are git-ignored but travel to the
+GPU box with the repo snapshot.  nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
@@ -19,7 +21,8 @@ ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libpeppa_b200.so")
-SELFTEST = os.path.join(CSRC, "pb2_selftest")
+OBJ_MEASURE = os.path.join(CSRC, "build_measure")
+LIB_MEASURE = os.path.join(CSRC, "libpeppa_b200_measure.so")
 
 LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu"]
 NVCC_FLAGS = [
@@ -36,9 +39,9 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def _digest(paths) -> str:
+def _digest(paths, extra=()) -> str:
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra)).encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode())
@@ -46,17 +49,17 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+def _compile(src: str, verbose: bool, objdir: str = OBJ, extra=()) -> str:
+    obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "peppa_b200.h"))
     stamp = obj + ".sha"
-    want = _digest([os.path.join(CSRC, src)] + headers)
+    want = _digest([os.path.join(CSRC, src)] + headers, extra)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
         return obj
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(OBJ, os.path.splitext(src)[0] + ".log")
+    log = os.path.join(objdir, os.path.splitext(src)[0] + ".log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
@@ -69,20 +72,26 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
-def build(verbose: bool = False, selftest: bool = True) -> str:
+def _link(lib: str, objs) -> None:
+    newest = max(os.path.getmtime(o) for o in objs)
+    if not os.path.exists(lib) or os.path.getmtime(lib) < newest:
+        tmp = lib + f".tmp{os.getpid()}"
+        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs], check=True)
+        os.replace(tmp, lib)        # atomic: another rank may be dlopen()ing the old file
+
+
+def build(verbose: bool = False, measure: bool = True) -> str:
+    """Compile (only what changed: per-source hashes) and link; returns the product library's path."""
+    jobs = [(s, OBJ, ()) for s in LIB_SOURCES]
+    if measure:
+        jobs += [(s, OBJ_MEASURE, ("-DPB2_MEASURE",)) for s in LIB_SOURCES]
     os.makedirs(OBJ, exist_ok=True)
-    srcs = list(LIB_SOURCES) + (["selftest.cu"] if selftest and os.path.exists(os.path.join(CSRC, "selftest.cu")) else [])
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = dict(zip(srcs, ex.map(lambda s: _compile(s, verbose), srcs)))
-    lib_objs = [objs[s] for s in LIB_SOURCES]
-    newest = max(os.path.getmtime(o) for o in lib_objs)
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *lib_objs]
-        subprocess.run(cmd, check=True)
-    if "selftest.cu" in objs:
-        if not os.path.exists(SELFTEST) or os.path.getmtime(SELFTEST) < max(newest, os.path.getmtime(objs["selftest.cu"])):
-            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-o", SELFTEST, objs["selftest.cu"], *lib_objs]
-            subprocess.run(cmd, check=True)
+    os.makedirs(OBJ_MEASURE, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        objs = list(ex.map(lambda j: _compile(j[0], verbose, j[1], j[2]), jobs))
+    _link(LIB, objs[:len(LIB_SOURCES)])
+    if measure:
+        _link(LIB_MEASURE, objs[len(LIB_SOURCES):])
     return LIB
 
 

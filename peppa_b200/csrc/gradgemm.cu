@@ -249,11 +249,17 @@ __device__ __forceinline__ void gg_body(const CUtensorMap& tm_g, const CUtensorM
             const uint32_t peer = (uint32_t)block + (uint32_t)(a.n_cb * kCtas);  // same tile slot, next group
             if (fold) {
                 if (lane == 0) {
+                    // The peer is a CTA of this grid that may not be resident yet when another kernel (an NCCL
+                    // reduction overlapped on a second stream, another tenant) holds SMs: being late is legal, so
+                    // this wait backs off instead of trapping after the couple of seconds a lost mbarrier arrive
+                    // gets.  Only a wait of minutes -- a protocol bug -- ends the kernel rather than hang the GPU.
                     const long long t0 = clock64();
+                    uint32_t ns = 100;
                     while (ld_acquire_u32(a.flags + peer) < (uint32_t)kEpiWarps) {
-                        __nanosleep(200);
-                        if (clock64() - t0 > PB2_WAIT_TIMEOUT_CYCLES) {
-                            printf("pb2: grad_gemm stream-K flag wait timed out (block %d)\n", block);
+                        __nanosleep(ns);
+                        if (ns < 8000) ns <<= 1;
+                        if (clock64() - t0 > 64 * PB2_WAIT_TIMEOUT_CYCLES) {
+                            printf("pb2: grad_gemm stream-K flag wait gave up after minutes (block %d)\n", block);
                             __trap();
                         }
                     }
@@ -352,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     else gg_body<true, BN, 1>(tm_g1, tm_z1, a1, (int)blockIdx.x - n0, (int)gridDim.x - n0);
 }
 
-static uint32_t g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
-static int g_units_cap = 0;
+PB2_KNOB_U32 g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
+PB2_KNOB g_units_cap = 0;
 
 constexpr int64_t kFlagBytes = 1024;  // flags of up to 256 CTAs, then the parked accumulators
 static int64_t workspace_bytes() { return kFlagBytes + (int64_t)sm_count() * BM * 512 * 4; }
@@ -415,12 +421,9 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
     }
     auto kern = grad_gemm_kernel<kTranspose, BN, kCtas>;
     constexpr int smem = Smem<BN, kCtas>::kTotal;
-    static bool configured = false;
-    if (!configured) {
-        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "grad_gemm");
-        if (rc) return rc;
-        configured = true;
-    }
+    static PerDeviceOnce configured;  // per instantiation and device
+    rc = ensure_dynamic_smem(configured, kern, smem, "grad_gemm");
+    if (rc) return rc;
     const int n_units = a.n_groups > 0 ? a.n_groups * a.n_cb : (int)std::min<int64_t>(a.n_tiles, units);
     rc = check_cuda(launch_ex(kern, (unsigned)(n_units * kCtas), (unsigned)kThreads, (size_t)smem, st, kCtas, tg, tz, a),
                     "grad_gemm launch");
@@ -441,12 +444,9 @@ static int launch_dual(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols,
     if (rc) return rc;
     auto kern = grad_gemm_dual_kernel<BN>;
     constexpr int smem = Smem<BN, 1>::kTotal;
-    static bool configured = false;
-    if (!configured) {
-        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "grad_gemm_dual");
-        if (rc) return rc;
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    rc = ensure_dynamic_smem(configured, kern, smem, "grad_gemm_dual");
+    if (rc) return rc;
     const int n0 = (int)a0.n_tiles, n1 = (int)a1.n_tiles;
     rc = check_cuda(launch_ex(kern, (unsigned)(n0 + n1), (unsigned)kThreads, (size_t)smem, st, 1, tg0, tz0, tg1, tz1, a0, a1, n0),
                     "grad_gemm_dual launch");
@@ -454,13 +454,14 @@ static int launch_dual(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols,
     return check_launch("grad_gemm_dual");
 }
 
-static int g_pair_mode = -1;  // test hook (pb2_debug_gg_pair): -1 = automatic, 0 = never, 1 = whenever legal
+PB2_KNOB g_pair_mode = -1;  // measurement build (pb2_debug_gg_pair): -1 = automatic, 0 = never, 1 = whenever legal
 
 }  // namespace gg
 }  // namespace pb2
 
 using namespace pb2;
 
+#ifdef PB2_MEASURE
 extern "C" int pb2_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep) {
     gg::g_mn_lbo = lbo;
     gg::g_mn_sbo = sbo;
@@ -476,6 +477,7 @@ extern "C" int pb2_debug_gg_pair(int mode) {
     gg::g_pair_mode = mode;
     return PB2_OK;
 }
+#endif
 
 extern "C" int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
                                   const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <utility>
 
 namespace pb2 {
@@ -15,10 +16,45 @@ int check_launch(const char* what);                 // cudaGetLastError -> PB2_O
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();                                     // SMs of the current device (cached per device)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of (kernel, DEVICE): a process that launches on
+// cuda:0 and then on cuda:1 has to opt in on both.  One bit per device, lock-free; a lost race only repeats the
+// (idempotent) attribute call.  Devices >= 64 set the attribute on every launch.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> bits{0};
+    static int device() {
+        int dev = 0;
+        return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+    }
+    bool done(int dev) const { return dev >= 0 && dev < 64 && ((bits.load(std::memory_order_acquire) >> dev) & 1u); }
+    void mark(int dev) {
+        if (dev >= 0 && dev < 64) bits.fetch_or(1ull << dev, std::memory_order_release);
+    }
+};
+// opt a kernel in to `smem` bytes of dynamic shared memory on the current device (once per device and call site)
+template <class K>
+inline int ensure_dynamic_smem(PerDeviceOnce& once, K kern, int smem, const char* what) {
+    const int dev = PerDeviceOnce::device();
+    if (once.done(dev)) return 0;
+    const int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
+    if (rc == 0) once.mark(dev);
+    return rc;
+}
+
 // 2-D row-major tensor map with 128-byte swizzle: inner dimension `cols` (contiguous), outer
 // `rows`, row pitch `ld_bytes`; box = box_cols x box_rows elements; out-of-bounds reads give 0.
 int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_bytes, uint32_t box_rows, uint32_t box_cols);
+
+// Measurement-only switches (tile-shape / cluster-variant selectors, wrong-result knock-outs) exist only in the
+// measurement build (-DPB2_MEASURE -> libpeppa_b200_measure.so, used by tools/ and the variant tests).  In the
+// product library they are compile-time constants: no pb2_debug_* export, no mutable global state.
+#ifdef PB2_MEASURE
+#define PB2_KNOB static int
+#define PB2_KNOB_U32 static uint32_t
+#else
+#define PB2_KNOB static constexpr int
+#define PB2_KNOB_U32 static constexpr uint32_t
+#endif
 
 // Launch helper: optional thread-block cluster, and -- while a PdlScope is alive on this thread -- the
 // programmatic-stream-serialization attribute (programmatic dependent launch): the kernel may start while its

@@ -497,17 +497,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 // kernel.  Measured for 2^20 rows 512 -> 512: row-split 0.659 ms, column-split 0.681 ms (0.937 ms with a
 // release-arrive + cluster fence instead of st.async: MEMBAR.GPU + CCTL.IVALL twice per tile).  The overlap it buys
 // is spent on the two cross-CTA exchanges per tile, so the simpler kernel stays the default.
-static int g_variant = 0;
+PB2_KNOB g_variant = 0;
 
 }  // namespace proj
 }  // namespace pb2
 
 using namespace pb2;
 
+#ifdef PB2_MEASURE
 extern "C" int pb2_debug_proj_variant(int v) {
     proj::g_variant = v;
     return PB2_OK;
 }
+#endif
 
 extern "C" int pb2_project_normalize(const void* x, const void* w, const float* bias, int64_t rows, int n_in, int n_out,
                                      int64_t ldx, int64_t ldw, float eps, void* out, int64_t ld_out, float* rinv,
@@ -535,26 +537,16 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
     a.eps = eps;
     a.rinv = rinv;
     a.norm = norm;
-    static bool configured = false;
-    if (!configured) {
-        rc = check_cuda(cudaFuncSetAttribute(proj::project_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             proj::kSmem),
-                        "project_normalize");
-        if (rc) return rc;
-        configured = true;
-    }
+    static PerDeviceOnce configured;
+    rc = ensure_dynamic_smem(configured, proj::project_normalize_kernel, proj::kSmem, "project_normalize");
+    if (rc) return rc;
     if (n_out % 128 == 0 && proj::g_variant == 2) {  // column-split pairs: two TMEM stages, epilogue overlaps the MMA
         CUtensorMap tx2;
         rc = make_tmap_2d(&tx2, x, 2, (uint64_t)rows, (uint64_t)n_in, (uint64_t)ldx * 2, 64, proj::BK);
         if (rc) return rc;
-        static bool configured2 = false;
-        if (!configured2) {
-            rc = check_cuda(cudaFuncSetAttribute(proj::project_normalize_split_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, proj::kS_Smem),
-                            "project_normalize");
-            if (rc) return rc;
-            configured2 = true;
-        }
+        static PerDeviceOnce configured2;
+        rc = ensure_dynamic_smem(configured2, proj::project_normalize_split_kernel, proj::kS_Smem, "project_normalize");
+        if (rc) return rc;
         const int64_t tiles = (rows + proj::BM - 1) / proj::BM;
         const int grid2 = 2 * (int)std::min<int64_t>(tiles, sm_count() / 2);
         rc = check_cuda(launch_ex(proj::project_normalize_split_kernel, (unsigned)grid2, (unsigned)proj::kThreads,

@@ -24,19 +24,47 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
     f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
+// Eight consecutive row elements as fp32, for the three input dtypes the reference's callers use (fp32 tensors,
+// fp16 under Lightning's `precision: 16`, bf16): the row-wise kernels read the TRUE input values -- only the tensor-
+// core operands are 16-bit (an fp32 matrix goes there as a split-bf16 pair, pb2_split_bf16).
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+    load8(p, f);
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(h[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+    }
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // ---------------------------------------------------------------------------------- row norms
-__global__ void __launch_bounds__(256) row_norms_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, int dim,
+template <typename T>
+__global__ void __launch_bounds__(256) row_norms_kernel(const T* __restrict__ x, int64_t n, int dim,
                                                         int64_t ld, float* __restrict__ rinv,
                                                         float* __restrict__ norm) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t r = warp; r < n; r += nwarps) {
-        const __nv_bfloat16* row = x + r * ld;
+        const T* row = x + r * ld;
         float ss = 0.f;
         for (int k = lane * 8; k < dim; k += 256) {
             float f[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(row + k), f);
+            load8(row + k, f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
         }
@@ -53,8 +81,9 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const __nv_bfloat16* __r
 // out = fp16(x * rinv): the B operand of the gradient GEMMs.  tcgen05 kind::f16 cannot mix an fp16
 // A with a bf16 B, so the gradient matrix (fp16, exact small integers for the hinge loss) is paired
 // with an fp16 copy of the normalised embeddings (|.| <= 1, 11-bit significand: rounding 2^-12).
+template <typename T>
 __global__ void __launch_bounds__(256)
-    rows_scale_f16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ rinv, int64_t n, int dim,
+    rows_scale_f16_kernel(const T* __restrict__ x, const float* __restrict__ rinv, int64_t n, int dim,
                           int64_t ld, __half* __restrict__ out, int64_t ld_out) {
     const int vec_per_row = dim / 8;
     const int64_t total = n * vec_per_row;
@@ -62,7 +91,7 @@ __global__ void __launch_bounds__(256)
         const int64_t r = i / vec_per_row;
         const int d = (int)(i % vec_per_row) * 8;
         float f[8];
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(x + r * ld + d), f);
+        load8(x + r * ld + d, f);
         const float s = rinv ? rinv[r] : 1.f;
         __half2 h[4];
 #pragma unroll
@@ -71,29 +100,38 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// y0 = x0 * c, y1 = x1 * c with c read on the device: the backward of a scalar loss whose gradients were produced in
-// the forward (autograd hands grad_output over as a device scalar).  One launch for both gradients, 16-byte vectors.
+// y0 = T(x0 * c), y1 = T(x1 * c) with c read on the device: the backward of a scalar loss whose gradients were
+// produced in the forward (autograd hands grad_output over as a device scalar).  The saved gradients are fp32 and
+// the product is rounded to the inputs' dtype LAST, like the reference's autograd under AMP: with a GradScaler
+// (grad_output = 65536) an fp16 gradient of ~1e-7 must not pass through fp16 before the scale is applied.
+// One launch for both gradients, 16-byte stores.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    scale_pair_kernel(const T* __restrict__ x0, const T* __restrict__ x1, int64_t n_vec, const float* __restrict__ coef,
+    scale_pair_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int64_t n_vec, const float* __restrict__ coef,
                       T* __restrict__ y0, T* __restrict__ y1) {
     constexpr int kPer = 16 / sizeof(T);
     const float c = *coef;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const bool second = i >= n_vec;
         const int64_t k = second ? i - n_vec : i;
-        const uint4 raw = *reinterpret_cast<const uint4*>((second ? x1 : x0) + k * kPer);
+        const float* src = (second ? x1 : x0) + k * kPer;
         T v[kPer];
-        *reinterpret_cast<uint4*>(v) = raw;
 #pragma unroll
-        for (int e = 0; e < kPer; ++e) v[e] = (T)((float)v[e] * c);
+        for (int e = 0; e < kPer; e += 4) {
+            const float4 f = *reinterpret_cast<const float4*>(src + e);
+            v[e] = (T)(f.x * c);
+            v[e + 1] = (T)(f.y * c);
+            v[e + 2] = (T)(f.z * c);
+            v[e + 3] = (T)(f.w * c);
+        }
         *reinterpret_cast<uint4*>((second ? y1 : y0) + k * kPer) = *reinterpret_cast<const uint4*>(v);
     }
 }
 
 // ----------------------------------------------------------------------------------- pair dot
+template <typename T>
 __global__ void __launch_bounds__(256)
-    pair_dot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+    pair_dot_kernel(const T* __restrict__ x, const T* __restrict__ y,
                     const int64_t* __restrict__ ix, const int64_t* __restrict__ iy, const float* __restrict__ rinv_x,
                     const float* __restrict__ rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy,
                     float* __restrict__ out, float* __restrict__ dist_out, float* __restrict__ thr_out) {
@@ -102,13 +140,13 @@ __global__ void __launch_bounds__(256)
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t k = warp; k < n; k += nwarps) {
         const int64_t rx = ix ? ix[k] : k, ry = iy ? iy[k] : k;
-        const __nv_bfloat16* px = x + rx * ldx;
-        const __nv_bfloat16* py = y + ry * ldy;
+        const T* px = x + rx * ldx;
+        const T* py = y + ry * ldy;
         float acc = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float a[8], b[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(px + d), a);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(py + d), b);
+            load8(px + d, a);
+            load8(py + d, b);
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
         }
@@ -257,16 +295,56 @@ __global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------- split-bf16 operands (fp32 inputs)
+// An fp32 matrix reaches the bf16 tensor cores as x = hi + lo (hi = bf16(x), lo = bf16(x - hi): 16 significand bits),
+// and  <x, y> ~= <hi_x, hi_y> + <lo_x, hi_y> + <hi_x, lo_y>  is ONE GEMM of contraction length 3 D over the
+// concatenated rows  X' = [hi | lo | hi]  (side 0)  and  Y' = [hi | hi | lo]  (side 1): no kernel of sim.cu changes,
+// the fp32 accumulator sums the three products.  The dropped lo*lo term and lo's own rounding are ~2^-18 per
+// product, i.e. ~2e-7 absolute on a cosine of 512-d unit vectors -- below the 1e-6 tie window of the rank parity bar.
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __nv_bfloat162 h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        const float2 hf = __bfloat1622float2(h[e]);
+        l[e] = __floats2bfloat162_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+    }
+    hi = *reinterpret_cast<const uint4*>(h);
+    lo = *reinterpret_cast<const uint4*>(l);
+}
+// out row = [hi | lo | hi] (side 0) or [hi | hi | lo] (side 1), each part `dim` wide
+__device__ __forceinline__ void store_split(__nv_bfloat16* out_row, int dim, int d, int side, const uint4& hi, const uint4& lo) {
+    *reinterpret_cast<uint4*>(out_row + d) = hi;
+    *reinterpret_cast<uint4*>(out_row + dim + d) = side ? hi : lo;
+    *reinterpret_cast<uint4*>(out_row + 2 * dim + d) = side ? lo : hi;
+}
+__global__ void __launch_bounds__(256)
+    split_bf16_kernel(const float* __restrict__ x, int64_t n, int dim, int64_t ld, int side, __nv_bfloat16* __restrict__ out,
+                      int64_t ld_out) {
+    const int vec_per_row = dim / 8;
+    const int64_t total = n * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int d = (int)(i % vec_per_row) * 8;
+        float f[8];
+        load8(x + r * ld + d, f);
+        uint4 hi, lo;
+        split8(f, hi, lo);
+        store_split(out + r * ld_out, dim, d, side, hi, lo);
+    }
+}
+
 // ------------------------------------------------------------------- fused small-batch path
 // One launch before the similarity pass of a training step (pig/loss.py:33-39 at batch size ~1k,
 // where launches dominate): per row i norms of V_i and A_i, the diagonal score, the fp16 normalised
 // copies for the gradient GEMMs, and zeroing of the count / partial buffers.
+template <typename T>
 __global__ void __launch_bounds__(256)
-    hinge_prep_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ a, int64_t n, int dim,
+    hinge_prep_kernel(const T* __restrict__ v, const T* __restrict__ a, int64_t n, int dim,
                       int64_t ldv, int64_t lda, float* __restrict__ rinv_v, float* __restrict__ rinv_a,
                       float* __restrict__ diag, __half* __restrict__ vh, __half* __restrict__ ah,
                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
-                      int n_partials) {
+                      int n_partials, __nv_bfloat16* __restrict__ vx, __nv_bfloat16* __restrict__ ax) {
     pdl_launch_dependents();
     pdl_wait();  // the workspace may still be read by the previous step's kernels
     const int lane = threadIdx.x & 31;
@@ -275,13 +353,13 @@ __global__ void __launch_bounds__(256)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_partials; i += (int64_t)gridDim.x * blockDim.x)
         loss_partial[i] = 0.f;
     for (int64_t r = warp; r < n; r += nwarps) {
-        const __nv_bfloat16* vr = v + r * ldv;
-        const __nv_bfloat16* ar = a + r * lda;
+        const T* vr = v + r * ldv;
+        const T* ar = a + r * lda;
         float sv = 0.f, sa = 0.f, dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(vr + d), x);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(ar + d), y);
+            load8(vr + d, x);
+            load8(ar + d, y);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 sv = fmaf(x[e], x[e], sv);
@@ -302,8 +380,8 @@ __global__ void __launch_bounds__(256)
         }
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(vr + d), x);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(ar + d), y);
+            load8(vr + d, x);
+            load8(ar + d, y);
             __half2 hx[4], hy[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -312,6 +390,13 @@ __global__ void __launch_bounds__(256)
             }
             *reinterpret_cast<uint4*>(vh + r * dim + d) = *reinterpret_cast<const uint4*>(hx);
             *reinterpret_cast<uint4*>(ah + r * dim + d) = *reinterpret_cast<const uint4*>(hy);
+            if (vx) {  // fp32 inputs: split-bf16 tensor-core operands [n, 3 dim] (S = V A^T: V is side 0, A side 1)
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                store_split(vx + r * 3 * dim, dim, d, 0, hi, lo);
+                split8(y, hi, lo);
+                store_split(ax + r * 3 * dim, dim, d, 1, hi, lo);
+            }
         }
     }
 }
@@ -341,10 +426,10 @@ __device__ __forceinline__ void store8<__half>(__half* dst, const float (&o)[8])
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
 }
 
-template <typename TOut>
+template <typename T, typename TOut>
 __global__ void __launch_bounds__(256)
     hinge_finish2_kernel(const float* __restrict__ p_v, const float* __restrict__ p_a,
-                         const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ a, int64_t n, int dim,
+                         const T* __restrict__ v, const T* __restrict__ a, int64_t n, int dim,
                          int64_t ldv, int64_t lda, const float* __restrict__ rinv_v, const float* __restrict__ rinv_a,
                          const float* __restrict__ diag, const int32_t* __restrict__ row_cnt,
                          const int32_t* __restrict__ col_cnt, const float* __restrict__ loss_partial, int n_partials,
@@ -359,8 +444,8 @@ __global__ void __launch_bounds__(256)
         const bool is_v = rr < n;
         const int64_t r = is_v ? rr : rr - n;
         const float* pr = (is_v ? p_v : p_a) + r * dim;
-        const __nv_bfloat16* xr = is_v ? v + r * ldv : a + r * lda;
-        const __nv_bfloat16* yr = is_v ? a + r * lda : v + r * ldv;
+        const T* xr = is_v ? v + r * ldv : a + r * lda;
+        const T* yr = is_v ? a + r * lda : v + r * ldv;
         const float rx = is_v ? rinv_v[r] : rinv_a[r];
         const float ry = is_v ? rinv_a[r] : rinv_v[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * ry;
@@ -368,8 +453,8 @@ __global__ void __launch_bounds__(256)
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), x);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), y);
+            load8(xr + d, x);
+            load8(yr + d, y);
             const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
             const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -379,8 +464,8 @@ __global__ void __launch_bounds__(256)
         dot = warp_sum(dot);
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8], o[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), x);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), y);
+            load8(xr + d, x);
+            load8(yr + d, y);
             const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
             const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -424,9 +509,10 @@ __global__ void __launch_bounds__(256)
 
 // ------------------------------------------------------------------------------ hinge finish
 // One warp per row; the row (p, x, y) is held in registers for dim <= 1024, else re-read.
+template <typename T>
 __global__ void __launch_bounds__(256)
-    hinge_finish_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ x,
-                        const __nv_bfloat16* __restrict__ y, const float* __restrict__ rinv_x,
+    hinge_finish_kernel(const float* __restrict__ p, int64_t ld_p, const T* __restrict__ x,
+                        const T* __restrict__ y, const float* __restrict__ rinv_x,
                         const float* __restrict__ rinv_y,
                         const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ col_cnt, int64_t rows,
                         int dim, int64_t ldx, int64_t ldy, float coef_host, const float* __restrict__ coef_dev,
@@ -439,13 +525,13 @@ __global__ void __launch_bounds__(256)
         const float rx = rinv_x[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * rinv_y[r];
         const float* pr = p + r * ld_p;
-        const __nv_bfloat16* xr = x + r * ldx;
-        const __nv_bfloat16* yr = y + r * ldy;
+        const T* xr = x + r * ldx;
+        const T* yr = y + r * ldy;
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float a[8], b[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), a);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), b);
+            load8(xr + d, a);
+            load8(yr + d, b);
             const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
             const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -455,8 +541,8 @@ __global__ void __launch_bounds__(256)
         dot = warp_sum(dot);
         for (int d = lane * 8; d < dim; d += 256) {
             float a[8], b[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(xr + d), a);
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(yr + d), b);
+            load8(xr + d, a);
+            load8(yr + d, b);
             const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
             const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
             const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
@@ -473,8 +559,9 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-    milnce_finish_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ y, int64_t rows,
+    milnce_finish_kernel(const float* __restrict__ p, int64_t ld_p, const T* __restrict__ y, int64_t rows,
                          int dim, int64_t ldy, float coef_host, const float* __restrict__ coef_dev,
                          float* __restrict__ grad, int64_t ld_grad) {
     const float coef = coef_host * (coef_dev ? coef_dev[0] : 1.f);
@@ -484,7 +571,7 @@ __global__ void __launch_bounds__(256)
         const int64_t r = i / vec_per_row;
         const int d = (int)(i % vec_per_row) * 8;
         float b[8];
-        bf16x8_to_f32(*reinterpret_cast<const uint4*>(y + r * ldy + d), b);
+        load8(y + r * ldy + d, b);
         const float4 p0 = *reinterpret_cast<const float4*>(p + r * ld_p + d);
         const float4 p1 = *reinterpret_cast<const float4*>(p + r * ld_p + d + 4);
         const float s = 1.0f / 8192.0f;
@@ -499,8 +586,9 @@ __global__ void __launch_bounds__(256)
 // MIL-NCE with K candidates per clip (pig/loss.py:19-25 views x as [N, N, K]): the positive term of row r
 // is sum_k w[r * group + k] * y[(r * group + k) / y_div] with w = softmax_k of the K paired logits.
 //   video side: group = K, y_div = 1 (the clip's K audio rows);  audio side: group = 1, y_div = K (its video).
+template <typename T>
 __global__ void __launch_bounds__(256)
-    milnce_finish_k_kernel(const float* __restrict__ p, int64_t ld_p, const __nv_bfloat16* __restrict__ y,
+    milnce_finish_k_kernel(const float* __restrict__ p, int64_t ld_p, const T* __restrict__ y,
                            const float* __restrict__ w, int64_t rows, int group, int y_div, int dim, int64_t ldy,
                            float coef_host, const float* __restrict__ coef_dev, float* __restrict__ grad,
                            int64_t ld_grad) {
@@ -514,7 +602,7 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < group; ++k) {
             const int64_t c = r * group + k;
             float b[8];
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(y + (c / y_div) * ldy + d), b);
+            load8(y + (c / y_div) * ldy + d, b);
             const float wk = w[c];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaf(wk, b[j], acc[j]);
@@ -625,59 +713,87 @@ using namespace pb2;
 static bool vec_ok(const void* p, int64_t ld_elems, int elem_bytes) {
     return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld_elems * elem_bytes) % 16 == 0;
 }
+static int elem_bytes(int dtype) { return dtype == PB2_F32 ? 4 : ((dtype == PB2_BF16 || dtype == PB2_F16) ? 2 : 0); }
+// run `...` with T bound to the element type of `dtype` (bf16 / fp16 / fp32 rows)
+#define PB2_ROWS_DISPATCH(dtype, ...)                       \
+    do {                                                    \
+        if ((dtype) == PB2_BF16) {                          \
+            using T = __nv_bfloat16;                        \
+            __VA_ARGS__;                                    \
+        } else if ((dtype) == PB2_F16) {                    \
+            using T = __half;                               \
+            __VA_ARGS__;                                    \
+        } else {                                            \
+            using T = float;                                \
+            __VA_ARGS__;                                    \
+        }                                                   \
+    } while (0)
 
-extern "C" int pb2_row_norms(const void* x, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream) {
+extern "C" int pb2_row_norms(const void* x, int dtype, int64_t n, int dim, int64_t ld, float* rinv, float* norm,
+                             void* stream) {
     if (n <= 0) return PB2_OK;
-    if (!x || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 2))
-        return set_error(PB2_ERR_ARG, "row_norms: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
-    row_norms_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, n, dim, ld, rinv,
-                                                                         norm);
+    const int es = elem_bytes(dtype);
+    if (!x || !es || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, es))
+        return set_error(PB2_ERR_ARG, "row_norms: need bf16 / fp16 / fp32 rows, dim %% 8 == 0, 16-byte aligned");
+    PB2_ROWS_DISPATCH(dtype, row_norms_kernel<T><<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>((const T*)x, n, dim, ld,
+                                                                                                    rinv, norm));
     return check_launch("row_norms");
 }
 
-extern "C" int pb2_rows_scale_f16(const void* x, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
-                                  int64_t ld_out, void* stream) {
+extern "C" int pb2_split_bf16(const float* x, int64_t n, int dim, int64_t ld, int side, void* out, int64_t ld_out,
+                              void* stream) {
     if (n <= 0) return PB2_OK;
-    if (!x || !out || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 2) || !vec_ok(out, ld_out, 2))
-        return set_error(PB2_ERR_ARG, "rows_scale_f16: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
+    if (!x || !out || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 4) || !vec_ok(out, ld_out, 2) || ld_out < 3 * (int64_t)dim ||
+        (side != 0 && side != 1))
+        return set_error(PB2_ERR_ARG, "split_bf16: need fp32 rows, dim %% 8 == 0, 16-byte aligned, ld_out >= 3 dim, side 0 / 1");
     const int64_t total = n * (dim / 8);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
-    rows_scale_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rinv, n, dim, ld,
-                                                                  (__half*)out, ld_out);
+    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, dim, ld, side, (__nv_bfloat16*)out, ld_out);
+    return check_launch("split_bf16");
+}
+
+extern "C" int pb2_rows_scale_f16(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
+                                  int64_t ld_out, void* stream) {
+    if (n <= 0) return PB2_OK;
+    const int es = elem_bytes(dtype);
+    if (!x || !out || !es || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, es) || !vec_ok(out, ld_out, 2))
+        return set_error(PB2_ERR_ARG, "rows_scale_f16: need bf16 / fp16 / fp32 rows, dim %% 8 == 0, 16-byte aligned");
+    const int64_t total = n * (dim / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    PB2_ROWS_DISPATCH(dtype, rows_scale_f16_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, rinv, n, dim, ld,
+                                                                                            (__half*)out, ld_out));
     return check_launch("rows_scale_f16");
 }
 
-extern "C" int pb2_scale_pair(const void* x0, const void* x1, int64_t n_elems, int dtype, const float* coef,
+extern "C" int pb2_scale_pair(const float* x0, const float* x1, int64_t n_elems, int out_dtype, const float* coef,
                               void* y0, void* y1, void* stream) {
     if (n_elems <= 0) return PB2_OK;
-    const int es = dtype == PB2_F32 ? 4 : 2;
+    const int es = out_dtype == PB2_F32 ? 4 : 2;
     auto ok = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (!ok(x0) || !ok(x1) || !ok(y0) || !ok(y1) || !coef || (n_elems * es) % 16 != 0 ||
-        (dtype != PB2_F32 && dtype != PB2_BF16 && dtype != PB2_F16))
-        return set_error(PB2_ERR_ARG, "scale_pair: need 16-byte aligned bf16 / fp16 / fp32 arrays of whole 16-byte vectors");
+        (out_dtype != PB2_F32 && out_dtype != PB2_BF16 && out_dtype != PB2_F16))
+        return set_error(PB2_ERR_ARG, "scale_pair: need 16-byte aligned fp32 inputs and bf16 / fp16 / fp32 outputs of whole 16-byte vectors");
     const int64_t n_vec = n_elems * es / 16;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((2 * n_vec + 255) / 256, (int64_t)sm_count() * 8));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == PB2_F32)
-        scale_pair_kernel<float><<<grid, 256, 0, st>>>((const float*)x0, (const float*)x1, n_vec, coef, (float*)y0, (float*)y1);
-    else if (dtype == PB2_BF16)
-        scale_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, n_vec, coef,
-                                                               (__nv_bfloat16*)y0, (__nv_bfloat16*)y1);
+    if (out_dtype == PB2_F32)
+        scale_pair_kernel<float><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (float*)y0, (float*)y1);
+    else if (out_dtype == PB2_BF16)
+        scale_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (__nv_bfloat16*)y0, (__nv_bfloat16*)y1);
     else
-        scale_pair_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x0, (const __half*)x1, n_vec, coef, (__half*)y0,
-                                                        (__half*)y1);
+        scale_pair_kernel<__half><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (__half*)y0, (__half*)y1);
     return check_launch("scale_pair");
 }
 
-extern "C" int pb2_pair_dot(const void* x, const void* y, const int64_t* ix, const int64_t* iy, const float* rinv_x,
-                            const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy, float* out,
-                            float* dist_out, float* thr_out, void* stream) {
+extern "C" int pb2_pair_dot(const void* x, const void* y, int dtype, const int64_t* ix, const int64_t* iy,
+                            const float* rinv_x, const float* rinv_y, int64_t n, int dim, int64_t ldx, int64_t ldy,
+                            float* out, float* dist_out, float* thr_out, void* stream) {
     if (n <= 0) return PB2_OK;
-    if (!x || !y || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2))
-        return set_error(PB2_ERR_ARG, "pair_dot: need bf16 rows, dim %% 8 == 0, 16-byte aligned");
-    pair_dot_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out,
-        thr_out);
+    const int es = elem_bytes(dtype);
+    if (!x || !y || !es || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ldx, es) || !vec_ok(y, ldy, es))
+        return set_error(PB2_ERR_ARG, "pair_dot: need bf16 / fp16 / fp32 rows, dim %% 8 == 0, 16-byte aligned");
+    PB2_ROWS_DISPATCH(dtype, pair_dot_kernel<T><<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)x, (const T*)y, ix, iy, rinv_x, rinv_y, n, dim, ldx, ldy, out, dist_out, thr_out));
     return check_launch("pair_dot");
 }
 
@@ -738,7 +854,7 @@ extern "C" int pb2_milnce_loss(const float* lse_row, const float* lse_col, const
     return check_launch("milnce_loss");
 }
 
-extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, const float* rinv_x,
+extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y, int dtype, const float* rinv_x,
                                 const float* rinv_y, const int32_t* row_cnt,
                                 const int32_t* col_cnt, int64_t rows, int dim, int64_t ldx, int64_t ldy,
                                 float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
@@ -746,31 +862,39 @@ extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, con
     if (rows <= 0) return PB2_OK;
     if (!p || !x || !y || !rinv_x || !rinv_y || !row_cnt || !col_cnt || !grad_x)
         return set_error(PB2_ERR_ARG, "hinge_finish: null");
-    if (dim % 8 != 0 || !vec_ok(x, ldx, 2) || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
-        return set_error(PB2_ERR_ARG, "hinge_finish: alignment");
-    hinge_finish_kernel<<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
-        p, ld_p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim,
-        ldx, ldy, coef_host, coef_dev, grad_x, ld_grad);
+    const int es = elem_bytes(dtype);
+    if (!es || dim % 8 != 0 || !vec_ok(x, ldx, es) || !vec_ok(y, ldy, es) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "hinge_finish: dtype / alignment");
+    PB2_ROWS_DISPATCH(dtype, hinge_finish_kernel<T><<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
+                                 p, ld_p, (const T*)x, (const T*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim, ldx, ldy,
+                                 coef_host, coef_dev, grad_x, ld_grad));
     return check_launch("hinge_finish");
 }
 
-extern "C" int pb2_hinge_prep(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
-                              float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
-                              float* loss_partial, int n_partials, void* stream) {
+extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda,
+                              float* rinv_v, float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt,
+                              int32_t* col_cnt, float* loss_partial, int n_partials, void* v_split, void* a_split,
+                              void* stream) {
     if (n <= 0) return PB2_OK;
     if (!v || !a || !rinv_v || !rinv_a || !diag || !vh || !ah || !row_cnt || !col_cnt || !loss_partial)
         return set_error(PB2_ERR_ARG, "hinge_prep: null");
-    if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(vh, dim, 2) || !vec_ok(ah, dim, 2))
-        return set_error(PB2_ERR_ARG, "hinge_prep: alignment");
-    int rc = check_cuda(launch_ex(hinge_prep_kernel, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream, 1,
-                                  (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag,
-                                  (__half*)vh, (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials),
-                        "hinge_prep");
+    const int es = elem_bytes(dtype);
+    if (!es || dim % 8 != 0 || !vec_ok(v, ldv, es) || !vec_ok(a, lda, es) || !vec_ok(vh, dim, 2) || !vec_ok(ah, dim, 2))
+        return set_error(PB2_ERR_ARG, "hinge_prep: dtype / alignment");
+    if ((v_split == nullptr) != (a_split == nullptr) || (v_split && (dtype != PB2_F32 || !vec_ok(v_split, 3 * (int64_t)dim, 2) ||
+                                                                     !vec_ok(a_split, 3 * (int64_t)dim, 2))))
+        return set_error(PB2_ERR_ARG, "hinge_prep: the split-bf16 outputs go together, for fp32 rows only");
+    cudaError_t e;
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_prep_kernel<T>, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream,
+                                           1, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
+                                           (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials, (__nv_bfloat16*)v_split,
+                                           (__nv_bfloat16*)a_split));
+    int rc = check_cuda(e, "hinge_prep");
     if (rc) return rc;
     return check_launch("hinge_prep");
 }
 
-extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int64_t n, int dim,
+extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim,
                                  int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag,
                                  const int32_t* row_cnt, const int32_t* col_cnt, const float* loss_partial,
                                  int n_partials, float margin, float coef, float* loss_out, void* d_v, void* d_a,
@@ -780,14 +904,16 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
         !d_v || !d_a)
         return set_error(PB2_ERR_ARG, "hinge_finish2: null");
     const int ob = out_dtype == PB2_F32 ? 4 : 2;
-    if (dim % 8 != 0 || !vec_ok(v, ldv, 2) || !vec_ok(a, lda, 2) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
+    const int es = elem_bytes(dtype);
+    if (!es || dim % 8 != 0 || !vec_ok(v, ldv, es) || !vec_ok(a, lda, es) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
         !vec_ok(d_v, dim, ob) || !vec_ok(d_a, dim, ob))
-        return set_error(PB2_ERR_ARG, "hinge_finish2: alignment");
+        return set_error(PB2_ERR_ARG, "hinge_finish2: dtype / alignment");
     cudaError_t e;
-#define PB2_FIN2(T)                                                                                                       \
-    e = launch_ex(hinge_finish2_kernel<T>, (unsigned)grid_for_warps(2 * n), 256u, (size_t)0, (cudaStream_t)stream, 1, p_v, p_a, \
-                  (const __nv_bfloat16*)v, (const __nv_bfloat16*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt,  \
-                  loss_partial, n_partials, margin, coef, loss_out, (T*)d_v, (T*)d_a)
+#define PB2_FIN2(TO)                                                                                                          \
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO>, (unsigned)grid_for_warps(2 * n), 256u, (size_t)0,     \
+                                           (cudaStream_t)stream, 1, p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, \
+                                           rinv_a, diag, row_cnt, col_cnt, loss_partial, n_partials, margin, coef, loss_out,  \
+                                           (TO*)d_v, (TO*)d_a))
     if (out_dtype == PB2_F32) PB2_FIN2(float);
     else if (out_dtype == PB2_BF16) PB2_FIN2(__nv_bfloat16);
     else if (out_dtype == PB2_F16) PB2_FIN2(__half);
@@ -798,32 +924,34 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
     return check_launch("hinge_finish2");
 }
 
-extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int64_t rows, int dim, int64_t ldy,
+extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int dtype, int64_t rows, int dim, int64_t ldy,
                                  float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad,
                                  void* stream) {
     if (rows <= 0) return PB2_OK;
     if (!p || !y || !grad_x) return set_error(PB2_ERR_ARG, "milnce_finish: null");
-    if (dim % 8 != 0 || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
-        return set_error(PB2_ERR_ARG, "milnce_finish: alignment");
+    const int es = elem_bytes(dtype);
+    if (!es || dim % 8 != 0 || !vec_ok(y, ldy, es) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "milnce_finish: dtype / alignment");
     const int64_t total = rows * (dim / 8);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
-    milnce_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const __nv_bfloat16*)y, rows, dim, ldy,
-                                                                coef_host, coef_dev, grad_x, ld_grad);
+    PB2_ROWS_DISPATCH(dtype, milnce_finish_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const T*)y, rows, dim, ldy,
+                                                                                           coef_host, coef_dev, grad_x, ld_grad));
     return check_launch("milnce_finish");
 }
 
-extern "C" int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, const float* w, int64_t rows, int group,
+extern "C" int pb2_milnce_finish_k(const float* p, int64_t ld_p, const void* y, int dtype, const float* w, int64_t rows, int group,
                                    int y_div, int dim, int64_t ldy, float coef_host, const float* coef_dev,
                                    float* grad_x, int64_t ld_grad, void* stream) {
     if (rows <= 0) return PB2_OK;
     if (!p || !y || !w || !grad_x) return set_error(PB2_ERR_ARG, "milnce_finish_k: null");
     if (group < 1 || y_div < 1) return set_error(PB2_ERR_ARG, "milnce_finish_k: group and y_div must be >= 1");
-    if (dim % 8 != 0 || !vec_ok(y, ldy, 2) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
-        return set_error(PB2_ERR_ARG, "milnce_finish_k: alignment");
+    const int es = elem_bytes(dtype);
+    if (!es || dim % 8 != 0 || !vec_ok(y, ldy, es) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
+        return set_error(PB2_ERR_ARG, "milnce_finish_k: dtype / alignment");
     const int64_t total = rows * (dim / 8);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
-    milnce_finish_k_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, ld_p, (const __nv_bfloat16*)y, w, rows, group, y_div,
-                                                                  dim, ldy, coef_host, coef_dev, grad_x, ld_grad);
+    PB2_ROWS_DISPATCH(dtype, milnce_finish_k_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                 p, ld_p, (const T*)y, w, rows, group, y_div, dim, ldy, coef_host, coef_dev, grad_x, ld_grad));
     return check_launch("milnce_finish_k");
 }
 

@@ -62,6 +62,7 @@ struct SimCommon {
     const float* rinv_y;  // may be null (=1)
     float scale;
     int diag_only;  // visit only tiles (rb, rb): paired scores (BN == BM)
+    uint32_t fmt;   // operand format of both X and Y: kFmtBF16 or kFmtF16 (kind::f16 takes either natively)
 };
 
 __device__ __forceinline__ void tile_coords(int64_t t, int n_rb, int n_cb, int& rb, int& cb) {
@@ -109,7 +110,11 @@ struct OutStage {
     const CUtensorMap* tmap;  // gradient matrix [rows, cols] fp16, box [32 x 64]
     uint32_t slab;            // running slab counter of this warp
     uint32_t mask;            // nbuf - 1 (1: double buffered, 0: one slab per tile and warp)
-    int skip;                 // measurement hooks (pb2_debug_force_bn bits 16..18): 1 no TMA store, 2 no STS, 4 no fence
+#ifdef PB2_MEASURE
+    int skip;                 // measurement build only (pb2_debug_force_bn bits 16..18): 1 no TMA store, 2 no STS, 4 no fence
+#else
+    static constexpr int skip = 0;
+#endif
     // 16 fp16 (two uint4) of this thread's row, chunk parity cp (0: columns 0-31, 1: columns 32-63)
     __device__ __forceinline__ void write(int lane, int cp, const uint32_t (&packed)[16]) {
         if (skip & 2) return;
@@ -995,7 +1000,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     } else if (warp == kMmaWarp) {
         // ====================================================================== MMA issuer
         if (lane == 0 && (crank == 0 || !kSharedMma)) {
-            constexpr uint32_t idesc = make_idesc(BM * (kSharedMma ? 2 : 1), BN, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+            const uint32_t idesc = make_idesc(BM * (kSharedMma ? 2 : 1), BN, c.fmt, c.fmt, kMajorK, kMajorK);
             // K-major 128B-swizzled operands: descriptor = {start >> 4 | LBO 16 B, SBO 1024 B | version | swizzle}.
             // Only the start address changes, linearly: one running low word, adds instead of rebuilds.
             const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
@@ -1103,7 +1108,9 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         os.tmap = &tm_out;
         os.slab = 0;
         os.mask = L::kOutBufs - 1;
+#ifdef PB2_MEASURE
         os.skip = c.diag_only < 0 ? -c.diag_only : 0;
+#endif
         int64_t it = 0;
         for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
             const int as = (int)(it & 1);
@@ -1175,7 +1182,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
 }
 
 // ------------------------------------------------------------------------------------ host
-static int g_skip_store = 0;  // measurement hook: pb2_debug_force_bn(bn | 0x10000)
+PB2_KNOB g_skip_store = 0;  // measurement build: pb2_debug_force_bn(bn | 0x10000)
 
 static int pick_bn(int64_t rows, int64_t cols, bool stores_g) {
     // widest tile that still yields at least ~one tile per SM; small problems are latency bound.
@@ -1196,7 +1203,7 @@ struct OutMatrix {  // optional fp16 gradient matrix drained by TMA stores
 };
 
 template <class Policy, int BN, int G, int kCtas>
-static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
+static int launch_sim(const void* x, const void* y, int dtype, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                       const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
                       const OutMatrix& om, cudaStream_t st, const char* what) {
     CUtensorMap tx, ty, to;
@@ -1230,21 +1237,19 @@ static int launch_sim(const void* x, const void* y, int64_t rows, int64_t cols, 
     c.rinv_x = rinv_x;
     c.rinv_y = rinv_y;
     c.scale = scale;
+    c.fmt = dtype == PB2_F16 ? (uint32_t)kFmtF16 : (uint32_t)kFmtBF16;
     auto kern = sim_kernel<Policy, BN, G, kCtas>;
     constexpr int smem = SimSmem<BN, G, uses_stage<Policy>::value, kCtas>::kTotal;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), what);
-        if (rc) return rc;
-        configured = true;
-    }
+    static PerDeviceOnce configured;  // per instantiation and device
+    rc = ensure_dynamic_smem(configured, kern, smem, what);
+    if (rc) return rc;
     const int grid = (int)std::min<int64_t>(c.n_tiles, pb2_sim_grid() / kCluster) * kCluster;
     rc = check_cuda(launch_ex(kern, (unsigned)grid, (unsigned)sim_threads(G), (size_t)smem, st, kCluster, tx, ty, to, c, pp), what);
     if (rc) return rc;
     return check_launch(what);
 }
 
-static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
+PB2_KNOB g_force_bn = 0;  // measurement build: pb2_debug_force_bn
 // pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, 2 = multicast clusters, 0 = independent CTAs, -1 = default.  Pairs are
 // correct (tools/gpu_probe.py simpair: identical counts / ranks) but measured SLOWER here -- hinge pass 1.34 vs
 // 1.23 ms, rank pass 0.843 vs 0.827 ms per 32768^2 block, sustained: a pair's MMA for tile t+2 waits for BOTH
@@ -1256,22 +1261,24 @@ static int g_force_bn = 0;  // test hook (pb2_debug_force_bn)
 // log-sum-exp 1.104-1.112 -> 1.055-1.084 ms) and slower with one (hinge + gradient matrix 1.216 -> 1.245 ms); inside
 // the real steps, where these passes alternate with the gradient GEMMs, they lose (65536-clip MIL-NCE step 16.0-16.9
 // -> 16.4-17.7 ms, 16384^2 recall call 0.38-0.41 -> 0.41-0.43 ms; tools/ab_milnce.py), so independent CTAs stay.
-static int g_sim_pair = -1;
+PB2_KNOB g_sim_pair = -1;
 
 template <class Policy>
-static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
+static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, int64_t cols, int dim, int64_t ldx, int64_t ldy,
                         const float* rinv_x, const float* rinv_y, float scale, const typename Policy::Params& pp,
                         void* stream, const char* what, int force_bn = 0, const OutMatrix& om = OutMatrix()) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (dim <= 0 || dim % BK != 0) return set_error(PB2_ERR_ARG, "%s: dim must be a positive multiple of 64", what);
     if (!x || !y) return set_error(PB2_ERR_ARG, "%s: null operand", what);
+    if (dtype != PB2_BF16 && dtype != PB2_F16)
+        return set_error(PB2_ERR_ARG, "%s: tensor-core operands are bf16 or fp16 (fp32 rows go through pb2_split_bf16)", what);
     if (rows > 0x7fffffffll * BM / 2 || cols > 0x7fffffffll) return set_error(PB2_ERR_ARG, "%s: too large", what);
     cudaStream_t st = (cudaStream_t)stream;
     int bn = force_bn ? force_bn : pick_bn(rows, cols, Policy::kStoresG);
     if (Policy::kStoresG && bn == 64) bn = 128;
     if (!Policy::kStoresG && bn == 192) bn = 256;
 #define PB2_SIM(B, GG, CC) \
-    launch_sim<Policy, B, GG, CC>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
+    launch_sim<Policy, B, GG, CC>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
     const bool pair = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 1;
     const bool mcast = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 2;
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
@@ -1301,6 +1308,7 @@ static int dispatch_sim(const void* x, const void* y, int64_t rows, int64_t cols
 using namespace pb2;
 
 extern "C" int pb2_sim_grid(void) { return sm_count(); }
+#ifdef PB2_MEASURE
 extern "C" int pb2_debug_sim_pair(int mode) {
     g_sim_pair = mode;
     return PB2_OK;
@@ -1311,9 +1319,10 @@ extern "C" int pb2_debug_force_bn(int bn) {
     g_force_bn = (bn == 64 || bn == 128 || bn == 192 || bn == 256) ? bn : 0;
     return PB2_OK;
 }
+#endif
 
 extern "C" int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                              int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* out,
+                              int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float* out,
                               int64_t ld_out, void* stream) {
     if (!out && rows > 0 && cols > 0) return set_error(PB2_ERR_ARG, "sim_matrix: null output");
     if (rows > 0 && cols > 0 && ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0 || ld_out < cols))
@@ -1322,22 +1331,22 @@ extern "C" int pb2_sim_matrix(const void* x, const void* y, const float* rinv_x,
     OutMatrix om;
     om.ptr = out;
     om.ld = ld_out;
-    return dispatch_sim<StorePolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+    return dispatch_sim<StorePolicy>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
                                      "sim_matrix", g_force_bn, om);
 }
 
-extern "C" int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim,
+extern "C" int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t n, int dim, int dtype,
                             int64_t ldx, int64_t ldy, float* out, float* dist_out, float* thr_out, void* stream) {
     DiagPolicy::Params pp{out, dist_out, thr_out};
-    return dispatch_sim<DiagPolicy>(x, y, n, n, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream, "sim_diag", 128);
+    return dispatch_sim<DiagPolicy>(x, y, dtype, n, n, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream, "sim_diag", 128);
 }
 
 extern "C" int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, const float* rinv_g,
                             const float* pos_thr, const int64_t* pos_col, int64_t rows, int64_t cols,
-                            int64_t col_offset, int dim, int64_t ldq, int64_t ldg, int32_t* rank, void* stream) {
+                            int64_t col_offset, int dim, int dtype, int64_t ldq, int64_t ldg, int32_t* rank, void* stream) {
     if (rows > 0 && cols > 0 && (!pos_thr || !pos_col || !rank)) return set_error(PB2_ERR_ARG, "sim_rank: null");
     RankPolicy::Params pp{pos_thr, pos_col, col_offset, rank};
-    return dispatch_sim<RankPolicy>(q, g, rows, cols, dim, ldq, ldg, rinv_q, rinv_g, 1.0f, pp, stream, "sim_rank",
+    return dispatch_sim<RankPolicy>(q, g, dtype, rows, cols, dim, ldq, ldg, rinv_q, rinv_g, 1.0f, pp, stream, "sim_rank",
                                     g_force_bn);
 }
 
@@ -1349,7 +1358,7 @@ static int check_gmat(const void* gmat, int64_t ld_g, int64_t cols, const char* 
 
 extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
                              const float* diag_row, const float* diag_col, int64_t rows, int64_t cols,
-                             int64_t row_offset, int64_t col_offset, int dim, int64_t ldx, int64_t ldy, float margin,
+                             int64_t row_offset, int64_t col_offset, int dim, int dtype, int64_t ldx, int64_t ldy, float margin,
                              float* loss_partial, int n_partials, int32_t* row_cnt, int32_t* col_cnt, void* gmat,
                              int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
@@ -1373,16 +1382,16 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
     om.ptr = gmat;
     om.ld = ld_g;
     if (rank)
-        return dispatch_sim<HingePolicyT<true>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
+        return dispatch_sim<HingePolicyT<true>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
                                                 "sim_hinge+rank", g_force_bn, om);
-    return dispatch_sim<HingePolicyT<false>>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
+    return dispatch_sim<HingePolicyT<false>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
                                              "sim_hinge", g_force_bn, om);
 }
 
 extern "C" int pb2_sim_lse_col_parts(int64_t rows) { return (int)((rows + BM - 1) / BM) * 4; }
 
 extern "C" int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                                int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float bound,
+                                int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float bound,
                                 float* row_part_sum, float* col_part_sum, void* stream) {
     if (rows > 0 && cols > 0 && (!row_part_sum || !col_part_sum)) return set_error(PB2_ERR_ARG, "sim_lse_both: null");
     const float shift = bound * 1.4426950408889634f;
@@ -1390,7 +1399,7 @@ extern "C" int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_
         return set_error(PB2_ERR_ARG, "sim_lse_both: needs 0 <= bound and bound * log2(e) <= 60 (use the two-pass path)");
     LseBothPolicy::Params pp{row_part_sum, col_part_sum, shift};
     const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
-    return dispatch_sim<LseBothPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+    return dispatch_sim<LseBothPolicy>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
                                        "sim_lse_both", bn);
 }
 
@@ -1398,18 +1407,18 @@ extern "C" int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_
 extern "C" int pb2_sim_lse_parts(int64_t cols) { return (int)((cols + 127) / 128) * 2; }
 
 extern "C" int pb2_sim_lse_rows(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
-                                int64_t cols, int dim, int64_t ldx, int64_t ldy, float scale, float* part_max,
+                                int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float* part_max,
                                 float* part_sum, void* stream) {
     if (rows > 0 && cols > 0 && (!part_max || !part_sum)) return set_error(PB2_ERR_ARG, "sim_lse_rows: null");
     LseRowPolicy::Params pp{part_max, part_sum};
     // 256-wide tiles once they fill the machine (the partial layout is the 128-column one either way)
     const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
-    return dispatch_sim<LseRowPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+    return dispatch_sim<LseRowPolicy>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
                                       "sim_lse_rows", bn);
 }
 
 extern "C" int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const float* rinv_y,
-                                const float* den_row, const float* den_col, int64_t rows, int64_t cols, int dim,
+                                const float* den_row, const float* den_col, int64_t rows, int64_t cols, int dim, int dtype,
                                 int64_t ldx, int64_t ldy, float scale, void* gmat, int64_t ld_g, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!den_row || !den_col || !gmat) return set_error(PB2_ERR_ARG, "sim_lse_grad: null");
@@ -1419,6 +1428,6 @@ extern "C" int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_
     OutMatrix om;
     om.ptr = gmat;
     om.ld = ld_g;
-    return dispatch_sim<LseGradPolicy>(x, y, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+    return dispatch_sim<LseGradPolicy>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
                                        "sim_lse_grad", g_force_bn, om);
 }

@@ -13,10 +13,10 @@ namespace {
 constexpr int64_t kAlign = 256;
 int64_t up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct Layout {
-    int64_t rinv_v, rinv_a, diag, part, row_cnt, col_cnt, vh, ah, g, pv, pa, total, ld_g;
+    int64_t rinv_v, rinv_a, diag, part, row_cnt, col_cnt, vh, ah, g, pv, pa, vx, ax, total, ld_g;
     int n_part;
 };
-Layout layout(int64_t n, int dim) {
+Layout layout(int64_t n, int dim, int in_dtype) {
     Layout L;
     L.n_part = pb2_sim_grid();
     L.ld_g = (n + 63) / 64 * 64;
@@ -37,14 +37,19 @@ Layout layout(int64_t n, int dim) {
     L.g = take(n * L.ld_g * 2);
     L.pv = take(n * dim * 4);
     L.pa = take(n * dim * 4);
+    // fp32 inputs: split-bf16 tensor-core operands [n, 3 dim] (pb2_split_bf16)
+    L.vx = in_dtype == PB2_F32 ? take(n * 3 * dim * 2) : -1;
+    L.ax = in_dtype == PB2_F32 ? take(n * 3 * dim * 2) : -1;
     L.total = o;
     return L;
 }
 }  // namespace
 
-extern "C" int64_t pb2_hinge_step_workspace(int64_t n, int dim) { return n > 0 && dim > 0 ? layout(n, dim).total : 0; }
+extern "C" int64_t pb2_hinge_step_workspace(int64_t n, int dim, int in_dtype) {
+    return n > 0 && dim > 0 ? layout(n, dim, in_dtype).total : 0;
+}
 
-extern "C" int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
+extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                               void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a,
                               int out_dtype, void* stream) {
     using pb2::set_error;
@@ -53,7 +58,9 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, 
     if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "hinge_step: dim must be a positive multiple of 64");
     if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0)
         return set_error(PB2_ERR_ARG, "hinge_step: workspace must be 256-byte aligned");
-    const Layout L = layout(n, dim);
+    if (in_dtype != PB2_BF16 && in_dtype != PB2_F16 && in_dtype != PB2_F32)
+        return set_error(PB2_ERR_ARG, "hinge_step: inputs are bf16, fp16 or fp32 rows");
+    const Layout L = layout(n, dim, in_dtype);
     if (workspace_bytes < L.total) return set_error(PB2_ERR_ARG, "hinge_step: workspace too small");
     char* w = static_cast<char*>(workspace);
     float* rinv_v = reinterpret_cast<float*>(w + L.rinv_v);
@@ -70,14 +77,20 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int64_t n, int dim, 
     // programmatic dependent launch between the four kernels: each one's prologue (barrier init, TMEM
     // allocation, descriptor prefetch) overlaps its predecessor's tail
     pb2::PdlScope pdl;
-    int rc = pb2_hinge_prep(v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part, stream);
+    // tensor-core operands: bf16 / fp16 rows as they are, fp32 rows as their split-bf16 pair (contraction length 3 dim)
+    const bool split = in_dtype == PB2_F32;
+    void* vx = split ? w + L.vx : nullptr;
+    void* ax = split ? w + L.ax : nullptr;
+    int rc = pb2_hinge_prep(v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part,
+                            vx, ax, stream);
     if (rc) return rc;
-    rc = pb2_sim_hinge(v, a, rinv_v, rinv_a, diag, diag, n, n, 0, 0, dim, ldv, lda, margin, part, -L.n_part, row_cnt,
-                       col_cnt, g, L.ld_g, nullptr, nullptr, stream);
+    rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, rinv_v, rinv_a, diag, diag, n, n, 0, 0, split ? 3 * dim : dim,
+                       split ? PB2_BF16 : in_dtype, split ? 3 * (int64_t)dim : ldv, split ? 3 * (int64_t)dim : lda, margin, part,
+                       -L.n_part, row_cnt, col_cnt, g, L.ld_g, nullptr, nullptr, stream);
     if (rc) return rc;
     // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
     rc = pb2_grad_gemm_dual(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, pv, pa, dim, dim, stream);
     if (rc) return rc;
-    return pb2_hinge_finish2(pv, pa, v, a, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, part, L.n_part, margin,
+    return pb2_hinge_finish2(pv, pa, v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, part, L.n_part, margin,
                              1.0f / ((float)n * (float)n), loss_out, d_v, d_a, out_dtype, stream);
 }

@@ -30,14 +30,15 @@ class _HingeFn(torch.autograd.Function):
     def forward(ctx, V, A, margin):
         if V.dim() != 2 or A.dim() != 2 or V.shape[0] != A.shape[0]:
             raise RuntimeError(f"TripletLoss expects V [N, D] and A [N, D]; got {tuple(V.shape)} and {tuple(A.shape)}")
-        vb = ops.as_bf16_rows(V)
-        ab = ops.as_bf16_rows(A, device=vb.device)
+        # rows in their own dtype (fp32 / fp16 / bf16: nothing is rounded; mixed dtypes meet in fp32)
+        vb, ab = ops.as_row_pair(V, A)
         dev = vb.device
         n = vb.shape[0]
         need_grad = any(ctx.needs_input_grad[:2])
-        if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the five-launch fused step
-            same = V.dtype == A.dtype and V.dtype in (torch.float32, torch.bfloat16, torch.float16)
-            loss, grads = ops.hinge_step(vb, ab, margin, V.dtype if same else torch.float32)
+        if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the four-launch fused step
+            # gradients stay fp32 until grad_output has been applied (backward): an AMP GradScaler's 65536 must
+            # reach an fp16 gradient of ~1e-7 before the rounding does
+            loss, grads = ops.hinge_step(vb, ab, margin, torch.float32)
             ctx.save_for_backward(grads)
             ctx.fused = True
             ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
@@ -46,6 +47,7 @@ class _HingeFn(torch.autograd.Function):
         rv, nv = ops.row_norms(vb)
         ra, na = ops.row_norms(ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
+        vx, ax = ops.mma_pair(vb, ab)                           # tensor-core operands (split-bf16 for fp32 rows)
         row_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
         col_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
         inv_n2 = 1.0 / float(n) ** 2
@@ -59,7 +61,7 @@ class _HingeFn(torch.autograd.Function):
                 g = ld = None
                 if need_grad:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                part = ops.sim_hinge(vb[r0:r1], ab[c0:c1], rv[r0:r1], ra[c0:c1], diag[r0:r1], diag[c0:c1], margin,
+                part = ops.sim_hinge(vx[r0:r1], ax[c0:c1], rv[r0:r1], ra[c0:c1], diag[r0:r1], diag[c0:c1], margin,
                                      row_cnt[r0:r1], col_cnt[c0:c1], g, ld or 0, row_offset=r0, col_offset=c0)
                 ops.hinge_loss_terms(loss, partials=part, alpha=inv_n2)
                 if need_grad:
@@ -88,8 +90,10 @@ class _HingeFn(torch.autograd.Function):
             (grads,) = ctx.saved_tensors
             vd, vdev, ad, adev, dv_, da_ = ctx.meta
             go = grad_out.detach().to(device=grads.device, dtype=torch.float32)
-            # two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy
-            g0, g1 = ops.scale_pair(grads[0], grads[1], go)
+            # two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy;
+            # scaled in fp32, rounded to the inputs' dtype last
+            same = vd == ad and vd in (torch.float32, torch.bfloat16, torch.float16)
+            g0, g1 = ops.scale_pair(grads[0], grads[1], go, vd if same else torch.float32)
             gV = g0[:, :dv_].to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
             gA = g1[:, :da_].to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
             return gV, gA, None
@@ -119,8 +123,8 @@ class _MilNceFn(torch.autograd.Function):
         if n == 0 or A.shape[0] % n != 0 or A.shape[0] == 0:   # the reference's x.view(N, N, -1) fails the same way
             raise RuntimeError(f"shape '[{n}, {n}, -1]' is invalid for input of size {n * A.shape[0]}")
         k = A.shape[0] // n
-        vb = ops.as_bf16_rows(V)
-        ab = ops.as_bf16_rows(A, device=vb.device)
+        vb, ab = ops.as_row_pair(V, A)
+        vx, ax = ops.mma_pair(vb, ab)         # tensor-core operands (split-bf16 for fp32 rows)
         dev = vb.device
         nk = n * k
         need_grad = any(ctx.needs_input_grad)
@@ -134,12 +138,12 @@ class _MilNceFn(torch.autograd.Function):
             lse_col = torch.full((nk,), float("-inf"), dtype=torch.float32, device=dev)
             for (r0, r1) in vblocks:
                 for (c0, c1) in ablocks:
-                    ops.sim_lse_both(vb[r0:r1], ab[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1], lse_col=lse_col[c0:c1])
+                    ops.sim_lse_both(vx[r0:r1], ax[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1], lse_col=lse_col[c0:c1])
         else:
             for (c0, c1) in ablocks:   # rows = videos, columns = audio candidates
-                lse_row = ops.sim_lse_rows(vb, ab[c0:c1], scale=inv_tau, lse=lse_row)
+                lse_row = ops.sim_lse_rows(vx, ax[c0:c1], scale=inv_tau, lse=lse_row)
             for (c0, c1) in vblocks:   # LSE over videos for every audio candidate = row LSE of A V^T
-                lse_col = ops.sim_lse_rows(ab, vb[c0:c1], scale=inv_tau, lse=lse_col)
+                lse_col = ops.sim_lse_rows(ax, vx[c0:c1], scale=inv_tau, lse=lse_col)
         if k == 1:
             diag = ops.pair_dot(vb, ab)
             if inv_tau != 1.0:
@@ -163,7 +167,7 @@ class _MilNceFn(torch.autograd.Function):
             for (r0, r1) in vblocks:
                 for (c0, c1) in ablocks:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                    ops.sim_lse_grad(vb[r0:r1], ab[c0:c1], den[r0:r1], den_a[c0:c1], g, ld, scale=inv_tau)
+                    ops.sim_lse_grad(vx[r0:r1], ax[c0:c1], den[r0:r1], den_a[c0:c1], g, ld, scale=inv_tau)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc_v)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc_a)
             if k == 1:

@@ -44,13 +44,11 @@ def _targets(correct, n_rows, n_cols, device):
 
 def _pair_ranks(candidates, references, correct):
     """int32 rank of every (row, target) pair plus the bookkeeping to fold pairs back into rows."""
-    qb = ops.as_bf16_rows(references)
-    gb = ops.as_bf16_rows(candidates, device=qb.device)
-    if qb.shape[1] != gb.shape[1]:
-        raise RuntimeError("candidates and references must have the same embedding size")
+    qb, gb = ops.as_row_pair(references, candidates)      # own dtype, sizes checked like the reference's matmul
     dev = qb.device
     rq, _ = ops.row_norms(qb)
     rg, _ = ops.row_norms(gb)
+    qb, gb = ops.mma_pair(qb, gb)                         # tensor-core operands (split-bf16 for fp32 rows)
     rows, cols, counts = _targets(correct, qb.shape[0], gb.shape[0], dev)
     if counts is None:
         q, rq_p = qb, rq
@@ -125,11 +123,10 @@ def _resampled_ranks(candidates, references, size, n_samples):
         torch.empty(0, size, dtype=torch.int64)
     g = len(candidates)
     if g * g <= _RESAMPLE_MATRIX_LIMIT and n_samples > 0:
-        qb = ops.as_bf16_rows(references)
-        gb = ops.as_bf16_rows(candidates, device=qb.device)
+        qb, gb = ops.as_row_pair(references, candidates)
         rq, _ = ops.row_norms(qb)
         rg, _ = ops.row_norms(gb)
-        scores = ops.sim_matrix(qb, gb, rq, rg)          # rows = references, as in pig/metrics.py:8
+        scores = ops.sim_matrix(*ops.mma_pair(qb, gb), rq, rg)          # rows = references, as in pig/metrics.py:8
         return ops.subset_rank(scores, ix.to(qb.device))
     ranks = [_pair_ranks(candidates[i], references[i], None)[0] for i in ix]      # huge galleries: per subset
     return torch.stack(ranks) if ranks else torch.empty(0, size, dtype=torch.int32)

@@ -53,28 +53,77 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def as_bf16_rows(x: torch.Tensor, device=None) -> torch.Tensor:
-    """2-D contiguous bf16 copy on the GPU with the feature dimension zero-padded to a multiple
-    of 64 (zero columns change neither dot products nor norms)."""
+_ROW_DTYPES = (torch.bfloat16, torch.float16, torch.float32)
+
+
+def as_rows(x: torch.Tensor, device=None, dtype=None) -> torch.Tensor:
+    """The embedding matrix as the kernels read it: 2-D, contiguous, on the GPU, IN ITS OWN DTYPE (bf16, fp16 or
+    fp32 -- nothing is rounded; other dtypes are taken as fp32), the feature dimension zero-padded to a multiple of
+    64 (zero columns change neither dot products nor norms).  No copy when the input already is all of that."""
     if x.dim() != 2:
         raise ValueError(f"expected a 2-D [N, D] embedding matrix, got shape {tuple(x.shape)}")
     dev = require_cuda(device if device is not None else x.device)
-    y = x.detach().to(device=dev, dtype=torch.bfloat16)
+    if dtype is None:
+        dtype = x.dtype if x.dtype in _ROW_DTYPES else torch.float32
+    y = x.detach()
+    if y.device != dev or y.dtype != dtype:
+        y = y.to(device=dev, dtype=dtype)
     d = y.shape[1]
     if d % 64 != 0:
         y = torch.nn.functional.pad(y, (0, 64 - d % 64))
-    return y.contiguous()
+    if not y.is_contiguous() or y.data_ptr() % 16 != 0:
+        y = y.contiguous()
+        if y.data_ptr() % 16 != 0:
+            y = y.clone()
+    return y
 
 
-def row_norms(x_bf16: torch.Tensor):
-    """(1/||x_i||, ||x_i||) in fp32 -- pig/util.py:11-12 without the divide."""
-    n, d = x_bf16.shape
-    rinv = torch.empty(n, dtype=torch.float32, device=x_bf16.device)
-    norm = torch.empty(n, dtype=torch.float32, device=x_bf16.device)
-    with torch.cuda.device(x_bf16.device):
-        check(_cabi.lib().pb2_row_norms(_ptr(x_bf16), n, d, x_bf16.stride(0), _ptr(rinv), _ptr(norm),
-                                        _stream(x_bf16.device)), "row_norms")
+def as_row_pair(x: torch.Tensor, y: torch.Tensor):
+    """Both matrices of a score computation through as_rows, on x's GPU and in ONE dtype (the kernels that read two
+    matrices take one element type): equal dtypes are kept, mixed ones meet in fp32 (exact for bf16 and fp16).
+    The feature sizes must agree like the reference's matmul demands (checked BEFORE the zero padding)."""
+    if x.dim() == 2 and y.dim() == 2 and x.shape[1] != y.shape[1]:
+        raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.shape[0]}x{x.shape[1]} and "
+                           f"{y.shape[1]}x{y.shape[0]})")
+    same = x.dtype == y.dtype and x.dtype in _ROW_DTYPES
+    dt = x.dtype if same else torch.float32
+    xr = as_rows(x, dtype=dt)
+    return xr, as_rows(y, device=xr.device, dtype=dt)
+
+
+def split_bf16(x_f32: torch.Tensor, side: int) -> torch.Tensor:
+    """[n, 3 d] bf16 split operand of an fp32 matrix: [hi | lo | hi] (side 0) or [hi | hi | lo] (side 1)."""
+    n, d = x_f32.shape
+    out = torch.empty(n, 3 * d, dtype=torch.bfloat16, device=x_f32.device)
+    with torch.cuda.device(x_f32.device):
+        check(_cabi.lib().pb2_split_bf16(_ptr(x_f32), n, d, x_f32.stride(0), int(side), _ptr(out), 3 * d,
+                                         _stream(x_f32.device)), "split_bf16")
+    return out
+
+
+def mma_pair(x: torch.Tensor, y: torch.Tensor):
+    """Tensor-core operands of S = X Y^T for rows from as_row_pair: bf16 / fp16 rows are used as they are
+    (tcgen05 kind::f16 takes both natively), fp32 rows become their split-bf16 pair (contraction length 3 d)."""
+    if x.dtype == torch.float32:
+        return split_bf16(x, 0), split_bf16(y, 1)
+    return x, y
+
+
+def row_norms(x: torch.Tensor):
+    """(1/||x_i||, ||x_i||) in fp32 -- pig/util.py:11-12 without the divide (x bf16 / fp16 / fp32 rows)."""
+    n, d = x.shape
+    rinv = torch.empty(n, dtype=torch.float32, device=x.device)
+    norm = torch.empty(n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_row_norms(_ptr(x), _DTYPE_CODE[x.dtype], n, d, x.stride(0), _ptr(rinv), _ptr(norm),
+                                        _stream(x.device)), "row_norms")
     return rinv, norm
+
+
+def _mm_code(x, y):
+    if x.dtype != y.dtype:
+        raise ValueError(f"operands must share one dtype, got {x.dtype} and {y.dtype} (see ops.as_row_pair)")
+    return _DTYPE_CODE[x.dtype]
 
 
 def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False, want_thr=False):
@@ -84,7 +133,7 @@ def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False, 
     dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
     thr = torch.empty(n, dtype=torch.float32, device=x.device) if want_thr else None
     with torch.cuda.device(x.device):
-        check(_cabi.lib().pb2_pair_dot(_ptr(x), _ptr(y), _ptr(ix), _ptr(iy), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1],
+        check(_cabi.lib().pb2_pair_dot(_ptr(x), _ptr(y), _mm_code(x, y), _ptr(ix), _ptr(iy), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1],
                                        x.stride(0), y.stride(0), _ptr(out), _ptr(dist), _ptr(thr), _stream(x.device)),
               "pair_dot")
     res = (out,) + ((dist,) if want_dist else ()) + ((thr,) if want_thr else ())
@@ -98,7 +147,7 @@ def sim_diag(x, y, rinv_x=None, rinv_y=None):
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     thr = torch.empty(n, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().pb2_sim_diag(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1], x.stride(0), y.stride(0),
+        check(_cabi.lib().pb2_sim_diag(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                        _ptr(out), _ptr(None), _ptr(thr), _stream(x.device)), "sim_diag")
     return out, thr
 
@@ -110,7 +159,7 @@ def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
     ld = max(4, (c + 3) // 4 * 4)
     buf = torch.empty(r, ld, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().pb2_sim_matrix(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0),
+        check(_cabi.lib().pb2_sim_matrix(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0),
                                          y.stride(0), float(scale), _ptr(buf), ld, _stream(x.device)), "sim_matrix")
     return buf[:, :c]
 
@@ -121,7 +170,7 @@ def sim_rank(q, g, rinv_q, rinv_g, pos_thr, pos_col, col_offset=0, rank=None):
         rank = torch.zeros(r, dtype=torch.int32, device=q.device)
     with torch.cuda.device(q.device), _timed("sim_rank", 2.0 * r * c * q.shape[1], q.device):
         check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_thr), _ptr(pos_col), r, c,
-                                       int(col_offset), q.shape[1], q.stride(0), g.stride(0), _ptr(rank),
+                                       int(col_offset), q.shape[1], _mm_code(q, g), q.stride(0), g.stride(0), _ptr(rank),
                                        _stream(q.device)), "sim_rank")
     return rank
 
@@ -155,7 +204,7 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
     part = torch.empty(n_part, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _timed("sim_hinge" + ("+rank" if rank is not None else ""), 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
-                                        int(row_offset), int(col_offset), x.shape[1], x.stride(0), y.stride(0),
+                                        int(row_offset), int(col_offset), x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                         float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
                                         int(ld_g), _ptr(pos_thr), _ptr(rank), _stream(x.device)), "sim_hinge")
     return part
@@ -173,7 +222,7 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
         lse = torch.empty(r, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _timed("sim_lse_rows", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
-        check(lib.pb2_sim_lse_rows(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0), y.stride(0),
+        check(lib.pb2_sim_lse_rows(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                    float(scale), _ptr(pmax), _ptr(psum), st), "sim_lse_rows")
         check(lib.pb2_lse_merge(_ptr(pmax), _ptr(psum), n_parts, r, _ptr(lse), int(accumulate), st), "lse_merge")
     return lse
@@ -198,7 +247,7 @@ def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None,
         lse_col = torch.empty(c, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device), _timed("sim_lse_both", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
-        check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], x.stride(0), y.stride(0),
+        check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                    float(scale), float(bound), _ptr(prow), _ptr(pcol), st), "sim_lse_both")
         check(lib.pb2_lse_merge_const(_ptr(prow), prow.shape[0], r, float(bound), _ptr(lse_row), int(acc_row), st),
               "lse_merge_const")
@@ -228,7 +277,7 @@ def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, s
     r, c = x.shape[0], y.shape[0]
     with torch.cuda.device(x.device), _timed("sim_lse_grad", 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_lse_grad(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(den_row), _ptr(den_col), r, c,
-                                           x.shape[1], x.stride(0), y.stride(0), float(scale), _ptr(gmat), int(ld_g),
+                                           x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0), float(scale), _ptr(gmat), int(ld_g),
                                            _stream(x.device)), "sim_lse_grad")
 
 
@@ -263,13 +312,14 @@ def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, acc
     return out
 
 
-def rows_scale_f16(x_bf16, rinv=None):
-    """fp16(x * rinv): the embedding operand of the gradient GEMMs."""
-    n, d = x_bf16.shape
-    out = torch.empty(n, d, dtype=torch.float16, device=x_bf16.device)
-    with torch.cuda.device(x_bf16.device):
-        check(_cabi.lib().pb2_rows_scale_f16(_ptr(x_bf16), _ptr(rinv), n, d, x_bf16.stride(0), _ptr(out), out.stride(0) if n else d,
-                                             _stream(x_bf16.device)), "rows_scale_f16")
+def rows_scale_f16(x, rinv=None, out=None):
+    """fp16(x * rinv): the embedding operand of the gradient GEMMs (x bf16 / fp16 / fp32 rows)."""
+    n, d = x.shape
+    if out is None:
+        out = torch.empty(n, d, dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_rows_scale_f16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(rinv), n, d, x.stride(0), _ptr(out),
+                                             out.stride(0) if n else d, _stream(x.device)), "rows_scale_f16")
     return out
 
 
@@ -277,7 +327,7 @@ def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_
     rows, d = x.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y),
+        check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _mm_code(x, y), _ptr(rinv_x), _ptr(rinv_y),
                                            _ptr(row_cnt), _ptr(col_cnt), rows, d, x.stride(0), y.stride(0), float(coef_host),
                                            _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(x.device)), "hinge_finish")
     return grad
@@ -287,7 +337,7 @@ def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
     rows, d = y.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
     with torch.cuda.device(y.device):
-        check(_cabi.lib().pb2_milnce_finish(_ptr(p), p.stride(0), _ptr(y), rows, d, y.stride(0), float(coef_host),
+        check(_cabi.lib().pb2_milnce_finish(_ptr(p), p.stride(0), _ptr(y), _DTYPE_CODE[y.dtype], rows, d, y.stride(0), float(coef_host),
                                             _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(y.device)), "milnce_finish")
     return grad
 
@@ -297,7 +347,7 @@ def milnce_finish_k(p, y, w, rows, group, y_div, coef_host=1.0):
     d = y.shape[1]
     grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
     with torch.cuda.device(y.device):
-        check(_cabi.lib().pb2_milnce_finish_k(_ptr(p), p.stride(0), _ptr(y), _ptr(w), rows, int(group), int(y_div), d,
+        check(_cabi.lib().pb2_milnce_finish_k(_ptr(p), p.stride(0), _ptr(y), _DTYPE_CODE[y.dtype], _ptr(w), rows, int(group), int(y_div), d,
                                               y.stride(0), float(coef_host), _ptr(None), _ptr(grad), grad.stride(0),
                                               _stream(y.device)), "milnce_finish_k")
     return grad
@@ -319,40 +369,45 @@ def project_normalize(x_bf16, w_bf16, bias=None, eps=1e-12):
     return out, rinv, norm
 
 
-_STEP_WORKSPACE = {}      # (device, n, d) -> uint8 workspace, reused across steps (stream-ordered reuse)
+_STEP_WORKSPACE = {}      # (device, stream, n, d, dtype) -> uint8 workspace, reused across steps ON THAT STREAM
 
 
 def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
-    """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768): one C call, five
-    launches (prep, fused similarity/hinge pass, two gradient GEMMs, finish).  Returns (loss 0-d fp32,
-    grads [2, n, d] in ``grad_dtype``: dV then dA)."""
+    """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768): one C call, four
+    launches (prep, fused similarity/hinge pass, both gradient GEMMs, finish).  vb / ab: rows from as_row_pair
+    (bf16, fp16 or fp32).  Returns (loss 0-d fp32, grads [2, n, d] in ``grad_dtype``: dV then dA)."""
     n, d = vb.shape
     dev = vb.device
     lib = _cabi.lib()
-    key = (dev, n, d)
-    ws = _STEP_WORKSPACE.get(key)
-    if ws is None or torch.cuda.is_current_stream_capturing():
+    code = _mm_code(vb, ab)
+    capturing = torch.cuda.is_current_stream_capturing()
+    # reuse is stream-ordered, so the cache is per stream: two steps of one shape on two streams never share
+    # scratch (a workspace handed to a graph capture belongs to that graph and is not cached)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, n, d, code)
+    ws = None if capturing else _STEP_WORKSPACE.get(key)
+    if ws is None:
         with torch.cuda.device(dev):
-            ws = torch.empty(int(lib.pb2_hinge_step_workspace(n, d)), dtype=torch.uint8, device=dev)
-        if not torch.cuda.is_current_stream_capturing():
+            ws = torch.empty(int(lib.pb2_hinge_step_workspace(n, d, code)), dtype=torch.uint8, device=dev)
+        if not capturing:
             if len(_STEP_WORKSPACE) > 8:
                 _STEP_WORKSPACE.clear()
             _STEP_WORKSPACE[key] = ws
     grads = torch.empty(2, n, d, dtype=grad_dtype, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _timed("hinge_step (5 kernels)", 6.0 * n * n * d, dev):
-        check(lib.pb2_hinge_step(_ptr(vb), _ptr(ab), n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws), ws.numel(),
+    with torch.cuda.device(dev), _timed("hinge_step (4 kernels)", 6.0 * n * n * d, dev):
+        check(lib.pb2_hinge_step(_ptr(vb), _ptr(ab), code, n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws), ws.numel(),
                                  _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), _DTYPE_CODE[grad_dtype], _stream(dev)),
               "hinge_step")
     return loss, grads
 
 
-def scale_pair(x0, x1, coef):
-    """(x0 * coef, x1 * coef) for a 0-d fp32 device tensor ``coef``: one launch, fresh contiguous results."""
-    assert x0.dtype == x1.dtype and x0.shape == x1.shape and x0.is_contiguous() and x1.is_contiguous()
-    y0, y1 = torch.empty_like(x0), torch.empty_like(x1)
+def scale_pair(x0, x1, coef, out_dtype=torch.float32):
+    """(x0 * coef, x1 * coef) rounded to ``out_dtype`` for fp32 ``x`` and a 0-d fp32 device tensor ``coef``: one
+    launch, fresh contiguous results (the scale is applied in fp32, the rounding comes last)."""
+    assert x0.dtype == x1.dtype == torch.float32 and x0.shape == x1.shape and x0.is_contiguous() and x1.is_contiguous()
+    y0, y1 = torch.empty_like(x0, dtype=out_dtype), torch.empty_like(x1, dtype=out_dtype)
     with torch.cuda.device(x0.device):
-        check(_cabi.lib().pb2_scale_pair(_ptr(x0), _ptr(x1), x0.numel(), _DTYPE_CODE[x0.dtype], _ptr(coef), _ptr(y0), _ptr(y1),
+        check(_cabi.lib().pb2_scale_pair(_ptr(x0), _ptr(x1), x0.numel(), _DTYPE_CODE[out_dtype], _ptr(coef), _ptr(y0), _ptr(y1),
                                          _stream(x0.device)), "scale_pair")
     return y0, y1
 

@@ -62,3 +62,16 @@ def rel_err(x, ref):
     ref = torch.as_tensor(ref, dtype=torch.float64).cpu()
     denom = ref.abs().max().clamp_min(1e-30)
     return ((x - ref).abs().max() / denom).item()
+
+
+def row_rel_err(x, ref):
+    """Row-wise relative error: max over rows i of ||x_i - ref_i||_2 / max(||ref_i||_2, 1% of the median row norm).
+    Beside the norm-wise bar it keeps a few wrong gradient rows from hiding under one large entry elsewhere; the
+    floor only protects rows whose true gradient is (nearly) zero."""
+    x = torch.as_tensor(x, dtype=torch.float64).cpu()
+    ref = torch.as_tensor(ref, dtype=torch.float64).cpu()
+    if x.dim() < 2:
+        return rel_err(x, ref)
+    rn = ref.norm(dim=-1)
+    floor = (0.01 * rn.median()).clamp_min(1e-30)
+    return ((x - ref).norm(dim=-1) / torch.maximum(rn, floor)).max().item()

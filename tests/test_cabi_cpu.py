@@ -21,7 +21,15 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert set(declared) == set(_cabi.SIGNATURES), "ctypes table and header disagree"
-    assert lib.pb2_version() == 1
+    assert lib.pb2_version() == 2
+    # the product library carries no debug switch (mutable global state); they live in the measurement build
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "pb2_sim_hinge" in syms and "pb2_debug" not in syms
+    with _cabi.measurement_library() as mlib:
+        for name in _cabi._DEBUG:
+            assert hasattr(mlib, name), name
+    assert _cabi.lib() is lib
 
 
 def test_argument_errors_are_reported_without_touching_a_device(lib):
@@ -101,14 +109,23 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_project_normalize(null, null, null, 8, 512, 512, 512, 512, 1e-12, null, 512, null, null, null) == 1
     assert lib.pb2_project_normalize(null, null, null, 0, 512, 512, 512, 512, 1e-12, null, 512, null, null, null) == 0
     assert lib.pb2_grad_gemm_dual(null, 1, 8, 8, 64, null, null, 1, 512, 512, 512, 1.0, null, null, 512, 512, null) == 1
-    assert lib.pb2_milnce_finish_k(null, 512, null, null, 8, 2, 1, 512, 512, 1.0, null, null, 512, null) == 1
+    assert lib.pb2_milnce_finish_k(null, 512, null, 0, null, 8, 2, 1, 512, 512, 1.0, null, null, 512, null) == 1
     assert lib.pb2_grad_gemm_workspace() >= 148 * 128 * 512 * 4
     # one-pass log-sum-exp: null partials and a bound whose shift would underflow fp32 are refused before any launch
     one = C.c_void_p(256)
-    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, 1.0, null, null, null) == 1
-    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, 100.0, one, one, null) == 1
-    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 512, 512, 1.0, -1.0, one, one, null) == 1
-    assert lib.pb2_sim_lse_both(one, one, null, null, 0, 8, 512, 512, 512, 1.0, 1.0, null, null, null) == 0
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 1.0, null, null, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 100.0, one, one, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, -1.0, one, one, null) == 1
+    assert lib.pb2_sim_lse_both(one, one, null, null, 0, 8, 512, 0, 512, 512, 1.0, 1.0, null, null, null) == 0
+    # operand dtypes: the tensor-core kernels take bf16 / fp16 (fp32 rows go through pb2_split_bf16), the row-wise
+    # kernels bf16 / fp16 / fp32; anything else is refused before a launch
+    assert lib.pb2_sim_rank(one, one, null, null, one, one, 8, 8, 0, 512, 2, 512, 512, one, null) == 1
+    assert b"split_bf16" in lib.pb2_last_error()
+    assert lib.pb2_row_norms(one, 7, 8, 512, 512, one, one, null) == 1
+    assert lib.pb2_split_bf16(one, 8, 512, 512, 2, one, 1536, null) == 1        # side is 0 or 1
+    assert lib.pb2_split_bf16(one, 8, 512, 512, 0, one, 512, null) == 1         # ld_out < 3 dim
+    assert lib.pb2_split_bf16(null, 0, 512, 512, 0, null, 1536, null) == 0
+    assert lib.pb2_hinge_step_workspace(1024, 512, 2) > lib.pb2_hinge_step_workspace(1024, 512, 0) > 0
     assert lib.pb2_sim_lse_col_parts(1000) == 32 and lib.pb2_sim_lse_col_parts(128) == 4
     assert lib.pb2_lse_merge_const(null, 4, 8, 1.0, null, 0, null) == 1 and lib.pb2_lse_merge_const(null, 4, 0, 1.0, null, 0, null) == 0
     assert lib.pb2_scale_pair(null, null, 64, 0, null, null, null, null) == 1

@@ -1,0 +1,74 @@
+"""Parity AT the headline configuration (BASELINE config 5): the 2^20 x 2^20 gallery the bench quotes its number on,
+and the ragged 1 000 000 (SURVEY section 8 header; H7).  The reference cannot run these (N^2 fp32 = 4 TiB), so the
+checker is the blockwise restatement of its formulas (``oracle/blockwise.py``, pinned to the full-matrix oracle and
+through it to the reference's own outputs in ``tests/test_oracle_golden.py``): exact ranks of 256 random queries
+against the whole gallery, those clips' dA and dV rows against the fp64 closed form, the recall histogram, and -- at
+2^18, where a blockwise pass over all N^2 scores takes seconds -- the whole loss.
+"""
+import pytest
+import torch
+
+from conftest import rel_err, row_rel_err
+from oracle import blockwise as B
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def gallery(n, alpha=4.0, seed=666):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    V = torch.nn.functional.normalize(torch.randn(n, 512, generator=g, device="cuda"), dim=1)
+    A = torch.nn.functional.normalize(alpha * V + torch.randn(n, 512, generator=g, device="cuda"), dim=1).bfloat16()
+    return A, V.bfloat16()
+
+
+@pytest.mark.parametrize("n", [1 << 20, 1_000_000])
+def test_gallery_step_at_the_headline_size(n):
+    from peppa_b200.gallery import GalleryStep
+    A, V = gallery(n)
+    step = GalleryStep(n, 512, margin=0.2, top_n=10)
+    out = step.run(A, V)
+    ranks, dA, dV = out["ranks"], out["dA"], out["dV"]
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:256].cuda()
+    # (1) exact ranks of 256 random queries (rows = audio queries, columns = all video clips: pig/metrics.py:8)
+    want, near, lo, hi = B.sampled_rank_bounds(V, A, rows)
+    got = ranks[rows].long()
+    bad = (got != want) & ~near
+    assert not bool(bad.any()), (int(bad.sum()), got[bad][:8].tolist(), want[bad][:8].tolist())
+    # with 10^6 candidates the 1e-6 window is populated for a good share of the rows (scores are ~1e-7 apart), so
+    # the exempted rows are bounded too: a rank may only move within the candidates inside the tie window
+    assert bool(((got >= lo) & (got <= hi)).all())
+    assert bool(((hi - lo)[~near] == 0).all()) and int((hi - lo).max()) < 64 and int((~near).sum()) >= 128
+    # (2) recall@n is the histogram of the ranks, monotone, row 0 == 0
+    rec = out["recall"].cpu()
+    assert rec[0] == 0 and bool((rec[1:] >= rec[:-1]).all())
+    for k in (1, 5, 10):
+        assert abs(rec[k].item() - (ranks < k).float().mean().item()) < 1e-6
+    assert 0.05 < rec[10].item() < 0.9                                # the alpha = 4 regime of SURVEY 8(d), thinned by 2^20 candidates
+    # (3) gradient rows of the sampled clips against the fp64 closed form: dA (rows of S) and dV (columns of S)
+    gA = B.hinge_grad_rows(A, V, rows, 0.2)
+    assert rel_err(dA[rows], gA) < TOL and row_rel_err(dA[rows], gA) < TOL
+    gV = B.hinge_grad_rows(V, A, rows, 0.2)                           # the loss is symmetric: columns <-> rows
+    assert rel_err(dV[rows], gV) < TOL and row_rel_err(dV[rows], gV) < TOL
+    # (4) every gradient row is orthogonal to its input row (normalisation Jacobian), over ALL rows
+    for grad, x in ((dA, A), (dV, V)):
+        dots = (grad * x.float()).sum(1).abs().max().item()
+        assert dots < 1e-4 * grad.norm(dim=1).max().item()
+    assert bool(torch.isfinite(out["loss"])) and out["loss"].item() > 0
+
+
+def test_gallery_loss_at_2_to_18_against_blockwise_fp64():
+    """The whole loss (not a sample): hinge over all 2^36 scores, scores per block in fp32 like the reference,
+    accumulated in fp64; plus exact ranks of EVERY row against the blockwise oracle."""
+    from peppa_b200.gallery import GalleryStep
+    n = 1 << 18
+    A, V = gallery(n, seed=7)
+    out = GalleryStep(n, 512, margin=0.2, top_n=10).run(A, V)
+    ref = B.hinge_loss_blockwise(A, V, 0.2, block=2048)
+    assert abs(out["loss"].item() - ref.item()) < 1e-4 * abs(ref.item()), (out["loss"].item(), ref.item())
+    want, near, lo, hi = B.sampled_rank_bounds(V, A, torch.arange(n, device="cuda"), block=2048)
+    got = out["ranks"].long()
+    bad = (got != want) & ~near
+    assert not bool(bad.any()), int(bad.sum())
+    assert bool(((got >= lo) & (got <= hi)).all())                   # near-tie rows: only within the tie window
+    assert int(near.sum()) < n // 5

@@ -10,7 +10,7 @@ import random
 import pytest
 import torch
 
-from conftest import golden_files, load_golden, rel_err
+from conftest import golden_files, load_golden, rel_err, row_rel_err
 from oracle import pig_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -31,6 +31,22 @@ def pb():
     import peppa_b200.triplet as triplet
     import peppa_b200.util as util
     return type("PB", (), dict(loss=loss, metrics=metrics, triplet=triplet, util=util))
+
+
+def near_rows_multi(candidates, references, correct, tol=1e-6):
+    """Rows of a multi-target ``correct`` where some target has another candidate within ``tol`` of its distance
+    (argsort's order -- and with it the reference's top-n overlap -- is unspecified there)."""
+    d = 1 - O.cosine_matrix(references, candidates)
+    near = torch.zeros(d.shape[0], dtype=torch.bool)
+    for j, t in torch.nonzero(correct).tolist():
+        near[j] |= int(((d[j] - d[j, t]).abs() <= tol).sum()) > 1
+    return near
+
+
+def near_rows_gpu(candidates, references, tol=1e-6, block=4096):
+    """The oracle's near-tie mask (identity targets) for galleries too large for the CPU oracle: fp32 torch on the GPU."""
+    from oracle import blockwise as B
+    return B.all_ranks(candidates.cuda(), references.cuda(), tol=tol, block=block)[1].cpu()
 
 
 def _grads(mod, V, A):
@@ -68,11 +84,11 @@ def test_recall_against_reference_golden(pb, name):
     assert bool(((got == g["recall_at_1_to_10"]) | near.unsqueeze(0)).all())
     # general multi-target `correct`
     multi = g["correct_multi"]
+    near_m = near_rows_multi(V, A, multi)               # rows where a TARGET of the row sits in a 1e-6 tie
     got = pb.metrics.recall_at_n(V.cuda(), A.cuda(), multi.cuda(), n=5)
-    ok = (got - g["recall_multi_at_5"]).abs() < 1e-6
-    assert int((~ok).sum()) <= int(near.sum()) + 2      # pairs involving a near-tie may differ
+    assert bool((((got - g["recall_multi_at_5"]).abs() < 1e-6) | near_m).all())
     got = pb.metrics.recall_at_1_to_n(V.cuda(), A.cuda(), multi.cuda(), N=10)
-    assert int(((got - g["recall_multi_1_to_10"]).abs() > 1e-6).any(dim=0).sum()) <= int(near.sum()) + 2
+    assert bool((((got - g["recall_multi_1_to_10"]).abs() < 1e-6) | near_m.unsqueeze(0)).all())
     # cosine_matrix and contrastive(M)
     M = pb.util.cosine_matrix(V.cuda(), A.cuda())
     assert (M.cpu() - g["cosine_VA"]).abs().max() < 2e-6
@@ -161,6 +177,7 @@ def test_losses_against_oracle(pb, n, alpha):
         rl, rdv, rda = ref()
         assert rel_err(loss, rl) < TOL, kind
         assert rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL, kind
+        assert row_rel_err(dV, rdv) < TOL and row_rel_err(dA, rda) < TOL, kind     # no wrong row hides under a large max
 
 
 def test_non_unit_norm_inputs(pb):
@@ -210,7 +227,7 @@ def test_retrieval_16k_properties(pb):
     inv = torch.empty_like(perm)
     inv[perm] = torch.arange(n)
     got_p = pb.metrics.recall_at_n(V[perm].cuda(), A.cuda(), inv.cuda(), n=10)
-    assert int((got_p != got[10]).sum()) <= 8                   # only near-ties may move
+    assert bool(((got_p == got[10]) | near_rows_gpu(V, A)).all())      # only rows in a 1e-6 near-tie may move
 
 
 def test_triplets_1m_properties(pb):
@@ -249,6 +266,7 @@ def test_gallery_step_single_gpu(pb, n, block):
     loss, dA, dV = O.hinge_loss_and_grads(A, V, 0.2)
     assert rel_err(out["loss"].cpu(), loss) < TOL
     assert rel_err(out["dA"].cpu(), dA) < TOL and rel_err(out["dV"].cpu(), dV) < TOL
+    assert row_rel_err(out["dA"].cpu(), dA) < TOL and row_rel_err(out["dV"].cpu(), dV) < TOL
     assert rel_err(out["loss"].cpu(), O.triplet_loss(V, A, 0.2)) < TOL        # symmetric in (V, A)
     ranks, near = O.ranks_identity(V, A)
     assert bool(((out["ranks"].cpu().long() == ranks) | near).all())
@@ -290,10 +308,15 @@ def test_resampled_recall_paths_agree(pb):
     finally:
         pb.metrics._RESAMPLE_MATRIX_LIMIT = old
     assert fast.shape == slow.shape == (20, 11, 100)
-    assert int((fast != slow).any(dim=1).sum()) <= 4
+    torch.manual_seed(7)
+    ix = torch.stack([torch.randperm(700)[:100] for _ in range(20)])           # the draws of pig/metrics.py:79-81
+    # a query is exempt only if, INSIDE ITS SUBSET, another candidate lies within 1e-6 of the positive
+    d = 1 - O.cosine_matrix(A, V)
+    near = torch.stack([(((d[i][:, i] - d[i, i].unsqueeze(1)).abs() <= 1e-6).sum(1) > 1) for i in ix])
+    assert bool(((fast == slow).all(dim=1) | near).all())
     torch.manual_seed(7)
     ref = O.resampled_recall_at_1_to_n(V, A, size=100, n_samples=20, N=10)
-    assert int((fast != ref).any(dim=1).sum()) <= 4
+    assert bool(((fast == ref).all(dim=1) | near).all())
 
 
 def test_cosine_matrix_odd_shapes_and_backward(pb):
@@ -317,14 +340,16 @@ def test_api_conformance_dtypes_layouts(pb):
     """Inputs the reference accepts must keep working: fp16 / fp32 / bf16, non-contiguous views, CPU tensors,
     an embedding size that is not a multiple of 64 (zero-padded internally), and the result types."""
     g = torch.Generator().manual_seed(12)
-    V = torch.nn.functional.normalize(torch.randn(200, 300, generator=g), dim=1).bfloat16().float()
-    A = torch.nn.functional.normalize(2.0 * V + torch.randn(200, 300, generator=g), dim=1).bfloat16().float()
-    rl, rdv, rda = O.hinge_loss_and_grads(V, A, 0.2)
-    ranks, near = O.ranks_identity(V, A)
+    V = torch.nn.functional.normalize(torch.randn(200, 300, generator=g), dim=1)       # full fp32 significands:
+    A = torch.nn.functional.normalize(2.0 * V + torch.randn(200, 300, generator=g), dim=1)   # not bf16-representable
     for make in (lambda x: x.cuda(), lambda x: x.cuda().half(), lambda x: x.cuda().bfloat16(),
                  lambda x: x.cuda().t().contiguous().t(), lambda x: x):
         v = make(V).requires_grad_(True)
         a = make(A).requires_grad_(True)
+        # the oracle sees exactly the values handed in (fp32 math on them), whatever their dtype
+        Vo, Ao = v.detach().float().cpu(), a.detach().float().cpu()
+        rl, rdv, rda = O.hinge_loss_and_grads(Vo, Ao, 0.2)
+        ranks, near = O.ranks_identity(Vo, Ao)
         loss = pb.loss.TripletLoss(0.2)(v, a)
         loss.backward()
         assert loss.device == v.device and v.grad.shape == (200, 300) and v.grad.dtype == v.dtype
@@ -457,7 +482,6 @@ def test_multicast_clusters_match_independent_ctas(pb):
     on one MMA) are measured options (default: independent CTAs); their results are bit-identical, also with an odd
     trailing row block."""
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
     n = 33 * 128 + 5
     V, A = emb(n, 4.0)
     vb, ab = V.cuda().bfloat16(), A.cuda().bfloat16()
@@ -467,13 +491,18 @@ def test_multicast_clusters_match_independent_ctas(pb):
     idx = torch.arange(n, device="cuda")
     bound = ops.logit_bound(ab, vb, 4.0)
     res = {}
-    try:
-        for mode in (0, 2, 1):
-            lib.pb2_debug_sim_pair(mode)
-            res[mode] = (ops.sim_rank(ab, vb, ra, rv, thr, idx), *ops.sim_lse_both(ab, vb, bound, scale=4.0),
-                         ops.sim_lse_rows(ab, vb, scale=4.0))
-    finally:
-        lib.pb2_debug_sim_pair(-1)
+    with _cabi.measurement_library() as lib:      # the selectors exist in the measurement build only
+        try:
+            for mode in (0, 2, 1):
+                lib.pb2_debug_sim_pair(mode)
+                res[mode] = (ops.sim_rank(ab, vb, ra, rv, thr, idx), *ops.sim_lse_both(ab, vb, bound, scale=4.0),
+                             ops.sim_lse_rows(ab, vb, scale=4.0))
+        finally:
+            lib.pb2_debug_sim_pair(-1)
+    res["product"] = (ops.sim_rank(ab, vb, ra, rv, thr, idx), *ops.sim_lse_both(ab, vb, bound, scale=4.0),
+                      ops.sim_lse_rows(ab, vb, scale=4.0))
+    for x, y in zip(res[0], res["product"]):       # the product library runs the independent-CTA kernels
+        assert torch.equal(x, y)
     for mode in (2, 1):
         for x, y in zip(res[0], res[mode]):
             assert torch.equal(x, y)
@@ -620,12 +649,13 @@ def test_encoder_tail_column_split_variant(pb):
         x = torch.randn(rows, n_in, generator=g).bfloat16().cuda()
         w = (torch.randn(n_out, n_in, generator=g) / n_in ** 0.5).bfloat16().cuda()
         b = torch.randn(n_out, generator=g).cuda()
-        _cabi.lib().pb2_debug_proj_variant(2)
-        try:
-            o2, r2, m2 = ops.project_normalize(x, w, b)
-            torch.cuda.synchronize()
-        finally:
-            _cabi.lib().pb2_debug_proj_variant(0)
+        with _cabi.measurement_library() as lib:
+            lib.pb2_debug_proj_variant(2)
+            try:
+                o2, r2, m2 = ops.project_normalize(x, w, b)
+                torch.cuda.synchronize()
+            finally:
+                lib.pb2_debug_proj_variant(0)
         o1, r1, m1 = ops.project_normalize(x, w, b)
         assert (o1.float() - o2.float()).abs().max().item() <= 2.0 ** -8 * o1.float().abs().max().item()
         assert rel_err(r2, 1.0 / o2.float().norm(dim=1)) < 1e-5       # rinv belongs to ITS rounded rows
@@ -685,9 +715,26 @@ def test_embedding_store_scoring(pb, tmp_path):
     ref_jit = O.resampled_recall_at_1_to_n(Vj, Aj, size=100, n_samples=3, N=10)
     ref_acc = O.score_triplets(V, A, dur, n_samples=3)["accuracy"]
     assert row["recall_fixed"].shape == (3, 11, 100)
-    assert (row["recall_fixed"].cpu() != ref_fixed).float().mean().item() < 2e-3     # near-tie rows only
-    assert (row["recall_jitter"].cpu() != ref_jit).float().mean().item() < 2e-3
-    assert torch.allclose(torch.as_tensor(row["triplet_acc"]).float().cpu(), torch.as_tensor(ref_acc).float(), atol=2e-3)
+    # the subsets the reference's RNG draws (3 randperms for the fixed set, then 3 for the jittered one); a query is
+    # exempt only when another candidate of ITS subset lies within 1e-6 of the positive
+    torch.manual_seed(666)
+    ix_f = torch.stack([torch.randperm(1536)[:100] for _ in range(3)])
+    ix_j = torch.stack([torch.randperm(1536)[:100] for _ in range(3)])
+
+    def near_of(Vx, Ax, ix):
+        d = 1 - O.cosine_matrix(Ax, Vx)
+        return torch.stack([(((d[i][:, i] - d[i, i].unsqueeze(1)).abs() <= 1e-6).sum(1) > 1) for i in ix])
+
+    assert bool(((row["recall_fixed"].cpu() == ref_fixed).all(dim=1) | near_of(V, A, ix_f)).all())
+    assert bool(((row["recall_jitter"].cpu() == ref_jit).all(dim=1) | near_of(Vj, Aj, ix_j)).all())
+    # triplet accuracy per resample: identical unless one of its pairs has |gap| < 1e-6 (sign undefined there)
+    random.seed(666)                # the sampler consumes `random` only (the recall draws above use torch's generator)
+    gaps = O.comparative_score_triplets([V], [A], dur, n_samples=3)["success"][0]
+    acc_got, acc_ref = torch.as_tensor(row["triplet_acc"]).float().cpu(), torch.as_tensor(ref_acc).float()
+    if bool((gaps.abs() < 1e-6).any()):
+        assert torch.allclose(acc_got, acc_ref, atol=float((gaps.abs() < 1e-6).sum()) / (gaps.numel() / 3) + 1e-6)
+    else:
+        assert torch.allclose(acc_got, acc_ref, atol=1e-6)
     assert torch.equal(row["recall_at_10_fixed"], row["recall_fixed"][:, 10, :])
 
 
@@ -721,7 +768,8 @@ def test_gallery_131k_properties(pb):
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(3)).cuda()
     p = step.run(A[perm].contiguous(), V[perm].contiguous())
     assert abs(p["loss"].item() - loss) < 1e-6 * abs(loss)
-    assert int((p["ranks"] != ranks[perm]).sum()) <= 8
+    near_all = near_rows_gpu(V, A, block=2048).cuda()                       # rows = audio queries, as in step.run(A, V)
+    assert bool(((p["ranks"] == ranks[perm]) | near_all[perm]).all())       # only rows in a 1e-6 near-tie may move
     assert rel_err(p["dA"], dA[perm]) < 1e-5
     # (5) deterministic
     again = step.run(A, V)

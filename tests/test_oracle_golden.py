@@ -126,3 +126,28 @@ def test_milnce_k_candidates_bit_exact(name):
     assert a.shape[0] == int(g["k"]) * v.shape[0]
     assert np.array_equal(loss.detach().numpy(), g["loss"])
     assert torch.equal(v.grad, g["dV"]) and torch.equal(a.grad, g["dA"])
+
+
+@pytest.mark.parametrize("name", ["sim_n257_a4.0.npz", "sim_n100_a0.5.npz"])
+def test_blockwise_matches_full_oracle(name):
+    """oracle/blockwise.py (the checker at 2^20, where the N x N matrix does not exist) gives the reference's own
+    recall vectors / loss / gradient rows at sizes where the reference ran: recall against the golden fixtures
+    (reference outputs), loss and gradient rows against the reference's autograd gradients stored there."""
+    from oracle import blockwise as B
+    if name not in golden_files("sim_n"):
+        pytest.skip(f"{name} not among the fixtures")
+    g = load_golden(name)
+    V, A = g["V"], g["A"]
+    n = V.shape[0]
+    ranks, near = B.all_ranks(V, A, block=96)                       # ragged blocks on purpose
+    r0, n0 = O.ranks_identity(V, A)
+    assert torch.equal(ranks, r0) and torch.equal(near, n0)
+    for k in (1, 5, 10):
+        assert bool((((ranks < k).float() == g[f"recall_at_{k}"]) | near).all())
+    assert abs(B.hinge_loss_blockwise(V, A, 0.2, block=96).item() - float(g["hinge_loss"])) < 1e-6 * abs(float(g["hinge_loss"]))
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(1))[:64]
+    dv = B.hinge_grad_rows(V, A, rows, 0.2)
+    da = B.hinge_grad_rows(A, V, rows, 0.2)                         # the loss is symmetric in its two arguments
+    scale_v, scale_a = g["hinge_dV"].abs().max(), g["hinge_dA"].abs().max()
+    assert (dv - g["hinge_dV"][rows].double()).abs().max() < 1e-5 * scale_v
+    assert (da - g["hinge_dA"][rows].double()).abs().max() < 1e-5 * scale_a

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     import torch
     from peppa_b200 import _cabi
+    _cabi.use_measurement_library()      # the pb2_debug_* selectors live in the measurement build only
     args = sys.argv[1:]
     if args and args[0].endswith(".so"):
         _cabi.LIB_PATH = os.path.abspath(args.pop(0))

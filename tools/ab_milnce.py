@@ -9,6 +9,7 @@ import torch  # noqa: E402
 from bench import synth_embeddings  # noqa: E402
 from gpu_probe import _t  # noqa: E402
 from peppa_b200 import _cabi, loss, metrics  # noqa: E402
+_cabi.use_measurement_library()      # the pb2_debug_* selectors live in the measurement build only
 
 lib = _cabi.lib()
 dev = torch.device("cuda", 0)

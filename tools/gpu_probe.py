@@ -10,6 +10,13 @@ import subprocess
 import sys
 import time
 
+
+def _measure_lib():
+    """The pb2_debug_* selectors live in the measurement build only."""
+    from peppa_b200 import _cabi
+    return _cabi.use_measurement_library()
+
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
@@ -61,7 +68,7 @@ def step_triplet():
 def step_simmatrix():
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     torch.manual_seed(0)
     for (r, c, d) in [(128, 256, 64), (128, 256, 512), (128, 64, 512), (300, 500, 512), (1024, 1024, 512), (1000, 1536, 128)]:
         x = torch.randn(r, d, device="cuda").bfloat16()
@@ -94,7 +101,7 @@ def step_rank():
     import torch
     from peppa_b200 import _cabi, metrics, ops
     from oracle import pig_oracle as O
-    lib = _cabi.lib()
+    lib = _measure_lib()
     for n, alpha in ((8, 4.0), (100, 0.5), (1000, 4.0), (4096, 0.5)):
         V, A = emb(n, alpha)
         ranks_ref, near = O.ranks_identity(V.float().cpu(), A.float().cpu())
@@ -169,7 +176,7 @@ def step_gradgemm_sweep():
     """Only if the default MN-major descriptor is wrong: try the plausible alternatives."""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     torch.manual_seed(0)
     r, c, d = 128, 128, 256
     g = torch.randn(r, c, device="cuda").half()
@@ -247,7 +254,7 @@ def step_hinge_perf():
     """sim_hinge(+rank) on a 32768 x 32768 block for each tile configuration (pb2_debug_force_bn)."""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     n = 32768
     V, A = emb(n)
     rv, _ = ops.row_norms(V)
@@ -280,7 +287,7 @@ def step_hinge_dim():
     """Is the fused hinge pass MMA-bound or epilogue-bound?  Time it at D = 128 .. 1024 (same epilogue work)."""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     n = 32768
     for d in (128, 256, 512, 1024):
         V, A = emb(n, d=d)
@@ -306,7 +313,7 @@ def step_simpair():
     """Similarity kernels on CTA pairs (cta_group::2) vs independent 128 x 256 tiles: same results, sustained time."""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     n = 32768
     V, A = emb(n)
     rv, _ = ops.row_norms(V)
@@ -372,7 +379,7 @@ def step_gg_units():
     (132 of 148 SMs) and is ahead under the power cap -- does leaving SMs idle help ours?"""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     n = 32768
     gm, ld = ops.gmat_alloc(n, n, "cuda")
     gm.copy_(torch.randint(0, 3, (n, ld), device="cuda").half())
@@ -392,7 +399,7 @@ def step_streamk():
     """grad_gemm: CTA pairs (cta_group::2) on/off x stream-K on/off: agreement with fp64, determinism, sustained time."""
     import torch
     from peppa_b200 import _cabi, ops
-    lib = _cabi.lib()
+    lib = _measure_lib()
     torch.manual_seed(0)
     for tr in (False, True):
         for (r, c, d) in [(20480, 2048, 512), (2048, 20480, 512), (20000, 1000, 512), (9000, 4100, 256), (40960, 640, 256)]:

@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from peppa_b200 import _cabi, ops  # noqa: E402
+_cabi.use_measurement_library()      # the pb2_debug_* selectors live in the measurement build only
 
 lib = _cabi.lib()
 n = 32768

@@ -8,7 +8,7 @@
  * dimension `ld*`.  Embedding rows may be bf16, fp16 or fp32 (`dtype`, a PB2_* code: the reference's
  * callers hand over fp32 tensors, fp16 under Lightning's `precision: 16` -- hparams_base.yaml:45,
  * pig/evaluation.py:70 -- or bf16): the row-wise kernels read the true values; the tensor-core kernels
- * (pb2_sim_*) take bf16 or fp16 operands natively and fp32 rows as their split-bf16 pair (pb2_split_bf16:
+ * (pb2_sim_*) take bf16 or fp16 operands natively and fp32 rows as their split-fp16 pair (pb2_split_f16:
  * contraction length 3 dim).  Operands are 16-byte aligned with dim % 64 == 0 (the Python side zero-pads
  * otherwise; zero padding changes neither dot products nor norms).  Every call only ENQUEUES work on `stream` (a cudaStream_t) and
  * returns a status: 0 = ok, non-zero = error, message via pb2_last_error().  Re-entrant; no
@@ -33,6 +33,10 @@ extern "C" {
 #define PB2_BF16 0
 #define PB2_F16 1
 #define PB2_F32 2
+/* one-byte gradient matrix (hinge indicator sums, exactly {0, 1, 2}) and its embedding operand: two 8-bit planes
+ * per row, [hi (s8) | lo (u8)], of q = round(xhat * 32512) = 256 hi + lo (pb2_rows_quant_i8) */
+#define PB2_U8 3
+#define PB2_I8_PLANES 4
 
 const char* pb2_last_error(void);
 int pb2_version(void);
@@ -52,11 +56,15 @@ int pb2_triplet_score(const void* anchor, const void* positive, const void* nega
  * norm[i] = ||x_i||_2; either output may be NULL.  x is bf16 / fp16 / fp32 (dtype). */
 int pb2_row_norms(const void* x, int dtype, int64_t n, int dim, int64_t ld, float* rinv, float* norm, void* stream);
 
-/* Split-bf16 tensor-core operand of an fp32 matrix x [n, dim]: hi = bf16(x), lo = bf16(x - hi);
- * out [n, 3 dim] bf16 = [hi | lo | hi] (side 0, the X operand) or [hi | hi | lo] (side 1, the Y operand), so that
- * ONE pb2_sim_* call with dim' = 3 dim accumulates <hi_x,hi_y> + <lo_x,hi_y> + <hi_x,lo_y> in fp32 (~2^-17
- * relative per product: the matmul of pig/util.py:13 on fp32 inputs without rounding them to bf16). */
-int pb2_split_bf16(const float* x, int64_t n, int dim, int64_t ld, int side, void* out, int64_t ld_out, void* stream);
+/* Split-fp16 tensor-core operand of an fp32 matrix x [n, dim]: per row, x' = x * rinv[i] * 2^e_i (rinv NULL = 1;
+ * e_i puts the row's largest component in [512, 1024)), hi = fp16(x'), lo = fp16(x' - hi) (22 significant bits);
+ * out [n, 3 dim] fp16 = [hi | lo | hi] (side 0, the X operand) or [hi | hi | lo] (side 1, the Y operand), and
+ * scale_out[i] = 2^-e_i.  ONE pb2_sim_* call with dtype = PB2_F16, dim' = 3 dim and rinv_x / rinv_y = the two
+ * scale_out vectors then accumulates <hi_x,hi_y> + <lo_x,hi_y> + <hi_x,lo_y> in fp32 and returns
+ * <x_i, y_j> * rinv_x[i] * rinv_y[j] to ~2^-22 relative per product -- the matmul of pig/util.py:13 on fp32
+ * inputs (which the reference normalises BEFORE its matmul, pig/util.py:11-12) without rounding them to bf16. */
+int pb2_split_f16(const float* x, const float* rinv, int64_t n, int dim, int64_t ld, int side, void* out, int64_t ld_out,
+                  float* scale_out, void* stream);
 
 /* out[k] = <x[ix[k]], y[iy[k]]> * sx * sy with sx = rinv_x[ix[k]] (1 if rinv_x == NULL), same
  * for sy; ix / iy NULL = k.  The diagonal M_ii of pig/loss.py:43 and the positive's score of
@@ -75,7 +83,7 @@ int pb2_sim_diag(const void* x, const void* y, const float* rinv_x, const float*
                  int64_t ldx, int64_t ldy, float* out, float* dist_out, float* thr_out, void* stream);
 
 /* ---- (a)/(b) similarity kernels: S = X * Y^T on the tcgen05 tensor cores (X and Y both bf16 or both fp16
- * -- `dtype` = PB2_BF16 / PB2_F16, kind::f16 takes either natively; fp32 rows via pb2_split_bf16 -- fp32
+ * -- `dtype` = PB2_BF16 / PB2_F16, kind::f16 takes either natively; fp32 rows via pb2_split_f16 -- fp32
  * accumulate in TMEM), epilogue fused per entry point; S itself reaches HBM only in
  * pb2_sim_matrix.  X is [rows, dim], Y is [cols, dim]; s_ij = <x_i,y_j> * rinv_x[i] * rinv_y[j]
  * * scale (rinv_* == NULL means 1). */
@@ -107,7 +115,9 @@ int pb2_subset_rank(const float* scores, int64_t ld, const int64_t* idx, int n_s
  *   loss_partial[cta] += ([zc >= 0] + [zr >= 0]) * s_ij    (fp32, one slot per CTA, deterministic);
  *     relu(zc) + relu(zr) summed = these partials + sum_j (margin - diag_col[j]) col_cnt[j]
  *     + sum_i (margin - diag_row[i]) row_cnt[i], completed by pb2_hinge_loss_terms
- *   gmat[i,j] = fp16( [zc >= 0] + [zr >= 0] ) in {0, 1, 2}                 (0 on the diagonal)
+ *   gmat[i,j] = [zc >= 0] + [zr >= 0] in {0, 1, 2}                         (0 on the diagonal)
+ *     as fp16 (g_dtype = PB2_F16, ld_g in elements) or as ONE BYTE per entry (g_dtype = PB2_U8: half the HBM
+ *     traffic of the gradient matrix; consumed by the kind::i8 path of pb2_grad_gemm*)
  * gmat may be NULL (forward only).  |n_partials| = capacity of loss_partial (>= pb2_sim_grid()); the buffer
  * is cleared first unless n_partials is negative (the caller already did, see pb2_hinge_prep).
  * If rank != NULL the same pass also does pb2_sim_rank with the diagonal as the positive:
@@ -115,7 +125,8 @@ int pb2_subset_rank(const float* scores, int64_t ld, const int64_t* idx, int n_s
 int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, const float* rinv_y, const float* diag_row,
                   const float* diag_col, int64_t rows, int64_t cols, int64_t row_offset, int64_t col_offset, int dim, int dtype,
                   int64_t ldx, int64_t ldy, float margin, float* loss_partial, int n_partials, int32_t* row_cnt,
-                  int32_t* col_cnt, void* gmat, int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream);
+                  int32_t* col_cnt, void* gmat, int g_dtype, int64_t ld_g, const float* pos_thr, int32_t* rank,
+                  void* stream);
 
 /* pig/loss.py:13-26 MILNCELoss: row-wise online log-sum-exp of s over all columns.
  * part_max / part_sum are [n_col_tiles * 2, rows] fp32 partials in the log2 domain
@@ -152,7 +163,9 @@ int pb2_sim_lse_grad(const void* x, const void* y, const float* rinv_x, const fl
                      float scale, void* gmat, int64_t ld_g, void* stream);
 
 /* ---- backward GEMMs on the tensor cores: out[M, dim] (=|+=) alpha * op(G) * Z with G [g_rows, g_cols]
- * and Z 16-bit (PB2_F16 or PB2_BF16 each), fp32 accumulate, fp32 out.  transpose == 0: out = G * Z
+ * and Z 16-bit (PB2_F16 or PB2_BF16 each), fp32 accumulate, fp32 out -- or G one byte per entry (PB2_U8, values
+ * {0, 1, 2}) with Z = PB2_I8_PLANES (pb2_rows_quant_i8; ld_g / ldz in bytes, dim % 256 == 0, contraction length
+ * <= 32768 per call): tcgen05.mma.kind::i8 with exact s32 accumulation of the two planes, joined in fp32.  transpose == 0: out = G * Z
  * (M = g_rows, Z is [g_cols, dim]); transpose != 0: out = G^T * Z (M = g_cols, Z is [g_rows, dim]).
  * The autograd backward of torch.matmul in pig/util.py:13 / pig/loss.py:19. */
 int pb2_grad_gemm(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, int transpose,
@@ -183,6 +196,12 @@ int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_
 int pb2_rows_scale_f16(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
                        int64_t ld_out, void* stream);
 
+/* The kind::i8 form of the same operand, for a one-byte (PB2_U8) gradient matrix: out [n, 2 dim] bytes =
+ * [hi plane (s8) | lo plane (u8)] of q = round(x * rinv * 32512) = 256 hi + lo (16 bits, one scale per tensor);
+ * pass it to pb2_grad_gemm* as z with z_dtype = PB2_I8_PLANES and ldz = ld_out (bytes). */
+int pb2_rows_quant_i8(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
+                      int64_t ld_out, void* stream);
+
 /* y0 = T(x0 * coef[0]), y1 = T(x1 * coef[0]) (x fp32, coef on the device; T = out_dtype PB2_BF16 / PB2_F16 /
  * PB2_F32; n_elems per array, whole 16-byte output vectors): the backward of pig/loss.py's scalar losses, whose
  * gradients are produced in the forward and kept in fp32 -- autograd's grad_output (e.g. a GradScaler's 65536
@@ -207,11 +226,12 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
  * col_cnt_i)) (NaN when a row norm is zero); d_v / d_a are [n, dim] in out_dtype (PB2_F32/BF16/F16).
  * Between them: pb2_sim_hinge with n_partials passed
  * NEGATIVE (= "already zeroed", no memset) and two pb2_grad_gemm.  v / a are bf16 / fp16 / fp32 rows (dtype);
- * for fp32 rows pb2_hinge_prep also writes their split-bf16 tensor-core operands v_split / a_split
- * ([n, 3 dim] bf16, see pb2_split_bf16; NULL otherwise). */
+ * for fp32 rows pb2_hinge_prep also writes their split-fp16 tensor-core operands v_split / a_split
+ * ([n, 3 dim] fp16) and scales scale_v / scale_a ([n] fp32), see pb2_split_f16; all NULL otherwise. */
 int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
                    float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
-                   float* loss_partial, int n_partials, void* v_split, void* a_split, void* stream);
+                   float* loss_partial, int n_partials, void* v_split, void* a_split, float* scale_v, float* scale_a,
+                   void* stream);
 int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv,
                       int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag, const int32_t* row_cnt,
                       const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,

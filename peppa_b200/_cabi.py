@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpeppa_b200.so")
 MEASURE_LIB_PATH = os.path.join(_HERE, "csrc", "libpeppa_b200_measure.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "peppa_b200.h")
 
-PB2_BF16, PB2_F16, PB2_F32 = 0, 1, 2
+PB2_BF16, PB2_F16, PB2_F32, PB2_U8, PB2_I8_PLANES = 0, 1, 2, 3, 4
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -30,13 +30,14 @@ SIGNATURES = {
     "pb2_sim_grid": [],
     "pb2_triplet_score": [_p, _p, _p, _p, _p, _p, _i64, _i, _i64, _i, _i, _p, _p],
     "pb2_row_norms": [_p, _i, _i64, _i, _i64, _p, _p, _p],
-    "pb2_split_bf16": [_p, _i64, _i, _i64, _i, _p, _i64, _p],
+    "pb2_split_f16": [_p, _p, _i64, _i, _i64, _i, _p, _i64, _p, _p],
     "pb2_pair_dot": [_p, _p, _i, _p, _p, _p, _p, _i64, _i, _i64, _i64, _p, _p, _p, _p],
     "pb2_sim_diag": [_p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _p, _p, _p, _p],
     "pb2_sim_matrix": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p],
     "pb2_sim_rank": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i64, _i64, _p, _p],
     "pb2_subset_rank": [_p, _i64, _p, _i, _i, _p, _p],
-    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i64, _p, _p, _p],
+    "pb2_sim_hinge": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i, _p, _p, _p, _i, _i64, _p, _p, _p],
+    "pb2_rows_quant_i8": [_p, _i, _p, _i64, _i, _i64, _p, _i64, _p],
     "pb2_sim_lse_parts": [_i64],
     "pb2_sim_lse_rows": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _p, _p],
     "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
@@ -50,7 +51,7 @@ SIGNATURES = {
     "pb2_grad_gemm_ws": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p, _i64, _p],
     "pb2_grad_gemm_dual": [_p, _i, _i64, _i64, _i64, _p, _p, _i, _i, _i64, _i64, _f, _p, _p, _i64, _i64, _p],
     "pb2_hinge_finish": [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
-    "pb2_hinge_prep": [_p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    "pb2_hinge_prep": [_p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
     "pb2_hinge_step_workspace": [_i64, _i, _i],
     "pb2_hinge_step": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],

@@ -274,6 +274,18 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::i8 (u8 / s8 operands, s32 accumulate; K = 32 per instruction) on a CTA pair: the one-byte gradient matrix
+__device__ __forceinline__ void umma_i8_pair_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive (once all previously issued MMAs completed) on the barrier at this smem offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile(
@@ -292,6 +304,13 @@ enum : uint32_t { kMajorK = 0, kMajorMN = 1 };
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n, uint32_t a_fmt, uint32_t b_fmt,
                                                   uint32_t a_major, uint32_t b_major) {
     return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_major << 15) | (b_major << 16) | ((n >> 3) << 17) |
+           ((m >> 4) << 24);
+}
+// kind::i8: D format 2 = s32, A / B format 0 = u8, 1 = s8 (probed on B200: tools/ubench/i8mma.cu)
+enum : uint32_t { kFmtU8 = 0, kFmtS8 = 1 };
+__host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t m, uint32_t n, uint32_t a_fmt, uint32_t b_fmt,
+                                                     uint32_t a_major, uint32_t b_major) {
+    return (2u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_major << 15) | (b_major << 16) | ((n >> 3) << 17) |
            ((m >> 4) << 24);
 }
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:

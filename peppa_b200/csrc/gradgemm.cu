@@ -50,6 +50,7 @@ struct Args {
     int n_groups;
     uint32_t* flags;  // [grid] arrival counters, zero between launches
     float4* parts;    // [grid][BN/4][128] raw accumulators of a CTA's tail segment
+    int z_lo_col;     // kind::i8 variant: first column of the low plane inside the two-plane embedding operand
 };
 
 template <int BN, int kCtas>
@@ -358,6 +359,248 @@ __global__ void __launch_bounds__(kThreads, 1)
     else gg_body<true, BN, 1>(tm_g1, tm_z1, a1, (int)blockIdx.x - n0, (int)gridDim.x - n0);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// kind::i8 variant: the hinge gradient matrix holds exactly {0, 1, 2}, so it travels as ONE byte per entry (u8,
+// written by sim.cu's HingePolicyT<.., true>) -- half the HBM bytes on the way out of the similarity pass and on
+// both ways into the gradient products.  The embedding operand is q = round(xhat * 32512) = 256 hi + lo as two
+// 8-bit planes [K, 2 dim] = [hi (s8) | lo (u8)] (pb2_rows_quant_i8: 16 bits, one scale for the tensor); the two
+// products G hi and G lo accumulate EXACTLY in s32 (|G hi| <= 2 * 127 * K < 2^31 for any block), and the epilogue
+// joins them: out (+)= alpha / 32512 * (256 acc_hi + acc_lo).  tcgen05.mma.kind::i8 issues 2.3x the MACs per second of
+// kind::f16 from the same operand bytes (tools/ubench/i8mma.cu), so two planes cost no more tensor time than the fp16
+// product they replace.
+//
+// CTA pairs only (cta_group::2, M = 256); a pair tile is 256 rows x 256 output columns, its two s32 accumulators
+// (hi plane at TMEM columns [0, 256), lo plane at [256, 512)) fill the 128 x 512 TMEM of each CTA: one accumulator
+// stage, like the 512-wide fp16 tile.  A stage of the TMA ring is 128 k-bytes deep:
+//   A = G   (transpose == 0): K-major   [128 rows x 128 k] u8          16 KiB  (+32 B per K = 32 instruction)
+//   A = G^T (transpose != 0): MN-major  [128 k-rows x 128 m] u8        16 KiB  (+4096 B per instruction, SBO 1024)
+//   B planes, always MN-major: [128 k-rows x 128 n] s8 and u8           2 x 16 KiB (this CTA's half of the 256 columns)
+// Stream-K, the parked accumulators and the fold are those of gg_body; the fold adds integers, so a cut row block is
+// bit-identical to an uncut one.
+namespace i8 {
+constexpr int kBK8 = 128, kUK8 = 32, BN_OUT = 256;
+constexpr int kTileA = BM * kBK8, kTileB = (BN_OUT / 2) * kBK8;
+constexpr int kStageBytes = kTileA + 2 * kTileB;
+constexpr int kStages = 4;
+constexpr int kTileBytes = kStages * kStageBytes;
+constexpr int kTotal = 1024 + kTileBytes + 256;
+constexpr int kTmemCols = 512;
+constexpr float kScale = 32512.0f;  // 127 * 256: q = round(xhat * kScale) in [-32512, 32512] = 256 * [-127, 127] + [0, 255]
+}  // namespace i8
+
+template <bool kTranspose>
+__global__ void __launch_bounds__(kThreads, 1)
+    grad_gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z, const Args a) {
+    using namespace i8;
+    constexpr int kCtas = 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTileBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* acc_full = bars + 2 * kStages;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int block = (int)blockIdx.x, nblocks = (int)gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+    if (warp == kTmaWarp && lane == 0) {
+        tma_prefetch_desc(&tm_g);
+        tma_prefetch_desc(&tm_z);
+    }
+    if (warp == kMmaWarp && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kEpiWarps * kCtas);  // the leader's collects both CTAs' epilogues
+        fence_mbar_init();
+    }
+    if (warp == kTmaWarp) tmem_alloc_pair(tmem_slot, kTmemCols);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == kTmaWarp) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for_each_segment<kCtas>(a, block, nblocks, [&](int rb, int cb, int kb0, int kb1) {
+                const int row0 = (rb * kCtas + (int)crank) * BM;
+                const int ncol = cb * BN_OUT + (int)crank * (BN_OUT / 2);  // this CTA's half of the tile's output columns
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sb_hi = sa + kTileA;
+                    uint8_t* sb_lo = sb_hi + kTileB;
+                    if (crank == 0) mbar_arrive_expect_tx(full + stage, kStageBytes * kCtas);
+                    const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+                    if (!kTranspose) tma_load_2d_pair(sa, &tm_g, lbar, kb * kBK8, row0, kEvictFirst);
+                    else tma_load_2d_pair(sa, &tm_g, lbar, row0, kb * kBK8, kEvictFirst);
+                    tma_load_2d_pair(sb_hi, &tm_z, lbar, ncol, kb * kBK8, kEvictLast);
+                    tma_load_2d_pair(sb_lo, &tm_z, lbar, a.z_lo_col + ncol, kb * kBK8, kEvictLast);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            });
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t kAMajor = kTranspose ? kMajorMN : kMajorK;
+            constexpr uint32_t idesc_hi = make_idesc_i8(BM * kCtas, BN_OUT, kFmtU8, kFmtS8, kAMajor, kMajorMN);
+            constexpr uint32_t idesc_lo = make_idesc_i8(BM * kCtas, BN_OUT, kFmtU8, kFmtU8, kAMajor, kMajorMN);
+            // K-major G tile: 128-byte rows, 8-row atoms (SBO 1024).  MN-major tiles: 128 bytes along M / N per k-row,
+            // 8 k-rows per 1024-byte atom (SBO 1024); a tile is ONE 128-element chunk along M / N, so LBO (the distance
+            // between such chunks) is never used -- set to the tile size.
+            const uint64_t dk = make_smem_desc(smem_u32(smem), 16, 1024);
+            const uint64_t dm = make_smem_desc(smem_u32(smem), 16384, 1024);
+            const uint32_t a_hi = (uint32_t)((kTranspose ? dm : dk) >> 32), b_hi = (uint32_t)(dm >> 32);
+            const uint32_t a_lo0 = (uint32_t)(kTranspose ? dm : dk), b_lo0 = (uint32_t)dm + (kTileA >> 4);
+            constexpr uint32_t a_kstep = kTranspose ? (kUK8 * 128) >> 4 : kUK8 >> 4;  // 32 k-rows of 128 B, or 32 bytes along a row
+            constexpr uint32_t b_kstep = (kUK8 * 128) >> 4;
+            constexpr uint32_t kStageLo = kStageBytes >> 4, kPlaneLo = kTileB >> 4;
+            int stage = 0;
+            uint32_t phase = 0, a_lo = a_lo0, b_lo = b_lo0;
+            int64_t it = 0;
+            for_each_segment<kCtas>(a, block, nblocks, [&](int, int, int kb0, int kb1) {
+                mbar_wait(acc_empty, (uint32_t)(it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < kBK8 / kUK8; ++k) {
+                        const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+                        umma_i8_pair_lohi(tmem_base, a_lo + k * a_kstep, b_lo + k * b_kstep, a_hi, b_hi, idesc_hi, acc);
+                        umma_i8_pair_lohi(tmem_base + BN_OUT, a_lo + k * a_kstep, b_lo + kPlaneLo + k * b_kstep, a_hi, b_hi,
+                                          idesc_lo, acc);
+                    }
+                    umma_commit_pair(empty + stage);
+                    a_lo += kStageLo;
+                    b_lo += kStageLo;
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                        a_lo = a_lo0;
+                        b_lo = b_lo0;
+                    }
+                }
+                umma_commit_pair(acc_full);
+                ++it;
+            });
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - kEpiWarp0) >> 2;  // which 128 of the tile's 256 output columns
+        int64_t it = 0;
+        for_each_segment<kCtas>(a, block, nblocks, [&](int rb, int cb, int kb0, int kb1) {
+            const int64_t row = ((int64_t)rb * kCtas + crank) * BM + quad * 32 + lane;
+            const bool park = kb0 > 0, fold = kb1 < a.kblocks;
+            const uint32_t peer = (uint32_t)block + (uint32_t)(a.n_cb * kCtas);  // same tile slot, next group
+            if (fold) {
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    uint32_t ns = 100;
+                    while (ld_acquire_u32(a.flags + peer) < (uint32_t)kEpiWarps) {  // see gg_body: late is legal
+                        __nanosleep(ns);
+                        if (ns < 8000) ns <<= 1;
+                        if (clock64() - t0 > 64 * PB2_WAIT_TIMEOUT_CYCLES) {
+                            printf("pb2: grad_gemm_i8 stream-K flag wait gave up after minutes (block %d)\n", block);
+                            __trap();
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            mbar_wait(acc_full, (uint32_t)(it & 1));
+            tc_fence_after();
+            const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int cbase = half * 128 + ch * 32;  // output column of the chunk inside the tile = TMEM column of its hi part
+                uint32_t vh[32], vl[32];
+                tmem_ld32(t_lane + cbase, vh);
+                tmem_ld32(t_lane + BN_OUT + cbase, vl);
+                tmem_ld_wait();
+                if (park) {  // raw s32 accumulators, [512 / 4][128] uint4 per CTA: consecutive lanes write consecutive 16 bytes
+                    float4* dh = a.parts + ((size_t)block * (kTmemCols / 4) + cbase / 4) * BM + quad * 32 + lane;
+                    float4* dl = dh + (size_t)(BN_OUT / 4) * BM;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        dh[j * BM] = make_float4(__uint_as_float(vh[4 * j]), __uint_as_float(vh[4 * j + 1]),
+                                                 __uint_as_float(vh[4 * j + 2]), __uint_as_float(vh[4 * j + 3]));
+                        dl[j * BM] = make_float4(__uint_as_float(vl[4 * j]), __uint_as_float(vl[4 * j + 1]),
+                                                 __uint_as_float(vl[4 * j + 2]), __uint_as_float(vl[4 * j + 3]));
+                    }
+                    continue;
+                }
+                if (fold) {  // integer adds: exact, order-free
+                    const float4* sh = a.parts + ((size_t)peer * (kTmemCols / 4) + cbase / 4) * BM + quad * 32 + lane;
+                    const float4* sl = sh + (size_t)(BN_OUT / 4) * BM;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 oh = __ldcg(sh + j * BM), ol = __ldcg(sl + j * BM);
+                        vh[4 * j] += __float_as_uint(oh.x);
+                        vh[4 * j + 1] += __float_as_uint(oh.y);
+                        vh[4 * j + 2] += __float_as_uint(oh.z);
+                        vh[4 * j + 3] += __float_as_uint(oh.w);
+                        vl[4 * j] += __float_as_uint(ol.x);
+                        vl[4 * j + 1] += __float_as_uint(ol.y);
+                        vl[4 * j + 2] += __float_as_uint(ol.z);
+                        vl[4 * j + 3] += __float_as_uint(ol.w);
+                    }
+                }
+                if (row < a.m) {
+                    float* dst = a.out + row * a.ld_out + (int64_t)cb * BN_OUT + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        // both accumulators are exact integers below 2^24 in magnitude for K <= 32768: exact in fp32
+                        float4 o = make_float4(fmaf((float)(int)vh[j], 256.f, (float)(int)vl[j]) * a.alpha,
+                                               fmaf((float)(int)vh[j + 1], 256.f, (float)(int)vl[j + 1]) * a.alpha,
+                                               fmaf((float)(int)vh[j + 2], 256.f, (float)(int)vl[j + 2]) * a.alpha,
+                                               fmaf((float)(int)vh[j + 3], 256.f, (float)(int)vl[j + 3]) * a.alpha);
+                        if (a.accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                            o.x += old.x;
+                            o.y += old.y;
+                            o.z += old.z;
+                            o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty), 0));
+            if (park) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) red_release_add_u32(a.flags + block, 1u);
+            }
+            if (fold) {
+                named_bar_sync(1, kEpiWarps * 32);
+                if (warp == kEpiWarp0 && lane == 0) a.flags[peer] = 0u;
+            }
+            ++it;
+        });
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kTmaWarp) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
 PB2_KNOB_U32 g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kstep = 2048;
 PB2_KNOB g_units_cap = 0;
 
@@ -394,6 +637,7 @@ static int prepare(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int
     a.n_groups = 0;
     a.flags = nullptr;
     a.parts = nullptr;
+    a.z_lo_col = 0;
     return PB2_OK;
 }
 
@@ -429,6 +673,56 @@ static int launch(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int6
                     "grad_gemm launch");
     if (rc) return rc;
     return check_launch("grad_gemm");
+}
+
+
+// out (=|+=) alpha * op(G) * Xhat for a one-byte G and the two-plane embedding operand (see grad_gemm_i8_kernel).
+template <bool kTranspose>
+static int launch_i8(const void* g, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z, int dim, int64_t ldz, float alpha,
+                     int accumulate, float* out, int64_t ld_out, void* workspace, cudaStream_t st) {
+    const int64_t m = kTranspose ? g_cols : g_rows;
+    const int64_t k = kTranspose ? g_rows : g_cols;
+    CUtensorMap tg, tz;
+    int rc = make_tmap_2d(&tg, g, 1, (uint64_t)g_rows, (uint64_t)g_cols, (uint64_t)ld_g, 128, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tz, z, 1, (uint64_t)k, (uint64_t)(2 * dim), (uint64_t)ldz, 128, 128);
+    if (rc) return rc;
+    Args a;
+    a.m = m;
+    a.k = k;
+    a.n_rb = (int)((m + 2 * BM - 1) / (2 * BM));
+    a.n_cb = dim / i8::BN_OUT;
+    a.n_tiles = (int64_t)a.n_rb * a.n_cb;
+    a.kblocks = (int)((k + i8::kBK8 - 1) / i8::kBK8);
+    a.alpha = alpha / i8::kScale;
+    a.accumulate = accumulate;
+    a.out = out;
+    a.ld_out = ld_out;
+    a.mn_lbo = a.mn_sbo = a.mn_kstep = a.idesc = 0;
+    a.n_groups = 0;
+    a.flags = nullptr;
+    a.parts = nullptr;
+    a.z_lo_col = dim;
+    int units = sm_count() / 2;
+    if (g_units_cap > 0 && g_units_cap < units) units = g_units_cap;
+    if (workspace && a.n_cb <= units && units * 2 <= 256) {
+        const int groups = units / a.n_cb;
+        const int64_t total = (int64_t)a.n_rb * a.kblocks;
+        if (a.n_tiles > units && a.n_tiles % units != 0 && total / groups >= a.kblocks) {
+            a.n_groups = groups;
+            a.flags = static_cast<uint32_t*>(workspace);
+            a.parts = reinterpret_cast<float4*>(static_cast<char*>(workspace) + kFlagBytes);
+        }
+    }
+    auto kern = grad_gemm_i8_kernel<kTranspose>;
+    static PerDeviceOnce configured;
+    rc = ensure_dynamic_smem(configured, kern, i8::kTotal, "grad_gemm_i8");
+    if (rc) return rc;
+    const int n_units = a.n_groups > 0 ? a.n_groups * a.n_cb : (int)std::min<int64_t>(a.n_tiles, units);
+    rc = check_cuda(launch_ex(kern, (unsigned)(n_units * 2), (unsigned)kThreads, (size_t)i8::kTotal, st, 2, tg, tz, a),
+                    "grad_gemm_i8 launch");
+    if (rc) return rc;
+    return check_launch("grad_gemm_i8");
 }
 
 // out0 = G Z0 and out1 = G^T Z1 in one grid (every tile of both products resident at once).
@@ -519,6 +813,19 @@ extern "C" int pb2_grad_gemm_ws(const void* gmat, int g_dtype, int64_t g_rows, i
     if (dim <= 0 || dim % 64 != 0) return set_error(PB2_ERR_ARG, "grad_gemm: dim must be a multiple of 64");
     if ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 4 != 0)
         return set_error(PB2_ERR_ARG, "grad_gemm: out must be 16-byte aligned with ld_out %% 4 == 0");
+    if (g_dtype == PB2_U8 || z_dtype == PB2_I8_PLANES) {  // one-byte gradient matrix x two-plane embeddings: kind::i8
+        if (g_dtype != PB2_U8 || z_dtype != PB2_I8_PLANES)
+            return set_error(PB2_ERR_ARG, "grad_gemm: a PB2_U8 gradient matrix goes with a PB2_I8_PLANES operand (pb2_rows_quant_i8)");
+        if (dim % 256 != 0) return set_error(PB2_ERR_ARG, "grad_gemm: the kind::i8 path needs dim %% 256 == 0");
+        if (ldz < 2 * (int64_t)dim) return set_error(PB2_ERR_ARG, "grad_gemm: the two-plane operand is [K, 2 dim] bytes");
+        if ((transpose ? g_rows : g_cols) > (1 << 15))
+            return set_error(PB2_ERR_ARG, "grad_gemm: kind::i8 contraction length is limited to 32768 per call (exact fp32 join)");
+        if (transpose)
+            return gg::launch_i8<true>(gmat, g_rows, g_cols, ld_g, z, dim, ldz, alpha, accumulate, out, ld_out, workspace,
+                                       (cudaStream_t)stream);
+        return gg::launch_i8<false>(gmat, g_rows, g_cols, ld_g, z, dim, ldz, alpha, accumulate, out, ld_out, workspace,
+                                    (cudaStream_t)stream);
+    }
     if ((g_dtype != PB2_F16 && g_dtype != PB2_BF16) || (z_dtype != PB2_F16 && z_dtype != PB2_BF16))
         return set_error(PB2_ERR_ARG, "grad_gemm: operands must be fp16 or bf16");
     cudaStream_t st = (cudaStream_t)stream;

@@ -64,7 +64,10 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t ro
     if (!fn) return set_error(PB2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_bytes & 15))
         return set_error(PB2_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
-    CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    // the data type only matters for out-of-bounds fill and interleaving, neither of which is used: 16-bit data of
+    // either format travels as BFLOAT16, bytes as UINT8
+    CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                             : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};

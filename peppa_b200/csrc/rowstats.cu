@@ -26,12 +26,12 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
 
 // Eight consecutive row elements as fp32, for the three input dtypes the reference's callers use (fp32 tensors,
 // fp16 under Lightning's `precision: 16`, bf16): the row-wise kernels read the TRUE input values -- only the tensor-
-// core operands are 16-bit (an fp32 matrix goes there as a split-bf16 pair, pb2_split_bf16).
+// core operands are 16-bit (an fp32 matrix goes there as a split-fp16 pair, pb2_split_f16).
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float (&f)[8]);
 template <>
 __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
-    load8(p, f);
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(p), f);
 }
 template <>
 __device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
@@ -97,6 +97,36 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e] * s, f[2 * e + 1] * s);
         *reinterpret_cast<uint4*>(out + r * ld_out + d) = *reinterpret_cast<const uint4*>(h);
+    }
+}
+
+// Two-plane 8-bit embedding operand of the kind::i8 gradient GEMMs: q = round(x * rinv * 32512) in [-32512, 32512]
+// (|x * rinv| <= 1 up to rounding; clamped), q = 256 hi + lo with hi in [-127, 127] (s8) and lo in [0, 255] (u8);
+// out row = [hi plane (dim bytes) | lo plane (dim bytes)].  16 bits with one scale for the tensor: the quantisation
+// step 3e-5 is ~7e-4 of a typical component of a 512-d unit vector and averages out over the >= 10^4 terms of a
+// gradient row (measured: DESIGN section 4.2).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    rows_quant_i8_kernel(const T* __restrict__ x, const float* __restrict__ rinv, int64_t n, int dim, int64_t ld,
+                         uint8_t* __restrict__ out, int64_t ld_out) {
+    const int vec_per_row = dim / 8;
+    const int64_t total = n * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / vec_per_row;
+        const int d = (int)(i % vec_per_row) * 8;
+        float f[8];
+        load8(x + r * ld + d, f);
+        const float s = (rinv ? rinv[r] : 1.f) * 32512.0f;
+        uint32_t hi[2] = {0u, 0u}, lo[2] = {0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float qf = fminf(fmaxf(rintf(f[e] * s), -32512.0f), 32512.0f);  // NaN (zero-norm row) -> -32512: any finite value
+            const int q = (int)qf;
+            hi[e >> 2] |= ((uint32_t)(q >> 8) & 0xffu) << (8 * (e & 3));   // arithmetic shift = floor division
+            lo[e >> 2] |= ((uint32_t)q & 0xffu) << (8 * (e & 3));
+        }
+        *reinterpret_cast<uint2*>(out + r * ld_out + d) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(out + r * ld_out + dim + d) = make_uint2(lo[0], lo[1]);
     }
 }
 
@@ -295,42 +325,68 @@ __global__ void __launch_bounds__(1024) milnce_loss_kernel(const float* __restri
     }
 }
 
-// ------------------------------------------------------------------- split-bf16 operands (fp32 inputs)
-// An fp32 matrix reaches the bf16 tensor cores as x = hi + lo (hi = bf16(x), lo = bf16(x - hi): 16 significand bits),
-// and  <x, y> ~= <hi_x, hi_y> + <lo_x, hi_y> + <hi_x, lo_y>  is ONE GEMM of contraction length 3 D over the
-// concatenated rows  X' = [hi | lo | hi]  (side 0)  and  Y' = [hi | hi | lo]  (side 1): no kernel of sim.cu changes,
-// the fp32 accumulator sums the three products.  The dropped lo*lo term and lo's own rounding are ~2^-18 per
-// product, i.e. ~2e-7 absolute on a cosine of 512-d unit vectors -- below the 1e-6 tie window of the rank parity bar.
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    __nv_bfloat162 h[4], l[4];
+// ------------------------------------------------------------------- split-fp16 operands (fp32 inputs)
+// An fp32 matrix reaches the 16-bit tensor cores as x' = hi + lo with hi = fp16(x'), lo = fp16(x' - hi) (22 significant
+// bits), where x' = x * r * 2^e is the row scaled (r = its 1/||x|| if given) and shifted so that its largest component
+// lies in [512, 1024): fp16's range is never an issue and lo never goes subnormal for components that matter.  Then
+//     <x'_i, y'_j> ~= <hi_x, hi_y> + <lo_x, hi_y> + <hi_x, lo_y>
+// is ONE kind::f16 GEMM of contraction length 3 D over the concatenated rows X' = [hi | lo | hi] (side 0) and
+// Y' = [hi | hi | lo] (side 1) -- no kernel of sim.cu changes, the fp32 accumulator sums the three products -- and the
+// epilogue's per-row factors are the exact powers of two 2^-e (scale_out) instead of 1/||x||.  The dropped lo*lo term
+// and lo's own rounding are ~2^-22 per product: ~2e-8 absolute on a cosine of 512-d unit vectors, far inside the 1e-6
+// tie window of the rank parity bar (a bf16 split, 16 bits, would leave ~7e-7 and fail it -- measured).
+__device__ __forceinline__ void split8_f16(const float (&x)[8], uint4& hi, uint4& lo) {
+    __half2 h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        h[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-        const float2 hf = __bfloat1622float2(h[e]);
-        l[e] = __floats2bfloat162_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+        h[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+        const float2 hf = __half22float2(h[e]);
+        l[e] = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
     }
     hi = *reinterpret_cast<const uint4*>(h);
     lo = *reinterpret_cast<const uint4*>(l);
 }
 // out row = [hi | lo | hi] (side 0) or [hi | hi | lo] (side 1), each part `dim` wide
-__device__ __forceinline__ void store_split(__nv_bfloat16* out_row, int dim, int d, int side, const uint4& hi, const uint4& lo) {
+__device__ __forceinline__ void store_split(__half* out_row, int dim, int d, int side, const uint4& hi, const uint4& lo) {
     *reinterpret_cast<uint4*>(out_row + d) = hi;
     *reinterpret_cast<uint4*>(out_row + dim + d) = side ? hi : lo;
     *reinterpret_cast<uint4*>(out_row + 2 * dim + d) = side ? lo : hi;
 }
+// exponent e with max * 2^e in [512, 1024) (0 for a zero / non-finite row: NaN and inf then propagate like the reference's)
+__device__ __forceinline__ int split_exponent(float row_max) {
+    if (!(row_max > 0.f) || !(row_max <= 3.0e38f)) return 0;
+    return max(-120, min(120, 9 - ilogbf(row_max)));
+}
+// one warp per row
 __global__ void __launch_bounds__(256)
-    split_bf16_kernel(const float* __restrict__ x, int64_t n, int dim, int64_t ld, int side, __nv_bfloat16* __restrict__ out,
-                      int64_t ld_out) {
-    const int vec_per_row = dim / 8;
-    const int64_t total = n * vec_per_row;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / vec_per_row;
-        const int d = (int)(i % vec_per_row) * 8;
-        float f[8];
-        load8(x + r * ld + d, f);
-        uint4 hi, lo;
-        split8(f, hi, lo);
-        store_split(out + r * ld_out, dim, d, side, hi, lo);
+    split_f16_kernel(const float* __restrict__ x, const float* __restrict__ rinv, int64_t n, int dim, int64_t ld, int side,
+                     __half* __restrict__ out, int64_t ld_out, float* __restrict__ scale_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const float* row = x + r * ld;
+        const float ri = rinv ? rinv[r] : 1.f;
+        float m = 0.f;
+        for (int d = lane * 8; d < dim; d += 256) {
+            float f[8];
+            load8(row + d, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m = fmaxf(m, fabsf(f[e] * ri));  // fmaxf drops NaN: a NaN row keeps e = 0 ...
+        }
+        m = warp_max(m);
+        const int e = split_exponent(m);
+        const float s = ldexpf(ri, e);                                   // ... and NaN / inf reach the operand through s
+        for (int d = lane * 8; d < dim; d += 256) {
+            float f[8];
+            load8(row + d, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] *= s;
+            uint4 hi, lo;
+            split8_f16(f, hi, lo);
+            store_split(out + r * ld_out, dim, d, side, hi, lo);
+        }
+        if (lane == 0) scale_out[r] = ldexpf(1.f, -e);
     }
 }
 
@@ -344,7 +400,8 @@ __global__ void __launch_bounds__(256)
                       int64_t ldv, int64_t lda, float* __restrict__ rinv_v, float* __restrict__ rinv_a,
                       float* __restrict__ diag, __half* __restrict__ vh, __half* __restrict__ ah,
                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
-                      int n_partials, __nv_bfloat16* __restrict__ vx, __nv_bfloat16* __restrict__ ax) {
+                      int n_partials, __half* __restrict__ vx, __half* __restrict__ ax, float* __restrict__ scale_v,
+                      float* __restrict__ scale_a) {
     pdl_launch_dependents();
     pdl_wait();  // the workspace may still be read by the previous step's kernels
     const int lane = threadIdx.x & 31;
@@ -355,7 +412,7 @@ __global__ void __launch_bounds__(256)
     for (int64_t r = warp; r < n; r += nwarps) {
         const T* vr = v + r * ldv;
         const T* ar = a + r * lda;
-        float sv = 0.f, sa = 0.f, dot = 0.f;
+        float sv = 0.f, sa = 0.f, dot = 0.f, mv = 0.f, ma = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
             load8(vr + d, x);
@@ -365,18 +422,31 @@ __global__ void __launch_bounds__(256)
                 sv = fmaf(x[e], x[e], sv);
                 sa = fmaf(y[e], y[e], sa);
                 dot = fmaf(x[e], y[e], dot);
+                mv = fmaxf(mv, fabsf(x[e]));
+                ma = fmaxf(ma, fabsf(y[e]));
             }
         }
         sv = warp_sum(sv);
         sa = warp_sum(sa);
         dot = warp_sum(dot);
         const float rv = 1.0f / sqrtf(sv), ra = 1.0f / sqrtf(sa);
+        // fp32 inputs: split-fp16 tensor-core operands of the NORMALISED rows (see split_f16_kernel)
+        int ev = 0, ea = 0;
+        if (vx) {
+            ev = split_exponent(warp_max(mv) * rv);
+            ea = split_exponent(warp_max(ma) * ra);
+        }
+        const float s_v = ldexpf(rv, ev), s_a = ldexpf(ra, ea);
         if (lane == 0) {
             rinv_v[r] = rv;
             rinv_a[r] = ra;
             diag[r] = __fmul_rn(__fmul_rn(dot, rv), ra);
             row_cnt[r] = 0;
             col_cnt[r] = 0;
+            if (vx) {
+                scale_v[r] = ldexpf(1.f, -ev);
+                scale_a[r] = ldexpf(1.f, -ea);
+            }
         }
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
@@ -390,11 +460,16 @@ __global__ void __launch_bounds__(256)
             }
             *reinterpret_cast<uint4*>(vh + r * dim + d) = *reinterpret_cast<const uint4*>(hx);
             *reinterpret_cast<uint4*>(ah + r * dim + d) = *reinterpret_cast<const uint4*>(hy);
-            if (vx) {  // fp32 inputs: split-bf16 tensor-core operands [n, 3 dim] (S = V A^T: V is side 0, A side 1)
+            if (vx) {  // split-fp16 tensor-core operands [n, 3 dim] (S = V A^T: V is side 0, A side 1)
                 uint4 hi, lo;
-                split8(x, hi, lo);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    x[e] *= s_v;
+                    y[e] *= s_a;
+                }
+                split8_f16(x, hi, lo);
                 store_split(vx + r * 3 * dim, dim, d, 0, hi, lo);
-                split8(y, hi, lo);
+                split8_f16(y, hi, lo);
                 store_split(ax + r * 3 * dim, dim, d, 1, hi, lo);
             }
         }
@@ -740,16 +815,15 @@ extern "C" int pb2_row_norms(const void* x, int dtype, int64_t n, int dim, int64
     return check_launch("row_norms");
 }
 
-extern "C" int pb2_split_bf16(const float* x, int64_t n, int dim, int64_t ld, int side, void* out, int64_t ld_out,
-                              void* stream) {
+extern "C" int pb2_split_f16(const float* x, const float* rinv, int64_t n, int dim, int64_t ld, int side, void* out,
+                             int64_t ld_out, float* scale_out, void* stream) {
     if (n <= 0) return PB2_OK;
-    if (!x || !out || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 4) || !vec_ok(out, ld_out, 2) || ld_out < 3 * (int64_t)dim ||
-        (side != 0 && side != 1))
-        return set_error(PB2_ERR_ARG, "split_bf16: need fp32 rows, dim %% 8 == 0, 16-byte aligned, ld_out >= 3 dim, side 0 / 1");
-    const int64_t total = n * (dim / 8);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
-    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, dim, ld, side, (__nv_bfloat16*)out, ld_out);
-    return check_launch("split_bf16");
+    if (!x || !out || !scale_out || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, 4) || !vec_ok(out, ld_out, 2) ||
+        ld_out < 3 * (int64_t)dim || (side != 0 && side != 1))
+        return set_error(PB2_ERR_ARG, "split_f16: need fp32 rows, dim %% 8 == 0, 16-byte aligned, ld_out >= 3 dim, side 0 / 1");
+    split_f16_kernel<<<grid_for_warps(n), 256, 0, (cudaStream_t)stream>>>(x, rinv, n, dim, ld, side, (__half*)out, ld_out,
+                                                                         scale_out);
+    return check_launch("split_f16");
 }
 
 extern "C" int pb2_rows_scale_f16(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
@@ -763,6 +837,19 @@ extern "C" int pb2_rows_scale_f16(const void* x, int dtype, const float* rinv, i
     PB2_ROWS_DISPATCH(dtype, rows_scale_f16_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, rinv, n, dim, ld,
                                                                                             (__half*)out, ld_out));
     return check_launch("rows_scale_f16");
+}
+
+extern "C" int pb2_rows_quant_i8(const void* x, int dtype, const float* rinv, int64_t n, int dim, int64_t ld, void* out,
+                                 int64_t ld_out, void* stream) {
+    if (n <= 0) return PB2_OK;
+    const int es = elem_bytes(dtype);
+    if (!x || !out || !es || dim <= 0 || dim % 8 != 0 || !vec_ok(x, ld, es) || !vec_ok(out, ld_out, 1) || ld_out < 2 * (int64_t)dim)
+        return set_error(PB2_ERR_ARG, "rows_quant_i8: need bf16 / fp16 / fp32 rows, dim %% 8 == 0, 16-byte aligned, ld_out >= 2 dim");
+    const int64_t total = n * (dim / 8);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    PB2_ROWS_DISPATCH(dtype, rows_quant_i8_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, rinv, n, dim, ld,
+                                                                                           (uint8_t*)out, ld_out));
+    return check_launch("rows_quant_i8");
 }
 
 extern "C" int pb2_scale_pair(const float* x0, const float* x1, int64_t n_elems, int out_dtype, const float* coef,
@@ -874,21 +961,22 @@ extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, con
 extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda,
                               float* rinv_v, float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt,
                               int32_t* col_cnt, float* loss_partial, int n_partials, void* v_split, void* a_split,
-                              void* stream) {
+                              float* scale_v, float* scale_a, void* stream) {
     if (n <= 0) return PB2_OK;
     if (!v || !a || !rinv_v || !rinv_a || !diag || !vh || !ah || !row_cnt || !col_cnt || !loss_partial)
         return set_error(PB2_ERR_ARG, "hinge_prep: null");
     const int es = elem_bytes(dtype);
     if (!es || dim % 8 != 0 || !vec_ok(v, ldv, es) || !vec_ok(a, lda, es) || !vec_ok(vh, dim, 2) || !vec_ok(ah, dim, 2))
         return set_error(PB2_ERR_ARG, "hinge_prep: dtype / alignment");
-    if ((v_split == nullptr) != (a_split == nullptr) || (v_split && (dtype != PB2_F32 || !vec_ok(v_split, 3 * (int64_t)dim, 2) ||
-                                                                     !vec_ok(a_split, 3 * (int64_t)dim, 2))))
-        return set_error(PB2_ERR_ARG, "hinge_prep: the split-bf16 outputs go together, for fp32 rows only");
+    if ((v_split == nullptr) != (a_split == nullptr) ||
+        (v_split && (dtype != PB2_F32 || !scale_v || !scale_a || !vec_ok(v_split, 3 * (int64_t)dim, 2) ||
+                     !vec_ok(a_split, 3 * (int64_t)dim, 2))))
+        return set_error(PB2_ERR_ARG, "hinge_prep: the split-fp16 outputs and their scales go together, for fp32 rows only");
     cudaError_t e;
     PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_prep_kernel<T>, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream,
                                            1, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
-                                           (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials, (__nv_bfloat16*)v_split,
-                                           (__nv_bfloat16*)a_split));
+                                           (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials, (__half*)v_split,
+                                           (__half*)a_split, scale_v, scale_a));
     int rc = check_cuda(e, "hinge_prep");
     if (rc) return rc;
     return check_launch("hinge_prep");

@@ -126,6 +126,16 @@ struct OutStage {
                 make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
         }
     }
+    // 32 bytes (two uint4) of this thread's row: chunk ch % 4 of a slab of 128 one-byte columns
+    __device__ __forceinline__ void write_u8(int lane, int c4, const uint32_t (&w)[8]) {
+        if (skip & 2) return;
+        uint8_t* row = buf + (slab & mask) * kOutSlabBytes + lane * 128;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c16 = (c4 * 2 + k) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(row + c16 * 16) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        }
+    }
     // 32 fp32 of this thread's row = one whole 128-byte swizzled row (slab = one 32-column chunk)
     __device__ __forceinline__ void write_f32(int lane, const float (&o)[32]) {
         uint8_t* row = buf + (slab & mask) * kOutSlabBytes + lane * 128;
@@ -168,6 +178,12 @@ struct OutStage {
         if ((ch & 1) == 0) begin_slab(lane);
         write(lane, ch & 1, packed);
         if (ch & 1) end_slab(lane, col_of_chunk - 32, row);
+    }
+    // One-byte gradient matrix: four 32-column chunks (8 words of 4 bytes per thread each) fill a slab of 128 columns.
+    __device__ __forceinline__ void stage_u8(int lane, int ch, const uint32_t (&w)[8], int32_t col_of_chunk, int32_t row) {
+        if ((ch & 3) == 0) begin_slab(lane);
+        write_u8(lane, ch & 3, w);
+        if ((ch & 3) == 3) end_slab(lane, col_of_chunk - 96, row);
     }
 };
 
@@ -219,6 +235,7 @@ constexpr int kMaxColRaw = 2, kMaxRowRaw = 4;
 // kStoresG (needs the OutStage), per-thread state as members.
 
 struct StorePolicy {
+    static constexpr bool kByteG = false;
     struct Params {
         float* out;
         int64_t ld;
@@ -258,6 +275,7 @@ struct StorePolicy {
 };
 
 struct RankPolicy {
+    static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     struct Params {
         const float* pos_thr;  // rank_threshold(fl32(1 - s_pos)) per row (pb2_sim_diag / pb2_pair_dot)
@@ -339,6 +357,7 @@ struct RankPolicy {
 // the diagonal tiles are visited): a gallery row that duplicates the positive then scores exactly
 // like it, as in the reference where both come out of one GEMM, and "strictly closer" stays strict.
 struct DiagPolicy {
+    static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     struct Params {
         float* out;   // s_k            (may be null)
@@ -415,8 +434,11 @@ struct HingeParams {
 #define PB2_HINGE_PIPES 0  // measurement builds: bit 0 column indicator on the ALU pipe, bits 1 / 2 row / rank indicator on the FMA pipe
 #endif
 constexpr float kBig = 1.329227995784916e36f;  // 2^120
-template <bool kRank>
+// kByteG: the gradient matrix leaves as ONE BYTE per entry (its values are exactly {0, 1, 2}) for the kind::i8
+// gradient GEMMs (gradgemm.cu): half the bytes written here and read there twice.
+template <bool kRank, bool kByteG_ = false>
 struct HingePolicyT {
+    static constexpr bool kByteG = kByteG_;
     static constexpr bool kStoresF32 = false;
     using Params = HingeParams;
     static constexpr int kColVecs = 2;  // rinv_y, -pred(thr_c) * 2^120 with thr_c = diag_col - margin
@@ -476,7 +498,7 @@ struct HingePolicyT {
         const int drel = dcol - cbase;                              // diagonal position inside this chunk
         const int nvalid = t.row_valid ? t.cols_valid - cbase : 0;  // valid columns of this row's chunk
         const int lane = threadIdx.x & 31;
-        uint32_t packed[16];
+        uint32_t packed[kByteG ? 8 : 16];
         uint32_t mine = 0;
         // independent accumulators: no serial dependency chain longer than 8 per chunk
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
@@ -546,9 +568,17 @@ struct HingePolicyT {
             if (q > 0) tot[q - 1] = __reduce_add_sync(0xffffffffu, pk_prev);
             pk_prev = pkq;
 #endif
-            const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
-            packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
-            packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            if constexpr (kByteG) {
+                // four entries in {0, 1, 2} -> four bytes: t = g0 + 256 g1 and u = g2 + 256 g3 are exact small integers;
+                // adding 2^23 parks them in the low mantissa bits, one PRMT joins the two 16-bit halves
+                const float2 tu = __fadd2_rn(make_float2(fmaf(g01.y, 256.f, g01.x), fmaf(g23.y, 256.f, g23.x)),
+                                             make_float2(8388608.f, 8388608.f));
+                packed[q] = __byte_perm(__float_as_uint(tu.x), __float_as_uint(tu.y), 0x5410);
+            } else {
+                const __half2 h01 = __float22half2_rn(g01), h23 = __float22half2_rn(g23);
+                packed[2 * q] = *reinterpret_cast<const uint32_t*>(&h01);
+                packed[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            }
             c4 = nc4;
             b4 = nb4;
         }
@@ -570,7 +600,8 @@ struct HingePolicyT {
         const int ccnt = (int)((mine >> ((lane & 3) * 6)) & 0x3fu);
         if (ccnt) atomicAdd(p.col_cnt + t.col0 + cbase + lane, ccnt);  // 0 for out-of-range columns
         if (p.has_gmat) {
-            os.stage(lane, ch, packed, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
+            if constexpr (kByteG) os.stage_u8(lane, ch, packed, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
+            else os.stage(lane, ch, packed, (int32_t)(t.col0 + cbase), (int32_t)(t.row0 + t.quad * 32));
         }
     }
     __device__ void chunk(const Params& p, const SimCommon&, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
@@ -601,6 +632,7 @@ struct HingePolicyT {
 };
 
 struct LseRowPolicy {
+    static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     struct Params {
         float* part_max;
@@ -698,6 +730,7 @@ struct LseRowPolicy {
 // Partials: row sums in the layout of pb2_sim_lse_parts (per 128 columns), column sums [4 * row blocks, cols];
 // both are merged by pb2_lse_merge_const.
 struct LseBothPolicy {
+    static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     static constexpr bool kStoresG = false;
     static constexpr bool kUsesStage = true;
@@ -806,6 +839,7 @@ struct LseBothPolicy {
 };
 
 struct LseGradPolicy {
+    static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     struct Params {
         const float* den_row;
@@ -1094,6 +1128,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         static_assert(BN % (32 * G) == 0, "column groups are whole 32-column chunks");
         constexpr int kChunks = BN / (32 * G);       // 32-column chunks per warp
         static_assert(!Policy::kStoresG || kChunks % 2 == 0, "gradient-matrix slabs are 64 columns wide");
+        static_assert(!Policy::kByteG || kChunks % 4 == 0, "one-byte gradient-matrix slabs are 128 columns wide");
         // with >= 3 warps per scheduler the TMEM load latency is hidden by the other warps; with 2 the
         // next chunk's load is kept in flight in a second register buffer
 #ifdef PB2_NO_PINGPONG  // measurement builds: one TMEM register buffer (32 fewer live registers)
@@ -1213,7 +1248,8 @@ static int launch_sim(const void* x, const void* y, int dtype, int64_t rows, int
     rc = make_tmap_2d(&ty, y, 2, (uint64_t)cols, (uint64_t)dim, (uint64_t)ldy * 2, BN / kCluster, BK);
     if (rc) return rc;
     if (Policy::kStoresG && om.ptr) {
-        rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
+        if (Policy::kByteG) rc = make_tmap_2d(&to, om.ptr, 1, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld, 32, 128);
+        else rc = make_tmap_2d(&to, om.ptr, 2, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 2, 32, 64);
         if (rc) return rc;
     } else if (Policy::kStoresF32 && om.ptr) {
         rc = make_tmap_2d(&to, om.ptr, 4, (uint64_t)rows, (uint64_t)cols, (uint64_t)om.ld * 4, 32, 32);
@@ -1271,7 +1307,7 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
     if (dim <= 0 || dim % BK != 0) return set_error(PB2_ERR_ARG, "%s: dim must be a positive multiple of 64", what);
     if (!x || !y) return set_error(PB2_ERR_ARG, "%s: null operand", what);
     if (dtype != PB2_BF16 && dtype != PB2_F16)
-        return set_error(PB2_ERR_ARG, "%s: tensor-core operands are bf16 or fp16 (fp32 rows go through pb2_split_bf16)", what);
+        return set_error(PB2_ERR_ARG, "%s: tensor-core operands are bf16 or fp16 (fp32 rows go through pb2_split_f16)", what);
     if (rows > 0x7fffffffll * BM / 2 || cols > 0x7fffffffll) return set_error(PB2_ERR_ARG, "%s: too large", what);
     cudaStream_t st = (cudaStream_t)stream;
     int bn = force_bn ? force_bn : pick_bn(rows, cols, Policy::kStoresG);
@@ -1283,6 +1319,8 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
     const bool mcast = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 2;
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
         return PB2_SIM(128, 2, 1);
+    } else if constexpr (Policy::kByteG) {
+        return PB2_SIM(256, 2, 1);  // a warp's 128 columns are one slab of bytes: 256-wide tiles only
     } else if constexpr (Policy::kStoresG) {
         if (bn == 192) return PB2_SIM(192, 3, 1);
         if (mcast) return PB2_SIM(256, 2, 3);
@@ -1350,9 +1388,9 @@ extern "C" int pb2_sim_rank(const void* q, const void* g, const float* rinv_q, c
                                     g_force_bn);
 }
 
-static int check_gmat(const void* gmat, int64_t ld_g, int64_t cols, const char* what) {
-    if (gmat && (ld_g % 8 != 0 || ld_g < cols || (reinterpret_cast<uintptr_t>(gmat) & 15)))
-        return set_error(PB2_ERR_ARG, "%s: gmat needs 16-byte alignment, ld_g %% 8 == 0 and ld_g >= cols", what);
+static int check_gmat(const void* gmat, int64_t ld_g, int64_t cols, const char* what, int elem_bytes = 2) {
+    if (gmat && ((ld_g * elem_bytes) % 16 != 0 || ld_g < cols || (reinterpret_cast<uintptr_t>(gmat) & 15)))
+        return set_error(PB2_ERR_ARG, "%s: gmat needs 16-byte alignment, a 16-byte multiple row pitch and ld_g >= cols", what);
     return PB2_OK;
 }
 
@@ -1360,14 +1398,17 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
                              const float* diag_row, const float* diag_col, int64_t rows, int64_t cols,
                              int64_t row_offset, int64_t col_offset, int dim, int dtype, int64_t ldx, int64_t ldy, float margin,
                              float* loss_partial, int n_partials, int32_t* row_cnt, int32_t* col_cnt, void* gmat,
-                             int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream) {
+                             int g_dtype, int64_t ld_g, const float* pos_thr, int32_t* rank, void* stream) {
     if (rows <= 0 || cols <= 0) return PB2_OK;
     if (!diag_row || !diag_col || !loss_partial || !row_cnt || !col_cnt)
         return set_error(PB2_ERR_ARG, "sim_hinge: null");
     const bool prezeroed = n_partials < 0;  // pb2_hinge_prep already cleared the partial buffer
     if (prezeroed) n_partials = -n_partials;
     if (n_partials < pb2_sim_grid()) return set_error(PB2_ERR_ARG, "sim_hinge: loss_partial too small");
-    int rc = check_gmat(gmat, ld_g, cols, "sim_hinge");
+    if (gmat && g_dtype != PB2_F16 && g_dtype != PB2_U8)
+        return set_error(PB2_ERR_ARG, "sim_hinge: the gradient matrix is PB2_F16 or PB2_U8");
+    const bool byte_g = gmat && g_dtype == PB2_U8;
+    int rc = check_gmat(gmat, ld_g, cols, "sim_hinge", byte_g ? 1 : 2);
     if (rc) return rc;
     if ((pos_thr == nullptr) != (rank == nullptr))
         return set_error(PB2_ERR_ARG, "sim_hinge: pos_thr and rank go together");
@@ -1381,6 +1422,13 @@ extern "C" int pb2_sim_hinge(const void* x, const void* y, const float* rinv_x, 
     OutMatrix om;
     om.ptr = gmat;
     om.ld = ld_g;
+    if (byte_g) {
+        if (rank)
+            return dispatch_sim<HingePolicyT<true, true>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp,
+                                                          stream, "sim_hinge+rank (u8 G)", 256, om);
+        return dispatch_sim<HingePolicyT<false, true>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
+                                                       "sim_hinge (u8 G)", 256, om);
+    }
     if (rank)
         return dispatch_sim<HingePolicyT<true>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, 1.0f, pp, stream,
                                                 "sim_hinge+rank", g_force_bn, om);

@@ -13,7 +13,7 @@ namespace {
 constexpr int64_t kAlign = 256;
 int64_t up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct Layout {
-    int64_t rinv_v, rinv_a, diag, part, row_cnt, col_cnt, vh, ah, g, pv, pa, vx, ax, total, ld_g;
+    int64_t rinv_v, rinv_a, diag, part, row_cnt, col_cnt, vh, ah, g, pv, pa, vx, ax, sv, sa, total, ld_g;
     int n_part;
 };
 Layout layout(int64_t n, int dim, int in_dtype) {
@@ -37,9 +37,11 @@ Layout layout(int64_t n, int dim, int in_dtype) {
     L.g = take(n * L.ld_g * 2);
     L.pv = take(n * dim * 4);
     L.pa = take(n * dim * 4);
-    // fp32 inputs: split-bf16 tensor-core operands [n, 3 dim] (pb2_split_bf16)
+    // fp32 inputs: split-fp16 tensor-core operands [n, 3 dim] and their per-row power-of-two scales (pb2_split_f16)
     L.vx = in_dtype == PB2_F32 ? take(n * 3 * dim * 2) : -1;
     L.ax = in_dtype == PB2_F32 ? take(n * 3 * dim * 2) : -1;
+    L.sv = in_dtype == PB2_F32 ? take(n * 4) : -1;
+    L.sa = in_dtype == PB2_F32 ? take(n * 4) : -1;
     L.total = o;
     return L;
 }
@@ -77,16 +79,20 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
     // programmatic dependent launch between the four kernels: each one's prologue (barrier init, TMEM
     // allocation, descriptor prefetch) overlaps its predecessor's tail
     pb2::PdlScope pdl;
-    // tensor-core operands: bf16 / fp16 rows as they are, fp32 rows as their split-bf16 pair (contraction length 3 dim)
+    // tensor-core operands: bf16 / fp16 rows as they are; fp32 rows as the split-fp16 pair of their normalised,
+    // power-of-two-scaled values (contraction length 3 dim), with the scales in place of 1/||row|| in the epilogue
     const bool split = in_dtype == PB2_F32;
     void* vx = split ? w + L.vx : nullptr;
     void* ax = split ? w + L.ax : nullptr;
+    float* sv = split ? reinterpret_cast<float*>(w + L.sv) : nullptr;
+    float* sa = split ? reinterpret_cast<float*>(w + L.sa) : nullptr;
     int rc = pb2_hinge_prep(v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part,
-                            vx, ax, stream);
+                            vx, ax, sv, sa, stream);
     if (rc) return rc;
-    rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, rinv_v, rinv_a, diag, diag, n, n, 0, 0, split ? 3 * dim : dim,
-                       split ? PB2_BF16 : in_dtype, split ? 3 * (int64_t)dim : ldv, split ? 3 * (int64_t)dim : lda, margin, part,
-                       -L.n_part, row_cnt, col_cnt, g, L.ld_g, nullptr, nullptr, stream);
+    rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, split ? sv : rinv_v, split ? sa : rinv_a, diag, diag, n, n, 0, 0,
+                       split ? 3 * dim : dim, split ? PB2_F16 : in_dtype, split ? 3 * (int64_t)dim : ldv,
+                       split ? 3 * (int64_t)dim : lda, margin, part,
+                       -L.n_part, row_cnt, col_cnt, g, PB2_F16, L.ld_g, nullptr, nullptr, stream);
     if (rc) return rc;
     // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
     rc = pb2_grad_gemm_dual(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, pv, pa, dim, dim, stream);

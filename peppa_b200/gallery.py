@@ -44,7 +44,7 @@ class GalleryStep:
 
     def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
                  group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None,
-                 loss: str = "hinge", temperature: float = 1.0, logit_bound=None):
+                 loss: str = "hinge", temperature: float = 1.0, logit_bound=None, byte_gmat=None):
         if loss not in ("hinge", "milnce"):
             raise ValueError("loss must be 'hinge' or 'milnce'")
         self.loss, self.inv_tau = loss, 1.0 / float(temperature)
@@ -74,7 +74,16 @@ class GalleryStep:
             self.p_v = torch.empty(n, dim, dtype=f32, device=dev)
             self.p_v_loc = torch.empty(nl, dim, dtype=f32, device=dev) if world > 1 else None
             br, bc = min(block, nl), min(block, n)
-            self.gmat, self.ld_g = self.ops.gmat_alloc(br, bc, dev)
+            # hinge: the gradient matrix is exactly {0, 1, 2} -> one byte per entry and kind::i8 gradient GEMMs
+            # (byte_gmat=False keeps the fp16 matrix; MIL-NCE's entries are softmax weights and stay fp16)
+            self.byte_gmat = (loss == "hinge" and dim % 256 == 0 and block <= 32768) if byte_gmat is None else bool(byte_gmat)
+            if self.byte_gmat and (loss != "hinge" or dim % 256 != 0 or block > 32768):
+                raise ValueError("byte_gmat needs the hinge loss, dim % 256 == 0 and block <= 32768")
+            if self.byte_gmat and backend is None:
+                self.gmat, self.ld_g = self.ops.gmat_alloc(br, bc, dev, torch.uint8)
+            else:
+                self.byte_gmat = False
+                self.gmat, self.ld_g = self.ops.gmat_alloc(br, bc, dev)
 
     # -- collectives (no-ops for world == 1) ------------------------------------------------------
     def _all_gather(self, out, loc):
@@ -128,8 +137,12 @@ class GalleryStep:
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
         if self.with_grad:
-            ah = ops.rows_scale_f16(a_loc, ra)
-            vh = ops.rows_scale_f16(v_full, rv_full)
+            if self.byte_gmat:      # two 8-bit planes per row: the operand of the kind::i8 gradient GEMMs
+                ah = ops.rows_quant_i8(a_loc, ra)
+                vh = ops.rows_quant_i8(v_full, rv_full)
+            else:
+                ah = ops.rows_scale_f16(a_loc, ra)
+                vh = ops.rows_scale_f16(v_full, rv_full)
             acc_a, acc_v = len(cblocks) > 1, len(rblocks) > 1
             if acc_a:
                 self.p_a.zero_()

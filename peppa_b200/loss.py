@@ -47,21 +47,23 @@ class _HingeFn(torch.autograd.Function):
         rv, nv = ops.row_norms(vb)
         ra, na = ops.row_norms(ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
-        vx, ax = ops.mma_pair(vb, ab)                           # tensor-core operands (split-bf16 for fp32 rows)
+        vx, ax, fv, fa = ops.mma_pair(vb, ab, rv, ra)           # tensor-core operands + epilogue factors (split-fp16 for fp32 rows)
         row_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
         col_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
         inv_n2 = 1.0 / float(n) ** 2
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         pv = pa = None
-        if need_grad:       # fp16 copies of the normalised embeddings: operands of the gradient GEMMs
-            vh, ah = ops.rows_scale_f16(vb, rv), ops.rows_scale_f16(ab, ra)
+        byte_g = need_grad and ops.byte_gmat_ok(vb.shape[1])       # entries are exactly {0, 1, 2}: one byte each
+        if need_grad:       # normalised embeddings as operands of the gradient GEMMs: two 8-bit planes, or fp16 copies
+            quant = ops.rows_quant_i8 if byte_g else ops.rows_scale_f16
+            vh, ah = quant(vb, rv), quant(ab, ra)
         blocks = _blocks(n, _MAX_BLOCK)
         for (r0, r1) in blocks:
             for (c0, c1) in blocks:
                 g = ld = None
                 if need_grad:
-                    g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                part = ops.sim_hinge(vx[r0:r1], ax[c0:c1], rv[r0:r1], ra[c0:c1], diag[r0:r1], diag[c0:c1], margin,
+                    g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev, torch.uint8 if byte_g else torch.float16)
+                part = ops.sim_hinge(vx[r0:r1], ax[c0:c1], fv[r0:r1], fa[c0:c1], diag[r0:r1], diag[c0:c1], margin,
                                      row_cnt[r0:r1], col_cnt[c0:c1], g, ld or 0, row_offset=r0, col_offset=c0)
                 ops.hinge_loss_terms(loss, partials=part, alpha=inv_n2)
                 if need_grad:
@@ -124,7 +126,8 @@ class _MilNceFn(torch.autograd.Function):
             raise RuntimeError(f"shape '[{n}, {n}, -1]' is invalid for input of size {n * A.shape[0]}")
         k = A.shape[0] // n
         vb, ab = ops.as_row_pair(V, A)
-        vx, ax = ops.mma_pair(vb, ab)         # tensor-core operands (split-bf16 for fp32 rows)
+        vx, ax, fv, fa = ops.mma_pair(vb, ab)      # tensor-core operands (+ power-of-two row scales of the split-fp16 pair for fp32 rows)
+        sl = (lambda t, a0, a1: None if t is None else t[a0:a1])
         dev = vb.device
         nk = n * k
         need_grad = any(ctx.needs_input_grad)
@@ -138,12 +141,13 @@ class _MilNceFn(torch.autograd.Function):
             lse_col = torch.full((nk,), float("-inf"), dtype=torch.float32, device=dev)
             for (r0, r1) in vblocks:
                 for (c0, c1) in ablocks:
-                    ops.sim_lse_both(vx[r0:r1], ax[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1], lse_col=lse_col[c0:c1])
+                    ops.sim_lse_both(vx[r0:r1], ax[c0:c1], bound, rinv_x=sl(fv, r0, r1), rinv_y=sl(fa, c0, c1), scale=inv_tau,
+                                     lse_row=lse_row[r0:r1], lse_col=lse_col[c0:c1])
         else:
             for (c0, c1) in ablocks:   # rows = videos, columns = audio candidates
-                lse_row = ops.sim_lse_rows(vx, ax[c0:c1], scale=inv_tau, lse=lse_row)
+                lse_row = ops.sim_lse_rows(vx, ax[c0:c1], rinv_x=fv, rinv_y=sl(fa, c0, c1), scale=inv_tau, lse=lse_row)
             for (c0, c1) in vblocks:   # LSE over videos for every audio candidate = row LSE of A V^T
-                lse_col = ops.sim_lse_rows(ax, vx[c0:c1], scale=inv_tau, lse=lse_col)
+                lse_col = ops.sim_lse_rows(ax, vx[c0:c1], rinv_x=fa, rinv_y=sl(fv, c0, c1), scale=inv_tau, lse=lse_col)
         if k == 1:
             diag = ops.pair_dot(vb, ab)
             if inv_tau != 1.0:
@@ -167,7 +171,8 @@ class _MilNceFn(torch.autograd.Function):
             for (r0, r1) in vblocks:
                 for (c0, c1) in ablocks:
                     g, ld = ops.gmat_alloc(r1 - r0, c1 - c0, dev)
-                    ops.sim_lse_grad(vx[r0:r1], ax[c0:c1], den[r0:r1], den_a[c0:c1], g, ld, scale=inv_tau)
+                    ops.sim_lse_grad(vx[r0:r1], ax[c0:c1], den[r0:r1], den_a[c0:c1], g, ld, rinv_x=sl(fv, r0, r1),
+                                     rinv_y=sl(fa, c0, c1), scale=inv_tau)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, ah[c0:c1], transpose=False, out=pv[r0:r1], accumulate=acc_v)
                     ops.grad_gemm(g, r1 - r0, c1 - c0, ld, vh[r0:r1], transpose=True, out=pa[c0:c1], accumulate=acc_a)
             if k == 1:

@@ -48,7 +48,7 @@ def _pair_ranks(candidates, references, correct):
     dev = qb.device
     rq, _ = ops.row_norms(qb)
     rg, _ = ops.row_norms(gb)
-    qb, gb = ops.mma_pair(qb, gb)                         # tensor-core operands (split-bf16 for fp32 rows)
+    qb, gb, rq, rg = ops.mma_pair(qb, gb, rq, rg)         # tensor-core operands + epilogue factors (split-fp16 for fp32 rows)
     rows, cols, counts = _targets(correct, qb.shape[0], gb.shape[0], dev)
     if counts is None:
         q, rq_p = qb, rq
@@ -126,7 +126,7 @@ def _resampled_ranks(candidates, references, size, n_samples):
         qb, gb = ops.as_row_pair(references, candidates)
         rq, _ = ops.row_norms(qb)
         rg, _ = ops.row_norms(gb)
-        scores = ops.sim_matrix(*ops.mma_pair(qb, gb), rq, rg)          # rows = references, as in pig/metrics.py:8
+        scores = ops.sim_matrix(*ops.mma_pair(qb, gb, rq, rg))          # rows = references, as in pig/metrics.py:8
         return ops.subset_rank(scores, ix.to(qb.device))
     ranks = [_pair_ranks(candidates[i], references[i], None)[0] for i in ix]      # huge galleries: per subset
     return torch.stack(ranks) if ranks else torch.empty(0, size, dtype=torch.int32)

@@ -11,9 +11,9 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from ._cabi import PB2_BF16, PB2_F16, PB2_F32, check
+from ._cabi import PB2_BF16, PB2_F16, PB2_F32, PB2_I8_PLANES, PB2_U8, check
 
-_DTYPE_CODE = {torch.bfloat16: PB2_BF16, torch.float16: PB2_F16, torch.float32: PB2_F32}
+_DTYPE_CODE = {torch.bfloat16: PB2_BF16, torch.float16: PB2_F16, torch.float32: PB2_F32, torch.uint8: PB2_U8}
 
 
 # bench.py sets this to a list to time individual kernels with CUDA events on the launching stream:
@@ -91,22 +91,29 @@ def as_row_pair(x: torch.Tensor, y: torch.Tensor):
     return xr, as_rows(y, device=xr.device, dtype=dt)
 
 
-def split_bf16(x_f32: torch.Tensor, side: int) -> torch.Tensor:
-    """[n, 3 d] bf16 split operand of an fp32 matrix: [hi | lo | hi] (side 0) or [hi | hi | lo] (side 1)."""
+def split_f16(x_f32: torch.Tensor, rinv, side: int):
+    """([n, 3 d] fp16 split operand, [n] fp32 power-of-two scales) of an fp32 matrix: the rows are multiplied by
+    ``rinv`` (None = 1) and by 2^e, split into fp16 hi + lo, and laid out [hi | lo | hi] (side 0) or [hi | hi | lo]
+    (side 1); the scales 2^-e take the place of ``rinv`` in the similarity kernels' epilogue."""
     n, d = x_f32.shape
-    out = torch.empty(n, 3 * d, dtype=torch.bfloat16, device=x_f32.device)
+    out = torch.empty(n, 3 * d, dtype=torch.float16, device=x_f32.device)
+    scale = torch.empty(n, dtype=torch.float32, device=x_f32.device)
     with torch.cuda.device(x_f32.device):
-        check(_cabi.lib().pb2_split_bf16(_ptr(x_f32), n, d, x_f32.stride(0), int(side), _ptr(out), 3 * d,
-                                         _stream(x_f32.device)), "split_bf16")
-    return out
+        check(_cabi.lib().pb2_split_f16(_ptr(x_f32), _ptr(rinv), n, d, x_f32.stride(0), int(side), _ptr(out), 3 * d,
+                                        _ptr(scale), _stream(x_f32.device)), "split_f16")
+    return out, scale
 
 
-def mma_pair(x: torch.Tensor, y: torch.Tensor):
-    """Tensor-core operands of S = X Y^T for rows from as_row_pair: bf16 / fp16 rows are used as they are
-    (tcgen05 kind::f16 takes both natively), fp32 rows become their split-bf16 pair (contraction length 3 d)."""
+def mma_pair(x: torch.Tensor, y: torch.Tensor, rinv_x=None, rinv_y=None):
+    """Tensor-core operands of S = X Y^T for rows from as_row_pair, with the per-row factors the similarity kernels'
+    epilogue applies: (x_op, y_op, fx, fy).  bf16 / fp16 rows are used as they are (tcgen05 kind::f16 takes both
+    natively) with fx = rinv_x, fy = rinv_y; fp32 rows become the split-fp16 pair of their rinv-scaled values
+    (contraction length 3 d) and fx / fy are the exact power-of-two scales of the split."""
     if x.dtype == torch.float32:
-        return split_bf16(x, 0), split_bf16(y, 1)
-    return x, y
+        xo, fx = split_f16(x, rinv_x, 0)
+        yo, fy = split_f16(y, rinv_y, 1)
+        return xo, yo, fx, fy
+    return x, y, rinv_x, rinv_y
 
 
 def row_norms(x: torch.Tensor):
@@ -190,10 +197,17 @@ def sim_grid(device) -> int:
         return int(_cabi.lib().pb2_sim_grid())
 
 
-def gmat_alloc(rows, cols, device):
-    """fp16 gradient-matrix buffer with a leading dimension padded for 16-byte vector stores."""
-    ld = ((cols + 63) // 64) * 64
-    return torch.empty(rows, ld, dtype=torch.float16, device=device), ld
+def gmat_alloc(rows, cols, device, dtype=torch.float16):
+    """Gradient-matrix buffer with a leading dimension padded to whole TMA boxes: fp16 (any loss), or uint8 -- one
+    byte per entry -- for the hinge loss, whose entries are exactly {0, 1, 2} (the kind::i8 gradient GEMMs)."""
+    pad = 128 if dtype == torch.uint8 else 64
+    ld = ((cols + pad - 1) // pad) * pad
+    return torch.empty(rows, ld, dtype=dtype, device=device), ld
+
+
+def byte_gmat_ok(dim):
+    """The one-byte gradient matrix needs whole 256-column output tiles in the kind::i8 gradient GEMMs."""
+    return dim % 256 == 0
 
 
 def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0,
@@ -206,7 +220,8 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
                                         int(row_offset), int(col_offset), x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                         float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
-                                        int(ld_g), _ptr(pos_thr), _ptr(rank), _stream(x.device)), "sim_hinge")
+                                        _DTYPE_CODE[gmat.dtype] if gmat is not None else PB2_F16, int(ld_g), _ptr(pos_thr),
+                                        _ptr(rank), _stream(x.device)), "sim_hinge")
     return part
 
 
@@ -298,7 +313,10 @@ def grad_gemm_workspace(device):
 
 def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, accumulate=False, stream_k=True):
     m = g_cols if transpose else g_rows
-    d = z.shape[1]
+    planes = gmat.dtype == torch.uint8        # one-byte G: z is the two-plane operand of rows_quant_i8, [K, 2 d] bytes
+    if planes and z.dtype != torch.uint8:
+        raise ValueError("a uint8 gradient matrix goes with the two-plane operand of ops.rows_quant_i8")
+    d = z.shape[1] // 2 if planes else z.shape[1]
     if out is None:
         out = torch.empty(m, d, dtype=torch.float32, device=z.device)
         accumulate = False
@@ -306,7 +324,7 @@ def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, acc
     ws = grad_gemm_workspace(z.device) if stream_k and m * d > 148 * 128 * 256 else None
     with torch.cuda.device(z.device), _timed("grad_gemm", 2.0 * g_rows * g_cols * d, z.device):
         check(_cabi.lib().pb2_grad_gemm_ws(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g),
-                                           int(bool(transpose)), _ptr(z), _DTYPE_CODE[z.dtype], d, z.stride(0),
+                                           int(bool(transpose)), _ptr(z), PB2_I8_PLANES if planes else _DTYPE_CODE[z.dtype], d, z.stride(0),
                                            float(alpha), int(bool(accumulate)), _ptr(out), out.stride(0), _ptr(ws),
                                            ws.numel() if ws is not None else 0, _stream(z.device)), "grad_gemm")
     return out
@@ -320,6 +338,18 @@ def rows_scale_f16(x, rinv=None, out=None):
     with torch.cuda.device(x.device):
         check(_cabi.lib().pb2_rows_scale_f16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(rinv), n, d, x.stride(0), _ptr(out),
                                              out.stride(0) if n else d, _stream(x.device)), "rows_scale_f16")
+    return out
+
+
+def rows_quant_i8(x, rinv=None, out=None):
+    """Two-plane 8-bit operand [n, 2 d] uint8 = [hi (s8) | lo (u8)] of round(x * rinv * 32512): the embedding
+    operand of the kind::i8 gradient GEMMs (x bf16 / fp16 / fp32 rows)."""
+    n, d = x.shape
+    if out is None:
+        out = torch.empty(n, 2 * d, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().pb2_rows_quant_i8(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(rinv), n, d, x.stride(0), _ptr(out),
+                                            out.stride(0) if n else 2 * d, _stream(x.device)), "rows_quant_i8")
     return out
 
 

@@ -14,7 +14,7 @@ def _cosine_forward(U, V):
     ub, vb = ops.as_row_pair(U, V)          # own dtype (fp32 / fp16 / bf16), sizes checked like the reference's matmul
     ru, nu = ops.row_norms(ub)
     rv, nv = ops.row_norms(vb)
-    return ops.sim_matrix(*ops.mma_pair(ub, vb), ru, rv), (ub, vb, ru, nu, rv, nv)
+    return ops.sim_matrix(*ops.mma_pair(ub, vb, ru, rv)), (ub, vb, ru, nu, rv, nv)
 
 
 class _CosineMatrix(torch.autograd.Function):

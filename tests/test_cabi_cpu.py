@@ -117,14 +117,19 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 100.0, one, one, null) == 1
     assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, -1.0, one, one, null) == 1
     assert lib.pb2_sim_lse_both(one, one, null, null, 0, 8, 512, 0, 512, 512, 1.0, 1.0, null, null, null) == 0
-    # operand dtypes: the tensor-core kernels take bf16 / fp16 (fp32 rows go through pb2_split_bf16), the row-wise
+    # operand dtypes: the tensor-core kernels take bf16 / fp16 (fp32 rows go through pb2_split_f16), the row-wise
     # kernels bf16 / fp16 / fp32; anything else is refused before a launch
     assert lib.pb2_sim_rank(one, one, null, null, one, one, 8, 8, 0, 512, 2, 512, 512, one, null) == 1
-    assert b"split_bf16" in lib.pb2_last_error()
+    assert b"split_f16" in lib.pb2_last_error()
     assert lib.pb2_row_norms(one, 7, 8, 512, 512, one, one, null) == 1
-    assert lib.pb2_split_bf16(one, 8, 512, 512, 2, one, 1536, null) == 1        # side is 0 or 1
-    assert lib.pb2_split_bf16(one, 8, 512, 512, 0, one, 512, null) == 1         # ld_out < 3 dim
-    assert lib.pb2_split_bf16(null, 0, 512, 512, 0, null, 1536, null) == 0
+    assert lib.pb2_split_f16(one, null, 8, 512, 512, 2, one, 1536, one, null) == 1        # side is 0 or 1
+    assert lib.pb2_split_f16(one, null, 8, 512, 512, 0, one, 512, one, null) == 1         # ld_out < 3 dim
+    assert lib.pb2_split_f16(null, null, 0, 512, 512, 0, null, 1536, null, null) == 0
+    # the one-byte gradient matrix pairs with the two-plane operand, and only with it
+    assert lib.pb2_grad_gemm(one, 3, 8, 8, 128, 0, one, 1, 512, 1024, 1.0, 0, one, 512, null) == 1
+    assert b"PB2_I8_PLANES" in lib.pb2_last_error()
+    assert lib.pb2_grad_gemm(one, 3, 8, 8, 128, 0, one, 4, 320, 1024, 1.0, 0, one, 512, null) == 1      # dim % 256
+    assert lib.pb2_rows_quant_i8(one, 0, null, 8, 512, 512, one, 512, null) == 1                        # ld_out < 2 dim
     assert lib.pb2_hinge_step_workspace(1024, 512, 2) > lib.pb2_hinge_step_workspace(1024, 512, 0) > 0
     assert lib.pb2_sim_lse_col_parts(1000) == 32 and lib.pb2_sim_lse_col_parts(128) == 4
     assert lib.pb2_lse_merge_const(null, 4, 8, 1.0, null, 0, null) == 1 and lib.pb2_lse_merge_const(null, 4, 0, 1.0, null, 0, null) == 0

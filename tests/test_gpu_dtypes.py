@@ -68,7 +68,9 @@ def test_losses_on_unrounded_inputs(pb, dtype, n):
         # an fp16 gradient tensor carries its own 2^-11 rounding per element; fp32 results meet the bar row by row
         tol = TOL if dtype == torch.float32 else 2e-3
         assert rel_err(v.grad.float().cpu(), dv0) < tol and rel_err(a.grad.float().cpu(), da0) < tol
-        assert row_rel_err(v.grad.float().cpu(), dv0) < 2 * tol and row_rel_err(a.grad.float().cpu(), da0) < 2 * tol
+        if dtype == torch.float32:      # fp16 gradients of ~1e-5 are fp16 SUBNORMALS (absolute step 6e-8): the row-wise
+            # bar is checked on fp32 results here and on loss-scaled fp16 ones in test_fp16_gradients_survive_a_gradscaler
+            assert row_rel_err(v.grad.cpu(), dv0) < tol and row_rel_err(a.grad.cpu(), da0) < tol
         assert v.grad.dtype == dtype
 
 

@@ -39,8 +39,8 @@ def sampled_ranks(candidates, references, rows, tol=1e-6, block=256):
 def sampled_rank_bounds(candidates, references, rows, tol=1e-6, block=256):
     """For galleries of ~10^6 candidates the 1e-6 tie window around the positive is no longer empty for a sizeable
     share of the rows (fp32 scores are ~1e-7 apart there), so beside (ranks, near) this returns the interval every
-    admissible ordering of the near-ties must respect: lo = #{c : dist[c] < dist[pos] - tol},
-    hi = #{c != pos : dist[c] <= dist[pos] + tol}.  Rows that are not near-ties have lo == hi == rank."""
+    admissible ordering of the near-ties must respect: lo = #{c closer and outside the tie window},
+    hi = #{c != pos closer or inside the window}.  Rows that are not near-ties have lo == hi == rank."""
     rows = torch.as_tensor(rows, device=references.device, dtype=torch.int64)
     C = _unit(candidates, torch.float32)
     out = [[], [], [], []]
@@ -48,10 +48,11 @@ def sampled_rank_bounds(candidates, references, rows, tol=1e-6, block=256):
         r = rows[s:s + block]
         d = 1 - _unit(references[r], torch.float32) @ C.T
         pos = d[torch.arange(r.numel(), device=d.device), r].unsqueeze(1)
-        out[0].append((d < pos).sum(1))
-        out[1].append(((d - pos).abs() <= tol).sum(1) > 1)
-        out[2].append((d < pos - tol).sum(1))
-        out[3].append((d <= pos + tol).sum(1) - 1)
+        closer, tie = d < pos, (d - pos).abs() <= tol               # one tie predicate for near, lo and hi
+        out[0].append(closer.sum(1))
+        out[1].append(tie.sum(1) > 1)
+        out[2].append((closer & ~tie).sum(1))
+        out[3].append((closer | tie).sum(1) - 1)
     return tuple(torch.cat(o) for o in out)
 
 
@@ -100,3 +101,38 @@ def hinge_grad_rows(X, Y, rows, margin):
     xr = Xh[rows]
     norm = torch.linalg.vector_norm(X[rows].double(), ord=2, dim=1, keepdim=True)
     return (g - xr * (g * xr).sum(1, keepdim=True)) / norm / float(n) ** 2
+
+
+def hinge_kink_counts(X, Y, margin, tol=1e-6, block=2048):
+    """The gradient of pig/loss.py:41-48 is DISCONTINUOUS where a hinge argument crosses zero: an entry with
+    |m + M_ij - M_jj| or |m + M_ij - M_ii| below the arithmetic's resolution may legitimately fall on either side
+    (fp32 against fp64, one summation order against another -- the reference against itself on another BLAS), and
+    each such entry moves row i of dX and row j of dY by one unit vector (+ one unit of the diagonal count) / N^2.
+    Returns k [N]: per clip, the number of entries of ITS row and ITS column within ``tol`` of a kink -- the
+    gradient-side twin of the 1e-6 near-tie exemption of the ranks."""
+    n = X.shape[0]
+    Xn, Yn = _unit(X, torch.float64), _unit(Y, torch.float64)
+    diag = (Xn * Yn).sum(1)
+    k = torch.zeros(n, dtype=torch.int64, device=X.device)
+    for s in range(0, n, block):
+        M = Xn[s:s + block] @ Yn.T
+        b = M.shape[0]
+        idx = torch.arange(b, device=X.device)
+        near = ((margin + M - diag.unsqueeze(0)).abs() <= tol).to(torch.int64) + \
+               ((margin + M - diag[s:s + b].unsqueeze(1)).abs() <= tol).to(torch.int64)
+        near[idx, s + idx] = 0
+        k[s:s + b] += near.sum(1)
+        k += near.sum(0)
+    return k
+
+
+def hinge_rows_within(got, ref, x, k, tol_rel=1e-3):
+    """Row-wise gradient check with the kink allowance: ||got_i - ref_i|| <= tol_rel * max(||ref_i||, 1% of the median
+    row norm) + 2 k_i / (||x_i|| N^2).  Returns (ok, worst ratio of error to allowance)."""
+    got, ref = got.double(), ref.double().to(got.device)
+    n = ref.shape[0]
+    rn = ref.norm(dim=1)
+    floor = (0.01 * rn.median()).clamp_min(1e-300)
+    allow = tol_rel * torch.maximum(rn, floor) + 2.0 * k.to(got.device).double() / (x.double().to(got.device).norm(dim=1) * float(n) ** 2)
+    ratio = ((got - ref).norm(dim=1) / allow).max().item()
+    return ratio <= 1.0, ratio

@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from conftest import rel_err, row_rel_err
+from oracle import blockwise as B
 from oracle import pig_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -70,7 +71,11 @@ def test_losses_on_unrounded_inputs(pb, dtype, n):
         assert rel_err(v.grad.float().cpu(), dv0) < tol and rel_err(a.grad.float().cpu(), da0) < tol
         if dtype == torch.float32:      # fp16 gradients of ~1e-5 are fp16 SUBNORMALS (absolute step 6e-8): the row-wise
             # bar is checked on fp32 results here and on loss-scaled fp16 ones in test_fp16_gradients_survive_a_gradscaler
-            assert row_rel_err(v.grad.cpu(), dv0) < tol and row_rel_err(a.grad.cpu(), da0) < tol
+            if isinstance(mod, pb.loss.TripletLoss):     # hinge: entries within 1e-6 of a kink may fall on either side
+                k = B.hinge_kink_counts(V, A, 0.2)
+                assert B.hinge_rows_within(v.grad.cpu(), dv0, V, k, tol)[0] and B.hinge_rows_within(a.grad.cpu(), da0, A, k, tol)[0]
+            else:
+                assert row_rel_err(v.grad.cpu(), dv0) < tol and row_rel_err(a.grad.cpu(), da0) < tol
         assert v.grad.dtype == dtype
 
 
@@ -86,7 +91,11 @@ def test_blocked_loss_on_fp32_inputs(pb):
             out = mod(v, a)
             out.backward()
             assert rel_err(out.cpu(), ref[0]) < TOL
-            assert row_rel_err(v.grad.cpu(), ref[1]) < TOL and row_rel_err(a.grad.cpu(), ref[2]) < TOL
+            if isinstance(mod, pb.loss.TripletLoss):
+                k = B.hinge_kink_counts(V, A, 0.2)
+                assert B.hinge_rows_within(v.grad.cpu(), ref[1], V, k, TOL)[0] and B.hinge_rows_within(a.grad.cpu(), ref[2], A, k, TOL)[0]
+            else:
+                assert row_rel_err(v.grad.cpu(), ref[1]) < TOL and row_rel_err(a.grad.cpu(), ref[2]) < TOL
     finally:
         pb.loss._MAX_BLOCK, pb.loss._LSE_BOTH_MIN_PAIRS = old
 

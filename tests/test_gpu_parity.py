@@ -49,6 +49,14 @@ def near_rows_gpu(candidates, references, tol=1e-6, block=4096):
     return B.all_ranks(candidates.cuda(), references.cuda(), tol=tol, block=block)[1].cpu()
 
 
+def hinge_rows_ok(got, ref, x, k):
+    """Row-wise 1e-3 bar for hinge gradients with the kink allowance of oracle/blockwise.py: an entry within 1e-6 of
+    a hinge kink may fall on either side (the gradient is discontinuous there) and moves its row by ~2 / N^2."""
+    from oracle import blockwise as B
+    ok, ratio = B.hinge_rows_within(got.cpu(), ref, x, k, TOL)
+    assert ok, ratio
+
+
 def _grads(mod, V, A):
     v = V.cuda().requires_grad_(True)
     a = A.cuda().requires_grad_(True)
@@ -177,7 +185,13 @@ def test_losses_against_oracle(pb, n, alpha):
         rl, rdv, rda = ref()
         assert rel_err(loss, rl) < TOL, kind
         assert rel_err(dV, rdv) < TOL and rel_err(dA, rda) < TOL, kind
-        assert row_rel_err(dV, rdv) < TOL and row_rel_err(dA, rda) < TOL, kind     # no wrong row hides under a large max
+        if kind == "hinge":           # row by row: no wrong row hides under a large max (kinks: see hinge_rows_ok)
+            from oracle import blockwise as B
+            k = B.hinge_kink_counts(V, A, 0.2)
+            hinge_rows_ok(dV, rdv, V, k)
+            hinge_rows_ok(dA, rda, A, k)
+        else:
+            assert row_rel_err(dV, rdv) < TOL and row_rel_err(dA, rda) < TOL, kind
 
 
 def test_non_unit_norm_inputs(pb):
@@ -266,7 +280,10 @@ def test_gallery_step_single_gpu(pb, n, block):
     loss, dA, dV = O.hinge_loss_and_grads(A, V, 0.2)
     assert rel_err(out["loss"].cpu(), loss) < TOL
     assert rel_err(out["dA"].cpu(), dA) < TOL and rel_err(out["dV"].cpu(), dV) < TOL
-    assert row_rel_err(out["dA"].cpu(), dA) < TOL and row_rel_err(out["dV"].cpu(), dV) < TOL
+    from oracle import blockwise as B
+    k = B.hinge_kink_counts(A, V, 0.2)
+    hinge_rows_ok(out["dA"], dA, A, k)
+    hinge_rows_ok(out["dV"], dV, V, k)
     assert rel_err(out["loss"].cpu(), O.triplet_loss(V, A, 0.2)) < TOL        # symmetric in (V, A)
     ranks, near = O.ranks_identity(V, A)
     assert bool(((out["ranks"].cpu().long() == ranks) | near).all())
@@ -665,7 +682,10 @@ def test_byte_gradient_matrix_equals_fp16_path(pb):
     assert rel_err(o8["dA"], o16["dA"]) < 3e-4 and rel_err(o8["dV"], o16["dV"]) < 3e-4
     loss, dA, dV = O.hinge_loss_and_grads(A, V, 0.2)
     assert rel_err(o8["dA"].cpu(), dA) < TOL and rel_err(o8["dV"].cpu(), dV) < TOL
-    assert row_rel_err(o8["dA"].cpu(), dA) < TOL and row_rel_err(o8["dV"].cpu(), dV) < TOL
+    from oracle import blockwise as B
+    k = B.hinge_kink_counts(A, V, 0.2)
+    hinge_rows_ok(o8["dA"], dA, A, k)
+    hinge_rows_ok(o8["dV"], dV, V, k)
     # the matrices themselves
     ra, _ = ops.row_norms(a)
     rv, _ = ops.row_norms(v)

@@ -231,7 +231,7 @@ int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, const void* y,
 int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float* rinv_v,
                    float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt, int32_t* col_cnt,
                    float* loss_partial, int n_partials, void* v_split, void* a_split, float* scale_v, float* scale_a,
-                   void* stream);
+                   const float* rinv_v_in, const float* rinv_a_in, void* stream);
 int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv,
                       int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag, const int32_t* row_cnt,
                       const int32_t* col_cnt, const float* loss_partial, int n_partials, float margin, float coef,
@@ -239,11 +239,13 @@ int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const v
 
 /* The five launches above behind one call (one FFI crossing per training step): workspace is a 256-byte
  * aligned device buffer of pb2_hinge_step_workspace(n, dim, in_dtype) bytes; n <= 32768 (one gradient-matrix
- * block); v / a are bf16 / fp16 / fp32 rows (in_dtype). */
+ * block); v / a are bf16 / fp16 / fp32 rows (in_dtype).  rinv_v_in / rinv_a_in (optional, NULL = compute): the
+ * 1/||row|| vectors a producer already holds -- pb2_project_normalize emits exactly these for its bf16 rows
+ * (SURVEY 8f row 3), so the loss does not re-derive the norms of embeddings the encoder tail just normalised. */
 int64_t pb2_hinge_step_workspace(int64_t n, int dim, int in_dtype);
 int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                    void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a, int out_dtype,
-                   void* stream);
+                   const float* rinv_v_in, const float* rinv_a_in, void* stream);
 
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int dtype, int64_t rows, int dim, int64_t ldy,

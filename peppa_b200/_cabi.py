@@ -51,10 +51,10 @@ SIGNATURES = {
     "pb2_grad_gemm_ws": [_p, _i, _i64, _i64, _i64, _i, _p, _i, _i, _i64, _f, _i, _p, _i64, _p, _i64, _p],
     "pb2_grad_gemm_dual": [_p, _i, _i64, _i64, _i64, _p, _p, _i, _i, _i64, _i64, _f, _p, _p, _i64, _i64, _p],
     "pb2_hinge_finish": [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _i64, _i64, _f, _p, _p, _i64, _p],
-    "pb2_hinge_prep": [_p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p],
+    "pb2_hinge_prep": [_p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
     "pb2_hinge_step_workspace": [_i64, _i, _i],
-    "pb2_hinge_step": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p],
+    "pb2_hinge_step": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p, _p, _p],
     "pb2_rows_scale_f16": [_p, _i, _p, _i64, _i, _i64, _p, _i64, _p],
     "pb2_scale_pair": [_p, _p, _i64, _i, _p, _p, _p, _p],
     "pb2_milnce_finish": [_p, _i64, _p, _i, _i64, _i, _i64, _f, _p, _p, _i64, _p],

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256)
                       float* __restrict__ diag, __half* __restrict__ vh, __half* __restrict__ ah,
                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
                       int n_partials, __half* __restrict__ vx, __half* __restrict__ ax, float* __restrict__ scale_v,
-                      float* __restrict__ scale_a) {
+                      float* __restrict__ scale_a, const float* __restrict__ rinv_v_in, const float* __restrict__ rinv_a_in) {
     pdl_launch_dependents();
     pdl_wait();  // the workspace may still be read by the previous step's kernels
     const int lane = threadIdx.x & 31;
@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(256)
         sv = warp_sum(sv);
         sa = warp_sum(sa);
         dot = warp_sum(dot);
-        const float rv = 1.0f / sqrtf(sv), ra = 1.0f / sqrtf(sa);
+        // 1/||row|| handed over by the producer of the rows (the encoder tail, pb2_project_normalize) is used as it is
+        const float rv = rinv_v_in ? rinv_v_in[r] : 1.0f / sqrtf(sv), ra = rinv_a_in ? rinv_a_in[r] : 1.0f / sqrtf(sa);
         // fp32 inputs: split-fp16 tensor-core operands of the NORMALISED rows (see split_f16_kernel)
         int ev = 0, ea = 0;
         if (vx) {
@@ -961,7 +962,7 @@ extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, con
 extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv, int64_t lda,
                               float* rinv_v, float* rinv_a, float* diag, void* vh, void* ah, int32_t* row_cnt,
                               int32_t* col_cnt, float* loss_partial, int n_partials, void* v_split, void* a_split,
-                              float* scale_v, float* scale_a, void* stream) {
+                              float* scale_v, float* scale_a, const float* rinv_v_in, const float* rinv_a_in, void* stream) {
     if (n <= 0) return PB2_OK;
     if (!v || !a || !rinv_v || !rinv_a || !diag || !vh || !ah || !row_cnt || !col_cnt || !loss_partial)
         return set_error(PB2_ERR_ARG, "hinge_prep: null");
@@ -976,7 +977,7 @@ extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n
     PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_prep_kernel<T>, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream,
                                            1, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
                                            (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials, (__half*)v_split,
-                                           (__half*)a_split, scale_v, scale_a));
+                                           (__half*)a_split, scale_v, scale_a, rinv_v_in, rinv_a_in));
     int rc = check_cuda(e, "hinge_prep");
     if (rc) return rc;
     return check_launch("hinge_prep");

@@ -53,7 +53,7 @@ extern "C" int64_t pb2_hinge_step_workspace(int64_t n, int dim, int in_dtype) {
 
 extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                               void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a,
-                              int out_dtype, void* stream) {
+                              int out_dtype, const float* rinv_v_in, const float* rinv_a_in, void* stream) {
     using pb2::set_error;
     if (n <= 0) return set_error(PB2_ERR_ARG, "hinge_step: empty batch");
     if (!v || !a || !workspace || !loss_out || !d_v || !d_a) return set_error(PB2_ERR_ARG, "hinge_step: null");
@@ -87,7 +87,7 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
     float* sv = split ? reinterpret_cast<float*>(w + L.sv) : nullptr;
     float* sa = split ? reinterpret_cast<float*>(w + L.sa) : nullptr;
     int rc = pb2_hinge_prep(v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part,
-                            vx, ax, sv, sa, stream);
+                            vx, ax, sv, sa, rinv_v_in, rinv_a_in, stream);
     if (rc) return rc;
     rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, split ? sv : rinv_v, split ? sa : rinv_a, diag, diag, n, n, 0, 0,
                        split ? 3 * dim : dim, split ? PB2_F16 : in_dtype, split ? 3 * (int64_t)dim : ldv,

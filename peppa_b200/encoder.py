@@ -9,7 +9,9 @@ what the scoring kernels take as ``rinv`` -- no fp32 round trip, no separate nor
 
 ``ProjectNormalize`` keeps ``nn.Linear``'s parameter names (``weight`` [out, in], ``bias`` [out]) so a
 checkpoint's ``project.*`` tensors load into it unchanged.  The forward GEMM is the hand-written kernel;
-the backward (dX = dY W, dW = dY^T X: plain library GEMMs outside the scoring path) uses torch.matmul.
+the backward (dX = dY W, dW = dY^T X) is two plain dense GEMMs with no epilogue to fuse and no operand the scoring
+kernels share -- library-GEMM territory by this project's own rule (cuBLAS for plain library GEMMs) -- so it stays
+torch.matmul; the scoring path never differentiates through it with anything but these two products.
 """
 from __future__ import annotations
 
@@ -68,6 +70,9 @@ def project_normalize(x, weight, bias=None, eps=1e-12, return_rinv=False):
     """``normalize(linear(x, weight, bias), p=2, dim=1)`` as bf16 (fp32 accumulate); optionally also the fp32
     ``1/||row||`` of the rounded rows (the ``rinv`` operand of the scoring kernels)."""
     out, rinv = _ProjectNormalizeFn.apply(x, weight, bias, float(eps))
+    # the rows travel with their 1/||row||: TripletLoss / recall_* / GalleryStep take it from the tag instead of
+    # recomputing the norms of embeddings this kernel just normalised (pig/util.py:11-12 after pig/models.py:109)
+    ops.tag_rinv(out, rinv)
     return (out, rinv) if return_rinv else out
 
 

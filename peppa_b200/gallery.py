@@ -111,8 +111,9 @@ class GalleryStep:
             a = b
         return works
 
-    def run(self, a_loc: torch.Tensor, v_loc: torch.Tensor):
-        """a_loc, v_loc: [n_local, dim] bf16 on this rank's GPU.  Returns a dict with the global loss
+    def run(self, a_loc: torch.Tensor, v_loc: torch.Tensor, rinv_a=None, rinv_v=None):
+        """a_loc, v_loc: [n_local, dim] bf16 on this rank's GPU; rinv_a / rinv_v: their fp32 1/||row|| if the caller
+        already holds them (the encoder tail emits them; rows tagged by it are recognised too).  Returns a dict with the global loss
         (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
         ([top_n + 1] fp32: global recall@n, row 0 == 0) and the local int32 ``ranks``."""
         import torch.distributed as dist
@@ -121,8 +122,11 @@ class GalleryStep:
         ops = self.ops
         nl, n, dev = self.n_local, self.n_total, self.device
         r0g = self.rank * nl                                  # global id of the first local row
-        ra, _ = ops.row_norms(a_loc)
-        rv, _ = ops.row_norms(v_loc)
+        known = getattr(ops, "known_rinv", lambda *_: None)
+        ra = rinv_a if rinv_a is not None else known(a_loc, a_loc)
+        rv = rinv_v if rinv_v is not None else known(v_loc, v_loc)
+        ra = ra if ra is not None else ops.row_norms(a_loc)[0]
+        rv = rv if rv is not None else ops.row_norms(v_loc)[0]
         diag, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv)        # S_ii and its rank threshold
         if self.world > 1:
             self._all_gather(self.v_full, v_loc)

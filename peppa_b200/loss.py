@@ -38,14 +38,14 @@ class _HingeFn(torch.autograd.Function):
         if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the four-launch fused step
             # gradients stay fp32 until grad_output has been applied (backward): an AMP GradScaler's 65536 must
             # reach an fp16 gradient of ~1e-7 before the rounding does
-            loss, grads = ops.hinge_step(vb, ab, margin, torch.float32)
+            # (embeddings that come from the encoder tail carry their 1/||row||: nothing re-derives the norms)
+            loss, grads = ops.hinge_step(vb, ab, margin, torch.float32, ops.known_rinv(V, vb), ops.known_rinv(A, ab))
             ctx.save_for_backward(grads)
             ctx.fused = True
             ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
             return loss.to(V.device)
         ctx.fused = False
-        rv, nv = ops.row_norms(vb)
-        ra, na = ops.row_norms(ab)
+        rv, ra = ops.rinv_of(V, vb), ops.rinv_of(A, ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
         vx, ax, fv, fa = ops.mma_pair(vb, ab, rv, ra)           # tensor-core operands + epilogue factors (split-fp16 for fp32 rows)
         row_cnt = torch.zeros(n, dtype=torch.int32, device=dev)

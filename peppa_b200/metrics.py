@@ -46,8 +46,7 @@ def _pair_ranks(candidates, references, correct):
     """int32 rank of every (row, target) pair plus the bookkeeping to fold pairs back into rows."""
     qb, gb = ops.as_row_pair(references, candidates)      # own dtype, sizes checked like the reference's matmul
     dev = qb.device
-    rq, _ = ops.row_norms(qb)
-    rg, _ = ops.row_norms(gb)
+    rq, rg = ops.rinv_of(references, qb), ops.rinv_of(candidates, gb)      # the encoder tail's 1/||row|| when tagged
     qb, gb, rq, rg = ops.mma_pair(qb, gb, rq, rg)         # tensor-core operands + epilogue factors (split-fp16 for fp32 rows)
     rows, cols, counts = _targets(correct, qb.shape[0], gb.shape[0], dev)
     if counts is None:

@@ -402,7 +402,33 @@ def project_normalize(x_bf16, w_bf16, bias=None, eps=1e-12):
 _STEP_WORKSPACE = {}      # (device, stream, n, d, dtype) -> uint8 workspace, reused across steps ON THAT STREAM
 
 
-def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
+def tag_rinv(rows: torch.Tensor, rinv: torch.Tensor) -> torch.Tensor:
+    """Remember on a tensor of embedding rows the fp32 1/||row|| its producer computed (the encoder tail emits it
+    with the rows).  The tag names the tensor's version counter, so an in-place edit voids it."""
+    rows._pb2_rinv = (rinv, rows._version)
+    return rows
+
+
+def known_rinv(original: torch.Tensor, rows: torch.Tensor):
+    """The tagged 1/||row|| of ``original`` if ``rows`` (what as_rows made of it) still IS that tensor's memory --
+    same storage, dtype and shape, untouched since the tag was set -- else None (the caller computes the norms)."""
+    tag = getattr(original, "_pb2_rinv", None)
+    if tag is None:
+        return None
+    rinv, version = tag
+    if (original._version != version or rows.data_ptr() != original.data_ptr() or rows.dtype != original.dtype
+            or rows.shape != original.shape or rinv.device != rows.device or rinv.shape != (rows.shape[0],)):
+        return None
+    return rinv
+
+
+def rinv_of(original, rows):
+    """1/||row|| of ``rows``: the producer's tagged vector when it is still valid, else pb2_row_norms."""
+    r = known_rinv(original, rows)
+    return r if r is not None else row_norms(rows)[0]
+
+
+def hinge_step(vb, ab, margin, grad_dtype=torch.float32, rinv_v=None, rinv_a=None):
     """Whole TripletLoss forward + gradients for one gradient-matrix block (n <= 32768): one C call, four
     launches (prep, fused similarity/hinge pass, both gradient GEMMs, finish).  vb / ab: rows from as_row_pair
     (bf16, fp16 or fp32).  Returns (loss 0-d fp32, grads [2, n, d] in ``grad_dtype``: dV then dA)."""
@@ -426,8 +452,8 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32):
     loss = torch.empty((), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _timed("hinge_step (4 kernels)", 6.0 * n * n * d, dev):
         check(lib.pb2_hinge_step(_ptr(vb), _ptr(ab), code, n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws), ws.numel(),
-                                 _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), _DTYPE_CODE[grad_dtype], _stream(dev)),
-              "hinge_step")
+                                 _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), _DTYPE_CODE[grad_dtype], _ptr(rinv_v), _ptr(rinv_a),
+                                 _stream(dev)), "hinge_step")
     return loss, grads
 
 

@@ -776,6 +776,44 @@ def test_encoder_tail_feeds_the_loss(pb):
     assert ref.item() > 1e-3 and rel_err(got, ref) < 5e-3     # embeddings are bf16-rounded before the loss
 
 
+def test_encoder_tail_rinv_is_consumed_not_recomputed(pb):
+    """SURVEY 8f row 3, second half: the tail's fp32 1/||row|| travels with its bf16 rows (a tag on the tensor) and
+    TripletLoss / recall_at_n / GalleryStep take it instead of running pb2_row_norms (or the norm part of
+    pb2_hinge_prep) again.  The tail sums the squares in its own order, so the two 1/||row|| agree to fp32 rounding,
+    not bit for bit; results agree to ~1e-6.  An in-place edit of the rows voids the tag."""
+    from peppa_b200 import encoder, ops
+    from peppa_b200.gallery import GalleryStep
+    g = torch.Generator().manual_seed(3)
+    n = 1024
+    fv = torch.randn(n, 512, generator=g).bfloat16().cuda()
+    fa = (fv.float().cpu() * 0.3 + torch.randn(n, 512, generator=g)).bfloat16().cuda()
+    tail = encoder.ProjectNormalize(512, 512).cuda()
+    ev, rv = tail(fv, return_rinv=True)
+    ea, ra = tail(fa, return_rinv=True)
+    assert ops.known_rinv(ev, ops.as_rows(ev)) is rv and ops.known_rinv(ea, ops.as_rows(ea)) is ra
+    assert (rv - ops.row_norms(ev.detach())[0]).abs().max().item() < 1e-6
+    calls = []
+    orig = ops.row_norms
+    ops.row_norms = lambda x: calls.append(tuple(x.shape)) or orig(x)
+    try:
+        lt = pb.loss.TripletLoss(0.2)(ev, ea)                                  # fused step: norms skipped in hinge_prep
+        rt = pb.metrics.recall_at_n(ev, ea, None, n=10)
+        gt = GalleryStep(n, 512).run(ea.detach(), ev.detach(), rinv_a=ra, rinv_v=rv)
+        assert calls == []                                                     # nothing recomputed a norm
+        lu = pb.loss.TripletLoss(0.2)(ev.detach().clone(), ea.detach().clone())   # untagged copies: norms recomputed
+        ru = pb.metrics.recall_at_n(ev.detach().clone(), ea.detach().clone(), None, n=10)
+        gu = GalleryStep(n, 512).run(ea.detach().clone(), ev.detach().clone())
+        assert len(calls) >= 4
+    finally:
+        ops.row_norms = orig
+    assert abs(lt.item() - lu.item()) < 1e-6 * abs(lu.item()) and abs(gt["loss"].item() - gu["loss"].item()) < 1e-6 * abs(lu.item())
+    assert int((rt != ru).sum()) <= 2 and rel_err(gt["dA"], gu["dA"]) < 1e-5       # a 1-ulp rinv may move a near-tie
+    lt.backward()                                                              # gradients flow back into the tail
+    assert tail.weight.grad is not None and bool(torch.isfinite(tail.weight.grad).all())
+    ev.detach().mul_(1.0)                                                      # any in-place edit bumps the version
+    assert ops.known_rinv(ev, ops.as_rows(ev)) is None
+
+
 def test_embedding_store_scoring(pb, tmp_path):
     """a gallery scored from the sharded store equals the same embeddings scored directly,
     and an evaluation row built from stores matches the oracle metrics with the reference's seeds."""

@@ -290,6 +290,38 @@ int pb2_project_normalize(const void* x, const void* w, const float* bias, int64
                           int64_t ldx, int64_t ldw, float eps, void* out, int64_t ld_out, float* rinv, float* norm,
                           void* stream);
 
+/* ---- multi-GPU: one process per GPU on one node; rank r owns rows [r N/P, (r+1) N/P).
+ *
+ * Peer memory over NVLink / NVSwitch.  pb2_ipc_export: CUDA IPC handle (PB2_IPC_HANDLE_BYTES bytes) of the
+ * allocation `ptr` lies in, plus ptr's byte offset inside it; ship both to the other ranks by any host channel.
+ * pb2_ipc_open (on the receiving rank, its own device current): maps the allocation with lazy peer access and
+ * returns its base (for pb2_ipc_close) and the peer pointer base + offset, usable by this device's kernels.
+ * pb2_peer_reduce: out[i] = sum_q src[q][i] (fp32, fixed order q = 0 .. n_src-1, n_src <= PB2_MAX_PEERS, n_elems
+ * a multiple of 4): the dV reduce-scatter of the sharded backward as ONE kernel of ours over peer memory -- the
+ * owner of a row block pulls every rank's partial rows and sums them; no collective kernel runs beside the
+ * tensor-core grids during the step.  `src` is a HOST array of device pointers (local or peer).  The caller orders
+ * the launch after a collective that every rank enters once its partials are complete (pb2_nccl_colstat_merge). */
+#define PB2_IPC_HANDLE_BYTES 64
+#define PB2_MAX_PEERS 16
+int pb2_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out);
+int pb2_ipc_open(const void* handle, int64_t offset, void** base_out, void** ptr_out);
+int pb2_ipc_close(void* base);
+int pb2_peer_reduce(const void* const* src, int n_src, int64_t n_elems, float* out, void* stream);
+
+/* NCCL steps of the sharded gallery for hosts that bring their own ncclComm_t (`comm`; the library binds NCCL at
+ * run time -- dlsym on the process, else dlopen("libnccl.so.2") -- pb2_nccl_available() says whether it found it):
+ *   pb2_nccl_gallery_allgather   rank r's rows (n_local x row_bytes raw bytes) -> all rows, rank-major (8e.1:
+ *                                embeddings, 1/||row||, diagonal scores)
+ *   pb2_nccl_colstat_merge       one NCCL group summing the column counts (int32 [n_total]), the scalar loss and
+ *                                the recall hit counts (fp32 [n_hits]) over the ranks (8e.3); NULL = skip that one
+ *   pb2_nccl_dv_reduce_scatter   dV partials [world * n_local, dim] fp32 -> this rank's summed rows (8e.4), for
+ *                                hosts without peer access (pb2_peer_reduce is the NVLink path) */
+int pb2_nccl_available(void);
+int pb2_nccl_gallery_allgather(void* comm, const void* local_rows, int64_t n_local, int64_t row_bytes, void* full_out,
+                               void* stream);
+int pb2_nccl_colstat_merge(void* comm, int32_t* col_cnt, int64_t n_total, float* loss, float* hits, int n_hits, void* stream);
+int pb2_nccl_dv_reduce_scatter(void* comm, const float* partial_full, int64_t n_local, int dim, float* out_local, void* stream);
+
 /* number of CTAs the persistent similarity kernels launch on the current device */
 int pb2_sim_grid(void);
 

@@ -63,6 +63,14 @@ SIGNATURES = {
     "pb2_sum_partials": [_p, _i, _f, _p, _p],
     "pb2_hinge_loss_terms": [_p, _i, _p, _p, _i64, _f, _f, _p, _i, _p],
     "pb2_milnce_loss": [_p, _p, _p, _i64, _p, _p, _p],
+    "pb2_ipc_export": [_p, _p, _p],
+    "pb2_ipc_open": [_p, _i64, _p, _p],
+    "pb2_ipc_close": [_p],
+    "pb2_peer_reduce": [_p, _i, _i64, _p, _p],
+    "pb2_nccl_available": [],
+    "pb2_nccl_gallery_allgather": [_p, _p, _i64, _i64, _p, _p],
+    "pb2_nccl_colstat_merge": [_p, _p, _i64, _p, _p, _i, _p],
+    "pb2_nccl_dv_reduce_scatter": [_p, _p, _i64, _i, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
 }
 _RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64,

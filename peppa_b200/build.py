@@ -24,7 +24,7 @@ LIB = os.path.join(CSRC, "libpeppa_b200.so")
 OBJ_MEASURE = os.path.join(CSRC, "build_measure")
 LIB_MEASURE = os.path.join(CSRC, "libpeppa_b200_measure.so")
 
-LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu"]
+LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu", "collective.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v",
@@ -76,7 +76,7 @@ def _link(lib: str, objs) -> None:
     newest = max(os.path.getmtime(o) for o in objs)
     if not os.path.exists(lib) or os.path.getmtime(lib) < newest:
         tmp = lib + f".tmp{os.getpid()}"
-        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs], check=True)
+        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"], check=True)
         os.replace(tmp, lib)        # atomic: another rank may be dlopen()ing the old file
 
 

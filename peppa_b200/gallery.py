@@ -5,15 +5,19 @@ Rank r owns rows [r*N/P, (r+1)*N/P) of both the audio matrix A and the video mat
 Rows of S are the local audio clips (queries, as in pig/metrics.py:8 where ``references`` = audio),
 columns are ALL video clips:
 
-  1. all-gather the video block (bf16), its row norms and the diagonal scores  (NCCL over NVLink)
-  2. fused tcgen05 pass over the [N/P x N] strip: hinge loss partials, indicator counts, rank
-     counts of the diagonal, and the fp16 gradient-matrix block           (pb2_sim_hinge + rank)
-  3. gradient GEMMs: dA rows are complete locally; dV partials are [N, D] per rank.  The strip is walked
-     column block by column block, and as soon as a column block's dV partial is complete it is reduced
-     to the rank that owns those video rows (asynchronously, on NCCL's stream, while the next column
-     block computes): the 2 GiB reduce-scatter of a 2^20 gallery hides behind the tensor work
-  4. all-reduce the column counts (int32) and the scalar loss
-  5. normalisation Jacobian (pb2_hinge_finish) on the local rows
+  1. all-gather the video block (bf16), its row norms and the diagonal scores (NCCL over NVLink), ASYNCHRONOUSLY:
+     the strip is walked column block by column block starting with the blocks this rank owns -- they need no
+     remote data -- and the gathered blocks are awaited only when the walk reaches the first remote one
+  2. fused tcgen05 pass over each [rows x column block]: hinge loss partials, indicator counts, rank counts of the
+     diagonal, and the gradient-matrix block (one byte per entry)            (pb2_sim_hinge + rank)
+  3. gradient GEMMs (kind::i8): dA rows are complete locally; dV partials are [N, D] per rank
+  4. all-reduce the column counts (int32), the scalar loss and the recall hits -- one small NCCL step that is also
+     the barrier after which every rank's dV partials are final
+  5. dV reduce-scatter over PEER MEMORY: every rank pulls the partial rows it owns from all ranks with P2P loads over
+     NVLink and sums them in a fixed order (pb2_peer_reduce on buffers exchanged as CUDA IPC handles).  No NCCL
+     kernel runs beside the persistent tensor-core grids during the step (round 1 reduced per column block with
+     ncclReduce, whose CTAs took SMs from the 148-CTA GEMM grids: +4 % on every overlapped launch at 8 GPUs)
+  6. normalisation Jacobian (pb2_hinge_finish) on the local rows
 
 The loss is symmetric in (V, A) (pig/loss.py:41-48 adds the row and the column hinge), so
 ``contrastive(cosine_matrix(A, V))`` equals the reference's ``TripletLoss(V, A)``; the gradients are
@@ -22,8 +26,8 @@ returned under their own names.  With world_size == 1 no collective is issued.
 ``loss="milnce"`` runs pig/loss.py:13-26 (MILNCELoss, K = 1, optional temperature) over the same sharding:
 row log-sum-exp of the local strip is complete locally; the column log-sum-exp is a partial per rank
 (over its own rows) and is merged across ranks (all-gather of the [N] partials + pb2_lse_combine); the
-backward recomputes the strip, writes the fp16 gradient-matrix blocks and reduce-scatters dV like the
-hinge path.  (No recall in this mode.)
+backward recomputes the strip, writes the fp16 gradient-matrix blocks and reduces dV like the hinge path.
+``with_recall=True`` adds recall@1..N of the same gallery (pb2_sim_rank on the local strip).
 """
 from __future__ import annotations
 
@@ -31,20 +35,62 @@ import torch
 
 from . import ops
 
-_BLOCK = 32768      # gradient-matrix block edge (rows x cols fp16 kept in HBM at once: 2 GiB)
+_BLOCK = 32768      # gradient-matrix block edge (rows x cols kept in HBM at once: 1 GiB of bytes, 2 GiB of fp16)
 
 
-def _blocks(n, step):
-    return [(s, min(n, s + step)) for s in range(0, n, step)]
+def _blocks(n, step, base=0):
+    return [(base + s, base + min(n, s + step)) for s in range(0, n, step)]
+
+
+class _PeerRows:
+    """The [N, D] fp32 dV partial of every rank, mapped into this process over CUDA IPC (one process per GPU, one
+    node): ``ptrs[q]`` is rank q's buffer as a device pointer usable by this GPU's kernels."""
+
+    def __init__(self, buf, rank, world, group, device):
+        import torch.distributed as dist
+        self.device, self.bases, self.ptrs = device, [], []
+        try:
+            mine = ops.ipc_export(buf)
+        except Exception:  # noqa: BLE001 -- every rank still takes part in the exchange below
+            mine = None
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        if any(h is None for h in handles):
+            raise RuntimeError("a rank could not export its buffer as a CUDA IPC handle")
+        try:
+            for q in range(world):
+                if q == rank:
+                    self.ptrs.append(buf.data_ptr())
+                else:
+                    base, ptr = ops.ipc_open(handles[q][0], handles[q][1], device)
+                    self.bases.append(base)
+                    self.ptrs.append(ptr)
+        except Exception:
+            self.close()
+            raise
+        self._keep = buf
+
+    def close(self):
+        for b in self.bases:
+            try:
+                ops.ipc_close(b, self.device)
+            except Exception:  # noqa: BLE001 -- interpreter shutdown: the driver unmaps with the context
+                pass
+        self.bases = []
 
 
 class GalleryStep:
     """Reusable buffers + one ``run`` per step.  ``group`` is a torch.distributed process group (or
-    None for the default group); ``world == 1`` needs no initialised process group at all."""
+    None for the default group); ``world == 1`` needs no initialised process group at all.
+
+    ``dv_reduce``: how the dV partials reach their owners when world > 1 -- "p2p" (our own kernel over peer memory, see
+    the module docstring), "nccl" (per column block ncclReduce overlapped with the tensor work; also what the gloo
+    orchestration tests run) or "auto" (default: p2p if the IPC exchange succeeds on every rank, else nccl)."""
 
     def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
                  group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None,
-                 loss: str = "hinge", temperature: float = 1.0, logit_bound=None, byte_gmat=None):
+                 loss: str = "hinge", temperature: float = 1.0, logit_bound=None, byte_gmat=None, dv_reduce="auto",
+                 with_recall=None):
         if loss not in ("hinge", "milnce"):
             raise ValueError("loss must be 'hinge' or 'milnce'")
         self.loss, self.inv_tau = loss, 1.0 / float(temperature)
@@ -61,6 +107,7 @@ class GalleryStep:
         self.device = ops.require_cuda(device) if backend is None else torch.device(device or "cpu")
         self.block = block
         self.with_grad = with_grad
+        self.with_recall = (loss == "hinge") if with_recall is None else bool(with_recall)
         dev, n, nl = self.device, self.n_total, n_local
         f32, i32 = torch.float32, torch.int32
         self.v_full = torch.empty(n, dim, dtype=torch.bfloat16, device=dev) if world > 1 else None
@@ -69,11 +116,14 @@ class GalleryStep:
         self.row_cnt = torch.empty(nl, dtype=i32, device=dev)
         self.col_cnt = torch.empty(n, dtype=i32, device=dev)
         self.ranks = torch.empty(nl, dtype=i32, device=dev)
+        self.peers = None
+        if dv_reduce not in ("auto", "p2p", "nccl"):
+            raise ValueError("dv_reduce must be 'auto', 'p2p' or 'nccl'")
         if with_grad:
             self.p_a = torch.empty(nl, dim, dtype=f32, device=dev)
             self.p_v = torch.empty(n, dim, dtype=f32, device=dev)
             self.p_v_loc = torch.empty(nl, dim, dtype=f32, device=dev) if world > 1 else None
-            br, bc = min(block, nl), min(block, n)
+            br = bc = min(block, nl)             # column blocks never straddle two owners
             # hinge: the gradient matrix is exactly {0, 1, 2} -> one byte per entry and kind::i8 gradient GEMMs
             # (byte_gmat=False keeps the fp16 matrix; MIL-NCE's entries are softmax weights and stay fp16)
             self.byte_gmat = (loss == "hinge" and dim % 256 == 0 and block <= 32768) if byte_gmat is None else bool(byte_gmat)
@@ -84,37 +134,79 @@ class GalleryStep:
             else:
                 self.byte_gmat = False
                 self.gmat, self.ld_g = self.ops.gmat_alloc(br, bc, dev)
+            if world > 1 and backend is None and dv_reduce != "nccl":
+                try:
+                    self.peers = _PeerRows(self.p_v, rank, world, group, dev)
+                except Exception:  # noqa: BLE001 -- e.g. a virtual-memory allocator segment has no IPC handle
+                    if dv_reduce == "p2p":
+                        raise
+                    self.peers = None
+                self._agree_on_peers()
+
+    def _agree_on_peers(self):
+        """Every rank uses the peer-memory path or none does (a collective decision, made once)."""
+        import torch.distributed as dist
+        ok = torch.tensor([1 if self.peers is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0 and self.peers is not None:
+            self.peers.close()
+            self.peers = None
+
+    def __del__(self):
+        if getattr(self, "peers", None) is not None:
+            self.peers.close()
 
     # -- collectives (no-ops for world == 1) ------------------------------------------------------
-    def _all_gather(self, out, loc):
+    def _all_gather(self, out, loc, async_op=False):
         import torch.distributed as dist
-        dist.all_gather_into_tensor(out, loc.contiguous(), group=self.group)
+        return dist.all_gather_into_tensor(out, loc.contiguous(), group=self.group, async_op=async_op)
 
-    def _reduce_scatter(self, out, full):
+    def _reduce_to_owner(self, full, c0, c1):
+        """NCCL / gloo path: start the reduction of rows [c0, c1) of a [N, D] partial to the rank owning them (summed in
+        place there).  Returns the pending work handle."""
         import torch.distributed as dist
-        if dist.get_backend(self.group) == "gloo":      # gloo has no reduce_scatter: all-reduce + slice
-            dist.all_reduce(full, group=self.group)
-            out.copy_(full[self.rank * self.n_local:(self.rank + 1) * self.n_local])
-        else:
-            dist.reduce_scatter_tensor(out, full, group=self.group)
+        owner = c0 // self.n_local
+        dst = dist.get_global_rank(self.group, owner) if self.group is not None else owner
+        return dist.reduce(full[c0:c1], dst=dst, group=self.group, async_op=True)
 
-    def _reduce_to_owners(self, full, c0, c1):
-        """Start the reduction of rows [c0, c1) of a [N, D] partial to the rank(s) owning them; the owner's
-        rows are summed in place.  Returns the pending work handles."""
-        import torch.distributed as dist
-        works, a = [], c0
-        while a < c1:
-            owner = a // self.n_local
-            b = min(c1, (owner + 1) * self.n_local)
-            dst = dist.get_global_rank(self.group, owner) if self.group is not None else owner
-            works.append(dist.reduce(full[a:b], dst=dst, group=self.group, async_op=True))
-            a = b
-        return works
+    def _column_blocks(self):
+        """[(c0, c1, local)] over all N columns, never straddling two owners: this rank's own blocks first (they need no
+        gathered data), then the other owners' in rank order."""
+        nl = self.n_local
+        owners = [self.rank] + [q for q in range(self.world) if q != self.rank]
+        return [(c0, c1, q == self.rank) for q in owners for (c0, c1) in _blocks(nl, self.block, q * nl)]
+
+    def _start_ready_reductions(self, done_c1, state):
+        """NCCL / gloo path: collectives must be issued in ONE order on every rank, while each rank walks its own
+        blocks first.  Reductions are therefore started owner by owner in rank order, as soon as this rank has
+        finished every block up to that point of the canonical order (its own blocks wait for their turn)."""
+        state["done"].add(done_c1)
+        while state["next"] < len(state["order"]):
+            c0, c1 = state["order"][state["next"]]
+            if c1 not in state["done"]:
+                break
+            state["pending"].append(self._reduce_to_owner(self.p_v, c0, c1))
+            state["next"] += 1
+
+    def _reduction_state(self):
+        order = [(c0, c1) for q in range(self.world) for (c0, c1) in _blocks(self.n_local, self.block, q * self.n_local)]
+        return {"order": order, "next": 0, "done": set(), "pending": []}
+
+    def _own_dv_rows(self):
+        """This rank's rows of the dV partials summed over the ranks: peer-memory pull (our kernel) or what NCCL left."""
+        nl, r0g = self.n_local, self.rank * self.n_local
+        if self.world == 1:
+            return self.p_v
+        if self.peers is not None:
+            off = r0g * self.dim * 4
+            ops.peer_reduce([p + off for p in self.peers.ptrs], self.p_v_loc)
+            return self.p_v_loc
+        return self.p_v[r0g:r0g + nl]        # reduced in place by _reduce_to_owner
 
     def run(self, a_loc: torch.Tensor, v_loc: torch.Tensor, rinv_a=None, rinv_v=None):
         """a_loc, v_loc: [n_local, dim] bf16 on this rank's GPU; rinv_a / rinv_v: their fp32 1/||row|| if the caller
-        already holds them (the encoder tail emits them; rows tagged by it are recognised too).  Returns a dict with the global loss
-        (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
+        already holds them (the encoder tail emits them; rows tagged by it are recognised too).  Returns a dict with
+        the global loss (0-d fp32), the local gradient rows ``dA``/``dV`` (fp32, None without grad), ``recall``
         ([top_n + 1] fp32: global recall@n, row 0 == 0) and the local int32 ``ranks``."""
         import torch.distributed as dist
         if self.loss == "milnce":
@@ -128,64 +220,71 @@ class GalleryStep:
         ra = ra if ra is not None else ops.row_norms(a_loc)[0]
         rv = rv if rv is not None else ops.row_norms(v_loc)[0]
         diag, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv)        # S_ii and its rank threshold
-        if self.world > 1:
-            self._all_gather(self.v_full, v_loc)
-            self._all_gather(self.rv_full, rv)
-            self._all_gather(self.diag_full, diag)
-            v_full, rv_full, diag_full = self.v_full, self.rv_full, self.diag_full
-        else:
-            v_full, rv_full, diag_full = v_loc, rv, diag
+        gathers = []
+        if self.world > 1:      # in flight while the local column blocks compute
+            gathers = [self._all_gather(self.v_full, v_loc, True), self._all_gather(self.rv_full, rv, True),
+                       self._all_gather(self.diag_full, diag, True)]
         self.row_cnt.zero_()
         self.col_cnt.zero_()
         self.ranks.zero_()
         loss = torch.zeros((), dtype=torch.float32, device=dev)
-        rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
+        rblocks, cblocks = _blocks(nl, self.block), self._column_blocks()
         if self.with_grad:
-            if self.byte_gmat:      # two 8-bit planes per row: the operand of the kind::i8 gradient GEMMs
-                ah = ops.rows_quant_i8(a_loc, ra)
-                vh = ops.rows_quant_i8(v_full, rv_full)
+            quant = ops.rows_quant_i8 if self.byte_gmat else ops.rows_scale_f16
+            ah = quant(a_loc, ra)               # embedding operands of the gradient GEMMs (two 8-bit planes / fp16)
+            vh_loc, vh_full = quant(v_loc, rv), None
+        red = self._reduction_state()
+        for ci, (c0, c1, local) in enumerate(cblocks):      # column blocks outermost: a block's dV partial completes early
+            if local:       # this rank's own video rows: no gathered data needed
+                vc, rvc, dc = v_loc[c0 - r0g:c1 - r0g], rv[c0 - r0g:c1 - r0g], diag[c0 - r0g:c1 - r0g]
+                vhc = vh_loc[c0 - r0g:c1 - r0g] if self.with_grad else None
             else:
-                ah = ops.rows_scale_f16(a_loc, ra)
-                vh = ops.rows_scale_f16(v_full, rv_full)
-            acc_a, acc_v = len(cblocks) > 1, len(rblocks) > 1
-            if acc_a:
-                self.p_a.zero_()
-            if acc_v:
-                self.p_v.zero_()
-        pending = []
-        for (c0, c1) in cblocks:            # column blocks outermost: a block's dV partial completes early
-            for (r0, r1) in rblocks:
-                part = ops.sim_hinge(a_loc[r0:r1], v_full[c0:c1], ra[r0:r1], rv_full[c0:c1], diag[r0:r1],
-                                     diag_full[c0:c1], self.margin, self.row_cnt[r0:r1], self.col_cnt[c0:c1],
-                                     self.gmat if self.with_grad else None, self.ld_g if self.with_grad else 0,
-                                     row_offset=r0g + r0, col_offset=c0, pos_thr=pos_thr[r0:r1],
-                                     rank=self.ranks[r0:r1])
+                for w in gathers:
+                    w.wait()
+                gathers = []
+                if self.with_grad and vh_full is None:
+                    vh_full = quant(self.v_full, self.rv_full)
+                vc, rvc, dc = self.v_full[c0:c1], self.rv_full[c0:c1], self.diag_full[c0:c1]
+                vhc = vh_full[c0:c1] if self.with_grad else None
+            for ri, (r0, r1) in enumerate(rblocks):
+                part = ops.sim_hinge(a_loc[r0:r1], vc, ra[r0:r1], rvc, diag[r0:r1], dc, self.margin, self.row_cnt[r0:r1],
+                                     self.col_cnt[c0:c1], self.gmat if self.with_grad else None,
+                                     self.ld_g if self.with_grad else 0, row_offset=r0g + r0, col_offset=c0,
+                                     pos_thr=pos_thr[r0:r1], rank=self.ranks[r0:r1])
                 ops.hinge_loss_terms(loss, partials=part)
-                if self.with_grad:
-                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vh[c0:c1], transpose=False,
-                                  out=self.p_a[r0:r1], accumulate=acc_a)
-                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True,
-                                  out=self.p_v[c0:c1], accumulate=acc_v)
-            if self.with_grad and self.world > 1:
-                pending += self._reduce_to_owners(self.p_v, c0, c1)
+                if self.with_grad:      # first contribution overwrites, later ones accumulate: no zero-fill pass, and
+                    # nothing touches a remote owner's rows of p_v before the gathers above have completed (peers may
+                    # still be pulling last step's partials until they enter this step's all-gather)
+                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vhc, transpose=False, out=self.p_a[r0:r1],
+                                  accumulate=ci > 0)
+                    ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True, out=self.p_v[c0:c1],
+                                  accumulate=ri > 0)
+            if self.with_grad and self.world > 1 and self.peers is None:
+                self._start_ready_reductions(c1, red)
+        for w in gathers:       # (a rank whose walk never left its own blocks: only possible with world == 1)
+            w.wait()
         ops.hinge_loss_terms(loss, diag=diag, cnt=self.row_cnt, margin=self.margin)      # local rows' term
         hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
         hits = hits.sum(dim=1).to(torch.float32)
         if self.world > 1:
+            # also the barrier of the peer-memory reduction: a rank enters it after its last gradient GEMM
             dist.all_reduce(self.col_cnt, group=self.group)
             dist.all_reduce(loss, group=self.group)
             dist.all_reduce(hits, group=self.group)
-            for w in pending:
+            for w in red["pending"]:
                 w.wait()
+            diag_full = self.diag_full
+        else:
+            diag_full = diag
         # column term from the merged counts (identical on every rank, added once after the all-reduce)
         ops.hinge_loss_terms(loss, diag=diag_full, cnt=self.col_cnt, margin=self.margin)
         inv_n2 = 1.0 / float(n) ** 2
         out = {"loss": loss * inv_n2, "recall": hits / float(n), "ranks": self.ranks, "dA": None, "dV": None}
         if self.with_grad:
             cc = self.col_cnt[r0g:r0g + nl]
-            p_v_loc = self.p_v[r0g:r0g + nl]      # this rank's rows: complete locally (world 1) or reduced in place
+            p_v_own = self._own_dv_rows()
             out["dA"] = ops.hinge_finish(self.p_a, a_loc, v_loc, ra, rv, self.row_cnt, cc, inv_n2)
-            out["dV"] = ops.hinge_finish(p_v_loc, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
+            out["dV"] = ops.hinge_finish(p_v_own, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
         return out
 
     def _run_milnce(self, a_loc, v_loc):
@@ -198,7 +297,8 @@ class GalleryStep:
             v_full = self.v_full
         else:
             v_full = v_loc
-        rblocks, cblocks = _blocks(nl, self.block), _blocks(n, self.block)
+        rblocks = _blocks(nl, self.block)
+        cblocks = [(c0, c1) for (c0, c1, _) in self._column_blocks()]
         lse_row = lse_col = None
         bound = self.logit_bound if self.logit_bound is not None else ops.logit_bound(a_loc, v_full, inv_tau)
         if bound <= ops.LSE_BOTH_MAX_BOUND:
@@ -227,9 +327,22 @@ class GalleryStep:
             diag = diag * inv_tau
         mean_loc, den_loc = ops.milnce_loss(lse_row, lse_col[r0g:r0g + nl].contiguous(), diag)
         loss = mean_loc * float(nl)
+        hits = None
+        if self.with_recall:        # recall@1..N of the same gallery (cosine ranking, pig/metrics.py:23-40) on the local strip
+            ra, _ = ops.row_norms(a_loc)
+            rv_full, _ = ops.row_norms(v_full)
+            _, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv_full[r0g:r0g + nl].contiguous())
+            self.ranks.zero_()
+            cols = torch.arange(r0g, r0g + nl, device=dev, dtype=torch.int64)
+            ops.sim_rank(a_loc, v_full, ra, rv_full, pos_thr, cols, rank=self.ranks)
+            hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
+            hits = hits.sum(dim=1).to(torch.float32)
         if self.world > 1:
             dist.all_reduce(loss, group=self.group)
-        out = {"loss": loss / float(n), "recall": None, "ranks": None, "dA": None, "dV": None}
+            if hits is not None:
+                dist.all_reduce(hits, group=self.group)
+        out = {"loss": loss / float(n), "recall": None if hits is None else hits / float(n),
+               "ranks": self.ranks if hits is not None else None, "dA": None, "dV": None}
         if not self.with_grad:
             return out
         if self.world > 1:
@@ -237,22 +350,23 @@ class GalleryStep:
         else:
             den_full = den_loc
         ah, vh = ops.rows_scale_f16(a_loc), ops.rows_scale_f16(v_full)
-        acc_a, acc_v = len(cblocks) > 1, len(rblocks) > 1
-        if acc_a:
-            self.p_a.zero_()
-        if acc_v:
-            self.p_v.zero_()
-        for (r0, r1) in rblocks:
-            for (c0, c1) in cblocks:
+        red = self._reduction_state()
+        for ci, (c0, c1) in enumerate(cblocks):
+            for ri, (r0, r1) in enumerate(rblocks):
                 ops.sim_lse_grad(a_loc[r0:r1], v_full[c0:c1], den_loc[r0:r1], den_full[c0:c1], self.gmat, self.ld_g,
                                  scale=inv_tau)
                 ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, vh[c0:c1], transpose=False, out=self.p_a[r0:r1],
-                              accumulate=acc_a)
+                              accumulate=ci > 0)
                 ops.grad_gemm(self.gmat, r1 - r0, c1 - c0, self.ld_g, ah[r0:r1], transpose=True, out=self.p_v[c0:c1],
-                              accumulate=acc_v)
+                              accumulate=ri > 0)
+            if self.world > 1 and self.peers is None:
+                self._start_ready_reductions(c1, red)
         if self.world > 1:
-            self._reduce_scatter(self.p_v_loc, self.p_v)
-        p_v_loc = self.p_v_loc if self.world > 1 else self.p_v
+            if self.peers is not None:      # stream-ordered barrier: every rank's partials are final once it has passed
+                dist.all_reduce(torch.zeros(1, dtype=torch.float32, device=dev), group=self.group)
+            for w in red["pending"]:
+                w.wait()
+        p_v_own = self._own_dv_rows()
         out["dA"] = ops.milnce_finish(self.p_a, v_loc, inv_tau / float(n))
-        out["dV"] = ops.milnce_finish(p_v_loc, a_loc, inv_tau / float(n))
+        out["dV"] = ops.milnce_finish(p_v_own, a_loc, inv_tau / float(n))
         return out

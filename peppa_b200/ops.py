@@ -353,6 +353,36 @@ def rows_quant_i8(x, rinv=None, out=None):
     return out
 
 
+def ipc_export(t: torch.Tensor):
+    """(64-byte CUDA IPC handle of the allocation ``t`` lies in, byte offset of ``t`` inside it)."""
+    handle = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    with torch.cuda.device(t.device):
+        check(_cabi.lib().pb2_ipc_export(_ptr(t), handle, C.byref(off)), "ipc_export")
+    return handle.raw, int(off.value)
+
+
+def ipc_open(handle: bytes, offset: int, device):
+    """Map a peer rank's allocation on ``device``; returns (base, pointer) as ints (base is for ipc_close)."""
+    base, ptr = C.c_void_p(0), C.c_void_p(0)
+    with torch.cuda.device(device):
+        check(_cabi.lib().pb2_ipc_open(C.c_char_p(handle), int(offset), C.byref(base), C.byref(ptr)), "ipc_open")
+    return int(base.value), int(ptr.value)
+
+
+def ipc_close(base: int, device):
+    with torch.cuda.device(device):
+        check(_cabi.lib().pb2_ipc_close(C.c_void_p(base)), "ipc_close")
+
+
+def peer_reduce(ptrs, out: torch.Tensor):
+    """out = sum over the device pointers ``ptrs`` (ints; local or peer memory, fp32, out.numel() elements each)."""
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    with torch.cuda.device(out.device), _timed("peer_reduce", float(len(ptrs) + 1) * out.numel() * 4, out.device):
+        check(_cabi.lib().pb2_peer_reduce(arr, len(ptrs), out.numel(), _ptr(out), _stream(out.device)), "peer_reduce")
+    return out
+
+
 def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
     rows, d = x.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=x.device)

@@ -43,7 +43,7 @@ class _HingeFn(torch.autograd.Function):
             ctx.save_for_backward(grads)
             ctx.fused = True
             ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
-            return loss.to(V.device)
+            return loss if loss.device == V.device else loss.to(V.device)
         ctx.fused = False
         rv, ra = ops.rinv_of(V, vb), ops.rinv_of(A, ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
@@ -91,13 +91,22 @@ class _HingeFn(torch.autograd.Function):
         if ctx.fused:       # one scale kernel for both gradients, already in the inputs' dtype
             (grads,) = ctx.saved_tensors
             vd, vdev, ad, adev, dv_, da_ = ctx.meta
-            go = grad_out.detach().to(device=grads.device, dtype=torch.float32)
+            go = grad_out.detach()
+            if go.device != grads.device or go.dtype != torch.float32:
+                go = go.to(device=grads.device, dtype=torch.float32)
             # two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy;
             # scaled in fp32, rounded to the inputs' dtype last
             same = vd == ad and vd in (torch.float32, torch.bfloat16, torch.float16)
             g0, g1 = ops.scale_pair(grads[0], grads[1], go, vd if same else torch.float32)
-            gV = g0[:, :dv_].to(device=vdev, dtype=vd) if ctx.needs_input_grad[0] else None
-            gA = g1[:, :da_].to(device=adev, dtype=ad) if ctx.needs_input_grad[1] else None
+            # (this is the batch-1k training step, launch bound: no view, cast or copy that is not needed)
+            d = grads.shape[2]
+            gV = gA = None
+            if ctx.needs_input_grad[0]:
+                gV = g0 if dv_ == d else g0[:, :dv_]
+                gV = gV if (gV.device == vdev and gV.dtype == vd) else gV.to(device=vdev, dtype=vd)
+            if ctx.needs_input_grad[1]:
+                gA = g1 if da_ == d else g1[:, :da_]
+                gA = gA if (gA.device == adev and gA.dtype == ad) else gA.to(device=adev, dtype=ad)
             return gV, gA, None
         dV, dA = ctx.saved_tensors
         vd, vdev, ad, adev = ctx.meta

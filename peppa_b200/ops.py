@@ -37,20 +37,54 @@ class _timed:
             EVENT_LOG.append((self.name, self.flops, self.s, self.e))
 
 
+_CUDA_OK = False
+
+
 def require_cuda(device=None) -> torch.device:
-    if not torch.cuda.is_available():
-        raise RuntimeError("peppa_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    global _CUDA_OK
+    if not _CUDA_OK:        # asked once: torch.cuda.is_available() re-reads the environment on every call
+        if not torch.cuda.is_available():
+            raise RuntimeError("peppa_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+        _CUDA_OK = True
     if device is not None and torch.device(device).type == "cuda":
         return torch.device(device)
     return torch.device("cuda", torch.cuda.current_device())
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    # a plain int (or None = NULL) for a c_void_p parameter: ctypes converts it without an intermediate object
+    return t.data_ptr() if t is not None else None
+
+
+def _dev_index(device):
+    idx = getattr(device, "index", None)
+    return idx if idx is not None else torch.cuda.current_device()
 
 
 def _stream(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    # the raw handle of torch's current stream on that device (a few hundred ns; current_stream() builds a Stream object)
+    return torch._C._cuda_getCurrentRawStream(_dev_index(device))
+
+
+class _on_device:
+    """``with _on_device(t.device):`` -- like torch.cuda.device(), but free when that device already is the current
+    one (every launch of a one-GPU-per-process run): a batch-1k training step is launch bound, and the stock context
+    manager costs several microseconds per call."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = _dev_index(device)
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
 
 
 _ROW_DTYPES = (torch.bfloat16, torch.float16, torch.float32)
@@ -98,7 +132,7 @@ def split_f16(x_f32: torch.Tensor, rinv, side: int):
     n, d = x_f32.shape
     out = torch.empty(n, 3 * d, dtype=torch.float16, device=x_f32.device)
     scale = torch.empty(n, dtype=torch.float32, device=x_f32.device)
-    with torch.cuda.device(x_f32.device):
+    with _on_device(x_f32.device):
         check(_cabi.lib().pb2_split_f16(_ptr(x_f32), _ptr(rinv), n, d, x_f32.stride(0), int(side), _ptr(out), 3 * d,
                                         _ptr(scale), _stream(x_f32.device)), "split_f16")
     return out, scale
@@ -121,7 +155,7 @@ def row_norms(x: torch.Tensor):
     n, d = x.shape
     rinv = torch.empty(n, dtype=torch.float32, device=x.device)
     norm = torch.empty(n, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_row_norms(_ptr(x), _DTYPE_CODE[x.dtype], n, d, x.stride(0), _ptr(rinv), _ptr(norm),
                                         _stream(x.device)), "row_norms")
     return rinv, norm
@@ -139,7 +173,7 @@ def pair_dot(x, y, ix=None, iy=None, rinv_x=None, rinv_y=None, want_dist=False, 
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     dist = torch.empty(n, dtype=torch.float32, device=x.device) if want_dist else None
     thr = torch.empty(n, dtype=torch.float32, device=x.device) if want_thr else None
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_pair_dot(_ptr(x), _ptr(y), _mm_code(x, y), _ptr(ix), _ptr(iy), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1],
                                        x.stride(0), y.stride(0), _ptr(out), _ptr(dist), _ptr(thr), _stream(x.device)),
               "pair_dot")
@@ -153,7 +187,7 @@ def sim_diag(x, y, rinv_x=None, rinv_y=None):
     n = x.shape[0]
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     thr = torch.empty(n, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_sim_diag(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), n, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                        _ptr(out), _ptr(None), _ptr(thr), _stream(x.device)), "sim_diag")
     return out, thr
@@ -165,7 +199,7 @@ def sim_matrix(x, y, rinv_x=None, rinv_y=None, scale=1.0):
     r, c = x.shape[0], y.shape[0]
     ld = max(4, (c + 3) // 4 * 4)
     buf = torch.empty(r, ld, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_sim_matrix(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0),
                                          y.stride(0), float(scale), _ptr(buf), ld, _stream(x.device)), "sim_matrix")
     return buf[:, :c]
@@ -175,7 +209,7 @@ def sim_rank(q, g, rinv_q, rinv_g, pos_thr, pos_col, col_offset=0, rank=None):
     r, c = q.shape[0], g.shape[0]
     if rank is None:
         rank = torch.zeros(r, dtype=torch.int32, device=q.device)
-    with torch.cuda.device(q.device), _timed("sim_rank", 2.0 * r * c * q.shape[1], q.device):
+    with _on_device(q.device), _timed("sim_rank", 2.0 * r * c * q.shape[1], q.device):
         check(_cabi.lib().pb2_sim_rank(_ptr(q), _ptr(g), _ptr(rinv_q), _ptr(rinv_g), _ptr(pos_thr), _ptr(pos_col), r, c,
                                        int(col_offset), q.shape[1], _mm_code(q, g), q.stride(0), g.stride(0), _ptr(rank),
                                        _stream(q.device)), "sim_rank")
@@ -186,14 +220,14 @@ def subset_rank(scores, idx):
     """scores [G, G] fp32 (rows = queries), idx [n_samples, size] int64 on the same device -> int32 ranks."""
     n_samples, size = idx.shape
     rank = torch.empty(n_samples, size, dtype=torch.int32, device=scores.device)
-    with torch.cuda.device(scores.device):
+    with _on_device(scores.device):
         check(_cabi.lib().pb2_subset_rank(_ptr(scores), scores.stride(0), _ptr(idx), n_samples, size, _ptr(rank),
                                           _stream(scores.device)), "subset_rank")
     return rank
 
 
 def sim_grid(device) -> int:
-    with torch.cuda.device(device):
+    with _on_device(device):
         return int(_cabi.lib().pb2_sim_grid())
 
 
@@ -216,7 +250,7 @@ def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt
     r, c = x.shape[0], y.shape[0]
     n_part = sim_grid(x.device)
     part = torch.empty(n_part, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device), _timed("sim_hinge" + ("+rank" if rank is not None else ""), 2.0 * r * c * x.shape[1], x.device):
+    with _on_device(x.device), _timed("sim_hinge" + ("+rank" if rank is not None else ""), 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
                                         int(row_offset), int(col_offset), x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                         float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
@@ -235,7 +269,7 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
     accumulate = lse is not None
     if lse is None:
         lse = torch.empty(r, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device), _timed("sim_lse_rows", 2.0 * r * c * x.shape[1], x.device):
+    with _on_device(x.device), _timed("sim_lse_rows", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
         check(lib.pb2_sim_lse_rows(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                    float(scale), _ptr(pmax), _ptr(psum), st), "sim_lse_rows")
@@ -260,7 +294,7 @@ def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None,
         lse_row = torch.empty(r, dtype=torch.float32, device=x.device)
     if lse_col is None:
         lse_col = torch.empty(c, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device), _timed("sim_lse_both", 2.0 * r * c * x.shape[1], x.device):
+    with _on_device(x.device), _timed("sim_lse_both", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
         check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
                                    float(scale), float(bound), _ptr(prow), _ptr(pcol), st), "sim_lse_both")
@@ -283,14 +317,14 @@ def lse_combine(parts):
     """parts [P, n] fp32 natural-log partial LSEs -> [n] log-sum-exp over P."""
     p_, n = parts.shape
     out = torch.empty(n, dtype=torch.float32, device=parts.device)
-    with torch.cuda.device(parts.device):
+    with _on_device(parts.device):
         check(_cabi.lib().pb2_lse_combine(_ptr(parts), p_, n, _ptr(out), _stream(parts.device)), "lse_combine")
     return out
 
 
 def sim_lse_grad(x, y, den_row, den_col, gmat, ld_g, rinv_x=None, rinv_y=None, scale=1.0):
     r, c = x.shape[0], y.shape[0]
-    with torch.cuda.device(x.device), _timed("sim_lse_grad", 2.0 * r * c * x.shape[1], x.device):
+    with _on_device(x.device), _timed("sim_lse_grad", 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_lse_grad(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(den_row), _ptr(den_col), r, c,
                                            x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0), float(scale), _ptr(gmat), int(ld_g),
                                            _stream(x.device)), "sim_lse_grad")
@@ -302,10 +336,10 @@ _GG_WORKSPACE = {}        # (device, stream) -> zero-initialised stream-K worksp
 def grad_gemm_workspace(device):
     """Stream-K workspace for the current stream of ``device`` (allocated and zeroed once; the kernel
     leaves its flag area zero, and reuse on one stream is stream-ordered)."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    key = (device, torch._C._cuda_getCurrentRawStream(_dev_index(device)))
     ws = _GG_WORKSPACE.get(key)
     if ws is None:
-        with torch.cuda.device(device):
+        with _on_device(device):
             ws = torch.zeros(int(_cabi.lib().pb2_grad_gemm_workspace()), dtype=torch.uint8, device=device)
         _GG_WORKSPACE[key] = ws
     return ws
@@ -322,7 +356,7 @@ def grad_gemm(gmat, g_rows, g_cols, ld_g, z, transpose, alpha=1.0, out=None, acc
         accumulate = False
     # small products are whole-tile anyway; skip the workspace (and its allocation under graph capture)
     ws = grad_gemm_workspace(z.device) if stream_k and m * d > 148 * 128 * 256 else None
-    with torch.cuda.device(z.device), _timed("grad_gemm", 2.0 * g_rows * g_cols * d, z.device):
+    with _on_device(z.device), _timed("grad_gemm", 2.0 * g_rows * g_cols * d, z.device):
         check(_cabi.lib().pb2_grad_gemm_ws(_ptr(gmat), _DTYPE_CODE[gmat.dtype], g_rows, g_cols, int(ld_g),
                                            int(bool(transpose)), _ptr(z), PB2_I8_PLANES if planes else _DTYPE_CODE[z.dtype], d, z.stride(0),
                                            float(alpha), int(bool(accumulate)), _ptr(out), out.stride(0), _ptr(ws),
@@ -335,7 +369,7 @@ def rows_scale_f16(x, rinv=None, out=None):
     n, d = x.shape
     if out is None:
         out = torch.empty(n, d, dtype=torch.float16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_rows_scale_f16(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(rinv), n, d, x.stride(0), _ptr(out),
                                              out.stride(0) if n else d, _stream(x.device)), "rows_scale_f16")
     return out
@@ -347,7 +381,7 @@ def rows_quant_i8(x, rinv=None, out=None):
     n, d = x.shape
     if out is None:
         out = torch.empty(n, 2 * d, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_rows_quant_i8(_ptr(x), _DTYPE_CODE[x.dtype], _ptr(rinv), n, d, x.stride(0), _ptr(out),
                                             out.stride(0) if n else 2 * d, _stream(x.device)), "rows_quant_i8")
     return out
@@ -357,7 +391,7 @@ def ipc_export(t: torch.Tensor):
     """(64-byte CUDA IPC handle of the allocation ``t`` lies in, byte offset of ``t`` inside it)."""
     handle = C.create_string_buffer(64)
     off = C.c_int64(0)
-    with torch.cuda.device(t.device):
+    with _on_device(t.device):
         check(_cabi.lib().pb2_ipc_export(_ptr(t), handle, C.byref(off)), "ipc_export")
     return handle.raw, int(off.value)
 
@@ -365,20 +399,20 @@ def ipc_export(t: torch.Tensor):
 def ipc_open(handle: bytes, offset: int, device):
     """Map a peer rank's allocation on ``device``; returns (base, pointer) as ints (base is for ipc_close)."""
     base, ptr = C.c_void_p(0), C.c_void_p(0)
-    with torch.cuda.device(device):
+    with _on_device(device):
         check(_cabi.lib().pb2_ipc_open(C.c_char_p(handle), int(offset), C.byref(base), C.byref(ptr)), "ipc_open")
     return int(base.value), int(ptr.value)
 
 
 def ipc_close(base: int, device):
-    with torch.cuda.device(device):
+    with _on_device(device):
         check(_cabi.lib().pb2_ipc_close(C.c_void_p(base)), "ipc_close")
 
 
 def peer_reduce(ptrs, out: torch.Tensor):
     """out = sum over the device pointers ``ptrs`` (ints; local or peer memory, fp32, out.numel() elements each)."""
     arr = (C.c_void_p * len(ptrs))(*ptrs)
-    with torch.cuda.device(out.device), _timed("peer_reduce", float(len(ptrs) + 1) * out.numel() * 4, out.device):
+    with _on_device(out.device), _timed("peer_reduce", float(len(ptrs) + 1) * out.numel() * 4, out.device):
         check(_cabi.lib().pb2_peer_reduce(arr, len(ptrs), out.numel(), _ptr(out), _stream(out.device)), "peer_reduce")
     return out
 
@@ -386,7 +420,7 @@ def peer_reduce(ptrs, out: torch.Tensor):
 def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_dev=None):
     rows, d = x.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         check(_cabi.lib().pb2_hinge_finish(_ptr(p), p.stride(0), _ptr(x), _ptr(y), _mm_code(x, y), _ptr(rinv_x), _ptr(rinv_y),
                                            _ptr(row_cnt), _ptr(col_cnt), rows, d, x.stride(0), y.stride(0), float(coef_host),
                                            _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(x.device)), "hinge_finish")
@@ -396,7 +430,7 @@ def hinge_finish(p, x, y, rinv_x, rinv_y, row_cnt, col_cnt, coef_host=1.0, coef_
 def milnce_finish(p, y, coef_host=1.0, coef_dev=None):
     rows, d = y.shape
     grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
-    with torch.cuda.device(y.device):
+    with _on_device(y.device):
         check(_cabi.lib().pb2_milnce_finish(_ptr(p), p.stride(0), _ptr(y), _DTYPE_CODE[y.dtype], rows, d, y.stride(0), float(coef_host),
                                             _ptr(coef_dev), _ptr(grad), grad.stride(0), _stream(y.device)), "milnce_finish")
     return grad
@@ -406,7 +440,7 @@ def milnce_finish_k(p, y, w, rows, group, y_div, coef_host=1.0):
     """MIL-NCE finish with K candidates per clip: see pb2_milnce_finish_k."""
     d = y.shape[1]
     grad = torch.empty(rows, d, dtype=torch.float32, device=y.device)
-    with torch.cuda.device(y.device):
+    with _on_device(y.device):
         check(_cabi.lib().pb2_milnce_finish_k(_ptr(p), p.stride(0), _ptr(y), _DTYPE_CODE[y.dtype], _ptr(w), rows, int(group), int(y_div), d,
                                               y.stride(0), float(coef_host), _ptr(None), _ptr(grad), grad.stride(0),
                                               _stream(y.device)), "milnce_finish_k")
@@ -422,7 +456,7 @@ def project_normalize(x_bf16, w_bf16, bias=None, eps=1e-12):
     out = torch.empty(rows, n_out, dtype=torch.bfloat16, device=dev)
     rinv = torch.empty(rows, dtype=torch.float32, device=dev)
     norm = torch.empty(rows, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _timed("project_normalize", 2.0 * rows * n_in * n_out, dev):
+    with _on_device(dev), _timed("project_normalize", 2.0 * rows * n_in * n_out, dev):
         check(_cabi.lib().pb2_project_normalize(_ptr(x_bf16), _ptr(w_bf16), _ptr(bias), rows, n_in, n_out, x_bf16.stride(0),
                                                 w_bf16.stride(0), float(eps), _ptr(out), out.stride(0) if rows else n_out,
                                                 _ptr(rinv), _ptr(norm), _stream(dev)), "project_normalize")
@@ -469,10 +503,10 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32, rinv_v=None, rinv_a=Non
     capturing = torch.cuda.is_current_stream_capturing()
     # reuse is stream-ordered, so the cache is per stream: two steps of one shape on two streams never share
     # scratch (a workspace handed to a graph capture belongs to that graph and is not cached)
-    key = (dev, torch.cuda.current_stream(dev).cuda_stream, n, d, code)
+    key = (dev, torch._C._cuda_getCurrentRawStream(_dev_index(dev)), n, d, code)
     ws = None if capturing else _STEP_WORKSPACE.get(key)
     if ws is None:
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ws = torch.empty(int(lib.pb2_hinge_step_workspace(n, d, code)), dtype=torch.uint8, device=dev)
         if not capturing:
             if len(_STEP_WORKSPACE) > 8:
@@ -480,7 +514,7 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32, rinv_v=None, rinv_a=Non
             _STEP_WORKSPACE[key] = ws
     grads = torch.empty(2, n, d, dtype=grad_dtype, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _timed("hinge_step (4 kernels)", 6.0 * n * n * d, dev):
+    with _on_device(dev), _timed("hinge_step (4 kernels)", 6.0 * n * n * d, dev):
         check(lib.pb2_hinge_step(_ptr(vb), _ptr(ab), code, n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws), ws.numel(),
                                  _ptr(loss), _ptr(grads[0]), _ptr(grads[1]), _DTYPE_CODE[grad_dtype], _ptr(rinv_v), _ptr(rinv_a),
                                  _stream(dev)), "hinge_step")
@@ -492,7 +526,7 @@ def scale_pair(x0, x1, coef, out_dtype=torch.float32):
     launch, fresh contiguous results (the scale is applied in fp32, the rounding comes last)."""
     assert x0.dtype == x1.dtype == torch.float32 and x0.shape == x1.shape and x0.is_contiguous() and x1.is_contiguous()
     y0, y1 = torch.empty_like(x0, dtype=out_dtype), torch.empty_like(x1, dtype=out_dtype)
-    with torch.cuda.device(x0.device):
+    with _on_device(x0.device):
         check(_cabi.lib().pb2_scale_pair(_ptr(x0), _ptr(x1), x0.numel(), _DTYPE_CODE[out_dtype], _ptr(coef), _ptr(y0), _ptr(y1),
                                          _stream(x0.device)), "scale_pair")
     return y0, y1
@@ -500,7 +534,7 @@ def scale_pair(x0, x1, coef, out_dtype=torch.float32):
 
 def sum_partials(part, alpha=1.0):
     out = torch.empty((), dtype=torch.float32, device=part.device)
-    with torch.cuda.device(part.device):
+    with _on_device(part.device):
         check(_cabi.lib().pb2_sum_partials(_ptr(part), part.numel(), float(alpha), _ptr(out), _stream(part.device)),
               "sum_partials")
     return out
@@ -508,7 +542,7 @@ def sum_partials(part, alpha=1.0):
 
 def hinge_loss_terms(out, partials=None, diag=None, cnt=None, margin=0.0, alpha=1.0, accumulate=True):
     """out (=|+=) alpha * (sum partials + sum (margin - diag) * cnt): completes the hinge loss."""
-    with torch.cuda.device(out.device):
+    with _on_device(out.device):
         check(_cabi.lib().pb2_hinge_loss_terms(_ptr(partials), partials.numel() if partials is not None else 0, _ptr(diag),
                                                _ptr(cnt), cnt.numel() if cnt is not None else 0, float(margin), float(alpha),
                                                _ptr(out), int(bool(accumulate)), _stream(out.device)), "hinge_loss_terms")
@@ -519,7 +553,7 @@ def milnce_loss(lse_row, lse_col, diag):
     n = lse_row.shape[0]
     den = torch.empty(n, dtype=torch.float32, device=lse_row.device)
     out = torch.empty((), dtype=torch.float32, device=lse_row.device)
-    with torch.cuda.device(lse_row.device):
+    with _on_device(lse_row.device):
         check(_cabi.lib().pb2_milnce_loss(_ptr(lse_row), _ptr(lse_col), _ptr(diag), n, _ptr(den), _ptr(out),
                                           _stream(lse_row.device)), "milnce_loss")
     return out, den
@@ -531,7 +565,7 @@ def contrastive_matrix(m, margin, want_grad, coef_dev=None):
     n_part = sim_grid(m.device) * 4
     work = torch.empty(n_part + 2 * n, dtype=torch.float32, device=m.device)  # partials | int32 counts
     grad = torch.empty(n, n, dtype=torch.float32, device=m.device) if want_grad else None
-    with torch.cuda.device(m.device):
+    with _on_device(m.device):
         check(_cabi.lib().pb2_contrastive_matrix(_ptr(m), n, m.stride(0), float(margin), _ptr(work), n_part, _ptr(grad),
                                                  n if want_grad else 0, 1.0 / float(n) ** 2, _ptr(coef_dev),
                                                  _stream(m.device)), "contrastive_matrix")
@@ -550,7 +584,7 @@ def triplet_score(anchor, positive, negative, ia=None, ip=None, in_=None, discre
     for m in (positive, negative):
         if m.shape[0] > 1 and m.stride(0) != ld:
             raise ValueError("triplet_score: operands must share a leading dimension")
-    with torch.cuda.device(anchor.device), _timed("triplet_score", float(t) * (3 * d * anchor.element_size() + 4), anchor.device):
+    with _on_device(anchor.device), _timed("triplet_score", float(t) * (3 * d * anchor.element_size() + 4), anchor.device):
         check(_cabi.lib().pb2_triplet_score(_ptr(anchor), _ptr(positive), _ptr(negative), _ptr(ia), _ptr(ip), _ptr(in_), t, d,
                                             ld, code, int(bool(discrete)), _ptr(out), _stream(anchor.device)),
               "triplet_score")

@@ -20,7 +20,9 @@ public API with pinned-host inputs copied in and the result read back every step
 kernel with the largest summed device time, timed live with CUDA events around each of its launches.
 ``--impl reference`` times the CPU port of the reference (oracle/pig_oracle.py, torch-CPU, all host
 threads) on a bounded sample of the same workload; /root/reference is pure Python and does not exist on
-the GPU box, so the oracle port is the reference arm.
+the GPU box, so the oracle port is the reference arm.  The gallery is drawn from ONE seed whatever the world size,
+and ``check`` (loss, recall, an order-independent hash of all ranks, gradient checksums, 64 rows verified against
+oracle/blockwise.py outside the timed region) is therefore the same at every ``--gpus N``.
 """
 from __future__ import annotations
 
@@ -429,6 +431,9 @@ def bench_gallery(args, rank, world, device, sync, all_max):
         "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
         "launches": m["launches"] * world, "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4 + 4 * (TOP_N + 1),
         "flops_per_unit": 6.0 * DIM, "scaling": "strong",
+        "dtype_note": "scores: bf16 embeddings, fp32 accumulate in TMEM (tcgen05 kind::f16), fp32 row/column normalisation in the "
+                      "epilogue; gradient products: the {0,1,2} gradient matrix as u8 x the normalised embeddings as two 8-bit "
+                      "planes (16 bits), exact s32 accumulate (tcgen05 kind::i8), joined and normalised in fp32",
         "check": check,
         "config": {"workload": f"gallery (BASELINE config 5): {n} x {n} audio-video gallery, hinge loss fwd+bwd + recall@1..10 from one "
                                "similarity pass, rows sharded over ranks", "gallery": n, "dim": DIM, "margin": MARGIN, "top_n": TOP_N,
@@ -728,7 +733,8 @@ def line_from(res, args, world, workload):
     line = {
         "metric": METRIC[workload], "value": value, "unit": res["unit"], "n_gpus": world, "steps": res.get("steps_used", args.steps),
         "warmup": args.warmup, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": res["config"], "roofline": res["roofline"], "kernels": res["kernels"],
+        "dtype": "bf16", "dtype_note": res.get("dtype_note", "bf16 operands, fp32 accumulate (tcgen05 kind::f16)"),
+        "data": "synthetic", "config": res["config"], "roofline": res["roofline"], "kernels": res["kernels"],
         "clocks": res["clocks"],
         "e2e": {"value": res["units"] / (res["ms_e2e"] * 1e-3), "unit": res["unit"], "h2d_bytes_per_step": res["h2d"],
                 "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["ms_e2e"]},

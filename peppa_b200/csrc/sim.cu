@@ -1320,6 +1320,10 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
         return PB2_SIM(128, 2, 1);
     } else if constexpr (Policy::kByteG) {
+#ifdef PB2_MEASURE  // the cluster variants with the one-byte gradient matrix (tools/ab_gallery_pair.py)
+        if (mcast) return PB2_SIM(256, 2, 3);
+        if (pair) return PB2_SIM(256, 2, 2);
+#endif
         return PB2_SIM(256, 2, 1);  // a warp's 128 columns are one slab of bytes: 256-wide tiles only
     } else if constexpr (Policy::kStoresG) {
         if (bn == 192) return PB2_SIM(192, 3, 1);

@@ -174,11 +174,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_wait(acc_full, (uint32_t)(it & 1));
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+            // Both passes keep the TMEM load of chunk c + 1 in flight while chunk c is processed (two register
+            // buffers, like sim.cu): with one accumulator stage the epilogue is NOT overlapped with the next tile's
+            // MMAs, so every exposed tcgen05.ld round trip (16 per tile and warp before) was dead time on the SM.
             float2 ssa = make_float2(0.f, 0.f), ssb = make_float2(0.f, 0.f);
-            for (int ch = ch0; ch < ch1; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + ch * 32, v);
-                tmem_ld_wait();
+            auto pass1 = [&](const uint32_t (&v)[32], int ch) {
                 const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -188,17 +188,28 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ssa = __ffma2_rn(y01, y01, ssa);
                     ssb = __ffma2_rn(y23, y23, ssb);
                 }
+            };
+            uint32_t va[32], vb[32];
+            if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);
+#pragma unroll 1
+            for (int ch = ch0; ch < ch1; ch += 2) {  // each half holds an even number of chunks
+                tmem_ld_wait();
+                __syncwarp();
+                tmem_ld32(t_lane + (ch + 1) * 32, vb);
+                pass1(va, ch);
+                tmem_ld_wait();
+                __syncwarp();
+                if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
+                pass1(vb, ch + 1);
             }
             red_s[half * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+            if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);  // pass 2's first chunk travels across the barrier
             named_bar_sync(1, kEpiWarps * 32);
             const float nrm = sqrtf(red_s[r] + red_s[BM + r]);
             const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
             const float2 sc2 = make_float2(scale, scale);
             float2 qa = make_float2(0.f, 0.f);
-            for (int ch = ch0; ch < ch1; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + ch * 32, v);
-                tmem_ld_wait();
+            auto pass2 = [&](const uint32_t (&v)[32], int ch) {
                 const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
                 uint32_t packed[16];
 #pragma unroll
@@ -236,6 +247,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                     }
                     ++n_slab;
                 }
+            };
+#pragma unroll 1
+            for (int ch = ch0; ch < ch1; ch += 2) {
+                tmem_ld_wait();
+                __syncwarp();
+                tmem_ld32(t_lane + (ch + 1) * 32, vb);
+                pass2(va, ch);
+                tmem_ld_wait();
+                __syncwarp();
+                if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
+                pass2(vb, ch + 1);
             }
             tc_fence_before();
             __syncwarp();

@@ -117,6 +117,7 @@ class GalleryStep:
         self.col_cnt = torch.empty(n, dtype=i32, device=dev)
         self.ranks = torch.empty(nl, dtype=i32, device=dev)
         self.peers = None
+        self.timeline = None        # set to [] to collect (label, CUDA event) marks of the next run (tools/timeline_multi_gpu.py)
         if dv_reduce not in ("auto", "p2p", "nccl"):
             raise ValueError("dv_reduce must be 'auto', 'p2p' or 'nccl'")
         if with_grad:
@@ -169,6 +170,13 @@ class GalleryStep:
         dst = dist.get_global_rank(self.group, owner) if self.group is not None else owner
         return dist.reduce(full[c0:c1], dst=dst, group=self.group, async_op=True)
 
+    def _mark(self, label):
+        """Timeline mark on the compute stream (only when ``self.timeline`` is a list: measurement runs)."""
+        if self.timeline is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.device))
+            self.timeline.append((label, e))
+
     def _column_blocks(self):
         """[(c0, c1, local)] over all N columns, never straddling two owners: this rank's own blocks first (they need no
         gathered data), then the other owners' in rank order."""
@@ -219,11 +227,13 @@ class GalleryStep:
         rv = rinv_v if rinv_v is not None else known(v_loc, v_loc)
         ra = ra if ra is not None else ops.row_norms(a_loc)[0]
         rv = rv if rv is not None else ops.row_norms(v_loc)[0]
+        self._mark("step start")
         diag, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv)        # S_ii and its rank threshold
         gathers = []
         if self.world > 1:      # in flight while the local column blocks compute
             gathers = [self._all_gather(self.v_full, v_loc, True), self._all_gather(self.rv_full, rv, True),
                        self._all_gather(self.diag_full, diag, True)]
+            self._mark("all-gathers issued (async); local column blocks start")
         self.row_cnt.zero_()
         self.col_cnt.zero_()
         self.ranks.zero_()
@@ -239,9 +249,12 @@ class GalleryStep:
                 vc, rvc, dc = v_loc[c0 - r0g:c1 - r0g], rv[c0 - r0g:c1 - r0g], diag[c0 - r0g:c1 - r0g]
                 vhc = vh_loc[c0 - r0g:c1 - r0g] if self.with_grad else None
             else:
-                for w in gathers:
-                    w.wait()
-                gathers = []
+                if gathers:
+                    self._mark("local column blocks done; waiting for the all-gathers")
+                    for w in gathers:
+                        w.wait()
+                    gathers = []
+                    self._mark("all-gathers complete on the compute stream; remote column blocks start")
                 if self.with_grad and vh_full is None:
                     vh_full = quant(self.v_full, self.rv_full)
                 vc, rvc, dc = self.v_full[c0:c1], self.rv_full[c0:c1], self.diag_full[c0:c1]
@@ -266,6 +279,7 @@ class GalleryStep:
         ops.hinge_loss_terms(loss, diag=diag, cnt=self.row_cnt, margin=self.margin)      # local rows' term
         hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
         hits = hits.sum(dim=1).to(torch.float32)
+        self._mark("last gradient GEMM enqueued; all-reduce of counts / loss / hits")
         if self.world > 1:
             # also the barrier of the peer-memory reduction: a rank enters it after its last gradient GEMM
             dist.all_reduce(self.col_cnt, group=self.group)
@@ -282,9 +296,12 @@ class GalleryStep:
         out = {"loss": loss * inv_n2, "recall": hits / float(n), "ranks": self.ranks, "dA": None, "dV": None}
         if self.with_grad:
             cc = self.col_cnt[r0g:r0g + nl]
+            self._mark("all-reduces complete; dV pull over peer memory starts")
             p_v_own = self._own_dv_rows()
+            self._mark("dV rows summed; Jacobians")
             out["dA"] = ops.hinge_finish(self.p_a, a_loc, v_loc, ra, rv, self.row_cnt, cc, inv_n2)
             out["dV"] = ops.hinge_finish(p_v_own, v_loc, a_loc, rv, ra, self.row_cnt, cc, inv_n2)
+        self._mark("step end")
         return out
 
     def _run_milnce(self, a_loc, v_loc):

@@ -293,6 +293,48 @@ def test_gallery_step_single_gpu(pb, n, block):
     assert torch.equal(again["dA"], out["dA"]) and again["loss"].item() == out["loss"].item()
 
 
+@pytest.mark.parametrize("n", [3, 70, 130, 257])
+def test_gallery_step_tiny_sizes(pb, n):
+    """The one-byte gradient matrix / kind::i8 path on galleries smaller than one tile (TMA clips every box)."""
+    from oracle import blockwise as B
+    from peppa_b200.gallery import GalleryStep
+    V, A = emb(n, 4.0)
+    out = GalleryStep(n, 512).run(A.cuda().bfloat16(), V.cuda().bfloat16())
+    loss, dA, dV = O.hinge_loss_and_grads(A, V, 0.2)
+    assert rel_err(out["loss"].cpu(), loss) < TOL
+    k = B.hinge_kink_counts(A, V, 0.2)
+    if float(dA.abs().max()) > 0:
+        assert rel_err(out["dA"].cpu(), dA) < 2 * TOL and rel_err(out["dV"].cpu(), dV) < 2 * TOL   # few terms: 16-bit planes average less
+        assert B.hinge_rows_within(out["dA"].cpu(), dA, A, k, 3 * TOL)[0]
+    ranks, near = O.ranks_identity(V, A)
+    assert bool(((out["ranks"].cpu().long() == ranks) | near).all())
+
+
+def test_triplet_loss_public_api_beyond_one_block(pb):
+    """TripletLoss through the public API at N = 40000 > 32768: the block-walking path with the one-byte gradient
+    matrix (blocks of 32768 and 7232), against the blockwise oracle (whole loss; 128 sampled gradient rows in fp64)."""
+    from oracle import blockwise as B
+    n = 40000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    V = torch.nn.functional.normalize(torch.randn(n, 512, generator=g, device="cuda"), dim=1)
+    A = torch.nn.functional.normalize(4.0 * V + torch.randn(n, 512, generator=g, device="cuda"), dim=1).bfloat16()
+    V = V.bfloat16()
+    v, a = V.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    loss = pb.loss.TripletLoss(0.2)(v, a)
+    loss.backward()
+    ref = B.hinge_loss_blockwise(V, A, 0.2)
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(2))[:128].cuda()
+    gV = B.hinge_grad_rows(V, A, rows, 0.2)
+    gA = B.hinge_grad_rows(A, V, rows, 0.2)
+    # bf16 gradient tensors (the inputs' dtype): 2^-9 relative rounding per element on top of the 1e-3 bar
+    assert v.grad.dtype == torch.bfloat16 and rel_err(v.grad[rows].float(), gV) < 2.0 ** -8 and rel_err(a.grad[rows].float(), gA) < 2.0 ** -8
+    vf, af = V.float().requires_grad_(True), A.float().requires_grad_(True)          # fp32 tensors in: fp32 gradients out
+    pb.loss.TripletLoss(0.2)(vf, af).backward()
+    assert rel_err(vf.grad[rows], gV) < TOL and rel_err(af.grad[rows], gA) < TOL
+    assert row_rel_err(vf.grad[rows], gV) < TOL and row_rel_err(af.grad[rows], gA) < TOL
+
+
 def test_rank_ties_are_strict(pb):
     """Duplicate gallery rows give candidates whose score equals the positive's exactly: they must not
     count (dist < dist_pos is strict, pig/metrics.py:8-12), in both the rank kernel and the fused
@@ -629,7 +671,7 @@ def test_grad_gemm_stream_k(pb, tr, r, c, d):
 
 @pytest.mark.parametrize("tr", [False, True])
 @pytest.mark.parametrize("r,c,d", [(20480, 2048, 512), (20000, 1000, 512), (9000, 4100, 256), (300, 30000, 512),
-                                   (32768, 32768, 512), (1200, 700, 768)])
+                                   (32768, 32768, 512), (1200, 700, 768), (130, 70, 256), (5, 3, 512)])
 def test_grad_gemm_i8_planes(pb, tr, r, c, d):
     """The kind::i8 gradient GEMM (one-byte G in {0, 1, 2} x two 8-bit planes of the normalised embeddings): EXACT
     against the integer product of the planes (s32 accumulation, exact fp32 join), within the quantisation step of

@@ -1,7 +1,7 @@
 """GPU parity on inputs that are NOT bf16-representable: the reference's callers hand over fp32 tensors and, under
 Lightning's ``precision: 16`` (hparams_base.yaml:45, pig/evaluation.py:70), fp16 ones.  Nothing may be rounded to
 bf16 on the way in: fp16 rows feed ``tcgen05.mma.kind::f16`` natively, fp32 rows as their split-bf16 pair
-(``pb2_split_bf16``, contraction length 3 D), and every row-wise kernel reads the true values.
+(``pb2_split_f16``: the split-fp16 pair of the normalised rows, contraction length 3 D), and every row-wise kernel reads the true values.
 
 Bars (BASELINE.json north_star): ranks identical to the oracle (fp32 math on the exact input values) except rows with
 another candidate within 1e-6 of the positive; loss and gradients within 1e-3 -- norm-wise AND per row.

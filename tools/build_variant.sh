@@ -10,10 +10,10 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 python -m peppa_b200.build > /dev/null
 mkdir -p "$ROOT/tools/ab"
 cd "$ROOT/peppa_b200/csrc"
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I ../../include -I . $2 \
-    -c sim.cu -o "build/sim_$1.variant.o"
-cd build
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I ../../include -I . -DPB2_MEASURE $2 \
+    -c sim.cu -o "build_measure/sim_$1.variant.o"
+cd build_measure      # variants are measurement builds: they link the -DPB2_MEASURE objects (pb2_debug_* selectors)
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$ROOT/tools/ab/lib_$1.so" \
-    host_util.o triplet.o rowstats.o "sim_$1.variant.o" gradgemm.o step.o proj.o
+    host_util.o triplet.o rowstats.o "sim_$1.variant.o" gradgemm.o step.o proj.o collective.o -ldl
 rm -f "sim_$1.variant.o"
 echo "$ROOT/tools/ab/lib_$1.so"

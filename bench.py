@@ -198,7 +198,7 @@ def roofline_of(kern, bound, step_ms=None):
     pk = peaks()
     if not kern:
         return None, {}
-    name, k = max(kern.items(), key=lambda kv: kv[1]["ms"])
+    name, k = max(((n, v) for n, v in kern.items() if bound == "hbm" or n != "peer_reduce"), key=lambda kv: kv[1]["ms"])
     extra = {}
     if bound == "hbm":
         achieved, peak, unit, src = k["work"] / (k["ms"] * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s", pk["source"]
@@ -213,8 +213,10 @@ def roofline_of(kern, bound, step_ms=None):
             "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)",
             "traffic_source": traffic_src,
             "peak_source": src, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"]}
+    # (the peer-memory pull of the sharded step is instrumented in bytes, not flops)
+    in_bytes = lambda n: bound == "hbm" or n == "peer_reduce"  # noqa: E731
     table = {n: {"launches": v["launches"], "ms_total": v["ms"],
-                 ("gbs" if bound == "hbm" else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if bound == "hbm" else 1e12)) if v["ms"] else None}
+                 ("gbs" if in_bytes(n) else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if in_bytes(n) else 1e12)) if v["ms"] else None}
              for n, v in kern.items()}
     return roof, table
 

@@ -116,6 +116,10 @@ class GalleryStep:
         self.row_cnt = torch.empty(nl, dtype=i32, device=dev)
         self.col_cnt = torch.empty(n, dtype=i32, device=dev)
         self.ranks = torch.empty(nl, dtype=i32, device=dev)
+        # loss partials of every (column block, row block) pass of a step: [passes, CTAs], cleared once per step and
+        # folded once at its end (instead of a memset + a fold launch per pass)
+        n_pass = len(_blocks(nl, block)) * len(_blocks(nl, block)) * world
+        self.loss_parts = torch.empty(n_pass, ops.sim_grid(dev), dtype=f32, device=dev) if (backend is None and loss == "hinge") else None
         self.peers = None
         self.timeline = None        # set to [] to collect (label, CUDA event) marks of the next run (tools/timeline_multi_gpu.py)
         if dv_reduce not in ("auto", "p2p", "nccl"):
@@ -239,6 +243,8 @@ class GalleryStep:
         self.ranks.zero_()
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         rblocks, cblocks = _blocks(nl, self.block), self._column_blocks()
+        if self.loss_parts is not None:
+            self.loss_parts.zero_()
         if self.with_grad:
             quant = ops.rows_quant_i8 if self.byte_gmat else ops.rows_scale_f16
             ah = quant(a_loc, ra)               # embedding operands of the gradient GEMMs (two 8-bit planes / fp16)
@@ -260,11 +266,13 @@ class GalleryStep:
                 vc, rvc, dc = self.v_full[c0:c1], self.rv_full[c0:c1], self.diag_full[c0:c1]
                 vhc = vh_full[c0:c1] if self.with_grad else None
             for ri, (r0, r1) in enumerate(rblocks):
+                extra = {} if self.loss_parts is None else {"part": self.loss_parts[ci * len(rblocks) + ri]}
                 part = ops.sim_hinge(a_loc[r0:r1], vc, ra[r0:r1], rvc, diag[r0:r1], dc, self.margin, self.row_cnt[r0:r1],
                                      self.col_cnt[c0:c1], self.gmat if self.with_grad else None,
                                      self.ld_g if self.with_grad else 0, row_offset=r0g + r0, col_offset=c0,
-                                     pos_thr=pos_thr[r0:r1], rank=self.ranks[r0:r1])
-                ops.hinge_loss_terms(loss, partials=part)
+                                     pos_thr=pos_thr[r0:r1], rank=self.ranks[r0:r1], **extra)
+                if self.loss_parts is None:
+                    ops.hinge_loss_terms(loss, partials=part)
                 if self.with_grad:      # first contribution overwrites, later ones accumulate: no zero-fill pass, and
                     # nothing touches a remote owner's rows of p_v before the gathers above have completed (peers may
                     # still be pulling last step's partials until they enter this step's all-gather)
@@ -276,6 +284,8 @@ class GalleryStep:
                 self._start_ready_reductions(c1, red)
         for w in gathers:       # (a rank whose walk never left its own blocks: only possible with world == 1)
             w.wait()
+        if self.loss_parts is not None:       # every pass's CTA partials in one fixed-order fold (fp64 inside)
+            ops.hinge_loss_terms(loss, partials=self.loss_parts.view(-1))
         ops.hinge_loss_terms(loss, diag=diag, cnt=self.row_cnt, margin=self.margin)      # local rows' term
         hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
         hits = hits.sum(dim=1).to(torch.float32)

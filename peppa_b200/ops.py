@@ -245,15 +245,22 @@ def byte_gmat_ok(dim):
 
 
 def sim_hinge(x, y, rinv_x, rinv_y, diag_row, diag_col, margin, row_cnt, col_cnt, gmat=None, ld_g=0,
-              row_offset=0, col_offset=0, pos_thr=None, rank=None):
-    """Returns the per-CTA loss partials (fp32 [grid])."""
+              row_offset=0, col_offset=0, pos_thr=None, rank=None, part=None):
+    """Returns the per-CTA loss partials (fp32 [grid]).  ``part``: a caller buffer of at least sim_grid() floats that
+    is ALREADY ZERO (e.g. one row of a per-step [blocks, grid] buffer cleared once): saves the per-call allocation and
+    memset launch of a block-walking step."""
     r, c = x.shape[0], y.shape[0]
     n_part = sim_grid(x.device)
-    part = torch.empty(n_part, dtype=torch.float32, device=x.device)
+    if part is None:
+        part = torch.empty(n_part, dtype=torch.float32, device=x.device)
+        n_arg = n_part
+    else:
+        assert part.numel() >= n_part and part.dtype == torch.float32 and part.is_contiguous()
+        n_arg = -n_part                                   # negative: "already cleared", no memset
     with _on_device(x.device), _timed("sim_hinge" + ("+rank" if rank is not None else ""), 2.0 * r * c * x.shape[1], x.device):
         check(_cabi.lib().pb2_sim_hinge(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), _ptr(diag_row), _ptr(diag_col), r, c,
                                         int(row_offset), int(col_offset), x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
-                                        float(margin), _ptr(part), n_part, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
+                                        float(margin), _ptr(part), n_arg, _ptr(row_cnt), _ptr(col_cnt), _ptr(gmat),
                                         _DTYPE_CODE[gmat.dtype] if gmat is not None else PB2_F16, int(ld_g), _ptr(pos_thr),
                                         _ptr(rank), _stream(x.device)), "sim_hinge")
     return part

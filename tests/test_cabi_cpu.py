@@ -130,6 +130,21 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert b"PB2_I8_PLANES" in lib.pb2_last_error()
     assert lib.pb2_grad_gemm(one, 3, 8, 8, 128, 0, one, 4, 320, 1024, 1.0, 0, one, 512, null) == 1      # dim % 256
     assert lib.pb2_rows_quant_i8(one, 0, null, 8, 512, 512, one, 512, null) == 1                        # ld_out < 2 dim
+    assert lib.pb2_grad_gemm(one, 3, 40000, 8, 128, 1, one, 4, 512, 1024, 1.0, 0, one, 512, null) == 1  # contraction > 32768
+    assert b"32768" in lib.pb2_last_error()
+    assert lib.pb2_sim_hinge(one, one, one, one, one, one, 8, 8, 0, 0, 512, 0, 512, 512, 0.2, one, 1 << 20, one, one, one, 2,
+                             128, null, null, null) == 1                                                # G is fp16 or u8
+    # multi-GPU entry points: argument checks need neither a device nor a communicator
+    arr = (C.c_void_p * 2)(256, 512)
+    assert lib.pb2_peer_reduce(arr, 0, 64, one, null) == 1 and lib.pb2_peer_reduce(arr, 17, 64, one, null) == 1
+    assert lib.pb2_peer_reduce(arr, 2, 63, one, null) == 1                                              # whole 16-byte vectors
+    assert lib.pb2_peer_reduce(arr, 2, 0, one, null) == 0
+    assert lib.pb2_ipc_export(null, null, null) == 1 and lib.pb2_ipc_open(null, 0, null, null) == 1 and lib.pb2_ipc_close(null) == 0
+    assert lib.pb2_nccl_gallery_allgather(null, one, 8, 1024, one, null) == 1
+    assert lib.pb2_nccl_gallery_allgather(null, one, 0, 1024, one, null) == 0
+    assert lib.pb2_nccl_colstat_merge(null, one, 8, one, one, 11, null) == 1
+    assert lib.pb2_nccl_dv_reduce_scatter(null, one, 8, 512, one, null) == 1
+    assert lib.pb2_nccl_available() in (0, 1)
     assert lib.pb2_hinge_step_workspace(1024, 512, 2) > lib.pb2_hinge_step_workspace(1024, 512, 0) > 0
     assert lib.pb2_sim_lse_col_parts(1000) == 32 and lib.pb2_sim_lse_col_parts(128) == 4
     assert lib.pb2_lse_merge_const(null, 4, 8, 1.0, null, 0, null) == 1 and lib.pb2_lse_merge_const(null, 4, 0, 1.0, null, 0, null) == 0

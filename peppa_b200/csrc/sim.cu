@@ -45,7 +45,10 @@ constexpr int kMaxEpiWarps = 16;
 // Epilogue warps come in groups of 4 (one per TMEM lane quadrant); G groups split the BN columns of a
 // tile between them.  More groups = more warps per scheduler to hide the epilogue's latencies.
 __host__ __device__ constexpr int sim_threads(int groups) { return (4 * groups + kAuxWarps) * 32; }
-constexpr int kGroupM = 8;
+#ifndef PB2_GROUP_M
+#define PB2_GROUP_M 8  // row blocks per band of the tile walk (measurement builds: tools/build_variant.sh X -DPB2_GROUP_M=16)
+#endif
+constexpr int kGroupM = PB2_GROUP_M;
 constexpr int kMaxColVecs = 3;
 constexpr int kColVecStride = 256;          // floats between column vectors in smem (= max BN)
 constexpr int kOutSlabBytes = 32 * 64 * 2;  // one warp's [32 rows x 64 fp16] staging slab (4 KiB)

@@ -16,10 +16,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     import torch
     from peppa_b200 import _cabi
-    _cabi.use_measurement_library()      # the pb2_debug_* selectors live in the measurement build only
     args = sys.argv[1:]
     if args and args[0].endswith(".so"):
-        _cabi.LIB_PATH = os.path.abspath(args.pop(0))
+        _cabi.MEASURE_LIB_PATH = os.path.abspath(args.pop(0))      # a variant built by tools/build_variant.sh
+    _cabi.use_measurement_library()      # the pb2_debug_* selectors live in the measurement build only
     pair = -1
     for a_ in list(args):
         if a_.startswith("pair="):          # pb2_debug_sim_pair: 0 = independent CTAs, 1 = CTA pairs, 2 = multicast clusters (default -1: per policy)
@@ -28,7 +28,7 @@ def main():
     what = args or ["hinge"]
     from peppa_b200 import ops
     from gpu_probe import _t, emb
-    name = os.path.basename(_cabi.LIB_PATH) + (f" pair={pair}" if pair >= 0 else "")
+    name = os.path.basename(_cabi.MEASURE_LIB_PATH) + (f" pair={pair}" if pair >= 0 else "")
     _cabi.lib().pb2_debug_sim_pair(pair)
     n = 32768
     V, A = emb(n)
@@ -41,7 +41,7 @@ def main():
     idx = torch.arange(n, device="cuda")
     flops = 2 * n * n * 512
     if "hinge" in what:
-        g, ld = ops.gmat_alloc(n, n, "cuda")
+        g, ld = ops.gmat_alloc(n, n, "cuda", torch.uint8)        # the product's one-byte gradient matrix
         ops.sim_hinge(A, V, ra, rv, diag, diag, 0.2, rc, cc, g, ld, pos_thr=thr, rank=rk)
         torch.cuda.synchronize()
         chk = (int(rc.sum()), int(cc.sum()), int(rk.sum()), float(g.float().sum()))

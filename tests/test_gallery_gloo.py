@@ -128,3 +128,32 @@ def test_two_rank_milnce_gallery_matches_closed_form(n_local, block, tmp_path):
     gdV = torch.cat([r[3] for r in res]).double()
     assert (gdA - a.grad).abs().max() / a.grad.abs().max() < 2e-3      # fp16 gradient matrix of the emulation
     assert (gdV - v.grad).abs().max() / v.grad.abs().max() < 2e-3
+
+
+def test_column_block_walk_and_reduction_order():
+    """Host logic of the sharded step without any process group: every rank walks ALL columns exactly once, its own
+    blocks first, blocks never straddle two owners; and the NCCL-path reductions are started in ONE canonical order
+    on every rank (owner by owner) however the ranks interleave their own blocks."""
+    sys.path.insert(0, HERE)
+    import emu_ops
+    from peppa_b200.gallery import GalleryStep
+    world, nl, block = 4, 100, 48
+    orders = []
+    for rank in range(world):
+        step = GalleryStep(nl, 128, rank=rank, world=world, device="cpu", block=block, backend=emu_ops, with_grad=False)
+        blocks = step._column_blocks()
+        cols = sorted((c0, c1) for c0, c1, _ in blocks)
+        assert cols[0][0] == 0 and cols[-1][1] == world * nl and all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
+        assert all(c0 // nl == (c1 - 1) // nl for c0, c1, _ in blocks)                      # one owner per block
+        n_own = len([b for b in blocks if b[2]])
+        assert all(b[2] for b in blocks[:n_own]) and not any(b[2] for b in blocks[n_own:])  # own blocks first
+        assert all(rank * nl <= c0 < (rank + 1) * nl for c0, _, loc in blocks if loc)
+        issued = []
+        step._reduce_to_owner = lambda full, c0, c1: issued.append((c0, c1)) or len(issued)
+        step.p_v = None
+        red = step._reduction_state()
+        for c0, c1, _ in blocks:
+            step._start_ready_reductions(c1, red)
+        assert red["next"] == len(red["order"]) and len(red["pending"]) == len(blocks)
+        orders.append(issued)
+    assert all(o == orders[0] for o in orders) and orders[0] == sorted(orders[0])          # same sequence on every rank

@@ -515,8 +515,267 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
-// pb2_debug_proj_variant: 2 = the column-split kernel (n_out % 128 == 0), anything else = the row-split single-stage
-// kernel.  Measured for 2^20 rows 512 -> 512: row-split 0.659 ms, column-split 0.681 ms (0.937 ms with a
+// ---------------------------------------------------------------------------------------------------------
+#ifdef PB2_MEASURE
+// Phased variant (round 2 experiment, measurement build only: pb2_debug_proj_variant(3)): the two column halves of the
+// accumulator are produced ONE AFTER THE OTHER
+// instead of interleaved -- MMA_A = x W[0:256]^T over all of K into TMEM columns [0, 256), then MMA_B = x W[256:512]^T
+// into [256, 512) (the x k-tiles are streamed twice; they hit L2 the second time) -- so that each half has its own
+// full / empty barrier and the epilogue overlaps the tensor pipe although the tile owns all of TMEM:
+//     MMA_A(t) | MMA_B(t)          | MMA_A(t+1)        | MMA_B(t+1) ...
+//              | pass1_A  pass1_B  | pass2_A  pass2_B  |
+// pass 1 (sum of squares) of half A runs under MMA_B, and the next tile's MMA_A starts as soon as pass 2 (scale /
+// round / store) has drained half A, i.e. under pass 2 of half B.  All eight epilogue warps work on the same half
+// (two warps per TMEM lane quadrant, each a contiguous run of 64-column slabs).  A stage of the TMA ring is one x
+// tile + this CTA's half of ONE W tile (32 KiB), five stages.  Correct (same tests as the product kernel) and NOT
+// faster: 0.645 ms against 0.652 ms for 2^20 rows -- streaming x twice costs what the overlap buys (W already
+// crosses L2 -> SM once per tile and pair: 768 KB per 134 MFLOP; with x twice 1 MB), so the product keeps the
+// interleaved kernel above.
+constexpr int kP_StageBytes = kXBytes + kWHalf;
+constexpr int kP_Stages = 5;
+constexpr int kP_Smem = kP_Stages * kP_StageBytes + kOutBytes + kRedBytes + 256;
+static_assert(kP_Smem <= 227 * 1024, "phased encoder tail: shared memory");
+
+__global__ void __launch_bounds__(kThreads, 1)
+    project_normalize_phased_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                                    const __grid_constant__ CUtensorMap tm_out, const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* out_stage = smem + kP_Stages * kP_StageBytes;
+    float* red_s = reinterpret_cast<float*>(out_stage + kOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_s) + kRedBytes);
+    uint64_t* full = bars;                 // [kP_Stages]
+    uint64_t* empty = bars + kP_Stages;    // [kP_Stages]
+    uint64_t* acc_full = empty + kP_Stages;   // [2]: halves A, B
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int64_t n_tiles = (a.rows + 2 * BM - 1) / (2 * BM);
+    const int64_t unit0 = blockIdx.x / 2, n_units = gridDim.x / 2;
+    if (warp == kTmaWarp && lane == 0) {
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_out);
+    }
+    if (warp == kMmaWarp && lane == 0) {
+        for (int s = 0; s < kP_Stages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(acc_full + h, 1);
+            mbar_init(acc_empty + h, 2 * kEpiWarps);  // the leader's collects both CTAs' epilogues
+        }
+        fence_mbar_init();
+    }
+    if (warp == kTmaWarp) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_half[2] = {a.n_out > 256 ? 256 : a.n_out, a.n_out > 256 ? a.n_out - 256 : 0};  // columns of halves A, B
+
+    if (warp == kTmaWarp) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = unit0; t < n_tiles; t += n_units) {
+                const int32_t xrow = (int32_t)((t * 2 + crank) * BM);
+                for (int h = 0; h < 2; ++h) {
+                    const int rows_w = n_half[h] / 2;  // this CTA's W rows of the half
+                    if (rows_w == 0) continue;
+                    const uint32_t tx = 2u * (uint32_t)(kXBytes + rows_w * BK * 2);  // both CTAs' bytes of a stage
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        uint8_t* sx = smem + stage * kP_StageBytes;
+                        uint8_t* sw = sx + kXBytes;
+                        if (crank == 0) mbar_arrive_expect_tx(full + stage, tx);
+                        const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+                        tma_load_2d_pair(sx, &tm_x, lbar, kb * BK, xrow, h == 0 ? kEvictNormal : kEvictFirst);
+                        for (int r0 = 0; r0 < rows_w; r0 += kWBox)
+                            tma_load_2d_pair(sw + r0 * (BK * 2), &tm_w, lbar, kb * BK, h * 256 + (int32_t)crank * rows_w + r0, kEvictLast);
+                        if (++stage == kP_Stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && crank == 0) {
+            uint32_t idesc[2];
+            idesc[0] = make_idesc(2 * BM, (uint32_t)n_half[0], kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+            idesc[1] = n_half[1] > 0 ? make_idesc(2 * BM, (uint32_t)n_half[1], kFmtBF16, kFmtBF16, kMajorK, kMajorK) : 0u;
+            const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+            constexpr uint32_t kStageLo = kP_StageBytes >> 4, kWLo = kXBytes >> 4, kKLo = (UK * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0, lo = lo0;
+            int64_t it = 0;
+            for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+                for (int h = 0; h < 2; ++h) {
+                    if (n_half[h] == 0) continue;
+                    mbar_wait(acc_empty + h, (uint32_t)(it & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_f16_pair_lohi(tmem_base + h * 256, lo + k * kKLo, lo + kWLo + k * kKLo, desc_hi, desc_hi, idesc[h],
+                                               (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(empty + stage);
+                        lo += kStageLo;
+                        if (++stage == kP_Stages) {
+                            stage = 0;
+                            phase ^= 1;
+                            lo = lo0;
+                        }
+                    }
+                    umma_commit_pair(acc_full + h);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread == row; in each half the quadrant's two warps take a contiguous run of 64-column slabs
+        const int quad = warp & 3, sub = warp >> 2;
+        uint8_t* slab = out_stage + warp * 2 * kSlabBytes;
+        uint32_t n_slab = 0;
+        int ch0[2], ch1[2];  // this warp's 32-column chunks of halves A and B (even counts: slabs are two chunks)
+        for (int h = 0; h < 2; ++h) {
+            const int pairs = n_half[h] / 64, first = (pairs + 1) / 2;
+            ch0[h] = sub == 0 ? 0 : 2 * first;
+            ch1[h] = sub == 0 ? 2 * first : 2 * pairs;
+        }
+        const int r = quad * 32 + lane;
+        const bool has_bias = a.bias != nullptr;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        int64_t it = 0;
+        for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+            const int64_t row0 = (t * 2 + crank) * BM, row = row0 + r;
+            const uint32_t par = (uint32_t)(it & 1);
+            float2 ssa = make_float2(0.f, 0.f), ssb = make_float2(0.f, 0.f);
+            uint32_t va[32], vb[32];
+            // ---- pass 1: sum of squares, half A under MMA_B
+            for (int h = 0; h < 2; ++h) {
+                if (n_half[h] == 0) continue;
+                mbar_wait(acc_full + h, par);
+                tc_fence_after();
+                const int c0 = ch0[h], c1 = ch1[h];
+                auto pass1 = [&](const uint32_t (&v)[32], int ch) {
+                    const float4* b4 = reinterpret_cast<const float4*>(a.bias + h * 256 + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float2 y01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+                        const float2 y23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
+                        ssa = __ffma2_rn(y01, y01, ssa);
+                        ssb = __ffma2_rn(y23, y23, ssb);
+                    }
+                };
+                if (c0 < c1) tmem_ld32(t_lane + h * 256 + c0 * 32, va);
+#pragma unroll 1
+                for (int ch = c0; ch < c1; ch += 2) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(t_lane + h * 256 + (ch + 1) * 32, vb);
+                    pass1(va, ch);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (ch + 2 < c1) tmem_ld32(t_lane + h * 256 + (ch + 2) * 32, va);
+                    pass1(vb, ch + 1);
+                }
+            }
+            red_s[sub * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+            named_bar_sync(1, kEpiWarps * 32);
+            const float nrm = sqrtf(red_s[r] + red_s[BM + r]);
+            const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
+            const float2 sc2 = make_float2(scale, scale);
+            float2 qa = make_float2(0.f, 0.f);
+            // ---- pass 2: scale / round / stage / store; half A is released to the next tile's MMA_A before half B is read
+            for (int h = 0; h < 2; ++h) {
+                if (n_half[h] == 0) continue;
+                const int c0 = ch0[h], c1 = ch1[h];
+                auto pass2 = [&](const uint32_t (&v)[32], int ch) {
+                    const float4* b4 = reinterpret_cast<const float4*>(a.bias + h * 256 + ch * 32);
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float2 e01 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y)), sc2);
+                        const float2 e23 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w)), sc2);
+                        const uint32_t p0 = pack_bf16(e01.x, e01.y), p1 = pack_bf16(e23.x, e23.y);
+                        packed[2 * j] = p0;
+                        packed[2 * j + 1] = p1;
+                        const float2 r01 = make_float2(__uint_as_float(p0 << 16), __uint_as_float(p0 & 0xffff0000u));
+                        const float2 r23 = make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+                        qa = __ffma2_rn(r01, r01, qa);
+                        qa = __ffma2_rn(r23, r23, qa);
+                    }
+                    const int cp = (ch - c0) & 1;
+                    uint8_t* sl = slab + (n_slab & 1) * kSlabBytes;
+                    if (cp == 0) {  // the slab about to be rewritten must have been read by its TMA store
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+                    uint8_t* srow = sl + lane * 128;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c16 = (cp * 4 + k) ^ (lane & 7);  // 128-byte swizzle
+                        *reinterpret_cast<uint4*>(srow + c16 * 16) =
+                            make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                    }
+                    if (cp) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tm_out, sl, h * 256 + (ch - 1) * 32, (int32_t)(row0 + quad * 32));
+                            tma_store_commit();
+                        }
+                        ++n_slab;
+                    }
+                };
+                if (c0 < c1) tmem_ld32(t_lane + h * 256 + c0 * 32, va);
+#pragma unroll 1
+                for (int ch = c0; ch < c1; ch += 2) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(t_lane + h * 256 + (ch + 1) * 32, vb);
+                    pass2(va, ch);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (ch + 2 < c1) tmem_ld32(t_lane + h * 256 + (ch + 2) * 32, va);
+                    pass2(vb, ch + 1);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + h), 0));  // this half may be overwritten
+            }
+            red_s[2 * BM + sub * BM + r] = qa.x + qa.y;
+            named_bar_sync(1, kEpiWarps * 32);
+            if (sub == 0 && row < a.rows) {
+                if (a.rinv) a.rinv[row] = 1.0f / sqrtf(red_s[2 * BM + r] + red_s[3 * BM + r]);  // no epsilon: the scoring kernels' convention
+                if (a.norm) a.norm[row] = nrm;
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+        __syncwarp();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
+    if (warp == kTmaWarp) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+#endif  // PB2_MEASURE
+
+// pb2_debug_proj_variant (measurement build): 0 = the interleaved single-stage kernel (the product), 2 = the column-split
+// kernel (n_out % 128 == 0), 3 = the phased kernel.  Measured for 2^20 rows 512 -> 512: row-split 0.659 ms, column-split 0.681 ms (0.937 ms with a
 // release-arrive + cluster fence instead of st.async: MEMBAR.GPU + CCTL.IVALL twice per tile).  The overlap it buys
 // is spent on the two cross-CTA exchanges per tile, so the simpler kernel stays the default.
 PB2_KNOB g_variant = 0;
@@ -579,6 +838,18 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
     }
     const int64_t n_tiles = (rows + 2 * proj::BM - 1) / (2 * proj::BM);
     const int grid = 2 * (int)std::min<int64_t>(n_tiles, sm_count() / 2);
+#ifdef PB2_MEASURE
+    if (proj::g_variant == 3) {  // phased halves: the epilogue overlaps the tensor pipe (experiment)
+        static PerDeviceOnce configured3;
+        rc = ensure_dynamic_smem(configured3, proj::project_normalize_phased_kernel, proj::kP_Smem, "project_normalize");
+        if (rc) return rc;
+        rc = check_cuda(launch_ex(proj::project_normalize_phased_kernel, (unsigned)grid, (unsigned)proj::kThreads,
+                                  (size_t)proj::kP_Smem, (cudaStream_t)stream, 2, tx, tw, to, a),
+                        "project_normalize launch");
+        if (rc) return rc;
+        return check_launch("project_normalize");
+    }
+#endif
     rc = check_cuda(launch_ex(proj::project_normalize_kernel, (unsigned)grid, (unsigned)proj::kThreads, (size_t)proj::kSmem,
                               (cudaStream_t)stream, 2, tx, tw, to, a),
                     "project_normalize launch");

@@ -978,3 +978,27 @@ def test_graft_entry_smoke(pb):
     """The driver's smoke(): one small invocation of the hot path on cuda:0 checked against the oracle."""
     import __graft_entry__ as entry
     entry.smoke()
+
+
+def test_bench_line_contract(pb):
+    """bench.py prints exactly one JSON line with the keys the driver reads (a single-GPU workload, seconds)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "retrieval16k", "--steps", "5", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "clocks", "e2e", "gpu_launches"):
+        assert key in rec, key
+    assert rec["value"] > 0 and rec["gpu_launches"] > 0 and rec["vs_baseline"] is None and "workload" in rec["config"]
+    roof = rec["roofline"]
+    assert roof["bound"] == "tensor" and 0.3 < roof["frac"] < 1.3 and roof["peak"] > 0 and "frac_of_burst" in roof
+    assert rec["e2e"]["h2d_bytes_per_step"] > 0 and rec["e2e"]["d2h_bytes_per_step"] > 0 and rec["e2e"]["value"] < rec["value"]
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert set(rec["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -218,6 +218,9 @@ def roofline_of(kern, bound, step_ms=None):
     table = {n: {"launches": v["launches"], "ms_total": v["ms"],
                  ("gbs" if in_bytes(n) else "tflops"): (v["work"] / (v["ms"] * 1e-3) / (1e9 if in_bytes(n) else 1e12)) if v["ms"] else None}
              for n, v in kern.items()}
+    for n, row in table.items():                  # every tensor-core kernel of the step against both measured bf16 rates
+        if row.get("tflops"):
+            row["frac_of_sustained"], row["frac_of_burst"] = row["tflops"] / pk["tf_sustained"], row["tflops"] / pk["tf_burst"]
     return roof, table
 
 
@@ -405,6 +408,11 @@ def bench_gallery(args, rank, world, device, sync, all_max):
     # resolve it to well under a percent, and the whole default run has to finish within minutes
     ms_e2e = all_max(timed(run_e2e, max(3, min(args.steps, 5)), 1, sync))
     roof, table = roofline_of(m["kernels"], "tensor", m["ms"])
+    if roof and roof["kernel"] == "grad_gemm":
+        roof["note"] = ("the hinge step's gradient products run on tcgen05 kind::i8 (one-byte gradient matrix x two 8-bit planes): "
+                        "`achieved` counts the ALGORITHMIC 2*N*N*D flops once, the kernel executes twice the MACs at the int8 rate, "
+                        "so the fraction of the measured bf16 (cuBLAS) peak can exceed 1; the step's bf16 kernel is sim_hinge+rank "
+                        "(kernels[...].frac_of_sustained)")
     out = m["out"]
     # ---- check block (outside the timed region): world-size independent by construction
     sums = torch.stack([rank_hash_terms(out["ranks"], rank * nl).sum(),

@@ -226,8 +226,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Every use hands a TMEM accumulator (ordered by tcgen05.wait::ld + tcgen05.fence, not by the generic proxy) back to
+// the leader's MMA warp, so the arrive carries the default semantics: `.release.cluster` costs a MEMBAR.ALL.GPU +
+// ERRBAR + CGAERRBAR per warp and tile, which waits for the warp's outstanding global stores and atomics.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's smem whose completion bytes are counted on `bar_cluster_addr` (the leader's barrier)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,

@@ -1289,17 +1289,19 @@ static int launch_sim(const void* x, const void* y, int dtype, int64_t rows, int
 }
 
 PB2_KNOB g_force_bn = 0;  // measurement build: pb2_debug_force_bn
-// pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, 2 = multicast clusters, 0 = independent CTAs, -1 = default.  Pairs are
-// correct (tools/gpu_probe.py simpair: identical counts / ranks) but measured SLOWER here -- hinge pass 1.34 vs
-// 1.23 ms, rank pass 0.843 vs 0.827 ms per 32768^2 block, sustained: a pair's MMA for tile t+2 waits for BOTH
-// CTAs' epilogues of tile t, and these kernels are bound by their epilogues, not by operand traffic (unlike the
-// gradient GEMM, whose gain came from the 512-wide pair tile reading G once).  2 = clusters of 2 with independent
-// MMAs and a multicast Y tile: within noise of independent CTAs (1.25 ms / 0.794 ms).  Kept as measured options.
-// -1 (default) = 0.  Third session, alternating builds on one board: back to back on a 32768^2 block the multicast
-// clusters are 2-3 % faster for the passes without an output tile (rank 0.836 -> 0.816-0.825 ms, one-pass
-// log-sum-exp 1.104-1.112 -> 1.055-1.084 ms) and slower with one (hinge + gradient matrix 1.216 -> 1.245 ms); inside
-// the real steps, where these passes alternate with the gradient GEMMs, they lose (65536-clip MIL-NCE step 16.0-16.9
-// -> 16.4-17.7 ms, 16384^2 recall call 0.38-0.41 -> 0.41-0.43 ms; tools/ab_milnce.py), so independent CTAs stay.
+// pb2_debug_sim_pair: 1 = CTA pairs whenever the tile is 256 wide, 2 = multicast clusters, 0 = independent CTAs, -1 = default = 1 when
+// the problem has at least a tile per SM.
+// CTA pairs (one M = 256 tcgen05.mma per two SMs; each CTA stages its X rows and half of the Y tile) move a third less
+// operand data per SM (L2 -> smem -> tensor core).  Through round 2 they measured 5 % SLOWER than independent CTAs and
+// stayed an option -- until the cause turned out to be the hand-back of the accumulator, not the coupling of the two
+// epilogues: `mbarrier.arrive.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, which every epilogue
+// warp paid once per tile while its count atomics and TMA stores were still in flight.  With the default-semantics
+// arrive (common.cuh: mbar_arrive_cluster; the TMEM hand-back is ordered by tcgen05.wait::ld + tcgen05.fence) pairs
+// win for every policy, back to back on a 32768^2 block on one board (tools/ab_hinge.py, profiles/r2_ab_sim_pairs.txt):
+// rank 0.855 -> 0.795 ms (1383 TF/s), one-pass log-sum-exp 1.14 -> 1.06 ms, hinge + rank + one-byte G 1.155 -> 1.13 ms;
+// inside the steps: 65536-clip MIL-NCE 16.8-18.4 -> 15.5-16.1 ms, 2^20 hinge gallery 2687-2697 -> 2676-2681 ms (that
+// step sits at the board's power cap, where time tracks energy).  2 = clusters of 2 with independent MMAs and a
+// multicast Y tile: within noise of independent CTAs; measurement builds only.
 PB2_KNOB g_sim_pair = -1;
 
 template <class Policy>
@@ -1318,19 +1320,26 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
     if (!Policy::kStoresG && bn == 192) bn = 256;
 #define PB2_SIM(B, GG, CC) \
     launch_sim<Policy, B, GG, CC>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, om, st, what)
-    const bool pair = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 1;
-    const bool mcast = bn == 256 && !std::is_same<Policy, DiagPolicy>::value && g_sim_pair == 2;
+    // pairs by default once every SM has a tile of its own (below that the passes are latency bound)
+    const bool many = ((rows + BM - 1) / BM) * ((cols + 255) / 256) >= sm_count();
+    const int cluster_mode = g_sim_pair >= 0 ? g_sim_pair : (many ? 1 : 0);
+    const bool pair = bn == 256 && cluster_mode == 1;
+#ifdef PB2_MEASURE
+    const bool mcast = bn == 256 && cluster_mode == 2;
+#endif
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
         return PB2_SIM(128, 2, 1);
     } else if constexpr (Policy::kByteG) {
-#ifdef PB2_MEASURE  // the cluster variants with the one-byte gradient matrix (tools/ab_gallery_pair.py)
+#ifdef PB2_MEASURE  // tools/ab_gallery_pair.py
         if (mcast) return PB2_SIM(256, 2, 3);
-        if (pair) return PB2_SIM(256, 2, 2);
 #endif
+        if (pair) return PB2_SIM(256, 2, 2);
         return PB2_SIM(256, 2, 1);  // a warp's 128 columns are one slab of bytes: 256-wide tiles only
     } else if constexpr (Policy::kStoresG) {
         if (bn == 192) return PB2_SIM(192, 3, 1);
+#ifdef PB2_MEASURE
         if (mcast) return PB2_SIM(256, 2, 3);
+#endif
         if (pair) return PB2_SIM(256, 2, 2);
 #ifdef PB2_HINGE_G4  // measurement builds: four column groups (16 epilogue warps, 64 columns each) on 256-wide tiles
         if (bn == 256) return PB2_SIM(256, 4, 1);
@@ -1339,7 +1348,9 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
 #endif
         return PB2_SIM(128, 2, 1);
     } else {
+#ifdef PB2_MEASURE
         if (mcast) return PB2_SIM(256, 2, 3);
+#endif
         if (pair) return PB2_SIM(256, 2, 2);
         if (bn == 256) return PB2_SIM(256, 2, 1);
         if (bn == 128) return PB2_SIM(128, 2, 1);

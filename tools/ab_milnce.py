@@ -1,5 +1,6 @@
-"""A/B of the multicast-cluster default inside one process: the 65536-clip MIL-NCE step (public API, fwd + bwd) and the
-16384^2 retrieval call with pb2_debug_sim_pair(0) (independent CTAs) and (-1) (default), alternately."""
+"""A/B of the similarity pass's cluster variants inside one process: the 65536-clip MIL-NCE step (public API, fwd + bwd)
+and the 16384^2 retrieval call with pb2_debug_sim_pair(0) (independent CTAs), (1) (CTA pairs, cta_group::2), (2)
+(multicast clusters) and (-1) (the product's default), alternately."""
 import os
 import sys
 
@@ -24,7 +25,7 @@ def step():
 
 
 for rep in range(3):
-    for mode in (0, -1):
+    for mode in (0, 1, 2, -1):
         lib.pb2_debug_sim_pair(mode)
         ms = _t(step, iters=5, warm=2)
         ms_r = _t(lambda: metrics.recall_at_1_to_n(v16, a16, None, N=10), iters=20, warm=3)

@@ -8,6 +8,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from bench import synth_embeddings  # noqa: E402
+from peppa_b200 import _cabi  # noqa: E402
+
+if os.environ.get("PB2_SIM_PAIR"):       # measurement build: pick the similarity pass's cluster variant (0 / 1 / 2)
+    _cabi.use_measurement_library().pb2_debug_sim_pair(int(os.environ["PB2_SIM_PAIR"]))
 from peppa_b200.gallery import GalleryStep  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768

@@ -1088,7 +1088,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             float* rv = rowvec + as * (kMaxRowVecs * BM);
             // phase 1: every global load of the tile (fetch_* = loads only), phase 2: arithmetic + smem stores
             constexpr int kColIters = (BN + 31) / 32, kRowIters = BM / 32;
-            uint32_t rc[kColIters][kMaxColRaw], rr[kRowIters][kMaxRowRaw];
+            uint32_t rc[kColIters][kMaxColRaw] = {}, rr[kRowIters][kMaxRowRaw] = {};
 #pragma unroll
             for (int i = 0; i < kColIters; ++i) {
                 const int col = lane + 32 * i;
@@ -1099,10 +1099,23 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                 const int r = lane + 32 * i;
                 Policy::fetch_row(p, c, row0 + r, row0 + r < c.rows, rr[i]);
             }
-            // keep the two phases apart: neither the front end nor ptxas may sink a load to its use
+            // keep the two phases apart: neither the front end nor ptxas may sink a load to its use.  The memory
+            // clobbers alone do not stop NVVM from hoisting the first ARITHMETIC on a loaded value above the barrier;
+            // ptxas may then allocate one register for several loads, and their round trips serialise (seen in a
+            // variant of the MIL-NCE gradient policy: seven loads in a row through one register, 1.42 instead of
+            // 1.05 ms per block; the shipped policies had two or three).  So every raw value is re-defined by a
+            // volatile move behind the barrier: all loads of a tile are in flight before the first use.
             asm volatile("" ::: "memory");
             __syncwarp();
             asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < kColIters; ++i)
+#pragma unroll
+                for (int k = 0; k < kMaxColRaw; ++k) asm volatile("mov.b32 %0, %0;" : "+r"(rc[i][k]));
+#pragma unroll
+            for (int i = 0; i < kRowIters; ++i)
+#pragma unroll
+                for (int k = 0; k < kMaxRowRaw; ++k) asm volatile("mov.b32 %0, %0;" : "+r"(rr[i][k]));
 #pragma unroll
             for (int i = 0; i < kColIters; ++i) {
                 const int col = lane + 32 * i;

@@ -32,6 +32,40 @@ def test_every_declared_symbol_is_exported(lib):
     assert _cabi.lib() is lib
 
 
+def test_sass_has_no_hot_loop_fences_and_no_serialised_loader_loads(lib):
+    """Two properties of the compiled kernels that cost 5-35 % when they broke and that no numerical test sees, read from
+    the SASS of the product library (cuobjdump ships with the toolkit):
+    (1) the similarity kernels' vector-loader warp issues every global load of a tile before the first use, i.e. no
+        load destination register is written twice (a reused register serialises the round trips; DESIGN.md 4.1);
+    (2) a CTA-pair kernel contains GPU-scope fences only for its two cluster barriers and its mbarrier initialisation,
+        not in the accumulator hand-back of the tile loop (`mbarrier.arrive.release.cluster` = MEMBAR.ALL.GPU)."""
+    import re
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    fn, loads, fences, n_sim = None, {}, {}, 0
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            n_sim += "sim_kernel" in fn
+            continue
+        if fn is None:
+            continue
+        if "sim_kernel" in fn and " LDG." in line:
+            dst = re.search(r"LDG\.\S+\s+(R\d+),", line).group(1)
+            loads.setdefault(fn, []).append(dst)
+        if "MEMBAR.ALL.GPU" in line and ("sim_kernel" in fn or "project_normalize" in fn):
+            fences[fn] = fences.get(fn, 0) + 1
+    assert n_sim >= 20 and loads, "no similarity kernels found in the SASS"
+    for f, dst in loads.items():
+        assert len(dst) == len(set(dst)), f"{f}: loader loads share a register: {dst}"
+    for f, n in fences.items():
+        assert n <= 2, f"{f}: {n} GPU-scope fences (expected the two cluster barriers only)"
+
+
 def test_argument_errors_are_reported_without_touching_a_device(lib):
     null = C.c_void_p(0)
     assert lib.pb2_triplet_score(null, null, null, null, null, null, 4, 512, 512, 0, 1, null, null) == 1

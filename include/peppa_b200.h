@@ -150,6 +150,15 @@ int pb2_sim_lse_col_parts(int64_t rows);
 int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
                      int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float bound,
                      float* row_part_sum, float* col_part_sum, void* stream);
+/* The same pass with the ranking of pb2_sim_rank fused in -- loss statistics and recall@k from ONE pass over the
+ * scores (pig/loss.py:13-26 + pig/metrics.py:23-40): rank[i] += #{ j != row_offset + i - col_offset :
+ * fl32(fl32(<x_i, y_j> * rank_rinv_x[i]) * rank_rinv_y[j]) >= pos_thr[i] }, pos_thr from pb2_sim_diag.  The logits keep
+ * rinv_x / rinv_y / scale (MILNCELoss does not re-normalise), the ranking takes its own 1 / ||row|| vectors
+ * (pig/util.py:11-12; null = 1).  Counts are bit-identical to pb2_sim_rank's. */
+int pb2_sim_lse_both_rank(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                          int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float bound,
+                          float* row_part_sum, float* col_part_sum, const float* rank_rinv_x, const float* rank_rinv_y,
+                          const float* pos_thr, int64_t row_offset, int64_t col_offset, int32_t* rank, void* stream);
 int pb2_lse_merge_const(const float* part_sum, int n_parts, int64_t n, float bound, float* lse, int accumulate,
                         void* stream);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pb2_lse_merge": [_p, _p, _i, _i64, _p, _i, _p],
     "pb2_sim_lse_col_parts": [_i64],
     "pb2_sim_lse_both": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _f, _p, _p, _p],
+    "pb2_sim_lse_both_rank": [_p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _p, _p],
     "pb2_lse_merge_const": [_p, _i, _i64, _f, _p, _i, _p],
     "pb2_lse_combine": [_p, _i, _i64, _p, _p],
     "pb2_sim_lse_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i64, _i64, _f, _p, _i64, _p],

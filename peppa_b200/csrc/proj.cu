@@ -23,8 +23,15 @@ namespace pb2 {
 namespace proj {
 
 constexpr int BM = 128, BK = 64, UK = 16;
-constexpr int kEpiWarps = 8, kMmaWarp = 8, kTmaWarp = 9;  // two epilogue warps per TMEM lane quadrant (column halves)
+constexpr int kEpiWarps = 8, kMmaWarp = 8, kTmaWarp = 9;  // the column-split / phased variants: two epilogue warps per TMEM lane quadrant
 constexpr int kThreads = 10 * 32;
+// The product kernel is templated on kParts = epilogue warps per TMEM lane quadrant (each takes a contiguous run of
+// 64-column slabs): 4 * kParts epilogue warps, then the MMA warp, then the TMA warp.
+template <int kParts> struct Cfg {
+    static constexpr int kEpi = 4 * kParts, kMma = kEpi, kTma = kEpi + 1, kThr = (kEpi + 2) * 32;
+    static constexpr int kSlabs = kParts == 2 ? 2 : 1;   // staging slabs per warp (64 KiB in all either way)
+    static constexpr int kRed = 2 * kParts * 128 * 4;     // per-row partial sums: [ss | q][part][row]
+};
 constexpr int kMaxOut = 512;
 // CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 spans the 128 rows of both CTAs; each CTA
 // stages its own x rows and HALF of W's rows for each of the two MMAs of a k-step, so a stage is 48 KiB instead
@@ -39,7 +46,7 @@ constexpr int kSlabBytes = 32 * 64 * 2;        // one warp's [32 rows x 64 bf16]
 constexpr int kOutBytes = kEpiWarps * 2 * kSlabBytes;
 constexpr int kBiasBytes = 0;                   // the bias is read through L1 (broadcast loads): shared memory is full
 constexpr int kRedBytes = 2 * 2 * BM * 4;      // per-row partial sums of the two column halves: [ss | q][half][row]
-constexpr int kSmem = kStages * kStageBytes + kOutBytes + kBiasBytes + kRedBytes + 256;
+constexpr int kSmem = kStages * kStageBytes + kOutBytes + kBiasBytes + 2 * kRedBytes + 256;  // room for kParts = 4
 
 struct Args {
     int64_t rows;
@@ -56,15 +63,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kParts>
+__global__ void __launch_bounds__(Cfg<kParts>::kThr, 1)
     project_normalize_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                              const __grid_constant__ CUtensorMap tm_out, const Args a) {
+    using C = Cfg<kParts>;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* out_stage = smem + kStages * kStageBytes;
-    float* bias_s = reinterpret_cast<float*>(out_stage + kOutBytes);
-    float* red_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_s) + kRedBytes);
+    float* red_s = reinterpret_cast<float*>(out_stage + kOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_s) + C::kRed);
     uint64_t* full = bars;                // [kStages]
     uint64_t* empty = bars + kStages;     // [kStages]
     uint64_t* acc_full = empty + kStages;
@@ -75,28 +83,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t crank = cluster_ctarank();  // 0 = leader (issues the MMAs)
     const int64_t n_tiles = (a.rows + 2 * BM - 1) / (2 * BM);  // pair tiles of 256 rows
     const int64_t unit0 = blockIdx.x / 2, n_units = gridDim.x / 2;
-    if (warp == kTmaWarp && lane == 0) {
+    if (warp == C::kTma && lane == 0) {
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_out);
     }
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == C::kMma && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 2 * kEpiWarps);  // the leader's collects both CTAs' epilogues
+        mbar_init(acc_empty, 2 * C::kEpi);  // the leader's collects both CTAs' epilogues
         fence_mbar_init();
     }
-    if (warp == kTmaWarp) tmem_alloc_pair(tmem_slot, 512);
+    if (warp == C::kTma) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n1 = a.n_out > 256 ? 256 : a.n_out, n2 = a.n_out - n1;  // N of the two MMAs of a k-step
 
-    if (warp == kTmaWarp) {
+    if (warp == C::kTma) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == C::kMma) {
         if (lane == 0 && crank == 0) {
             const uint32_t idesc1 = make_idesc(2 * BM, (uint32_t)n1, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
             const uint32_t idesc2 = n2 > 0 ? make_idesc(2 * BM, (uint32_t)n2, kFmtBF16, kFmtBF16, kMajorK, kMajorK) : 0u;
@@ -157,15 +165,17 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else {
-        // ===== epilogue: thread == row; warps 0-3 take the first half of the 32-column chunks, warps 4-7 the
-        // second; two passes over the accumulator (sum of squares, then scale / round / stage), the halves'
-        // per-row partial sums meet in shared memory in a fixed order (deterministic)
-        const int quad = warp & 3, half = warp >> 2;
-        uint8_t* slab = out_stage + warp * 2 * kSlabBytes;
+        // ===== epilogue: thread == row; the kParts warps of a TMEM lane quadrant take contiguous runs of 64-column
+        // slabs; two passes over the accumulator (sum of squares, then scale / round / stage), the parts' per-row
+        // partial sums meet in shared memory in a fixed order (deterministic).  With the single 128 x 512 accumulator
+        // stage the epilogue is NOT overlapped with the next tile's MMAs, so its length counts in full: kParts = 2
+        // hides the TMEM round trips with two register buffers per warp, kParts = 4 with four warps per scheduler.
+        const int quad = warp & 3, part = warp >> 2;
+        uint8_t* slab = out_stage + warp * C::kSlabs * kSlabBytes;
         uint32_t n_slab = 0;
-        const int n_chunks = a.n_out / 32;
-        const int ch0 = half == 0 ? 0 : (n_chunks + 1) / 2 / 2 * 2;           // even split point (slabs are 2 chunks)
-        const int ch1 = half == 0 ? (n_chunks + 1) / 2 / 2 * 2 : n_chunks;
+        const int pairs = a.n_out / 64, base = pairs / kParts, rem = pairs % kParts;
+        const int ch0 = 2 * (part * base + (part < rem ? part : rem));
+        const int ch1 = ch0 + 2 * (base + (part < rem ? 1 : 0));
         const int r = quad * 32 + lane;
         const bool has_bias = a.bias != nullptr;
         int64_t it = 0;
@@ -174,9 +184,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_wait(acc_full, (uint32_t)(it & 1));
             tc_fence_after();
             const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-            // Both passes keep the TMEM load of chunk c + 1 in flight while chunk c is processed (two register
-            // buffers, like sim.cu): with one accumulator stage the epilogue is NOT overlapped with the next tile's
-            // MMAs, so every exposed tcgen05.ld round trip (16 per tile and warp before) was dead time on the SM.
             float2 ssa = make_float2(0.f, 0.f), ssb = make_float2(0.f, 0.f);
             auto pass1 = [&](const uint32_t (&v)[32], int ch) {
                 const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
@@ -189,26 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ssb = __ffma2_rn(y23, y23, ssb);
                 }
             };
-            uint32_t va[32], vb[32];
-            if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);
-#pragma unroll 1
-            for (int ch = ch0; ch < ch1; ch += 2) {  // each half holds an even number of chunks
-                tmem_ld_wait();
-                __syncwarp();
-                tmem_ld32(t_lane + (ch + 1) * 32, vb);
-                pass1(va, ch);
-                tmem_ld_wait();
-                __syncwarp();
-                if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
-                pass1(vb, ch + 1);
-            }
-            red_s[half * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
-            if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);  // pass 2's first chunk travels across the barrier
-            named_bar_sync(1, kEpiWarps * 32);
-            const float nrm = sqrtf(red_s[r] + red_s[BM + r]);
-            const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
-            const float2 sc2 = make_float2(scale, scale);
             float2 qa = make_float2(0.f, 0.f);
+            float2 sc2;
             auto pass2 = [&](const uint32_t (&v)[32], int ch) {
                 const float4* b4 = reinterpret_cast<const float4*>(a.bias + ch * 32);
                 uint32_t packed[16];
@@ -226,9 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                     qa = __ffma2_rn(r23, r23, qa);
                 }
                 const int cp = (ch - ch0) & 1;
-                uint8_t* sl = slab + (n_slab & 1) * kSlabBytes;
+                uint8_t* sl = slab + (C::kSlabs == 2 ? (n_slab & 1) : 0u) * kSlabBytes;
                 if (cp == 0) {  // the slab about to be rewritten must have been read by its TMA store
-                    if (lane == 0) tma_store_wait_read<1>();
+                    if (lane == 0) tma_store_wait_read<C::kSlabs - 1>();
                     __syncwarp();
                 }
                 uint8_t* srow = sl + lane * 128;
@@ -248,23 +237,336 @@ __global__ void __launch_bounds__(kThreads, 1)
                     ++n_slab;
                 }
             };
+            float nrm;
+            auto row_scale = [&]() {  // after the barrier: the parts' sums of squares in a fixed order
+                float ss = red_s[r];
+#pragma unroll
+                for (int p = 1; p < kParts; ++p) ss += red_s[p * BM + r];
+                nrm = sqrtf(ss);
+                const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
+                sc2 = make_float2(scale, scale);
+            };
+            if constexpr (kParts == 2) {
+                // Both passes keep the TMEM load of chunk c + 1 in flight while chunk c is processed (two register
+                // buffers, like sim.cu).
+                uint32_t va[32], vb[32];
+                if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);
 #pragma unroll 1
-            for (int ch = ch0; ch < ch1; ch += 2) {
-                tmem_ld_wait();
-                __syncwarp();
-                tmem_ld32(t_lane + (ch + 1) * 32, vb);
-                pass2(va, ch);
-                tmem_ld_wait();
-                __syncwarp();
-                if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
-                pass2(vb, ch + 1);
+                for (int ch = ch0; ch < ch1; ch += 2) {  // each part holds an even number of chunks
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(t_lane + (ch + 1) * 32, vb);
+                    pass1(va, ch);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
+                    pass1(vb, ch + 1);
+                }
+                red_s[part * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+                if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);  // pass 2's first chunk travels across the barrier
+                named_bar_sync(1, C::kEpi * 32);
+                row_scale();
+#pragma unroll 1
+                for (int ch = ch0; ch < ch1; ch += 2) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    tmem_ld32(t_lane + (ch + 1) * 32, vb);
+                    pass2(va, ch);
+                    tmem_ld_wait();
+                    __syncwarp();
+                    if (ch + 2 < ch1) tmem_ld32(t_lane + (ch + 2) * 32, va);
+                    pass2(vb, ch + 1);
+                }
+            } else {
+                uint32_t va[32];
+#pragma unroll 1
+                for (int ch = ch0; ch < ch1; ++ch) {
+                    tmem_ld32(t_lane + ch * 32, va);
+                    tmem_ld_wait();
+                    pass1(va, ch);
+                }
+                red_s[part * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+                if (ch0 < ch1) tmem_ld32(t_lane + ch0 * 32, va);  // pass 2's first chunk travels across the barrier
+                named_bar_sync(1, C::kEpi * 32);
+                row_scale();
+#pragma unroll 1
+                for (int ch = ch0; ch < ch1; ++ch) {
+                    tmem_ld_wait();
+                    __syncwarp();
+                    pass2(va, ch);
+                    if (ch + 1 < ch1) tmem_ld32(t_lane + (ch + 1) * 32, va);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty), 0));  // the leader's MMA warp
-            red_s[2 * BM + half * BM + r] = qa.x + qa.y;
-            named_bar_sync(1, kEpiWarps * 32);
-            if (half == 0 && row < a.rows) {
+            red_s[(kParts + part) * BM + r] = qa.x + qa.y;
+            named_bar_sync(1, C::kEpi * 32);
+            if (part == 0 && row < a.rows) {
+                float q = red_s[kParts * BM + r];
+#pragma unroll
+                for (int p = 1; p < kParts; ++p) q += red_s[(kParts + p) * BM + r];
+                if (a.rinv) a.rinv[row] = 1.0f / sqrtf(q);  // no epsilon: the scoring kernels' convention
+                if (a.norm) a.norm[row] = nrm;
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+        __syncwarp();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
+    if (warp == C::kTma) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Resident-x phased kernel (n_in <= 512, n_out % 128 == 0: the reference's Linear(512, 512) tails).
+//
+// What bounds the interleaved kernel above is that its two halves cannot overlap: the 128 x 512 fp32 accumulator is
+// all of TMEM, so a tile costs an MMA phase (8192 tensor cycles, and 384 KB per SM through L2 at the chip's
+// ~43 B/cycle/SM: ~9 k cycles) PLUS a two-pass epilogue that reads 2 x 256 KB out of TMEM at its 64 B/cycle (>= 8192
+// cycles, whatever the number of epilogue warps: sixteen warps measured the same as eight).  Here the accumulator is
+// produced in PHASES of 128 output columns, one after the other, each with its own full / empty barrier:
+//     MMA_0 | MMA_1 | MMA_2 | MMA_3           | MMA_0' | MMA_1' ...
+//           | p1_0  | p1_1  | p1_2  p1_3 p2_0 | p2_1   | p2_2 ...
+// pass 1 (sum of squares) of phase q runs under MMA_{q+1}; the next tile's MMA_q starts as soon as pass 2 (scale /
+// round / store) has drained phase q.  Only pass 1 of the last phase and pass 2 of the first are exposed.  The phased
+// variant of the measurement build streamed x once per phase and lost to L2 what it won; here the pair's x tile
+// (128 x n_in bf16 per CTA, <= 128 KiB) STAYS in shared memory for all phases -- slot kb is refilled with the next
+// tile's k-block as soon as the last phase has consumed it -- and only W streams (8 KiB stages: this CTA's 64 rows of
+// a phase's 128, one k-block; eight stages in flight), so a tile moves the same 384 KB per SM as before.
+constexpr int kR_MaxKb = 8;                        // n_in <= 512
+constexpr int kR_WBytes = 64 * 1024;               // the W ring
+constexpr int kR_Epi = 8, kR_Mma = 8, kR_TmaW = 9, kR_TmaX = 10, kR_Threads = 11 * 32;
+constexpr int kR_OutBytes = kR_Epi * kSlabBytes;   // one staging slab per epilogue warp
+constexpr int kR_Smem = kR_MaxKb * kXBytes + kR_WBytes + kR_OutBytes + kRedBytes + 512;
+static_assert(kR_Smem <= 227 * 1024, "resident encoder tail: shared memory");
+
+// kPW: output columns per phase = N of its MMAs (128 or 256)
+template <int kPW>
+__global__ void __launch_bounds__(kR_Threads, 1)
+    project_normalize_resident_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                                      const __grid_constant__ CUtensorMap tm_out, const Args a) {
+    constexpr int kWStage = (kPW / 2) * BK * 2;    // this CTA's half of a phase's W rows, one k-block
+    constexpr int kWStages = kR_WBytes / kWStage;
+    constexpr int kMaxPhases = kMaxOut / kPW;
+    constexpr int kSL = kPW / 128;                 // 64-column slabs per phase and warp
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* xs = smem;
+    uint8_t* ws = xs + kR_MaxKb * kXBytes;
+    uint8_t* out_stage = ws + kR_WBytes;
+    float* red_s = reinterpret_cast<float*>(out_stage + kR_OutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_s) + kRedBytes);
+    uint64_t* x_full = bars;                      // [kR_MaxKb]
+    uint64_t* x_empty = x_full + kR_MaxKb;        // [kR_MaxKb]
+    uint64_t* w_full = x_empty + kR_MaxKb;        // [kWStages]
+    uint64_t* w_empty = w_full + kWStages;        // [kWStages]
+    uint64_t* acc_full = w_empty + kWStages;      // [kMaxPhases]
+    uint64_t* acc_empty = acc_full + kMaxPhases;  // [kMaxPhases]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxPhases);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int64_t n_tiles = (a.rows + 2 * BM - 1) / (2 * BM);
+    const int64_t unit0 = blockIdx.x / 2, n_units = gridDim.x / 2;
+    const int n_phases = a.n_out / kPW, n_kb = a.kblocks;
+    if (warp == kR_TmaW && lane == 0) {
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_out);
+    }
+    if (warp == kR_Mma && lane == 0) {
+        for (int s = 0; s < kR_MaxKb; ++s) {
+            mbar_init(x_full + s, 1);
+            mbar_init(x_empty + s, 1);
+        }
+        for (int s = 0; s < kWStages; ++s) {
+            mbar_init(w_full + s, 1);
+            mbar_init(w_empty + s, 1);
+        }
+        for (int q = 0; q < kMaxPhases; ++q) {
+            mbar_init(acc_full + q, 1);
+            mbar_init(acc_empty + q, 2 * kR_Epi);  // the leader's collects both CTAs' epilogues
+        }
+        fence_mbar_init();
+    }
+    if (warp == kR_TmaW) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kR_TmaW) {
+        if (lane == 0) {  // W: [phase][k-block] stages, this CTA's half of the phase's rows
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = unit0; t < n_tiles; t += n_units)
+                for (int q = 0; q < n_phases; ++q)
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        mbar_wait(w_empty + stage, phase ^ 1);
+                        if (crank == 0) mbar_arrive_expect_tx(w_full + stage, 2 * kWStage);  // both CTAs' bytes
+                        tma_load_2d_pair(ws + stage * kWStage, &tm_w, mapa_u32(smem_u32(w_full + stage), 0), kb * BK,
+                                         q * kPW + (int32_t)crank * (kPW / 2), kEvictLast);
+                        if (++stage == kWStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+        }
+    } else if (warp == kR_TmaX) {
+        if (lane == 0) {  // x: slot kb is refilled once the last phase of the previous tile has consumed it
+            int64_t it = 0;
+            for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+                const int32_t xrow = (int32_t)((t * 2 + crank) * BM);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(x_empty + kb, (uint32_t)(it & 1) ^ 1);
+                    if (crank == 0) mbar_arrive_expect_tx(x_full + kb, 2 * kXBytes);
+                    tma_load_2d_pair(xs + kb * kXBytes, &tm_x, mapa_u32(smem_u32(x_full + kb), 0), kb * BK, xrow, kEvictFirst);
+                }
+            }
+        }
+    } else if (warp == kR_Mma) {
+        if (lane == 0 && crank == 0) {
+            const uint32_t idesc = make_idesc(2 * BM, (uint32_t)kPW, kFmtBF16, kFmtBF16, kMajorK, kMajorK);
+            const uint64_t d0 = make_smem_desc(smem_u32(xs), 16, 1024);
+            const uint32_t desc_hi = (uint32_t)(d0 >> 32), xlo0 = (uint32_t)d0;
+            const uint32_t wlo0 = (uint32_t)make_smem_desc(smem_u32(ws), 16, 1024);
+            constexpr uint32_t kXLo = kXBytes >> 4, kWLo = kWStage >> 4, kKLo = (UK * 2) >> 4;
+            int stage = 0;
+            uint32_t phase = 0, wlo = wlo0;
+            int64_t it = 0;
+            for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+                for (int q = 0; q < n_phases; ++q) {
+                    mbar_wait(acc_empty + q, (uint32_t)(it & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * kPW);
+                    uint32_t xlo = xlo0;
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        if (q == 0) mbar_wait(x_full + kb, (uint32_t)(it & 1));
+                        mbar_wait(w_full + stage, phase);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_f16_pair_lohi(d_tmem, xlo + k * kKLo, wlo + k * kKLo, desc_hi, desc_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(w_empty + stage);
+                        if (q == n_phases - 1) umma_commit_pair(x_empty + kb);
+                        xlo += kXLo;
+                        wlo += kWLo;
+                        if (++stage == kWStages) {
+                            stage = 0;
+                            phase ^= 1;
+                            wlo = wlo0;
+                        }
+                    }
+                    umma_commit_pair(acc_full + q);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: thread == row; of a phase's kPW columns warps 0-3 take the first half (kSL 64-column slabs),
+        // warps 4-7 the second; the halves' per-row partial sums meet in shared memory in a fixed order (deterministic)
+        const int quad = warp & 3, sub = warp >> 2;
+        uint8_t* sl = out_stage + warp * kSlabBytes;
+        const int r = quad * 32 + lane;
+        const bool has_bias = a.bias != nullptr;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int n_slabs = n_phases * kSL;   // this warp's slabs of a tile; slab i: phase i / kSL, columns below
+        auto slab_col = [&](int i) { return (i / kSL) * kPW + (sub * kSL + i % kSL) * 64; };
+        int64_t it = 0;
+        for (int64_t t = unit0; t < n_tiles; t += n_units, ++it) {
+            const int64_t row0 = (t * 2 + crank) * BM, row = row0 + r;
+            const uint32_t par = (uint32_t)(it & 1);
+            float2 ssa = make_float2(0.f, 0.f), ssb = make_float2(0.f, 0.f);
+            uint32_t va[32], vb[32];
+            auto pass1 = [&](const uint32_t (&v)[32], int col) {
+                const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float2 y01 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+                    const float2 y23 = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
+                    ssa = __ffma2_rn(y01, y01, ssa);
+                    ssb = __ffma2_rn(y23, y23, ssb);
+                }
+            };
+            // ---- pass 1: sum of squares, phase q under the MMAs of phase q + 1
+#pragma unroll 1
+            for (int i = 0; i < n_slabs; ++i) {
+                if (i % kSL == 0) {
+                    mbar_wait(acc_full + i / kSL, par);
+                    tc_fence_after();
+                }
+                const int col = slab_col(i);
+                tmem_ld32(t_lane + col, va);
+                tmem_ld32(t_lane + col + 32, vb);
+                tmem_ld_wait();
+                pass1(va, col);
+                pass1(vb, col + 32);
+            }
+            red_s[sub * BM + r] = (ssa.x + ssa.y) + (ssb.x + ssb.y);
+            tmem_ld32(t_lane + slab_col(0), va);  // pass 2's first loads travel across the barrier
+            tmem_ld32(t_lane + slab_col(0) + 32, vb);
+            named_bar_sync(1, kR_Epi * 32);
+            const float nrm = sqrtf(red_s[r] + red_s[BM + r]);
+            const float scale = 1.0f / fmaxf(nrm, a.eps);  // F.normalize: x / max(||x||, eps)
+            const float2 sc2 = make_float2(scale, scale);
+            float2 qa = make_float2(0.f, 0.f);
+            auto pass2 = [&](const uint32_t (&v)[32], int col, int cp) {
+                const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = has_bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float2 e01 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y)), sc2);
+                    const float2 e23 = __fmul2_rn(__fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w)), sc2);
+                    const uint32_t p0 = pack_bf16(e01.x, e01.y), p1 = pack_bf16(e23.x, e23.y);
+                    packed[2 * j] = p0;
+                    packed[2 * j + 1] = p1;
+                    const float2 r01 = make_float2(__uint_as_float(p0 << 16), __uint_as_float(p0 & 0xffff0000u));
+                    const float2 r23 = make_float2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+                    qa = __ffma2_rn(r01, r01, qa);
+                    qa = __ffma2_rn(r23, r23, qa);
+                }
+                uint8_t* srow = sl + lane * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c16 = (cp * 4 + k) ^ (lane & 7);  // 128-byte swizzle
+                    *reinterpret_cast<uint4*>(srow + c16 * 16) =
+                        make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                }
+            };
+            // ---- pass 2: scale / round / stage / store; phase q goes back to the next tile's MMAs as soon as it is read
+#pragma unroll 1
+            for (int i = 0; i < n_slabs; ++i) {
+                const int col = slab_col(i);
+                tmem_ld_wait();
+                if (i % kSL == kSL - 1) tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (i % kSL == kSL - 1) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + i / kSL), 0));  // the phase is in registers
+                    tma_store_wait_read<0>();                                                               // the slab's previous store has read it
+                }
+                __syncwarp();
+                pass2(va, col, 0);
+                pass2(vb, col + 32, 1);
+                if (i + 1 < n_slabs) {
+                    tmem_ld32(t_lane + slab_col(i + 1), va);
+                    tmem_ld32(t_lane + slab_col(i + 1) + 32, vb);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, sl, col, (int32_t)(row0 + quad * 32));
+                    tma_store_commit();
+                }
+            }
+            red_s[2 * BM + sub * BM + r] = qa.x + qa.y;
+            named_bar_sync(1, kR_Epi * 32);
+            if (sub == 0 && row < a.rows) {
                 if (a.rinv) a.rinv[row] = 1.0f / sqrtf(red_s[2 * BM + r] + red_s[3 * BM + r]);  // no epsilon: the scoring kernels' convention
                 if (a.norm) a.norm[row] = nrm;
             }
@@ -274,12 +576,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     tc_fence_before();
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer still signals it
-    if (warp == kTmaWarp) {
+    if (warp == kR_TmaW) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 512);
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // Column-split variant (n_out % 128 == 0; measured option, see g_variant below): the two CTAs of a cluster take the SAME 128 rows and half of the
@@ -818,9 +1119,6 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
     a.eps = eps;
     a.rinv = rinv;
     a.norm = norm;
-    static PerDeviceOnce configured;
-    rc = ensure_dynamic_smem(configured, proj::project_normalize_kernel, proj::kSmem, "project_normalize");
-    if (rc) return rc;
     if (n_out % 128 == 0 && proj::g_variant == 2) {  // column-split pairs: two TMEM stages, epilogue overlaps the MMA
         CUtensorMap tx2;
         rc = make_tmap_2d(&tx2, x, 2, (uint64_t)rows, (uint64_t)n_in, (uint64_t)ldx * 2, 64, proj::BK);
@@ -850,8 +1148,45 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
         return check_launch("project_normalize");
     }
 #endif
-    rc = check_cuda(launch_ex(proj::project_normalize_kernel, (unsigned)grid, (unsigned)proj::kThreads, (size_t)proj::kSmem,
-                              (cudaStream_t)stream, 2, tx, tw, to, a),
+    if ((proj::g_variant == 5 || proj::g_variant == 6) && a.kblocks <= proj::kR_MaxKb) {  // x resident, phased accumulator
+        const int pw = proj::g_variant == 5 ? 128 : 256;
+        if (n_out % pw == 0) {
+            CUtensorMap twp;
+            rc = make_tmap_2d(&twp, w, 2, (uint64_t)n_out, (uint64_t)n_in, (uint64_t)ldw * 2, pw / 2, proj::BK);
+            if (rc) return rc;
+            static PerDeviceOnce configured5, configured6;
+            if (pw == 128) {
+                rc = ensure_dynamic_smem(configured5, proj::project_normalize_resident_kernel<128>, proj::kR_Smem, "project_normalize");
+                if (rc) return rc;
+                rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<128>, (unsigned)grid, (unsigned)proj::kR_Threads,
+                                          (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
+                                "project_normalize launch");
+            } else {
+                rc = ensure_dynamic_smem(configured6, proj::project_normalize_resident_kernel<256>, proj::kR_Smem, "project_normalize");
+                if (rc) return rc;
+                rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<256>, (unsigned)grid, (unsigned)proj::kR_Threads,
+                                          (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
+                                "project_normalize launch");
+            }
+            if (rc) return rc;
+            return check_launch("project_normalize");
+        }
+    }
+    if (proj::g_variant == 4) {  // sixteen epilogue warps (four per TMEM lane quadrant and scheduler)
+        static PerDeviceOnce configured4;
+        rc = ensure_dynamic_smem(configured4, proj::project_normalize_kernel<4>, proj::kSmem, "project_normalize");
+        if (rc) return rc;
+        rc = check_cuda(launch_ex(proj::project_normalize_kernel<4>, (unsigned)grid, (unsigned)proj::Cfg<4>::kThr,
+                                  (size_t)proj::kSmem, (cudaStream_t)stream, 2, tx, tw, to, a),
+                        "project_normalize launch");
+        if (rc) return rc;
+        return check_launch("project_normalize");
+    }
+    static PerDeviceOnce configured;
+    rc = ensure_dynamic_smem(configured, proj::project_normalize_kernel<2>, proj::kSmem, "project_normalize");
+    if (rc) return rc;
+    rc = check_cuda(launch_ex(proj::project_normalize_kernel<2>, (unsigned)grid, (unsigned)proj::Cfg<2>::kThr,
+                              (size_t)proj::kSmem, (cudaStream_t)stream, 2, tx, tw, to, a),
                     "project_normalize launch");
     if (rc) return rc;
     return check_launch("project_normalize");

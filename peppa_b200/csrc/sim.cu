@@ -732,42 +732,81 @@ struct LseRowPolicy {
 // two shuffles) and leave as one fp32 per (32-row group, column): fixed order, no atomics, bit-reproducible.
 // Partials: row sums in the layout of pb2_sim_lse_parts (per 128 columns), column sums [4 * row blocks, cols];
 // both are merged by pb2_lse_merge_const.
-struct LseBothPolicy {
+// kRank: the same pass also counts, per row, the columns whose COSINE beats the positive's (recall@k of the gallery,
+// pig/metrics.py:23-40) -- the loss statistics use the caller's logits (raw dot products over a temperature for
+// pig.loss.MILNCELoss), the ranking re-normalises like pig.util.cosine_matrix, so the count takes its own 1 / ||row||
+// vectors and scores every element a second time from the same accumulator: s = fl32(fl32(acc * ra_i) * rv_j), the
+// very expression (and bits) of RankPolicy, compared with the threshold of pb2_sim_diag.
+struct LseBothParams {
+    float* row_part_sum;  // [pb2_sim_lse_parts(cols), rows]
+    float* col_part_sum;  // [pb2_sim_lse_col_parts(rows), cols]
+    float shift;          // M: log2-domain upper bound of the logits
+    // kRank only
+    const float* rank_rinv_x;  // 1 / ||x_i|| of the ranking (may be null = 1)
+    const float* rank_rinv_y;  // 1 / ||y_j||
+    const float* pos_thr;      // rank_threshold(fl32(1 - s_pos)) per row
+    int64_t row_offset, col_offset;  // the positive of row i is global column row_offset + i
+    int32_t* rank;
+};
+template <bool kRank>
+struct LseBothPolicyT {
     static constexpr bool kByteG = false;
     static constexpr bool kStoresF32 = false;
     static constexpr bool kStoresG = false;
     static constexpr bool kUsesStage = true;
-    struct Params {
-        float* row_part_sum;  // [pb2_sim_lse_parts(cols), rows]
-        float* col_part_sum;  // [pb2_sim_lse_col_parts(rows), cols]
-        float shift;          // M: log2-domain upper bound of the logits
-    };
-    static constexpr int kColVecs = 1;
+    using Params = LseBothParams;
+    static constexpr int kColVecs = kRank ? 2 : 1;  // rinv_y of the logits; rinv_y of the ranking
     float ri, s;
+    float rri, thr_k;
+    float2 rk2;
+    int dcol;
     __device__ void kernel_begin(const Params&) {}
-    __device__ static void fetch_col(const Params&, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
+    __device__ static void fetch_col(const Params& p, const SimCommon& c, int64_t col, bool valid, uint32_t* raw) {
         raw[0] = ldu(c.rinv_y, col, valid, kOneBits);
+        if (kRank) raw[1] = ldu(p.rank_rinv_y, col, valid, kOneBits);
     }
     __device__ static void make_col(const Params&, const SimCommon&, bool valid, const uint32_t* raw, float* v) {
         v[0] = valid ? __uint_as_float(raw[0]) : 0.f;
+        if (kRank) v[1] = valid ? __uint_as_float(raw[1]) : PB2_NAN;  // an out-of-range column never counts
     }
-    static constexpr int kRowVecs = 1;
-    __device__ static void fetch_row(const Params&, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
+    static constexpr int kRowVecs = kRank ? 4 : 1;  // logit factor; ranking 1 / ||x||, rank threshold, positive's column
+    __device__ static void fetch_row(const Params& p, const SimCommon& c, int64_t row, bool valid, uint32_t* raw) {
         raw[0] = ldu(c.rinv_x, row, valid, kOneBits);
+        if (kRank) {
+            raw[1] = ldu(p.rank_rinv_x, row, valid, kOneBits);
+            raw[2] = ldu(p.pos_thr, row, valid, 0u);
+        }
     }
-    __device__ static void make_row(const Params&, const SimCommon& c, int64_t, bool valid, const uint32_t* raw, float* v) {
+    __device__ static void make_row(const Params& p, const SimCommon& c, int64_t row, bool valid, const uint32_t* raw, float* v) {
         v[0] = (valid ? __uint_as_float(raw[0]) : 0.f) * c.scale * 1.4426950408889634f;  // log2 domain
+        if (kRank) {
+            v[1] = valid ? __uint_as_float(raw[1]) : 0.f;
+            v[2] = valid ? __uint_as_float(raw[2]) : PB2_INF;  // an out-of-range row never counts
+            const int64_t rel = valid ? (p.row_offset + row) - p.col_offset : -1;
+            v[3] = __int_as_float((rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1);
+        }
     }
-    __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx&, const float* rv) {
+    __device__ void tile_begin(const Params&, const SimCommon&, const TileCtx& t, const float* rv) {
         ri = rv[0];
         s = 0.f;
+        if (kRank) {
+            rri = rv[128];
+            thr_k = rv[256];
+            rk2 = make_float2(0.f, 0.f);
+            const int g = __float_as_int(rv[384]);
+            const int64_t rel = (int64_t)g - t.col0;
+            dcol = (g >= 0 && rel >= 0 && rel < 0x7fffffff) ? (int)rel : -1;
+        }
     }
     __device__ void chunk(const Params& p, const SimCommon& c, const TileCtx& t, int ch, int cbase, const uint32_t (&v)[32],
                           const float* cv, OutStage& os) {
         const int nvalid = t.cols_valid - cbase;
         if (nvalid <= 0) return;  // warp-uniform
-        // kSlow: ragged last column tile, or rows past the end in this warp (those elements add nothing)
-        if (__any_sync(0xffffffffu, nvalid < 32 || !t.row_valid)) chunk_impl<true>(p, c, t, cbase, v, cv, os);
+        // kSlow: ragged last column tile, or rows past the end in this warp (those elements add nothing); with kRank
+        // also a chunk that holds some row's positive (it never counts against itself)
+        bool slow = nvalid < 32 || !t.row_valid;
+        if (kRank) slow = slow || (dcol - cbase >= 0 && dcol - cbase < 32);
+        if (__any_sync(0xffffffffu, slow)) chunk_impl<true>(p, c, t, cbase, v, cv, os);
         else chunk_impl<false>(p, c, t, cbase, v, cv, os);
     }
     template <bool kSlow>
@@ -779,11 +818,30 @@ struct LseBothPolicy {
         const float2 neg = make_float2(-p.shift, -p.shift);
         float e[32];
         float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+        [[maybe_unused]] const float4* ck4 = reinterpret_cast<const float4*>(cv + kColVecStride);
+        [[maybe_unused]] const float2 rri2 = make_float2(rri, rri);
+        [[maybe_unused]] const int drel = dcol - cbase;
+        [[maybe_unused]] float2 rka = make_float2(0.f, 0.f), rkb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float4 c4 = cv4[q];
             const float2 d0 = __fadd2_rn(score2(v[4 * q], v[4 * q + 1], ri2, c4.x, c4.y), neg);
             const float2 d1 = __fadd2_rn(score2(v[4 * q + 2], v[4 * q + 3], ri2, c4.z, c4.w), neg);
+            if constexpr (kRank) {  // cosine of the same accumulator entries against the positive's threshold (ALU pipe)
+                const float4 k4 = ck4[q];
+                const float2 r01 = score2(v[4 * q], v[4 * q + 1], rri2, k4.x, k4.y);
+                const float2 r23 = score2(v[4 * q + 2], v[4 * q + 3], rri2, k4.z, k4.w);
+                float2 i01 = make_float2(fset_ge(r01.x, thr_k), fset_ge(r01.y, thr_k));
+                float2 i23 = make_float2(fset_ge(r23.x, thr_k), fset_ge(r23.y, thr_k));
+                if (kSlow) {
+                    if (4 * q + 0 == drel) i01.x = 0.f;
+                    if (4 * q + 1 == drel) i01.y = 0.f;
+                    if (4 * q + 2 == drel) i23.x = 0.f;
+                    if (4 * q + 3 == drel) i23.y = 0.f;
+                }
+                rka = __fadd2_rn(rka, i01);
+                rkb = __fadd2_rn(rkb, i23);
+            }
             e[4 * q + 0] = ex2_approx(d0.x);
             e[4 * q + 1] = ex2_approx(d0.y);
             e[4 * q + 2] = ex2_approx(d1.x);
@@ -798,6 +856,7 @@ struct LseBothPolicy {
             a23 = __fadd2_rn(a23, make_float2(e[4 * q + 2], e[4 * q + 3]));
         }
         s += (a01.x + a01.y) + (a23.x + a23.y);
+        if (kRank) rk2 = __fadd2_rn(rk2, __fadd2_rn(rka, rkb));
         // column sums over this warp's 32 rows: transpose through the slab
         const int lane = lane_id();
         os.write_f32(lane, e);
@@ -829,6 +888,10 @@ struct LseBothPolicy {
     }
     __device__ void tile_end(const Params& p, const SimCommon& c, const TileCtx& t) {
         if (!t.row_valid) return;
+        if (kRank) {
+            const int rk = (int)(rk2.x + rk2.y);  // exact: small integers in fp32
+            if (rk) atomicAdd(p.rank + t.row, rk);
+        }
         // row-sum partials: two slots per 128 columns like LseRowPolicy (pb2_sim_lse_parts)
         if (t.warp_cols == 64) {
             p.row_part_sum[((int64_t)t.cb * 2 + t.half) * c.rows + t.row] = s;
@@ -1476,10 +1539,29 @@ extern "C" int pb2_sim_lse_both(const void* x, const void* y, const float* rinv_
     const float shift = bound * 1.4426950408889634f;
     if (!(bound >= 0.f) || !(shift <= 60.f))
         return set_error(PB2_ERR_ARG, "sim_lse_both: needs 0 <= bound and bound * log2(e) <= 60 (use the two-pass path)");
-    LseBothPolicy::Params pp{row_part_sum, col_part_sum, shift};
+    LseBothParams pp{row_part_sum, col_part_sum, shift, nullptr, nullptr, nullptr, 0, 0, nullptr};
     const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
-    return dispatch_sim<LseBothPolicy>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
-                                       "sim_lse_both", bn);
+    return dispatch_sim<LseBothPolicyT<false>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+                                               "sim_lse_both", bn);
+}
+
+// The same pass with the ranking of pb2_sim_rank fused in (north-star kernels (a) + (b) from one S pass): `rank[i]` +=
+// the number of columns j != row_offset + i - col_offset whose cosine fl32(fl32(<x_i, y_j> * rank_rinv_x[i]) *
+// rank_rinv_y[j]) reaches pos_thr[i] (pb2_sim_diag's threshold).  Counts are bit-identical to pb2_sim_rank's.
+extern "C" int pb2_sim_lse_both_rank(const void* x, const void* y, const float* rinv_x, const float* rinv_y, int64_t rows,
+                                     int64_t cols, int dim, int dtype, int64_t ldx, int64_t ldy, float scale, float bound,
+                                     float* row_part_sum, float* col_part_sum, const float* rank_rinv_x,
+                                     const float* rank_rinv_y, const float* pos_thr, int64_t row_offset, int64_t col_offset,
+                                     int32_t* rank, void* stream) {
+    if (rows > 0 && cols > 0 && (!row_part_sum || !col_part_sum || !pos_thr || !rank))
+        return set_error(PB2_ERR_ARG, "sim_lse_both_rank: null");
+    const float shift = bound * 1.4426950408889634f;
+    if (!(bound >= 0.f) || !(shift <= 60.f))
+        return set_error(PB2_ERR_ARG, "sim_lse_both_rank: needs 0 <= bound and bound * log2(e) <= 60 (use the two-pass path)");
+    LseBothParams pp{row_part_sum, col_part_sum, shift, rank_rinv_x, rank_rinv_y, pos_thr, row_offset, col_offset, rank};
+    const int bn = g_force_bn == 256 || g_force_bn == 128 ? g_force_bn : (pick_bn(rows, cols, false) == 256 ? 256 : 128);
+    return dispatch_sim<LseBothPolicyT<true>>(x, y, dtype, rows, cols, dim, ldx, ldy, rinv_x, rinv_y, scale, pp, stream,
+                                              "sim_lse_both_rank", bn);
 }
 
 // LSE partial layout is fixed to the 128-column tile so the caller can size buffers up front.

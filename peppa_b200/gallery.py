@@ -27,7 +27,8 @@ returned under their own names.  With world_size == 1 no collective is issued.
 row log-sum-exp of the local strip is complete locally; the column log-sum-exp is a partial per rank
 (over its own rows) and is merged across ranks (all-gather of the [N] partials + pb2_lse_combine); the
 backward recomputes the strip, writes the fp16 gradient-matrix blocks and reduces dV like the hinge path.
-``with_recall=True`` adds recall@1..N of the same gallery (pb2_sim_rank on the local strip).
+``with_recall=True`` adds recall@1..N of the same gallery from the SAME pass as the loss statistics
+(pb2_sim_lse_both_rank; a separate pb2_sim_rank pass only when the logits have no usable bound).
 """
 from __future__ import annotations
 
@@ -328,14 +329,23 @@ class GalleryStep:
         cblocks = [(c0, c1) for (c0, c1, _) in self._column_blocks()]
         lse_row = lse_col = None
         bound = self.logit_bound if self.logit_bound is not None else ops.logit_bound(a_loc, v_full, inv_tau)
+        ranked = False
+        if self.with_recall:        # recall@1..N of the same gallery (cosine ranking, pig/metrics.py:23-40) on the local strip
+            ra, _ = ops.row_norms(a_loc)
+            rv_full, _ = ops.row_norms(v_full)
+            _, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv_full[r0g:r0g + nl].contiguous())
+            self.ranks.zero_()
         if bound <= ops.LSE_BOTH_MAX_BOUND:
-            # bounded logits: rows (complete locally) and columns (over THIS rank's rows) from one pass per block
+            # bounded logits: rows (complete locally) and columns (over THIS rank's rows) from one pass per block --
+            # and the rank counts of the recall from the same pass (pb2_sim_lse_both_rank)
             lse_row = torch.full((nl,), float("-inf"), dtype=torch.float32, device=dev)
             lse_col = torch.full((n,), float("-inf"), dtype=torch.float32, device=dev)
             for (r0, r1) in rblocks:
                 for (c0, c1) in cblocks:
+                    fused = (ra[r0:r1], rv_full[c0:c1], pos_thr[r0:r1], r0g + r0, c0, self.ranks[r0:r1]) if self.with_recall else None
                     ops.sim_lse_both(a_loc[r0:r1], v_full[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1],
-                                     lse_col=lse_col[c0:c1])
+                                     lse_col=lse_col[c0:c1], rank=fused)
+            ranked = self.with_recall
         else:
             for (c0, c1) in cblocks:      # x = A_loc V^T / tau: rows complete locally
                 lse_row = ops.sim_lse_rows(a_loc, v_full[c0:c1], scale=inv_tau, lse=lse_row)
@@ -355,13 +365,10 @@ class GalleryStep:
         mean_loc, den_loc = ops.milnce_loss(lse_row, lse_col[r0g:r0g + nl].contiguous(), diag)
         loss = mean_loc * float(nl)
         hits = None
-        if self.with_recall:        # recall@1..N of the same gallery (cosine ranking, pig/metrics.py:23-40) on the local strip
-            ra, _ = ops.row_norms(a_loc)
-            rv_full, _ = ops.row_norms(v_full)
-            _, pos_thr = ops.sim_diag(a_loc, v_loc, ra, rv_full[r0g:r0g + nl].contiguous())
-            self.ranks.zero_()
-            cols = torch.arange(r0g, r0g + nl, device=dev, dtype=torch.int64)
-            ops.sim_rank(a_loc, v_full, ra, rv_full, pos_thr, cols, rank=self.ranks)
+        if self.with_recall:
+            if not ranked:          # unbounded logits took the two-pass statistics: the ranking is its own pass
+                cols = torch.arange(r0g, r0g + nl, device=dev, dtype=torch.int64)
+                ops.sim_rank(a_loc, v_full, ra, rv_full, pos_thr, cols, rank=self.ranks)
             hits = (self.ranks.unsqueeze(0) < torch.arange(self.top_n + 1, device=dev, dtype=torch.int32).unsqueeze(1))
             hits = hits.sum(dim=1).to(torch.float32)
         if self.world > 1:

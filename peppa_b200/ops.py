@@ -287,11 +287,15 @@ def sim_lse_rows(x, y, rinv_x=None, rinv_y=None, scale=1.0, lse=None):
 LSE_BOTH_MAX_BOUND = 60.0 / 1.4426950408889634     # pb2_sim_lse_both refuses bound * log2(e) > 60
 
 
-def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None):
+def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None, rank=None):
     """Row AND column log-sum-exp of s = scale * <x_i, y_j> from one pass, for |s| <= ``bound``.
 
     Returns (lse_row [rows], lse_col [cols]); tensors passed in are log-added into (blocks of a larger matrix:
-    ``lse_row[r0:r1]`` over the column blocks, ``lse_col[c0:c1]`` over the row blocks)."""
+    ``lse_row[r0:r1]`` over the column blocks, ``lse_col[c0:c1]`` over the row blocks).
+
+    ``rank=(rank_rinv_x, rank_rinv_y, pos_thr, row_offset, col_offset, counts)`` fuses the ranking of ``sim_rank`` into
+    the same pass: ``counts[i]`` (int32, accumulated) += the columns other than the positive (global column
+    ``row_offset + i``, this block starting at ``col_offset``) whose cosine reaches ``pos_thr[i]``."""
     r, c = x.shape[0], y.shape[0]
     lib = _cabi.lib()
     prow = torch.empty(int(lib.pb2_sim_lse_parts(c)), r, dtype=torch.float32, device=x.device)
@@ -303,8 +307,15 @@ def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None,
         lse_col = torch.empty(c, dtype=torch.float32, device=x.device)
     with _on_device(x.device), _timed("sim_lse_both", 2.0 * r * c * x.shape[1], x.device):
         st = _stream(x.device)
-        check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0), y.stride(0),
-                                   float(scale), float(bound), _ptr(prow), _ptr(pcol), st), "sim_lse_both")
+        if rank is None:
+            check(lib.pb2_sim_lse_both(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y), x.stride(0),
+                                       y.stride(0), float(scale), float(bound), _ptr(prow), _ptr(pcol), st), "sim_lse_both")
+        else:
+            rrx, rry, pos_thr, row_off, col_off, counts = rank
+            check(lib.pb2_sim_lse_both_rank(_ptr(x), _ptr(y), _ptr(rinv_x), _ptr(rinv_y), r, c, x.shape[1], _mm_code(x, y),
+                                            x.stride(0), y.stride(0), float(scale), float(bound), _ptr(prow), _ptr(pcol),
+                                            _ptr(rrx), _ptr(rry), _ptr(pos_thr), int(row_off), int(col_off), _ptr(counts), st),
+                  "sim_lse_both_rank")
         check(lib.pb2_lse_merge_const(_ptr(prow), prow.shape[0], r, float(bound), _ptr(lse_row), int(acc_row), st),
               "lse_merge_const")
         check(lib.pb2_lse_merge_const(_ptr(pcol), pcol.shape[0], c, float(bound), _ptr(lse_col), int(acc_col), st),

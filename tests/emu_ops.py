@@ -99,9 +99,17 @@ def logit_bound(x, y, scale=1.0):
         * abs(float(scale)) * 1.0001
 
 
-def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None):
+def sim_lse_both(x, y, bound, rinv_x=None, rinv_y=None, scale=1.0, lse_row=None, lse_col=None, rank=None):
     s = (x.float() @ y.float().T) * scale
     assert float(s.abs().max()) <= bound
+    if rank is not None:        # the fused ranking (pb2_sim_lse_both_rank); sim_diag above keeps the distance as threshold
+        rrx, rry, pos_dist, row_off, col_off, counts = rank
+        cos = (x.float() @ y.float().T) * rrx[:, None] * rry[None, :]
+        closer = (1.0 - cos) < pos_dist[:, None]
+        rel = torch.arange(x.shape[0]) + (row_off - col_off)
+        ok = (rel >= 0) & (rel < y.shape[0])
+        closer[torch.nonzero(ok).flatten(), rel[ok]] = False          # the positive never counts against itself
+        counts += closer.sum(dim=1).to(counts.dtype)
     e = torch.exp2(s * 1.4426950408889634 - bound * 1.4426950408889634)      # the kernel's fixed-shift sums
     row = (bound * 1.4426950408889634 + torch.log2(e.sum(dim=1))) * 0.6931471805599453
     col = (bound * 1.4426950408889634 + torch.log2(e.sum(dim=0))) * 0.6931471805599453

@@ -33,9 +33,10 @@ def _worker_milnce(rank, world, port, n_local, block, outdir):
         V, A = _emb(n_local * world, 4.0)
         sl = slice(rank * n_local, (rank + 1) * n_local)
         step = GalleryStep(n_local, V.shape[1], rank=rank, world=world, device="cpu", block=block, backend=emu_ops,
-                           loss="milnce", temperature=0.5)
+                           loss="milnce", temperature=0.5, with_recall=True)
         out = step.run(A[sl].contiguous(), V[sl].contiguous())
-        torch.save((rank, out["loss"].item(), out["dA"].clone(), out["dV"].clone()), os.path.join(outdir, f"rank{rank}.pt"))
+        torch.save((rank, out["loss"].item(), out["dA"].clone(), out["dV"].clone(), out["ranks"].clone(), out["recall"].clone()),
+                   os.path.join(outdir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -128,6 +129,15 @@ def test_two_rank_milnce_gallery_matches_closed_form(n_local, block, tmp_path):
     gdV = torch.cat([r[3] for r in res]).double()
     assert (gdA - a.grad).abs().max() / a.grad.abs().max() < 2e-3      # fp16 gradient matrix of the emulation
     assert (gdV - v.grad).abs().max() / v.grad.abs().max() < 2e-3
+    # the ranking fused into the statistics pass (with_recall=True): cosine ranks of the whole gallery, row-sharded
+    cos = torch.nn.functional.normalize(A.float(), dim=1) @ torch.nn.functional.normalize(V.float(), dim=1).T
+    d = 1.0 - cos
+    closer = d < torch.diagonal(d)[:, None]
+    granks = closer.sum(dim=1).to(torch.int32)
+    near = ((d - torch.diagonal(d)[:, None]).abs() < 1e-6).sum(dim=1) > 1
+    got = torch.cat([r[4] for r in res])
+    assert bool(((got == granks) | near).all())
+    assert torch.equal(res[0][5], res[1][5]) and abs(res[0][5][10].item() - (got < 10).float().mean().item()) < 1e-6
 
 
 def test_column_block_walk_and_reduction_order():

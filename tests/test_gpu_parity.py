@@ -536,6 +536,41 @@ def test_sim_lse_both_against_fp64(pb, r, c, d, scale):
         ops.sim_lse_both(xb, yb, 100.0, scale=scale)                 # 2^(-2 * 144) would underflow: refused
 
 
+@pytest.mark.parametrize("n,scale", [(1000, 1.0), (4229, 1.0 / 0.07), (9000, 4.0)])
+def test_sim_lse_both_rank_fused(pb, n, scale):
+    """North-star kernels (a) + (b) from ONE pass over the scores: pb2_sim_lse_both_rank gives the log-sum-exp
+    statistics of pb2_sim_lse_both (bit for bit) and the rank counts of pb2_sim_rank (bit for bit), whole and in
+    blocks with row / column offsets; the ranks equal the oracle's outside near-ties."""
+    from oracle import pig_oracle as O
+    from peppa_b200 import ops
+    V, A = emb(n, 4.0)
+    vb, ab = V.cuda().bfloat16(), A.cuda().bfloat16()
+    rv, _ = ops.row_norms(vb)
+    ra, _ = ops.row_norms(ab)
+    _, thr = ops.sim_diag(ab, vb, ra, rv)
+    idx = torch.arange(n, device="cuda")
+    bound = ops.logit_bound(ab, vb, scale)
+    ref_rank = ops.sim_rank(ab, vb, ra, rv, thr, idx)
+    ref_lr, ref_lc = ops.sim_lse_both(ab, vb, bound, scale=scale)
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    lr, lc = ops.sim_lse_both(ab, vb, bound, scale=scale, rank=(ra, rv, thr, 0, 0, cnt))
+    assert torch.equal(lr, ref_lr) and torch.equal(lc, ref_lc)
+    assert torch.equal(cnt, ref_rank)
+    ranks, near = O.ranks_identity(V.bfloat16().float(), A.bfloat16().float())
+    assert bool(((cnt.cpu() == ranks) | near).all())
+    # blocks: the positive of local row i of a row block starting at r0 is global column r0 + i
+    cnt2 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ar = torch.full((n,), float("-inf"), device="cuda")
+    ac = torch.full((n,), float("-inf"), device="cuda")
+    rh, chf = n // 2 + 3, n // 3 + 1
+    for (r0, r1) in ((0, rh), (rh, n)):
+        for (c0, c1) in ((0, chf), (chf, n)):
+            ops.sim_lse_both(ab[r0:r1], vb[c0:c1], bound, scale=scale, lse_row=ar[r0:r1], lse_col=ac[c0:c1],
+                             rank=(ra[r0:r1], rv[c0:c1], thr[r0:r1], r0, c0, cnt2[r0:r1]))
+    assert torch.equal(cnt2, ref_rank)
+    assert (ar - ref_lr).abs().max() < 1e-5 and (ac - ref_lc).abs().max() < 1e-5
+
+
 def test_cluster_variants_match_independent_ctas(pb):
     """The similarity pass runs on CTA pairs (cta_group::2, one M = 256 MMA per two SMs) once every SM has a tile;
     independent CTAs and the multicast clusters are the measurement build's options.  All three are bit-identical for
@@ -801,7 +836,7 @@ def test_encoder_tail_column_split_variant(pb):
         w = (torch.randn(n_out, n_in, generator=g) / n_in ** 0.5).bfloat16().cuda()
         b = torch.randn(n_out, generator=g).cuda()
         o1, r1, m1 = ops.project_normalize(x, w, b)
-        for variant in (2, 3):       # 2: column split over a CTA pair; 3: phased halves (both measured, neither faster)
+        for variant in (2, 3, 4, 5, 6):  # 2: column split over a CTA pair; 3: phased halves; 4: sixteen epilogue warps; 5 / 6: resident x, 128 / 256-column phases
             if variant == 2 and n_out % 128 != 0:
                 continue
             with _cabi.measurement_library() as lib:

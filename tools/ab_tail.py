@@ -1,0 +1,30 @@
+"""A/B of the encoder tail's variants (pb2_debug_proj_variant of the measurement build) on 2^20 rows 512 -> 512:
+variants alternate in one process on one board, 50 launches back to back per figure."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from gpu_probe import _t  # noqa: E402
+from peppa_b200 import _cabi, ops  # noqa: E402
+
+lib = _cabi.use_measurement_library()
+variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "4"])]
+n = 1 << 20
+g = torch.Generator(device="cuda").manual_seed(1)
+x = torch.randn(n, 512, generator=g, device="cuda").bfloat16()
+w = (torch.randn(512, 512, generator=g, device="cuda") / 512 ** 0.5).bfloat16()
+b = torch.randn(512, generator=g, device="cuda") * 0.1
+ref = None
+for rep in range(3):
+    for v in variants:
+        lib.pb2_debug_proj_variant(v)
+        out, rinv, nrm = ops.project_normalize(x, w, b)
+        if ref is None:
+            ref = out.float()
+        dmax = (out.float() - ref).abs().max().item()
+        ms = _t(lambda: ops.project_normalize(x, w, b), iters=50, warm=5)
+        tf = 2.0 * n * 512 * 512 / ms / 1e9
+        print(f"variant {v}: {ms:.4f} ms = {tf:.0f} TF/s, {n * (1024 + 1024 + 8) / ms / 1e9:.2f} TB/s, max |out - variant {variants[0]}| {dmax:.2e}", flush=True)
+lib.pb2_debug_proj_variant(0)

@@ -109,6 +109,7 @@ class GalleryStep:
         self.block = block
         self.with_grad = with_grad
         self.with_recall = (loss == "hinge") if with_recall is None else bool(with_recall)
+        self.fuse_rank = True       # MIL-NCE: rank counts from the statistics pass (False: a separate pb2_sim_rank pass; tools/ A/B)
         dev, n, nl = self.device, self.n_total, n_local
         f32, i32 = torch.float32, torch.int32
         self.v_full = torch.empty(n, dim, dtype=torch.bfloat16, device=dev) if world > 1 else None
@@ -342,10 +343,11 @@ class GalleryStep:
             lse_col = torch.full((n,), float("-inf"), dtype=torch.float32, device=dev)
             for (r0, r1) in rblocks:
                 for (c0, c1) in cblocks:
-                    fused = (ra[r0:r1], rv_full[c0:c1], pos_thr[r0:r1], r0g + r0, c0, self.ranks[r0:r1]) if self.with_recall else None
+                    fused = ((ra[r0:r1], rv_full[c0:c1], pos_thr[r0:r1], r0g + r0, c0, self.ranks[r0:r1])
+                             if self.with_recall and self.fuse_rank else None)
                     ops.sim_lse_both(a_loc[r0:r1], v_full[c0:c1], bound, scale=inv_tau, lse_row=lse_row[r0:r1],
                                      lse_col=lse_col[c0:c1], rank=fused)
-            ranked = self.with_recall
+            ranked = self.with_recall and self.fuse_rank
         else:
             for (c0, c1) in cblocks:      # x = A_loc V^T / tau: rows complete locally
                 lse_row = ops.sim_lse_rows(a_loc, v_full[c0:c1], scale=inv_tau, lse=lse_row)

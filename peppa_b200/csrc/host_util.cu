@@ -104,8 +104,11 @@ int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t ro
     cuuint64_t strides[1] = {ld_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    // boxes with 128-byte rows use the 128-byte swizzle (every operand and output slab); a box with 64-byte rows (the
+    // encoder tail's half slabs) the 64-byte one: 16-byte piece index bits [4:5] ^= address bits [7:8]
+    const CUtensorMapSwizzle sw = (uint64_t)box_cols * (uint64_t)elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(PB2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     slot.key = key;
     slot.map = *map;

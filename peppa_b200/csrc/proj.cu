@@ -10,11 +10,15 @@
 //
 // One CTA owns 128 rows and ALL n_out <= 512 output features: the 128 x 512 fp32 accumulator is the whole
 // of TMEM, so the row norm is complete inside the CTA and y never exists in HBM.  CTAs work in pairs
-// (tcgen05 cta_group::2): x tiles [128 x 64] per CTA and W tiles [n_out x 64] split between the two CTAs
-// stream through a three-stage TMA ring; the leader's thread issues the MMAs (two of M = 256, N <= 256
-// per k-step); eight epilogue warps (thread == row, two column halves per TMEM lane quadrant) read the
-// accumulator twice -- sum of squares, then scale / round / stage -- with packed fp32 math, and the bf16
-// tile leaves through swizzled slabs and TMA stores.
+// (tcgen05 cta_group::2, one MMA of M = 256 per two SMs).  Two kernels:
+//   * resident-x phased kernel (n_in <= 512, n_out % 256 == 0 -- the reference's Linear(512, 512)): the pair's x tile
+//     stays in shared memory, W streams, and the accumulator is produced in two phases of 256 columns with their own
+//     full / empty barriers, so the two-pass epilogue of one phase runs under the MMAs of the other;
+//   * interleaved kernel (every other shape): x and W tiles stream through a three-stage TMA ring, two MMAs of N <= 256
+//     per k-step fill all of TMEM, then the epilogue runs (MMA and epilogue do not overlap).
+// Eight epilogue warps (thread == row, two column halves per TMEM lane quadrant) read the accumulator twice -- sum of
+// squares, then scale / round / stage -- with packed fp32 math; the bf16 tile leaves through 128-byte-swizzled slabs
+// and TMA stores.
 #include "common.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
@@ -345,7 +349,10 @@ constexpr int kR_OutBytes = kR_Epi * kSlabBytes;   // one staging slab per epilo
 constexpr int kR_Smem = kR_MaxKb * kXBytes + kR_WBytes + kR_OutBytes + kRedBytes + 512;
 static_assert(kR_Smem <= 227 * 1024, "resident encoder tail: shared memory");
 
-// kPW: output columns per phase = N of its MMAs (128 or 256)
+// kPW: output columns per phase = N of its MMAs.  256 is the product; 128 (four phases, more overlap on paper) is a
+// measurement option and 35 % SLOWER: an M = 256 pair MMA of N = 128 reads 6 KB of operands from each CTA's shared
+// memory per 64 tensor cycles (96 B/cycle, against 64 B/cycle at N = 256), which together with the TMA fill and the
+// epilogue's staging exceeds the 128 B/cycle a shared memory delivers -- the tensor pipe waits for its A operand.
 template <int kPW>
 __global__ void __launch_bounds__(kR_Threads, 1)
     project_normalize_resident_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -467,8 +474,11 @@ __global__ void __launch_bounds__(kR_Threads, 1)
             }
         }
     } else {
-        // ===== epilogue: thread == row; of a phase's kPW columns warps 0-3 take the first half (kSL 64-column slabs),
-        // warps 4-7 the second; the halves' per-row partial sums meet in shared memory in a fixed order (deterministic)
+        // ===== epilogue: thread == row; of a phase's kPW columns warps 0-3 take the first half (kSL 64-column slabs), warps
+        // 4-7 the second; the halves' per-row partial sums meet in shared memory in a fixed order (deterministic).  A
+        // slab's two chunks are loaded and waited for together; one 4 KiB staging slab per warp.  (Tried and dropped:
+        // chunk-wise register ping-pong with 2 KiB half slabs under the 64-byte swizzle, so that a store's read of the
+        // slab overlaps the next chunk's arithmetic -- correct, 8 % slower: twice the TMA stores.)
         const int quad = warp & 3, sub = warp >> 2;
         uint8_t* sl = out_stage + warp * kSlabBytes;
         const int r = quad * 32 + lane;
@@ -571,6 +581,7 @@ __global__ void __launch_bounds__(kR_Threads, 1)
                 if (a.norm) a.norm[row] = nrm;
             }
         }
+    
         if (lane == 0) tma_store_wait_all<0>();
         __syncwarp();
     }
@@ -1075,10 +1086,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 #endif  // PB2_MEASURE
 
-// pb2_debug_proj_variant (measurement build): 0 = the interleaved single-stage kernel (the product), 2 = the column-split
-// kernel (n_out % 128 == 0), 3 = the phased kernel.  Measured for 2^20 rows 512 -> 512: row-split 0.659 ms, column-split 0.681 ms (0.937 ms with a
-// release-arrive + cluster fence instead of st.async: MEMBAR.GPU + CCTL.IVALL twice per tile).  The overlap it buys
-// is spent on the two cross-CTA exchanges per tile, so the simpler kernel stays the default.
+// pb2_debug_proj_variant (measurement build): 0 = the product's choice (the resident-x phased kernel when n_in <= 512 and
+// n_out % 256 == 0, else the interleaved kernel), 1 = the interleaved kernel always, 2 = column split (n_out % 128 == 0),
+// 3 = phased halves with x streamed twice, 4 = interleaved with sixteen epilogue warps, 5 = resident x with 128-column
+// phases.  2^20 rows 512 -> 512, variants alternating on one board (tools/ab_tail.py): interleaved 0.62 ms alone /
+// 0.75 ms sustained, resident-256 0.56 / 0.61 ms, resident-128 0.74 / 0.88, sixteen warps 0.63 / 0.70, column split 0.68,
+// phased halves 0.645.
 PB2_KNOB g_variant = 0;
 
 }  // namespace proj
@@ -1148,30 +1161,35 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
         return check_launch("project_normalize");
     }
 #endif
-    if ((proj::g_variant == 5 || proj::g_variant == 6) && a.kblocks <= proj::kR_MaxKb) {  // x resident, phased accumulator
-        const int pw = proj::g_variant == 5 ? 128 : 256;
-        if (n_out % pw == 0) {
-            CUtensorMap twp;
-            rc = make_tmap_2d(&twp, w, 2, (uint64_t)n_out, (uint64_t)n_in, (uint64_t)ldw * 2, pw / 2, proj::BK);
+    // n_in <= 512 and whole phases: x resident in shared memory, accumulator produced in phases (the product for the
+    // reference's Linear(512, 512) tails); everything else takes the interleaved kernel
+    const int pw = proj::g_variant == 5 ? 128 : 256;
+    if ((proj::g_variant == 0 || proj::g_variant == 5) && a.kblocks <= proj::kR_MaxKb && n_out % pw == 0) {
+        CUtensorMap twp;
+        rc = make_tmap_2d(&twp, w, 2, (uint64_t)n_out, (uint64_t)n_in, (uint64_t)ldw * 2, pw / 2, proj::BK);
+        if (rc) return rc;
+        static PerDeviceOnce configured_r256;
+        if (pw == 256) {
+            rc = ensure_dynamic_smem(configured_r256, proj::project_normalize_resident_kernel<256>, proj::kR_Smem, "project_normalize");
             if (rc) return rc;
-            static PerDeviceOnce configured5, configured6;
-            if (pw == 128) {
-                rc = ensure_dynamic_smem(configured5, proj::project_normalize_resident_kernel<128>, proj::kR_Smem, "project_normalize");
-                if (rc) return rc;
-                rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<128>, (unsigned)grid, (unsigned)proj::kR_Threads,
-                                          (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
-                                "project_normalize launch");
-            } else {
-                rc = ensure_dynamic_smem(configured6, proj::project_normalize_resident_kernel<256>, proj::kR_Smem, "project_normalize");
-                if (rc) return rc;
-                rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<256>, (unsigned)grid, (unsigned)proj::kR_Threads,
-                                          (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
-                                "project_normalize launch");
-            }
-            if (rc) return rc;
-            return check_launch("project_normalize");
+            rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<256>, (unsigned)grid, (unsigned)proj::kR_Threads,
+                                      (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
+                            "project_normalize launch");
         }
+#ifdef PB2_MEASURE
+        else {
+            static PerDeviceOnce configured_r128;
+            rc = ensure_dynamic_smem(configured_r128, proj::project_normalize_resident_kernel<128>, proj::kR_Smem, "project_normalize");
+            if (rc) return rc;
+            rc = check_cuda(launch_ex(proj::project_normalize_resident_kernel<128>, (unsigned)grid, (unsigned)proj::kR_Threads,
+                                      (size_t)proj::kR_Smem, (cudaStream_t)stream, 2, tx, twp, to, a),
+                            "project_normalize launch");
+        }
+#endif
+        if (rc) return rc;
+        return check_launch("project_normalize");
     }
+#ifdef PB2_MEASURE
     if (proj::g_variant == 4) {  // sixteen epilogue warps (four per TMEM lane quadrant and scheduler)
         static PerDeviceOnce configured4;
         rc = ensure_dynamic_smem(configured4, proj::project_normalize_kernel<4>, proj::kSmem, "project_normalize");
@@ -1182,6 +1200,7 @@ extern "C" int pb2_project_normalize(const void* x, const void* w, const float* 
         if (rc) return rc;
         return check_launch("project_normalize");
     }
+#endif
     static PerDeviceOnce configured;
     rc = ensure_dynamic_smem(configured, proj::project_normalize_kernel<2>, proj::kSmem, "project_normalize");
     if (rc) return rc;

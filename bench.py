@@ -44,7 +44,7 @@ TOP_N = 10
 METRIC = {"gallery": "similarity pairs/sec (loss fwd+bwd + recall@1..10)", "train1024": "similarity pairs/sec (loss fwd+bwd)",
           "retrieval16k": "similarity pairs/sec (recall@1..10)", "triplets1m": "triplets/sec (triplet_accuracy)",
           "encoder_tail": "rows/sec (Linear 512x512 + L2-normalise + bf16 + rinv)",
-          "milnce64k": "similarity pairs/sec (MIL-NCE loss fwd+bwd)",
+          "milnce64k": "similarity pairs/sec (MIL-NCE loss fwd+bwd, recall@k)",
           "eval1467": "subset pairs/sec (500 x recall@1..10 over 100-clip subsets + 500 triplet resamples)"}
 
 
@@ -453,15 +453,16 @@ def bench_gallery(args, rank, world, device, sync, all_max):
 
 
 def bench_milnce64k(args, device, sync):
-    """North-star kernel (a): MIL-NCE (pig/loss.py:13-26) forward + backward over a 65536-clip gallery with a
-    temperature -- tensor-core logits with online row and column log-sum-exp (the N x N logits never reach HBM)
-    and the fused backward (recomputed logits -> fp16 gradient matrix -> two tensor-core GEMMs)."""
+    """North-star kernels (a) + (b): MIL-NCE (pig/loss.py:13-26) forward + backward and recall@1..10 over a 65536-clip
+    gallery with a temperature -- tensor-core logits with row and column log-sum-exp and the rank counts from ONE pass
+    (the N x N logits never reach HBM) and the fused backward (recomputed logits -> fp16 gradient matrix -> two
+    tensor-core GEMMs)."""
     import torch
     from peppa_b200.gallery import GalleryStep
     n = 65536
     a_dev, v_dev = synth_embeddings(n, 666, device)
     a_host, v_host = a_dev.cpu().pin_memory(), v_dev.cpu().pin_memory()
-    step = GalleryStep(n, DIM, device=device, loss="milnce", temperature=0.07)
+    step = GalleryStep(n, DIM, device=device, loss="milnce", temperature=0.07, with_recall=True)
     steps, warm = max(args.steps, 5), max(args.warmup, 3)
     m = measure(lambda: step.run(a_dev, v_dev), steps, warm, sync, device)
     a_in, v_in = torch.empty_like(a_dev), torch.empty_like(v_dev)
@@ -476,9 +477,11 @@ def bench_milnce64k(args, device, sync):
     return {
         "units": float(n) * float(n), "unit": "pairs/s", "ms": m["ms"], "ms_e2e": ms_e2e, "roofline": roof, "kernels": table,
         "launches": m["launches"], "clocks": m["clocks"], "h2d": 2 * n * DIM * 2, "d2h": 4, "flops_per_unit": 6.0 * DIM,
-        "scaling": "weak", "check": {"loss": m["out"]["loss"].item()}, "steps_used": steps,
-        "config": {"workload": "milnce64k (north-star kernel a): MILNCELoss fwd+bwd, 65536 x 65536 logits, temperature 0.07, online "
-                               "row + column log-sum-exp, fused backward", "gallery": n, "dim": DIM, "temperature": 0.07,
+        "scaling": "weak", "check": {"loss": m["out"]["loss"].item(), "recall_at_1": m["out"]["recall"][1].item(),
+                                     "recall_at_10": m["out"]["recall"][10].item()}, "steps_used": steps,
+        "config": {"workload": "milnce64k (north-star kernels a + b): MILNCELoss fwd+bwd + recall@1..10, 65536 x 65536 logits, temperature "
+                               "0.07, row + column log-sum-exp AND the rank counts from one pass, fused backward", "gallery": n, "dim": DIM,
+                   "temperature": 0.07,
                    "l2": "2 GiB gradient-matrix blocks and 128 MiB of embeddings per step exceed the 126 MB L2; no flush needed"}}
 
 

@@ -541,6 +541,10 @@ __global__ void __launch_bounds__(kR_Threads, 1)
                     qa = __ffma2_rn(r01, r01, qa);
                     qa = __ffma2_rn(r23, r23, qa);
                 }
+                if (cp == 0) {  // the slab's previous store must have read it (waited for after this chunk's arithmetic; before it: same time)
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
                 uint8_t* srow = sl + lane * 128;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -556,10 +560,8 @@ __global__ void __launch_bounds__(kR_Threads, 1)
                 tmem_ld_wait();
                 if (i % kSL == kSL - 1) tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (i % kSL == kSL - 1) mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + i / kSL), 0));  // the phase is in registers
-                    tma_store_wait_read<0>();                                                               // the slab's previous store has read it
-                }
+                if (lane == 0 && i % kSL == kSL - 1)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(acc_empty + i / kSL), 0));  // the phase is in registers
                 __syncwarp();
                 pass2(va, col, 0);
                 pass2(vb, col + 32, 1);

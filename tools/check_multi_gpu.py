@@ -124,8 +124,16 @@ def main():
             e_loss = abs(out["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item())
             e_da, e_dv = rel(out["dA"], ref["dA"][sl]), rel(out["dV"], ref["dV"][sl])
             same_ranks = torch.equal(out["ranks"], ref["ranks"][sl])
-            note(f"milnce dv_reduce={mode} vs world=1", e_loss < 1e-5 and e_da < 1e-3 and e_dv < 1e-3 and same_ranks,
-                 loss_rel=f"{e_loss:.2e}", dA_rel=f"{e_da:.2e}", dV_rel=f"{e_dv:.2e}", ranks_identical=same_ranks)
+            if "rank_pass" not in refs:     # the ranks of the fused statistics + rank pass against the separate rank pass
+                ra_, _ = ops.row_norms(A)
+                rv_, _ = ops.row_norms(V)
+                _, thr_ = ops.sim_diag(A, V, ra_, rv_)
+                refs["rank_pass"] = ops.sim_rank(A, V, ra_, rv_, thr_, torch.arange(n, device=dev))
+            same_pass = torch.equal(ref["ranks"], refs["rank_pass"])
+            note(f"milnce dv_reduce={mode} vs world=1 (recall ranks from the statistics pass)",
+                 e_loss < 1e-5 and e_da < 1e-3 and e_dv < 1e-3 and same_ranks and same_pass,
+                 loss_rel=f"{e_loss:.2e}", dA_rel=f"{e_da:.2e}", dV_rel=f"{e_dv:.2e}", ranks_identical=same_ranks,
+                 ranks_equal_separate_rank_pass=same_pass)
         del step, out
         gc.collect()
         dist.barrier()

@@ -151,6 +151,11 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 100.0, one, one, null) == 1
     assert lib.pb2_sim_lse_both(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, -1.0, one, one, null) == 1
     assert lib.pb2_sim_lse_both(one, one, null, null, 0, 8, 512, 0, 512, 512, 1.0, 1.0, null, null, null) == 0
+    # the same pass with the rank counts fused in: the threshold and count vectors are required, same bound rule
+    assert lib.pb2_sim_lse_both_rank(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 1.0, one, one, null, null, null, 0, 0, one, null) == 1
+    assert lib.pb2_sim_lse_both_rank(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 1.0, one, one, null, null, one, 0, 0, null, null) == 1
+    assert lib.pb2_sim_lse_both_rank(one, one, null, null, 8, 8, 512, 0, 512, 512, 1.0, 100.0, one, one, null, null, one, 0, 0, one, null) == 1
+    assert lib.pb2_sim_lse_both_rank(one, one, null, null, 0, 8, 512, 0, 512, 512, 1.0, 1.0, null, null, null, null, null, 0, 0, null, null) == 0
     # operand dtypes: the tensor-core kernels take bf16 / fp16 (fp32 rows go through pb2_split_f16), the row-wise
     # kernels bf16 / fp16 / fp32; anything else is refused before a launch
     assert lib.pb2_sim_rank(one, one, null, null, one, one, 8, 8, 0, 512, 2, 512, 512, one, null) == 1

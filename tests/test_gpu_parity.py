@@ -506,6 +506,30 @@ def test_gallery_step_milnce_single_gpu(pb, n, block):
     assert rel_err(out["loss"].cpu(), O.milnce_loss(V, A)) < TOL     # the loss itself is symmetric
 
 
+@pytest.mark.parametrize("n,block,tau", [(1100, 384, 0.5), (5000, 2048, 0.07), (4096, 32768, 0.07)])
+def test_gallery_step_milnce_with_recall(pb, n, block, tau):
+    """GalleryStep(loss='milnce', with_recall=True): the recall ranks come out of the statistics pass
+    (pb2_sim_lse_both_rank, block by block with row / column offsets).  Ranks equal the oracle's outside near-ties and the
+    separate rank pass bit for bit; loss and gradients are those of the step without recall, bit for bit."""
+    from peppa_b200.gallery import GalleryStep
+    V, A = emb(n, 4.0)
+    ab, vb = A.cuda().bfloat16(), V.cuda().bfloat16()
+    fused = GalleryStep(n, 512, block=block, loss="milnce", temperature=tau, with_recall=True).run(ab, vb)
+    split = GalleryStep(n, 512, block=block, loss="milnce", temperature=tau, with_recall=True)
+    split.fuse_rank = False
+    split = split.run(ab, vb)
+    plain = GalleryStep(n, 512, block=block, loss="milnce", temperature=tau).run(ab, vb)
+    assert torch.equal(fused["ranks"], split["ranks"]) and torch.equal(fused["recall"], split["recall"])
+    assert torch.equal(fused["loss"], plain["loss"]) and torch.equal(fused["dA"], plain["dA"]) and torch.equal(fused["dV"], plain["dV"])
+    ranks, near = O.ranks_identity(V, A)          # candidates = video (columns), references = audio (rows)
+    got = fused["ranks"].cpu()
+    assert bool(((got == ranks) | near).all())
+    for k in (1, 5, 10):
+        exact = (ranks < k).float().mean().item()
+        assert abs(fused["recall"][k].item() - exact) <= near.float().mean().item() + 1e-6
+    assert plain["recall"] is None and fused["recall"][0].item() == 0.0
+
+
 @pytest.mark.parametrize("r,c,d,scale", [(1000, 1500, 512, 1.0), (300, 70, 64, 14.0), (4096, 4100, 256, 5.0), (129, 33, 512, 1.0 / 0.07)])
 def test_sim_lse_both_against_fp64(pb, r, c, d, scale):
     """One pass over the logits gives both directions of the log-sum-exp (pig/loss.py:23-25: x and x.permute(1,0,2)):
@@ -797,7 +821,10 @@ def test_byte_gradient_matrix_equals_fp16_path(pb):
 
 
 @pytest.mark.parametrize("rows,n_in,n_out,bias", [(1000, 512, 512, True), (5, 512, 512, False), (300, 28, 512, True),
-                                                  (4096, 768, 256, True), (129, 512, 64, True), (2000, 1024, 384, True)])
+                                                  (4096, 768, 256, True), (129, 512, 64, True), (2000, 1024, 384, True),
+                                                  # several 256-row tiles per CTA pair (the resident-x kernel's barrier
+                                                  # phases across tiles; the interleaved kernel's for n_in > 512)
+                                                  (70001, 512, 512, True), (40000, 256, 256, False), (50000, 768, 512, True)])
 def test_encoder_tail_project_normalize(pb, rows, n_in, n_out, bias):
     """nn.Linear + F.normalize of the reference encoders (pig/models.py:96-109, :130-150) as one
     tcgen05 kernel; bf16 operands, fp32 accumulate, bf16 output.  Tolerances: the output is the bf16 rounding of

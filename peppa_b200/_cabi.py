@@ -111,6 +111,29 @@ def _bind(handle, table):
     return handle
 
 
+FAST_PATH = os.path.join(_HERE, "csrc", "_pb2_fast.so")
+_fast = None
+
+
+def fast():
+    """The C++ autograd glue over the same C ABI (csrc/torch_fast.cpp) for the launch-bound training step, or None:
+    not built (older checkouts), the measurement build is active (tools / variant tests route through ctypes), or
+    PEPPA_B200_NO_FAST=1.  Both paths end in pb2_hinge_step / pb2_scale_pair of the product library."""
+    global _fast
+    if _fast is None:
+        _fast = False
+        if os.environ.get("PEPPA_B200_NO_FAST") != "1" and os.path.exists(FAST_PATH):
+            import importlib.util
+            lib()                           # the product library first: the extension's DT_NEEDED resolves to the same file
+            spec = importlib.util.spec_from_file_location("_pb2_fast", FAST_PATH)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _fast = mod
+    if _fast is False or (_measure is not None and _lib is _measure):
+        return None
+    return _fast
+
+
 _measure = None
 
 

@@ -40,11 +40,13 @@ def _nvcc() -> str:
 
 
 def _digest(paths, extra=()) -> str:
+    # what the object depends on, not where the checkout lives: the GPU box runs a copy under another path, and its
+    # prebuilt objects must count as current there
     h = hashlib.sha256()
-    h.update(" ".join(list(NVCC_FLAGS) + list(extra)).encode())
-    for p in sorted(paths):
+    h.update(" ".join([f for f in list(NVCC_FLAGS) + list(extra) if not os.path.isabs(f)]).encode())
+    for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())
             h.update(f.read())
     return h.hexdigest()
 
@@ -80,6 +82,46 @@ def _link(lib: str, objs) -> None:
         os.replace(tmp, lib)        # atomic: another rank may be dlopen()ing the old file
 
 
+FAST_SRC = os.path.join(CSRC, "torch_fast.cpp")
+FAST_LIB = os.path.join(CSRC, "_pb2_fast.so")
+
+
+def build_fast(verbose: bool = False) -> str:
+    """The C++ autograd glue for the launch-bound training step (csrc/torch_fast.cpp): g++ against torch's headers and
+    the product library (no CUDA code in it).  Rebuilt when its source, the header or torch's version changes."""
+    import sysconfig
+
+    import torch
+    tdir = os.path.dirname(torch.__file__)
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_pb2_fast",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-I", os.path.join(tdir, "include"), "-I", os.path.join(tdir, "include", "torch", "csrc", "api", "include"),
+           "-I", sysconfig.get_paths()["include"], "-I", "/usr/local/cuda/include", "-I", INCLUDE, FAST_SRC, "-o", FAST_LIB + ".tmp",
+           "-L", os.path.join(tdir, "lib"), "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+           "-L", CSRC, "-lpeppa_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.join(tdir, "lib")]
+    # the stamp names what the binary depends on, not where the checkout lives (the GPU box runs a copy elsewhere)
+    h = hashlib.sha256(f"{torch.__version__} abi{int(torch._C._GLIBCXX_USE_CXX11_ABI)} py{sys.version_info[:2]} -O2 c++17".encode())
+    for p_ in (FAST_SRC, os.path.join(INCLUDE, "peppa_b200.h")):
+        with open(p_, "rb") as f:
+            h.update(f.read())
+    stamp, want = FAST_LIB + ".sha", h.hexdigest()
+    if os.path.exists(FAST_LIB) and os.path.exists(stamp) and open(stamp).read() == want:
+        return FAST_LIB
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(OBJ, "torch_fast.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on torch_fast.cpp")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    os.replace(FAST_LIB + ".tmp", FAST_LIB)
+    with open(stamp, "w") as f:
+        f.write(want)
+    return FAST_LIB
+
+
 def build(verbose: bool = False, measure: bool = True) -> str:
     """Compile (only what changed: per-source hashes) and link; returns the product library's path."""
     jobs = [(s, OBJ, ()) for s in LIB_SOURCES]
@@ -92,6 +134,7 @@ def build(verbose: bool = False, measure: bool = True) -> str:
     _link(LIB, objs[:len(LIB_SOURCES)])
     if measure:
         _link(LIB_MEASURE, objs[len(LIB_SOURCES):])
+    build_fast(verbose)
     return LIB
 
 

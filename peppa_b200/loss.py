@@ -11,12 +11,13 @@ from __future__ import annotations
 import torch
 import torch.nn
 
-from . import ops
+from . import _cabi, ops
 from .util import cosine_matrix  # noqa: F401  (pig/loss.py re-exports its own copy, :51-55)
 
 # Largest gradient-matrix block kept in HBM at once (rows x cols fp16).  Bigger problems are
 # walked block by block with accumulating gradient GEMMs.
 _MAX_BLOCK = 32768
+_FAST_DTYPES = (torch.bfloat16, torch.float16, torch.float32)
 # MIL-NCE problems from this many logits on take the one-pass row + column log-sum-exp (pb2_sim_lse_both)
 _LSE_BOTH_MIN_PAIRS = 1 << 26
 
@@ -234,6 +235,16 @@ class TripletLoss(torch.nn.Module):
            V: Tensor of embeddings (e.g. video)
            A: Tensor of embeddings (e.g. audio)
         """
+        # the batch-~1k training step is host bound: inputs that need no conversion go through the C++ autograd node
+        # (csrc/torch_fast.cpp: the same pb2_hinge_step / pb2_scale_pair calls without the Python round trips)
+        if (V.is_cuda and A.is_cuda and V.dim() == 2 and V.shape == A.shape and V.dtype == A.dtype and V.device == A.device
+                and V.dtype in _FAST_DTYPES and V.shape[1] % 64 == 0 and 0 < V.shape[0] <= _MAX_BLOCK
+                and V.stride(1) == 1 and A.stride(1) == 1 and V.stride(0) % 8 == 0 and A.stride(0) % 8 == 0
+                and (V.requires_grad or A.requires_grad) and torch.is_grad_enabled() and ops.EVENT_LOG is None
+                and V.data_ptr() % 16 == 0 and A.data_ptr() % 16 == 0):
+            fast = _cabi.fast()
+            if fast is not None:
+                return fast.triplet_loss(V, A, float(self.margin), ops.known_rinv(V, V), ops.known_rinv(A, A))
         return _HingeFn.apply(V, A, float(self.margin))
 
 

@@ -1085,3 +1085,54 @@ def test_bench_line_contract(pb):
     assert rec["e2e"]["h2d_bytes_per_step"] > 0 and rec["e2e"]["d2h_bytes_per_step"] > 0 and rec["e2e"]["value"] < rec["value"]
     assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
     assert set(rec["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_triplet_loss_cxx_autograd_node_matches_ctypes_path(pb, dtype):
+    """The launch-bound training step (BASELINE config 2) goes through csrc/torch_fast.cpp when the inputs need no
+    conversion: a C++ autograd node around the SAME pb2_hinge_step / pb2_scale_pair calls.  Loss and gradients are bit
+    for bit those of the Python autograd.Function; grad_output is applied in fp32 before the rounding; the node works
+    under CUDA graph capture; inputs that need a conversion still take the Python path."""
+    from peppa_b200 import _cabi
+    from peppa_b200.loss import _HingeFn
+    assert _cabi.fast() is not None, "csrc/_pb2_fast.so not built / not loadable"
+    V, A = emb(1024, 4.0)
+    for scale in (1.0, 65536.0):
+        v1, a1 = V.cuda().to(dtype).requires_grad_(True), A.cuda().to(dtype).requires_grad_(True)
+        v2, a2 = V.cuda().to(dtype).requires_grad_(True), A.cuda().to(dtype).requires_grad_(True)
+        l1 = pb.loss.TripletLoss(0.2)(v1, a1)
+        assert "HingeStepFn" in l1.grad_fn.name()                            # the C++ node
+        (l1 * scale).backward()
+        l2 = _HingeFn.apply(v2, a2, 0.2)
+        (l2 * scale).backward()
+        assert torch.equal(l1, l2) and torch.equal(v1.grad, v2.grad) and torch.equal(a1.grad, a2.grad)
+        assert v1.grad.dtype == dtype and a1.grad.dtype == dtype
+    ref_loss, ref_dv, ref_da = O.hinge_loss_and_grads(v1.detach().float().cpu(), a1.detach().float().cpu(), 0.2)
+    assert rel_err(l1.detach().cpu(), ref_loss) < TOL
+    # conversions needed -> the Python path (zero-padded feature dimension; non-contiguous rows)
+    vp, ap = V[:, :500].cuda().to(dtype).requires_grad_(True), A[:, :500].cuda().to(dtype).requires_grad_(True)
+    assert "HingeStepFn" not in pb.loss.TripletLoss(0.2)(vp, ap).grad_fn.name()
+    # CUDA graph capture of forward + backward through the C++ node
+    vs, as_ = V.cuda().to(dtype).requires_grad_(True), A.cuda().to(dtype).requires_grad_(True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            vs.grad = as_.grad = None
+            pb.loss.TripletLoss(0.2)(vs, as_).backward()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    vs.grad = as_.grad = None
+    with torch.cuda.graph(g):
+        lg = pb.loss.TripletLoss(0.2)(vs, as_)
+        lg.backward()
+    g.replay()
+    torch.cuda.synchronize()
+    gv, ga = _grad_of(pb, V, A, dtype)
+    assert torch.equal(lg, l1) and torch.equal(vs.grad, gv) and torch.equal(as_.grad, ga)
+
+
+def _grad_of(pb, V, A, dtype):
+    v, a = V.cuda().to(dtype).requires_grad_(True), A.cuda().to(dtype).requires_grad_(True)
+    pb.loss.TripletLoss(0.2)(v, a).backward()
+    return v.grad, a.grad

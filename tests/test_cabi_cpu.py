@@ -291,3 +291,17 @@ print("ok")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-3000:]
     assert inspect.isfunction(__import__("peppa_b200").install)
+
+
+def test_cxx_autograd_glue_loads_and_refuses_cpu_tensors():
+    """csrc/torch_fast.cpp (the training step's autograd node in C++) is built in-tree, loads without a GPU and -- like
+    every other path -- has no CPU fallback: CPU tensors are refused, not computed."""
+    import os
+
+    from peppa_b200 import loss
+    fast = _cabi.fast()
+    assert fast is not None and os.path.exists(_cabi.FAST_PATH)
+    with pytest.raises(RuntimeError, match="one CUDA device"):
+        fast.triplet_loss(torch.zeros(4, 64), torch.zeros(4, 64), 0.2)
+    with pytest.raises(RuntimeError):          # the public module on CPU tensors: the ctypes path's refusal
+        loss.TripletLoss(0.2)(torch.zeros(4, 64, requires_grad=True), torch.zeros(4, 64))

@@ -125,10 +125,15 @@ def fast():
         if os.environ.get("PEPPA_B200_NO_FAST") != "1" and os.path.exists(FAST_PATH):
             import importlib.util
             lib()                           # the product library first: the extension's DT_NEEDED resolves to the same file
-            spec = importlib.util.spec_from_file_location("_pb2_fast", FAST_PATH)
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            _fast = mod
+            try:
+                spec = importlib.util.spec_from_file_location("_pb2_fast", FAST_PATH)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _fast = mod
+            except (ImportError, OSError) as e:     # e.g. built against another torch: the ctypes path does the same work
+                import warnings
+                warnings.warn(f"peppa_b200: {FAST_PATH} does not load ({e}); TripletLoss keeps the ctypes path "
+                              "(rebuild with `python -m peppa_b200.build`)")
     if _fast is False or (_measure is not None and _lib is _measure):
         return None
     return _fast

@@ -976,20 +976,25 @@ struct uses_stage<P, typename std::enable_if<P::kUsesStage>::type> : std::true_t
 
 template <int BN, int G, bool kOut, int kCtas>
 struct SimSmem {
-    static constexpr int kStageBytes = (BM + (kCtas == 2 ? BN / 2 : BN)) * BK * 2;  // a pair CTA stages half of Y
+    // kCtas == 4: CTA pairs whose X strip (128 rows x dim <= 512: eight k-block slots of 16 KiB) STAYS in shared memory
+    // while the pair walks a run of column tiles; only Y streams through the ring
+    static constexpr bool kResX = kCtas == 4;
+    static constexpr int kXSlots = kResX ? 8 : 0;
+    static constexpr int kXBytes = BM * BK * 2;
+    static constexpr int kStageBytes = kResX ? (BN / 2) * BK * 2 : (BM + (kCtas == 2 ? BN / 2 : BN)) * BK * 2;  // a pair CTA stages half of Y
     // shared memory not spent on staging goes to the TMA pipeline: bytes in flight bound the MMA rate
-    static constexpr int kOutBufs = G >= 3 ? 1 : 2;  // G >= 3: one 64-column slab per warp and tile
+    static constexpr int kOutBufs = (G >= 3 || kResX) ? 1 : 2;  // G >= 3: one 64-column slab per warp and tile
     static constexpr int kOutBytes = kOut ? 4 * G * kOutBufs * kOutSlabBytes : 0;
     static constexpr int kColVecBytes = 2 * kMaxColVecs * kColVecStride * 4 + 2 * kMaxRowVecs * BM * 4;  // col + row vectors
     static constexpr int kBarBytes = 512;
-    static constexpr int kBudget = 227 * 1024 - kOutBytes - kColVecBytes - kBarBytes;
+    static constexpr int kBudget = 227 * 1024 - kOutBytes - kColVecBytes - kBarBytes - kXSlots * kXBytes;
     static constexpr int kFit = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
 #ifdef PB2_STAGE_CAP  // measurement builds: how much of the tile period is TMA bytes in flight?
     static constexpr int kStages = kFit > PB2_STAGE_CAP ? PB2_STAGE_CAP : kFit;
 #else
     static constexpr int kStages = kFit;
 #endif
-    static constexpr int kTileBytes = kStages * kStageBytes;
+    static constexpr int kTileBytes = kXSlots * kXBytes + kStages * kStageBytes;
     static constexpr int kTotal = kTileBytes + kOutBytes + kColVecBytes + kBarBytes;
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
@@ -1019,7 +1024,9 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint64_t* vec_full = acc_empty + 2;          // [2]
     uint64_t* vec_empty = vec_full + 2;          // [2] the epilogue is done with a vector buffer (CTA-local)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vec_empty + 2);
+    uint64_t* x_full = vec_empty + 2;            // [kXSlots] resident X strip (kCtas == 4)
+    uint64_t* x_empty = x_full + L::kXSlots;     // [kXSlots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + L::kXSlots);
     float* rowvec = colvec + 2 * kMaxColVecs * kColVecStride;  // [acc stage][vec][128]
     float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [kMaxEpiWarps]
 
@@ -1027,10 +1034,25 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     const int lane = threadIdx.x & 31;
     constexpr int kLoaderWarp = 4 * G, kMmaWarp = 4 * G + 1, kTmaWarp = 4 * G + 2;
     constexpr int kCluster = kCtas >= 2 ? 2 : 1;    // CTAs per cluster
-    constexpr bool kSharedMma = kCtas == 2;         // one M = 256 MMA per pair
+    constexpr bool kSharedMma = kCtas == 2 || kCtas == 4;  // one M = 256 MMA per pair
     constexpr bool kMcast = kCtas == 3;             // independent MMAs, Y tile multicast
+    constexpr bool kResX = L::kResX;                // pairs with a resident X strip
     const uint32_t crank = kCluster == 2 ? cluster_ctarank() : 0u;  // pairs: 0 = leader (issues the MMAs)
     const int64_t unit0 = blockIdx.x / kCluster, n_units = gridDim.x / kCluster;  // tiles are dealt to CTAs / clusters
+    // Tile walk.  Default: tile unit0, unit0 + n_units, ... of the banded order (concurrent CTAs share operands in L2).
+    // Resident X: each pair takes ONE contiguous range of the row-block-major order, so that consecutive tiles keep
+    // their row block (the X strip is loaded two or three times per launch instead of once per tile).
+    const int64_t t_first = kResX ? (unit0 * c.n_tiles) / n_units : unit0;
+    const int64_t t_last = kResX ? ((unit0 + 1) * c.n_tiles) / n_units : c.n_tiles;
+    const int64_t t_step = kResX ? 1 : n_units;
+    auto coords = [&](int64_t t, int& rb, int& cb) {
+        if (kResX) {
+            rb = (int)(t / c.n_cb);
+            cb = (int)(t - (int64_t)rb * c.n_cb);
+        } else {
+            tile_coords(t, c.n_rb, c.n_cb, rb, cb);
+        }
+    };
 
     if (warp == kTmaWarp && lane == 0) {
         tma_prefetch_desc(&tm_x);
@@ -1047,6 +1069,10 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             mbar_init(acc_empty + a, kEpiWarps * (kSharedMma ? 2 : 1));  // a pair leader's collects both CTAs' epilogues
             mbar_init(vec_full + a, 1);
             mbar_init(vec_empty + a, kEpiWarps);
+        }
+        for (int s = 0; s < L::kXSlots; ++s) {
+            mbar_init(x_full + s, 1);
+            mbar_init(x_empty + s, 1);
         }
         fence_mbar_init();
     }
@@ -1067,11 +1093,30 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = unit0; t < c.n_tiles; t += n_units) {
+            [[maybe_unused]] uint32_t x_gen = 0;  // resident X: strips loaded so far
+            for (int64_t t = t_first; t < t_last; t += t_step) {
                 int rb, cb;
-                tile_coords(t, c.n_rb, c.n_cb, rb, cb);
+                coords(t, rb, cb);
                 const int xrow = (rb * kCluster + (int)crank) * BM, yrow = cb * BN + (int)crank * (BN / kCluster);
+                [[maybe_unused]] const bool new_x = kResX && (t == t_first || cb == 0);
                 for (int kb = 0; kb < c.kblocks; ++kb) {
+                    if constexpr (kResX) {
+                        if (new_x) {  // slot kb is free once the previous strip's last tile has consumed it
+                            mbar_wait(x_empty + kb, (x_gen & 1u) ^ 1u);
+                            if (crank == 0) mbar_arrive_expect_tx(x_full + kb, 2 * L::kXBytes);
+                            tma_load_2d_pair(smem + kb * L::kXBytes, &tm_x, mapa_u32(smem_u32(x_full + kb), 0), kb * BK, xrow,
+                                             PB2_OPERAND_POLICY);
+                        }
+                        mbar_wait(empty + stage, phase ^ 1);
+                        if (crank == 0) mbar_arrive_expect_tx(full + stage, 2 * L::kStageBytes);
+                        tma_load_2d_pair(smem + L::kXSlots * L::kXBytes + stage * L::kStageBytes, &tm_y,
+                                         mapa_u32(smem_u32(full + stage), 0), kb * BK, yrow, PB2_OPERAND_POLICY);
+                        if (++stage == L::kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sx = smem + stage * L::kStageBytes;
                     uint8_t* sy = sx + BM * BK * 2;
@@ -1095,6 +1140,7 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
                         phase ^= 1;
                     }
                 }
+                if (kResX && new_x) ++x_gen;
             }
         }
     } else if (warp == kMmaWarp) {
@@ -1106,34 +1152,51 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
             const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 1024);
             const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
             constexpr uint32_t kStageLo = L::kStageBytes >> 4, kYLo = (BM * BK * 2) >> 4, kKLo = (UK * 2) >> 4;
+            [[maybe_unused]] constexpr uint32_t kXLo = L::kXBytes >> 4, kRingLo = (L::kXSlots * L::kXBytes) >> 4;
             int stage = 0;
-            uint32_t phase = 0, lo = lo0;
+            uint32_t phase = 0, lo = lo0 + (kResX ? kRingLo : 0u);
+            [[maybe_unused]] uint32_t x_gen = 0;
             int64_t it = 0;
-            for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
+            for (int64_t t = t_first; t < t_last; t += t_step, ++it) {
                 const int as = (int)(it & 1);
+                [[maybe_unused]] bool new_x = false, last_x = false;
+                if constexpr (kResX) {
+                    const int64_t cb = t % c.n_cb;
+                    new_x = t == t_first || cb == 0;
+                    last_x = t + 1 == t_last || cb + 1 == c.n_cb;
+                }
                 mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < c.kblocks; ++kb) {
+                    if constexpr (kResX) {
+                        if (new_x) mbar_wait(x_full + kb, x_gen & 1u);
+                    }
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        if (kSharedMma) umma_f16_pair_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, desc_hi, idesc, acc);
+                        if constexpr (kResX)
+                            umma_f16_pair_lohi(d_tmem, lo0 + kb * kXLo + k * kKLo, lo + k * kKLo, desc_hi, desc_hi, idesc, acc);
+                        else if (kSharedMma) umma_f16_pair_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, desc_hi, idesc, acc);
                         else umma_f16_lohi(d_tmem, lo + k * kKLo, lo + kYLo + k * kKLo, desc_hi, idesc, acc);
                     }
                     // stage reusable (in both CTAs of a cluster) once these MMAs have read it
                     if (kSharedMma) umma_commit_pair(empty + stage);
                     else if (kMcast) umma_commit_mcast(empty + stage, (uint16_t)3);
                     else umma_commit(empty + stage);
+                    if constexpr (kResX) {
+                        if (last_x) umma_commit_pair(x_empty + kb);  // the strip's last tile: slot kb may take the next strip
+                    }
                     lo += kStageLo;
                     if (++stage == L::kStages) {
                         stage = 0;
                         phase ^= 1;
-                        lo = lo0;
+                        lo = lo0 + (kResX ? kRingLo : 0u);
                     }
                 }
+                if (kResX && last_x) ++x_gen;
                 if (kSharedMma) umma_commit_pair(acc_full + as);  // accumulator complete -> both epilogues
                 else umma_commit(acc_full + as);
             }
@@ -1141,10 +1204,10 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     } else if (warp == kLoaderWarp) {
         // ============================ vector loader: per-column and per-row epilogue operands -> smem
         int64_t it = 0;
-        for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
+        for (int64_t t = t_first; t < t_last; t += t_step, ++it) {
             const int as = (int)(it & 1);
             int rb, cb;
-            tile_coords(t, c.n_rb, c.n_cb, rb, cb);
+            coords(t, rb, cb);
             const int64_t row0 = ((int64_t)rb * kCluster + crank) * BM, col0 = (int64_t)cb * BN;
             mbar_wait(vec_empty + as, (uint32_t)((it >> 1) & 1) ^ 1);  // the epilogue is done with this buffer
             float* cv = colvec + as * (kMaxColVecs * kColVecStride);
@@ -1226,10 +1289,10 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
         os.skip = c.diag_only < 0 ? -c.diag_only : 0;
 #endif
         int64_t it = 0;
-        for (int64_t t = unit0; t < c.n_tiles; t += n_units, ++it) {
+        for (int64_t t = t_first; t < t_last; t += t_step, ++it) {
             const int as = (int)(it & 1);
             int rb, cb;
-            tile_coords(t, c.n_rb, c.n_cb, rb, cb);
+            coords(t, rb, cb);
             TileCtx ctx;
             ctx.row0 = ((int64_t)rb * kCluster + crank) * BM;
             ctx.col0 = (int64_t)cb * BN;
@@ -1403,11 +1466,25 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
 #ifdef PB2_MEASURE
     const bool mcast = bn == 256 && cluster_mode == 2;
 #endif
+#ifdef PB2_MEASURE
+    // 3 = CTA pairs with a resident X strip (dim <= 512; built for the one-byte-G hinge pass and the rank pass): the pair
+    // takes a contiguous run of column tiles of ONE row block and keeps that block's X strip in shared memory, so only Y
+    // streams (half of the pass's L2 -> SM operand traffic).  Measured, modes alternating on one board: hinge + rank +
+    // one-byte G on a 32768^2 block alone 1.15 -> 1.11 ms sustained (-3 %), the rank pass 0.80 -> 0.82 ms (+3 %: its ring
+    // is five 16 KiB stages of Y instead of four of X + Y) -- and INSIDE the 262144-clip gallery step 164.9-165.2 ->
+    // 163.8-164.4 ms on one box, 162.8-162.9 -> 162.8-163.1 ms on the next: nothing, the step sits at the power cap
+    // (profiles/r2b_ab_gallery_resx.txt).  By the rule of section 4.1 (a change is kept when the step that contains it
+    // moves) plain pairs stay the product; the variant stays bit-identical and selectable here.
+    const bool resx = bn == 256 && dim / BK <= 8 && g_sim_pair == 3;
+#endif
     if constexpr (std::is_same<Policy, DiagPolicy>::value) {
         return PB2_SIM(128, 2, 1);
     } else if constexpr (Policy::kByteG) {
 #ifdef PB2_MEASURE  // tools/ab_gallery_pair.py
         if (mcast) return PB2_SIM(256, 2, 3);
+#endif
+#ifdef PB2_MEASURE
+        if (resx) return PB2_SIM(256, 2, 4);
 #endif
         if (pair) return PB2_SIM(256, 2, 2);
         return PB2_SIM(256, 2, 1);  // a warp's 128 columns are one slab of bytes: 256-wide tiles only
@@ -1426,6 +1503,10 @@ static int dispatch_sim(const void* x, const void* y, int dtype, int64_t rows, i
     } else {
 #ifdef PB2_MEASURE
         if (mcast) return PB2_SIM(256, 2, 3);
+        if constexpr (std::is_same<Policy, RankPolicy>::value) {
+            if (resx) return PB2_SIM(256, 2, 4);
+        }
+        if (cluster_mode == 3) return PB2_SIM(256, 2, 2);  // policies without a resident-X build: plain pairs
 #endif
         if (pair) return PB2_SIM(256, 2, 2);
         if (bn == 256) return PB2_SIM(256, 2, 1);

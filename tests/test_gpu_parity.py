@@ -597,7 +597,8 @@ def test_sim_lse_both_rank_fused(pb, n, scale):
 
 def test_cluster_variants_match_independent_ctas(pb):
     """The similarity pass runs on CTA pairs (cta_group::2, one M = 256 MMA per two SMs) once every SM has a tile;
-    independent CTAs and the multicast clusters are the measurement build's options.  All three are bit-identical for
+    independent CTAs, the multicast clusters and pairs with a resident X strip (mode 3: one-byte hinge pass and rank
+    pass) are the measurement build's options.  All four are bit-identical for
     every policy -- rank, both log-sum-exp passes, the MIL-NCE gradient matrix, the stored score matrix, the hinge pass
     with the fp16 and the one-byte gradient matrix -- also with an odd trailing row block."""
     from peppa_b200 import _cabi, ops
@@ -629,7 +630,7 @@ def test_cluster_variants_match_independent_ctas(pb):
     res = {}
     with _cabi.measurement_library() as lib:      # the selectors exist in the measurement build only
         try:
-            for mode in (0, 2, 1):
+            for mode in (0, 2, 3, 1):              # 3: pairs with a resident X strip (one-byte hinge pass, rank pass)
                 lib.pb2_debug_sim_pair(mode)
                 res[mode] = everything()
         finally:
@@ -637,7 +638,7 @@ def test_cluster_variants_match_independent_ctas(pb):
     res["product"] = everything()
     for x, y in zip(res[1], res["product"]):       # the product library runs the CTA pairs at this size
         assert torch.equal(x, y)
-    for mode in (2, 1):
+    for mode in (2, 3, 1):
         for k, (x, y) in enumerate(zip(res[0], res[mode])):
             if x.dim() == 0:                       # the loss: per-CTA partials, another tile-to-CTA deal
                 assert abs(x.item() - y.item()) <= 1e-6 * abs(x.item()), (mode, k)

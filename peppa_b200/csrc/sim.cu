@@ -967,7 +967,8 @@ struct LseGradPolicy {
 // ---------------------------------------------------------------------------------- kernel
 // kCtas: 1 = independent CTAs; 2 = CTA pairs sharing one MMA (cta_group::2); 3 = clusters of 2 whose CTAs take
 // the tiles (rb, cb) and (rb + 1, cb), run independent MMAs and share the Y tile: each loads half of it and
-// multicasts that half to both (a third fewer L2 lookups, no coupling through the accumulators).
+// multicasts that half to both (a third fewer L2 lookups, no coupling through the accumulators); 4 = CTA pairs whose X
+// strip stays resident in shared memory across a run of column tiles (measurement builds; see dispatch_sim).
 // does the policy need the per-warp staging slabs (gradient-matrix / fp32 output tiles, or the column-sum transpose)?
 template <class P, class = void>
 struct uses_stage : std::integral_constant<bool, P::kStoresG || P::kStoresF32> {};

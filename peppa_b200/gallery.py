@@ -86,7 +86,11 @@ class GalleryStep:
 
     ``dv_reduce``: how the dV partials reach their owners when world > 1 -- "p2p" (our own kernel over peer memory, see
     the module docstring), "nccl" (per column block ncclReduce overlapped with the tensor work; also what the gloo
-    orchestration tests run) or "auto" (default: p2p if the IPC exchange succeeds on every rank, else nccl)."""
+    orchestration tests run) or "auto" (default: p2p if the IPC exchange succeeds on every rank, else nccl).
+
+    ``with_recall``: recall@1..top_n (and the int32 ranks) of the same gallery; default on for the hinge loss (the rank
+    counts come out of the hinge pass) and off for MIL-NCE, where switching it on takes the counts out of the one-pass
+    log-sum-exp statistics (``fuse_rank``, an attribute for A/B tools: False runs a separate rank pass instead)."""
 
     def __init__(self, n_local: int, dim: int, margin: float = 0.2, top_n: int = 10, rank: int = 0, world: int = 1,
                  group=None, device=None, block: int = _BLOCK, with_grad: bool = True, backend=None,

@@ -1,5 +1,8 @@
-"""A/B of the encoder tail's variants (pb2_debug_proj_variant of the measurement build) on 2^20 rows 512 -> 512:
-variants alternate in one process on one board, 50 launches back to back per figure."""
+"""A/B of the encoder tail's variants (pb2_debug_proj_variant of the measurement build: 0 the product's choice = resident x
+with 256-column phases for this shape, 1 interleaved kernel, 2 column split, 3 phased halves, 4 sixteen epilogue warps, 5
+resident x with 128-column phases) on 2^20 rows 512 -> 512: variants alternate in one process on one board, 30 launches
+back to back per figure, minimum (~alone) and median (~sustained) over the rounds.
+    python tools/ab_tail.py [variants, default 1,0] [rounds, default 8]"""
 import os
 import sys
 

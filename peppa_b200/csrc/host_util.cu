@@ -13,6 +13,7 @@ namespace pb2 {
 
 static thread_local char g_err[512] = "";
 thread_local int g_pdl_depth = 0;
+thread_local int g_operands_ready_depth = 0;
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;

@@ -66,6 +66,18 @@ struct PdlScope {
     PdlScope() { ++g_pdl_depth; }
     ~PdlScope() { --g_pdl_depth; }
 };
+// While an OperandsReadyScope is alive on this thread, the similarity pass launched through here may fetch its X / Y
+// operand tiles BEFORE griddepcontrol.wait: the caller promises that they were complete before the pass's predecessor
+// in the stream passed its own wait (pb2_hinge_step: the raw input rows, with hinge_prep waiting before it triggers).
+extern thread_local int g_operands_ready_depth;
+struct OperandsReadyScope {
+    explicit OperandsReadyScope(bool on) : on_(on) { g_operands_ready_depth += on_; }
+    ~OperandsReadyScope() { g_operands_ready_depth -= on_; }
+    OperandsReadyScope(const OperandsReadyScope&) = delete;
+    OperandsReadyScope& operator=(const OperandsReadyScope&) = delete;
+   private:
+    int on_;
+};
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, int cluster,

@@ -402,8 +402,11 @@ __global__ void __launch_bounds__(256)
                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ col_cnt, float* __restrict__ loss_partial,
                       int n_partials, __half* __restrict__ vx, __half* __restrict__ ax, float* __restrict__ scale_v,
                       float* __restrict__ scale_a, const float* __restrict__ rinv_v_in, const float* __restrict__ rinv_a_in) {
+    // Wait first, trigger second: the workspace may still be read by the previous step's kernels, and the similarity
+    // pass that follows reads v / a before ITS wait (OperandsReadyScope) -- it may only be launched once everything
+    // ahead of this kernel in the stream, i.e. the producer of v and a, is complete.
+    pdl_wait();
     pdl_launch_dependents();
-    pdl_wait();  // the workspace may still be read by the previous step's kernels
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -514,9 +517,12 @@ __global__ void __launch_bounds__(256)
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
+    // the LAST block only folds the loss (serial fp64 work that would otherwise sit behind block 0's rows, on the
+    // step's critical path at batch ~1k); the others share the rows
+    const bool fold_block = blockIdx.x == gridDim.x - 1;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t rr = warp; rr < 2 * n; rr += nwarps) {
+    const int64_t nwarps = (int64_t)(gridDim.x - 1) * (blockDim.x >> 5);
+    for (int64_t rr = fold_block ? 2 * n : warp; rr < 2 * n; rr += nwarps) {
         const bool is_v = rr < n;
         const int64_t r = is_v ? rr : rr - n;
         const float* pr = (is_v ? p_v : p_a) + r * dim;
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(256)
             store8<TOut>(out + d, o);
         }
     }
-    if (blockIdx.x == 0) {
+    if (fold_block) {
         __shared__ double sh[8];
         __shared__ int sbad[8];
         double acc = 0.0;
@@ -999,7 +1005,7 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
         return set_error(PB2_ERR_ARG, "hinge_finish2: dtype / alignment");
     cudaError_t e;
 #define PB2_FIN2(TO)                                                                                                          \
-    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO>, (unsigned)grid_for_warps(2 * n), 256u, (size_t)0,     \
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO>, (unsigned)grid_for_warps(2 * n) + 1u, 256u, (size_t)0, \
                                            (cudaStream_t)stream, 1, p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, \
                                            rinv_a, diag, row_cnt, col_cnt, loss_partial, n_partials, margin, coef, loss_out,  \
                                            (TO*)d_v, (TO*)d_a))

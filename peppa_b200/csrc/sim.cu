@@ -66,6 +66,9 @@ struct SimCommon {
     float scale;
     int diag_only;  // visit only tiles (rb, rb): paired scores (BN == BM)
     uint32_t fmt;   // operand format of both X and Y: kFmtBF16 or kFmtF16 (kind::f16 takes either natively)
+    // programmatic dependent launch: X and Y were complete before the predecessor passed ITS griddepcontrol.wait
+    // (host_util.h: OperandsReadyScope), so the TMA / MMA warps start on them while the predecessor still runs
+    int early_operands;
 };
 
 __device__ __forceinline__ void tile_coords(int64_t t, int n_rb, int n_cb, int& rb, int& cb) {
@@ -1087,7 +1090,18 @@ __global__ void __launch_bounds__(sim_threads(G), 1)
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
+    // Everything above overlapped the previous kernel's tail; global memory from here on.  With early operands (the
+    // launch-bound training step only: 128-wide tiles of the fp16-G hinge pass; every other instantiation keeps the
+    // plain wait and its code) the producer and MMA warps skip the wait: they only read X / Y (complete by the
+    // caller's promise), shared memory and TMEM, so the main loop of the first tile runs beside the predecessor
+    // (pb2_hinge_step: hinge_prep, whose 1/||row|| and diagonal only the loader and epilogue warps read -- behind
+    // their own wait).
+    constexpr bool kEarlyOk = std::is_same<Policy, HingePolicyT<false, false>>::value && BN == 128 && kCtas == 1;
+    if constexpr (kEarlyOk) {
+        if (!(c.early_operands && (warp == kTmaWarp || warp == kMmaWarp))) pdl_wait();
+    } else {
+        pdl_wait();
+    }
 
     if (warp == kTmaWarp) {
         // ===================================================================== TMA producer
@@ -1417,6 +1431,7 @@ static int launch_sim(const void* x, const void* y, int dtype, int64_t rows, int
     c.rinv_y = rinv_y;
     c.scale = scale;
     c.fmt = dtype == PB2_F16 ? (uint32_t)kFmtF16 : (uint32_t)kFmtBF16;
+    c.early_operands = g_operands_ready_depth > 0 ? 1 : 0;
     auto kern = sim_kernel<Policy, BN, G, kCtas>;
     constexpr int smem = SimSmem<BN, G, uses_stage<Policy>::value, kCtas>::kTotal;
     static PerDeviceOnce configured;  // per instantiation and device

@@ -89,10 +89,17 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
     int rc = pb2_hinge_prep(v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part,
                             vx, ax, sv, sa, rinv_v_in, rinv_a_in, stream);
     if (rc) return rc;
-    rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, split ? sv : rinv_v, split ? sa : rinv_a, diag, diag, n, n, 0, 0,
-                       split ? 3 * dim : dim, split ? PB2_F16 : in_dtype, split ? 3 * (int64_t)dim : ldv,
-                       split ? 3 * (int64_t)dim : lda, margin, part,
-                       -L.n_part, row_cnt, col_cnt, g, PB2_F16, L.ld_g, nullptr, nullptr, stream);
+    // bf16 / fp16 rows are the caller's own tensors: complete before hinge_prep (which waits BEFORE it triggers its
+    // dependents) got past its wait, so the similarity pass streams them through the tensor cores while hinge_prep
+    // still computes the norms and the diagonal its epilogue needs.  The split operands of fp32 rows are hinge_prep's
+    // own output: no early start there.
+    {
+        pb2::OperandsReadyScope early(!split);
+        rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, split ? sv : rinv_v, split ? sa : rinv_a, diag, diag, n, n, 0, 0,
+                           split ? 3 * dim : dim, split ? PB2_F16 : in_dtype, split ? 3 * (int64_t)dim : ldv,
+                           split ? 3 * (int64_t)dim : lda, margin, part,
+                           -L.n_part, row_cnt, col_cnt, g, PB2_F16, L.ld_g, nullptr, nullptr, stream);
+    }
     if (rc) return rc;
     // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
     rc = pb2_grad_gemm_dual(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, pv, pa, dim, dim, stream);

@@ -78,7 +78,7 @@ _RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2
             "pb2_grad_gemm_workspace": C.c_int64}
 # selectors / knock-outs of the MEASUREMENT build only (libpeppa_b200_measure.so, -DPB2_MEASURE): not in the public
 # header and not exported by the product library
-_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_gg_pair": [_i], "pb2_debug_proj_variant": [_i], "pb2_debug_gg_units": [_i], "pb2_debug_sim_pair": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
+_DEBUG = {"pb2_debug_force_bn": [_i], "pb2_debug_gg_pair": [_i], "pb2_debug_proj_variant": [_i], "pb2_debug_gg_units": [_i], "pb2_debug_sim_pair": [_i], "pb2_debug_step_stages": [_i], "pb2_debug_set_mn_desc": [C.c_uint32, C.c_uint32, C.c_uint32]}
 
 _lib = None
 

@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(256)
     scale_pair_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int64_t n_vec, const float* __restrict__ coef,
                       T* __restrict__ y0, T* __restrict__ y1) {
     constexpr int kPer = 16 / sizeof(T);
+    pdl_launch_dependents();
+    pdl_wait();  // launched with programmatic stream serialization: scheduled while its predecessor drains
     const float c = *coef;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const bool second = i >= n_vec;
@@ -394,7 +396,9 @@ __global__ void __launch_bounds__(256)
 // One launch before the similarity pass of a training step (pig/loss.py:33-39 at batch size ~1k,
 // where launches dominate): per row i norms of V_i and A_i, the diagonal score, the fp16 normalised
 // copies for the gradient GEMMs, and zeroing of the count / partial buffers.
-template <typename T>
+// kRegs (dim <= 512): a row pair stays in registers between the norms and the normalised copies (one memory round
+// trip; the step at batch ~1k is latency bound).
+template <typename T, bool kRegs>
 __global__ void __launch_bounds__(256)
     hinge_prep_kernel(const T* __restrict__ v, const T* __restrict__ a, int64_t n, int dim,
                       int64_t ldv, int64_t lda, float* __restrict__ rinv_v, float* __restrict__ rinv_a,
@@ -416,10 +420,7 @@ __global__ void __launch_bounds__(256)
         const T* vr = v + r * ldv;
         const T* ar = a + r * lda;
         float sv = 0.f, sa = 0.f, dot = 0.f, mv = 0.f, ma = 0.f;
-        for (int d = lane * 8; d < dim; d += 256) {
-            float x[8], y[8];
-            load8(vr + d, x);
-            load8(ar + d, y);
+        auto accumulate = [&](const float (&x)[8], const float (&y)[8]) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 sv = fmaf(x[e], x[e], sv);
@@ -427,6 +428,26 @@ __global__ void __launch_bounds__(256)
                 dot = fmaf(x[e], y[e], dot);
                 mv = fmaxf(mv, fabsf(x[e]));
                 ma = fmaxf(ma, fabsf(y[e]));
+            }
+        };
+        [[maybe_unused]] float xs[2][8], ys[2][8];
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (lane * 8 + 256 * i < dim) {
+                    load8(vr + lane * 8 + 256 * i, xs[i]);
+                    load8(ar + lane * 8 + 256 * i, ys[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (lane * 8 + 256 * i < dim) accumulate(xs[i], ys[i]);
+        } else {
+            for (int d = lane * 8; d < dim; d += 256) {
+                float x[8], y[8];
+                load8(vr + d, x);
+                load8(ar + d, y);
+                accumulate(x, y);
             }
         }
         sv = warp_sum(sv);
@@ -452,10 +473,7 @@ __global__ void __launch_bounds__(256)
                 scale_a[r] = ldexpf(1.f, -ea);
             }
         }
-        for (int d = lane * 8; d < dim; d += 256) {
-            float x[8], y[8];
-            load8(vr + d, x);
-            load8(ar + d, y);
+        auto emit = [&](int d, float (&x)[8], float (&y)[8]) {
             __half2 hx[4], hy[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -475,6 +493,18 @@ __global__ void __launch_bounds__(256)
                 store_split(vx + r * 3 * dim, dim, d, 0, hi, lo);
                 split8_f16(y, hi, lo);
                 store_split(ax + r * 3 * dim, dim, d, 1, hi, lo);
+            }
+        };
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if (lane * 8 + 256 * i < dim) emit(lane * 8 + 256 * i, xs[i], ys[i]);
+        } else {
+            for (int d = lane * 8; d < dim; d += 256) {
+                float x[8], y[8];
+                load8(vr + d, x);
+                load8(ar + d, y);
+                emit(d, x, y);
             }
         }
     }
@@ -505,7 +535,9 @@ __device__ __forceinline__ void store8<__half>(__half* dst, const float (&o)[8])
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
 }
 
-template <typename T, typename TOut>
+// kRegs (dim <= 512): the row's x, y and p stay in registers between the dot product and the result -- every load of a
+// row is in flight at once, one memory round trip instead of three (the step at batch ~1k is latency bound).
+template <typename T, typename TOut, bool kRegs>
 __global__ void __launch_bounds__(256)
     hinge_finish2_kernel(const float* __restrict__ p_v, const float* __restrict__ p_a,
                          const T* __restrict__ v, const T* __restrict__ a, int64_t n, int dim,
@@ -532,6 +564,38 @@ __global__ void __launch_bounds__(256)
         const float ry = is_v ? rinv_a[r] : rinv_v[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * ry;
         TOut* out = (is_v ? d_v : d_a) + r * dim;
+        if constexpr (kRegs) {
+            float x[2][8], y[2][8], pv[2][8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int d = lane * 8 + 256 * i;
+                if (d < dim) {
+                    load8(xr + d, x[i]);
+                    load8(yr + d, y[i]);
+                    load8(pr + d, pv[i]);
+                }
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (lane * 8 + 256 * i < dim) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(gd, y[i][e], pv[i][e]), x[i][e] * rx, dot);
+                }
+            }
+            dot = warp_sum(dot);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int d = lane * 8 + 256 * i;
+                if (d < dim) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[i][e], pv[i][e]) - x[i][e] * rx * dot);
+                    store8<TOut>(out + d, o);
+                }
+            }
+            continue;
+        }
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float x[8], y[8];
@@ -562,10 +626,26 @@ __global__ void __launch_bounds__(256)
         double acc = 0.0;
         int bad = 0;
         for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += (double)loss_partial[i];
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            acc += (double)(margin - diag[i]) * (double)(row_cnt[i] + col_cnt[i]);
-            const float x = rinv_v[i], y = rinv_a[i];
-            bad |= !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
+        // four rows per thread and trip: their loads are in flight together; the sum keeps its order (i ascending)
+        for (int64_t i0 = threadIdx.x; i0 < n; i0 += 4 * (int64_t)blockDim.x) {
+            float dg[4], x[4], y[4];
+            int cnt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + (int64_t)u * blockDim.x;
+                const bool ok = i < n;
+                dg[u] = ok ? diag[i] : 0.f;
+                cnt[u] = ok ? row_cnt[i] + col_cnt[i] : 0;
+                x[u] = ok ? rinv_v[i] : 1.f;
+                y[u] = ok ? rinv_a[i] : 1.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + (int64_t)u * blockDim.x < n) {
+                    acc += (double)(margin - dg[u]) * (double)cnt[u];
+                    bad |= !(fabsf(x[u]) <= 3.0e38f) || !(fabsf(y[u]) <= 3.0e38f);
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -870,12 +950,20 @@ extern "C" int pb2_scale_pair(const float* x0, const float* x1, int64_t n_elems,
     const int64_t n_vec = n_elems * es / 16;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((2 * n_vec + 255) / 256, (int64_t)sm_count() * 8));
     cudaStream_t st = (cudaStream_t)stream;
+    // the backward of the launch-bound training step: its launch overlaps the tail of whatever precedes it in the stream
+    // (autograd's ones_like fill, or hinge_finish2 itself)
+    PdlScope pdl;
+    cudaError_t e;
     if (out_dtype == PB2_F32)
-        scale_pair_kernel<float><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (float*)y0, (float*)y1);
+        e = launch_ex(scale_pair_kernel<float>, (unsigned)grid, 256u, (size_t)0, st, 1, x0, x1, n_vec, coef, (float*)y0, (float*)y1);
     else if (out_dtype == PB2_BF16)
-        scale_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (__nv_bfloat16*)y0, (__nv_bfloat16*)y1);
+        e = launch_ex(scale_pair_kernel<__nv_bfloat16>, (unsigned)grid, 256u, (size_t)0, st, 1, x0, x1, n_vec, coef,
+                      (__nv_bfloat16*)y0, (__nv_bfloat16*)y1);
     else
-        scale_pair_kernel<__half><<<grid, 256, 0, st>>>(x0, x1, n_vec, coef, (__half*)y0, (__half*)y1);
+        e = launch_ex(scale_pair_kernel<__half>, (unsigned)grid, 256u, (size_t)0, st, 1, x0, x1, n_vec, coef, (__half*)y0,
+                      (__half*)y1);
+    const int rc = check_cuda(e, "scale_pair");
+    if (rc) return rc;
     return check_launch("scale_pair");
 }
 
@@ -980,10 +1068,14 @@ extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n
                      !vec_ok(a_split, 3 * (int64_t)dim, 2))))
         return set_error(PB2_ERR_ARG, "hinge_prep: the split-fp16 outputs and their scales go together, for fp32 rows only");
     cudaError_t e;
-    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_prep_kernel<T>, (unsigned)grid_for_warps(n), 256u, (size_t)0, (cudaStream_t)stream,
-                                           1, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, diag, (__half*)vh,
-                                           (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials, (__half*)v_split,
-                                           (__half*)a_split, scale_v, scale_a, rinv_v_in, rinv_a_in));
+#define PB2_PREP(REGS)                                                                                                     \
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_prep_kernel<T, REGS>, (unsigned)grid_for_warps(n), 256u, (size_t)0,       \
+                                           (cudaStream_t)stream, 1, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, \
+                                           diag, (__half*)vh, (__half*)ah, row_cnt, col_cnt, loss_partial, n_partials,     \
+                                           (__half*)v_split, (__half*)a_split, scale_v, scale_a, rinv_v_in, rinv_a_in))
+    if (dim <= 512) PB2_PREP(true);
+    else PB2_PREP(false);
+#undef PB2_PREP
     int rc = check_cuda(e, "hinge_prep");
     if (rc) return rc;
     return check_launch("hinge_prep");
@@ -1004,16 +1096,22 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
         !vec_ok(d_v, dim, ob) || !vec_ok(d_a, dim, ob))
         return set_error(PB2_ERR_ARG, "hinge_finish2: dtype / alignment");
     cudaError_t e;
-#define PB2_FIN2(TO)                                                                                                          \
-    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO>, (unsigned)grid_for_warps(2 * n) + 1u, 256u, (size_t)0, \
-                                           (cudaStream_t)stream, 1, p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, \
-                                           rinv_a, diag, row_cnt, col_cnt, loss_partial, n_partials, margin, coef, loss_out,  \
-                                           (TO*)d_v, (TO*)d_a))
+#define PB2_FIN2_(TO, REGS)                                                                                                   \
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO, REGS>, (unsigned)grid_for_warps(2 * n) + 1u, 256u,     \
+                                           (size_t)0, (cudaStream_t)stream, 1, p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, \
+                                           lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, loss_partial, n_partials, margin, coef, \
+                                           loss_out, (TO*)d_v, (TO*)d_a))
+#define PB2_FIN2(TO)                    \
+    do {                                \
+        if (dim <= 512) PB2_FIN2_(TO, true); \
+        else PB2_FIN2_(TO, false);      \
+    } while (0)
     if (out_dtype == PB2_F32) PB2_FIN2(float);
     else if (out_dtype == PB2_BF16) PB2_FIN2(__nv_bfloat16);
     else if (out_dtype == PB2_F16) PB2_FIN2(__half);
     else return set_error(PB2_ERR_ARG, "hinge_finish2: unknown output dtype");
 #undef PB2_FIN2
+#undef PB2_FIN2_
     int rc = check_cuda(e, "hinge_finish2");
     if (rc) return rc;
     return check_launch("hinge_finish2");

@@ -45,7 +45,17 @@ Layout layout(int64_t n, int dim, int in_dtype) {
     L.total = o;
     return L;
 }
+PB2_KNOB g_step_stages = 4;  // measurement build (pb2_debug_step_stages): stop the step after its first k kernels
 }  // namespace
+
+#ifdef PB2_MEASURE
+// Timing only (tools/timeline_train1024.py: the cost of each kernel INSIDE the chained step): 1 = hinge_prep, 2 = + the
+// similarity pass, 3 = + the gradient products, 4 = the whole step.  Truncated steps leave loss / gradients unwritten.
+extern "C" int pb2_debug_step_stages(int k) {
+    g_step_stages = k >= 1 && k <= 4 ? k : 4;
+    return PB2_OK;
+}
+#endif
 
 extern "C" int64_t pb2_hinge_step_workspace(int64_t n, int dim, int in_dtype) {
     return n > 0 && dim > 0 ? layout(n, dim, in_dtype).total : 0;
@@ -88,7 +98,7 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
     float* sa = split ? reinterpret_cast<float*>(w + L.sa) : nullptr;
     int rc = pb2_hinge_prep(v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, vh, ah, row_cnt, col_cnt, part, L.n_part,
                             vx, ax, sv, sa, rinv_v_in, rinv_a_in, stream);
-    if (rc) return rc;
+    if (rc || g_step_stages < 2) return rc;
     // bf16 / fp16 rows are the caller's own tensors: complete before hinge_prep (which waits BEFORE it triggers its
     // dependents) got past its wait, so the similarity pass streams them through the tensor cores while hinge_prep
     // still computes the norms and the diagonal its epilogue needs.  The split operands of fp32 rows are hinge_prep's
@@ -100,10 +110,10 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
                            split ? 3 * (int64_t)dim : lda, margin, part,
                            -L.n_part, row_cnt, col_cnt, g, PB2_F16, L.ld_g, nullptr, nullptr, stream);
     }
-    if (rc) return rc;
+    if (rc || g_step_stages < 3) return rc;
     // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
     rc = pb2_grad_gemm_dual(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, pv, pa, dim, dim, stream);
-    if (rc) return rc;
+    if (rc || g_step_stages < 4) return rc;
     return pb2_hinge_finish2(pv, pa, v, a, in_dtype, n, dim, ldv, lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, part, L.n_part, margin,
                              1.0f / ((float)n * (float)n), loss_out, d_v, d_a, out_dtype, stream);
 }

@@ -1137,3 +1137,38 @@ def _grad_of(pb, V, A, dtype):
     v, a = V.cuda().to(dtype).requires_grad_(True), A.cuda().to(dtype).requires_grad_(True)
     pb.loss.TripletLoss(0.2)(v, a).backward()
     return v.grad, a.grad
+
+
+@pytest.mark.parametrize("dtype,n", [(torch.bfloat16, 1024), (torch.float16, 1000), (torch.bfloat16, 2048), (torch.float32, 1024)])
+def test_training_step_operands_written_right_before(pb, dtype, n):
+    """Inside pb2_hinge_step the similarity pass fetches its operand tiles BEFORE griddepcontrol.wait (they are the
+    caller's rows, complete before hinge_prep got past its own wait; csrc/step.cu, host_util.h: OperandsReadyScope),
+    and the backward's scale launch triggers its dependents early.  Chain of 24 steps without a host sync in which
+    every step's inputs are written by the kernels right ahead of it -- the previous step's gradients as they leave
+    pb2_scale_pair, then rows a torch kernel derives from them -- against the same chain with a device sync around
+    every step: the kernels are deterministic, so any operand fetched too early shows as a different bit."""
+    V0, A0 = emb(n, 4.0)
+
+    def chain(sync):
+        v, a = V0.cuda().to(dtype), A0.cuda().to(dtype)
+        out = []
+        for it in range(24):
+            v, a = v.detach().requires_grad_(True), a.detach().requires_grad_(True)
+            if sync:
+                torch.cuda.synchronize()
+            loss = pb.loss.TripletLoss(0.2)(v, a)
+            (loss * float(n * n)).backward()      # gradient entries of order 1 in every dtype (fp16 would flush 1 / N^2)
+            if sync:
+                torch.cuda.synchronize()
+            out.append((loss.detach(), v.grad, a.grad))
+            if it % 2 == 0:          # the gradients themselves (directions matter, cosine ignores their scale) ...
+                v, a = v.grad, a.grad
+            else:                    # ... or rows a torch kernel writes from them right before the next step
+                v, a = (V0.cuda() + 0.1 * v.grad.float()).to(dtype), (A0.cuda() + 0.1 * a.grad.float()).to(dtype)
+        torch.cuda.synchronize()
+        return out
+
+    free, synced = chain(False), chain(True)
+    for it, ((l1, dv1, da1), (l2, dv2, da2)) in enumerate(zip(free, synced)):
+        assert torch.isfinite(l2), it
+        assert torch.equal(l1, l2) and torch.equal(dv1, dv2) and torch.equal(da1, da2), it

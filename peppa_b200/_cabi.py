@@ -103,8 +103,10 @@ def lib():
     return _lib
 
 
-def _bind(handle, table):
+def _bind(handle, table, optional=()):
     for name, args in table.items():
+        if name in optional and not hasattr(handle, name):      # an older variant build under tools/ab/ (A/B runs)
+            continue
         fn = getattr(handle, name)  # AttributeError if the export is missing
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
@@ -152,7 +154,7 @@ class measurement_library:
         if _measure is None:
             if not os.path.exists(MEASURE_LIB_PATH):
                 raise RuntimeError(f"peppa_b200: measurement library not built ({MEASURE_LIB_PATH}); run `python -m peppa_b200.build`")
-            _measure = _bind(C.CDLL(MEASURE_LIB_PATH), {**SIGNATURES, **_DEBUG})
+            _measure = _bind(C.CDLL(MEASURE_LIB_PATH), {**SIGNATURES, **_DEBUG}, optional=_DEBUG)
         self._saved = lib()
         _lib = _measure
         return _measure

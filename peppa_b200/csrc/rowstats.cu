@@ -549,10 +549,11 @@ __global__ void __launch_bounds__(256)
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    // the LAST block only folds the loss (serial fp64 work that would otherwise sit behind block 0's rows, on the
-    // step's critical path at batch ~1k); the others share the rows
-    const bool fold_block = blockIdx.x == gridDim.x - 1;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // block 0 only folds the loss (serial fp64 work that would otherwise sit behind a block's rows, on the step's
+    // critical path at batch ~1k; first in the grid, so that it runs beside the first wave of a large grid); the
+    // others share the rows
+    const bool fold_block = blockIdx.x == 0;
+    const int64_t warp = ((int64_t)blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)(gridDim.x - 1) * (blockDim.x >> 5);
     for (int64_t rr = fold_block ? 2 * n : warp; rr < 2 * n; rr += nwarps) {
         const bool is_v = rr < n;
@@ -670,8 +671,9 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------ hinge finish
-// One warp per row; the row (p, x, y) is held in registers for dim <= 1024, else re-read.
-template <typename T>
+// One warp per row; kRegs (dim <= 512): the row (p, x, y) is held in registers between the dot product and the
+// result (one pass over HBM / L2 instead of two), else re-read.
+template <typename T, bool kRegs>
 __global__ void __launch_bounds__(256)
     hinge_finish_kernel(const float* __restrict__ p, int64_t ld_p, const T* __restrict__ x,
                         const T* __restrict__ y, const float* __restrict__ rinv_x,
@@ -689,6 +691,43 @@ __global__ void __launch_bounds__(256)
         const float* pr = p + r * ld_p;
         const T* xr = x + r * ldx;
         const T* yr = y + r * ldy;
+        if constexpr (kRegs) {
+            float a[2][8], b[2][8], pv[2][8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int d = lane * 8 + 256 * i;
+                if (d < dim) {
+                    load8(xr + d, a[i]);
+                    load8(yr + d, b[i]);
+                    load8(pr + d, pv[i]);
+                }
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (lane * 8 + 256 * i < dim) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(gd, b[i][e], pv[i][e]), a[i][e] * rx, dot);
+                }
+            }
+            dot = warp_sum(dot);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int d = lane * 8 + 256 * i;
+                if (d < dim) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float g = fmaf(gd, b[i][e], pv[i][e]);
+                        o[e] = coef * rx * (g - a[i][e] * rx * dot);
+                    }
+                    float* gr = grad + r * ld_grad + d;
+                    *reinterpret_cast<float4*>(gr) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(gr + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            continue;
+        }
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
             float a[8], b[8];
@@ -1047,7 +1086,12 @@ extern "C" int pb2_hinge_finish(const float* p, int64_t ld_p, const void* x, con
     const int es = elem_bytes(dtype);
     if (!es || dim % 8 != 0 || !vec_ok(x, ldx, es) || !vec_ok(y, ldy, es) || !vec_ok(p, ld_p, 4) || !vec_ok(grad_x, ld_grad, 4))
         return set_error(PB2_ERR_ARG, "hinge_finish: dtype / alignment");
-    PB2_ROWS_DISPATCH(dtype, hinge_finish_kernel<T><<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
+    if (dim <= 512)
+        PB2_ROWS_DISPATCH(dtype, hinge_finish_kernel<T, true><<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
+                                 p, ld_p, (const T*)x, (const T*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim, ldx, ldy,
+                                 coef_host, coef_dev, grad_x, ld_grad));
+    else
+        PB2_ROWS_DISPATCH(dtype, hinge_finish_kernel<T, false><<<grid_for_warps(rows), 256, 0, (cudaStream_t)stream>>>(
                                  p, ld_p, (const T*)x, (const T*)y, rinv_x, rinv_y, row_cnt, col_cnt, rows, dim, ldx, ldy,
                                  coef_host, coef_dev, grad_x, ld_grad));
     return check_launch("hinge_finish");

@@ -256,6 +256,25 @@ int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int di
                    void* workspace, int64_t workspace_bytes, float* loss_out, void* d_v, void* d_a, int out_dtype,
                    const float* rinv_v_in, const float* rinv_a_in, void* stream);
 
+/* The same step as an autograd pair (pig/models.py:262: `loss = self.loss(V, A)` ... `loss.backward()`): FOUR launches
+ * for forward + backward instead of the five of pb2_hinge_step + pb2_scale_pair, and no fp32 gradient round trip.
+ * pb2_hinge_forward = pb2_hinge_prep -> pb2_sim_hinge -> both gradient products, with the scalar loss folded by a spare
+ * CTA of the product grid (a launch of its own when the products do not fit one grid): loss_out is final when it
+ * returns.  What the backward needs -- G A^ and G^T V^ (fp32), 1/||row||, the indicator counts -- stays in `state`, a
+ * 256-byte aligned device buffer of pb2_hinge_state_bytes(n, dim) bytes owned by the caller (one per forward whose
+ * backward is still to come); `workspace` (pb2_hinge_forward_workspace bytes) is scratch and may be reused at once.
+ * pb2_hinge_backward = ONE launch: d_v / d_a ([n, dim], out_dtype) = the gradients of the mean hinge loss times
+ * grad_out[0] (device fp32 scalar, autograd's grad_output; NULL = 1), multiplied in fp32 BEFORE the rounding to
+ * out_dtype -- an AMP loss scale reaches an fp16 gradient of ~1e-7 before the rounding does.  v / a: the rows the
+ * forward saw.  Same bits as pb2_hinge_step followed by pb2_scale_pair. */
+int64_t pb2_hinge_forward_workspace(int64_t n, int dim, int in_dtype);
+int64_t pb2_hinge_state_bytes(int64_t n, int dim);
+int pb2_hinge_forward(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
+                      void* workspace, int64_t workspace_bytes, void* state, int64_t state_bytes, float* loss_out,
+                      const float* rinv_v_in, const float* rinv_a_in, void* stream);
+int pb2_hinge_backward(const void* state, int64_t state_bytes, const void* v, const void* a, int in_dtype, int64_t n, int dim,
+                       int64_t ldv, int64_t lda, const float* grad_out, void* d_v, void* d_a, int out_dtype, void* stream);
+
 /* MIL-NCE finish: grad_x[i] = coef * (p_i * 2^-13 - y_i) (coef = grad_out / N). */
 int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int dtype, int64_t rows, int dim, int64_t ldy,
                       float coef_host, const float* coef_dev, float* grad_x, int64_t ld_grad, void* stream);

@@ -56,6 +56,10 @@ SIGNATURES = {
     "pb2_hinge_finish2": [_p, _p, _p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i, _f, _f, _p, _p, _p, _i, _p],
     "pb2_hinge_step_workspace": [_i64, _i, _i],
     "pb2_hinge_step": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _p, _p, _i, _p, _p, _p],
+    "pb2_hinge_forward_workspace": [_i64, _i, _i],
+    "pb2_hinge_state_bytes": [_i64, _i],
+    "pb2_hinge_forward": [_p, _p, _i, _i64, _i, _i64, _i64, _f, _p, _i64, _p, _i64, _p, _p, _p, _p],
+    "pb2_hinge_backward": [_p, _i64, _p, _p, _i, _i64, _i, _i64, _i64, _p, _p, _p, _i, _p],
     "pb2_rows_scale_f16": [_p, _i, _p, _i64, _i, _i64, _p, _i64, _p],
     "pb2_scale_pair": [_p, _p, _i64, _i, _p, _p, _p, _p],
     "pb2_milnce_finish": [_p, _i64, _p, _i, _i64, _i, _i64, _f, _p, _p, _i64, _p],
@@ -74,7 +78,7 @@ SIGNATURES = {
     "pb2_nccl_dv_reduce_scatter": [_p, _p, _i64, _i, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
 }
-_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64,
+_RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64, "pb2_hinge_forward_workspace": C.c_int64, "pb2_hinge_state_bytes": C.c_int64,
             "pb2_grad_gemm_workspace": C.c_int64}
 # selectors / knock-outs of the MEASUREMENT build only (libpeppa_b200_measure.so, -DPB2_MEASURE): not in the public
 # header and not exported by the product library
@@ -120,7 +124,7 @@ _fast = None
 def fast():
     """The C++ autograd glue over the same C ABI (csrc/torch_fast.cpp) for the launch-bound training step, or None:
     not built (older checkouts), the measurement build is active (tools / variant tests route through ctypes), or
-    PEPPA_B200_NO_FAST=1.  Both paths end in pb2_hinge_step / pb2_scale_pair of the product library."""
+    PEPPA_B200_NO_FAST=1.  Both paths end in pb2_hinge_forward / pb2_hinge_backward of the product library."""
     global _fast
     if _fast is None:
         _fast = False

@@ -21,6 +21,7 @@
 // its head (its LAST segment, reached ~a whole range later) adds them in its epilogue.  No atomics on the
 // output, fixed summation order, bit-reproducible.
 #include "common.cuh"
+#include "fold.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
 
@@ -350,13 +351,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 // Both backward products of one gradient-matrix block in ONE launch: CTAs [0, n0) compute out0 = G Z0, the
 // rest out1 = G^T Z1.  A batch-1k training step is launch bound (each of these GEMMs is ~64 short tiles), and
 // the two products are independent, so they share a grid instead of queueing behind each other.
+// fold.loss_out != nullptr (pb2_hinge_forward): one more CTA at the end of the grid folds the step's scalar loss from
+// what the similarity pass left behind, beside the products instead of in a launch of its own.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
     grad_gemm_dual_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_z0,
                           const __grid_constant__ CUtensorMap tm_g1, const __grid_constant__ CUtensorMap tm_z1, const Args a0,
-                          const Args a1, const int n0) {
-    if ((int)blockIdx.x < n0) gg_body<false, BN, 1>(tm_g0, tm_z0, a0, (int)blockIdx.x, n0);
-    else gg_body<true, BN, 1>(tm_g1, tm_z1, a1, (int)blockIdx.x - n0, (int)gridDim.x - n0);
+                          const Args a1, const int n0, const int n1, const HingeFold fold) {
+    if ((int)blockIdx.x < n0) {
+        gg_body<false, BN, 1>(tm_g0, tm_z0, a0, (int)blockIdx.x, n0);
+    } else if ((int)blockIdx.x < n0 + n1) {
+        gg_body<true, BN, 1>(tm_g1, tm_z1, a1, (int)blockIdx.x - n0, n1);
+    } else {
+        extern __shared__ __align__(1024) uint8_t smem[];
+        pdl_launch_dependents();
+        pdl_wait();
+        if (threadIdx.x < 256)
+            hinge_loss_fold(fold, (int)threadIdx.x, reinterpret_cast<double*>(smem), reinterpret_cast<int*>(smem + 64), 1);
+    }
 }
 
 
@@ -729,7 +741,7 @@ static int launch_i8(const void* g, int64_t g_rows, int64_t g_cols, int64_t ld_g
 template <int BN>
 static int launch_dual(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0, const void* z1,
                        int z_fmt, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0, float* out1, int64_t ld_out0,
-                       int64_t ld_out1, cudaStream_t st) {
+                       int64_t ld_out1, const HingeFold& fold, cudaStream_t st) {
     CUtensorMap tg0, tz0, tg1, tz1;
     Args a0, a1;
     int rc = prepare<false, BN, 1>(g, g_fmt, g_rows, g_cols, ld_g, z0, z_fmt, dim, ldz0, alpha, 0, out0, ld_out0, &tg0, &tz0, &a0);
@@ -742,7 +754,8 @@ static int launch_dual(const void* g, int g_fmt, int64_t g_rows, int64_t g_cols,
     rc = ensure_dynamic_smem(configured, kern, smem, "grad_gemm_dual");
     if (rc) return rc;
     const int n0 = (int)a0.n_tiles, n1 = (int)a1.n_tiles;
-    rc = check_cuda(launch_ex(kern, (unsigned)(n0 + n1), (unsigned)kThreads, (size_t)smem, st, 1, tg0, tz0, tg1, tz1, a0, a1, n0),
+    const unsigned grid = (unsigned)(n0 + n1) + (fold.loss_out ? 1u : 0u);
+    rc = check_cuda(launch_ex(kern, grid, (unsigned)kThreads, (size_t)smem, st, 1, tg0, tz0, tg1, tz1, a0, a1, n0, n1, fold),
                     "grad_gemm_dual launch");
     if (rc) return rc;
     return check_launch("grad_gemm_dual");
@@ -773,9 +786,10 @@ extern "C" int pb2_debug_gg_pair(int mode) {
 }
 #endif
 
-extern "C" int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
-                                  const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
-                                  float* out1, int64_t ld_out0, int64_t ld_out1, void* stream) {
+int pb2::grad_gemm_dual_fold(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
+                             const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
+                             float* out1, int64_t ld_out0, int64_t ld_out1, const HingeFold& fold, bool* folded, void* stream) {
+    if (folded) *folded = false;
     if (g_rows <= 0 || g_cols <= 0) return PB2_OK;
     if (!gmat || !z0 || !z1 || !out0 || !out1) return set_error(PB2_ERR_ARG, "grad_gemm_dual: null");
     // one wave: every 128 x 64 tile of both products gets its own CTA; otherwise two ordinary launches
@@ -789,8 +803,16 @@ extern "C" int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows,
     }
     const int gf = g_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
     const int zf = z_dtype == PB2_F16 ? (int)kFmtF16 : (int)kFmtBF16;
+    if (folded) *folded = fold.loss_out != nullptr;
     return gg::launch_dual<64>(gmat, gf, g_rows, g_cols, ld_g, z0, z1, zf, dim, ldz0, ldz1, alpha, out0, out1, ld_out0, ld_out1,
-                               (cudaStream_t)stream);
+                               fold, (cudaStream_t)stream);
+}
+
+extern "C" int pb2_grad_gemm_dual(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0,
+                                  const void* z1, int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0,
+                                  float* out1, int64_t ld_out0, int64_t ld_out1, void* stream) {
+    return grad_gemm_dual_fold(gmat, g_dtype, g_rows, g_cols, ld_g, z0, z1, z_dtype, dim, ldz0, ldz1, alpha, out0, out1, ld_out0,
+                               ld_out1, HingeFold(), nullptr, stream);
 }
 
 extern "C" int64_t pb2_grad_gemm_workspace(void) { return gg::workspace_bytes(); }

@@ -40,6 +40,34 @@ inline int ensure_dynamic_smem(PerDeviceOnce& once, K kern, int smem, const char
     return rc;
 }
 
+// The scalar hinge loss of a training step from what the similarity pass left behind (device code: fold.cuh):
+// loss = coef * (sum of the CTA partials + sum_i (margin - diag_i) (row_cnt_i + col_cnt_i)), NaN if any 1/||row|| is
+// not finite (the reference's 0/0).  Runs in 256 threads of ONE block: block 0 of hinge_finish2, or a spare CTA of the
+// dual gradient-product grid (pb2_hinge_forward).  loss_out == nullptr: no fold.
+struct HingeFold {
+    const float* loss_partial = nullptr;
+    int n_partials = 0;
+    const float* diag = nullptr;
+    const int32_t* row_cnt = nullptr;
+    const int32_t* col_cnt = nullptr;
+    const float* rinv_v = nullptr;
+    const float* rinv_a = nullptr;
+    int64_t n = 0;
+    float margin = 0.f, coef = 0.f;
+    float* loss_out = nullptr;
+};
+// pb2_grad_gemm_dual with the loss fold in a CTA of its own at the end of the grid (gradgemm.cu).  *folded says whether
+// the launch took the fold (it does whenever both products fit one grid); otherwise the caller launches hinge_fold.
+int grad_gemm_dual_fold(const void* gmat, int g_dtype, int64_t g_rows, int64_t g_cols, int64_t ld_g, const void* z0, const void* z1,
+                        int z_dtype, int dim, int64_t ldz0, int64_t ldz1, float alpha, float* out0, float* out1, int64_t ld_out0,
+                        int64_t ld_out1, const HingeFold& fold, bool* folded, void* stream);
+int hinge_fold(const HingeFold& fold, void* stream);  // the fold as a launch of its own (rowstats.cu)
+// pb2_hinge_finish2 with an optional device-side factor (autograd's grad_output, applied in fp32 before the rounding)
+// and an optional loss fold (fold.loss_out != nullptr: block 0 of the grid) (rowstats.cu)
+int hinge_finish2_ex(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim, int64_t ldv,
+                     int64_t lda, const float* rinv_v, const float* rinv_a, const int32_t* row_cnt, const int32_t* col_cnt,
+                     float coef, const float* coef_dev, const HingeFold& fold, void* d_v, void* d_a, int out_dtype, void* stream);
+
 // 2-D row-major tensor map with 128-byte swizzle: inner dimension `cols` (contiguous), outer
 // `rows`, row pitch `ld_bytes`; box = box_cols x box_rows elements; out-of-bounds reads give 0.
 int make_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,

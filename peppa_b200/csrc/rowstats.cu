@@ -4,6 +4,7 @@
 // elementwise contrastive(M) of pig/loss.py:41-48 for callers that hold a materialised matrix.
 // All are HBM/L2-bound: one warp per row with 16-byte loads.
 #include "common.cuh"
+#include "fold.cuh"
 #include "host_util.h"
 #include "peppa_b200.h"
 
@@ -537,25 +538,32 @@ __device__ __forceinline__ void store8<__half>(__half* dst, const float (&o)[8])
 
 // kRegs (dim <= 512): the row's x, y and p stay in registers between the dot product and the result -- every load of a
 // row is in flight at once, one memory round trip instead of three (the step at batch ~1k is latency bound).
+// coef_dev (optional): autograd's grad_output, applied in fp32 to the finished fp32 gradient, the rounding to TOut last
+// (bit for bit what hinge_finish2 -> fp32 -> pb2_scale_pair produces).  fold.loss_out != nullptr: block 0 only folds the
+// scalar loss (serial fp64 work that would otherwise sit behind a block's rows, on the step's critical path at batch
+// ~1k; first in the grid, so that it runs beside the first wave of a large grid) and the other blocks share the rows.
 template <typename T, typename TOut, bool kRegs>
 __global__ void __launch_bounds__(256)
     hinge_finish2_kernel(const float* __restrict__ p_v, const float* __restrict__ p_a,
                          const T* __restrict__ v, const T* __restrict__ a, int64_t n, int dim,
                          int64_t ldv, int64_t lda, const float* __restrict__ rinv_v, const float* __restrict__ rinv_a,
-                         const float* __restrict__ diag, const int32_t* __restrict__ row_cnt,
-                         const int32_t* __restrict__ col_cnt, const float* __restrict__ loss_partial, int n_partials,
-                         float margin, float coef, float* __restrict__ loss_out, TOut* __restrict__ d_v,
+                         const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ col_cnt, float coef,
+                         const float* __restrict__ coef_dev, const HingeFold fold, TOut* __restrict__ d_v,
                          TOut* __restrict__ d_a) {
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    // block 0 only folds the loss (serial fp64 work that would otherwise sit behind a block's rows, on the step's
-    // critical path at batch ~1k; first in the grid, so that it runs beside the first wave of a large grid); the
-    // others share the rows
-    const bool fold_block = blockIdx.x == 0;
-    const int64_t warp = ((int64_t)blockIdx.x - 1) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)(gridDim.x - 1) * (blockDim.x >> 5);
-    for (int64_t rr = fold_block ? 2 * n : warp; rr < 2 * n; rr += nwarps) {
+    const int first = fold.loss_out ? 1 : 0;
+    if (first && blockIdx.x == 0) {
+        __shared__ double sh[8];
+        __shared__ int sbad[8];
+        hinge_loss_fold(fold, (int)threadIdx.x, sh, sbad, 1);
+        return;
+    }
+    const float cdev = coef_dev ? coef_dev[0] : 1.f;
+    const int64_t warp = ((int64_t)blockIdx.x - first) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)(gridDim.x - first) * (blockDim.x >> 5);
+    for (int64_t rr = warp; rr < 2 * n; rr += nwarps) {
         const bool is_v = rr < n;
         const int64_t r = is_v ? rr : rr - n;
         const float* pr = (is_v ? p_v : p_a) + r * dim;
@@ -565,6 +573,14 @@ __global__ void __launch_bounds__(256)
         const float ry = is_v ? rinv_a[r] : rinv_v[r];
         const float gd = -(float)(row_cnt[r] + col_cnt[r]) * ry;
         TOut* out = (is_v ? d_v : d_a) + r * dim;
+        auto result = [&](float (&o)[8], const float (&x)[8], const float (&y)[8], const float (&pv)[8], float dot) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[e], pv[e]) - x[e] * rx * dot);
+            if (coef_dev) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(o[e], cdev);
+            }
+        };
         if constexpr (kRegs) {
             float x[2][8], y[2][8], pv[2][8];
 #pragma unroll
@@ -590,8 +606,7 @@ __global__ void __launch_bounds__(256)
                 const int d = lane * 8 + 256 * i;
                 if (d < dim) {
                     float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[i][e], pv[i][e]) - x[i][e] * rx * dot);
+                    result(o, x[i], y[i], pv[i], dot);
                     store8<TOut>(out + d, o);
                 }
             }
@@ -599,75 +614,32 @@ __global__ void __launch_bounds__(256)
         }
         float dot = 0.f;
         for (int d = lane * 8; d < dim; d += 256) {
-            float x[8], y[8];
+            float x[8], y[8], pv[8];
             load8(xr + d, x);
             load8(yr + d, y);
-            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
-            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
-            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            load8(pr + d, pv);
 #pragma unroll
             for (int e = 0; e < 8; ++e) dot = fmaf(fmaf(gd, y[e], pv[e]), x[e] * rx, dot);
         }
         dot = warp_sum(dot);
         for (int d = lane * 8; d < dim; d += 256) {
-            float x[8], y[8], o[8];
+            float x[8], y[8], pv[8], o[8];
             load8(xr + d, x);
             load8(yr + d, y);
-            const float4 p0 = *reinterpret_cast<const float4*>(pr + d);
-            const float4 p1 = *reinterpret_cast<const float4*>(pr + d + 4);
-            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = coef * rx * (fmaf(gd, y[e], pv[e]) - x[e] * rx * dot);
+            load8(pr + d, pv);
+            result(o, x, y, pv, dot);
             store8<TOut>(out + d, o);
         }
     }
-    if (fold_block) {
-        __shared__ double sh[8];
-        __shared__ int sbad[8];
-        double acc = 0.0;
-        int bad = 0;
-        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += (double)loss_partial[i];
-        // four rows per thread and trip: their loads are in flight together; the sum keeps its order (i ascending)
-        for (int64_t i0 = threadIdx.x; i0 < n; i0 += 4 * (int64_t)blockDim.x) {
-            float dg[4], x[4], y[4];
-            int cnt[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + (int64_t)u * blockDim.x;
-                const bool ok = i < n;
-                dg[u] = ok ? diag[i] : 0.f;
-                cnt[u] = ok ? row_cnt[i] + col_cnt[i] : 0;
-                x[u] = ok ? rinv_v[i] : 1.f;
-                y[u] = ok ? rinv_a[i] : 1.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (i0 + (int64_t)u * blockDim.x < n) {
-                    acc += (double)(margin - dg[u]) * (double)cnt[u];
-                    bad |= !(fabsf(x[u]) <= 3.0e38f) || !(fabsf(y[u]) <= 3.0e38f);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-        }
-        if (lane == 0) {
-            sh[threadIdx.x >> 5] = acc;
-            sbad[threadIdx.x >> 5] = bad;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            int b = 0;
-            for (int w = 0; w < 8; ++w) {
-                t += sh[w];
-                b |= sbad[w];
-            }
-            loss_out[0] = b ? __int_as_float(0x7fc00000) : (float)(t * (double)coef);
-        }
-    }
+}
+
+// the fold as a launch of its own (pb2_hinge_forward when the gradient products do not fit one grid)
+__global__ void __launch_bounds__(256) hinge_fold_kernel(const HingeFold fold) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ double sh[8];
+    __shared__ int sbad[8];
+    hinge_loss_fold(fold, (int)threadIdx.x, sh, sbad, 1);
 }
 
 // ------------------------------------------------------------------------------ hinge finish
@@ -1125,30 +1097,28 @@ extern "C" int pb2_hinge_prep(const void* v, const void* a, int dtype, int64_t n
     return check_launch("hinge_prep");
 }
 
-extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim,
-                                 int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag,
-                                 const int32_t* row_cnt, const int32_t* col_cnt, const float* loss_partial,
-                                 int n_partials, float margin, float coef, float* loss_out, void* d_v, void* d_a,
-                                 int out_dtype, void* stream) {
+int pb2::hinge_finish2_ex(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim,
+                          int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const int32_t* row_cnt,
+                          const int32_t* col_cnt, float coef, const float* coef_dev, const HingeFold& fold, void* d_v, void* d_a,
+                          int out_dtype, void* stream) {
     if (n <= 0) return PB2_OK;
-    if (!p_v || !p_a || !v || !a || !rinv_v || !rinv_a || !diag || !row_cnt || !col_cnt || !loss_partial || !loss_out ||
-        !d_v || !d_a)
+    if (!p_v || !p_a || !v || !a || !rinv_v || !rinv_a || !row_cnt || !col_cnt || !d_v || !d_a)
         return set_error(PB2_ERR_ARG, "hinge_finish2: null");
     const int ob = out_dtype == PB2_F32 ? 4 : 2;
     const int es = elem_bytes(dtype);
     if (!es || dim % 8 != 0 || !vec_ok(v, ldv, es) || !vec_ok(a, lda, es) || !vec_ok(p_v, dim, 4) || !vec_ok(p_a, dim, 4) ||
         !vec_ok(d_v, dim, ob) || !vec_ok(d_a, dim, ob))
         return set_error(PB2_ERR_ARG, "hinge_finish2: dtype / alignment");
+    const unsigned grid = (unsigned)grid_for_warps(2 * n) + (fold.loss_out ? 1u : 0u);
     cudaError_t e;
 #define PB2_FIN2_(TO, REGS)                                                                                                   \
-    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO, REGS>, (unsigned)grid_for_warps(2 * n) + 1u, 256u,     \
-                                           (size_t)0, (cudaStream_t)stream, 1, p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, \
-                                           lda, rinv_v, rinv_a, diag, row_cnt, col_cnt, loss_partial, n_partials, margin, coef, \
-                                           loss_out, (TO*)d_v, (TO*)d_a))
-#define PB2_FIN2(TO)                    \
-    do {                                \
+    PB2_ROWS_DISPATCH(dtype, e = launch_ex(hinge_finish2_kernel<T, TO, REGS>, grid, 256u, (size_t)0, (cudaStream_t)stream, 1, \
+                                           p_v, p_a, (const T*)v, (const T*)a, n, dim, ldv, lda, rinv_v, rinv_a, row_cnt,     \
+                                           col_cnt, coef, coef_dev, fold, (TO*)d_v, (TO*)d_a))
+#define PB2_FIN2(TO)                         \
+    do {                                     \
         if (dim <= 512) PB2_FIN2_(TO, true); \
-        else PB2_FIN2_(TO, false);      \
+        else PB2_FIN2_(TO, false);           \
     } while (0)
     if (out_dtype == PB2_F32) PB2_FIN2(float);
     else if (out_dtype == PB2_BF16) PB2_FIN2(__nv_bfloat16);
@@ -1159,6 +1129,36 @@ extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void*
     int rc = check_cuda(e, "hinge_finish2");
     if (rc) return rc;
     return check_launch("hinge_finish2");
+}
+
+int pb2::hinge_fold(const HingeFold& fold, void* stream) {
+    if (!fold.loss_out) return PB2_OK;
+    const int rc = check_cuda(launch_ex(hinge_fold_kernel, 1u, 256u, (size_t)0, (cudaStream_t)stream, 1, fold), "hinge_fold");
+    if (rc) return rc;
+    return check_launch("hinge_fold");
+}
+
+extern "C" int pb2_hinge_finish2(const float* p_v, const float* p_a, const void* v, const void* a, int dtype, int64_t n, int dim,
+                                 int64_t ldv, int64_t lda, const float* rinv_v, const float* rinv_a, const float* diag,
+                                 const int32_t* row_cnt, const int32_t* col_cnt, const float* loss_partial,
+                                 int n_partials, float margin, float coef, float* loss_out, void* d_v, void* d_a,
+                                 int out_dtype, void* stream) {
+    if (n <= 0) return PB2_OK;
+    if (!diag || !loss_partial || !loss_out) return set_error(PB2_ERR_ARG, "hinge_finish2: null");
+    HingeFold fold;
+    fold.loss_partial = loss_partial;
+    fold.n_partials = n_partials;
+    fold.diag = diag;
+    fold.row_cnt = row_cnt;
+    fold.col_cnt = col_cnt;
+    fold.rinv_v = rinv_v;
+    fold.rinv_a = rinv_a;
+    fold.n = n;
+    fold.margin = margin;
+    fold.coef = coef;
+    fold.loss_out = loss_out;
+    return hinge_finish2_ex(p_v, p_a, v, a, dtype, n, dim, ldv, lda, rinv_v, rinv_a, row_cnt, col_cnt, coef, nullptr, fold, d_v, d_a,
+                            out_dtype, stream);
 }
 
 extern "C" int pb2_milnce_finish(const float* p, int64_t ld_p, const void* y, int dtype, int64_t rows, int dim, int64_t ldy,

@@ -2,8 +2,8 @@
 // trains with: pig/models.py:262 -> pig/loss.py:33-39 + autograd).  That step is HOST bound: its kernels take ~28 us,
 // the Python glue of a torch.autograd.Function (ctypes marshalling of 17 arguments, tensor allocations, the engine's
 // round trip through Python for backward) ~140 us.  This file is the same glue in C++: one autograd node whose forward is
-// ONE call of pb2_hinge_step (four launches) and whose backward is ONE call of pb2_scale_pair.  No kernels here and no
-// arithmetic: everything numeric is behind include/peppa_b200.h.  peppa_b200/loss.py takes this path when the inputs
+// ONE call of pb2_hinge_forward (three launches) and whose backward is ONE call of pb2_hinge_backward (one launch).  No
+// kernels here and no arithmetic: everything numeric is behind include/peppa_b200.h.  peppa_b200/loss.py takes this path when the inputs
 // need no conversion (CUDA, 2-D, one dtype of bf16 / fp16 / fp32, contiguous rows, D % 64 == 0, N <= 32768) and the
 // ctypes path otherwise; both end in the same entry points.
 #include <torch/extension.h>
@@ -76,40 +76,40 @@ class HingeStepFn : public torch::autograd::Function<HingeStepFn> {
         const auto stream = c10::cuda::getCurrentCUDAStream(V.get_device());
         const bool capturing = c10::cuda::currentStreamCaptureStatusMayInitCtx() != c10::cuda::CaptureStatus::None;
         at::Tensor ws = step_workspace(V, (void*)stream.stream(), n, d, code, capturing);
-        // gradients stay fp32 until grad_output has been applied (an AMP GradScaler's 65536 must reach an fp16 gradient
-        // of ~1e-7 before the rounding does)
-        at::Tensor grads = at::empty({2, n, d}, V.options().dtype(at::kFloat));
+        // what the backward needs (both gradient products, 1/||row||, the indicator counts) stays in a buffer of this
+        // call's own; grad_output is applied there in fp32 before the rounding (an AMP GradScaler's 65536 must reach an
+        // fp16 gradient of ~1e-7 before the rounding does)
+        at::Tensor state = at::empty({pb2_hinge_state_bytes(n, (int)d)}, V.options().dtype(at::kByte));
         at::Tensor loss = at::empty({}, V.options().dtype(at::kFloat));
         const float* rv = rinv_v.has_value() && rinv_v->defined() ? rinv_v->data_ptr<float>() : nullptr;
         const float* ra = rinv_a.has_value() && rinv_a->defined() ? rinv_a->data_ptr<float>() : nullptr;
-        float* g = grads.data_ptr<float>();
-        const int rc = pb2_hinge_step(V.data_ptr(), A.data_ptr(), code, n, (int)d, V.stride(0), A.stride(0), (float)margin,
-                                      ws.data_ptr(), ws.numel(), loss.data_ptr<float>(), g, g + n * d, PB2_F32, rv, ra,
-                                      (void*)stream.stream());
-        if (rc != PB2_OK) fail("hinge_step", rc);
-        ctx->save_for_backward({grads});
+        const int rc = pb2_hinge_forward(V.data_ptr(), A.data_ptr(), code, n, (int)d, V.stride(0), A.stride(0), (float)margin,
+                                         ws.data_ptr(), ws.numel(), state.data_ptr(), state.numel(), loss.data_ptr<float>(), rv,
+                                         ra, (void*)stream.stream());
+        if (rc != PB2_OK) fail("hinge_forward", rc);
+        ctx->save_for_backward({state, V, A});
         ctx->saved_data["code"] = (int64_t)code;
         return loss;
     }
 
     static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
                                                    torch::autograd::variable_list grad_outputs) {
-        const at::Tensor grads = ctx->get_saved_variables()[0];
+        const auto saved = ctx->get_saved_variables();
+        const at::Tensor &state = saved[0], &V = saved[1], &A = saved[2];
         const int code = (int)ctx->saved_data["code"].toInt();
-        const int64_t n = grads.size(1), d = grads.size(2);
+        const int64_t n = V.size(0), d = V.size(1);
         at::Tensor go = grad_outputs[0];
-        if (!go.is_cuda() || go.get_device() != grads.get_device() || go.scalar_type() != at::kFloat)
-            go = go.to(grads.options());
+        if (!go.is_cuda() || go.get_device() != state.get_device() || go.scalar_type() != at::kFloat)
+            go = go.to(state.options().dtype(at::kFloat));
         go = go.contiguous();
-        const c10::cuda::CUDAGuard guard(grads.device());
-        const auto stream = c10::cuda::getCurrentCUDAStream(grads.get_device());
-        const at::ScalarType out_t = code == PB2_BF16 ? at::kBFloat16 : (code == PB2_F16 ? at::kHalf : at::kFloat);
-        // two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy
-        at::Tensor g0 = at::empty({n, d}, grads.options().dtype(out_t)), g1 = at::empty({n, d}, grads.options().dtype(out_t));
-        const float* g = grads.data_ptr<float>();
-        const int rc = pb2_scale_pair(g, g + n * d, n * d, code, go.data_ptr<float>(), g0.data_ptr(), g1.data_ptr(),
-                                      (void*)stream.stream());
-        if (rc != PB2_OK) fail("scale_pair", rc);
+        const c10::cuda::CUDAGuard guard(state.device());
+        const auto stream = c10::cuda::getCurrentCUDAStream(state.get_device());
+        // two fresh contiguous tensors in the inputs' dtype: AccumulateGrad takes them without a copy
+        at::Tensor g0 = at::empty({n, d}, V.options()), g1 = at::empty({n, d}, V.options());
+        const int rc = pb2_hinge_backward(state.data_ptr(), state.numel(), V.data_ptr(), A.data_ptr(), code, n, (int)d, V.stride(0),
+                                          A.stride(0), go.data_ptr<float>(), g0.data_ptr(), g1.data_ptr(), code,
+                                          (void*)stream.stream());
+        if (rc != PB2_OK) fail("hinge_backward", rc);
         return {g0, g1, at::Tensor(), at::Tensor(), at::Tensor()};
     }
 };
@@ -123,6 +123,6 @@ at::Tensor triplet_loss(const at::Tensor& V, const at::Tensor& A, double margin,
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "peppa_b200: C++ autograd glue over the C ABI for the launch-bound training step";
-    m.def("triplet_loss", &triplet_loss, "TripletLoss forward (+ autograd node) through pb2_hinge_step / pb2_scale_pair",
+    m.def("triplet_loss", &triplet_loss, "TripletLoss forward (+ autograd node) through pb2_hinge_forward / pb2_hinge_backward",
           py::arg("V"), py::arg("A"), py::arg("margin"), py::arg("rinv_v") = py::none(), py::arg("rinv_a") = py::none());
 }

@@ -3,8 +3,8 @@
 ``TripletLoss(margin)(V, A)`` (pig/loss.py:28-39) and ``MILNCELoss()(V, A)`` (pig/loss.py:5-26)
 never materialise the N x N similarity matrix: the tcgen05 GEMM's epilogue reduces it to the
 loss, the indicator counts / log-sum-exp statistics and an fp16 gradient matrix, and two more
-tensor-core GEMMs turn that into dV and dA.  Gradients are produced during ``forward`` (the
-loss is a scalar, so backward is a scale by ``grad_output``).
+tensor-core GEMMs turn that into dV and dA.  The gradient products run during ``forward`` (the loss is a
+scalar); ``backward`` is one launch that applies the normalisation Jacobians and ``grad_output``.
 """
 from __future__ import annotations
 
@@ -36,12 +36,13 @@ class _HingeFn(torch.autograd.Function):
         dev = vb.device
         n = vb.shape[0]
         need_grad = any(ctx.needs_input_grad[:2])
-        if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the four-launch fused step
-            # gradients stay fp32 until grad_output has been applied (backward): an AMP GradScaler's 65536 must
-            # reach an fp16 gradient of ~1e-7 before the rounding does
+        if need_grad and n <= _MAX_BLOCK:       # one gradient-matrix block: the fused step, 3 + 1 launches
+            # forward: prep, similarity / hinge pass, both gradient products (+ the loss fold beside them); the Jacobians
+            # wait for grad_output (backward), which is applied in fp32 before the rounding: an AMP GradScaler's 65536
+            # must reach an fp16 gradient of ~1e-7 before the rounding does
             # (embeddings that come from the encoder tail carry their 1/||row||: nothing re-derives the norms)
-            loss, grads = ops.hinge_step(vb, ab, margin, torch.float32, ops.known_rinv(V, vb), ops.known_rinv(A, ab))
-            ctx.save_for_backward(grads)
+            loss, state = ops.hinge_forward(vb, ab, margin, ops.known_rinv(V, vb), ops.known_rinv(A, ab))
+            ctx.save_for_backward(state, vb, ab)
             ctx.fused = True
             ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
             return loss if loss.device == V.device else loss.to(V.device)
@@ -89,18 +90,18 @@ class _HingeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        if ctx.fused:       # one scale kernel for both gradients, already in the inputs' dtype
-            (grads,) = ctx.saved_tensors
+        if ctx.fused:       # one launch: both Jacobians times grad_output, already in the inputs' dtype
+            state, vb, ab = ctx.saved_tensors
             vd, vdev, ad, adev, dv_, da_ = ctx.meta
             go = grad_out.detach()
-            if go.device != grads.device or go.dtype != torch.float32:
-                go = go.to(device=grads.device, dtype=torch.float32)
+            if go.device != state.device or go.dtype != torch.float32:
+                go = go.to(device=state.device, dtype=torch.float32)
             # two fresh contiguous tensors (not views of one buffer): AccumulateGrad takes them without a copy;
             # scaled in fp32, rounded to the inputs' dtype last
             same = vd == ad and vd in (torch.float32, torch.bfloat16, torch.float16)
-            g0, g1 = ops.scale_pair(grads[0], grads[1], go, vd if same else torch.float32)
+            g0, g1 = ops.hinge_backward(state, vb, ab, go, vd if same else torch.float32)
             # (this is the batch-1k training step, launch bound: no view, cast or copy that is not needed)
-            d = grads.shape[2]
+            d = vb.shape[1]
             gV = gA = None
             if ctx.needs_input_grad[0]:
                 gV = g0 if dv_ == d else g0[:, :dv_]
@@ -236,7 +237,7 @@ class TripletLoss(torch.nn.Module):
            A: Tensor of embeddings (e.g. audio)
         """
         # the batch-~1k training step is host bound: inputs that need no conversion go through the C++ autograd node
-        # (csrc/torch_fast.cpp: the same pb2_hinge_step / pb2_scale_pair calls without the Python round trips)
+        # (csrc/torch_fast.cpp: the same pb2_hinge_forward / pb2_hinge_backward calls without the Python round trips)
         if (V.is_cuda and A.is_cuda and V.dim() == 2 and V.shape == A.shape and V.dtype == A.dtype and V.device == A.device
                 and V.dtype in _FAST_DTYPES and V.shape[1] % 64 == 0 and 0 < V.shape[0] <= _MAX_BLOCK
                 and V.stride(1) == 1 and A.stride(1) == 1 and V.stride(0) % 8 == 0 and A.stride(0) % 8 == 0

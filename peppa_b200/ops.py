@@ -539,6 +539,48 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32, rinv_v=None, rinv_a=Non
     return loss, grads
 
 
+def hinge_forward(vb, ab, margin, rinv_v=None, rinv_a=None):
+    """Forward half of the TripletLoss step for one gradient-matrix block (n <= 32768): one C call, three launches
+    (prep, fused similarity / hinge pass, both gradient GEMMs with the scalar loss folded beside them).  Returns
+    (loss 0-d fp32, state): ``state`` is a fresh uint8 tensor holding what ``hinge_backward`` needs (both products,
+    1/||row||, the indicator counts); the scratch is the per-stream workspace of ``hinge_step``."""
+    n, d = vb.shape
+    dev = vb.device
+    lib = _cabi.lib()
+    code = _mm_code(vb, ab)
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (dev, torch._C._cuda_getCurrentRawStream(_dev_index(dev)), n, d, code)
+    ws = None if capturing else _STEP_WORKSPACE.get(key)
+    with _on_device(dev):
+        if ws is None:
+            ws = torch.empty(int(lib.pb2_hinge_step_workspace(n, d, code)), dtype=torch.uint8, device=dev)
+            if not capturing:
+                if len(_STEP_WORKSPACE) > 8:
+                    _STEP_WORKSPACE.clear()
+                _STEP_WORKSPACE[key] = ws
+        state = torch.empty(int(lib.pb2_hinge_state_bytes(n, d)), dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with _timed("hinge_forward (3 kernels)", 6.0 * n * n * d, dev):
+            check(lib.pb2_hinge_forward(_ptr(vb), _ptr(ab), code, n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws),
+                                        ws.numel(), _ptr(state), state.numel(), _ptr(loss), _ptr(rinv_v), _ptr(rinv_a),
+                                        _stream(dev)), "hinge_forward")
+    return loss, state
+
+
+def hinge_backward(state, vb, ab, grad_out, out_dtype=torch.float32):
+    """Backward half: (dV, dA) [n, d] in ``out_dtype`` = the mean hinge loss's gradients times the 0-d fp32 device tensor
+    ``grad_out``, multiplied in fp32 before the rounding; one launch, two fresh contiguous tensors."""
+    n, d = vb.shape
+    dev = vb.device
+    with _on_device(dev):
+        g0 = torch.empty(n, d, dtype=out_dtype, device=dev)
+        g1 = torch.empty(n, d, dtype=out_dtype, device=dev)
+        check(_cabi.lib().pb2_hinge_backward(_ptr(state), state.numel(), _ptr(vb), _ptr(ab), _mm_code(vb, ab), n, d, vb.stride(0),
+                                             ab.stride(0), _ptr(grad_out), _ptr(g0), _ptr(g1), _DTYPE_CODE[out_dtype],
+                                             _stream(dev)), "hinge_backward")
+    return g0, g1
+
+
 def scale_pair(x0, x1, coef, out_dtype=torch.float32):
     """(x0 * coef, x1 * coef) rounded to ``out_dtype`` for fp32 ``x`` and a 0-d fp32 device tensor ``coef``: one
     launch, fresh contiguous results (the scale is applied in fp32, the rounding comes last)."""

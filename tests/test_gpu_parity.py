@@ -1172,3 +1172,26 @@ def test_training_step_operands_written_right_before(pb, dtype, n):
     for it, ((l1, dv1, da1), (l2, dv2, da2)) in enumerate(zip(free, synced)):
         assert torch.isfinite(l2), it
         assert torch.equal(l1, l2) and torch.equal(dv1, dv2) and torch.equal(da1, da2), it
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("n", [1024, 1000, 2304, 4100])
+def test_hinge_forward_backward_pair_equals_one_call_step(pb, dtype, n):
+    """pb2_hinge_forward + pb2_hinge_backward (3 + 1 launches: the loss folded beside the gradient products -- in a CTA
+    of their grid at n = 1024 / 1000, as a launch of its own when they do not fit one grid --, grad_output applied in
+    the Jacobian kernel before the rounding) against pb2_hinge_step + pb2_scale_pair (4 + 1 launches, fp32 gradients in
+    between): loss and gradients bit for bit, for grad_output 1 and an AMP loss scale; the backward may run twice."""
+    from peppa_b200 import ops
+    V, A = emb(n, 4.0)
+    vb, ab = ops.as_row_pair(V.cuda().to(dtype), A.cuda().to(dtype))
+    loss1, grads = ops.hinge_step(vb, ab, 0.2)
+    loss2, state = ops.hinge_forward(vb, ab, 0.2)
+    assert torch.equal(loss1, loss2) and torch.isfinite(loss1)
+    ref_loss, _, _ = O.hinge_loss_and_grads(vb.float().cpu(), ab.float().cpu(), 0.2)
+    assert rel_err(loss2.cpu(), ref_loss) < TOL
+    for scale in (1.0, 65536.0, 1.0):
+        go = torch.tensor(scale, dtype=torch.float32, device="cuda")
+        g0, g1 = ops.scale_pair(grads[0], grads[1], go, dtype)
+        h0, h1 = ops.hinge_backward(state, vb, ab, go, dtype)
+        assert torch.equal(g0, h0) and torch.equal(g1, h1)
+        assert h0.dtype == dtype and float(h0.float().abs().sum()) > 0

@@ -44,13 +44,13 @@ def main():
             keep = fn()
         return g, keep
 
-    names = {1: "hinge_prep", 2: "+ similarity pass", 3: "+ gradient products", 4: "+ finish (whole C call)"}
+    names = {1: "hinge_prep", 2: "+ similarity pass", 3: "+ gradient products", 4: "+ finish (whole pb2_hinge_step)"}
     prev = 0.0
     for k in (1, 2, 3, 4):
         _cabi.lib().pb2_debug_step_stages(k)
         g, keep = graph_of(lambda: ops.hinge_step(v, a, 0.2))
         us = min(timed(g.replay, 2000, 200, sync) for _ in range(3)) * 1e3
-        print(f"n={n} stages 1..{k} {names[k]:28s}: {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
+        print(f"n={n} stages 1..{k} {names[k]:32s}: {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
         prev = us
     _cabi.lib().pb2_debug_step_stages(4)
 
@@ -60,7 +60,19 @@ def main():
 
     g, keep = graph_of(with_scale)
     us = min(timed(g.replay, 2000, 200, sync) for _ in range(3)) * 1e3
-    print(f"n={n} whole C call + scale_pair                    : {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
+    print(f"n={n} pb2_hinge_step + pb2_scale_pair (4 + 1 launches)    : {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
+    # the autograd pair the public module uses: forward = prep, pass, products (+ the loss fold in their grid)
+    g, keep = graph_of(lambda: ops.hinge_forward(v, a, 0.2))
+    fwd = min(timed(g.replay, 2000, 200, sync) for _ in range(3)) * 1e3
+    print(f"n={n} pb2_hinge_forward (3 launches)                       : {fwd:6.2f} us/replay", flush=True)
+
+    def pair():
+        loss, state = ops.hinge_forward(v, a, 0.2)
+        return ops.hinge_backward(state, v, a, one, torch.bfloat16)
+
+    g, keep = graph_of(pair)
+    us = min(timed(g.replay, 2000, 200, sync) for _ in range(3)) * 1e3
+    print(f"n={n} pb2_hinge_forward + pb2_hinge_backward (3 + 1)       : {us:6.2f} us/replay  (+{us - fwd:5.2f})", flush=True)
     prev = us
     mod = TripletLoss(0.2)
     vv, aa = v.clone().requires_grad_(True), a.clone().requires_grad_(True)
@@ -74,7 +86,7 @@ def main():
 
     g, keep = graph_of(step)
     us = min(timed(g.replay, 2000, 200, sync) for _ in range(3)) * 1e3
-    print(f"n={n} public module + autograd                     : {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
+    print(f"n={n} public module + autograd (ones_like fill)              : {us:6.2f} us/replay  (+{us - prev:5.2f})", flush=True)
 
 
 if __name__ == "__main__":

@@ -534,7 +534,7 @@ def bench_eval1467(args, device, sync):
 
 def bench_train1024(args, device, sync):
     """Config 2: TripletLoss fwd+bwd at batch 1024 x 512 bf16 through peppa_b200.loss.TripletLoss + autograd.
-    The step is launch bound (5 library kernels + 2 torch kernels), so ``value`` replays it as a CUDA graph; the
+    The step is launch bound (4 library kernels + autograd's ones_like fill), so ``value`` replays it as a CUDA graph; the
     per-kernel events and ``e2e`` run it eagerly."""
     import torch
     from peppa_b200.loss import TripletLoss

@@ -190,6 +190,21 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert lib.pb2_scale_pair(null, null, 64, 0, null, null, null, null) == 1
     assert lib.pb2_scale_pair(one, one, 63, 2, one, one, one, null) == 1        # not whole 16-byte vectors
     assert lib.pb2_scale_pair(null, null, 0, 0, null, null, null, null) == 0
+    # the training step as an autograd pair: sizes, nulls, alignment and too-small buffers are refused before any launch
+    ws, st = lib.pb2_hinge_forward_workspace(1024, 512, 0), lib.pb2_hinge_state_bytes(1024, 512)
+    assert 0 < ws and st >= 2 * 1024 * 512 * 4 and lib.pb2_hinge_step_workspace(1024, 512, 0) == ws + st
+    assert lib.pb2_hinge_state_bytes(0, 512) == 0
+    assert lib.pb2_hinge_forward(one, one, 0, 1024, 512, 512, 512, 0.2, null, ws, one, st, one, null, null, null) == 1   # null workspace
+    assert lib.pb2_hinge_forward(one, one, 0, 1024, 512, 512, 512, 0.2, one, ws - 1, one, st, one, null, null, null) == 1
+    assert b"workspace too small" in lib.pb2_last_error()
+    assert lib.pb2_hinge_forward(one, one, 0, 1024, 512, 512, 512, 0.2, one, ws, one, st - 1, one, null, null, null) == 1
+    assert b"state too small" in lib.pb2_last_error()
+    assert lib.pb2_hinge_forward(one, one, 0, 1024, 512, 512, 512, 0.2, one, ws, C.c_void_p(264), st, one, null, null, null) == 1  # alignment
+    assert lib.pb2_hinge_forward(one, one, 7, 1024, 512, 512, 512, 0.2, one, ws, one, st, one, null, null, null) == 1    # dtype
+    assert lib.pb2_hinge_forward(one, one, 0, 0, 512, 512, 512, 0.2, one, ws, one, st, one, null, null, null) == 1       # empty batch
+    assert lib.pb2_hinge_backward(null, st, one, one, 0, 1024, 512, 512, 512, null, one, one, 0, null) == 1
+    assert lib.pb2_hinge_backward(one, st - 1, one, one, 0, 1024, 512, 512, 512, null, one, one, 0, null) == 1
+    assert lib.pb2_hinge_backward(one, st, one, one, 0, 1024, 500, 512, 512, null, one, one, 0, null) == 1              # dim % 64
 
 
 def test_triplet_scorer_keeps_the_reference_interface(monkeypatch):

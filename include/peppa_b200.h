@@ -266,7 +266,9 @@ int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_t n, int di
  * pb2_hinge_backward = ONE launch: d_v / d_a ([n, dim], out_dtype) = the gradients of the mean hinge loss times
  * grad_out[0] (device fp32 scalar, autograd's grad_output; NULL = 1), multiplied in fp32 BEFORE the rounding to
  * out_dtype -- an AMP loss scale reaches an fp16 gradient of ~1e-7 before the rounding does.  v / a: the rows the
- * forward saw.  Same bits as pb2_hinge_step followed by pb2_scale_pair. */
+ * forward saw.  Same bits as pb2_hinge_step followed by pb2_scale_pair.
+ * state == NULL (state_bytes ignored): the loss alone, for a forward no backward will follow (validation) -- prep,
+ * the hinge pass without a gradient matrix, the fold; workspace then needs pb2_hinge_step_workspace bytes. */
 int64_t pb2_hinge_forward_workspace(int64_t n, int dim, int in_dtype);
 int64_t pb2_hinge_state_bytes(int64_t n, int dim);
 int pb2_hinge_forward(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,

@@ -7,7 +7,8 @@
 //                         backward products in one grid) -> hinge_finish2 (Jacobians + scalar loss)
 //   pb2_hinge_forward   the forward half, three launches: hinge_prep -> sim_hinge -> grad_gemm_dual with the scalar loss
 //                         folded by a spare CTA of the product grid; what the backward needs (both products, 1/||row||,
-//                         the indicator counts) stays in a caller-owned STATE buffer
+//                         the indicator counts) stays in a caller-owned STATE buffer; without one (state == NULL) it is
+//                         the loss alone: hinge_prep -> sim_hinge without a gradient matrix -> the fold
 //   pb2_hinge_backward  the backward half, one launch: hinge_finish2 over the state with autograd's grad_output applied
 //                         in fp32 before the rounding to the gradients' dtype
 // Forward + backward are four launches like pb2_hinge_step, against its five with the pb2_scale_pair a deferred
@@ -103,7 +104,7 @@ int check_common(const char* what, const void* v, const void* a, int in_dtype, i
 // alive.  *stages_done: how far a truncated measurement step got.
 int forward_launches(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                      char* w, const Layout& L, const State& st, const float* rinv_v_in, const float* rinv_a_in,
-                     pb2::HingeFold fold, bool fold_in_forward, bool* complete, void* stream) {
+                     pb2::HingeFold fold, bool fold_in_forward, bool loss_only, bool* complete, void* stream) {
     *complete = false;
     float* diag = reinterpret_cast<float*>(w + L.diag);
     float* part = reinterpret_cast<float*>(w + L.part);
@@ -128,14 +129,18 @@ int forward_launches(const void* v, const void* a, int in_dtype, int64_t n, int 
         pb2::OperandsReadyScope early(!split);
         rc = pb2_sim_hinge(split ? vx : v, split ? ax : a, split ? sv : st.rinv_v, split ? sa : st.rinv_a, diag, diag, n, n, 0, 0,
                            split ? 3 * dim : dim, split ? PB2_F16 : in_dtype, split ? 3 * (int64_t)dim : ldv,
-                           split ? 3 * (int64_t)dim : lda, margin, part, -L.n_part, st.row_cnt, st.col_cnt, g, PB2_F16, L.ld_g,
-                           nullptr, nullptr, stream);
+                           split ? 3 * (int64_t)dim : lda, margin, part, -L.n_part, st.row_cnt, st.col_cnt,
+                           loss_only ? nullptr : g, PB2_F16, L.ld_g, nullptr, nullptr, stream);
     }
     if (rc || g_step_stages < 3) return rc;
     fold.loss_partial = part;
     fold.n_partials = L.n_part;
     fold.diag = diag;
     if (!fold_in_forward) fold.loss_out = nullptr;
+    if (loss_only) {  // no gradient matrix, no products: the fold is the third and last launch
+        *complete = true;
+        return pb2::hinge_fold(fold, stream);
+    }
     // dV partials = G A^, dA partials = G^T V^: one launch when all their tiles fit the machine at once
     bool folded = false;
     rc = pb2::grad_gemm_dual_fold(g, PB2_F16, n, n, L.ld_g, ah, vh, PB2_F16, dim, dim, dim, 1.0f, st.pv, st.pa, dim, dim, fold,
@@ -200,7 +205,7 @@ extern "C" int pb2_hinge_step(const void* v, const void* a, int in_dtype, int64_
     pb2::PdlScope pdl;
     pb2::HingeFold fold = fold_of(st, n, margin, loss_out);
     bool complete = false;
-    rc = forward_launches(v, a, in_dtype, n, dim, ldv, lda, margin, w, L, st, rinv_v_in, rinv_a_in, fold, false, &complete, stream);
+    rc = forward_launches(v, a, in_dtype, n, dim, ldv, lda, margin, w, L, st, rinv_v_in, rinv_a_in, fold, false, false, &complete, stream);
     if (rc || !complete) return rc;
     fold.loss_partial = reinterpret_cast<float*>(w + L.part);
     fold.n_partials = L.n_part;
@@ -215,17 +220,22 @@ extern "C" int pb2_hinge_forward(const void* v, const void* a, int in_dtype, int
     using pb2::set_error;
     int rc = check_common("hinge_forward", v, a, in_dtype, n, dim);
     if (rc) return rc;
-    if (!workspace || !state || !loss_out) return set_error(PB2_ERR_ARG, "hinge_forward: null");
+    if (!workspace || !loss_out) return set_error(PB2_ERR_ARG, "hinge_forward: null");
     if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(state)) & (kAlign - 1)) != 0)
         return set_error(PB2_ERR_ARG, "hinge_forward: workspace and state must be 256-byte aligned");
     const Layout L = layout(n, dim, in_dtype);
-    if (workspace_bytes < L.total) return set_error(PB2_ERR_ARG, "hinge_forward: workspace too small");
-    if (state_bytes < state_layout(n, dim).total) return set_error(PB2_ERR_ARG, "hinge_forward: state too small");
-    const State st = state_at(state, n, dim);
+    const StateLayout S = state_layout(n, dim);
+    // state == NULL: the loss alone (no gradient matrix, no products); 1/||row|| and the counts then live behind the
+    // scratch, in a workspace of pb2_hinge_step_workspace bytes
+    const bool loss_only = state == nullptr;
+    if (workspace_bytes < L.total + (loss_only ? S.total : 0)) return set_error(PB2_ERR_ARG, "hinge_forward: workspace too small");
+    if (!loss_only && state_bytes < S.total) return set_error(PB2_ERR_ARG, "hinge_forward: state too small");
+    char* w = static_cast<char*>(workspace);
+    const State st = state_at(loss_only ? static_cast<void*>(w + L.total) : state, n, dim);
     pb2::PdlScope pdl;
     bool complete = false;
-    return forward_launches(v, a, in_dtype, n, dim, ldv, lda, margin, static_cast<char*>(workspace), L, st, rinv_v_in, rinv_a_in,
-                            fold_of(st, n, margin, loss_out), true, &complete, stream);
+    return forward_launches(v, a, in_dtype, n, dim, ldv, lda, margin, w, L, st, rinv_v_in, rinv_a_in, fold_of(st, n, margin, loss_out),
+                            true, loss_only, &complete, stream);
 }
 
 extern "C" int pb2_hinge_backward(const void* state, int64_t state_bytes, const void* v, const void* a, int in_dtype, int64_t n,

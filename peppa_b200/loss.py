@@ -47,6 +47,9 @@ class _HingeFn(torch.autograd.Function):
             ctx.meta = (V.dtype, V.device, A.dtype, A.device, V.shape[1], A.shape[1])
             return loss if loss.device == V.device else loss.to(V.device)
         ctx.fused = False
+        if 0 < n <= _MAX_BLOCK:                 # the loss alone (validation): prep, the pass without a gradient matrix, the fold
+            loss, _ = ops.hinge_forward(vb, ab, margin, ops.known_rinv(V, vb), ops.known_rinv(A, ab), want_state=False)
+            return loss if loss.device == V.device else loss.to(V.device)
         rv, ra = ops.rinv_of(V, vb), ops.rinv_of(A, ab)
         diag = ops.pair_dot(vb, ab, rinv_x=rv, rinv_y=ra)       # M_ii, pig/loss.py:43
         vx, ax, fv, fa = ops.mma_pair(vb, ab, rv, ra)           # tensor-core operands + epilogue factors (split-fp16 for fp32 rows)

@@ -539,11 +539,12 @@ def hinge_step(vb, ab, margin, grad_dtype=torch.float32, rinv_v=None, rinv_a=Non
     return loss, grads
 
 
-def hinge_forward(vb, ab, margin, rinv_v=None, rinv_a=None):
+def hinge_forward(vb, ab, margin, rinv_v=None, rinv_a=None, want_state=True):
     """Forward half of the TripletLoss step for one gradient-matrix block (n <= 32768): one C call, three launches
     (prep, fused similarity / hinge pass, both gradient GEMMs with the scalar loss folded beside them).  Returns
     (loss 0-d fp32, state): ``state`` is a fresh uint8 tensor holding what ``hinge_backward`` needs (both products,
-    1/||row||, the indicator counts); the scratch is the per-stream workspace of ``hinge_step``."""
+    1/||row||, the indicator counts); the scratch is the per-stream workspace of ``hinge_step``.
+    ``want_state=False``: the loss alone (prep, the pass without a gradient matrix, the fold); state is None."""
     n, d = vb.shape
     dev = vb.device
     lib = _cabi.lib()
@@ -558,12 +559,12 @@ def hinge_forward(vb, ab, margin, rinv_v=None, rinv_a=None):
                 if len(_STEP_WORKSPACE) > 8:
                     _STEP_WORKSPACE.clear()
                 _STEP_WORKSPACE[key] = ws
-        state = torch.empty(int(lib.pb2_hinge_state_bytes(n, d)), dtype=torch.uint8, device=dev)
+        state = torch.empty(int(lib.pb2_hinge_state_bytes(n, d)), dtype=torch.uint8, device=dev) if want_state else None
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        with _timed("hinge_forward (3 kernels)", 6.0 * n * n * d, dev):
+        with _timed("hinge_forward (3 kernels)", (6.0 if want_state else 2.0) * n * n * d, dev):
             check(lib.pb2_hinge_forward(_ptr(vb), _ptr(ab), code, n, d, vb.stride(0), ab.stride(0), float(margin), _ptr(ws),
-                                        ws.numel(), _ptr(state), state.numel(), _ptr(loss), _ptr(rinv_v), _ptr(rinv_a),
-                                        _stream(dev)), "hinge_forward")
+                                        ws.numel(), _ptr(state), state.numel() if want_state else 0, _ptr(loss), _ptr(rinv_v),
+                                        _ptr(rinv_a), _stream(dev)), "hinge_forward")
     return loss, state
 
 

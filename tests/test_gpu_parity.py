@@ -1195,3 +1195,25 @@ def test_hinge_forward_backward_pair_equals_one_call_step(pb, dtype, n):
         h0, h1 = ops.hinge_backward(state, vb, ab, go, dtype)
         assert torch.equal(g0, h0) and torch.equal(g1, h1)
         assert h0.dtype == dtype and float(h0.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("dtype,n", [(torch.bfloat16, 1024), (torch.float16, 1000), (torch.float32, 300), (torch.bfloat16, 4100)])
+def test_loss_alone_equals_the_training_loss(pb, dtype, n):
+    """A forward no backward will follow (validation: torch.no_grad, or inputs without requires_grad) takes
+    pb2_hinge_forward without a state buffer -- prep, the hinge pass without a gradient matrix, the fold: three
+    launches, and the same bits as the loss of the training step (and the oracle's value to 1e-3)."""
+    V, A = emb(n, 4.0)
+    v, a = V.cuda().to(dtype), A.cuda().to(dtype)
+    mod = pb.loss.TripletLoss(0.2)
+    with torch.no_grad():
+        l0 = mod(v, a)
+    l1 = mod(v, a)                                                    # no requires_grad
+    l2 = mod(v.clone().requires_grad_(True), a.clone().requires_grad_(True))
+    assert not l0.requires_grad and l2.requires_grad
+    assert torch.equal(l0, l1) and torch.equal(l0, l2.detach())
+    ref_loss, _, _ = O.hinge_loss_and_grads(v.float().cpu(), a.float().cpu(), 0.2)
+    assert rel_err(l0.cpu(), ref_loss) < TOL
+    z = v.clone()
+    z[3] = 0                                                          # a zero row: NaN like the reference's 0 / 0
+    with torch.no_grad():
+        assert torch.isnan(mod(z, a))

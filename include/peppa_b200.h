@@ -355,6 +355,19 @@ int pb2_nccl_dv_reduce_scatter(void* comm, const float* partial_full, int64_t n_
 /* number of CTAs the persistent similarity kernels launch on the current device */
 int pb2_sim_grid(void);
 
+/* ---- host side of the duration-matched triplet sampler (pig/triplet.py:99-104 over pig/util.py shuffled / grouped /
+ * pairs).  No device work: these replay, on a COPY of Python's MT19937 state, exactly the draws the reference makes on
+ * the global `random` generator, so a seeded evaluation draws the same triplets and leaves the generator in the same
+ * state, without 1.5 million interpreter-level calls per 500 samples.  mt_state: the 625 words of random.getstate()[1]
+ * (624 state words + the index), updated in place -- the caller hands it back through random.setstate().
+ * pb2_host_random_doubles: out[i] = the next n values of random.random().
+ * pb2_host_sample_pairs: groups g = items[group_start[g] .. group_start[g + 1]) (clips of one duration, in the order of
+ * grouped()); per sample and group: xs = shuffled(group), then for each of pairs(xs) target, distractor =
+ * random.sample(pair, 2); pos / neg [n_samples * sum_g floor(len_g / 2)] int64 in the reference's order. */
+int pb2_host_random_doubles(uint32_t* mt_state, int64_t n, double* out);
+int pb2_host_sample_pairs(uint32_t* mt_state, const int64_t* items, const int64_t* group_start, int64_t n_groups,
+                          int64_t n_samples, int64_t* pos, int64_t* neg);
+
 #ifdef __cplusplus
 }
 #endif

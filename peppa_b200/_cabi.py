@@ -77,6 +77,8 @@ SIGNATURES = {
     "pb2_nccl_colstat_merge": [_p, _p, _i64, _p, _p, _i, _p],
     "pb2_nccl_dv_reduce_scatter": [_p, _p, _i64, _i, _p, _p],
     "pb2_contrastive_matrix": [_p, _i64, _i64, _f, _p, _i, _p, _i64, _f, _p, _p],
+    "pb2_host_random_doubles": [_p, _i64, _p],
+    "pb2_host_sample_pairs": [_p, _p, _p, _i64, _i64, _p, _p],
 }
 _RESTYPE = {"pb2_last_error": C.c_char_p, "pb2_launch_count": C.c_longlong, "pb2_hinge_step_workspace": C.c_int64, "pb2_hinge_forward_workspace": C.c_int64, "pb2_hinge_state_bytes": C.c_int64,
             "pb2_grad_gemm_workspace": C.c_int64}

@@ -24,7 +24,7 @@ LIB = os.path.join(CSRC, "libpeppa_b200.so")
 OBJ_MEASURE = os.path.join(CSRC, "build_measure")
 LIB_MEASURE = os.path.join(CSRC, "libpeppa_b200_measure.so")
 
-LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu", "collective.cu"]
+LIB_SOURCES = ["host_util.cu", "triplet.cu", "rowstats.cu", "sim.cu", "gradgemm.cu", "step.cu", "proj.cu", "collective.cu", "sampler.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v",

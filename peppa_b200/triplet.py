@@ -1,8 +1,8 @@
 """Drop-in for the scoring half of ``pig/triplet.py`` (lines 17-29 and 63-121).
 
-The duration-matched sampler stays in Python and consumes ``random`` in exactly the reference's
-order (seeded runs draw identical triplets), with the duration grouping hoisted out of the sample loop
-(SURVEY 8f row 2); the arithmetic of *all* samples runs in one launch of the fused gather + cosine-gap
+The duration-matched sampler consumes ``random`` in exactly the reference's order (seeded runs draw identical
+triplets and leave the generator in the same state), with the duration grouping hoisted out of the sample loop
+ and the draws themselves replayed in C++ on a copy of the generator's state (csrc/sampler.cu); the arithmetic of *all* samples runs in one launch of the fused gather + cosine-gap
 kernel, so ``audio[pos]``, ``video[pos]``, ``video[neg]`` are never materialised.
 ``TripletScorer`` (pig/triplet.py:31-61) is the encode-side caller: the class below keeps its interface and
 imports the dataset (``pig.data``) and Lightning only when it is used -- the encoders and the data pipeline are
@@ -10,12 +10,13 @@ not part of this package; its ``_score`` is ``score_triplets`` below.
 """
 from __future__ import annotations
 
+import ctypes as C
 import random
 from dataclasses import dataclass
 
 import torch
 
-from . import ops
+from . import _cabi, ops
 from .metrics import triplet_accuracy  # noqa: F401
 from .util import grouped, shuffled
 
@@ -114,6 +115,39 @@ def _sample2_is_two_randbelow():
     return _FAST_SAMPLE2
 
 
+_NATIVE_SAMPLER = None
+
+
+def _native_sampler():
+    """The C++ replay of the sampler's draws (csrc/sampler.cu: ``pb2_host_random_doubles`` / ``pb2_host_sample_pairs``
+    on a copy of the generator's MT19937 state), or None.  Taken only after it has reproduced THIS interpreter's
+    ``random.random()`` and ``random.sample(pair, 2)`` -- values and final generator state -- on a private generator;
+    otherwise the Python loops below keep drawing."""
+    global _NATIVE_SAMPLER
+    if _NATIVE_SAMPLER is None:
+        ok = False
+        try:
+            lib = _cabi.lib()
+            a, b = random.Random(20211), random.Random(20211)
+            st = b.getstate()
+            ok = st[0] == 3 and len(st[1]) == 625 and _sample2_is_two_randbelow()
+            if ok:
+                mt = (C.c_uint32 * 625)(*st[1])
+                out = (C.c_double * 1500)()
+                ok = lib.pb2_host_random_doubles(mt, 1500, out) == 0 and list(out) == [a.random() for _ in range(1500)]
+                items = (C.c_int64 * 7)(*range(7))
+                start = (C.c_int64 * 4)(0, 1, 3, 7)
+                pos, neg = (C.c_int64 * 9)(), (C.c_int64 * 9)()
+                ok = ok and lib.pb2_host_sample_pairs(mt, items, start, 3, 3, pos, neg) == 0
+                want = [random.Random.sample(a, p, 2) for _ in range(3) for grp in ([0], [1, 2], [3, 4, 5, 6])
+                        for p in pairs(sorted(grp, key=lambda _: a.random()))]
+                ok = ok and [list(t) for t in zip(pos, neg)] == want and tuple(mt) == a.getstate()[1]
+        except Exception:           # library without the entry points (an older build): the Python loops
+            ok = False
+        _NATIVE_SAMPLER = ok
+    return _NATIVE_SAMPLER
+
+
 def _sampled_index_pairs(duration, n_samples):
     """``n_samples`` draws of ``zip(*_triplets(range(len(duration)), lambda idx: duration[idx]))`` as two int64
     tensors [n_samples, pairs].  Sorting and grouping by duration consume no randomness, so they are done once; the
@@ -124,6 +158,22 @@ def _sampled_index_pairs(duration, n_samples):
     groups = [list(items) for _, items in grouped(range(len(keys)), key=keys.__getitem__)]
     if n_samples > 0 and not any(len(items) > 1 for items in groups):
         pos_idx, neg_idx = zip(*[])      # no two clips share a duration: the reference's unpack raises ValueError
+    per_sample = sum(len(items) // 2 for items in groups)
+    if n_samples > 0 and _native_sampler():
+        # the same draws on a copy of the global generator's state, handed back afterwards (csrc/sampler.cu)
+        version, words, gauss = random.getstate()
+        mt = (C.c_uint32 * 625)(*words)
+        flat = [i for items in groups for i in items]
+        starts = [0]
+        for items in groups:
+            starts.append(starts[-1] + len(items))
+        pos_t = torch.empty(n_samples, per_sample, dtype=torch.int64)
+        neg_t = torch.empty(n_samples, per_sample, dtype=torch.int64)
+        _cabi.check(_cabi.lib().pb2_host_sample_pairs(mt, (C.c_int64 * len(flat))(*flat), (C.c_int64 * len(starts))(*starts),
+                                                      len(groups), n_samples, pos_t.data_ptr(), neg_t.data_ptr()),
+                    "host_sample_pairs")
+        random.setstate((version, tuple(mt), gauss))
+        return pos_t, neg_t
     pos, neg = [], []
     if _sample2_is_two_randbelow():
         getrandbits = random.getrandbits
@@ -147,7 +197,6 @@ def _sampled_index_pairs(duration, n_samples):
                     target, distractor = sample(p, 2)
                     pos.append(target)
                     neg.append(distractor)
-    per_sample = sum(len(items) // 2 for items in groups)
     return (torch.tensor(pos, dtype=torch.int64).view(n_samples, per_sample),
             torch.tensor(neg, dtype=torch.int64).view(n_samples, per_sample))
 

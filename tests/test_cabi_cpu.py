@@ -119,6 +119,31 @@ def test_sampler_matches_golden_without_device():
         assert torch.equal(pos, g["draws"][:, 0].to(torch.int64)) and torch.equal(neg, g["draws"][:, 1].to(torch.int64))
         assert random.getstate() == state           # leaves the generator where the reference's loop leaves it
     triplet._FAST_SAMPLE2 = None
+    # the loop above ran on the C++ replay of the draws (csrc/sampler.cu) for fast = True: it must have been active,
+    # and it must equal the Python loops -- triplets and final generator state -- also on awkward group structures
+    # (singletons, odd groups, a generator whose state index sits mid-block) and over a long run
+    assert triplet._native_sampler() is True
+    gen = torch.Generator().manual_seed(7)
+    for n_items, n_vals, n_samples, burn in ((2, 1, 3, 0), (9, 4, 7, 1), (200, 11, 40, 617), (1467, 40, 25, 5)):
+        d = torch.randint(0, n_vals, (n_items,), generator=gen).float()
+        if n_items == 9:
+            d[0] = 99.0                                  # a clip alone in its group still costs one random() per sample
+        out = []
+        for native in (True, False):
+            triplet._NATIVE_SAMPLER = native
+            random.seed(4242)
+            for _ in range(burn):
+                random.random()
+            out.append(triplet._sampled_index_pairs(d, n_samples) + (random.getstate(),))
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+        assert out[0][0].shape[0] == n_samples and out[0][0].numel() > 0
+    triplet._NATIVE_SAMPLER = None
+    null = C.c_void_p(0)
+    lib = _cabi.lib()
+    assert lib.pb2_host_sample_pairs(null, null, null, 3, 2, null, null) == 1 and lib.pb2_host_sample_pairs(null, null, null, 0, 2, null, null) == 0
+    bad = (C.c_uint32 * 625)()
+    bad[624] = 700
+    assert lib.pb2_host_random_doubles(bad, 1, (C.c_double * 1)()) == 1        # state index out of range
 
 
 def test_encoder_tail_module_is_state_dict_compatible_with_linear():

@@ -14,6 +14,6 @@ nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler
     -c sim.cu -o "build_measure/sim_$1.variant.o"
 cd build_measure      # variants are measurement builds: they link the -DPB2_MEASURE objects (pb2_debug_* selectors)
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$ROOT/tools/ab/lib_$1.so" \
-    host_util.o triplet.o rowstats.o "sim_$1.variant.o" gradgemm.o step.o proj.o collective.o -ldl
+    host_util.o triplet.o rowstats.o "sim_$1.variant.o" gradgemm.o step.o proj.o collective.o sampler.o -ldl
 rm -f "sim_$1.variant.o"
 echo "$ROOT/tools/ab/lib_$1.so"

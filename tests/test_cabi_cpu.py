@@ -121,10 +121,11 @@ def test_sampler_matches_golden_without_device():
     triplet._FAST_SAMPLE2 = None
     # the loop above ran on the C++ replay of the draws (csrc/sampler.cu) for fast = True: it must have been active,
     # and it must equal the Python loops -- triplets and final generator state -- also on awkward group structures
-    # (singletons, odd groups, a generator whose state index sits mid-block) and over a long run
+    # (singletons, odd groups, a generator whose state index sits mid-block, one group of 1500 clips = the bucket sort's
+    # long buckets, one of 2600 = the (key, position) pair sort) and over a long run
     assert triplet._native_sampler() is True
     gen = torch.Generator().manual_seed(7)
-    for n_items, n_vals, n_samples, burn in ((2, 1, 3, 0), (9, 4, 7, 1), (200, 11, 40, 617), (1467, 40, 25, 5)):
+    for n_items, n_vals, n_samples, burn in ((2, 1, 3, 0), (9, 4, 7, 1), (200, 11, 40, 617), (1467, 40, 25, 5), (1500, 1, 3, 0), (2600, 1, 2, 3)):
         d = torch.randint(0, n_vals, (n_items,), generator=gen).float()
         if n_items == 9:
             d[0] = 99.0                                  # a clip alone in its group still costs one random() per sample

@@ -101,7 +101,8 @@ int check_common(const char* what, const void* v, const void* a, int in_dtype, i
 
 // hinge_prep -> sim_hinge -> both gradient products.  fold.loss_out != nullptr: the scalar loss is folded beside the
 // products (a spare CTA of their grid, or a launch of its own when they do not fit one grid); the caller's PdlScope is
-// alive.  *stages_done: how far a truncated measurement step got.
+// alive.  loss_only: no gradient matrix and no products, the fold is the last launch.  *complete: false when a
+// measurement build truncated the step (pb2_debug_step_stages).
 int forward_launches(const void* v, const void* a, int in_dtype, int64_t n, int dim, int64_t ldv, int64_t lda, float margin,
                      char* w, const Layout& L, const State& st, const float* rinv_v_in, const float* rinv_a_in,
                      pb2::HingeFold fold, bool fold_in_forward, bool loss_only, bool* complete, void* stream) {

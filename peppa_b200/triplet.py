@@ -122,28 +122,24 @@ def _native_sampler():
     """The C++ replay of the sampler's draws (csrc/sampler.cu: ``pb2_host_random_doubles`` / ``pb2_host_sample_pairs``
     on a copy of the generator's MT19937 state), or None.  Taken only after it has reproduced THIS interpreter's
     ``random.random()`` and ``random.sample(pair, 2)`` -- values and final generator state -- on a private generator;
-    otherwise the Python loops below keep drawing."""
+    if another interpreter ever draws differently, the Python loops below keep drawing."""
     global _NATIVE_SAMPLER
     if _NATIVE_SAMPLER is None:
-        ok = False
-        try:
-            lib = _cabi.lib()
-            a, b = random.Random(20211), random.Random(20211)
-            st = b.getstate()
-            ok = st[0] == 3 and len(st[1]) == 625 and _sample2_is_two_randbelow()
-            if ok:
-                mt = (C.c_uint32 * 625)(*st[1])
-                out = (C.c_double * 1500)()
-                ok = lib.pb2_host_random_doubles(mt, 1500, out) == 0 and list(out) == [a.random() for _ in range(1500)]
-                items = (C.c_int64 * 7)(*range(7))
-                start = (C.c_int64 * 4)(0, 1, 3, 7)
-                pos, neg = (C.c_int64 * 9)(), (C.c_int64 * 9)()
-                ok = ok and lib.pb2_host_sample_pairs(mt, items, start, 3, 3, pos, neg) == 0
-                want = [random.Random.sample(a, p, 2) for _ in range(3) for grp in ([0], [1, 2], [3, 4, 5, 6])
-                        for p in pairs(sorted(grp, key=lambda _: a.random()))]
-                ok = ok and [list(t) for t in zip(pos, neg)] == want and tuple(mt) == a.getstate()[1]
-        except Exception:           # library without the entry points (an older build): the Python loops
-            ok = False
+        lib = _cabi.lib()           # no library, no sampler: raises like every other entry of this package
+        a, b = random.Random(20211), random.Random(20211)
+        st = b.getstate()
+        ok = st[0] == 3 and len(st[1]) == 625 and _sample2_is_two_randbelow()
+        if ok:
+            mt = (C.c_uint32 * 625)(*st[1])
+            out = (C.c_double * 1500)()
+            ok = lib.pb2_host_random_doubles(mt, 1500, out) == 0 and list(out) == [a.random() for _ in range(1500)]
+            items = (C.c_int64 * 7)(*range(7))
+            start = (C.c_int64 * 4)(0, 1, 3, 7)
+            pos, neg = (C.c_int64 * 9)(), (C.c_int64 * 9)()
+            ok = ok and lib.pb2_host_sample_pairs(mt, items, start, 3, 3, pos, neg) == 0
+            want = [a.sample(p, 2) for _ in range(3) for grp in ([0], [1, 2], [3, 4, 5, 6])
+                    for p in pairs(sorted(grp, key=lambda _: a.random()))]
+            ok = ok and [list(t) for t in zip(pos, neg)] == want and tuple(mt) == a.getstate()[1]
         _NATIVE_SAMPLER = ok
     return _NATIVE_SAMPLER
 

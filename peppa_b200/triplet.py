@@ -197,6 +197,14 @@ def _sampled_index_pairs(duration, n_samples):
             torch.tensor(neg, dtype=torch.int64).view(n_samples, per_sample))
 
 
+def _durations_of(duration, pos):
+    """``torch.cat([duration[p] for p in pos])`` (pig/triplet.py:77-79, :94-96): one gather instead of one per sample when
+    ``duration`` is a 1-D tensor; anything else, and the empty case with its error, stays the reference's expression."""
+    if isinstance(duration, torch.Tensor) and duration.dim() == 1 and pos.shape[0] > 0:
+        return duration[pos.reshape(-1)]
+    return torch.cat([duration[p] for p in pos])
+
+
 def comparative_score_triplets(video_set, audio_set, duration, n_samples=100):
     vids = [_as_rows(v) for v in video_set]
     auds = [_as_rows(a, device=vids[k].device).to(vids[k].dtype) for k, a in enumerate(audio_set)]
@@ -205,7 +213,7 @@ def comparative_score_triplets(video_set, audio_set, duration, n_samples=100):
     success = [_gather_scores(auds[k], vids[k], pos.reshape(-1), neg.reshape(-1), discrete=False)
                .to(device=video_set[k].device, dtype=video_set[k].dtype) for k in range(len(video_set))]
     return {'success': success,
-            'duration': torch.cat([duration[p] for p in pos])}
+            'duration': _durations_of(duration, pos)}
 
 
 def score_triplets(video, audio, duration, n_samples=100):
@@ -220,7 +228,7 @@ def score_triplets(video, audio, duration, n_samples=100):
     else:
         accuracy = torch.tensor([])
     return {'accuracy': accuracy,
-            'duration': torch.cat([duration[p] for p in pos])}
+            'duration': _durations_of(duration, pos)}
 
 
 def _triplets(clips, criterion):
